@@ -1,0 +1,98 @@
+"""The named systems of BASELINE.json's configs, built with the model mirror.
+
+Each builder cites the reference script it restates.  The marionette (config 5) is loaded
+from a flattened description (``trep_b200/data/puppet.json``) that was produced from the
+reference's own ``trep/puppets/puppets.py`` by ``oracle/gen_golden.py`` — re-typing the
+86-frame skeleton here would only be a copy of data.
+"""
+from __future__ import annotations
+
+import math
+import os
+
+from . import model as M
+from .desc import SystemDesc
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+
+
+def pendulum(links=1) -> M.System:
+    """N-link pendulum: RX joint + TZ(-1) point mass per link, default gravity.
+    (examples/pendulum.py:36-71)"""
+    s = M.System(name="pendulum%d" % links)
+    M.Gravity(s, name="Gravity")
+    frame = s.world_frame
+    for link in range(links):
+        frame = M.Frame(frame, M.D.RX, "link-%d" % link, "link-%d" % link)
+        frame = M.Frame(frame, M.D.TZ, -1)
+        frame.set_mass(1.0)
+    s.get_config("link-0").q = math.pi / 4.0
+    return s
+
+
+def damped_pendulum() -> M.System:
+    """(examples/damped-pendulum.py:13-20)"""
+    s = M.System(name="damped_pendulum")
+    s.import_frames([M.ty(3), M.rx("theta"), [M.tz(-3, mass=1)]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 1.2)
+    return s
+
+
+def pend_on_cart(torque_force=False) -> M.System:
+    """(examples/pend-on-cart-optimization.py:48-64)"""
+    s = M.System(name="pend_on_cart%d" % (2 if torque_force else 1))
+    s.import_frames([
+        M.tx("x", name="Cart", mass=10.0), [
+            M.rz("theta", name="PendulumBase"), [
+                M.ty(-1.0, name="Pendulum", mass=1.0)]]])
+    M.Gravity(s, (0, -9.8, 0))
+    M.Damping(s, 0.01)
+    M.ConfigForce(s, "x", "x-force")
+    if torque_force:
+        M.ConfigForce(s, "theta", "theta-force")
+    return s
+
+
+def dual_pendulums() -> M.System:
+    """(examples/dual_pendulums.py:28-43)"""
+    s = M.System(name="dual_pendulums")
+    s.import_frames([
+        M.rx("theta1"), [M.tz(2, mass=1, name="pend1")],
+        M.ty(1), [M.rx("theta2"), [M.tz(2, mass=1, name="pend2")]]])
+    M.LinearSpring(s, "pend1", "pend2", k=20, x0=1)
+    M.LinearDamper(s, "pend1", "pend2", c=1)
+    M.Gravity(s, name="Gravity")
+    s.q = [3, -3]
+    return s
+
+
+def tase_pendulum() -> M.System:
+    """Known-answer pendulum of examples/papers/tase2012/pend-single-step.py:8-27."""
+    s = M.System(name="tase_pendulum")
+    s.import_frames([M.rz("theta_1", name="PendAngle"), [M.ty(-1.0, name="PendMass", mass=1.0)]])
+    M.Gravity(s, (0, -9.8, 0))
+    M.ConfigForce(s, "theta_1", "tau")
+    return s
+
+
+def puppet_desc() -> SystemDesc:
+    """Marionette with string constraints (trep/puppets/puppets.py:220-310,
+    examples/puppet-optimization.py:217-218): nd=22, nk=18, nc=6, 86 frames."""
+    return SystemDesc.load(os.path.join(_DATA, "puppet.json"))
+
+
+def named_desc(name) -> SystemDesc:
+    if name == "puppet":
+        return puppet_desc()
+    table = {
+        "pendulum1": lambda: pendulum(1), "pendulum5": lambda: pendulum(5),
+        "damped_pendulum": damped_pendulum, "pend_on_cart1": lambda: pend_on_cart(False),
+        "pend_on_cart2": lambda: pend_on_cart(True), "dual_pendulums": dual_pendulums,
+        "tase_pendulum": tase_pendulum,
+    }
+    return table[name]().describe()
+
+
+NAMED = ["pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2",
+         "dual_pendulums", "tase_pendulum", "puppet"]
