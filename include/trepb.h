@@ -1,0 +1,192 @@
+/* trepb.h — C ABI of the B200-native batched MidpointVI library (libtrepb.so).
+ *
+ * Drop-in boundary for ONE path of MurpheyLab/trep: the midpoint variational integrator's
+ * DEL step and its linearization, evaluated over a batch of independent instances.
+ * Plain C, plain pointers and sizes, no Python and no torch types.
+ *
+ * What each entry point replaces in the reference (paths relative to the reference root):
+ *
+ *   trepb_system_create      the "synchronize" product of trep/system.py:672-840 +
+ *                            trep/frame.py:658-721 (frame order, config_gen, cache_index,
+ *                            masses) and the plugin structs of trep/_trep/trep.h:305-375,
+ *                            flattened (see trepb_sysdesc).
+ *   trepb_step_batch*        _trep._MidpointVI._solve_DEL  == MidpointVI_solve_DEL
+ *                            (trep/_trep/midpointvi.c:691-747, exported as C-API slot
+ *                            capi_MidpointVI_solve_DEL, trep/_trep/c_api.h:88,693), looped
+ *                            the way MidpointVI.step does (trep/midpointvi.py:174-201):
+ *                            q1<-q2, p1<-p2, kinematic part of q2 <- k2, Newton start = q1.
+ *   trepb_calc_p2_batch*     _MidpointVI.calc_p2 (trep/_trep/midpointvi.c:491-504,2702-2708),
+ *                            i.e. MidpointVI.initialize_from_configs (midpointvi.py:155-172).
+ *   trepb_linearize_batch*   DSystem.set + fdx + fdu for every k of
+ *                            DSystem.linearize_trajectory (trep/discopt/dsystem.py:229-250,
+ *                            284-317, 406-423) == solve_DEL + MidpointVI_calc_deriv1
+ *                            (trep/_trep/midpointvi.c:1100-1120).
+ *   status[] / iters[]       the reference's exceptions (ConvergenceError midpointvi.c:715-718,
+ *                            singular LU math-code.c:393-398) become per-instance codes; the
+ *                            batch is never aborted.
+ *
+ * All matrices are row-major doubles.  Per-instance arrays are packed instance-major
+ * ("[B][n]"): instance b's vector starts at ptr + b*n.
+ *
+ * `_dev` entry points take DEVICE pointers (inputs already resident in HBM) and enqueue on
+ * `stream` (a cudaStream_t passed as void*; NULL = default stream) without synchronizing.
+ * The un-suffixed entry points take HOST pointers, copy in, run, copy out and synchronize.
+ *
+ * Every function returns 0 on success, non-zero on failure; trepb_last_error() describes
+ * the failure.  There is no CPU fallback: without a CUDA device every compute entry point
+ * fails with TREPB_ERR_CUDA.
+ */
+#ifndef TREPB_H
+#define TREPB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TREPB_ABI_VERSION 1
+
+/* error codes */
+#define TREPB_OK 0
+#define TREPB_ERR_INVALID 1   /* bad description / arguments */
+#define TREPB_ERR_CUDA 2      /* CUDA runtime / no device */
+#define TREPB_ERR_COMPILE 3   /* NVRTC specialisation failed */
+#define TREPB_ERR_UNSUPPORTED 4
+
+/* frame transform kinds (trep/_trep/trep.h:168-273) */
+#define TREPB_WORLD 0
+#define TREPB_TX 1
+#define TREPB_TY 2
+#define TREPB_TZ 3
+#define TREPB_RX 4
+#define TREPB_RY 5
+#define TREPB_RZ 6
+#define TREPB_CONST_SE3 7
+
+/* potential / force / constraint kinds: the built-in C plugin kinds on the path */
+#define TREPB_POT_GRAVITY 0        /* d = gx gy gz                       potentials/gravity.c      */
+#define TREPB_POT_LINEAR_SPRING 1  /* i = frame1 frame2 ; d = k x0       potentials/linearspring.c */
+#define TREPB_POT_CONFIG_SPRING 2  /* i = config        ; d = k q0       potentials/configspring.c */
+#define TREPB_FORCE_DAMPING 0      /* i = dpool offset, nd ; coefficients per dyn config  forces/damping.c */
+#define TREPB_FORCE_CONFIG 1       /* i = config input                   forces/configforce.c      */
+#define TREPB_FORCE_LINEAR_DAMPER 2/* i = ipool offset, npath ; d = c    forces/lineardamper.c     */
+#define TREPB_CON_DISTANCE 0       /* i = frame1 frame2 config|-1 ; d = distance tolerance  constraints/distance.c */
+#define TREPB_CON_POINT1D 1        /* i = frame1 frame2 component ; d = - tolerance         constraints/point.c    */
+
+/* Flattened system.  Frame 0 is the world frame; frames are in pre-order (parent before child),
+ * configs are [dynamic..., kinematic...].  Arrays are only read during trepb_system_create. */
+typedef struct trepb_sysdesc {
+    int32_t n_frames, nd, nk, nu;
+    int32_t n_potentials, n_forces, n_constraints;
+    int32_t n_ipool, n_dpool, _pad;
+    const int32_t* frame_parent;  /* [n_frames]      -1 for world                       */
+    const int32_t* frame_kind;    /* [n_frames]      TREPB_TX ...                       */
+    const int32_t* frame_config;  /* [n_frames]      driving config or -1               */
+    const double*  frame_value;   /* [n_frames]      constant transform parameter       */
+    const double*  frame_se3;     /* [n_frames][12]  row-major [R|p] for CONST_SE3      */
+    const double*  frame_mass;    /* [n_frames][4]   m Ixx Iyy Izz                      */
+    const int32_t* pot_kind;   const int32_t* pot_i;   const double* pot_d;    /* [n][1],[n][4],[n][4] */
+    const int32_t* force_kind; const int32_t* force_i; const double* force_d;
+    const int32_t* con_kind;   const int32_t* con_i;   const double* con_d;
+    const int32_t* ipool;      const double* dpool;
+} trepb_sysdesc;
+
+typedef struct trepb_system trepb_system; /* opaque */
+
+/* flags for trepb_system_create */
+#define TREPB_FLAG_NO_SPECIALIZE 1  /* use the table-driven general kernels even for small systems */
+
+int  trepb_abi_version(void);
+const char* trepb_last_error(void);
+
+/* Validate + flatten + upload tables to `device`; for small unconstrained systems also JIT a
+ * specialised kernel (NVRTC, cached on disk next to the library). */
+int  trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out);
+void trepb_system_destroy(trepb_system* sys);
+int  trepb_system_dims(const trepb_system* sys, int32_t* nq, int32_t* nd, int32_t* nk,
+                       int32_t* nu, int32_t* nc);
+/* 1 if a specialised (compile-time frame tree) kernel is in use, 0 if table-driven. */
+int  trepb_system_is_specialized(const trepb_system* sys);
+/* Emit the generated constexpr-system header text for this description (for inspection /
+ * ahead-of-time builds).  Returns required size incl. NUL; writes at most `cap` bytes. */
+int  trepb_codegen(const trepb_sysdesc* desc, char* buf, int cap);
+
+/* Per-batch arguments of a step.  Scalars apply to every instance. */
+typedef struct trepb_step_args {
+    int64_t batch;       /* B                                                              */
+    int32_t nsteps;      /* consecutive steps per instance (>= 1)                          */
+    int32_t max_iterations; /* Newton cap; reference default 200 (midpointvi.py:174)       */
+    double  t0;          /* time of the incoming state (t1 of the first step)              */
+    double  dt;          /* step length                                                    */
+    double  tolerance;   /* DEL tolerance; reference default 1e-10 (midpointvi.py:20)      */
+    /* inputs */
+    const double* q1;    /* [B][nq]  state configuration                                   */
+    const double* p1;    /* [B][nd]  state momentum                                        */
+    const double* u1;    /* [B][nsteps][nu] or NULL if nu == 0 (or to use zeros)           */
+    const double* k2;    /* [B][nsteps][nk] kinematic configs at the end of each step      */
+    const double* q2_guess;     /* [B][nd] Newton start for the FIRST step, or NULL (= q1) */
+    const double* lambda_guess; /* [B][nc] or NULL (= 0)                                   */
+    /* outputs (state after the last step) */
+    double* q2;          /* [B][nq]                                                        */
+    double* p2;          /* [B][nd]                                                        */
+    double* lambda1;     /* [B][nc]  may be NULL when nc == 0                              */
+    int32_t* iters;      /* [B] Newton iterations summed over the steps; may be NULL       */
+    int32_t* status;     /* [B] 0 ok, -1 not converged, -2 singular Jacobian               */
+    /* optional trajectory capture: every `sample_every`-th step's (q2,p2), 0 = off        */
+    int32_t sample_every;
+    int32_t _pad;
+    double* traj_q;      /* [B][nsteps/sample_every][nq] */
+    double* traj_p;      /* [B][nsteps/sample_every][nd] */
+} trepb_step_args;
+
+int trepb_step_batch(trepb_system* sys, const trepb_step_args* args);                   /* host pointers   */
+int trepb_step_batch_dev(trepb_system* sys, const trepb_step_args* args, void* stream); /* device pointers */
+
+/* p2 from two consecutive configurations (initialize_from_configs). q0,q1: [B][nq] -> p: [B][nd] */
+int trepb_calc_p2_batch(trepb_system* sys, int64_t batch, double dt,
+                        const double* q0, const double* q1, double* p);
+int trepb_calc_p2_batch_dev(trepb_system* sys, int64_t batch, double dt,
+                            const double* q0, const double* q1, double* p, void* stream);
+
+/* One linearization per instance: solve the step from (q1,p1,u1,k2[,guess]) then first
+ * derivatives.  A: [B][nX][nX], B: [B][nX][nU] with nX = 2*nq, nU = nu+nk (DSystem layout).
+ * Raw first-derivative arrays in the reference's storage layout [wrt][out] are optional. */
+typedef struct trepb_lin_args {
+    int64_t batch;
+    int32_t max_iterations;
+    int32_t _pad;
+    double  tolerance;
+    const double* t1;    /* [B] or NULL -> use t1_scalar */
+    const double* t2;    /* [B] or NULL -> use t1_scalar + dt_scalar */
+    double  t1_scalar, dt_scalar;
+    const double* q1; const double* p1; const double* u1; const double* k2;  /* [B][nq],[B][nd],[B][nu],[B][nk] */
+    const double* q2_guess; const double* lambda_guess;                      /* [B][nd],[B][nc] or NULL */
+    double* q2; double* p2; double* lambda1;       /* may be NULL */
+    int32_t* iters; int32_t* status;               /* iters may be NULL */
+    double* A; double* B;                          /* may be NULL */
+    double* q2_dq1; double* q2_dp1; double* q2_du1; double* q2_dk2;  /* [B][nq|nd|nu|nk][nd] or NULL */
+    double* p2_dq1; double* p2_dp1; double* p2_du1; double* p2_dk2;
+    double* l1_dq1; double* l1_dp1; double* l1_du1; double* l1_dk2;  /* [B][..][nc] or NULL */
+} trepb_lin_args;
+
+int trepb_linearize_batch(trepb_system* sys, const trepb_lin_args* args);
+int trepb_linearize_batch_dev(trepb_system* sys, const trepb_lin_args* args, void* stream);
+
+/* Device utilities so that a C host (no torch) can own HBM buffers. */
+int trepb_device_count(int* n);
+int trepb_malloc(int device, int64_t bytes, void** ptr);
+int trepb_free(int device, void* ptr);
+int trepb_memcpy_h2d(int device, void* dst, const void* src, int64_t bytes);
+int trepb_memcpy_d2h(int device, void* dst, const void* src, int64_t bytes);
+int trepb_synchronize(int device);
+/* Time of the most recent kernel launched by a *_dev / host entry point on this system, in
+ * milliseconds, measured with CUDA events on the launching stream (valid after a sync). */
+int trepb_last_kernel_ms(trepb_system* sys, float* ms);
+/* FP64 FMA micro-benchmark (roofline denominator): achieved TFLOP/s of a DFMA-saturating kernel. */
+int trepb_measure_fp64_peak(int device, double* tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TREPB_H */

@@ -1,0 +1,106 @@
+// TEST INFRASTRUCTURE (not shipped, not a fallback): compiles the shared host/device math of
+// trep_b200/csrc/trepb_math.cuh with g++ so that the algebra can be checked against the golden
+// vectors on a machine without a GPU.  The product path (libtrepb.so) never links this file.
+#include <stdlib.h>
+#include <string>
+#include <vector>
+#include "../include/trepb.h"
+#include "../trep_b200/csrc/trepb_math.cuh"
+#include "../trep_b200/csrc/trepb_pack.h"
+
+using namespace trepb;
+
+namespace {
+struct Host {
+    PackedSys P;
+    RtSys sys;
+    WsStrided ws;
+    std::vector<double> slab;
+    bool init(const trepb_sysdesc* d) {
+        std::string err;
+        if (!pack_system(d, &P, &err)) return false;
+        sys = P.view(P.blob.data());
+        int n = ws.layout(sys.nf, sys.nd, sys.nk, sys.nu, sys.nc);
+        slab.assign(n, 0.0);
+        ws.base = slab.data();
+        ws.stride = 1;
+        return true;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int th_step(const trepb_sysdesc* d, int nsteps, double t0, double dt, double tol, int maxit,
+            const double* q1, const double* p1, const double* u1, const double* k2,
+            const double* q2_guess, const double* lam_guess, double* q2, double* p2, double* lam,
+            int* iters) {
+    Host h;
+    if (!h.init(d)) return -100;
+    RtSys& s = h.sys;
+    WsStrided& ws = h.ws;
+    const int nd = s.nd, nk = s.nk, nq = nd + nk, nu = s.nu, nc = s.nc;
+    for (int i = 0; i < nq; ++i) { ws.q1(i) = q1[i]; ws.q2(i) = q1[i]; }
+    for (int i = 0; i < nd; ++i) { ws.p1(i) = p1[i]; if (q2_guess) ws.q2(i) = q2_guess[i]; }
+    for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
+    int total = 0;
+    double t1 = t0;
+    for (int st = 0; st < nsteps; ++st) {
+        if (st > 0) {
+            for (int i = 0; i < nq; ++i) ws.q1(i) = ws.q2(i);
+            for (int i = 0; i < nd; ++i) ws.p1(i) = ws.p2(i);
+        }
+        for (int i = 0; i < nu; ++i) ws.u1(i) = u1 ? u1[st * nu + i] : 0.0;
+        for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[st * nk + i];
+        const double t2 = t1 + dt;
+        int it = solve_del(s, ws, t1, t2, tol, maxit);
+        if (it < 0) return it;
+        total += it;
+        t1 = t2;
+    }
+    for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
+    for (int i = 0; i < nd; ++i) p2[i] = ws.p2(i);
+    for (int c = 0; c < nc; ++c) lam[c] = ws.lam(c);
+    *iters = total;
+    return 0;
+}
+
+int th_calc_p2(const trepb_sysdesc* d, double dt, const double* q0, const double* q1, double* p) {
+    Host h;
+    if (!h.init(d)) return -100;
+    for (int i = 0; i < h.sys.nd + h.sys.nk; ++i) { h.ws.q1(i) = q0[i]; h.ws.q2(i) = q1[i]; }
+    for (int i = 0; i < h.sys.nu; ++i) h.ws.u1(i) = 0.0;
+    calc_p2(h.sys, h.ws, 0.0, dt);
+    for (int i = 0; i < h.sys.nd; ++i) p[i] = h.ws.p2(i);
+    return 0;
+}
+
+// raw[12] = q2_dq1 q2_dp1 q2_du1 q2_dk2 p2_dq1 ... l1_dk2 ; any may be null
+int th_linearize(const trepb_sysdesc* d, double t1, double t2, double tol, int maxit,
+                 const double* q1, const double* p1, const double* u1, const double* k2,
+                 const double* q2_guess, const double* lam_guess, double* q2, double* p2,
+                 double* lam, int* iters, double* A, double* B, double** raw) {
+    Host h;
+    if (!h.init(d)) return -100;
+    RtSys& s = h.sys;
+    WsStrided& ws = h.ws;
+    const int nd = s.nd, nk = s.nk, nq = nd + nk, nu = s.nu, nc = s.nc;
+    for (int i = 0; i < nq; ++i) { ws.q1(i) = q1[i]; ws.q2(i) = q1[i]; }
+    for (int i = 0; i < nd; ++i) { ws.p1(i) = p1[i]; if (q2_guess) ws.q2(i) = q2_guess[i]; }
+    for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
+    for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
+    for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
+    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    if (it < 0) return it;
+    *iters = it;
+    for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
+    for (int i = 0; i < nd; ++i) p2[i] = ws.p2(i);
+    for (int c = 0; c < nc; ++c) lam[c] = ws.lam(c);
+    Deriv1Out o;
+    o.q2_dq1 = raw[0]; o.q2_dp1 = raw[1]; o.q2_du1 = raw[2]; o.q2_dk2 = raw[3];
+    o.p2_dq1 = raw[4]; o.p2_dp1 = raw[5]; o.p2_du1 = raw[6]; o.p2_dk2 = raw[7];
+    o.l1_dq1 = raw[8]; o.l1_dp1 = raw[9]; o.l1_du1 = raw[10]; o.l1_dk2 = raw[11];
+    o.A = A; o.B = B; o.es = 1;
+    return deriv1(s, ws, t1, t2, o);
+}
+}

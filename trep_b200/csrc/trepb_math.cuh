@@ -1,0 +1,1149 @@
+// Batched MidpointVI math: one *instance* per call, host+device, no Python, no allocation.
+//
+// What is computed is what the reference computes in trep/_trep/midpointvi.c:391-1120
+// (set_state / set_midpoint, calc_f, calc_bar_Df_*, DEL_solved, MidpointVI_solve_DEL,
+// calc_deriv1_cache, calc_M2, calc_proj_inv, calc_deriv1) on top of the Lagrangian sums of
+// trep/_trep/system.c:129-557 and the frame caches of trep/_trep/frame.c:839-2081.
+//
+// HOW it is computed is different (this is not a port).  The reference caches 4x4 matrices
+// g, dg/dq, d2g/dqdq, vb, dvb/dq, ... per frame and per ancestor tuple and sums
+// <vb_x, vb_y> over masses for every index pair.  Here the same quantities come from a
+// two-pass recursion in link coordinates with 6-vectors (v, w) in the reference's `unhat`
+// order (math-code.c:275-284):
+//
+//   pass 1 (root->leaf)  V_f  = Ad(lg_f^-1) V_parent + s_f dq_f            body velocity
+//                        W_f  = [Ad(lg_f^-1) V_parent, s_f]                = d vb / d q_f
+//   pass 2 (leaf->root)  Ic_f = I_f + sum_children Ad^T Ic_child Ad        composite inertia
+//                        mu_f = I_f V_f + sum_children Ad^T mu_child       composite momentum
+//   per joint j          L_ddq(j)   = s_j . mu_j          L_dq(j) = W_j . mu_j - dV/dq_j
+//                        H_j = Ic_j s_j ,  G_j = Ic_j W_j - ad*_{s_j} mu_j
+//   per ancestor i of j  (H, G carried up the chain as force vectors)
+//                        L_ddqddq(i,j) = s_i.H   L_ddqdq(i,j) = s_i.G   L_ddqdq(j,i) = W_i.H
+//                        L_dqdq(i,j)   = W_i.G  (+ gravity: w_i . (P_j x g))
+//
+// using  d s_i/d q_j = [s_i, s_j] for i above j (Lie bracket of twists) — the identities
+// behind Johnson & Murphey's eqs. (3)-(10) that frame.c implements entry by entry.
+// Cost per evaluation is O(frames + sum_j depth(j)) instead of O(masses * depth^2) 4x4 products.
+// Points (constraints, springs, dampers) use world-frame kinematics:
+//   dp_F/dq_j = a_j (prismatic) | a_j x (p_F - o_j) (revolute),   d2p_F/dq_i dq_j = w_i x dp_F/dq_j.
+//
+// Everything is templated on  Sys (RtSys | generated constexpr system)  and
+// Ws (WsStrided | WsStatic<Sys>) so the same source is the general kernel and the
+// fully-unrolled specialised kernel.
+#pragma once
+#include <math.h>
+#include "trepb_sys.h"
+#include "trepb_ws.h"
+
+namespace trepb {
+
+#if defined(__CUDA_ARCH__)
+#define TREPB_UNROLL _Pragma("unroll")
+#else
+#define TREPB_UNROLL
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// small helpers
+// ---------------------------------------------------------------------------------------------
+struct Axis {
+    int a, b, c;
+    bool rot;
+};
+TREPB_HD Axis axis_of(int kind) {
+    Axis x;
+    int k = kind - K_TX;
+    x.rot = k >= 3;
+    x.a = x.rot ? k - 3 : k;
+    x.b = (x.a + 1) % 3;
+    x.c = (x.a + 2) % 3;
+    return x;
+}
+TREPB_HD int symi(int r, int s) {  // index into (00,11,22,01,02,12)
+    return r == s ? r : (r + s + 2);
+}
+TREPB_HD void cross3(const double* x, const double* y, double* o) {
+    o[0] = x[1] * y[2] - x[2] * y[1];
+    o[1] = x[2] * y[0] - x[0] * y[2];
+    o[2] = x[0] * y[1] - x[1] * y[0];
+}
+TREPB_HD double dot3(const double* x, const double* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; }
+TREPB_HD double dot6(const double* x, const double* y) {
+    return x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3] + x[4] * y[4] + x[5] * y[5];
+}
+// planar rotation of components (b,c):  R^T x  (parent->child)  and  R x  (child->parent)
+TREPB_HD void rotT(double* x, int b, int c, double cs, double sn) {
+    double xb = x[b], xc = x[c];
+    x[b] = cs * xb + sn * xc;
+    x[c] = -sn * xb + cs * xc;
+}
+TREPB_HD void rotF(double* x, int b, int c, double cs, double sn) {
+    double xb = x[b], xc = x[c];
+    x[b] = cs * xb - sn * xc;
+    x[c] = sn * xb + cs * xc;
+}
+TREPB_HD void sincos_(double x, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(x, s, c);
+#else
+    *s = sin(x);
+    *c = cos(x);
+#endif
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 1: root -> leaf.  Inputs ws.qe (evaluation configuration) and ws.dq.
+//   with_vel   : body velocities V, W and gravity direction gf (needed at the midpoint)
+//   with_world : world pose Rw, pw of the frames that carry points (constraints/springs)
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
+    TREPB_UNROLL
+    for (int f = 1; f < sys.NF(); ++f) {
+        const int par = sys.parent(f), kind = sys.kind(f), cfg = sys.config(f);
+        const bool vel = with_vel && sys.mass_below(f);
+        const bool wrl = with_world && sys.need_world(f);
+        if (!vel && !wrl) continue;
+        const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+        double g[3], V[6], R[9], p[3];
+        if (vel) {
+            if (par == 0) {
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = sys.gravity(k);
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k] = 0.0;
+            } else {
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = ws.gf(par, k);
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k] = ws.V(par, k);
+            }
+        }
+        if (wrl) {
+            if (par == 0) {
+                TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k] = 0.0;
+            } else {
+                TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k] = ws.Rw(par, k);
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k] = ws.pw(par, k);
+            }
+        }
+        if (kind == K_CONST_SE3) {
+            double lR[9], lp[3];
+            TREPB_UNROLL for (int r = 0; r < 3; ++r) {
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) lR[r * 3 + c] = sys.se3(f, r * 4 + c);
+                lp[r] = sys.se3(f, r * 4 + 3);
+            }
+            if (vel) {
+                double t[3], u[3];
+                // v' = R^T (v + w x p), w' = R^T w, g' = R^T g
+                cross3(V + 3, lp, t);
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) t[k] += V[k];
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) u[c] = lR[c] * t[0] + lR[3 + c] * t[1] + lR[6 + c] * t[2];
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) t[c] = lR[c] * V[3] + lR[3 + c] * V[4] + lR[6 + c] * V[5];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) { V[k] = u[k]; V[3 + k] = t[k]; }
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) u[c] = lR[c] * g[0] + lR[3 + c] * g[1] + lR[6 + c] * g[2];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = u[k];
+            }
+            if (wrl) {
+                double Rn[9];
+                TREPB_UNROLL for (int r = 0; r < 3; ++r) {
+                    p[r] += R[r * 3] * lp[0] + R[r * 3 + 1] * lp[1] + R[r * 3 + 2] * lp[2];
+                }
+                TREPB_UNROLL for (int r = 0; r < 3; ++r)
+                    TREPB_UNROLL for (int c = 0; c < 3; ++c)
+                        Rn[r * 3 + c] = R[r * 3] * lR[c] + R[r * 3 + 1] * lR[3 + c] + R[r * 3 + 2] * lR[6 + c];
+                TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k] = Rn[k];
+            }
+        } else {
+            const Axis ax = axis_of(kind);
+            if (ax.rot) {
+                double sn, cs;
+                sincos_(x, &sn, &cs);
+                ws.cs(f, 0) = cs;
+                ws.cs(f, 1) = sn;
+                if (vel) {
+                    rotT(g, ax.b, ax.c, cs, sn);
+                    rotT(V, ax.b, ax.c, cs, sn);
+                    rotT(V + 3, ax.b, ax.c, cs, sn);
+                }
+                if (wrl) {
+                    TREPB_UNROLL for (int r = 0; r < 3; ++r) {
+                        double rb = R[r * 3 + ax.b], rc = R[r * 3 + ax.c];
+                        R[r * 3 + ax.b] = cs * rb + sn * rc;
+                        R[r * 3 + ax.c] = -sn * rb + cs * rc;
+                    }
+                }
+            } else {
+                if (vel) {
+                    // v' = v + w x (x e_a)
+                    V[ax.b] += x * V[3 + ax.c];
+                    V[ax.c] -= x * V[3 + ax.b];
+                }
+                if (wrl) {
+                    TREPB_UNROLL for (int r = 0; r < 3; ++r) p[r] += x * R[r * 3 + ax.a];
+                }
+            }
+            if (vel && cfg >= 0) {
+                // W = [S, s] with S the velocity carried in from the parent
+                double W[6];
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = 0.0;
+                if (ax.rot) {
+                    W[ax.b] = V[ax.c];          // v_S x e_a
+                    W[ax.c] = -V[ax.b];
+                    W[3 + ax.b] = V[3 + ax.c];  // w_S x e_a
+                    W[3 + ax.c] = -V[3 + ax.b];
+                    V[3 + ax.a] += ws.dq(cfg);
+                } else {
+                    W[ax.b] = V[3 + ax.c];      // w_S x e_a
+                    W[ax.c] = -V[3 + ax.b];
+                    V[ax.a] += ws.dq(cfg);
+                }
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.W(f, k) = W[k];
+            }
+        }
+        if (vel) {
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.gf(f, k) = g[k];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.V(f, k) = V[k];
+        }
+        if (wrl) {
+            TREPB_UNROLL for (int k = 0; k < 9; ++k) ws.Rw(f, k) = R[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.pw(f, k) = p[k];
+        }
+    }
+}
+
+// force-vector transform child -> parent through frame f:  f' = R f, n' = R n + p x (R f)
+template <class Sys, class Ws>
+TREPB_HD void force_up(const Sys& sys, Ws& ws, int f, double* F) {
+    const int kind = sys.kind(f);
+    if (kind == K_CONST_SE3) {
+        double a[3], b[3], lp[3], t[3];
+        TREPB_UNROLL for (int r = 0; r < 3; ++r) {
+            a[r] = sys.se3(f, r * 4) * F[0] + sys.se3(f, r * 4 + 1) * F[1] + sys.se3(f, r * 4 + 2) * F[2];
+            b[r] = sys.se3(f, r * 4) * F[3] + sys.se3(f, r * 4 + 1) * F[4] + sys.se3(f, r * 4 + 2) * F[5];
+            lp[r] = sys.se3(f, r * 4 + 3);
+        }
+        cross3(lp, a, t);
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) { F[k] = a[k]; F[3 + k] = b[k] + t[k]; }
+    } else {
+        const Axis ax = axis_of(kind);
+        if (ax.rot) {
+            const double cs = ws.cs(f, 0), sn = ws.cs(f, 1);
+            rotF(F, ax.b, ax.c, cs, sn);
+            rotF(F + 3, ax.b, ax.c, cs, sn);
+        } else {
+            const int cfg = sys.config(f);
+            const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+            F[3 + ax.b] -= x * F[ax.c];
+            F[3 + ax.c] += x * F[ax.b];
+        }
+    }
+}
+// free-vector transform child -> parent
+template <class Sys, class Ws>
+TREPB_HD void vec_up(const Sys& sys, Ws& ws, int f, double* N) {
+    const int kind = sys.kind(f);
+    if (kind == K_CONST_SE3) {
+        double a[3];
+        TREPB_UNROLL for (int r = 0; r < 3; ++r)
+            a[r] = sys.se3(f, r * 4) * N[0] + sys.se3(f, r * 4 + 1) * N[1] + sys.se3(f, r * 4 + 2) * N[2];
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) N[k] = a[k];
+    } else {
+        const Axis ax = axis_of(kind);
+        if (ax.rot) rotF(N, ax.b, ax.c, ws.cs(f, 0), ws.cs(f, 1));
+    }
+}
+
+// (f, n) = I (v, w) for I = (m, h, Isym6):  f = m v + w x h ,  n = Ibar w + h x v
+TREPB_HD void inertia_apply(double m, const double* h, const double* I, const double* X, double* F) {
+    double t[3];
+    cross3(X + 3, h, t);
+    TREPB_UNROLL for (int k = 0; k < 3; ++k) F[k] = m * X[k] + t[k];
+    cross3(h, X, t);
+    F[3] = I[0] * X[3] + I[3] * X[4] + I[4] * X[5] + t[0];
+    F[4] = I[3] * X[3] + I[1] * X[4] + I[5] * X[5] + t[1];
+    F[5] = I[4] * X[3] + I[5] * X[4] + I[2] * X[5] + t[2];
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass 2: leaf -> root.  order 1: Lq, Lv.  order 2: also Lqq, Lvq, Lvv (all nq x nq).
+// Potentials other than gravity are added by add_potentials().
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
+    const int nq = sys.NQ();
+    TREPB_UNROLL for (int i = 0; i < nq; ++i) {
+        ws.Lq(i) = 0.0;
+        ws.Lv(i) = 0.0;
+    }
+    if (order >= 2) {
+        TREPB_UNROLL for (int i = 0; i < nq; ++i)
+            TREPB_UNROLL for (int j = 0; j < nq; ++j) {
+                ws.Lqq(i, j) = 0.0;
+                ws.Lvq(i, j) = 0.0;
+                ws.Lvv(i, j) = 0.0;
+            }
+    }
+    // own inertia / momentum
+    TREPB_UNROLL
+    for (int f = 1; f < sys.NF(); ++f) {
+        if (!sys.mass_below(f)) continue;
+        const double m = sys.mass(f, 0);
+        ws.Im(f) = m;
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.Ih(f, k) = 0.0;
+        if (order >= 2) {
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) {
+                ws.II(f, k) = sys.mass(f, 1 + k);
+                ws.II(f, 3 + k) = 0.0;
+            }
+        }
+        if (sys.has_mass(f)) {
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) {
+                ws.mu(f, k) = m * ws.V(f, k);
+                ws.mu(f, 3 + k) = sys.mass(f, 1 + k) * ws.V(f, 3 + k);
+            }
+        } else {
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.mu(f, k) = 0.0;
+        }
+    }
+    TREPB_UNROLL
+    for (int f = sys.NF() - 1; f >= 1; --f) {
+        if (!sys.mass_below(f)) continue;
+        const int kind = sys.kind(f), cfg = sys.config(f), par = sys.parent(f);
+        double m = ws.Im(f), h[3], I[6], mu[6], g[3];
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) { h[k] = ws.Ih(f, k); g[k] = ws.gf(f, k); }
+        TREPB_UNROLL for (int k = 0; k < 6; ++k) mu[k] = ws.mu(f, k);
+        if (order >= 2) { TREPB_UNROLL for (int k = 0; k < 6; ++k) I[k] = ws.II(f, k); }
+
+        if (cfg >= 0) {
+            const Axis ax = axis_of(kind);
+            double W[6];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = ws.W(f, k);
+            // first order: L_ddq = s.mu ; L_dq = W.mu + g.(m v_s + w_s x h)
+            double hxg[3];
+            cross3(h, g, hxg);
+            ws.Lv(cfg) = ax.rot ? mu[3 + ax.a] : mu[ax.a];
+            ws.Lq(cfg) = dot6(W, mu) + (sys.gravity_on() ? (ax.rot ? hxg[ax.a] : m * g[ax.a]) : 0.0);
+            if (order >= 2) {
+                double H[6], G[6], N[3], P[3], t[3];
+                // H = Ic s
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) H[k] = 0.0;
+                if (ax.rot) {
+                    H[ax.b] = -h[ax.c];  // e_a x h
+                    H[ax.c] = h[ax.b];
+                    H[3 + ax.a] = I[symi(ax.a, ax.a)];
+                    H[3 + ax.b] = I[symi(ax.a, ax.b)];
+                    H[3 + ax.c] = I[symi(ax.a, ax.c)];
+                } else {
+                    H[ax.a] = m;
+                    H[3 + ax.b] = h[ax.c];  // h x e_a
+                    H[3 + ax.c] = -h[ax.b];
+                }
+                // G = Ic W - ad*_s mu ;  ad*_s mu = (f x w_s, n x w_s + f x v_s)
+                inertia_apply(m, h, I, W, G);
+                if (ax.rot) {
+                    G[ax.b] -= mu[ax.c];
+                    G[ax.c] += mu[ax.b];
+                    G[3 + ax.b] -= mu[3 + ax.c];
+                    G[3 + ax.c] += mu[3 + ax.b];
+                } else {
+                    G[3 + ax.b] -= mu[ax.c];
+                    G[3 + ax.c] += mu[ax.b];
+                }
+                // gravity second derivative:  N = P x g ,  P = m v_s + w_s x h
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) P[k] = 0.0;
+                if (ax.rot) {
+                    P[ax.b] = -h[ax.c];
+                    P[ax.c] = h[ax.b];
+                } else {
+                    P[ax.a] = m;
+                }
+                cross3(P, g, N);
+                (void)t;
+                // walk to the root
+                int cur = f;
+                for (;;) {
+                    const int ci = sys.config(cur);
+                    if (ci >= 0) {
+                        const Axis ai = axis_of(sys.kind(cur));
+                        const double sH = ai.rot ? H[3 + ai.a] : H[ai.a];
+                        const double sG = ai.rot ? G[3 + ai.a] : G[ai.a];
+                        double Wi[6];
+                        TREPB_UNROLL for (int k = 0; k < 6; ++k) Wi[k] = ws.W(cur, k);
+                        double WG = dot6(Wi, G);
+                        if (sys.gravity_on() && ai.rot) WG += N[ai.a];
+                        if (ci == cfg) {
+                            ws.Lvv(cfg, cfg) = sH;
+                            ws.Lvq(cfg, cfg) = sG;
+                            ws.Lqq(cfg, cfg) = WG;
+                        } else {
+                            ws.Lvv(ci, cfg) = sH;
+                            ws.Lvv(cfg, ci) = sH;
+                            ws.Lvq(ci, cfg) = sG;
+                            ws.Lvq(cfg, ci) = dot6(Wi, H);
+                            ws.Lqq(ci, cfg) = WG;
+                            ws.Lqq(cfg, ci) = WG;
+                        }
+                    }
+                    const int up = sys.parent(cur);
+                    if (up == 0) break;
+                    force_up(sys, ws, cur, H);
+                    force_up(sys, ws, cur, G);
+                    if (sys.gravity_on()) vec_up(sys, ws, cur, N);
+                    cur = up;
+                }
+            }
+        }
+        if (par == 0) continue;
+        // accumulate composite momentum / inertia into the parent
+        force_up(sys, ws, f, mu);
+        TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.mu(par, k) += mu[k];
+        if (kind == K_CONST_SE3) {
+            double R[9], lp[3], hr[3];
+            TREPB_UNROLL for (int r = 0; r < 3; ++r) {
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) R[r * 3 + c] = sys.se3(f, r * 4 + c);
+                lp[r] = sys.se3(f, r * 4 + 3);
+            }
+            TREPB_UNROLL for (int r = 0; r < 3; ++r) hr[r] = R[r * 3] * h[0] + R[r * 3 + 1] * h[1] + R[r * 3 + 2] * h[2];
+            if (order >= 2) {
+                // Ibar' = R Ibar R^T + 2(hr.p)1 - hr p^T - p hr^T + m(|p|^2 1 - p p^T)
+                double M[9], T[9];
+                M[0] = I[0]; M[4] = I[1]; M[8] = I[2];
+                M[1] = M[3] = I[3]; M[2] = M[6] = I[4]; M[5] = M[7] = I[5];
+                TREPB_UNROLL for (int r = 0; r < 3; ++r)
+                    TREPB_UNROLL for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = R[r * 3] * M[c] + R[r * 3 + 1] * M[3 + c] + R[r * 3 + 2] * M[6 + c];
+                const double hp = dot3(hr, lp), pp = dot3(lp, lp);
+                TREPB_UNROLL for (int r = 0; r < 3; ++r)
+                    TREPB_UNROLL for (int c = r; c < 3; ++c) {
+                        double v = T[r * 3] * R[c * 3] + T[r * 3 + 1] * R[c * 3 + 1] + T[r * 3 + 2] * R[c * 3 + 2];
+                        v += -hr[r] * lp[c] - lp[r] * hr[c] - m * lp[r] * lp[c];
+                        if (r == c) v += 2.0 * hp + m * pp;
+                        ws.II(par, symi(r, c)) += v;
+                    }
+            }
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.Ih(par, k) += hr[k] + m * lp[k];
+            ws.Im(par) += m;
+        } else {
+            const Axis ax = axis_of(kind);
+            if (ax.rot) {
+                const double cs = ws.cs(f, 0), sn = ws.cs(f, 1);
+                if (order >= 2) {
+                    const int iaa = symi(ax.a, ax.a), ibb = symi(ax.b, ax.b), icc = symi(ax.c, ax.c);
+                    const int iab = symi(ax.a, ax.b), iac = symi(ax.a, ax.c), ibc = symi(ax.b, ax.c);
+                    const double c2 = cs * cs, s2 = sn * sn, sc = sn * cs;
+                    ws.II(par, iaa) += I[iaa];
+                    ws.II(par, iab) += cs * I[iab] - sn * I[iac];
+                    ws.II(par, iac) += sn * I[iab] + cs * I[iac];
+                    ws.II(par, ibb) += c2 * I[ibb] - 2.0 * sc * I[ibc] + s2 * I[icc];
+                    ws.II(par, icc) += s2 * I[ibb] + 2.0 * sc * I[ibc] + c2 * I[icc];
+                    ws.II(par, ibc) += sc * (I[ibb] - I[icc]) + (c2 - s2) * I[ibc];
+                }
+                rotF(h, ax.b, ax.c, cs, sn);
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.Ih(par, k) += h[k];
+                ws.Im(par) += m;
+            } else {
+                const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+                if (order >= 2) {
+                    const int ibb = symi(ax.b, ax.b), icc = symi(ax.c, ax.c);
+                    const int iab = symi(ax.a, ax.b), iac = symi(ax.a, ax.c);
+                    const double d = 2.0 * h[ax.a] * x + m * x * x;
+                    TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.II(par, k) += I[k];
+                    ws.II(par, ibb) += d;
+                    ws.II(par, icc) += d;
+                    ws.II(par, iab) -= x * h[ax.b];
+                    ws.II(par, iac) -= x * h[ax.c];
+                }
+                h[ax.a] += m * x;
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.Ih(par, k) += h[k];
+                ws.Im(par) += m;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// world-frame point kinematics
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void joint_axis_w(const Sys& sys, Ws& ws, int j, double* aw, bool* rot, int* fj) {
+    const int f = sys.cfg_frame(j);
+    const Axis ax = axis_of(sys.kind(f));
+    TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = ws.Rw(f, r * 3 + ax.a);
+    *rot = ax.rot;
+    *fj = f;
+}
+template <class Sys, class Ws>
+TREPB_HD void frame_pos(const Sys& sys, Ws& ws, int F, double* p) {
+    if (F == 0) { p[0] = p[1] = p[2] = 0.0; }
+    else { TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k] = ws.pw(F, k); }
+}
+// d p_F / d q_j   (zero when F does not depend on q_j; trep/_trep/frame.c:2247-2262)
+template <class Sys, class Ws>
+TREPB_HD void dpoint(const Sys& sys, Ws& ws, int F, int j, double* out) {
+    out[0] = out[1] = out[2] = 0.0;
+    if (F == 0 || sys.cfg_frame(j) < 0 || !sys.dep(F, j)) return;
+    double aw[3];
+    bool rot;
+    int fj;
+    joint_axis_w(sys, ws, j, aw, &rot, &fj);
+    if (rot) {
+        double r[3];
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) r[k] = ws.pw(F, k) - ws.pw(fj, k);
+        cross3(aw, r, out);
+    } else {
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) out[k] = aw[k];
+    }
+}
+// d2 p_F / d q_i d q_j
+template <class Sys, class Ws>
+TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, double* out) {
+    out[0] = out[1] = out[2] = 0.0;
+    if (F == 0 || sys.cfg_frame(i) < 0 || sys.cfg_frame(j) < 0) return;
+    if (!sys.dep(F, i) || !sys.dep(F, j)) return;
+    // the upper joint's axis crosses the lower joint's first derivative
+    int up = i, lo = j;
+    if (!sys.dep(sys.cfg_frame(j), i)) { up = j; lo = i; }
+    double aw[3], d[3];
+    bool rot;
+    int fu;
+    joint_axis_w(sys, ws, up, aw, &rot, &fu);
+    if (!rot) return;
+    dpoint(sys, ws, F, lo, d);
+    cross3(aw, d, out);
+}
+
+// v = pA - pB and dv_j = d(pA-pB)/dq_j for all configs into ws.dv
+template <class Sys, class Ws>
+TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, double* v) {
+    double pa[3], pb[3];
+    frame_pos(sys, ws, A, pa);
+    frame_pos(sys, ws, B, pb);
+    TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+    TREPB_UNROLL
+    for (int j = 0; j < sys.NQ(); ++j) {
+        double da[3], db[3];
+        dpoint(sys, ws, A, j, da);
+        dpoint(sys, ws, B, j, db);
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.dv(j, k) = da[k] - db[k];
+    }
+}
+template <class Sys, class Ws>
+TREPB_HD void pair_second(const Sys& sys, Ws& ws, int A, int B, int i, int j, double* ddv) {
+    double a[3], b[3];
+    ddpoint(sys, ws, A, i, j, a);
+    ddpoint(sys, ws, B, i, j, b);
+    TREPB_UNROLL for (int k = 0; k < 3; ++k) ddv[k] = a[k] - b[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// constraints (trep/_trep/constraints/distance.c:16-100, point.c:16-46)
+//   mode bit 0: h -> ws.hc      bit 1: Dh -> dest (Dh1 or Dh2)     bit 2: DDhl += lam_c * h_c,ij
+// World pose must be current (pass1 with_world at the wanted evaluation point).
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
+    const int nq = sys.NQ();
+    if (mode & 4) {
+        TREPB_UNROLL for (int i = 0; i < nq; ++i)
+            TREPB_UNROLL for (int j = 0; j < nq; ++j) ws.DDhl(i, j) = 0.0;
+    }
+    TREPB_UNROLL
+    for (int c = 0; c < sys.NC(); ++c) {
+        const int kind = sys.con_kind(c);
+        const int A = sys.con_i(c, 0), B = sys.con_i(c, 1), third = sys.con_i(c, 2);
+        double v[3];
+        pair_first(sys, ws, A, B, v);
+        if (kind == C_DISTANCE) {
+            const double d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
+            if (mode & 1) ws.hc(c) = dot3(v, v) - d * d;
+            if (mode & 2) {
+                TREPB_UNROLL
+                for (int j = 0; j < nq; ++j) {
+                    double val = 0.0;
+                    if (sys.dep(A, j) || sys.dep(B, j) || third == j) {
+                        val = v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2);
+                        if (third == j) val -= d;
+                        val *= 2.0;
+                    }
+                    if (which_dh == 1) ws.Dh1(c, j) = val; else ws.Dh2(c, j) = val;
+                }
+            }
+            if (mode & 4) {
+                const double lam = ws.lam(c);
+                TREPB_UNROLL
+                for (int i = 0; i < nq; ++i) {
+                    if (!(sys.dep(A, i) || sys.dep(B, i) || third == i)) continue;
+                    TREPB_UNROLL
+                    for (int j = i; j < nq; ++j) {
+                        if (!(sys.dep(A, j) || sys.dep(B, j) || third == j)) continue;
+                        double ddv[3];
+                        pair_second(sys, ws, A, B, i, j, ddv);
+                        double val = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2)
+                                   + v[0] * ddv[0] + v[1] * ddv[1] + v[2] * ddv[2];
+                        if (third == i && third == j) val -= 1.0;
+                        val *= 2.0 * lam;
+                        ws.DDhl(i, j) += val;
+                        if (j != i) ws.DDhl(j, i) += val;
+                    }
+                }
+            }
+        } else {  // C_POINT1D
+            const int comp = third;
+            if (mode & 1) ws.hc(c) = v[comp];
+            if (mode & 2) {
+                TREPB_UNROLL
+                for (int j = 0; j < nq; ++j) {
+                    const double val = ws.dv(j, comp);
+                    if (which_dh == 1) ws.Dh1(c, j) = val; else ws.Dh2(c, j) = val;
+                }
+            }
+            if (mode & 4) {
+                const double lam = ws.lam(c);
+                TREPB_UNROLL
+                for (int i = 0; i < nq; ++i)
+                    TREPB_UNROLL
+                    for (int j = i; j < nq; ++j) {
+                        double ddv[3];
+                        pair_second(sys, ws, A, B, i, j, ddv);
+                        const double val = lam * ddv[comp];
+                        ws.DDhl(i, j) += val;
+                        if (j != i) ws.DDhl(j, i) += val;
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// potentials other than gravity, at the current point (potentials/linearspring.c:30-74,
+// configspring.c:22-38).  order as in pass2.
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
+    const int nq = sys.NQ();
+    TREPB_UNROLL
+    for (int p = 0; p < sys.NPOT(); ++p) {
+        const int kind = sys.pot_kind(p);
+        if (kind == P_CONFIG_SPRING) {
+            const int c = sys.pot_i(p, 0);
+            const double k = sys.pot_d(p, 0), q0 = sys.pot_d(p, 1);
+            ws.Lq(c) -= k * (ws.qe(c) - q0);
+            if (order >= 2) ws.Lqq(c, c) -= k;
+        } else if (kind == P_LINEAR_SPRING) {
+            const int A = sys.pot_i(p, 0), B = sys.pot_i(p, 1);
+            const double k = sys.pot_d(p, 0), x0 = sys.pot_d(p, 1);
+            double v[3];
+            pair_first(sys, ws, A, B, v);
+            const double x = sqrt(dot3(v, v));
+            TREPB_UNROLL
+            for (int j = 0; j < nq; ++j) {
+                double dx = (1.0 / x) * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
+                ws.dxs(j) = dx;
+                double val = k * (x - x0) * dx;
+                if (isnan(dx) && x0 == 0.0) val = 0.0;
+                ws.Lq(j) -= val;
+            }
+            if (order >= 2) {
+                TREPB_UNROLL
+                for (int i = 0; i < nq; ++i)
+                    TREPB_UNROLL
+                    for (int j = i; j < nq; ++j) {
+                        if (!(sys.dep(A, i) || sys.dep(B, i)) || !(sys.dep(A, j) || sys.dep(B, j))) continue;
+                        double ddv[3];
+                        pair_second(sys, ws, A, B, i, j, ddv);
+                        const double vdi = v[0] * ws.dv(i, 0) + v[1] * ws.dv(i, 1) + v[2] * ws.dv(i, 2);
+                        const double didj = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2);
+                        const double dix = ws.dxs(i), djx = ws.dxs(j);
+                        const double ddx = -djx / (x * x) * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
+                        const double val = k * dix * djx + k * (x - x0) * ddx;
+                        ws.Lqq(i, j) -= val;
+                        if (j != i) ws.Lqq(j, i) -= val;
+                    }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// forces at the current point (forces/damping.c, configforce.c, lineardamper.c + tapemeasure.c)
+//   order 1: Fo        order 2: also Fq, Fv, Fu
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
+    const int nq = sys.NQ(), nd = sys.ND();
+    TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.Fo(j) = 0.0;
+    if (order >= 2) {
+        TREPB_UNROLL for (int j = 0; j < nd; ++j) {
+            TREPB_UNROLL for (int i = 0; i < nq; ++i) { ws.Fq(j, i) = 0.0; ws.Fv(j, i) = 0.0; }
+            TREPB_UNROLL for (int u = 0; u < sys.NU(); ++u) ws.Fu(j, u) = 0.0;
+        }
+    }
+    TREPB_UNROLL
+    for (int fo = 0; fo < sys.NFORCE(); ++fo) {
+        const int kind = sys.force_kind(fo);
+        if (kind == F_DAMPING) {
+            const int off = sys.force_i(fo, 0);
+            TREPB_UNROLL
+            for (int j = 0; j < nd; ++j) {
+                const double c = sys.dpool(off + j);
+                ws.Fo(j) += -c * ws.dq(j);
+                if (order >= 2) ws.Fv(j, j) += -c;
+            }
+        } else if (kind == F_CONFIG) {
+            const int c = sys.force_i(fo, 0), u = sys.force_i(fo, 1);
+            if (c < nd) {
+                ws.Fo(c) += ws.u1(u);
+                if (order >= 2) ws.Fu(c, u) += 1.0;
+            }
+        } else if (kind == F_LINEAR_DAMPER) {
+            // single-segment tape measure between two frames (forces/lineardamper.py:34)
+            const int off = sys.force_i(fo, 0);
+            const int A = sys.ipool(off), B = sys.ipool(off + 1);
+            const double cdamp = sys.force_d(fo, 0);
+            double v[3];
+            pair_first(sys, ws, A, B, v);
+            const double x = sqrt(dot3(v, v));
+            double vel = 0.0;
+            // dx_j only where exactly one end depends on q_j (tapemeasure.py:97-110)
+            TREPB_UNROLL
+            for (int j = 0; j < nq; ++j) {
+                double dx = 0.0;
+                if (sys.dep(A, j) != sys.dep(B, j))
+                    dx = 1.0 / x * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
+                ws.dxs(j) = dx;
+                vel += dx * ws.dq(j);
+            }
+            TREPB_UNROLL
+            for (int j = 0; j < nd; ++j) {
+                if (sys.dep(A, j) == sys.dep(B, j)) continue;
+                ws.Fo(j) += -cdamp * vel * ws.dxs(j);
+            }
+            if (order >= 2) {
+                // ddx(j,i) = TapeMeasure_length_dqdq(q_j, q_i) ; vel_dq(i) = sum_k ddx(k,i) dq_k
+                TREPB_UNROLL
+                for (int i = 0; i < nq; ++i) {
+                    if (sys.dep(A, i) == sys.dep(B, i)) continue;
+                    double veldq = 0.0;
+                    TREPB_UNROLL
+                    for (int k = 0; k < nq; ++k) {
+                        double ddx = 0.0;
+                        if (sys.dep(A, k) != sys.dep(B, k)) {
+                            double ddv[3];
+                            pair_second(sys, ws, A, B, k, i, ddv);
+                            const double dkdi = ws.dv(k, 0) * ws.dv(i, 0) + ws.dv(k, 1) * ws.dv(i, 1) + ws.dv(k, 2) * ws.dv(i, 2);
+                            double t = ws.dxs(k) * ws.dxs(i) - dkdi - dot3(v, ddv);
+                            ddx = -1.0 / x * t;
+                        }
+                        veldq += ddx * ws.dq(k);
+                        if (k < nd) ws.Fq(k, i) += -cdamp * vel * ddx;  // second term of f_dq
+                    }
+                    TREPB_UNROLL
+                    for (int j = 0; j < nd; ++j) {
+                        if (sys.dep(A, j) == sys.dep(B, j)) continue;
+                        ws.Fq(j, i) += -cdamp * veldq * ws.dxs(j);
+                        ws.Fv(j, i) += -cdamp * ws.dxs(i) * ws.dxs(j);
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Crout LU with implicit scaling, exactly the reference's pivoting rules
+// (trep/_trep/math-code.c:337-432) so that pivot choices - and therefore rounding - agree.
+// A(i,j) accessor object, piv/scales arrays in the workspace.  Returns false if singular.
+// ---------------------------------------------------------------------------------------------
+template <class MatAcc, class PivAcc, class ScaleAcc>
+TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol) {
+    for (int i = 0; i < n; ++i) {
+        double s = -1.0;
+        for (int j = 0; j < n; ++j) {
+            const double a = fabs(A(i, j));
+            if (a > s) s = a;
+        }
+        scales(i) = 1.0 / s;
+        piv(i) = (double)i;
+    }
+    for (int j = 0; j < n; ++j) {
+        for (int i = 0; i < j; ++i) {
+            double a = A(i, j);
+            for (int k = 0; k < i; ++k) a -= A(i, k) * A(k, j);
+            A(i, j) = a;
+        }
+        double pv = -1.0;
+        int pi = 0;
+        for (int i = j; i < n; ++i) {
+            double a = A(i, j);
+            for (int k = 0; k < j; ++k) a -= A(i, k) * A(k, j);
+            A(i, j) = a;
+            const double t = fabs(a * scales(i));
+            if (t > pv) { pv = t; pi = i; }
+        }
+        if (pv <= tol) return false;
+        if (pi != j) {
+            const double ti = piv(j); piv(j) = piv(pi); piv(pi) = ti;
+            for (int k = 0; k < n; ++k) { const double t = A(j, k); A(j, k) = A(pi, k); A(pi, k) = t; }
+            scales(pi) = scales(j);
+        }
+        const double d = A(j, j);
+        for (int i = j + 1; i < n; ++i) A(i, j) /= d;
+    }
+    return true;
+}
+// solves in place: b <- A^-1 b  (math-code.c:434-461); x is scratch of length n
+template <class MatAcc, class PivAcc, class BAcc, class XAcc>
+TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x) {
+    for (int i = 0; i < n; ++i) {
+        double t = b((int)piv(i));
+        for (int j = 0; j < i; ++j) t -= A(i, j) * x(j);
+        x(i) = t;
+    }
+    for (int i = n - 1; i >= 0; --i) {
+        double t = x(i);
+        for (int j = i + 1; j < n; ++j) t -= A(i, j) * x(j);
+        t = t / A(i, i);
+        x(i) = t;
+    }
+    for (int i = 0; i < n; ++i) b(i) = x(i);
+}
+
+// accessor adaptors over workspace arrays
+#define TREPB_ACC2(NAME, FIELD)                                         \
+    template <class Ws> struct NAME {                                   \
+        Ws* w;                                                          \
+        TREPB_HD double& operator()(int i, int j) const { return w->FIELD(i, j); } \
+    };
+#define TREPB_ACC1(NAME, FIELD)                                         \
+    template <class Ws> struct NAME {                                   \
+        Ws* w;                                                          \
+        TREPB_HD double& operator()(int i) const { return w->FIELD(i); } \
+    };
+TREPB_ACC2(AccDf, Df) TREPB_ACC2(AccM2, M2) TREPB_ACC2(AccPJ, PJ)
+TREPB_ACC1(AccPiv, piv) TREPB_ACC1(AccLus, lus) TREPB_ACC1(AccLux, lux) TREPB_ACC1(AccFr, fr)
+TREPB_ACC1(AccM2p, M2p) TREPB_ACC1(AccPJp, PJp) TREPB_ACC1(AccTnd, tnd) TREPB_ACC1(AccTnc, tnc)
+TREPB_ACC1(AccCol, col)
+template <class Ws> struct AccTdcCol {  // column k of Tdc (nd x nc)
+    Ws* w; int k;
+    TREPB_HD double& operator()(int i) const { return w->Tdc(i, k); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// evaluation-point setters (midpointvi.c:401-457)
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, double dt) {  // 0 = midpoint, 1 = q1, 2 = q2
+    TREPB_UNROLL
+    for (int i = 0; i < sys.NQ(); ++i) {
+        const double a = ws.q1(i), b = ws.q2(i);
+        ws.qe(i) = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
+        ws.dq(i) = (b - a) / dt;
+    }
+}
+
+// Lagrangian + forces at the midpoint.  order 1: residual terms.  order 2: Jacobian terms too.
+template <class Sys, class Ws>
+TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
+    set_point(sys, ws, 0, dt);
+    pass1(sys, ws, true, sys.pairs_on());
+    pass2(sys, ws, order);
+    add_potentials(sys, ws, order);
+    forces_eval(sys, ws, order);
+}
+
+// ---------------------------------------------------------------------------------------------
+// MidpointVI_solve_DEL (midpointvi.c:691-747).  Inputs in ws: q1, p1, u1, q2 (dyn part = Newton
+// start, kin part = k2), lam (start).  Outputs in ws: q2, lam, p2.  Returns the iteration count
+// (>= 0) or ST_NOT_CONVERGED / ST_SINGULAR.
+// ---------------------------------------------------------------------------------------------
+template <class Sys, class Ws>
+TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol, int max_it) {
+    const int nd = sys.ND(), nc = sys.NC(), nr = nd + nc;
+    const double dt = t2 - t1;
+    int iterations = 0;
+    if (nc > 0) {
+        set_point(sys, ws, 1, dt);
+        pass1(sys, ws, false, true);
+        constraints_eval(sys, ws, 2, 1);  // Dh1 = Dh(q1)
+    }
+    for (;;) {
+        // ---- calc_f (midpointvi.c:533-565)
+        eval_mid(sys, ws, dt, 1);
+        TREPB_UNROLL
+        for (int j = 0; j < nd; ++j) {
+            double f = ws.p1(j) + (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
+            TREPB_UNROLL for (int c = 0; c < nc; ++c) f -= ws.Dh1(c, j) * ws.lam(c);
+            ws.fr(j) = f;
+        }
+        if (nc > 0) {
+            set_point(sys, ws, 2, dt);
+            pass1(sys, ws, false, true);
+            constraints_eval(sys, ws, 1, 2);
+            TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
+        }
+        // ---- DEL_solved (midpointvi.c:672-689)
+        double nrm = 0.0;
+        TREPB_UNROLL for (int j = 0; j < nd; ++j) nrm += ws.fr(j) * ws.fr(j);
+        bool solved = !(sqrt(nrm) > tol);
+        TREPB_UNROLL for (int c = 0; c < nc; ++c)
+            if (fabs(ws.fr(nd + c)) > sys.con_d(c, 1)) solved = false;
+        if (solved) break;
+        if (iterations > max_it) return ST_NOT_CONVERGED;
+
+        // ---- Jacobian (midpointvi.c:577-670), same accumulation order as the reference
+        eval_mid(sys, ws, dt, 2);
+        TREPB_UNROLL for (int k = 0; k < nd; ++k)
+            TREPB_UNROLL for (int i = 0; i < nd; ++i)
+                ws.Df(k, i) = 0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i);
+        TREPB_UNROLL
+        for (int k = 0; k < nd; ++k) {
+            ws.Df(k, k) += 0.25 * dt * ws.Lqq(k, k);
+            ws.Df(k, k) -= 1.0 / dt * ws.Lvv(k, k);
+            TREPB_UNROLL for (int i = 0; i < nd; ++i) {
+                const double val = 0.5 * ws.Lvq(i, k);
+                ws.Df(k, i) += val;
+                ws.Df(i, k) -= val;
+            }
+            TREPB_UNROLL for (int i = 0; i < k; ++i) {
+                double val = 0.25 * dt * ws.Lqq(k, i);
+                ws.Df(k, i) += val;
+                ws.Df(i, k) += val;
+                val = 1.0 / dt * ws.Lvv(k, i);
+                ws.Df(k, i) -= val;
+                ws.Df(i, k) -= val;
+            }
+        }
+        if (nc > 0) {
+            set_point(sys, ws, 2, dt);
+            pass1(sys, ws, false, true);
+            constraints_eval(sys, ws, 2, 2);  // Dh2 = Dh(q2)
+            TREPB_UNROLL for (int i = 0; i < nd; ++i)
+                TREPB_UNROLL for (int c = 0; c < nc; ++c) {
+                    ws.Df(i, nd + c) = -ws.Dh1(c, i);
+                    ws.Df(nd + c, i) = ws.Dh2(c, i);
+                }
+            TREPB_UNROLL for (int a = 0; a < nc; ++a)
+                TREPB_UNROLL for (int b = 0; b < nc; ++b) ws.Df(nd + a, nd + b) = 0.0;
+        }
+        if (nr == 1) {
+            // 1x1: the reference's LU reduces to a scaled-pivot test and one division
+            const double a = ws.Df(0, 0);
+            if (!(fabs(a) > 0.0)) return ST_SINGULAR;
+            ws.fr(0) = ws.fr(0) / a;
+        } else {
+            if (!lu_decomp(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+            lu_solve(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws});
+        }
+        TREPB_UNROLL for (int k = 0; k < nd; ++k) ws.q2(k) -= ws.fr(k);
+        TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.lam(c) -= ws.fr(nd + c);
+        iterations++;
+    }
+    // p2 = D2L2 at the midpoint of the converged (q1, q2): the order-1 tables of the last
+    // residual evaluation are exactly that point (midpointvi.c:742-743, 491-504).
+    TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
+    return iterations;
+}
+
+// calc_p2 alone (midpointvi.c:2702-2708) for initialize_from_configs
+template <class Sys, class Ws>
+TREPB_HD void calc_p2(const Sys& sys, Ws& ws, double t1, double t2) {
+    const double dt = t2 - t1;
+    eval_mid(sys, ws, dt, 1);
+    TREPB_UNROLL for (int j = 0; j < sys.ND(); ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
+}
+
+// ---------------------------------------------------------------------------------------------
+// First derivatives (midpointvi.c:749-1120).  Requires a solved step in ws (q1,q2,lam,u1).
+// Output arrays use the reference's raw storage layout [wrt][out] (midpointvi.py:59-70);
+// any pointer may be null.  A / B follow DSystem.fdx / fdu (dsystem.py:284-317), row-major.
+// ---------------------------------------------------------------------------------------------
+struct Deriv1Out {
+    double *q2_dq1, *q2_dp1, *q2_du1, *q2_dk2;
+    double *p2_dq1, *p2_dp1, *p2_du1, *p2_dk2;
+    double *l1_dq1, *l1_dp1, *l1_du1, *l1_dk2;
+    double *A, *B;
+    long es;  // element stride of every output array (1 = contiguous per instance)
+};
+
+template <class Sys, class Ws>
+TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Out& o) {
+    const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nc = sys.NC(), nu = sys.NU();
+    const double dt = t2 - t1;
+    const int nX = 2 * nq, nU = nu + nk;
+    // ---- constraint derivatives at q1 and q2
+    if (nc > 0) {
+        set_point(sys, ws, 1, dt);
+        pass1(sys, ws, false, true);
+        constraints_eval(sys, ws, 2 | 4, 1);  // Dh1, DDhl = sum_c lam_c DDh_c(q1)
+        set_point(sys, ws, 2, dt);
+        pass1(sys, ws, false, true);
+        constraints_eval(sys, ws, 2, 2);      // Dh2
+    }
+    // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861), same accumulation order
+    eval_mid(sys, ws, dt, 2);
+    TREPB_UNROLL for (int i1 = 0; i1 < nq; ++i1)
+        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+            const double v1 = 0.5 * dt * ws.Fq(i2, i1), v2 = ws.Fv(i2, i1);
+            ws.T11(i1, i2) = v1 - v2;
+            ws.T21(i1, i2) = v1 + v2;
+            ws.T12(i1, i2) = 0.0;
+            ws.T22(i1, i2) = 0.0;
+        }
+    TREPB_UNROLL
+    for (int i1 = 0; i1 < nd; ++i1) {
+        double v1 = 0.25 * dt * ws.Lqq(i1, i1), v2 = 1.0 / dt * ws.Lvv(i1, i1);
+        ws.T11(i1, i1) += v1 + v2;
+        ws.T21(i1, i1) += v1 - v2;
+        ws.T12(i1, i1) += v1 - v2;
+        ws.T22(i1, i1) += v1 + v2;
+        TREPB_UNROLL for (int i2 = 0; i2 < nq; ++i2) {
+            v1 = 0.5 * ws.Lvq(i1, i2);
+            ws.T11(i2, i1) -= v1;
+            ws.T21(i2, i1) -= v1;
+            ws.T12(i2, i1) += v1;
+            ws.T22(i2, i1) += v1;
+            if (i2 < nd) {
+                ws.T11(i1, i2) -= v1;
+                ws.T21(i1, i2) += v1;
+                ws.T12(i1, i2) -= v1;
+                ws.T22(i1, i2) += v1;
+            }
+        }
+        TREPB_UNROLL for (int i2 = 0; i2 < i1; ++i2) {
+            v1 = 0.25 * dt * ws.Lqq(i1, i2);
+            v2 = 1.0 / dt * ws.Lvv(i1, i2);
+            ws.T11(i2, i1) += v1 + v2;
+            ws.T21(i2, i1) += v1 - v2;
+            ws.T12(i2, i1) += v1 - v2;
+            ws.T22(i2, i1) += v1 + v2;
+            ws.T11(i1, i2) += v1 + v2;   // i2 < i1 < nd always holds here
+            ws.T21(i1, i2) += v1 - v2;
+            ws.T12(i1, i2) += v1 - v2;
+            ws.T22(i1, i2) += v1 + v2;
+        }
+    }
+    TREPB_UNROLL
+    for (int i1 = nd; i1 < nq; ++i1) {
+        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+            const double v1 = 0.5 * ws.Lvq(i1, i2);
+            ws.T11(i1, i2) -= v1;
+            ws.T21(i1, i2) += v1;
+            ws.T12(i1, i2) -= v1;
+            ws.T22(i1, i2) += v1;
+        }
+        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+            const double v1 = 0.25 * dt * ws.Lqq(i1, i2), v2 = 1.0 / dt * ws.Lvv(i1, i2);
+            ws.T11(i1, i2) += v1 + v2;
+            ws.T21(i1, i2) += v1 - v2;
+            ws.T12(i1, i2) += v1 - v2;
+            ws.T22(i1, i2) += v1 + v2;
+        }
+    }
+    TREPB_UNROLL for (int u = 0; u < nu; ++u)
+        TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.T3(u, j) = dt * ws.Fu(j, u);
+
+    // ---- calc_M2 (midpointvi.c:891-908)
+    TREPB_UNROLL for (int a = 0; a < nd; ++a)
+        TREPB_UNROLL for (int b = 0; b < nd; ++b) ws.M2(a, b) = ws.T21(b, a);
+    if (!lu_decomp(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+    // ---- calc_proj_inv (midpointvi.c:910-927): proj = -Dh2_d M2^-1 Dh1^T
+    if (nc > 0) {
+        TREPB_UNROLL for (int i = 0; i < nd; ++i)
+            TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.Tdc(i, c) = ws.Dh1(c, i);
+        for (int c = 0; c < nc; ++c)
+            lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTdcCol<Ws>{&ws, c}, AccLux<Ws>{&ws});
+        for (int a = 0; a < nc; ++a)
+            for (int b = 0; b < nc; ++b) {
+                double s = 0.0;
+                for (int k = 0; k < nd; ++k) s += ws.Dh2(a, k) * ws.Tdc(k, b);
+                ws.PJ(a, b) = -s;
+            }
+        if (!lu_decomp(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+    }
+
+    // ---- calc_deriv1 (midpointvi.c:929-1098): one right-hand side per wrt-variable
+    // kind 0: q1_i   1: p1_i   2: u1_i   3: k2_i
+    const long es = o.es;
+    for (int kindv = 0; kindv < 4; ++kindv) {
+        const int count = kindv == 0 ? nq : (kindv == 1 ? nd : (kindv == 2 ? nu : nk));
+        for (int i = 0; i < count; ++i) {
+            // explicit part c
+            for (int j = 0; j < nd; ++j) {
+                double c;
+                if (kindv == 0) {
+                    c = -ws.T11(i, j);
+                    if (nc > 0) c += ws.DDhl(i, j);
+                } else if (kindv == 1) {
+                    c = (j == i) ? -1.0 : 0.0;
+                } else if (kindv == 2) {
+                    c = -ws.T3(i, j);
+                } else {
+                    c = -ws.T21(nd + i, j);
+                }
+                ws.tnd(j) = c;
+                ws.col(j) = c;
+            }
+            if (nc > 0) {
+                lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
+                for (int c = 0; c < nc; ++c) {
+                    double s = 0.0;
+                    for (int j = 0; j < nd; ++j) s += ws.Dh2(c, j) * ws.tnd(j);
+                    if (kindv == 3) s += ws.Dh2(c, nd + i);
+                    ws.tnc(c) = s;
+                }
+                lu_solve(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+                for (int j = 0; j < nd; ++j) {
+                    double s = ws.col(j);
+                    for (int c = 0; c < nc; ++c) s += ws.Dh1(c, j) * ws.tnc(c);
+                    ws.col(j) = s;
+                }
+            }
+            lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
+            // p2 derivative row
+            double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
+            double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+            double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+            for (int j = 0; j < nd; ++j) {
+                double pv = kindv == 0 ? ws.T12(i, j) : (kindv == 3 ? ws.T22(nd + i, j) : 0.0);
+                for (int k = 0; k < nd; ++k) pv += ws.T22(k, j) * ws.col(k);
+                const double qv = ws.col(j);
+                if (q2o) q2o[(long)(i * nd + j) * es] = qv;
+                if (p2o) p2o[(long)(i * nd + j) * es] = pv;
+                // A / B blocks
+                if (kindv == 0) {
+                    if (o.A) { o.A[(long)(j * nX + i) * es] = qv; o.A[(long)((nq + j) * nX + i) * es] = pv; }
+                } else if (kindv == 1) {
+                    if (o.A) { o.A[(long)(j * nX + nq + i) * es] = qv; o.A[(long)((nq + j) * nX + nq + i) * es] = pv; }
+                } else if (kindv == 2) {
+                    if (o.B) { o.B[(long)(j * nU + i) * es] = qv; o.B[(long)((nq + j) * nU + i) * es] = pv; }
+                } else {
+                    if (o.B) { o.B[(long)(j * nU + nu + i) * es] = qv; o.B[(long)((nq + j) * nU + nu + i) * es] = pv; }
+                }
+            }
+            if (l1o) for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c);
+        }
+    }
+    // constant blocks of A and B
+    if (o.A) {
+        for (int r = 0; r < nX; ++r)
+            for (int c = 0; c < nX; ++c) {
+                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
+                if (dyn_row && c < nq + nd) continue;  // written above
+                double v = 0.0;
+                if (r >= nq + nd && c >= nd && c < nq && (r - nq - nd) == (c - nd)) v = -1.0 / dt;
+                o.A[(long)(r * nX + c) * es] = v;
+            }
+    }
+    if (o.B) {
+        for (int r = 0; r < nX; ++r)
+            for (int c = 0; c < nU; ++c) {
+                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
+                if (dyn_row) continue;
+                double v = 0.0;
+                if (r >= nd && r < nq && c >= nu && (r - nd) == (c - nu)) v = 1.0;
+                if (r >= nq + nd && c >= nu && (r - nq - nd) == (c - nu)) v = 1.0 / dt;
+                o.B[(long)(r * nU + c) * es] = v;
+            }
+    }
+    return ST_OK;
+}
+
+}  // namespace trepb
