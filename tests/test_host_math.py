@@ -1,0 +1,65 @@
+"""CPU check of the shared host/device MidpointVI math against the reference's golden vectors.
+
+The same header (trep_b200/csrc/trepb_math.cuh) is what the CUDA kernels instantiate, so these
+tests pin the algebra on a machine without a GPU; the `-m gpu` tests pin the kernels proper."""
+import numpy as np
+import pytest
+
+import golden_util as G
+import hostmath as H
+
+
+@pytest.mark.parametrize("name", G.ALL)
+def test_cases_step_and_deriv1(name):
+    g = G.golden(name)
+    d = G.desc(name)
+    n = g["case_q1"].shape[0]
+    flips = 0
+    for c in range(n):
+        out = H.linearize(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c],
+                          g["case_p1"][c], g["case_u1"][c], g["case_k2"][c],
+                          q2_guess=g["case_q2_guess"][c], lam_guess=g["case_lambda_guess"][c])
+        assert out["rc"] == 0
+        flips += int(out["iters"] != int(g["case_iters"][c]))
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+        for k in G.RAW:
+            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+    assert flips == 0, "Newton iteration counts differ from the reference in %d cases" % flips
+
+
+@pytest.mark.parametrize("name", G.SMALL)
+def test_rollout(name):
+    g = G.golden(name)
+    if "roll_q" not in g:
+        pytest.skip("no rollout recorded")
+    d = G.desc(name)
+    dt, nsteps, sample = float(g["roll_dt"]), int(g["roll_nsteps"]), int(g["roll_sample"])
+    p0 = H.calc_p2(d, dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0, g["roll_p_init"], name + " p_init")
+    if d.nu:
+        t = dt * (1 + np.arange(nsteps))
+        u = np.stack([1.5 * np.sin(2.0 * t)] + [0.2 * np.cos(t)] * (d.nu - 1), axis=1)
+    else:
+        u = None
+    rc, q2, p2, lam, iters = H.step(d, nsteps, dt, dt, g["roll_q1"], p0, u1=u)
+    assert rc == 0
+    # chaotic systems amplify rounding differences along a rollout; the bound is loose on purpose,
+    # single-step parity is pinned by test_cases_step_and_deriv1
+    G.assert_close(q2, g["roll_q"][-1], name + " final q", rtol=1e-6)
+    G.assert_close(p2, g["roll_p"][-1], name + " final p", rtol=1e-6)
+    assert abs(iters - int(g["roll_iters"].sum())) <= max(2, nsteps // 100)
+
+
+def test_puppet_rollout():
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
+    p0 = H.calc_p2(d, dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0, g["roll_p"][0], "puppet p_init")
+    rc, q2, p2, lam, iters = H.step(d, nsteps, dt, dt, g["roll_q1"], p0, k2=g["roll_k2"])
+    assert rc == 0
+    G.assert_close(q2, g["roll_q"][-1], "puppet final q", rtol=1e-8)
+    G.assert_close(p2, g["roll_p"][-1], "puppet final p", rtol=1e-8)
+    G.assert_close(lam, g["roll_lambda"][-1], "puppet final lambda", rtol=1e-8)
+    assert iters == int(g["roll_iters"].sum())
