@@ -51,7 +51,7 @@ extern "C" {
 #define TREPB_OK 0
 #define TREPB_ERR_INVALID 1   /* bad description / arguments */
 #define TREPB_ERR_CUDA 2      /* CUDA runtime / no device */
-#define TREPB_ERR_COMPILE 3   /* NVRTC specialisation failed */
+#define TREPB_ERR_COMPILE 3   /* reserved */
 #define TREPB_ERR_UNSUPPORTED 4
 
 /* frame transform kinds (trep/_trep/trep.h:168-273) */
@@ -100,17 +100,28 @@ typedef struct trepb_system trepb_system; /* opaque */
 int  trepb_abi_version(void);
 const char* trepb_last_error(void);
 
-/* Validate + flatten + upload tables to `device`; for small unconstrained systems also JIT a
- * specialised kernel (NVRTC, cached on disk next to the library). */
+/* Validate + flatten + upload tables to `device`.  If the description's structural hash matches
+ * one of the systems specialised ahead of time (generated constexpr system, fully unrolled,
+ * register-resident; see trepb_codegen) that kernel set is used, otherwise the table-driven
+ * general kernels. */
 int  trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out);
 void trepb_system_destroy(trepb_system* sys);
 int  trepb_system_dims(const trepb_system* sys, int32_t* nq, int32_t* nd, int32_t* nk,
                        int32_t* nu, int32_t* nc);
 /* 1 if a specialised (compile-time frame tree) kernel is in use, 0 if table-driven. */
 int  trepb_system_is_specialized(const trepb_system* sys);
-/* Emit the generated constexpr-system header text for this description (for inspection /
- * ahead-of-time builds).  Returns required size incl. NUL; writes at most `cap` bytes. */
-int  trepb_codegen(const trepb_sysdesc* desc, char* buf, int cap);
+const char* trepb_system_kernel_name(const trepb_system* sys);
+/* Launch facts of kernel `which` (0 step, 1 calc_p2, 2 linearize) for this system. */
+int  trepb_kernel_info(trepb_system* sys, int which, int32_t* regs, int32_t* local_bytes,
+                       int32_t* blocks_per_sm, int32_t* block, int32_t* smem_bytes);
+/* Host-only (no device needed): check a description; emit the generated constexpr-system type
+ * `struct_name` for it (returns required size incl. NUL, writes at most `cap` bytes; -1 on an
+ * invalid description); structural hash used to match specialised kernels. */
+int  trepb_validate(const trepb_sysdesc* desc);
+int  trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap);
+uint64_t trepb_desc_hash(const trepb_sysdesc* desc);
+int  trepb_num_specialized(void);
+const char* trepb_specialized_name(int i);
 
 /* Per-batch arguments of a step.  Scalars apply to every instance. */
 typedef struct trepb_step_args {
@@ -177,6 +188,9 @@ int trepb_linearize_batch_dev(trepb_system* sys, const trepb_lin_args* args, voi
 int trepb_device_count(int* n);
 int trepb_malloc(int device, int64_t bytes, void** ptr);
 int trepb_free(int device, void* ptr);
+int trepb_host_alloc(int64_t bytes, void** ptr);   /* pinned host memory */
+int trepb_host_free(void* ptr);
+int trepb_memset(int device, void* dst, int value, int64_t bytes);
 int trepb_memcpy_h2d(int device, void* dst, const void* src, int64_t bytes);
 int trepb_memcpy_d2h(int device, void* dst, const void* src, int64_t bytes);
 int trepb_synchronize(int device);

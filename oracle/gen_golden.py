@@ -32,13 +32,12 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, HERE)
 
-import build_ref  # noqa: E402
+import ref_systems as R  # noqa: E402
 
-build_ref.build("/root/reference")
-trep = build_ref.import_ref()
-from trep import tx, ty, tz, rx, ry, rz  # noqa: E402
-from trep import discopt  # noqa: E402
-import trep.puppets  # noqa: E402
+trep = R.trep
+discopt = R.discopt
+REF_BUILDERS = R.REF_BUILDERS
+ref_tase_pendulum, ref_puppet = R.ref_tase_pendulum, R.ref_puppet
 
 from trep_b200 import model as M  # noqa: E402
 from trep_b200 import systems as S  # noqa: E402
@@ -51,79 +50,6 @@ D1_NAMES = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1"
 D2_SUFFIX = ["dq1dq1", "dq1dp1", "dq1du1", "dq1dk2", "dp1dp1", "dp1du1", "dp1dk2", "du1du1",
              "du1dk2", "dk2dk2"]
 D2_NAMES = [p + "_" + s for p in ("q2", "p2", "l1") for s in D2_SUFFIX]
-
-
-# ---- reference-side builders (same scripts as the examples cited in trep_b200/systems.py) ----
-def ref_pendulum(links):
-    system = trep.System()
-    trep.potentials.Gravity(system, name="Gravity")
-    frame = system.world_frame
-    for link in range(links):
-        frame = trep.Frame(frame, trep.RX, "link-%d" % link, "link-%d" % link)
-        frame = trep.Frame(frame, trep.TZ, -1)
-        frame.set_mass(1.0)
-    system.get_config("link-0").q = math.pi / 4.0
-    return system
-
-
-def ref_damped_pendulum():
-    system = trep.System()
-    system.import_frames([ty(3), rx("theta"), [tz(-3, mass=1)]])
-    trep.potentials.Gravity(system, (0, 0, -9.8))
-    trep.forces.Damping(system, 1.2)
-    return system
-
-
-def ref_pend_on_cart(torque):
-    system = trep.System()
-    system.import_frames([
-        tx('x', name='Cart', mass=10.0), [
-            rz('theta', name="PendulumBase"), [
-                ty(-1.0, name="Pendulum", mass=1.0)]]])
-    trep.potentials.Gravity(system, (0, -9.8, 0))
-    trep.forces.Damping(system, 0.01)
-    trep.forces.ConfigForce(system, 'x', 'x-force')
-    if torque:
-        trep.forces.ConfigForce(system, 'theta', 'theta-force')
-    return system
-
-
-def ref_dual_pendulums():
-    system = trep.System()
-    system.import_frames([
-        rx('theta1'), [tz(2, mass=1, name='pend1')],
-        ty(1), [rx('theta2'), [tz(2, mass=1, name='pend2')]]])
-    trep.potentials.LinearSpring(system, 'pend1', 'pend2', k=20, x0=1)
-    trep.forces.LinearDamper(system, 'pend1', 'pend2', c=1)
-    trep.potentials.Gravity(system, name="Gravity")
-    system.q = [3, -3]
-    return system
-
-
-def ref_tase_pendulum():
-    system = trep.System()
-    system.import_frames([trep.rz("theta_1", name="PendAngle"), [trep.ty(-1.0, name="PendMass", mass=1.0)]])
-    trep.potentials.Gravity(system, (0, -9.8, 0))
-    trep.forces.ConfigForce(system, "theta_1", "tau")
-    return system
-
-
-def ref_puppet():
-    puppet = trep.puppets.Puppet(joint_forces=False, string_forces=False, string_constraints=True)
-    puppet.q = {
-        'torso_rx': -0.05, 'torso_tz': 0.0, 'lelbow_rx': 1.57, 'relbow_rx': 1.57,
-        'lhip_rx': math.pi / 2 - 0.6, 'rhip_rx': math.pi / 2 - 0.6,
-        'lknee_rx': -math.pi / 2 + 0.6, 'rknee_rx': -math.pi / 2 + 0.6}
-    puppet.project_string_controls()
-    return puppet
-
-
-REF_BUILDERS = {
-    "pendulum1": lambda: ref_pendulum(1), "pendulum5": lambda: ref_pendulum(5),
-    "damped_pendulum": ref_damped_pendulum, "pend_on_cart1": lambda: ref_pend_on_cart(False),
-    "pend_on_cart2": lambda: ref_pend_on_cart(True), "dual_pendulums": ref_dual_pendulums,
-    "tase_pendulum": ref_tase_pendulum, "puppet": ref_puppet,
-}
 
 
 # ---- recording ---------------------------------------------------------------------------------

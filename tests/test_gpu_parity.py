@@ -1,0 +1,225 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (libtrepb.so), against
+  (a) the committed golden vectors recorded from the reference itself, and
+  (b) the reference itself (oracle/_ref, unmodified numerics) run on seeded random batches.
+
+Bar (BASELINE.json north_star): 1e-10 relative in fp64, identical Newton iteration counts.
+Iteration counts can legitimately flip by one when an iterate lands within rounding distance of
+the 1e-10 convergence threshold ("iteration-count parity"); the tests
+therefore require identical counts on the golden cases and bound the flip fraction on the
+random batches, checking that flipped instances still agree to 1e-10.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from trep_b200 import lib as L
+    assert L.device_count() > 0, "GPU tests need a CUDA device"
+    return L
+
+
+@pytest.fixture(scope="module")
+def ref():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_systems as R
+    return R
+
+
+def _systems(lib, name):
+    """(label, System) for the specialised kernel (if one exists) and the general kernel."""
+    d = G.desc(name)
+    out = []
+    s = lib.System(d)
+    if s.specialized:
+        out.append(("spec", s))
+        out.append(("general", lib.System(d, specialize=False)))
+    else:
+        out.append(("general", s))
+    return out
+
+
+@pytest.mark.parametrize("name", G.ALL)
+def test_golden_cases(lib, name):
+    g = G.golden(name)
+    for label, s in _systems(lib, name):
+        if name in G.SMALL and name != "pendulum5":
+            assert label != "spec" or s.specialized
+        out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                          t2=g["case_t2"], q2_guess=g["case_q2_guess"],
+                          lambda_guess=g["case_lambda_guess"], want_raw=True)
+        assert np.all(out["status"] == 0), (label, out["status"])
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k], g["case_" + k], "%s[%s] %s" % (name, label, k))
+        for k in G.RAW:
+            G.assert_close(out[k], g["case_" + k], "%s[%s] %s" % (name, label, k))
+        assert np.array_equal(out["iters"], g["case_iters"]), (label, out["iters"], g["case_iters"])
+
+
+@pytest.mark.parametrize("name", G.SMALL)
+def test_golden_rollout(lib, name):
+    g = G.golden(name)
+    if "roll_q" not in g:
+        pytest.skip("no rollout recorded")
+    dt, nsteps, sample = float(g["roll_dt"]), int(g["roll_nsteps"]), int(g["roll_sample"])
+    for label, s in _systems(lib, name):
+        p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+        G.assert_close(p0[0], g["roll_p_init"], name + " p_init")
+        u = None
+        if s.nu:
+            t = dt * (1 + np.arange(nsteps))
+            u = np.stack([1.5 * np.sin(2.0 * t)] + [0.2 * np.cos(t)] * (s.nu - 1), axis=1)[None]
+        out = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, u1=u, sample_every=sample)
+        assert out["status"][0] == 0
+        ns = nsteps // sample
+        # early samples are tight; chaotic growth of rounding differences loosens later ones
+        G.assert_close(out["traj_q"][0, 0], g["roll_q"][1], "%s[%s] first sample q" % (name, label), rtol=1e-9)
+        G.assert_close(out["traj_q"][0, :ns], g["roll_q"][1:1 + ns], "%s[%s] traj q" % (name, label), rtol=1e-6)
+        G.assert_close(out["traj_p"][0, :ns], g["roll_p"][1:1 + ns], "%s[%s] traj p" % (name, label), rtol=1e-6)
+        assert abs(int(out["iters"][0]) - int(g["roll_iters"].sum())) <= max(2, nsteps // 100)
+
+
+def test_puppet_rollout(lib):
+    g = G.golden("puppet")
+    s = lib.System(G.desc("puppet"))
+    dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
+    p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0[0], g["roll_p"][0], "puppet p_init")
+    out = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, k2=g["roll_k2"][None], sample_every=1)
+    assert out["status"][0] == 0
+    G.assert_close(out["traj_q"][0], g["roll_q"][1:], "puppet traj q", rtol=1e-8)
+    G.assert_close(out["traj_p"][0], g["roll_p"][1:], "puppet traj p", rtol=1e-8)
+    G.assert_close(out["lambda1"][0], g["roll_lambda"][-1], "puppet lambda", rtol=1e-8)
+    assert int(out["iters"][0]) == int(g["roll_iters"].sum())
+
+
+RANDOM = {
+    #  name            B    q-range  p-scale u-scale
+    "damped_pendulum": (512, np.pi, 5.0, 0.0),
+    "pendulum1": (256, np.pi, 2.0, 0.0),
+    "pendulum5": (64, np.pi, 2.0, 0.0),
+    "pend_on_cart1": (512, np.pi, 3.0, 2.0),
+    "pend_on_cart2": (256, np.pi, 3.0, 2.0),
+    "dual_pendulums": (512, np.pi, 3.0, 0.0),
+}
+
+
+@pytest.mark.parametrize("name", sorted(RANDOM))
+def test_random_batch_vs_reference(lib, ref, name):
+    """Seeded random batch, ragged size (not a multiple of the warp or CTA size)."""
+    B, qr, ps, us = RANDOM[name]
+    B += 3
+    rng = np.random.default_rng(1234)
+    system, mvi = ref.make_mvi(name)
+    nq, nd, nu = mvi.nq, mvi.nd, mvi.nu
+    q1 = rng.uniform(-qr, qr, (B, nq))
+    p1 = rng.normal(0, ps, (B, nd))
+    u1 = rng.uniform(-us, us, (B, nu))
+    k2 = np.zeros((B, 0))
+    t1 = rng.uniform(0, 5, B)
+    t2 = t1 + 0.01
+    want = ref.run_cases(mvi, t1, t2, q1, p1, u1, k2)
+    for label, s in _systems(lib, name):
+        out = s.linearize(q1, p1, u1, k2, t1=t1, t2=t2)
+        assert np.array_equal(out["status"], want["status"])
+        for k in ("q2", "p2", "A", "B"):
+            G.assert_close(out[k], want[k], "%s[%s] %s" % (name, label, k))
+        flips = int(np.sum(out["iters"] != want["iters"]))
+        assert flips <= max(1, B // 100), "%s[%s]: %d/%d iteration counts differ" % (name, label, flips, B)
+
+
+def test_puppet_random_vs_reference(lib, ref):
+    """Marionette: perturbed points of the golden trajectory against the reference itself."""
+    g = G.golden("puppet")
+    rng = np.random.default_rng(7)
+    system, mvi = ref.make_mvi("puppet")
+    nd = mvi.nd
+    B = 12
+    idx = rng.integers(1, 58, B)
+    q1 = g["roll_q"][idx].copy()
+    p1 = g["roll_p"][idx].copy()
+    q1[:, :nd] += rng.normal(0, 0.02, (B, nd))
+    p1 += rng.normal(0, 0.02, (B, nd))
+    k2 = g["roll_k2"][idx]          # kinematic configs at the end of step idx -> idx+1
+    lam = g["roll_lambda"][idx - 1]
+    t1 = 0.01 * (idx + 1)
+    t2 = t1 + 0.01
+    want = ref.run_cases(mvi, t1, t2, q1, p1, np.zeros((B, 0)), k2, lambda_guess=lam)
+    s = lib.System(G.desc("puppet"))
+    out = s.linearize(q1, p1, None, k2, t1=t1, t2=t2, lambda_guess=lam)
+    assert np.array_equal(out["status"], want["status"])
+    ok = want["status"] == 0
+    for k in ("q2", "p2", "lambda1", "A", "B"):
+        G.assert_close(out[k][ok], want[k][ok], "puppet " + k)
+    assert np.array_equal(out["iters"][ok], want["iters"][ok])
+
+
+def test_device_pointer_entry_points_match_host(lib):
+    """*_dev entry points (inputs resident in HBM) give the same bits as the host entry points."""
+    g = G.golden("pend_on_cart1")
+    s = lib.System(G.desc("pend_on_cart1"))
+    B = 1000
+    rng = np.random.default_rng(3)
+    q1 = rng.uniform(-3, 3, (B, 2)); p1 = rng.normal(0, 3, (B, 2)); u1 = rng.uniform(-2, 2, (B, 1))
+    host = s.linearize(q1, p1, u1, None, t1=0.0, dt=0.01)
+    db = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(a)
+    dq, dp, du = db(q1), db(p1), db(u1)
+    dA = lib.DeviceBuffer(0, (B, 4, 4)); dB = lib.DeviceBuffer(0, (B, 4, 1))
+    dq2 = lib.DeviceBuffer(0, (B, 2)); dp2 = lib.DeviceBuffer(0, (B, 2))
+    dit = lib.DeviceBuffer(0, (B,), np.int32); dst = lib.DeviceBuffer(0, (B,), np.int32)
+    s.linearize_raw(True, B, dq, dp, du, None, dst, t1_scalar=0.0, dt_scalar=0.01, q2=dq2, p2=dp2,
+                    iters=dit, A=dA, B=dB)
+    lib.synchronize(0)
+    assert s.last_kernel_ms() > 0
+    assert np.array_equal(dA.download(), host["A"])
+    assert np.array_equal(dB.download(), host["B"])
+    assert np.array_equal(dq2.download(), host["q2"])
+    assert np.array_equal(dit.download(), host["iters"])
+    assert np.all(dst.download() == 0)
+
+
+def test_status_codes_not_converged_and_empty_batch(lib):
+    s = lib.System(G.desc("damped_pendulum"))
+    # max_iterations = 0 with a start far from the root: the reference raises ConvergenceError
+    # after exceeding max_iterations (midpointvi.c:715-718); here: status -1, batch continues
+    q1 = np.array([[0.5], [0.0]]); p1 = np.array([[40.0], [0.0]])
+    out = s.step(q1, p1, 0.0, 0.01, max_iterations=0)
+    assert out["status"][0] == -1
+    # second instance: q=0,p=0 is an exact fixed point -> converged with 0 iterations
+    assert out["status"][1] == 0 and out["iters"][1] == 0
+    out = s.step(np.zeros((0, 1)), np.zeros((0, 1)), 0.0, 0.01)
+    assert out["q2"].shape == (0, 1)
+
+
+def test_full_size_properties(lib):
+    """BASELINE config 2 at full width (2^20 damped pendulums), size-independent properties:
+    duplicated instances give identical bits wherever they sit in the batch, and a long rollout
+    equals the same rollout split into two launches (restartability)."""
+    s = lib.System(G.desc("damped_pendulum"))
+    B = 1 << 20
+    rng = np.random.default_rng(0)
+    th0 = rng.uniform(-np.pi, np.pi, 1024)
+    th1 = th0 + rng.uniform(-0.02, 0.02, 1024)
+    q0 = np.tile(th0, B // 1024)[:, None]
+    q1 = np.tile(th1, B // 1024)[:, None]
+    p = s.calc_p2(0.01, q0, q1)
+    a = s.step(q1, p, 0.01, 0.01, nsteps=40)
+    assert np.all(a["status"] == 0)
+    qq = a["q2"].reshape(B // 1024, 1024)
+    assert np.all(qq == qq[0]), "same inputs must give the same bits at every batch position"
+    b1 = s.step(q1[:4096], p[:4096], 0.01, 0.01, nsteps=15)
+    b2 = s.step(b1["q2"], b1["p2"], 0.01 + 15 * 0.01, 0.01, nsteps=25)
+    # t0 differs by rounding between one 40-step launch and 15+25 -> compare to 1e-12
+    G.assert_close(b2["q2"], a["q2"][:4096], "split rollout q", rtol=1e-12)
+    G.assert_close(b2["p2"], a["p2"][:4096], "split rollout p", rtol=1e-12)
+    assert np.array_equal(b1["iters"] + b2["iters"], a["iters"][:4096]) or \
+        np.mean(b1["iters"] + b2["iters"] != a["iters"][:4096]) < 1e-3

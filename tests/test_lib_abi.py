@@ -1,0 +1,91 @@
+"""CPU tests of the C-ABI boundary: the library loads, exports every symbol include/trepb.h
+declares, validates descriptions, generates specialised system types, and refuses to compute
+without a CUDA device (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as G
+from trep_b200 import build, desc as D, lib, systems
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "trepb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(trepb_\w+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    syms = header_symbols()
+    assert len(syms) >= 25
+    raw = lib.raw()
+    missing = [s for s in syms if not hasattr(raw, s)]
+    assert not missing, missing
+    assert set(lib.EXPORTS) == set(syms)
+    assert raw.trepb_abi_version() == 1
+
+
+def test_ctypes_struct_layout_matches_header():
+    # field order/size of the argument structs as declared in include/trepb.h (LP64)
+    assert C.sizeof(lib.StepArgs) == 8 + 4 + 4 + 3 * 8 + 11 * 8 + 4 + 4 + 2 * 8
+    assert C.sizeof(lib.LinArgs) == 8 + 4 + 4 + 8 + 2 * 8 + 2 * 8 + 6 * 8 + 5 * 8 + 2 * 8 + 12 * 8
+    assert C.sizeof(D.CSysDesc) == 10 * 4 + 17 * 8
+
+
+@pytest.mark.parametrize("name", G.ALL)
+def test_descriptions_validate_and_hash(name):
+    d = G.desc(name)
+    lib.validate(d)
+    h = lib.desc_hash(d)
+    assert h != 0
+    assert h == lib.desc_hash(D.SystemDesc.from_json(d.to_json())), "hash must survive a JSON round trip"
+
+
+def test_specialised_registry_and_codegen():
+    names = lib.specialized_names()
+    for n in build.AOT_SYSTEMS:
+        assert n in names
+    text, h = build.codegen(G.desc("pend_on_cart1"))
+    assert "struct CtSys" in text and "kND = 2" in text and "kNU = 1" in text
+    assert ("0x%016x" % h) in text
+    assert h == lib.desc_hash(G.desc("pend_on_cart1"))
+    # a parameter change is a different specialisation
+    s = systems.pend_on_cart()
+    s.world_frame.children[0].set_mass(11.0)
+    assert lib.desc_hash(s.describe()) != h
+
+
+def test_invalid_descriptions_are_refused():
+    d = G.desc("damped_pendulum")
+    bad = D.SystemDesc.from_json(d.to_json())
+    bad.pot_kind = np.array([9], np.int32)
+    with pytest.raises(lib.TrepbError) as e:
+        lib.validate(bad)
+    assert "no device implementation" in str(e.value)
+    bad = D.SystemDesc.from_json(d.to_json())
+    bad.frame_parent = np.array([-1, 2, 1, 2], np.int32)
+    with pytest.raises(lib.TrepbError):
+        lib.validate(bad)
+
+
+@pytest.mark.skipif(lib.device_count() > 0, reason="checks the no-GPU behaviour")
+def test_compute_fails_loudly_without_a_device():
+    with pytest.raises(lib.TrepbError) as e:
+        lib.System(G.desc("damped_pendulum"))
+    assert e.value.code == 2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "trep_b200")
+    pat = re.compile(r"^\s*(from|import)\s+.*(oracle|ref_systems|build_ref|hostmath)", re.M)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                assert not pat.search(open(os.path.join(root, f)).read()), f
+            if f.endswith((".cu", ".cuh", ".h", ".cc")):
+                assert "oracle" not in open(os.path.join(root, f)).read(), f

@@ -1,0 +1,522 @@
+// C ABI of libtrepb.so (include/trepb.h): system handles, launch geometry, host<->device staging.
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <mutex>
+#include <string>
+
+#include "../../include/trepb.h"
+#include "trepb_codegen.h"
+#include "trepb_err.h"
+#include "trepb_kernels.cuh"
+#include "trepb_pack.h"
+
+using namespace trepb;
+
+namespace {
+int fail(int code, const std::string& m) { last_error() = m; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    last_error() = std::string(what) + ": " + cudaGetErrorString(e);
+    return TREPB_ERR_CUDA;
+}
+#define CU(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return cuda_fail(e_, #call); } while (0)
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+}  // namespace
+
+namespace trepb {
+SpecRegistry& spec_registry() {
+    static SpecRegistry r = {{nullptr}, 0};
+    return r;
+}
+}  // namespace trepb
+
+struct trepb_system {
+    int device = 0;
+    PackedSys P;
+    RtSys dview;            // RtSys whose pointers are device addresses
+    char* dblob = nullptr;
+    int blob_bytes = 0;
+    const KernelSet* ks = nullptr;
+    int sms = 0;
+    int block = 128;
+    int bps[3] = {1, 1, 1};      // resident CTAs per SM for step / p2 / lin
+    size_t lin_stage_bytes = 0;  // dynamic smem of the staged linearize kernel (0: no staging)
+    int lin_bps_staged = 1;
+    // general path workspace
+    WsStrided wsl;               // layout (base filled per launch)
+    int ws_doubles = 0;
+    DevBuf ws;
+    // staging for the host-pointer entry points
+    DevBuf hb[32];
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    std::mutex mu;       // serialises launches on this handle
+    std::mutex mu_host;  // serialises the host-pointer entry points (they share staging buffers)
+};
+
+extern "C" {
+
+int trepb_abi_version(void) { return TREPB_ABI_VERSION; }
+const char* trepb_last_error(void) { return last_error().c_str(); }
+
+int trepb_device_count(int* n) {
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *n = 0; return cuda_fail(e, "cudaGetDeviceCount"); }
+    *n = c;
+    return TREPB_OK;
+}
+
+int trepb_num_specialized(void) { return spec_registry().n; }
+const char* trepb_specialized_name(int i) {
+    SpecRegistry& r = spec_registry();
+    return (i >= 0 && i < r.n) ? r.sets[i]->name : nullptr;
+}
+
+int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out) {
+    if (!out) return fail(TREPB_ERR_INVALID, "null output handle");
+    *out = nullptr;
+    trepb_system* s = new trepb_system();
+    std::string err;
+    if (!pack_system(desc, &s->P, &err)) { delete s; return fail(TREPB_ERR_INVALID, err); }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        delete s;
+        return fail(TREPB_ERR_CUDA, std::string("no CUDA device (there is no CPU fallback): ") +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= ndev) { delete s; return fail(TREPB_ERR_INVALID, "device index out of range"); }
+    s->device = device;
+#define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = cuda_fail(e_, #call); trepb_system_destroy(s); return rc_; } } while (0)
+    CUS(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUS(cudaGetDeviceProperties(&prop, device));
+    s->sms = prop.multiProcessorCount;
+    s->blob_bytes = (int)((s->P.blob.size() + 15) & ~size_t(15));
+    CUS(cudaMalloc((void**)&s->dblob, s->blob_bytes));
+    CUS(cudaMemset(s->dblob, 0, s->blob_bytes));
+    CUS(cudaMemcpy(s->dblob, s->P.blob.data(), s->P.blob.size(), cudaMemcpyHostToDevice));
+    s->dview = s->P.view(s->dblob);
+    // kernel selection
+    s->ks = general_kernels();
+    if (!(flags & TREPB_FLAG_NO_SPECIALIZE)) {
+        const unsigned long long h = desc_hash(s->P);
+        SpecRegistry& r = spec_registry();
+        for (int i = 0; i < r.n; ++i)
+            if (r.sets[i]->hash == h) { s->ks = r.sets[i]; break; }
+    }
+    const RtSys& ps = s->P.proto;
+    s->ws_doubles = s->wsl.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc);
+    const size_t base_smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
+    if (base_smem > 200 * 1024) { trepb_system_destroy(s); return fail(TREPB_ERR_UNSUPPORTED, "system description exceeds shared memory"); }
+    for (int w = 0; w < 3; ++w) {
+        int b = 0;
+        CUS(s->ks->occupancy(w, s->block, base_smem, &b, nullptr));
+        s->bps[w] = b > 0 ? b : 1;
+    }
+    if (s->ks->specialized) {
+        const int nq = ps.nd + ps.nk, nX = 2 * nq, nU = ps.nu + ps.nk;
+        const size_t st = (size_t)(nX * nX + nX * nU) * sizeof(double) * s->block;
+        if (st <= 160 * 1024) {
+            int b = 0;
+            CUS(s->ks->occupancy(2, s->block, st, &b, nullptr));
+            if (b > 0) { s->lin_stage_bytes = st; s->lin_bps_staged = b; }
+        }
+    }
+    CUS(cudaEventCreate(&s->ev0));
+    CUS(cudaEventCreate(&s->ev1));
+#undef CUS
+    *out = s;
+    return TREPB_OK;
+}
+
+void trepb_system_destroy(trepb_system* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->dblob) cudaFree(s->dblob);
+    s->ws.release();
+    for (auto& b : s->hb) b.release();
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+int trepb_system_dims(const trepb_system* s, int32_t* nq, int32_t* nd, int32_t* nk, int32_t* nu, int32_t* nc) {
+    if (!s) return fail(TREPB_ERR_INVALID, "null system");
+    const RtSys& p = s->P.proto;
+    if (nq) *nq = p.nd + p.nk;
+    if (nd) *nd = p.nd;
+    if (nk) *nk = p.nk;
+    if (nu) *nu = p.nu;
+    if (nc) *nc = p.nc;
+    return TREPB_OK;
+}
+
+int trepb_system_is_specialized(const trepb_system* s) { return s && s->ks->specialized; }
+const char* trepb_system_kernel_name(const trepb_system* s) { return s ? s->ks->name : ""; }
+
+int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_bytes, int32_t* blocks_per_sm,
+                      int32_t* block, int32_t* smem_bytes) {
+    if (!s || which < 0 || which > 2) return fail(TREPB_ERR_INVALID, "bad arguments");
+    CU(cudaSetDevice(s->device));
+    KernelInfo ki;
+    int b = 0;
+    size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
+    if (which == 2 && s->lin_stage_bytes) smem = s->lin_stage_bytes;
+    CU(s->ks->occupancy(which, s->block, smem, &b, &ki));
+    if (regs) *regs = ki.regs;
+    if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
+    if (blocks_per_sm) *blocks_per_sm = b;
+    if (block) *block = s->block;
+    if (smem_bytes) *smem_bytes = (int32_t)smem;
+    return TREPB_OK;
+}
+
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+// grid for `batch` instances at `bps` resident CTAs per SM; for the general path also sizes the
+// workspace slab (one column per launched thread).
+int make_cfg(trepb_system* s, long long batch, int bps, size_t smem, cudaStream_t stream, LaunchCfg* c) {
+    const long long need = (batch + s->block - 1) / s->block;
+    long long grid = need;
+    if (!s->ks->specialized) {
+        long long resident = (long long)s->sms * bps;
+        if (grid > resident) grid = resident;
+        // keep the slab within a quarter of the free memory
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_cta = (size_t)s->ws_doubles * sizeof(double) * s->block;
+        const size_t budget = (free_b + s->ws.cap) / 4;
+        if ((size_t)grid * per_cta > budget) grid = (long long)(budget / per_cta);
+        if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the workspace slab");
+        CU(s->ws.ensure((size_t)grid * per_cta));
+    } else {
+        if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+    }
+    if (grid < 1) grid = 1;
+    c->grid = (int)grid;
+    c->block = s->block;
+    c->smem = smem;
+    c->stream = stream;
+    c->sys = s->ks->specialized ? nullptr : &s->dview;
+    c->dblob = s->dblob;
+    c->blob_bytes = s->blob_bytes;
+    c->ws = s->wsl;
+    c->ws.base = (double*)s->ws.p;
+    c->ws.stride = 0;
+    return TREPB_OK;
+}
+
+struct Timed {
+    trepb_system* s;
+    cudaStream_t st;
+    Timed(trepb_system* s_, cudaStream_t st_) : s(s_), st(st_) { cudaEventRecord(s->ev0, st); }
+    ~Timed() { cudaEventRecord(s->ev1, st); s->timed = true; }
+};
+
+}  // namespace
+
+extern "C" {
+
+int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    const RtSys& ps = s->P.proto;
+    if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
+    if (!a->q1 || !a->p1 || !a->q2 || !a->p2 || !a->status) return fail(TREPB_ERR_INVALID, "q1, p1, q2, p2 and status are required");
+    if (ps.nk > 0 && !a->k2) return fail(TREPB_ERR_INVALID, "k2 is required for a system with kinematic configs");
+    if (!(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    if (a->sample_every < 0) return fail(TREPB_ERR_INVALID, "sample_every must be >= 0");
+    if (a->batch == 0) return TREPB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    StepParams p;
+    p.batch = a->batch; p.nsteps = a->nsteps; p.max_it = a->max_iterations;
+    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance;
+    p.q1 = a->q1; p.p1 = a->p1; p.u1 = ps.nu ? a->u1 : nullptr; p.k2 = a->k2; p.q2g = a->q2_guess;
+    p.lamg = ps.nc ? a->lambda_guess : nullptr;
+    p.q2 = a->q2; p.p2 = a->p2; p.lam = ps.nc ? a->lambda1 : nullptr; p.iters = a->iters; p.status = a->status;
+    p.sample_every = a->sample_every;
+    p.nsamples = a->sample_every > 0 ? a->nsteps / a->sample_every : 0;
+    p.traj_q = a->traj_q; p.traj_p = a->traj_p;
+    LaunchCfg c;
+    int rc = make_cfg(s, a->batch, s->bps[0], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    if (rc) return rc;
+    Timed t(s, c.stream);
+    CU(s->ks->step(c, p));
+    return TREPB_OK;
+}
+
+int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1,
+                            double* pout, void* stream) {
+    if (!s || !q0 || !q1 || !pout) return fail(TREPB_ERR_INVALID, "null argument");
+    if (batch < 0 || !(dt != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or dt");
+    if (batch == 0) return TREPB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    P2Params p;
+    p.batch = batch; p.dt = dt; p.q0 = q0; p.q1 = q1; p.p = pout;
+    LaunchCfg c;
+    int rc = make_cfg(s, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    if (rc) return rc;
+    Timed t(s, c.stream);
+    CU(s->ks->p2(c, p));
+    return TREPB_OK;
+}
+
+int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* stream) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    const RtSys& ps = s->P.proto;
+    if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    if (!a->q1 || !a->p1 || !a->status) return fail(TREPB_ERR_INVALID, "q1, p1 and status are required");
+    if (ps.nk > 0 && !a->k2) return fail(TREPB_ERR_INVALID, "k2 is required for a system with kinematic configs");
+    if (ps.nu > 0 && !a->u1) return fail(TREPB_ERR_INVALID, "u1 is required for a system with inputs");
+    if (!a->t2 && !(a->dt_scalar != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    if (a->batch == 0) return TREPB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    LinParams p;
+    p.batch = a->batch; p.max_it = a->max_iterations; p.tol = a->tolerance;
+    p.t1s = a->t1_scalar; p.dts = a->dt_scalar; p.t1 = a->t1; p.t2 = a->t2;
+    p.q1 = a->q1; p.p1 = a->p1; p.u1 = a->u1; p.k2 = a->k2; p.q2g = a->q2_guess;
+    p.lamg = ps.nc ? a->lambda_guess : nullptr;
+    p.q2 = a->q2; p.p2 = a->p2; p.lam = ps.nc ? a->lambda1 : nullptr; p.iters = a->iters; p.status = a->status;
+    p.A = a->A; p.B = (ps.nu + ps.nk) > 0 ? a->B : nullptr;
+    double* raw[12] = {a->q2_dq1, a->q2_dp1, a->q2_du1, a->q2_dk2, a->p2_dq1, a->p2_dp1, a->p2_du1, a->p2_dk2,
+                       a->l1_dq1, a->l1_dp1, a->l1_du1, a->l1_dk2};
+    for (int i = 0; i < 12; ++i) p.raw[i] = raw[i];
+    const bool stage = s->lin_stage_bytes > 0 && (p.A || p.B);
+    p.stage = stage ? 1 : 0;
+    LaunchCfg c;
+    const size_t smem = s->ks->specialized ? (stage ? s->lin_stage_bytes : 0) : (size_t)s->blob_bytes;
+    int rc = make_cfg(s, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, (cudaStream_t)stream, &c);
+    if (rc) return rc;
+    if (stage) {
+        // persistent-style grid: the staged kernel loops with a warp-uniform bound
+        long long resident = (long long)s->sms * s->lin_bps_staged;
+        if (c.grid > resident) c.grid = (int)resident;
+    }
+    Timed t(s, c.stream);
+    CU(s->ks->lin(c, p));
+    return TREPB_OK;
+}
+
+int trepb_last_kernel_ms(trepb_system* s, float* ms) {
+    if (!s || !ms) return fail(TREPB_ERR_INVALID, "null argument");
+    if (!s->timed) return fail(TREPB_ERR_INVALID, "no kernel has been launched on this system");
+    CU(cudaSetDevice(s->device));
+    CU(cudaEventSynchronize(s->ev1));
+    CU(cudaEventElapsedTime(ms, s->ev0, s->ev1));
+    return TREPB_OK;
+}
+
+// ---- device utilities -------------------------------------------------------------------------
+int trepb_malloc(int device, int64_t bytes, void** ptr) {
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(ptr, (size_t)(bytes > 0 ? bytes : 1)));
+    return TREPB_OK;
+}
+int trepb_free(int device, void* ptr) {
+    CU(cudaSetDevice(device));
+    CU(cudaFree(ptr));
+    return TREPB_OK;
+}
+int trepb_host_alloc(int64_t bytes, void** ptr) {
+    CU(cudaHostAlloc(ptr, (size_t)(bytes > 0 ? bytes : 1), cudaHostAllocDefault));
+    return TREPB_OK;
+}
+int trepb_host_free(void* ptr) {
+    CU(cudaFreeHost(ptr));
+    return TREPB_OK;
+}
+int trepb_memcpy_h2d(int device, void* dst, const void* src, int64_t bytes) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyHostToDevice));
+    return TREPB_OK;
+}
+int trepb_memcpy_d2h(int device, void* dst, const void* src, int64_t bytes) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
+    return TREPB_OK;
+}
+int trepb_memset(int device, void* dst, int value, int64_t bytes) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemset(dst, value, (size_t)bytes));
+    return TREPB_OK;
+}
+int trepb_synchronize(int device) {
+    CU(cudaSetDevice(device));
+    CU(cudaDeviceSynchronize());
+    return TREPB_OK;
+}
+
+// ---- host-pointer entry points: copy in, run, copy out, synchronize ---------------------------
+}  // extern "C"
+
+namespace {
+struct Stager {
+    trepb_system* s;
+    int k = 0;
+    struct Out { void* host; void* dev; size_t bytes; } outs[24];
+    int nout = 0;
+    int err = 0;
+    explicit Stager(trepb_system* s_) : s(s_) {}
+    template <class T>
+    const T* in(const T* host, size_t count) {
+        if (!host || err) return nullptr;
+        DevBuf& b = s->hb[k++];
+        const size_t bytes = count * sizeof(T);
+        cudaError_t e = b.ensure(bytes ? bytes : 8);
+        if (e == cudaSuccess && bytes) e = cudaMemcpyAsync(b.p, host, bytes, cudaMemcpyHostToDevice, 0);
+        if (e != cudaSuccess) { err = cuda_fail(e, "staging host input"); return nullptr; }
+        return (const T*)b.p;
+    }
+    template <class T>
+    T* out(T* host, size_t count) {
+        if (!host || err) return nullptr;
+        DevBuf& b = s->hb[k++];
+        const size_t bytes = count * sizeof(T);
+        cudaError_t e = b.ensure(bytes ? bytes : 8);
+        if (e != cudaSuccess) { err = cuda_fail(e, "staging host output"); return nullptr; }
+        outs[nout++] = {host, b.p, bytes};
+        return (T*)b.p;
+    }
+    int finish() {
+        for (int i = 0; i < nout; ++i)
+            if (outs[i].bytes) CU(cudaMemcpyAsync(outs[i].host, outs[i].dev, outs[i].bytes, cudaMemcpyDeviceToHost, 0));
+        CU(cudaStreamSynchronize(0));
+        return TREPB_OK;
+    }
+};
+}  // namespace
+
+extern "C" {
+
+int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    trepb_step_args d = *a;
+    d.q1 = st.in(a->q1, B * nq); d.p1 = st.in(a->p1, B * nd);
+    d.u1 = st.in(a->u1, B * a->nsteps * nu); d.k2 = st.in(a->k2, B * a->nsteps * nk);
+    d.q2_guess = st.in(a->q2_guess, B * nd); d.lambda_guess = st.in(a->lambda_guess, B * nc);
+    d.q2 = st.out(a->q2, B * nq); d.p2 = st.out(a->p2, B * nd); d.lambda1 = st.out(a->lambda1, B * nc);
+    d.iters = st.out(a->iters, B); d.status = st.out(a->status, B);
+    const size_t ns = a->sample_every > 0 ? (size_t)(a->nsteps / a->sample_every) : 0;
+    d.traj_q = st.out(a->traj_q, B * ns * nq); d.traj_p = st.out(a->traj_p, B * ns * nd);
+    if (st.err) return st.err;
+    int rc = trepb_step_batch_dev(s, &d, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
+int trepb_calc_p2_batch(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1, double* p) {
+    if (!s) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)batch, nq = ps.nd + ps.nk;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    const double* dq0 = st.in(q0, B * nq);
+    const double* dq1 = st.in(q1, B * nq);
+    double* dp = st.out(p, B * ps.nd);
+    if (st.err) return st.err;
+    int rc = trepb_calc_p2_batch_dev(s, batch, dt, dq0, dq1, dp, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
+int trepb_linearize_batch(trepb_system* s, const trepb_lin_args* a) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
+    const size_t nX = 2 * nq, nU = nu + nk;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    trepb_lin_args d = *a;
+    d.t1 = st.in(a->t1, B); d.t2 = st.in(a->t2, B);
+    d.q1 = st.in(a->q1, B * nq); d.p1 = st.in(a->p1, B * nd); d.u1 = st.in(a->u1, B * nu); d.k2 = st.in(a->k2, B * nk);
+    d.q2_guess = st.in(a->q2_guess, B * nd); d.lambda_guess = st.in(a->lambda_guess, B * nc);
+    d.q2 = st.out(a->q2, B * nq); d.p2 = st.out(a->p2, B * nd); d.lambda1 = st.out(a->lambda1, B * nc);
+    d.iters = st.out(a->iters, B); d.status = st.out(a->status, B);
+    d.A = st.out(a->A, B * nX * nX); d.B = st.out(a->B, B * nX * nU);
+    d.q2_dq1 = st.out(a->q2_dq1, B * nq * nd); d.q2_dp1 = st.out(a->q2_dp1, B * nd * nd);
+    d.q2_du1 = st.out(a->q2_du1, B * nu * nd); d.q2_dk2 = st.out(a->q2_dk2, B * nk * nd);
+    d.p2_dq1 = st.out(a->p2_dq1, B * nq * nd); d.p2_dp1 = st.out(a->p2_dp1, B * nd * nd);
+    d.p2_du1 = st.out(a->p2_du1, B * nu * nd); d.p2_dk2 = st.out(a->p2_dk2, B * nk * nd);
+    d.l1_dq1 = st.out(a->l1_dq1, B * nq * nc); d.l1_dp1 = st.out(a->l1_dp1, B * nd * nc);
+    d.l1_du1 = st.out(a->l1_du1, B * nu * nc); d.l1_dk2 = st.out(a->l1_dk2, B * nk * nc);
+    if (st.err) return st.err;
+    int rc = trepb_linearize_batch_dev(s, &d, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
+}  // extern "C"
+
+// ---- FP64 roofline denominator ------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" int trepb_measure_fp64_peak(int device, double* tflops) {
+    if (!tflops) return fail(TREPB_ERR_INVALID, "null argument");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 15;
+    double* out = nullptr;
+    CU(cudaMalloc((void**)&out, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CU(cudaEventRecord(e0, 0));
+        dfma_kernel<<<blocks, threads>>>(out, iters, 0.999999, 1e-7);
+        CU(cudaEventRecord(e1, 0));
+        CU(cudaEventSynchronize(e1));
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, e0, e1));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads;
+        const double tf = fl / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *tflops = best;
+    return TREPB_OK;
+}

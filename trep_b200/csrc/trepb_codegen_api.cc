@@ -1,0 +1,44 @@
+// Host-only part of the C ABI: code generation and description hashing (include/trepb.h).
+// Built twice: into libtrepb.so, and on its own (g++, no CUDA) as the build-time generator that
+// trep_b200/build.py loads to emit gen/spec_*.cu for the ahead-of-time specialised systems.
+#include <string.h>
+#include <string>
+
+#include "../../include/trepb.h"
+#include "trepb_codegen.h"
+#include "trepb_err.h"
+#include "trepb_pack.h"
+
+using namespace trepb;
+
+extern "C" {
+
+int trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap) {
+    PackedSys P;
+    std::string err;
+    if (!pack_system(desc, &P, &err)) { last_error() = err; return -1; }
+    const std::string text = codegen_system(P, struct_name && *struct_name ? struct_name : "CtSys");
+    const int need = (int)text.size() + 1;
+    if (buf && cap > 0) {
+        const int n = need <= cap ? need - 1 : cap - 1;
+        memcpy(buf, text.data(), n);
+        buf[n] = 0;
+    }
+    return need;
+}
+
+uint64_t trepb_desc_hash(const trepb_sysdesc* desc) {
+    PackedSys P;
+    std::string err;
+    if (!pack_system(desc, &P, &err)) { last_error() = err; return 0; }
+    return desc_hash(P);
+}
+
+int trepb_validate(const trepb_sysdesc* desc) {
+    PackedSys P;
+    std::string err;
+    if (!pack_system(desc, &P, &err)) { last_error() = err; return TREPB_ERR_INVALID; }
+    return TREPB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,382 @@
+// CUDA kernels of the batched MidpointVI path (sm_100a, fp64): one thread per instance.
+//
+//   step_kernel       trepb_step_batch*      == MidpointVI.step looped in-kernel
+//                                               (trep/midpointvi.py:174-201 -> midpointvi.c:691-747)
+//   p2_kernel         trepb_calc_p2_batch*   == MidpointVI.calc_p2 (midpointvi.c:491-504)
+//   linearize_kernel  trepb_linearize_batch* == solve_DEL + calc_deriv1 + DSystem.fdx/fdu
+//                                               (midpointvi.c:1100-1120, dsystem.py:284-317)
+//
+// The same kernel templates are instantiated
+//   * on RtSys + WsStrided  - the table-driven general path: the packed system description is
+//     staged into shared memory once per CTA, the per-instance workspace lives in a global slab
+//     laid out [element][thread] so every workspace access of a warp is one coalesced line;
+//   * on a generated constexpr system + WsStatic - the specialised path for small systems: all
+//     loops unrolled, workspace in registers, no table reads at all.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "trepb_math.cuh"
+
+namespace trepb {
+
+struct StepParams {
+    long long batch;
+    int nsteps, max_it;
+    double t0, dt, tol;
+    const double *q1, *p1, *u1, *k2, *q2g, *lamg;
+    double *q2, *p2, *lam;
+    int *iters, *status;
+    int sample_every, nsamples;
+    double *traj_q, *traj_p;
+};
+
+struct P2Params {
+    long long batch;
+    double dt;
+    const double *q0, *q1;
+    double* p;
+};
+
+struct LinParams {
+    long long batch;
+    int max_it;
+    double tol, t1s, dts;
+    const double *t1, *t2;
+    const double *q1, *p1, *u1, *k2, *q2g, *lamg;
+    double *q2, *p2, *lam;
+    int *iters, *status;
+    double *A, *B;
+    double* raw[12];  // q2_dq1 q2_dp1 q2_du1 q2_dk2 p2_d* l1_d*
+    int stage;        // 1: stage A/B through shared memory for coalesced stores
+};
+
+// What a kernel launch needs besides its parameters.
+struct LaunchCfg {
+    int grid, block;
+    size_t smem;
+    cudaStream_t stream;
+    const RtSys* sys;       // host copy of the device view (general path); ignored when specialised
+    const char* dblob;      // device address of the packed blob
+    int blob_bytes;
+    WsStrided ws;           // workspace slab view (general path)
+};
+
+struct KernelInfo {
+    int regs, max_threads;
+    size_t static_smem, local_bytes;
+};
+
+struct KernelSet {
+    const char* name;
+    unsigned long long hash;  // 0: general
+    int specialized;
+    int nX, nU;
+    cudaError_t (*step)(const LaunchCfg&, const StepParams&);
+    cudaError_t (*p2)(const LaunchCfg&, const P2Params&);
+    cudaError_t (*lin)(const LaunchCfg&, const LinParams&);
+    // which: 0 step, 1 p2, 2 lin.  blocks_per_sm at (block, smem).
+    cudaError_t (*occupancy)(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
+};
+
+// registry of ahead-of-time specialised systems (filled by static initialisers of gen/*.cu)
+struct SpecRegistry {
+    static constexpr int kMax = 64;
+    const KernelSet* sets[kMax];
+    int n;
+};
+SpecRegistry& spec_registry();
+struct SpecRegistrar {
+    explicit SpecRegistrar(const KernelSet* ks) {
+        SpecRegistry& r = spec_registry();
+        if (r.n < SpecRegistry::kMax) r.sets[r.n++] = ks;
+    }
+};
+const KernelSet* general_kernels();
+
+#if defined(__CUDACC__)
+// ---------------------------------------------------------------------------------------------
+template <class Sys, bool S = Sys::kStatic>
+struct Ctx;
+
+// specialised: system is a type, workspace is a local object
+template <class Sys>
+struct Ctx<Sys, true> {
+    using WsT = WsStatic<Sys>;
+    Sys sys;
+    WsT ws;
+    __device__ __forceinline__ Ctx(const RtSys&, const char*, int, const WsStrided&, long, long) {}
+};
+
+// general: tables staged in shared memory, strided workspace
+template <class Sys>
+struct Ctx<Sys, false> {
+    using WsT = WsStrided;
+    RtSys sys;
+    WsT ws;
+    __device__ __forceinline__ Ctx(const RtSys& s, const char* dblob, int blob_bytes, const WsStrided& w,
+                                   long tid, long nthreads) {
+        extern __shared__ double smem_[];
+        const int n8 = (blob_bytes + 7) / 8;
+        const double* src = (const double*)dblob;
+        for (int i = threadIdx.x; i < n8; i += blockDim.x) smem_[i] = src[i];
+        __syncthreads();
+        sys = s.rebased(dblob, (const char*)smem_);
+        ws = w;
+        ws.base = w.base + tid;
+        ws.stride = nthreads;
+    }
+};
+
+template <class Sys>
+__global__ void __launch_bounds__(128)
+step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const StepParams p) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nth = (long)gridDim.x * blockDim.x;
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    auto& sys = c.sys;
+    auto& ws = c.ws;
+    const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    for (long b = tid; b < p.batch; b += nth) {
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nq; ++i) {
+            const double v = p.q1[b * nq + i];
+            ws.q1(i) = v;
+            ws.q2(i) = v;
+        }
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nd; ++i) {
+            ws.p1(i) = p.p1[b * nd + i];
+            if (p.q2g) ws.q2(i) = p.q2g[b * nd + i];
+        }
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nc; ++i) ws.lam(i) = p.lamg ? p.lamg[b * nc + i] : 0.0;
+        int total = 0, status = ST_OK;
+        double t1 = p.t0;
+        for (int st = 0; st < p.nsteps; ++st) {
+            if (st > 0) {
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nq; ++i) ws.q1(i) = ws.q2(i);
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nd; ++i) ws.p1(i) = ws.p2(i);
+            }
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nu; ++i) ws.u1(i) = p.u1 ? p.u1[(b * p.nsteps + st) * nu + i] : 0.0;
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nk; ++i) ws.q2(nd + i) = p.k2[(b * p.nsteps + st) * nk + i];
+            const double t2 = t1 + p.dt;
+            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            if (it < 0) { status = it; break; }
+            total += it;
+            t1 = t2;
+            if (p.sample_every > 0 && (st + 1) % p.sample_every == 0) {
+                const long row = b * p.nsamples + (st + 1) / p.sample_every - 1;
+                if (p.traj_q) {
+                    TREPB_UNROLL_SYS
+                    for (int i = 0; i < nq; ++i) p.traj_q[row * nq + i] = ws.q2(i);
+                }
+                if (p.traj_p) {
+                    TREPB_UNROLL_SYS
+                    for (int i = 0; i < nd; ++i) p.traj_p[row * nd + i] = ws.p2(i);
+                }
+            }
+        }
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nq; ++i) p.q2[b * nq + i] = ws.q2(i);
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nd; ++i) p.p2[b * nd + i] = ws.p2(i);
+        if (p.lam) {
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nc; ++i) p.lam[b * nc + i] = ws.lam(i);
+        }
+        if (p.iters) p.iters[b] = total;
+        p.status[b] = status;
+    }
+}
+
+template <class Sys>
+__global__ void __launch_bounds__(128)
+p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const P2Params p) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nth = (long)gridDim.x * blockDim.x;
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    auto& sys = c.sys;
+    auto& ws = c.ws;
+    const int nd = sys.ND(), nq = sys.NQ(), nu = sys.NU();
+    for (long b = tid; b < p.batch; b += nth) {
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nq; ++i) {
+            ws.q1(i) = p.q0[b * nq + i];
+            ws.q2(i) = p.q1[b * nq + i];
+        }
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nu; ++i) ws.u1(i) = 0.0;
+        calc_p2(sys, ws, 0.0, p.dt);
+        TREPB_UNROLL_SYS
+        for (int i = 0; i < nd; ++i) p.p[b * nd + i] = ws.p2(i);
+    }
+}
+
+template <class Sys>
+__global__ void __launch_bounds__(128)
+lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nth = (long)gridDim.x * blockDim.x;
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    auto& sys = c.sys;
+    auto& ws = c.ws;
+    const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    const int nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
+    extern __shared__ double smem_[];
+    // loop bound is uniform per warp so that the staged stores can be warp-cooperative
+    const long bend = ((p.batch + 31) / 32) * 32;
+    for (long b = tid; b < bend; b += nth) {
+        const bool live = b < p.batch;
+        int it = 0, status = ST_OK;
+        Deriv1Out o;
+        double t1 = 0.0, t2 = 0.0;
+        if (live) {
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nq; ++i) {
+                const double v = p.q1[b * nq + i];
+                ws.q1(i) = v;
+                ws.q2(i) = v;
+            }
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nd; ++i) {
+                ws.p1(i) = p.p1[b * nd + i];
+                if (p.q2g) ws.q2(i) = p.q2g[b * nd + i];
+            }
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nk; ++i) ws.q2(nd + i) = p.k2[b * nk + i];
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nu; ++i) ws.u1(i) = p.u1[b * nu + i];
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nc; ++i) ws.lam(i) = p.lamg ? p.lamg[b * nc + i] : 0.0;
+            t1 = p.t1 ? p.t1[b] : p.t1s;
+            t2 = p.t2 ? p.t2[b] : (t1 + p.dts);
+            it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            if (it < 0) { status = it; it = 0; }
+            if (p.q2) {
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nq; ++i) p.q2[b * nq + i] = ws.q2(i);
+            }
+            if (p.p2) {
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nd; ++i) p.p2[b * nd + i] = ws.p2(i);
+            }
+            if (p.lam) {
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nc; ++i) p.lam[b * nc + i] = ws.lam(i);
+            }
+        }
+#define TREPB_RAW(idx, member, rows, cols) \
+        o.member = p.raw[idx] ? p.raw[idx] + b * (long)((rows) * (cols)) : nullptr;
+        TREPB_RAW(0, q2_dq1, nq, nd) TREPB_RAW(1, q2_dp1, nd, nd) TREPB_RAW(2, q2_du1, nu, nd) TREPB_RAW(3, q2_dk2, nk, nd)
+        TREPB_RAW(4, p2_dq1, nq, nd) TREPB_RAW(5, p2_dp1, nd, nd) TREPB_RAW(6, p2_du1, nu, nd) TREPB_RAW(7, p2_dk2, nk, nd)
+        TREPB_RAW(8, l1_dq1, nq, nc) TREPB_RAW(9, l1_dp1, nd, nc) TREPB_RAW(10, l1_du1, nu, nc) TREPB_RAW(11, l1_dk2, nk, nc)
+#undef TREPB_RAW
+        o.es = 1;
+        if (p.stage) {
+            // thread-private slot of the CTA tile; stride nA+nB keeps the A and B rows of one
+            // instance together
+            double* slot = smem_ + (long)threadIdx.x * (nA + nB);
+            o.A = p.A ? slot : nullptr;
+            o.B = p.B ? slot + nA : nullptr;
+        } else {
+            o.A = p.A ? p.A + b * nA : nullptr;
+            o.B = p.B ? p.B + b * nB : nullptr;
+        }
+        if (live && status == ST_OK) {
+            const int r = deriv1(sys, ws, t1, t2, o);
+            if (r < 0) status = r;
+        }
+        if (live) {
+            if (p.iters) p.iters[b] = it;
+            p.status[b] = status;
+        }
+        if (p.stage) {
+            // warp-cooperative coalesced copy: the 32 instances of a warp are contiguous in A and B
+            __syncwarp();
+            const int lane = threadIdx.x & 31;
+            const long b0 = b - lane;
+            const long nlive = p.batch - b0 < 32 ? p.batch - b0 : 32;
+            const double* tile = smem_ + (long)(threadIdx.x - lane) * (nA + nB);
+            if (p.A) {
+                double* dstA = p.A + b0 * nA;
+                for (long e = lane; e < nlive * nA; e += 32) dstA[e] = tile[(e / nA) * (nA + nB) + e % nA];
+            }
+            if constexpr (!Sys::kStatic || (Sys::kStatic && (Sys{}.NU() + Sys{}.NK()) > 0)) {
+                if (p.B && nB > 0) {
+                    const int nBs = nB > 0 ? nB : 1;
+                    double* dstB = p.B + b0 * nB;
+                    for (long e = lane; e < nlive * nB; e += 32) dstB[e] = tile[(e / nBs) * (nA + nB) + nA + e % nBs];
+                }
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <class Sys>
+struct Launchers {
+    static cudaError_t prep(const void* fn, size_t smem) {
+        if (smem > 48 * 1024)
+            return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        return cudaSuccess;
+    }
+    static cudaError_t step(const LaunchCfg& c, const StepParams& p) {
+        RtSys rs{};
+        if (c.sys) rs = *c.sys;
+        cudaError_t e = prep((const void*)step_kernel<Sys>, c.smem);
+        if (e != cudaSuccess) return e;
+        step_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        return cudaGetLastError();
+    }
+    static cudaError_t p2(const LaunchCfg& c, const P2Params& p) {
+        RtSys rs{};
+        if (c.sys) rs = *c.sys;
+        cudaError_t e = prep((const void*)p2_kernel<Sys>, c.smem);
+        if (e != cudaSuccess) return e;
+        p2_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        return cudaGetLastError();
+    }
+    static cudaError_t lin(const LaunchCfg& c, const LinParams& p) {
+        RtSys rs{};
+        if (c.sys) rs = *c.sys;
+        cudaError_t e = prep((const void*)lin_kernel<Sys>, c.smem);
+        if (e != cudaSuccess) return e;
+        lin_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        return cudaGetLastError();
+    }
+    static cudaError_t occupancy(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info) {
+        const void* fn = which == 0 ? (const void*)step_kernel<Sys>
+                       : which == 1 ? (const void*)p2_kernel<Sys> : (const void*)lin_kernel<Sys>;
+        cudaFuncAttributes a;
+        cudaError_t e = cudaFuncGetAttributes(&a, fn);
+        if (e != cudaSuccess) return e;
+        if (info) {
+            info->regs = a.numRegs;
+            info->max_threads = a.maxThreadsPerBlock;
+            info->static_smem = a.sharedSizeBytes;
+            info->local_bytes = a.localSizeBytes;
+        }
+        e = prep(fn, smem);
+        if (e != cudaSuccess) return e;
+        return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, block, smem);
+    }
+};
+
+template <class Sys>
+KernelSet make_kernelset(const char* name, unsigned long long hash, int specialized, int nX, int nU) {
+    KernelSet k;
+    k.name = name; k.hash = hash; k.specialized = specialized; k.nX = nX; k.nU = nU;
+    k.step = &Launchers<Sys>::step;
+    k.p2 = &Launchers<Sys>::p2;
+    k.lin = &Launchers<Sys>::lin;
+    k.occupancy = &Launchers<Sys>::occupancy;
+    return k;
+}
+#endif  // __CUDACC__
+
+}  // namespace trepb

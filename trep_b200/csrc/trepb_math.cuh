@@ -37,10 +37,17 @@
 
 namespace trepb {
 
-#if defined(__CUDA_ARCH__)
+// TREPB_UNROLL      small fixed-count loops (3/6/9): always fully unrolled so the 3- and 6-vectors
+//                   stay in registers.
+// TREPB_UNROLL_SYS  loops over system-sized ranges (frames, configs, constraints ...): fully
+//                   unrolled for a compile-time system (Sys::kUnroll large), left rolled for the
+//                   table-driven system (Sys::kUnroll == 1).
+#if defined(__CUDACC__)
 #define TREPB_UNROLL _Pragma("unroll")
+#define TREPB_UNROLL_SYS _Pragma("unroll (Sys::kUnroll)")
 #else
 #define TREPB_UNROLL
+#define TREPB_UNROLL_SYS
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -98,7 +105,7 @@ TREPB_HD void sincos_(double x, double* s, double* c) {
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int f = 1; f < sys.NF(); ++f) {
         const int par = sys.parent(f), kind = sys.kind(f), cfg = sys.config(f);
         const bool vel = with_vel && sys.mass_below(f);
@@ -269,20 +276,20 @@ TREPB_HD void inertia_apply(double m, const double* h, const double* I, const do
 template <class Sys, class Ws>
 TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
     const int nq = sys.NQ();
-    TREPB_UNROLL for (int i = 0; i < nq; ++i) {
+    TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) {
         ws.Lq(i) = 0.0;
         ws.Lv(i) = 0.0;
     }
     if (order >= 2) {
-        TREPB_UNROLL for (int i = 0; i < nq; ++i)
-            TREPB_UNROLL for (int j = 0; j < nq; ++j) {
+        TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i)
+            TREPB_UNROLL_SYS for (int j = 0; j < nq; ++j) {
                 ws.Lqq(i, j) = 0.0;
                 ws.Lvq(i, j) = 0.0;
                 ws.Lvv(i, j) = 0.0;
             }
     }
     // own inertia / momentum
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int f = 1; f < sys.NF(); ++f) {
         if (!sys.mass_below(f)) continue;
         const double m = sys.mass(f, 0);
@@ -303,7 +310,7 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
             TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.mu(f, k) = 0.0;
         }
     }
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int f = sys.NF() - 1; f >= 1; --f) {
         if (!sys.mass_below(f)) continue;
         const int kind = sys.kind(f), cfg = sys.config(f), par = sys.parent(f);
@@ -359,7 +366,8 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                 (void)t;
                 // walk to the root
                 int cur = f;
-                for (;;) {
+                TREPB_UNROLL_SYS
+                for (int lvl = 0; lvl < sys.MAXDEPTH(); ++lvl) {
                     const int ci = sys.config(cur);
                     if (ci >= 0) {
                         const Axis ai = axis_of(sys.kind(cur));
@@ -517,7 +525,7 @@ TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, double* v) {
     frame_pos(sys, ws, A, pa);
     frame_pos(sys, ws, B, pb);
     TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int j = 0; j < sys.NQ(); ++j) {
         double da[3], db[3];
         dpoint(sys, ws, A, j, da);
@@ -542,10 +550,10 @@ template <class Sys, class Ws>
 TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
     const int nq = sys.NQ();
     if (mode & 4) {
-        TREPB_UNROLL for (int i = 0; i < nq; ++i)
-            TREPB_UNROLL for (int j = 0; j < nq; ++j) ws.DDhl(i, j) = 0.0;
+        TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i)
+            TREPB_UNROLL_SYS for (int j = 0; j < nq; ++j) ws.DDhl(i, j) = 0.0;
     }
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int c = 0; c < sys.NC(); ++c) {
         const int kind = sys.con_kind(c);
         const int A = sys.con_i(c, 0), B = sys.con_i(c, 1), third = sys.con_i(c, 2);
@@ -555,7 +563,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
             const double d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
             if (mode & 1) ws.hc(c) = dot3(v, v) - d * d;
             if (mode & 2) {
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int j = 0; j < nq; ++j) {
                     double val = 0.0;
                     if (sys.dep(A, j) || sys.dep(B, j) || third == j) {
@@ -568,10 +576,10 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
             }
             if (mode & 4) {
                 const double lam = ws.lam(c);
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i) {
                     if (!(sys.dep(A, i) || sys.dep(B, i) || third == i)) continue;
-                    TREPB_UNROLL
+                    TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
                         if (!(sys.dep(A, j) || sys.dep(B, j) || third == j)) continue;
                         double ddv[3];
@@ -589,7 +597,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
             const int comp = third;
             if (mode & 1) ws.hc(c) = v[comp];
             if (mode & 2) {
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int j = 0; j < nq; ++j) {
                     const double val = ws.dv(j, comp);
                     if (which_dh == 1) ws.Dh1(c, j) = val; else ws.Dh2(c, j) = val;
@@ -597,9 +605,9 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
             }
             if (mode & 4) {
                 const double lam = ws.lam(c);
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
-                    TREPB_UNROLL
+                    TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
                         double ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
@@ -619,7 +627,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
 template <class Sys, class Ws>
 TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
     const int nq = sys.NQ();
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int p = 0; p < sys.NPOT(); ++p) {
         const int kind = sys.pot_kind(p);
         if (kind == P_CONFIG_SPRING) {
@@ -633,7 +641,7 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
             double v[3];
             pair_first(sys, ws, A, B, v);
             const double x = sqrt(dot3(v, v));
-            TREPB_UNROLL
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nq; ++j) {
                 double dx = (1.0 / x) * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
                 ws.dxs(j) = dx;
@@ -642,9 +650,9 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
                 ws.Lq(j) -= val;
             }
             if (order >= 2) {
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
-                    TREPB_UNROLL
+                    TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
                         if (!(sys.dep(A, i) || sys.dep(B, i)) || !(sys.dep(A, j) || sys.dep(B, j))) continue;
                         double ddv[3];
@@ -669,19 +677,19 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
 template <class Sys, class Ws>
 TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
     const int nq = sys.NQ(), nd = sys.ND();
-    TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.Fo(j) = 0.0;
+    TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.Fo(j) = 0.0;
     if (order >= 2) {
-        TREPB_UNROLL for (int j = 0; j < nd; ++j) {
-            TREPB_UNROLL for (int i = 0; i < nq; ++i) { ws.Fq(j, i) = 0.0; ws.Fv(j, i) = 0.0; }
-            TREPB_UNROLL for (int u = 0; u < sys.NU(); ++u) ws.Fu(j, u) = 0.0;
+        TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) {
+            TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) { ws.Fq(j, i) = 0.0; ws.Fv(j, i) = 0.0; }
+            TREPB_UNROLL_SYS for (int u = 0; u < sys.NU(); ++u) ws.Fu(j, u) = 0.0;
         }
     }
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int fo = 0; fo < sys.NFORCE(); ++fo) {
         const int kind = sys.force_kind(fo);
         if (kind == F_DAMPING) {
             const int off = sys.force_i(fo, 0);
-            TREPB_UNROLL
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nd; ++j) {
                 const double c = sys.dpool(off + j);
                 ws.Fo(j) += -c * ws.dq(j);
@@ -703,7 +711,7 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
             const double x = sqrt(dot3(v, v));
             double vel = 0.0;
             // dx_j only where exactly one end depends on q_j (tapemeasure.py:97-110)
-            TREPB_UNROLL
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nq; ++j) {
                 double dx = 0.0;
                 if (sys.dep(A, j) != sys.dep(B, j))
@@ -711,18 +719,18 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
                 ws.dxs(j) = dx;
                 vel += dx * ws.dq(j);
             }
-            TREPB_UNROLL
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nd; ++j) {
                 if (sys.dep(A, j) == sys.dep(B, j)) continue;
                 ws.Fo(j) += -cdamp * vel * ws.dxs(j);
             }
             if (order >= 2) {
                 // ddx(j,i) = TapeMeasure_length_dqdq(q_j, q_i) ; vel_dq(i) = sum_k ddx(k,i) dq_k
-                TREPB_UNROLL
+                TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i) {
                     if (sys.dep(A, i) == sys.dep(B, i)) continue;
                     double veldq = 0.0;
-                    TREPB_UNROLL
+                    TREPB_UNROLL_SYS
                     for (int k = 0; k < nq; ++k) {
                         double ddx = 0.0;
                         if (sys.dep(A, k) != sys.dep(B, k)) {
@@ -735,7 +743,7 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
                         veldq += ddx * ws.dq(k);
                         if (k < nd) ws.Fq(k, i) += -cdamp * vel * ddx;  // second term of f_dq
                     }
-                    TREPB_UNROLL
+                    TREPB_UNROLL_SYS
                     for (int j = 0; j < nd; ++j) {
                         if (sys.dep(A, j) == sys.dep(B, j)) continue;
                         ws.Fq(j, i) += -cdamp * veldq * ws.dxs(j);
@@ -752,10 +760,15 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
 // (trep/_trep/math-code.c:337-432) so that pivot choices - and therefore rounding - agree.
 // A(i,j) accessor object, piv/scales arrays in the workspace.  Returns false if singular.
 // ---------------------------------------------------------------------------------------------
-template <class MatAcc, class PivAcc, class ScaleAcc>
+// For a compile-time system (Sys::kStatic) every array index must be a loop counter so that the
+// matrix lives in registers after full unrolling: the row swap and the permuted gather become
+// predicated selects.  Arithmetic and pivot rule are the same in both flavours.
+template <class Sys, class MatAcc, class PivAcc, class ScaleAcc>
 TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol) {
+    TREPB_UNROLL_SYS
     for (int i = 0; i < n; ++i) {
         double s = -1.0;
+        TREPB_UNROLL_SYS
         for (int j = 0; j < n; ++j) {
             const double a = fabs(A(i, j));
             if (a > s) s = a;
@@ -763,16 +776,21 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol
         scales(i) = 1.0 / s;
         piv(i) = (double)i;
     }
+    TREPB_UNROLL_SYS
     for (int j = 0; j < n; ++j) {
+        TREPB_UNROLL_SYS
         for (int i = 0; i < j; ++i) {
             double a = A(i, j);
+            TREPB_UNROLL_SYS
             for (int k = 0; k < i; ++k) a -= A(i, k) * A(k, j);
             A(i, j) = a;
         }
         double pv = -1.0;
         int pi = 0;
+        TREPB_UNROLL_SYS
         for (int i = j; i < n; ++i) {
             double a = A(i, j);
+            TREPB_UNROLL_SYS
             for (int k = 0; k < j; ++k) a -= A(i, k) * A(k, j);
             A(i, j) = a;
             const double t = fabs(a * scales(i));
@@ -780,29 +798,66 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol
         }
         if (pv <= tol) return false;
         if (pi != j) {
-            const double ti = piv(j); piv(j) = piv(pi); piv(pi) = ti;
-            for (int k = 0; k < n; ++k) { const double t = A(j, k); A(j, k) = A(pi, k); A(pi, k) = t; }
-            scales(pi) = scales(j);
+            if constexpr (Sys::kStatic) {
+                // selects with unconditional loads/stores: a branch on (pi == i) would let the
+                // optimiser substitute the dynamic `pi` for the loop counter and index memory
+                TREPB_UNROLL_SYS
+                for (int i = j + 1; i < n; ++i) {
+                    const bool sw = (pi == i);
+                    const double pj = piv(j), pi_ = piv(i);
+                    piv(j) = sw ? pi_ : pj;
+                    piv(i) = sw ? pj : pi_;
+                    TREPB_UNROLL_SYS
+                    for (int k = 0; k < n; ++k) {
+                        const double aj = A(j, k), ai = A(i, k);
+                        A(j, k) = sw ? ai : aj;
+                        A(i, k) = sw ? aj : ai;
+                    }
+                    const double sj = scales(j), si = scales(i);
+                    scales(i) = sw ? sj : si;
+                }
+            } else {
+                const double ti = piv(j); piv(j) = piv(pi); piv(pi) = ti;
+                for (int k = 0; k < n; ++k) { const double t = A(j, k); A(j, k) = A(pi, k); A(pi, k) = t; }
+                scales(pi) = scales(j);
+            }
         }
         const double d = A(j, j);
+        TREPB_UNROLL_SYS
         for (int i = j + 1; i < n; ++i) A(i, j) /= d;
     }
     return true;
 }
 // solves in place: b <- A^-1 b  (math-code.c:434-461); x is scratch of length n
-template <class MatAcc, class PivAcc, class BAcc, class XAcc>
+template <class Sys, class MatAcc, class PivAcc, class BAcc, class XAcc>
 TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x) {
+    TREPB_UNROLL_SYS
     for (int i = 0; i < n; ++i) {
-        double t = b((int)piv(i));
+        double t;
+        if constexpr (Sys::kStatic) {
+            t = 0.0;
+            const int src = (int)piv(i);
+            TREPB_UNROLL_SYS
+            for (int k = 0; k < n; ++k) {
+                const double bk = b(k);
+                t = (src == k) ? bk : t;
+            }
+        } else {
+            t = b((int)piv(i));
+        }
+        TREPB_UNROLL_SYS
         for (int j = 0; j < i; ++j) t -= A(i, j) * x(j);
         x(i) = t;
     }
+    TREPB_UNROLL_SYS
     for (int i = n - 1; i >= 0; --i) {
         double t = x(i);
+        TREPB_UNROLL_SYS
         for (int j = i + 1; j < n; ++j) t -= A(i, j) * x(j);
         t = t / A(i, i);
         x(i) = t;
     }
+    TREPB_UNROLL_SYS
     for (int i = 0; i < n; ++i) b(i) = x(i);
 }
 
@@ -831,7 +886,7 @@ template <class Ws> struct AccTdcCol {  // column k of Tdc (nd x nc)
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, double dt) {  // 0 = midpoint, 1 = q1, 2 = q2
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int i = 0; i < sys.NQ(); ++i) {
         const double a = ws.q1(i), b = ws.q2(i);
         ws.qe(i) = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
@@ -867,42 +922,42 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
     for (;;) {
         // ---- calc_f (midpointvi.c:533-565)
         eval_mid(sys, ws, dt, 1);
-        TREPB_UNROLL
+        TREPB_UNROLL_SYS
         for (int j = 0; j < nd; ++j) {
             double f = ws.p1(j) + (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
-            TREPB_UNROLL for (int c = 0; c < nc; ++c) f -= ws.Dh1(c, j) * ws.lam(c);
+            TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) f -= ws.Dh1(c, j) * ws.lam(c);
             ws.fr(j) = f;
         }
         if (nc > 0) {
             set_point(sys, ws, 2, dt);
             pass1(sys, ws, false, true);
             constraints_eval(sys, ws, 1, 2);
-            TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
+            TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
         }
         // ---- DEL_solved (midpointvi.c:672-689)
         double nrm = 0.0;
-        TREPB_UNROLL for (int j = 0; j < nd; ++j) nrm += ws.fr(j) * ws.fr(j);
+        TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) nrm += ws.fr(j) * ws.fr(j);
         bool solved = !(sqrt(nrm) > tol);
-        TREPB_UNROLL for (int c = 0; c < nc; ++c)
+        TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c)
             if (fabs(ws.fr(nd + c)) > sys.con_d(c, 1)) solved = false;
         if (solved) break;
         if (iterations > max_it) return ST_NOT_CONVERGED;
 
         // ---- Jacobian (midpointvi.c:577-670), same accumulation order as the reference
         eval_mid(sys, ws, dt, 2);
-        TREPB_UNROLL for (int k = 0; k < nd; ++k)
-            TREPB_UNROLL for (int i = 0; i < nd; ++i)
+        TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k)
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
                 ws.Df(k, i) = 0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i);
-        TREPB_UNROLL
+        TREPB_UNROLL_SYS
         for (int k = 0; k < nd; ++k) {
             ws.Df(k, k) += 0.25 * dt * ws.Lqq(k, k);
             ws.Df(k, k) -= 1.0 / dt * ws.Lvv(k, k);
-            TREPB_UNROLL for (int i = 0; i < nd; ++i) {
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) {
                 const double val = 0.5 * ws.Lvq(i, k);
                 ws.Df(k, i) += val;
                 ws.Df(i, k) -= val;
             }
-            TREPB_UNROLL for (int i = 0; i < k; ++i) {
+            TREPB_UNROLL_SYS for (int i = 0; i < k; ++i) {
                 double val = 0.25 * dt * ws.Lqq(k, i);
                 ws.Df(k, i) += val;
                 ws.Df(i, k) += val;
@@ -915,13 +970,13 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             set_point(sys, ws, 2, dt);
             pass1(sys, ws, false, true);
             constraints_eval(sys, ws, 2, 2);  // Dh2 = Dh(q2)
-            TREPB_UNROLL for (int i = 0; i < nd; ++i)
-                TREPB_UNROLL for (int c = 0; c < nc; ++c) {
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
+                TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) {
                     ws.Df(i, nd + c) = -ws.Dh1(c, i);
                     ws.Df(nd + c, i) = ws.Dh2(c, i);
                 }
-            TREPB_UNROLL for (int a = 0; a < nc; ++a)
-                TREPB_UNROLL for (int b = 0; b < nc; ++b) ws.Df(nd + a, nd + b) = 0.0;
+            TREPB_UNROLL_SYS for (int a = 0; a < nc; ++a)
+                TREPB_UNROLL_SYS for (int b = 0; b < nc; ++b) ws.Df(nd + a, nd + b) = 0.0;
         }
         if (nr == 1) {
             // 1x1: the reference's LU reduces to a scaled-pivot test and one division
@@ -929,16 +984,16 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             if (!(fabs(a) > 0.0)) return ST_SINGULAR;
             ws.fr(0) = ws.fr(0) / a;
         } else {
-            if (!lu_decomp(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
-            lu_solve(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws});
+            if (!lu_decomp<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+            lu_solve<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws});
         }
-        TREPB_UNROLL for (int k = 0; k < nd; ++k) ws.q2(k) -= ws.fr(k);
-        TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.lam(c) -= ws.fr(nd + c);
+        TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k) ws.q2(k) -= ws.fr(k);
+        TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.lam(c) -= ws.fr(nd + c);
         iterations++;
     }
     // p2 = D2L2 at the midpoint of the converged (q1, q2): the order-1 tables of the last
     // residual evaluation are exactly that point (midpointvi.c:742-743, 491-504).
-    TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
+    TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
     return iterations;
 }
 
@@ -947,7 +1002,7 @@ template <class Sys, class Ws>
 TREPB_HD void calc_p2(const Sys& sys, Ws& ws, double t1, double t2) {
     const double dt = t2 - t1;
     eval_mid(sys, ws, dt, 1);
-    TREPB_UNROLL for (int j = 0; j < sys.ND(); ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
+    TREPB_UNROLL_SYS for (int j = 0; j < sys.ND(); ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -979,22 +1034,22 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     }
     // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861), same accumulation order
     eval_mid(sys, ws, dt, 2);
-    TREPB_UNROLL for (int i1 = 0; i1 < nq; ++i1)
-        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+    TREPB_UNROLL_SYS for (int i1 = 0; i1 < nq; ++i1)
+        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
             const double v1 = 0.5 * dt * ws.Fq(i2, i1), v2 = ws.Fv(i2, i1);
             ws.T11(i1, i2) = v1 - v2;
             ws.T21(i1, i2) = v1 + v2;
             ws.T12(i1, i2) = 0.0;
             ws.T22(i1, i2) = 0.0;
         }
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int i1 = 0; i1 < nd; ++i1) {
         double v1 = 0.25 * dt * ws.Lqq(i1, i1), v2 = 1.0 / dt * ws.Lvv(i1, i1);
         ws.T11(i1, i1) += v1 + v2;
         ws.T21(i1, i1) += v1 - v2;
         ws.T12(i1, i1) += v1 - v2;
         ws.T22(i1, i1) += v1 + v2;
-        TREPB_UNROLL for (int i2 = 0; i2 < nq; ++i2) {
+        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nq; ++i2) {
             v1 = 0.5 * ws.Lvq(i1, i2);
             ws.T11(i2, i1) -= v1;
             ws.T21(i2, i1) -= v1;
@@ -1007,7 +1062,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 ws.T22(i1, i2) += v1;
             }
         }
-        TREPB_UNROLL for (int i2 = 0; i2 < i1; ++i2) {
+        TREPB_UNROLL_SYS for (int i2 = 0; i2 < i1; ++i2) {
             v1 = 0.25 * dt * ws.Lqq(i1, i2);
             v2 = 1.0 / dt * ws.Lvv(i1, i2);
             ws.T11(i2, i1) += v1 + v2;
@@ -1020,16 +1075,16 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
             ws.T22(i1, i2) += v1 + v2;
         }
     }
-    TREPB_UNROLL
+    TREPB_UNROLL_SYS
     for (int i1 = nd; i1 < nq; ++i1) {
-        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
             const double v1 = 0.5 * ws.Lvq(i1, i2);
             ws.T11(i1, i2) -= v1;
             ws.T21(i1, i2) += v1;
             ws.T12(i1, i2) -= v1;
             ws.T22(i1, i2) += v1;
         }
-        TREPB_UNROLL for (int i2 = 0; i2 < nd; ++i2) {
+        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
             const double v1 = 0.25 * dt * ws.Lqq(i1, i2), v2 = 1.0 / dt * ws.Lvv(i1, i2);
             ws.T11(i1, i2) += v1 + v2;
             ws.T21(i1, i2) += v1 - v2;
@@ -1037,35 +1092,42 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
             ws.T22(i1, i2) += v1 + v2;
         }
     }
-    TREPB_UNROLL for (int u = 0; u < nu; ++u)
-        TREPB_UNROLL for (int j = 0; j < nd; ++j) ws.T3(u, j) = dt * ws.Fu(j, u);
+    TREPB_UNROLL_SYS for (int u = 0; u < nu; ++u)
+        TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.T3(u, j) = dt * ws.Fu(j, u);
 
     // ---- calc_M2 (midpointvi.c:891-908)
-    TREPB_UNROLL for (int a = 0; a < nd; ++a)
-        TREPB_UNROLL for (int b = 0; b < nd; ++b) ws.M2(a, b) = ws.T21(b, a);
-    if (!lu_decomp(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+    TREPB_UNROLL_SYS for (int a = 0; a < nd; ++a)
+        TREPB_UNROLL_SYS for (int b = 0; b < nd; ++b) ws.M2(a, b) = ws.T21(b, a);
+    if (!lu_decomp<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
     // ---- calc_proj_inv (midpointvi.c:910-927): proj = -Dh2_d M2^-1 Dh1^T
     if (nc > 0) {
-        TREPB_UNROLL for (int i = 0; i < nd; ++i)
-            TREPB_UNROLL for (int c = 0; c < nc; ++c) ws.Tdc(i, c) = ws.Dh1(c, i);
+        TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
+            TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.Tdc(i, c) = ws.Dh1(c, i);
+        TREPB_UNROLL_SYS
         for (int c = 0; c < nc; ++c)
-            lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTdcCol<Ws>{&ws, c}, AccLux<Ws>{&ws});
+            lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTdcCol<Ws>{&ws, c}, AccLux<Ws>{&ws});
+        TREPB_UNROLL_SYS
         for (int a = 0; a < nc; ++a)
+            TREPB_UNROLL_SYS
             for (int b = 0; b < nc; ++b) {
                 double s = 0.0;
+                TREPB_UNROLL_SYS
                 for (int k = 0; k < nd; ++k) s += ws.Dh2(a, k) * ws.Tdc(k, b);
                 ws.PJ(a, b) = -s;
             }
-        if (!lu_decomp(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+        if (!lu_decomp<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
     }
 
     // ---- calc_deriv1 (midpointvi.c:929-1098): one right-hand side per wrt-variable
     // kind 0: q1_i   1: p1_i   2: u1_i   3: k2_i
     const long es = o.es;
+    TREPB_UNROLL_SYS
     for (int kindv = 0; kindv < 4; ++kindv) {
         const int count = kindv == 0 ? nq : (kindv == 1 ? nd : (kindv == 2 ? nu : nk));
+        TREPB_UNROLL_SYS
         for (int i = 0; i < count; ++i) {
             // explicit part c
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nd; ++j) {
                 double c;
                 if (kindv == 0) {
@@ -1082,27 +1144,33 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 ws.col(j) = c;
             }
             if (nc > 0) {
-                lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
+                lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
+                TREPB_UNROLL_SYS
                 for (int c = 0; c < nc; ++c) {
                     double s = 0.0;
+                    TREPB_UNROLL_SYS
                     for (int j = 0; j < nd; ++j) s += ws.Dh2(c, j) * ws.tnd(j);
                     if (kindv == 3) s += ws.Dh2(c, nd + i);
                     ws.tnc(c) = s;
                 }
-                lu_solve(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+                lu_solve<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+                TREPB_UNROLL_SYS
                 for (int j = 0; j < nd; ++j) {
                     double s = ws.col(j);
+                    TREPB_UNROLL_SYS
                     for (int c = 0; c < nc; ++c) s += ws.Dh1(c, j) * ws.tnc(c);
                     ws.col(j) = s;
                 }
             }
-            lu_solve(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
+            lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
             // p2 derivative row
             double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
             double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
             double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+            TREPB_UNROLL_SYS
             for (int j = 0; j < nd; ++j) {
                 double pv = kindv == 0 ? ws.T12(i, j) : (kindv == 3 ? ws.T22(nd + i, j) : 0.0);
+                TREPB_UNROLL_SYS
                 for (int k = 0; k < nd; ++k) pv += ws.T22(k, j) * ws.col(k);
                 const double qv = ws.col(j);
                 if (q2o) q2o[(long)(i * nd + j) * es] = qv;
@@ -1118,12 +1186,17 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                     if (o.B) { o.B[(long)(j * nU + nu + i) * es] = qv; o.B[(long)((nq + j) * nU + nu + i) * es] = pv; }
                 }
             }
-            if (l1o) for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c);
+            if (l1o) {
+                TREPB_UNROLL_SYS
+                for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c);
+            }
         }
     }
     // constant blocks of A and B
     if (o.A) {
+        TREPB_UNROLL_SYS
         for (int r = 0; r < nX; ++r)
+            TREPB_UNROLL_SYS
             for (int c = 0; c < nX; ++c) {
                 const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
                 if (dyn_row && c < nq + nd) continue;  // written above
@@ -1133,7 +1206,9 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
             }
     }
     if (o.B) {
+        TREPB_UNROLL_SYS
         for (int r = 0; r < nX; ++r)
+            TREPB_UNROLL_SYS
             for (int c = 0; c < nU; ++c) {
                 const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
                 if (dyn_row) continue;

@@ -67,6 +67,14 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
             cfg_frame[c] = f;
         }
     }
+    int max_depth = 1;
+    {
+        std::vector<int> depth(nf, 0);
+        for (int f = 1; f < nf; ++f) {
+            depth[f] = depth[d->frame_parent[f]] + 1;
+            if (depth[f] > max_depth) max_depth = depth[f];
+        }
+    }
     auto frame_ok = [&](int f) { return f >= 0 && f < nf; };
     // dep[f][c]
     std::vector<uint8_t> dep((size_t)nf * (nq > 0 ? nq : 1), 0), mass_below(nf, 0), need_world(nf, 0);
@@ -132,7 +140,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
     P.cfg_frame = cfg_frame; P.dep = dep; P.mass_below = mass_below; P.need_world = need_world;
     memset(&P.proto, 0, sizeof(P.proto));
     P.proto.nf = nf; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
-    P.proto.npot = np; P.proto.nforce = nfo;
+    P.proto.npot = np; P.proto.nforce = nfo; P.proto.max_depth = max_depth;
     for (int j = 0; j < 3; ++j) P.proto.grav[j] = grav[j];
     P.proto.has_gravity = has_grav; P.proto.has_pairs = has_pairs;
     P.blob.clear();

@@ -31,7 +31,7 @@ enum ConKind { C_DISTANCE = 0, C_POINT1D };
 enum Status { ST_OK = 0, ST_NOT_CONVERGED = -1, ST_SINGULAR = -2 };
 
 struct RtSys {
-    int nf, nd, nk, nu, nc, npot, nforce;
+    int nf, nd, nk, nu, nc, npot, nforce, max_depth;
     const int32_t* frame_parent;
     const int32_t* frame_kind;
     const int32_t* frame_config;
@@ -51,6 +51,8 @@ struct RtSys {
     int has_pairs;             // any point-pair element (spring/damper/constraint)
 
     static constexpr bool kStatic = false;
+    static constexpr int kUnroll = 1;   // system-sized loops stay rolled (see TREPB_UNROLL_SYS)
+    TREPB_HD int MAXDEPTH() const { return max_depth; }
     TREPB_HD int NF() const { return nf; }
     TREPB_HD int ND() const { return nd; }
     TREPB_HD int NK() const { return nk; }
@@ -86,6 +88,22 @@ struct RtSys {
     TREPB_HD double gravity(int k) const { return grav[k]; }
     TREPB_HD bool gravity_on() const { return has_gravity != 0; }
     TREPB_HD bool pairs_on() const { return has_pairs != 0; }
+
+    // Same tables at another address (the kernels stage the packed blob into shared memory).
+    TREPB_HD RtSys rebased(const char* from, const char* to) const {
+        RtSys s = *this;
+#define TREPB_RB(T, p) s.p = (const T*)(to + ((const char*)p - from));
+        TREPB_RB(int32_t, frame_parent) TREPB_RB(int32_t, frame_kind) TREPB_RB(int32_t, frame_config)
+        TREPB_RB(double, frame_value) TREPB_RB(double, frame_se3) TREPB_RB(double, frame_mass)
+        TREPB_RB(int32_t, cfg_frame_) TREPB_RB(uint8_t, dep_) TREPB_RB(uint8_t, mass_below_)
+        TREPB_RB(uint8_t, need_world_)
+        TREPB_RB(int32_t, pot_kind_) TREPB_RB(int32_t, pot_i_) TREPB_RB(double, pot_d_)
+        TREPB_RB(int32_t, force_kind_) TREPB_RB(int32_t, force_i_) TREPB_RB(double, force_d_)
+        TREPB_RB(int32_t, con_kind_) TREPB_RB(int32_t, con_i_) TREPB_RB(double, con_d_)
+        TREPB_RB(int32_t, ipool_) TREPB_RB(double, dpool_)
+#undef TREPB_RB
+        return s;
+    }
 };
 
 }  // namespace trepb

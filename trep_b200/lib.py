@@ -1,0 +1,355 @@
+"""ctypes binding of libtrepb.so (the C ABI declared in include/trepb.h).
+
+There is no fallback: if the library has not been built (``python -m trep_b200.build``) the
+import of this module raises, and every compute call needs a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import desc as D
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIBPATH = os.path.join(HERE, "libtrepb.so")
+
+if not os.path.exists(LIBPATH):
+    raise ImportError("trep_b200/libtrepb.so is missing: build it with `python -m trep_b200.build` "
+                      "(there is no CPU fallback)")
+_lib = C.CDLL(LIBPATH)
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+
+class StepArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("nsteps", C.c_int32), ("max_iterations", C.c_int32),
+                ("t0", C.c_double), ("dt", C.c_double), ("tolerance", C.c_double),
+                ("q1", C.c_void_p), ("p1", C.c_void_p), ("u1", C.c_void_p), ("k2", C.c_void_p),
+                ("q2_guess", C.c_void_p), ("lambda_guess", C.c_void_p),
+                ("q2", C.c_void_p), ("p2", C.c_void_p), ("lambda1", C.c_void_p),
+                ("iters", C.c_void_p), ("status", C.c_void_p),
+                ("sample_every", C.c_int32), ("_pad", C.c_int32),
+                ("traj_q", C.c_void_p), ("traj_p", C.c_void_p)]
+
+
+RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2_dk2",
+       "l1_dq1", "l1_dp1", "l1_du1", "l1_dk2"]
+
+
+class LinArgs(C.Structure):
+    _fields_ = ([("batch", C.c_int64), ("max_iterations", C.c_int32), ("_pad", C.c_int32),
+                 ("tolerance", C.c_double), ("t1", C.c_void_p), ("t2", C.c_void_p),
+                 ("t1_scalar", C.c_double), ("dt_scalar", C.c_double),
+                 ("q1", C.c_void_p), ("p1", C.c_void_p), ("u1", C.c_void_p), ("k2", C.c_void_p),
+                 ("q2_guess", C.c_void_p), ("lambda_guess", C.c_void_p),
+                 ("q2", C.c_void_p), ("p2", C.c_void_p), ("lambda1", C.c_void_p),
+                 ("iters", C.c_void_p), ("status", C.c_void_p), ("A", C.c_void_p), ("B", C.c_void_p)]
+                + [(n, C.c_void_p) for n in RAW])
+
+
+_lib.trepb_last_error.restype = C.c_char_p
+_lib.trepb_system_kernel_name.restype = C.c_char_p
+_lib.trepb_specialized_name.restype = C.c_char_p
+_lib.trepb_desc_hash.restype = C.c_uint64
+_lib.trepb_system_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+_lib.trepb_system_destroy.argtypes = [C.c_void_p]
+_lib.trepb_system_destroy.restype = None
+_lib.trepb_system_is_specialized.argtypes = [C.c_void_p]
+_lib.trepb_system_kernel_name.argtypes = [C.c_void_p]
+_lib.trepb_step_batch.argtypes = [C.c_void_p, C.POINTER(StepArgs)]
+_lib.trepb_step_batch_dev.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
+_lib.trepb_linearize_batch.argtypes = [C.c_void_p, C.POINTER(LinArgs)]
+_lib.trepb_linearize_batch_dev.argtypes = [C.c_void_p, C.POINTER(LinArgs), C.c_void_p]
+_lib.trepb_calc_p2_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
+_lib.trepb_calc_p2_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]
+_lib.trepb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+_lib.trepb_kernel_info.argtypes = [C.c_void_p, C.c_int] + [_ip] * 5
+_lib.trepb_malloc.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
+_lib.trepb_free.argtypes = [C.c_int, C.c_void_p]
+_lib.trepb_host_alloc.argtypes = [C.c_int64, C.POINTER(C.c_void_p)]
+_lib.trepb_host_free.argtypes = [C.c_void_p]
+_lib.trepb_memcpy_h2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+_lib.trepb_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+_lib.trepb_memset.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64]
+_lib.trepb_measure_fp64_peak.argtypes = [C.c_int, _dp]
+
+EXPORTS = [
+    "trepb_abi_version", "trepb_last_error", "trepb_system_create", "trepb_system_destroy",
+    "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_kernel_name",
+    "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash",
+    "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
+    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_linearize_batch",
+    "trepb_linearize_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
+    "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
+    "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
+]
+
+
+class TrepbError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("trepb error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _check(rc):
+    if rc != 0:
+        raise TrepbError(rc, (_lib.trepb_last_error() or b"").decode())
+
+
+def raw():
+    """The ctypes library object (for symbol checks)."""
+    return _lib
+
+
+def device_count():
+    n = C.c_int(0)
+    rc = _lib.trepb_device_count(C.byref(n))
+    return n.value if rc == 0 else 0
+
+
+def specialized_names():
+    return [_lib.trepb_specialized_name(i).decode() for i in range(_lib.trepb_num_specialized())]
+
+
+def desc_hash(desc):
+    cd, keep = D.to_c(desc)
+    return int(_lib.trepb_desc_hash(C.byref(cd)))
+
+
+def validate(desc):
+    cd, keep = D.to_c(desc)
+    _check(_lib.trepb_validate(C.byref(cd)))
+
+
+def measure_fp64_peak(device=0):
+    v = C.c_double(0)
+    _check(_lib.trepb_measure_fp64_peak(device, C.byref(v)))
+    return v.value
+
+
+def synchronize(device=0):
+    _check(_lib.trepb_synchronize(device))
+
+
+class DeviceBuffer:
+    """HBM buffer owned through the C ABI (so that a host without torch can drive the library)."""
+
+    def __init__(self, device, shape, dtype=np.float64):
+        self.device, self.shape, self.dtype = device, tuple(shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape, dtype=np.int64)) * self.dtype.itemsize
+        p = C.c_void_p()
+        _check(_lib.trepb_malloc(device, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def data_ptr(self):
+        return self.ptr
+
+    def upload(self, host):
+        host = np.ascontiguousarray(host, dtype=self.dtype)
+        assert host.nbytes == self.nbytes, (host.shape, self.shape)
+        _check(_lib.trepb_memcpy_h2d(self.device, self.ptr, host.ctypes.data, self.nbytes))
+        return self
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.shape, self.dtype)
+        _check(_lib.trepb_memcpy_d2h(self.device, out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def zero(self):
+        _check(_lib.trepb_memset(self.device, self.ptr, 0, self.nbytes))
+        return self
+
+    def free(self):
+        if self.ptr:
+            _lib.trepb_free(self.device, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def pinned_empty(shape, dtype=np.float64):
+    """numpy array backed by pinned host memory (cudaHostAlloc) for the end-to-end path."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    p = C.c_void_p()
+    _check(_lib.trepb_host_alloc(max(n, 1), C.byref(p)))
+    buf = (C.c_char * max(n, 1)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
+    arr._trepb_keep = buf  # noqa
+    return arr
+
+
+def _ptr(x):
+    """Address of a numpy array / DeviceBuffer / torch tensor, or None."""
+    if x is None:
+        return None
+    if isinstance(x, np.ndarray):
+        return x.ctypes.data
+    return x.data_ptr()
+
+
+class System:
+    """Handle of a flattened system resident on one GPU (trepb_system)."""
+
+    def __init__(self, desc: D.SystemDesc, device=0, specialize=True):
+        self.desc = desc
+        self.device = device
+        cd, self._keep = D.to_c(desc)
+        h = C.c_void_p()
+        _check(_lib.trepb_system_create(C.byref(cd), device, 0 if specialize else 1, C.byref(h)))
+        self._h = h
+        self.nq, self.nd, self.nk, self.nu, self.nc = desc.nq, desc.nd, desc.nk, desc.nu, desc.nc
+        self.nX, self.nU = desc.nX, desc.nU
+
+    @property
+    def specialized(self):
+        return bool(_lib.trepb_system_is_specialized(self._h))
+
+    @property
+    def kernel_name(self):
+        return _lib.trepb_system_kernel_name(self._h).decode()
+
+    def kernel_info(self, which):
+        v = [C.c_int32(0) for _ in range(5)]
+        _check(_lib.trepb_kernel_info(self._h, which, *[C.byref(x) for x in v]))
+        return dict(zip(["regs", "local_bytes", "blocks_per_sm", "block", "smem_bytes"], [x.value for x in v]))
+
+    def last_kernel_ms(self):
+        ms = C.c_float(0)
+        _check(_lib.trepb_last_kernel_ms(self._h, C.byref(ms)))
+        return ms.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            _lib.trepb_system_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- raw calls: every array argument is a pointer-like (numpy => host entry point,
+    #      anything with data_ptr() => device entry point); the caller owns shapes/dtypes ----------
+    def step_raw(self, on_device, batch, nsteps, t0, dt, q1, p1, u1, k2, q2_guess, lambda_guess,
+                 q2, p2, lambda1, iters, status, tolerance=1e-10, max_iterations=200,
+                 sample_every=0, traj_q=None, traj_p=None, stream=None):
+        a = StepArgs(batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt,
+                     tolerance=tolerance, q1=_ptr(q1), p1=_ptr(p1), u1=_ptr(u1), k2=_ptr(k2),
+                     q2_guess=_ptr(q2_guess), lambda_guess=_ptr(lambda_guess), q2=_ptr(q2),
+                     p2=_ptr(p2), lambda1=_ptr(lambda1), iters=_ptr(iters), status=_ptr(status),
+                     sample_every=sample_every, traj_q=_ptr(traj_q), traj_p=_ptr(traj_p))
+        if on_device:
+            _check(_lib.trepb_step_batch_dev(self._h, C.byref(a), stream))
+        else:
+            _check(_lib.trepb_step_batch(self._h, C.byref(a)))
+
+    def linearize_raw(self, on_device, batch, q1, p1, u1, k2, status, t1=None, t2=None,
+                      t1_scalar=0.0, dt_scalar=0.0, q2_guess=None, lambda_guess=None, q2=None,
+                      p2=None, lambda1=None, iters=None, A=None, B=None, raw=None,
+                      tolerance=1e-10, max_iterations=200, stream=None):
+        a = LinArgs(batch=batch, max_iterations=max_iterations, tolerance=tolerance, t1=_ptr(t1),
+                    t2=_ptr(t2), t1_scalar=t1_scalar, dt_scalar=dt_scalar, q1=_ptr(q1), p1=_ptr(p1),
+                    u1=_ptr(u1), k2=_ptr(k2), q2_guess=_ptr(q2_guess),
+                    lambda_guess=_ptr(lambda_guess), q2=_ptr(q2), p2=_ptr(p2),
+                    lambda1=_ptr(lambda1), iters=_ptr(iters), status=_ptr(status), A=_ptr(A), B=_ptr(B))
+        for n, v in (raw or {}).items():
+            setattr(a, n, _ptr(v))
+        if on_device:
+            _check(_lib.trepb_linearize_batch_dev(self._h, C.byref(a), stream))
+        else:
+            _check(_lib.trepb_linearize_batch(self._h, C.byref(a)))
+
+    def calc_p2_raw(self, on_device, batch, dt, q0, q1, p, stream=None):
+        if on_device:
+            _check(_lib.trepb_calc_p2_batch_dev(self._h, batch, dt, _ptr(q0), _ptr(q1), _ptr(p), stream))
+        else:
+            _check(_lib.trepb_calc_p2_batch(self._h, batch, dt, _ptr(q0), _ptr(q1), _ptr(p)))
+
+    # ---- numpy convenience (host entry points) ---------------------------------------------------
+    def _f(self, x, shape):
+        x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+        return x.reshape(shape)
+
+    def calc_p2(self, dt, q0, q1):
+        q0 = np.atleast_2d(np.asarray(q0, float))
+        B = q0.shape[0]
+        q0, q1 = self._f(q0, (B, self.nq)), self._f(q1, (B, self.nq))
+        p = np.empty((B, self.nd))
+        self.calc_p2_raw(False, B, float(dt), q0, q1, p)
+        return p
+
+    def step(self, q1, p1, t0, dt, nsteps=1, u1=None, k2=None, q2_guess=None, lambda_guess=None,
+             tolerance=1e-10, max_iterations=200, sample_every=0):
+        """`nsteps` consecutive MidpointVI steps for every instance.  Returns a dict with the
+        final q2, p2, lambda1, iters (summed), status and optionally the sampled trajectory."""
+        q1 = np.atleast_2d(np.asarray(q1, float))
+        B = q1.shape[0]
+        q1, p1 = self._f(q1, (B, self.nq)), self._f(p1, (B, self.nd))
+        u1 = None if (u1 is None or self.nu == 0) else self._f(u1, (B, nsteps, self.nu))
+        if self.nk:
+            k2 = self._f(k2, (B, nsteps, self.nk))
+        else:
+            k2 = None
+        q2g = None if q2_guess is None else self._f(q2_guess, (B, self.nd))
+        lg = None if (lambda_guess is None or self.nc == 0) else self._f(lambda_guess, (B, self.nc))
+        out = dict(q2=np.empty((B, self.nq)), p2=np.empty((B, self.nd)),
+                   lambda1=np.zeros((B, self.nc)), iters=np.zeros(B, np.int32),
+                   status=np.zeros(B, np.int32))
+        ns = nsteps // sample_every if sample_every > 0 else 0
+        if ns:
+            out["traj_q"] = np.empty((B, ns, self.nq))
+            out["traj_p"] = np.empty((B, ns, self.nd))
+        self.step_raw(False, B, nsteps, float(t0), float(dt), q1, p1, u1, k2, q2g, lg, out["q2"],
+                      out["p2"], out["lambda1"] if self.nc else None, out["iters"], out["status"],
+                      tolerance, max_iterations, sample_every, out.get("traj_q"), out.get("traj_p"))
+        return out
+
+    def linearize(self, q1, p1, u1=None, k2=None, t1=0.0, t2=None, dt=None, q2_guess=None,
+                  lambda_guess=None, want_raw=False, tolerance=1e-10, max_iterations=200):
+        """One DSystem-style linearization per instance: solve the step, then A (fdx) and B (fdu)."""
+        q1 = np.atleast_2d(np.asarray(q1, float))
+        B = q1.shape[0]
+        q1, p1 = self._f(q1, (B, self.nq)), self._f(p1, (B, self.nd))
+        u1 = self._f(u1 if u1 is not None else np.zeros((B, self.nu)), (B, self.nu))
+        k2 = self._f(k2 if k2 is not None else np.zeros((B, self.nk)), (B, self.nk))
+        q2g = None if q2_guess is None else self._f(q2_guess, (B, self.nd))
+        lg = None if (lambda_guess is None or self.nc == 0) else self._f(lambda_guess, (B, self.nc))
+        t1a = t2a = None
+        t1s = dts = 0.0
+        if np.ndim(t1) == 0 and (t2 is None or np.ndim(t2) == 0):
+            t1s = float(t1)
+            dts = float(dt) if t2 is None else float(t2) - float(t1)
+            if t2 is not None:
+                # keep the reference's dt = t2 - t1 rounding: pass both as arrays
+                t1a = np.full(B, float(t1)); t2a = np.full(B, float(t2))
+        else:
+            t1a = self._f(np.broadcast_to(t1, (B,)), (B,))
+            t2a = self._f(np.broadcast_to(t2, (B,)), (B,))
+        out = dict(q2=np.empty((B, self.nq)), p2=np.empty((B, self.nd)), lambda1=np.zeros((B, self.nc)),
+                   iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32),
+                   A=np.empty((B, self.nX, self.nX)), B=np.zeros((B, self.nX, self.nU)))
+        rawbufs = {}
+        if want_raw:
+            wrt = {"dq1": self.nq, "dp1": self.nd, "du1": self.nu, "dk2": self.nk}
+            for n in RAW:
+                rawbufs[n] = np.zeros((B, wrt[n[3:]], self.nc if n.startswith("l1") else self.nd))
+            out.update(rawbufs)
+        self.linearize_raw(False, B, q1, p1, u1 if self.nu else None, k2 if self.nk else None,
+                           out["status"], t1=t1a, t2=t2a, t1_scalar=t1s, dt_scalar=dts, q2_guess=q2g,
+                           lambda_guess=lg, q2=out["q2"], p2=out["p2"],
+                           lambda1=out["lambda1"] if self.nc else None, iters=out["iters"],
+                           A=out["A"], B=out["B"] if self.nU else None,
+                           raw={k: v for k, v in rawbufs.items() if v.size},
+                           tolerance=tolerance, max_iterations=max_iterations)
+        return out
