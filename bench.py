@@ -1,0 +1,372 @@
+#!/usr/bin/env python3
+"""bench.py - headline benchmark of the batched MidpointVI path (driver contract).
+
+Workload (BASELINE.json configs[1]): 2^20 independent damped pendulums
+(examples/damped-pendulum.py) stepped 1000 MidpointVI steps; one bench "step" = one pass of the
+hot path over that batch = 1.048576e9 DEL steps per GPU.  Metric: DEL steps/s, whole job.
+
+  value      device-resident inputs, CUDA-event time of the step kernel, max over ranks
+  e2e        the same pass through the host-pointer C-ABI call (trepb_step_batch) with pinned
+             host buffers: H2D of (q1,p1), kernel, D2H of (q2,p2,iters,status) inside the timed region
+  roofline   the step kernel against the FP64 pipe (this kernel is on-chip/compute bound; the
+             denominator is an in-run DFMA micro-benchmark since MEASURED_PEAKS.json has no
+             fp64 entry) - see DESIGN.md "Roofline accounting"
+  secondary  linearizations/s for pend-on-cart (HBM-bound, with its own hbm roofline) and the
+             marionette, same run
+  cpu_baseline  the reference's own C path (oracle/_ref) in a tight C loop on all host cores,
+             bounded sample
+
+`--impl reference` times only the reference arm (rank 0; other ranks exit).
+Multi-GPU (torchrun): the batch shards across ranks with no data-path collective (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+BATCH = 1 << 20
+NSTEPS = 1000
+DT = 0.01
+METRIC = "batched DEL steps/s (MidpointVI, damped pendulum)"
+UNIT = "DEL steps/s"
+WORKLOAD = "W2: 2^20 damped pendulums (examples/damped-pendulum.py) x 1000 MidpointVI steps per GPU"
+# executed fp64 flops per DEL step of step_kernel<damped_pendulum> (ncu sass op counters,
+# profiles/r01_step_flops.txt; FMA = 2) - the algorithmic figure of DESIGN.md "Roofline accounting"
+FLOPS_PER_STEP = None  # filled from profiles/flops.json if present
+
+
+def workload_inputs(batch, seed=0):
+    """theta0 ~ U(-pi,pi), theta1 = theta0 + U(-0.02,0.02)."""
+    rng = np.random.default_rng(seed)
+    th0 = rng.uniform(-np.pi, np.pi, (batch, 1))
+    th1 = th0 + rng.uniform(-0.02, 0.02, (batch, 1))
+    return th0, th1
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                 "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "power_w_max": float(max(power)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_setup(ngpus):
+    """torch.distributed only when launched under torchrun with WORLD_SIZE > 1."""
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        return dist, rank, local, world
+    return None, 0, 0, 1
+
+
+def reference_arm(args, rank, world):
+    """Times the reference's own C implementation on the host cores (oracle/_ref)."""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    cores = len(os.sched_getaffinity(0))
+    th0, th1 = workload_inputs(BATCH)
+    # bounded sample: per step each core advances `per` instances by NSTEPS steps (~1-2 s)
+    per = 64
+    h = cb.Harness("damped_pendulum")
+    p = h.R  # noqa
+    # p from two configurations exactly like the GPU arm (initialize_from_configs)
+    pinit = np.zeros((cores * per, 1))
+    for i in range(cores * per):
+        h.mvi.initialize_from_configs(0.0, th0[i], DT, th1[i])
+        pinit[i] = h.mvi.p2
+    shards = [(th1[i * per:(i + 1) * per], pinit[i * per:(i + 1) * per], NSTEPS, DT) for i in range(cores)]
+    for _ in range(max(args.warmup, 1)):
+        cb.time_parallel("damped_pendulum", "rollouts", shards, reps=1)
+    rates = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r, procs, wall = cb.time_parallel("damped_pendulum", "rollouts", shards, reps=3)
+        rates.append(r)
+    wall = time.perf_counter() - t0
+    value = float(np.mean(rates))
+    units_per_step = cores * per * NSTEPS * 3
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": units_per_step / value * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": "%d instances x %d steps x 3 repeats per bench step" % (cores * per, NSTEPS)},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference",
+                         "sample": "%d processes x %d instances x %d steps x 3, oracle/_ref (unmodified reference C, gcc -O2) "
+                                   "driven by oracle/ref_harness.c" % (cores, per, NSTEPS)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def secondary(lib, systems, device, fp64_peak, hbm_peak):
+    """linearizations/s for pend-on-cart (W3-shaped batch) and the marionette (W5), device resident."""
+    out = []
+    rng = np.random.default_rng(1)
+    # ---- pend-on-cart: inputs+outputs ~1 GB >> L2
+    d = systems.named_desc("pend_on_cart1")
+    s = lib.System(d, device=device)
+    B = 1 << 22
+    q1 = rng.uniform(-0.5, 0.5, (B, 2)); p1 = rng.normal(0, 1, (B, 2)); u1 = rng.uniform(-2, 2, (B, 1))
+    up = lambda a: lib.DeviceBuffer(device, a.shape, a.dtype).upload(a)
+    dq, dp, du = up(q1), up(p1), up(u1)
+    q2 = lib.DeviceBuffer(device, (B, 2)); p2 = lib.DeviceBuffer(device, (B, 2))
+    it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+    A = lib.DeviceBuffer(device, (B, 4, 4)); Bm = lib.DeviceBuffer(device, (B, 4, 1))
+    ms = []
+    for rep in range(6):
+        s.linearize_raw(True, B, dq, dp, du, None, st, t1_scalar=0.0, dt_scalar=DT, q2=q2, p2=p2, iters=it, A=A, B=Bm)
+        lib.synchronize(device)
+        if rep >= 2:
+            ms.append(s.last_kernel_ms())
+    t = float(np.mean(ms))
+    # algorithmic bytes/linearization: in q1,p1,u1 = 40 B; out A,B = 160 B, q2,p2 = 32 B, iters+status = 8 B
+    byt = 40 + 160 + 32 + 8
+    out.append({"metric": "linearizations/s (pend-on-cart, solve + deriv1 -> A,B)", "value": B / t * 1e3, "unit": "linearizations/s",
+                "batch": B, "ms": t, "newton_iters_mean": float(it.download().mean()),
+                "roofline": {"bound": "hbm", "achieved": B * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": B * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt}})
+    for b in (dq, dp, du, q2, p2, it, st, A, Bm):
+        b.free()
+    s.close()
+    # ---- marionette
+    d = systems.named_desc("puppet")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
+    s = lib.System(d, device=device)
+    B = 32768
+    idx = rng.integers(1, 58, B)
+    q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
+    q1[:, :d.nd] += rng.normal(0, 0.02, (B, d.nd)); p1 += rng.normal(0, 0.02, (B, d.nd))
+    dq, dp, dk, dl = up(q1), up(p1), up(g["roll_k2"][idx]), up(g["roll_lambda"][idx - 1])
+    q2 = lib.DeviceBuffer(device, (B, d.nq)); p2 = lib.DeviceBuffer(device, (B, d.nd)); l2 = lib.DeviceBuffer(device, (B, d.nc))
+    it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+    A = lib.DeviceBuffer(device, (B, d.nX, d.nX)); Bm = lib.DeviceBuffer(device, (B, d.nX, d.nU))
+    ms = []
+    for rep in range(4):
+        s.linearize_raw(True, B, dq, dp, None, dk, st, t1_scalar=0.0, dt_scalar=DT, lambda_guess=dl, q2=q2, p2=p2,
+                        lambda1=l2, iters=it, A=A, B=Bm)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    t = float(np.mean(ms))
+    out.append({"metric": "linearizations/s (marionette nd22/nk18/nc6, solve + deriv1 -> A,B)", "value": B / t * 1e3,
+                "unit": "linearizations/s", "batch": B, "ms": t, "newton_iters_mean": float(it.download().mean()),
+                "ok_fraction": float((st.download() == 0).mean())})
+    for b in (dq, dp, dk, dl, q2, p2, l2, it, st, A, Bm):
+        b.free()
+    s.close()
+    return out
+
+
+def cpu_baseline_sample():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    cores = len(os.sched_getaffinity(0))
+    th0, th1 = workload_inputs(4096)
+    h = cb.Harness("damped_pendulum")
+    per = 8
+    n = min(cores * per, 4096)
+    pinit = np.zeros((n, 1))
+    for i in range(n):
+        h.mvi.initialize_from_configs(0.0, th0[i], DT, th1[i])
+        pinit[i] = h.mvi.p2
+    shards = [(th1[i * per:(i + 1) * per], pinit[i * per:(i + 1) * per], NSTEPS, DT) for i in range(n // per)]
+    rate, procs, wall = cb.time_parallel("damped_pendulum", "rollouts", shards, reps=2)
+    return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
+            "sample": "%d processes x %d instances x %d steps x 2 of the same workload; oracle/_ref (unmodified reference C, "
+                      "gcc -O2) in the tight C loop of oracle/ref_harness.c; wall %.1f s" % (procs, per, NSTEPS, wall)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="trepb")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        rank = int(os.environ.get("RANK", "0"))
+        reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
+        return
+
+    dist, rank, local, world = dist_setup(args.gpus)
+    from trep_b200 import lib, systems
+    if lib.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    device = local
+    d = systems.named_desc("damped_pendulum")
+    s = lib.System(d, device=device)
+    assert s.specialized, "the damped-pendulum specialisation must be compiled in"
+    th0, th1 = workload_inputs(BATCH, seed=rank)   # each rank its own shard of the global batch
+
+    # ---- device-resident arm --------------------------------------------------------------------
+    up = lambda a: lib.DeviceBuffer(device, a.shape, a.dtype).upload(a)
+    dq0, dq1 = up(th0), up(th1)
+    dp = lib.DeviceBuffer(device, (BATCH, 1))
+    s.calc_p2_raw(True, BATCH, DT, dq0, dq1, dp)     # initialize_from_configs
+    q2 = lib.DeviceBuffer(device, (BATCH, 1)); p2 = lib.DeviceBuffer(device, (BATCH, 1))
+    it = lib.DeviceBuffer(device, (BATCH,), np.int32); st = lib.DeviceBuffer(device, (BATCH,), np.int32)
+    flush = lib.DeviceBuffer(device, (256 << 20,), np.uint8)   # > 126 MB L2
+
+    def one_step():
+        flush.zero()
+        s.step_raw(True, BATCH, NSTEPS, DT, DT, dq1, dp, None, None, None, None, q2, p2, None, it, st)
+        lib.synchronize(device)
+        return s.last_kernel_ms()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        lib.synchronize(device)
+
+    for _ in range(args.warmup):
+        one_step()
+    fp64_peak = lib.measure_fp64_peak(device)
+    sampler = ClockSampler(device)
+    sampler.start()
+    barrier()
+    times = [one_step() for _ in range(args.steps)]
+    barrier()
+    clocks = sampler.stop()
+    total_ms = float(np.sum(times))
+    iters_mean = float(it.download().mean()) / NSTEPS
+    ok = bool(np.all(st.download() == 0))
+
+    # ---- end-to-end arm: host-pointer C-ABI call, pinned buffers, copies inside the timed region --
+    hq = lib.pinned_empty((BATCH, 1)); hp = lib.pinned_empty((BATCH, 1))
+    hq[:] = th1; hp[:] = dp.download()
+    hq2 = lib.pinned_empty((BATCH, 1)); hp2 = lib.pinned_empty((BATCH, 1))
+    hit = lib.pinned_empty((BATCH,), np.int32); hst = lib.pinned_empty((BATCH,), np.int32)
+
+    def one_e2e():
+        t0 = time.perf_counter()
+        s.step_raw(False, BATCH, NSTEPS, DT, DT, hq, hp, None, None, None, None, hq2, hp2, None, hit, hst)
+        return (time.perf_counter() - t0) * 1e3
+
+    for _ in range(2):
+        one_e2e()
+    barrier()
+    e2e_times = [one_e2e() for _ in range(args.steps)]
+    barrier()
+    e2e_ms = float(np.sum(e2e_times))
+    assert np.array_equal(hq2, q2.download()), "host and device entry points must agree bit for bit"
+
+    # ---- max over ranks ---------------------------------------------------------------------------
+    if dist is not None:
+        import torch
+        t = torch.tensor([total_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_ms = float(t[0]), float(t[1])
+    units = float(BATCH) * NSTEPS * args.steps * world
+    value = units / (total_ms * 1e-3)
+    e2e_value = units / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        flops_per_step = None
+        fj = os.path.join(ROOT, "profiles", "flops.json")
+        if os.path.exists(fj):
+            flops_per_step = json.load(open(fj)).get("damped_pendulum_step_flops_per_del_step")
+        kms = total_ms / args.steps
+        roof = {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None,
+                "peak_source": "in-run DFMA micro-benchmark (trepb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                "kernel": "step_kernel<damped_pendulum>", "kernel_ms": kms}
+        if flops_per_step:
+            ach = flops_per_step * BATCH * NSTEPS / (kms * 1e-3) / 1e12
+            roof.update(achieved=ach, frac=ach / fp64_peak, flops_per_unit=flops_per_step)
+        else:
+            roof.update(achieved=None, frac=None)
+        hbm_peak = 6451.2
+        mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp):
+            hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": BATCH, "nsteps": NSTEPS, "dt": DT,
+                       "l2": "flushed between timed iterations (256 MB memset)", "kernel": s.kernel_name,
+                       "newton_iters_per_step": iters_mean, "all_converged": ok,
+                       "sharding": "independent instances block-partitioned over ranks, no data-path collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": BATCH * 16,
+                    "d2h_bytes_per_step": BATCH * 24, "ms_per_step": e2e_ms / args.steps,
+                    "api": "trepb_step_batch (host pointers, pinned)"},
+            "gpu_launches": args.steps * world,
+            "clocks": clocks,
+            "roofline": roof,
+        }
+        if world == 1 and not args.no_secondary:
+            line["secondary"] = secondary(lib, systems, device, fp64_peak, hbm_peak)
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

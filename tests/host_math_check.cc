@@ -101,6 +101,6 @@ int th_linearize(const trepb_sysdesc* d, double t1, double t2, double tol, int m
     o.p2_dq1 = raw[4]; o.p2_dp1 = raw[5]; o.p2_du1 = raw[6]; o.p2_dk2 = raw[7];
     o.l1_dq1 = raw[8]; o.l1_dp1 = raw[9]; o.l1_du1 = raw[10]; o.l1_dk2 = raw[11];
     o.A = A; o.B = B; o.es = 1;
-    return deriv1(s, ws, t1, t2, o);
+    return deriv1(s, ws, t1, t2, o, true);  // same call sequence as lin_kernel
 }
 }

@@ -195,8 +195,18 @@ namespace {
 
 // grid for `batch` instances at `bps` resident CTAs per SM; for the general path also sizes the
 // workspace slab (one column per launched thread).
-int make_cfg(trepb_system* s, long long batch, int bps, size_t smem, cudaStream_t stream, LaunchCfg* c) {
-    const long long need = (batch + s->block - 1) / s->block;
+int make_cfg(trepb_system* s, int which, long long batch, int bps, size_t smem, cudaStream_t stream, LaunchCfg* c) {
+    int block = s->block;
+    if (!s->ks->specialized) {
+        // small batches of big systems: narrower CTAs so that every SM gets work
+        while (block > 32 && (batch + block - 1) / block < 2LL * s->sms) block /= 2;
+        if (block != s->block) {
+            int b = 0;
+            CU(s->ks->occupancy(which, block, smem, &b, nullptr));
+            bps = b > 0 ? b : 1;
+        }
+    }
+    const long long need = (batch + block - 1) / block;
     long long grid = need;
     if (!s->ks->specialized) {
         long long resident = (long long)s->sms * bps;
@@ -204,7 +214,7 @@ int make_cfg(trepb_system* s, long long batch, int bps, size_t smem, cudaStream_
         // keep the slab within a quarter of the free memory
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cta = (size_t)s->ws_doubles * sizeof(double) * s->block;
+        const size_t per_cta = (size_t)s->ws_doubles * sizeof(double) * block;
         const size_t budget = (free_b + s->ws.cap) / 4;
         if ((size_t)grid * per_cta > budget) grid = (long long)(budget / per_cta);
         if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the workspace slab");
@@ -214,7 +224,7 @@ int make_cfg(trepb_system* s, long long batch, int bps, size_t smem, cudaStream_
     }
     if (grid < 1) grid = 1;
     c->grid = (int)grid;
-    c->block = s->block;
+    c->block = block;
     c->smem = smem;
     c->stream = stream;
     c->sys = s->ks->specialized ? nullptr : &s->dview;
@@ -258,7 +268,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     p.nsamples = a->sample_every > 0 ? a->nsteps / a->sample_every : 0;
     p.traj_q = a->traj_q; p.traj_p = a->traj_p;
     LaunchCfg c;
-    int rc = make_cfg(s, a->batch, s->bps[0], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    int rc = make_cfg(s, 0, a->batch, s->bps[0], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
     CU(s->ks->step(c, p));
@@ -275,7 +285,7 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
     P2Params p;
     p.batch = batch; p.dt = dt; p.q0 = q0; p.q1 = q1; p.p = pout;
     LaunchCfg c;
-    int rc = make_cfg(s, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    int rc = make_cfg(s, 1, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
     CU(s->ks->p2(c, p));
@@ -307,7 +317,7 @@ int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* st
     p.stage = stage ? 1 : 0;
     LaunchCfg c;
     const size_t smem = s->ks->specialized ? (stage ? s->lin_stage_bytes : 0) : (size_t)s->blob_bytes;
-    int rc = make_cfg(s, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, (cudaStream_t)stream, &c);
+    int rc = make_cfg(s, 2, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, (cudaStream_t)stream, &c);
     if (rc) return rc;
     if (stage) {
         // persistent-style grid: the staged kernel loops with a warp-uniform bound

@@ -287,7 +287,7 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
             o.B = p.B ? p.B + b * nB : nullptr;
         }
         if (live && status == ST_OK) {
-            const int r = deriv1(sys, ws, t1, t2, o);
+            const int r = deriv1(sys, ws, t1, t2, o, true);
             if (r < 0) status = r;
         }
         if (live) {

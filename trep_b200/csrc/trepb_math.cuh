@@ -163,9 +163,11 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
             if (ax.rot) {
                 double sn, cs;
                 sincos_(x, &sn, &cs);
-                ws.cs(f, 0) = cs;
-                ws.cs(f, 1) = sn;
                 if (vel) {
+                    // kept for pass 2 (force transforms); world-only passes at q1/q2 must not
+                    // disturb the midpoint values (eval_mid_again)
+                    ws.cs(f, 0) = cs;
+                    ws.cs(f, 1) = sn;
                     rotT(g, ax.b, ax.c, cs, sn);
                     rotT(V, ax.b, ax.c, cs, sn);
                     rotT(V + 3, ax.b, ax.c, cs, sn);
@@ -904,6 +906,22 @@ TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
     forces_eval(sys, ws, order);
 }
 
+// Second-order tables at the SAME midpoint as the preceding eval_mid(order 1): pass 1 (the
+// sin/cos, velocities and W vectors) is still valid in the workspace, only the evaluation
+// configuration (and, when pair elements are evaluated at the midpoint, the world poses) may
+// have been moved to q1/q2 by the constraint passes in between.  The reference re-walks its
+// whole cache here (set_midpoint clears every cache flag, midpointvi.c:437-457).
+template <class Sys, class Ws>
+TREPB_HD void eval_mid_again(const Sys& sys, Ws& ws, double dt) {
+    if (sys.NC() > 0) {
+        set_point(sys, ws, 0, dt);
+        if (sys.pairs_mid()) pass1(sys, ws, false, true);
+    }
+    pass2(sys, ws, 2);
+    add_potentials(sys, ws, 2);
+    forces_eval(sys, ws, 2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // MidpointVI_solve_DEL (midpointvi.c:691-747).  Inputs in ws: q1, p1, u1, q2 (dyn part = Newton
 // start, kin part = k2), lam (start).  Outputs in ws: q2, lam, p2.  Returns the iteration count
@@ -944,7 +962,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
         if (iterations > max_it) return ST_NOT_CONVERGED;
 
         // ---- Jacobian (midpointvi.c:577-670), same accumulation order as the reference
-        eval_mid(sys, ws, dt, 2);
+        eval_mid_again(sys, ws, dt);
         TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k)
             TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
                 ws.Df(k, i) = 0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i);
@@ -1019,7 +1037,7 @@ struct Deriv1Out {
 };
 
 template <class Sys, class Ws>
-TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Out& o) {
+TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Out& o, bool mid_valid = false) {
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nc = sys.NC(), nu = sys.NU();
     const double dt = t2 - t1;
     const int nX = 2 * nq, nU = nu + nk;
@@ -1032,8 +1050,14 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2, 2);      // Dh2
     }
-    // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861), same accumulation order
-    eval_mid(sys, ws, dt, 2);
+    // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861), same accumulation order.
+    // mid_valid: the workspace still holds pass 1 of the converged midpoint (solve_del just ran)
+    if (mid_valid) {
+        if (nc == 0) set_point(sys, ws, 0, dt);
+        eval_mid_again(sys, ws, dt);
+    } else {
+        eval_mid(sys, ws, dt, 2);
+    }
     TREPB_UNROLL_SYS for (int i1 = 0; i1 < nq; ++i1)
         TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
             const double v1 = 0.5 * dt * ws.Fq(i2, i1), v2 = ws.Fv(i2, i1);

@@ -92,7 +92,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
         while (f > 0 && !need_world[f]) { need_world[f] = 1; f = d->frame_parent[f]; }
     };
     double grav[3] = {0, 0, 0};
-    int has_grav = 0, has_pairs = 0;
+    int has_grav = 0, has_pairs = 0, has_pairs_mid = 0;
     for (int i = 0; i < np; ++i) {
         const int k = d->pot_kind[i];
         const int32_t* ii = d->pot_i + 4 * i;
@@ -101,7 +101,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
             has_grav = 1;
         } else if (k == TREPB_POT_LINEAR_SPRING) {
             if (!frame_ok(ii[0]) || !frame_ok(ii[1])) return fail("LinearSpring frame index out of range");
-            mark_world(ii[0]); mark_world(ii[1]); has_pairs = 1;
+            mark_world(ii[0]); mark_world(ii[1]); has_pairs = 1; has_pairs_mid = 1;
         } else if (k == TREPB_POT_CONFIG_SPRING) {
             if (ii[0] < 0 || ii[0] >= nq) return fail("ConfigSpring config index out of range");
         } else return fail("unknown potential kind (Python-defined / spline potentials have no device implementation)");
@@ -120,7 +120,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
                 if (!frame_ok(d->ipool[ii[0] + j])) return fail("LinearDamper frame index out of range");
                 mark_world(d->ipool[ii[0] + j]);
             }
-            has_pairs = 1;
+            has_pairs = 1; has_pairs_mid = 1;
         } else return fail("unknown force kind (wrench / Python-defined forces have no device implementation)");
     }
     for (int i = 0; i < nc; ++i) {
@@ -142,7 +142,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
     P.proto.nf = nf; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
     P.proto.npot = np; P.proto.nforce = nfo; P.proto.max_depth = max_depth;
     for (int j = 0; j < 3; ++j) P.proto.grav[j] = grav[j];
-    P.proto.has_gravity = has_grav; P.proto.has_pairs = has_pairs;
+    P.proto.has_gravity = has_grav; P.proto.has_pairs = has_pairs; P.proto.has_pairs_mid = has_pairs_mid;
     P.blob.clear();
     int k = 0;
     auto put = [&](const void* src, size_t bytes) {

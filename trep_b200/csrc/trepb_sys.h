@@ -49,6 +49,7 @@ struct RtSys {
     double grav[3];            // sum of all Gravity potentials
     int has_gravity;
     int has_pairs;             // any point-pair element (spring/damper/constraint)
+    int has_pairs_mid;         // pair elements evaluated at the midpoint (spring/damper)
 
     static constexpr bool kStatic = false;
     static constexpr int kUnroll = 1;   // system-sized loops stay rolled (see TREPB_UNROLL_SYS)
@@ -88,6 +89,7 @@ struct RtSys {
     TREPB_HD double gravity(int k) const { return grav[k]; }
     TREPB_HD bool gravity_on() const { return has_gravity != 0; }
     TREPB_HD bool pairs_on() const { return has_pairs != 0; }
+    TREPB_HD bool pairs_mid() const { return has_pairs_mid != 0; }
 
     // Same tables at another address (the kernels stage the packed blob into shared memory).
     TREPB_HD RtSys rebased(const char* from, const char* to) const {

@@ -184,7 +184,6 @@ def pinned_empty(shape, dtype=np.float64):
     _check(_lib.trepb_host_alloc(max(n, 1), C.byref(p)))
     buf = (C.c_char * max(n, 1)).from_address(p.value)
     arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape, dtype=np.int64))).reshape(shape)
-    arr._trepb_keep = buf  # noqa
     return arr
 
 
