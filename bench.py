@@ -126,7 +126,7 @@ def reference_arm(args, rank, world):
     cores = len(os.sched_getaffinity(0))
     th0, th1 = workload_inputs(BATCH)
     # bounded sample: per step each core advances `per` instances by NSTEPS steps (~1-2 s)
-    per = 64
+    per = 256
     h = cb.Harness("damped_pendulum")
     p = h.R  # noqa
     # p from two configurations exactly like the GPU arm (initialize_from_configs)
@@ -222,18 +222,19 @@ def cpu_baseline_sample():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline as cb
     cores = len(os.sched_getaffinity(0))
-    th0, th1 = workload_inputs(4096)
+    cores_ = len(os.sched_getaffinity(0))
+    th0, th1 = workload_inputs(cores_ * 512)
     h = cb.Harness("damped_pendulum")
-    per = 8
-    n = min(cores * per, 4096)
+    per = 512
+    n = cores * per
     pinit = np.zeros((n, 1))
     for i in range(n):
         h.mvi.initialize_from_configs(0.0, th0[i], DT, th1[i])
         pinit[i] = h.mvi.p2
     shards = [(th1[i * per:(i + 1) * per], pinit[i * per:(i + 1) * per], NSTEPS, DT) for i in range(n // per)]
-    rate, procs, wall = cb.time_parallel("damped_pendulum", "rollouts", shards, reps=2)
+    rate, procs, wall = cb.time_parallel("damped_pendulum", "rollouts", shards, reps=3)
     return {"value": rate, "unit": UNIT, "cores": procs, "kind": "reference",
-            "sample": "%d processes x %d instances x %d steps x 2 of the same workload; oracle/_ref (unmodified reference C, "
+            "sample": "%d processes x %d instances x %d steps x 3 of the same workload; oracle/_ref (unmodified reference C, "
                       "gcc -O2) in the tight C loop of oracle/ref_harness.c; wall %.1f s" % (procs, per, NSTEPS, wall)}
 
 

@@ -1,0 +1,164 @@
+"""Batched mirror of the part of ``trep.discopt.DSystem`` that sits on the hot path
+(trep/discopt/dsystem.py:19-66 state layout, :229-250 set, :284-317 fdx/fdu, :406-423
+linearize_trajectory).
+
+State / input layout is the reference's:  X = [Q(nq); p(nd); v(nk)],  U = [u(nu); rho(nk)].
+
+``linearize_trajectory`` treats every time-step k (and every rollout) as an independent instance -
+exactly what the reference's loop does (it *sets* the state at every k, dsystem.py:413-415) - and
+evaluates all of them in one kernel launch.  With ``torch.distributed`` initialised the instances
+are block-partitioned over the ranks and the A/B slabs are all-gathered (the only exchange this
+path has).
+"""
+from __future__ import annotations
+
+from collections import namedtuple
+
+import numpy as np
+
+from .midpointvi import ConvergenceError, MidpointVI
+
+
+def shard_range(n, rank, world):
+    """Contiguous block partition of n instances: [lo, hi) of `rank`."""
+    base, rem = divmod(n, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_gather_blocks(local, n_total, dist=None):
+    """Concatenate per-rank slabs [n_local, ...] -> [n_total, ...] on every rank.  `dist` is
+    torch.distributed (initialised) or None for a single process."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    counts = [shard_range(n_total, r, world) for r in range(world)]
+    width = max(hi - lo for lo, hi in counts)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    pad = np.zeros((width,) + local.shape[1:], dtype=local.dtype)
+    pad[:local.shape[0]] = local
+    mine = torch.from_numpy(pad).to(dev)
+    parts = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine)
+    return np.concatenate([p.cpu().numpy()[:hi - lo] for p, (lo, hi) in zip(parts, counts)], axis=0)
+
+
+class DSystem:
+    linearization_return = namedtuple("linearization", "A B")
+    trajectory_return = namedtuple("trajectory", "X U")
+
+    def __init__(self, varint: MidpointVI, t):
+        self.varint = varint
+        self._time = np.array(t, dtype=np.float64).squeeze()
+        v = varint
+        self._nQ, self._np, self._nv, self._nu, self._nrho = v.nq, v.nd, v.nk, v.nu, v.nk
+        self._nX = self._nQ + self._np + self._nv
+        self._nU = self._nu + self._nrho
+
+    nX = property(lambda s: s._nX)
+    nU = property(lambda s: s._nU)
+    time = property(lambda s: s._time)
+
+    def kf(self):
+        return len(self._time) - 1
+
+    # ---- state packing (dsystem.py:118-226) -----------------------------------------------------------
+    def build_state(self, Q=None, p=None, v=None):
+        parts = [x for x in (Q, p, v) if x is not None]
+        lead = np.asarray(parts[0]).shape[:-1] if parts else ()
+        X = np.zeros(lead + (self._nX,))
+        if Q is not None: X[..., :self._nQ] = Q
+        if p is not None: X[..., self._nQ:self._nQ + self._np] = p
+        if v is not None: X[..., self._nQ + self._np:] = v
+        return X
+
+    def build_input(self, u=None, rho=None):
+        parts = [x for x in (u, rho) if x is not None]
+        lead = np.asarray(parts[0]).shape[:-1] if parts else ()
+        U = np.zeros(lead + (self._nU,))
+        if u is not None: U[..., :self._nu] = u
+        if rho is not None: U[..., self._nu:] = rho
+        return U
+
+    def split_state(self, X):
+        X = np.asarray(X)
+        return X[..., :self._nQ], X[..., self._nQ:self._nQ + self._np], X[..., self._nQ + self._np:]
+
+    def split_input(self, U):
+        U = np.asarray(U)
+        return U[..., :self._nu], U[..., self._nu:]
+
+    # ---- the hot path ----------------------------------------------------------------------------------
+    def linearize(self, X, U, t1, t2, X_hint=None, dist=None, compute=None):
+        """A[i] = fdx, B[i] = fdu of instance i: DSystem.set(X[i], U[i], k, xk_hint=X_hint[i]) +
+        fdx() + fdu() of the reference.  X [n,nX], U [n,nU], t1/t2 [n]."""
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        n = X.shape[0]
+        world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+        rank = dist.get_rank() if world > 1 else 0
+        lo, hi = shard_range(n, rank, world)
+        q1, p1, _ = self.split_state(X[lo:hi])
+        u1, rho2 = self.split_input(U[lo:hi])
+        hint = None if X_hint is None else np.asarray(X_hint, float)[lo:hi, :self._np]
+        t1 = np.broadcast_to(np.asarray(t1, float), (n,))[lo:hi]
+        t2 = np.broadcast_to(np.asarray(t2, float), (n,))[lo:hi]
+        fn = compute or self._device_linearize
+        A, B, status = fn(q1, p1, u1, rho2, t1, t2, hint)
+        A = all_gather_blocks(A, n, dist)
+        B = all_gather_blocks(B, n, dist)
+        status = all_gather_blocks(status, n, dist)
+        bad = np.flatnonzero(status != 0)
+        if bad.size:
+            raise ConvergenceError("%d of %d linearizations failed (first: instance %d, status %d)"
+                                   % (bad.size, n, bad[0], status[bad[0]]), status)
+        return self.linearization_return(A, B)
+
+    def _device_linearize(self, q1, p1, u1, rho2, t1, t2, hint):
+        out = self.varint.sys.linearize(q1, p1, u1, rho2, t1=t1, t2=t2, q2_guess=hint,
+                                        tolerance=self.varint.tolerance)
+        return out["A"], out["B"], out["status"]
+
+    def linearize_trajectory(self, X, U, dist=None, compute=None):
+        """Linearization about a trajectory (dsystem.py:406-423).  X [K+1, nX], U [K, nU] for one
+        trajectory or X [R, K+1, nX], U [R, K, nU] for R rollouts sharing `time`.
+        Returns (A, B) with shapes [..., K, nX, nX], [..., K, nX, nU]."""
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        single = X.ndim == 2
+        if single:
+            X, U = X[None], U[None]
+        R, K = X.shape[0], X.shape[1] - 1
+        assert U.shape[1] >= K and len(self._time) >= K + 1
+        t1 = np.tile(self._time[:K], R)
+        t2 = np.tile(self._time[1:K + 1], R)
+        A, B = self.linearize(X[:, :K].reshape(R * K, -1), U[:, :K].reshape(R * K, -1), t1, t2,
+                              X_hint=X[:, 1:K + 1].reshape(R * K, -1), dist=dist, compute=compute)
+        A = A.reshape(R, K, self._nX, self._nX)
+        B = B.reshape(R, K, self._nX, self._nU)
+        if single:
+            A, B = A[0], B[0]
+        return self.linearization_return(A, B)
+
+    def simulate(self, X0, U):
+        """Rollouts X[k+1] = f(X[k], U[k], k) from X0 [R, nX] with U [R, K, nU] in one launch
+        (what repeated DSystem.step calls do, dsystem.py:253-281).  Returns X [R, K+1, nX]."""
+        X0, U = np.atleast_2d(np.asarray(X0, float)), np.asarray(U, float)
+        if U.ndim == 2:
+            U = U[None]
+        R, K = U.shape[0], U.shape[1]
+        dts = np.diff(self._time[:K + 1])
+        assert np.allclose(dts, dts[0], rtol=1e-9, atol=0), "the in-kernel time loop needs a uniform time grid"
+        q0, p0, _ = self.split_state(X0)
+        u, rho = self.split_input(U)
+        v = self.varint
+        v.initialize_from_state(self._time[0], q0, p0)
+        out = v.simulate(K, float(dts[0]), u=u if self._nu else None, k=rho if self._nv else None, sample_every=1)
+        Q = np.concatenate([q0[:, None, :], out["traj_q"]], axis=1)
+        P = np.concatenate([p0[:, None, :], out["traj_p"]], axis=1)
+        X = np.zeros((R, K + 1, self._nX))
+        X[..., :self._nQ] = Q
+        X[..., self._nQ:self._nQ + self._np] = P
+        if self._nv:
+            X[:, 0, self._nQ + self._np:] = X0[:, self._nQ + self._np:]
+            X[:, 1:, self._nQ + self._np:] = (Q[:, 1:, self._np:] - Q[:, :-1, self._np:]) / dts[0]
+        return X

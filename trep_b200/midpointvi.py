@@ -1,0 +1,156 @@
+"""Batched mirror of the reference's ``trep.MidpointVI`` Python shell (trep/midpointvi.py:19-732).
+
+Same method names, argument meaning and error behaviour; every state array gains a leading batch
+axis (``q1`` is ``[B, nq]`` ...).  All numerics run in the CUDA library through the C ABI
+(``trep_b200.lib``) - there is no CPU path.
+
+    mvi = MidpointVI(system)                      # model mirror, SystemDesc or a live trep.System
+    mvi.initialize_from_configs(0.0, q0, dt, q1)  # [B, nq] each
+    iters = mvi.step(mvi.t2 + dt, u1, k2)         # one DEL step for every instance
+    mvi.simulate(1000, dt)                        # many steps inside one kernel launch
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import desc as D
+from . import lib, model
+
+
+class ConvergenceError(Exception):
+    """Mirror of trep.ConvergenceError (trep/_trep/_trep.c:142): raised when at least one instance
+    failed; ``.status`` holds the per-instance codes (0 ok, -1 not converged, -2 singular)."""
+
+    def __init__(self, msg, status):
+        super().__init__(msg)
+        self.status = status
+
+
+def as_desc(system) -> D.SystemDesc:
+    if isinstance(system, D.SystemDesc):
+        return system
+    if isinstance(system, model.System):
+        return system.describe()
+    return model.flatten_trep_system(system)   # live reference trep.System (duck-typed)
+
+
+class MidpointVI:
+    def __init__(self, system, tolerance=1e-10, device=0, specialize=True):
+        self.desc = as_desc(system)
+        self.sys = lib.System(self.desc, device=device, specialize=specialize)
+        self.tolerance = float(tolerance)
+        d = self.desc
+        self.nq, self.nd, self.nk, self.nu, self.nc = d.nq, d.nd, d.nk, d.nu, d.nc
+        self.t1 = self.t2 = 0.0
+        self.q1 = self.q2 = self.p1 = self.p2 = self.u1 = self.lambda1 = None
+        self.status = None
+        self._lin = None
+
+    # ---- initialisation (midpointvi.py:138-172) --------------------------------------------------
+    def _b(self, x, n):
+        x = np.asarray(x, dtype=np.float64)
+        if x.ndim == 1:
+            x = x[None, :]
+        assert x.shape[1] == n, "expected trailing dimension %d, got %r" % (n, x.shape)
+        return np.ascontiguousarray(x)
+
+    def initialize_from_state(self, t1, q1, p1, lambda1=None):
+        self.q1 = self.q2 = self._b(q1, self.nq)
+        self.p1 = self.p2 = self._b(p1, self.nd)
+        self.t1 = self.t2 = float(t1)
+        B = self.q1.shape[0]
+        self.lambda1 = np.zeros((B, self.nc)) if lambda1 is None else self._b(lambda1, self.nc)
+        self._lin = None
+
+    def initialize_from_configs(self, t0, q0, t1, q1, lambda1=None):
+        q0, q1 = self._b(q0, self.nq), self._b(q1, self.nq)
+        self.t1, self.t2 = float(t0), float(t1)
+        self.q1, self.q2 = q0, q1
+        self.p2 = self.sys.calc_p2(self.t2 - self.t1, q0, q1)
+        self.p1 = None
+        B = q1.shape[0]
+        self.lambda1 = np.zeros((B, self.nc)) if lambda1 is None else self._b(lambda1, self.nc)
+        self._lin = None
+
+    @property
+    def batch(self):
+        return 0 if self.q2 is None else self.q2.shape[0]
+
+    # ---- stepping (midpointvi.py:174-201) ---------------------------------------------------------
+    def _check(self, status):
+        self.status = status
+        bad = np.flatnonzero(status != 0)
+        if bad.size:
+            raise ConvergenceError("%d of %d instances failed (first: instance %d, status %d) at t=%s"
+                                   % (bad.size, status.size, bad[0], status[bad[0]], self.t2), status)
+
+    def step(self, t2, u1=tuple(), k2=tuple(), max_iterations=200, q2_hint=None, lambda1_hint=None):
+        """Advance every instance to time t2.  Returns the per-instance Newton iteration counts."""
+        B = self.batch
+        u1 = np.broadcast_to(np.asarray(u1, float).reshape(-1, self.nu) if self.nu else np.zeros((1, 0)), (B, self.nu))
+        k2 = np.broadcast_to(np.asarray(k2, float).reshape(-1, self.nk) if self.nk else np.zeros((1, 0)), (B, self.nk))
+        self.q1, self.p1, self.u1 = self.q2, self.p2, np.ascontiguousarray(u1)
+        self.t1, t0 = self.t2, self.t2
+        hint = None if q2_hint is None else self._b(q2_hint, np.asarray(q2_hint).shape[-1])[:, :self.nd]
+        lam = self.lambda1 if lambda1_hint is None else self._b(lambda1_hint, self.nc)
+        out = self.sys.step(self.q1, self.p1, t0, float(t2) - t0, nsteps=1,
+                            u1=u1[:, None, :] if self.nu else None, k2=k2[:, None, :] if self.nk else None,
+                            q2_guess=hint, lambda_guess=lam if self.nc else None,
+                            tolerance=self.tolerance, max_iterations=max_iterations)
+        self.t2 = float(t2)
+        self.q2, self.p2, self.lambda1 = out["q2"], out["p2"], out["lambda1"]
+        self._lin = None
+        self._check(out["status"])
+        return out["iters"]
+
+    def simulate(self, nsteps, dt, u=None, k=None, max_iterations=200, sample_every=0):
+        """`nsteps` steps of length dt inside one kernel launch (the Monte-Carlo / rollout path).
+        u: [B, nsteps, nu], k: [B, nsteps, nk] (kinematic configs at the END of each step).
+        Returns dict(iters, traj_q, traj_p) - trajectories only if sample_every > 0."""
+        out = self.sys.step(self.q2, self.p2, self.t2, float(dt), nsteps=nsteps, u1=u, k2=k,
+                            lambda_guess=self.lambda1 if self.nc else None, tolerance=self.tolerance,
+                            max_iterations=max_iterations, sample_every=sample_every)
+        # state before the last step is only known when a trajectory was captured
+        self.q1 = self.p1 = None
+        t = self.t2
+        for _ in range(nsteps):       # same accumulation as repeated step(t2 + dt) calls
+            self.t1, t = t, t + float(dt)
+        self.t2 = t
+        self.q2, self.p2, self.lambda1 = out["q2"], out["p2"], out["lambda1"]
+        self._lin = None
+        self._check(out["status"])
+        return out
+
+    @property
+    def v2(self):
+        """Discrete kinematic velocity (q2k - q1k)/(t2 - t1)  (midpointvi.py:325-333)."""
+        if self.t2 != self.t1 and self.q1 is not None:
+            return ((self.q2 - self.q1) / (self.t2 - self.t1))[:, self.nd:]
+        return None
+
+    # ---- first derivatives (midpointvi.py:337-420): getters return [B, out, wrt] ---------------------
+    def _calc_deriv1(self):
+        if self._lin is None:
+            assert self.q1 is not None and self.p1 is not None, "derivatives need the state before the step"
+            out = self.sys.linearize(self.q1, self.p1, self.u1, self.q2[:, self.nd:], t1=self.t1, t2=self.t2,
+                                     q2_guess=self.q2[:, :self.nd], lambda_guess=self.lambda1 if self.nc else None,
+                                     want_raw=True, tolerance=self.tolerance)
+            self._check(out["status"])
+            self._lin = out
+        return self._lin
+
+    def _get(self, name):
+        return np.ascontiguousarray(np.swapaxes(self._calc_deriv1()[name], 1, 2))
+
+    def q2_dq1(self): return self._get("q2_dq1")
+    def q2_dp1(self): return self._get("q2_dp1")
+    def q2_du1(self): return self._get("q2_du1")
+    def q2_dk2(self): return self._get("q2_dk2")
+    def p2_dq1(self): return self._get("p2_dq1")
+    def p2_dp1(self): return self._get("p2_dp1")
+    def p2_du1(self): return self._get("p2_du1")
+    def p2_dk2(self): return self._get("p2_dk2")
+    def lambda1_dq1(self): return self._get("l1_dq1")
+    def lambda1_dp1(self): return self._get("l1_dp1")
+    def lambda1_du1(self): return self._get("l1_du1")
+    def lambda1_dk2(self): return self._get("l1_dk2")
