@@ -17,6 +17,8 @@
  *                            q1<-q2, p1<-p2, kinematic part of q2 <- k2, Newton start = q1.
  *   trepb_calc_p2_batch*     _MidpointVI.calc_p2 (trep/_trep/midpointvi.c:491-504,2702-2708),
  *                            i.e. MidpointVI.initialize_from_configs (midpointvi.py:155-172).
+ *   trepb_deriv2_batch*      _MidpointVI._calc_deriv2 (trep/_trep/midpointvi.c:2516-2545): the
+ *                            second-derivative tensors q2/p2/lambda1 _d{q1,p1,u1,k2}d{q1,p1,u1,k2}.
  *   trepb_linearize_batch*   DSystem.set + fdx + fdu for every k of
  *                            DSystem.linearize_trajectory (trep/discopt/dsystem.py:229-250,
  *                            284-317, 406-423) == solve_DEL + MidpointVI_calc_deriv1
@@ -183,6 +185,23 @@ typedef struct trepb_lin_args {
 
 int trepb_linearize_batch(trepb_system* sys, const trepb_lin_args* args);
 int trepb_linearize_batch_dev(trepb_system* sys, const trepb_lin_args* args, void* stream);
+
+/* Second derivatives of the discrete flow: _MidpointVI._calc_deriv2 == MidpointVI_calc_deriv2
+ * (trep/_trep/midpointvi.c:2516-2545), after the same solve + first derivatives as
+ * trepb_linearize_batch (all of `lin`'s outputs stay optional).  Tensors use the reference's
+ * storage layout [B][wrt A][wrt B][output] (trep/_trep/trep.h:439-473, getters
+ * trep/midpointvi.py:366-731); same-type pairs are stored in full (both symmetric halves).
+ *   d2[10*which + kind]   which: 0 q2 (output = nd), 1 p2 (nd), 2 lambda1 (nc)
+ *                         kind : 0 q1q1  1 q1p1  2 q1u1  3 q1k2  4 p1p1  5 p1u1  6 p1k2
+ *                                7 u1u1  8 u1k2  9 k2k2          (q1: nq, p1: nd, u1: nu, k2: nk)
+ * Any entry may be NULL. */
+typedef struct trepb_d2_args {
+    trepb_lin_args lin;
+    double* d2[30];
+} trepb_d2_args;
+
+int trepb_deriv2_batch(trepb_system* sys, const trepb_d2_args* args);
+int trepb_deriv2_batch_dev(trepb_system* sys, const trepb_d2_args* args, void* stream);
 
 /* Device utilities so that a C host (no torch) can own HBM buffers. */
 int trepb_device_count(int* n);

@@ -5,7 +5,7 @@
 #include <string>
 #include <vector>
 #include "../include/trepb.h"
-#include "../trep_b200/csrc/trepb_math.cuh"
+#include "../trep_b200/csrc/trepb_kernels.cuh"
 #include "../trep_b200/csrc/trepb_pack.h"
 
 using namespace trepb;
@@ -102,5 +102,58 @@ int th_linearize(const trepb_sysdesc* d, double t1, double t2, double tol, int m
     o.l1_dq1 = raw[8]; o.l1_dp1 = raw[9]; o.l1_du1 = raw[10]; o.l1_dk2 = raw[11];
     o.A = A; o.B = B; o.es = 1;
     return deriv1(s, ws, t1, t2, o, true);  // same call sequence as lin_kernel
+}
+
+// Second derivatives through the same per-pair function the d2 kernel runs (trepb_d2.cuh), on the
+// host: solve + deriv1 (+ aux export), then every pair s <= t.  d2[30] as in trepb_d2_args.
+int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxit,
+              const double* q1, const double* p1, const double* u1, const double* k2,
+              const double* q2_guess, const double* lam_guess, double** d2) {
+    Host h;
+    if (!h.init(d)) return -100;
+    RtSys& s = h.sys;
+    WsStrided& ws = h.ws;
+    const int nd = s.nd, nk = s.nk, nq = nd + nk, nu = s.nu, nc = s.nc;
+    for (int i = 0; i < nq; ++i) { ws.q1(i) = q1[i]; ws.q2(i) = q1[i]; }
+    for (int i = 0; i < nd; ++i) { ws.p1(i) = p1[i]; if (q2_guess) ws.q2(i) = q2_guess[i]; }
+    for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
+    for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
+    for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
+    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    if (it < 0) return it;
+    std::vector<double> q2(nq), lam(nc + 1), uu(nu + 1);
+    for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
+    for (int c = 0; c < nc; ++c) lam[c] = ws.lam(c);
+    for (int i = 0; i < nu; ++i) uu[i] = u1[i];
+    const int cnt[4] = {nq, nd, nu, nk};
+    std::vector<double> qd[4], ld[4], pd[4];
+    for (int i = 0; i < 4; ++i) { qd[i].assign(cnt[i] * nd + 1, 0.0); pd[i].assign(cnt[i] * nd + 1, 0.0); ld[i].assign(cnt[i] * nc + 1, 0.0); }
+    Deriv1Out o;
+    o.q2_dq1 = qd[0].data(); o.q2_dp1 = qd[1].data(); o.q2_du1 = qd[2].data(); o.q2_dk2 = qd[3].data();
+    o.p2_dq1 = pd[0].data(); o.p2_dp1 = pd[1].data(); o.p2_du1 = pd[2].data(); o.p2_dk2 = pd[3].data();
+    o.l1_dq1 = ld[0].data(); o.l1_dp1 = ld[1].data(); o.l1_du1 = ld[2].data(); o.l1_dk2 = ld[3].data();
+    o.A = nullptr; o.B = nullptr; o.es = 1;
+    int rc = deriv1(s, ws, t1, t2, o, true);
+    if (rc) return rc;
+    AuxLayout al;
+    al.set(nd, nc);
+    std::vector<double> aux(al.size + 1);
+    export_aux(s, ws, aux.data());
+    // hyper-dual workspace
+    WsStridedT<HD> wh;
+    const int n = wh.layout(s.nf, nd, nk, nu, nc, true);
+    std::vector<HD> slab(n + 1);
+    wh.base = slab.data();
+    wh.stride = 1;
+    D2Params p;
+    p.batch = 1; p.nx = nq + nd + nu + nk; p.npairs = p.nx * (p.nx + 1) / 2;
+    p.t1s = t1; p.dts = t2 - t1; p.t1 = &t1; p.t2 = &t2;
+    p.q1 = q1; p.u1 = uu.data(); p.q2 = q2.data(); p.lam = lam.data();
+    for (int i = 0; i < 4; ++i) { p.q2_d[i] = qd[i].data(); p.l1_d[i] = ld[i].data(); }
+    p.aux = aux.data(); p.auxl = al; p.status = nullptr;
+    for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
+    for (int a = 0; a < p.nx; ++a)
+        for (int b = a; b < p.nx; ++b) deriv2_pair(s, wh, p, 0, a, b);
+    return 0;
 }
 }

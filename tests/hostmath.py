@@ -14,7 +14,8 @@ ROOT = os.path.dirname(HERE)
 SO = os.path.join(HERE, "_build", "libhostmath.so")
 SRC = os.path.join(HERE, "host_math_check.cc")
 DEPS = [SRC] + [os.path.join(ROOT, "trep_b200", "csrc", f)
-                for f in ("trepb_math.cuh", "trepb_sys.h", "trepb_ws.h", "trepb_pack.h")]
+                for f in ("trepb_math.cuh", "trepb_sys.h", "trepb_ws.h", "trepb_pack.h", "trepb_hd.h",
+                          "trepb_d2.cuh", "trepb_kernels.cuh")]
 
 _lib = None
 
@@ -26,7 +27,7 @@ def load():
     os.makedirs(os.path.dirname(SO), exist_ok=True)
     if not os.path.exists(SO) or any(os.path.getmtime(d) > os.path.getmtime(SO) for d in DEPS):
         subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-std=c++17", "-shared", "-fPIC",
-                               "-x", "c++", SRC, "-o", SO])
+                               "-I/usr/local/cuda/include", "-x", "c++", SRC, "-o", SO])
     _lib = C.CDLL(SO)
     return _lib
 
@@ -98,3 +99,30 @@ def linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1
     out.update(rc=rc, q2=q2, p2=p2, lambda1=lam[:desc.nc], iters=it.value, A=A,
                B=B[:, :desc.nU])
     return out
+
+
+D2_KINDS = ["dq1dq1", "dq1dp1", "dq1du1", "dq1dk2", "dp1dp1", "dp1du1", "dp1dk2", "du1du1", "du1dk2", "dk2dk2"]
+D2_WHICH = ["q2", "p2", "l1"]
+
+
+def deriv2(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200):
+    lib = load()
+    cd, keep = D.to_c(desc)
+    q1, p1, u1, k2 = _c(q1), _c(p1), _c(u1), _c(k2)
+    q2g = None if q2_guess is None else _c(q2_guess)
+    lg = None if lam_guess is None else _c(lam_guess)
+    cnt = {"dq1": desc.nq, "dp1": desc.nd, "du1": desc.nu, "dk2": desc.nk}
+    out, ptrs = {}, []
+    for w in D2_WHICH:
+        for kd in D2_KINDS:
+            sh = (cnt[kd[:3]], cnt[kd[3:]], desc.nc if w == "l1" else desc.nd)
+            buf = np.zeros(max(int(np.prod(sh)), 1))
+            out[w + "_" + kd] = (buf, sh)
+            ptrs.append(_dp(buf))
+    arr = (C.POINTER(C.c_double) * 30)(*ptrs)
+    lib.th_deriv2.restype = C.c_int
+    rc = lib.th_deriv2(C.byref(cd), C.c_double(t1), C.c_double(t2), C.c_double(tol), C.c_int(maxit),
+                       _dp(q1), _dp(p1), _dp(u1), _dp(k2), _dp(q2g), _dp(lg), arr)
+    res = {n: b[:int(np.prod(sh))].reshape(sh) for n, (b, sh) in out.items()}
+    res["rc"] = rc
+    return res

@@ -223,3 +223,52 @@ def test_full_size_properties(lib):
     G.assert_close(b2["p2"], a["p2"][:4096], "split rollout p", rtol=1e-12)
     assert np.array_equal(b1["iters"] + b2["iters"], a["iters"][:4096]) or \
         np.mean(b1["iters"] + b2["iters"] != a["iters"][:4096]) < 1e-3
+
+
+D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"]
+
+
+@pytest.mark.parametrize("name", D2_SYSTEMS)
+def test_golden_second_derivatives(lib, name):
+    """Every second-derivative tensor against the reference's _calc_deriv2 (golden cases)."""
+    g = G.golden(name)
+    for label, s in _systems(lib, name):
+        out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                       t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
+        assert np.all(out["status"] == 0)
+        G.assert_close(out["A"], g["case_A"], "%s[%s] A" % (name, label))
+        for n in s.d2_shapes(1):
+            G.assert_close(out[n], g["case_" + n], "%s[%s] %s" % (name, label, n))
+
+
+def test_puppet_second_derivatives(lib):
+    """Marionette (nd 22, nk 18, nc 6): all 30 tensors of one golden case (1.76 MB of doubles)."""
+    g = G.golden("puppet")
+    g2 = np.load(os.path.join(G.GOLD, "puppet_deriv2.npz"))
+    c = int(g2["case_index"][0])
+    s = lib.System(G.desc("puppet"))
+    sl = slice(c, c + 1)
+    out = s.deriv2(g["case_q1"][sl], g["case_p1"][sl], None, g["case_k2"][sl], t1=g["case_t1"][sl],
+                   t2=g["case_t2"][sl], q2_guess=g["case_q2_guess"][sl], lambda_guess=g["case_lambda_guess"][sl])
+    assert out["status"][0] == 0
+    for n in s.d2_shapes(1):
+        G.assert_close(out[n], g2["case_" + n], "puppet " + n)
+
+
+def test_second_derivatives_by_finite_differences_where_the_reference_has_none(lib):
+    """dual_pendulums: the reference cannot run _calc_deriv2 here (LinearSpring has no C V_dqdqdq,
+    potentials/linearspring.c); the tensors are checked against central differences of this
+    library's own first derivatives instead."""
+    s = lib.System(G.desc("dual_pendulums"))
+    rng = np.random.default_rng(11)
+    q1 = rng.uniform(-1, 1, (1, 2)); p1 = rng.normal(0, 1, (1, 2))
+    out = s.deriv2(q1, p1, t1=0.0, dt=0.01)
+    eps = 1e-6
+    for a in range(2):
+        dq = np.zeros((1, 2)); dq[0, a] = eps
+        lp = s.linearize(q1 + dq, p1, t1=0.0, dt=0.01, want_raw=True, tolerance=1e-13)
+        lm = s.linearize(q1 - dq, p1, t1=0.0, dt=0.01, want_raw=True, tolerance=1e-13)
+        fd = (lp["q2_dq1"] - lm["q2_dq1"]) / (2 * eps)      # [1][b][out] = d/dq1_a of q2_dq1[b][out]
+        assert np.max(np.abs(fd[0] - out["q2_dq1dq1"][0, a])) < 2e-6 * max(1.0, np.max(np.abs(fd)))
+        fd = (lp["p2_dp1"] - lm["p2_dp1"]) / (2 * eps)
+        assert np.max(np.abs(fd[0] - out["p2_dq1dp1"][0, a])) < 2e-6 * max(1.0, np.max(np.abs(fd)))

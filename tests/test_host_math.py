@@ -63,3 +63,39 @@ def test_puppet_rollout():
     G.assert_close(p2, g["roll_p"][-1], "puppet final p", rtol=1e-8)
     G.assert_close(lam, g["roll_lambda"][-1], "puppet final lambda", rtol=1e-8)
     assert iters == int(g["roll_iters"].sum())
+
+
+D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"]
+
+
+@pytest.mark.parametrize("name", D2_SYSTEMS)
+def test_second_derivatives(name):
+    """Hyper-dual second derivatives (the per-pair function of the d2 kernel) against the
+    reference's _calc_deriv2 tensors."""
+    g = G.golden(name)
+    d = G.desc(name)
+    for c in range(min(4, g["case_q1"].shape[0])):
+        out = H.deriv2(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c],
+                       g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
+                       lam_guess=g["case_lambda_guess"][c])
+        assert out["rc"] == 0
+        for w in H.D2_WHICH:
+            for kd in H.D2_KINDS:
+                n = w + "_" + kd
+                G.assert_close(out[n], g["case_" + n][c], "%s case %d %s" % (name, c, n))
+
+
+def test_puppet_second_derivatives():
+    import os
+    g = G.golden("puppet")
+    g2 = np.load(os.path.join(G.GOLD, "puppet_deriv2.npz"))
+    c = int(g2["case_index"][0])
+    d = G.desc("puppet")
+    out = H.deriv2(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c],
+                   g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
+                   lam_guess=g["case_lambda_guess"][c])
+    assert out["rc"] == 0
+    for w in H.D2_WHICH:
+        for kd in H.D2_KINDS:
+            n = w + "_" + kd
+            G.assert_close(out[n], g2["case_" + n][0], "puppet " + n)

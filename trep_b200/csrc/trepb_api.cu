@@ -61,8 +61,14 @@ struct trepb_system {
     WsStrided wsl;               // layout (base filled per launch)
     int ws_doubles = 0;
     DevBuf ws;
+    // second-derivative path: hyper-dual workspace slab + deriv1 scratch (raw arrays, aux, q2, lambda)
+    WsStridedT<HD> wsl_hd;
+    int ws_hd_elems = 0;
+    DevBuf ws_hd;
+    DevBuf d2s[12];
+    int bps_d2 = 1;
     // staging for the host-pointer entry points
-    DevBuf hb[32];
+    DevBuf hb[64];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     std::mutex mu;       // serialises launches on this handle
@@ -130,6 +136,12 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         CUS(s->ks->occupancy(w, s->block, base_smem, &b, nullptr));
         s->bps[w] = b > 0 ? b : 1;
     }
+    s->ws_hd_elems = s->wsl_hd.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, true);
+    {
+        int b = 0;
+        CUS(s->ks->d2_occupancy(s->block, base_smem, &b, nullptr));
+        s->bps_d2 = b > 0 ? b : 1;
+    }
     if (s->ks->specialized) {
         const int nq = ps.nd + ps.nk, nX = 2 * nq, nU = ps.nu + ps.nk;
         const size_t st = (size_t)(nX * nX + nX * nU) * sizeof(double) * s->block;
@@ -151,6 +163,8 @@ void trepb_system_destroy(trepb_system* s) {
     cudaSetDevice(s->device);
     if (s->dblob) cudaFree(s->dblob);
     s->ws.release();
+    s->ws_hd.release();
+    for (auto& b : s->d2s) b.release();
     for (auto& b : s->hb) b.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
@@ -292,8 +306,11 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
     return TREPB_OK;
 }
 
-int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* stream) {
-    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+}  // extern "C"
+
+namespace {
+// validates + launches the linearize kernel; the caller holds s->mu
+int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, double* aux, int aux_size) {
     const RtSys& ps = s->P.proto;
     if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
     if (!a->q1 || !a->p1 || !a->status) return fail(TREPB_ERR_INVALID, "q1, p1 and status are required");
@@ -301,7 +318,6 @@ int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* st
     if (ps.nu > 0 && !a->u1) return fail(TREPB_ERR_INVALID, "u1 is required for a system with inputs");
     if (!a->t2 && !(a->dt_scalar != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
     if (a->batch == 0) return TREPB_OK;
-    std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->device));
     LinParams p;
     p.batch = a->batch; p.max_it = a->max_iterations; p.tol = a->tolerance;
@@ -313,11 +329,12 @@ int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* st
     double* raw[12] = {a->q2_dq1, a->q2_dp1, a->q2_du1, a->q2_dk2, a->p2_dq1, a->p2_dp1, a->p2_du1, a->p2_dk2,
                        a->l1_dq1, a->l1_dp1, a->l1_du1, a->l1_dk2};
     for (int i = 0; i < 12; ++i) p.raw[i] = raw[i];
+    p.aux = aux; p.aux_size = aux_size;
     const bool stage = s->lin_stage_bytes > 0 && (p.A || p.B);
     p.stage = stage ? 1 : 0;
     LaunchCfg c;
     const size_t smem = s->ks->specialized ? (stage ? s->lin_stage_bytes : 0) : (size_t)s->blob_bytes;
-    int rc = make_cfg(s, 2, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, (cudaStream_t)stream, &c);
+    int rc = make_cfg(s, 2, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, stream, &c);
     if (rc) return rc;
     if (stage) {
         // persistent-style grid: the staged kernel loops with a warp-uniform bound
@@ -326,6 +343,86 @@ int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* st
     }
     Timed t(s, c.stream);
     CU(s->ks->lin(c, p));
+    return TREPB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* stream) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> lk(s->mu);
+    return lin_launch(s, a, (cudaStream_t)stream, nullptr, 0);
+}
+
+int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream_) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    const RtSys& ps = s->P.proto;
+    const int nd = ps.nd, nk = ps.nk, nq = nd + nk, nu = ps.nu, nc = ps.nc;
+    const long long B = a->lin.batch;
+    if (B < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    if (B == 0) return TREPB_OK;
+    cudaStream_t stream = (cudaStream_t)stream_;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    // deriv1 products this kernel consumes: use the caller's arrays where given, scratch otherwise
+    trepb_lin_args la = a->lin;
+    const size_t cnt[4] = {(size_t)nq, (size_t)nd, (size_t)nu, (size_t)nk};
+    double** qd[4] = {&la.q2_dq1, &la.q2_dp1, &la.q2_du1, &la.q2_dk2};
+    double** ld[4] = {&la.l1_dq1, &la.l1_dp1, &la.l1_du1, &la.l1_dk2};
+    int k = 0;
+    for (int i = 0; i < 4; ++i) {
+        if (!*qd[i]) { CU(s->d2s[k].ensure((size_t)B * cnt[i] * nd * sizeof(double) + 8)); *qd[i] = (double*)s->d2s[k].p; }
+        ++k;
+        if (!*ld[i]) { CU(s->d2s[k].ensure((size_t)B * cnt[i] * nc * sizeof(double) + 8)); *ld[i] = (double*)s->d2s[k].p; }
+        ++k;
+    }
+    if (!la.q2) { CU(s->d2s[k].ensure((size_t)B * nq * sizeof(double))); la.q2 = (double*)s->d2s[k].p; }
+    ++k;
+    if (nc && !la.lambda1) { CU(s->d2s[k].ensure((size_t)B * nc * sizeof(double))); la.lambda1 = (double*)s->d2s[k].p; }
+    ++k;
+    AuxLayout al;
+    al.set(nd, nc);
+    CU(s->d2s[k].ensure((size_t)B * al.size * sizeof(double)));
+    double* aux = (double*)s->d2s[k].p;
+    int rc = lin_launch(s, &la, stream, aux, al.size);
+    if (rc) return rc;
+    // ---- second-derivative kernel: one thread per (instance, pair)
+    D2Params p;
+    p.batch = B;
+    p.nx = nq + nd + nu + nk;
+    p.npairs = p.nx * (p.nx + 1) / 2;
+    p.t1s = la.t1_scalar; p.dts = la.dt_scalar; p.t1 = la.t1; p.t2 = la.t2;
+    p.q1 = la.q1; p.u1 = la.u1; p.q2 = la.q2; p.lam = la.lambda1;
+    for (int i = 0; i < 4; ++i) { p.q2_d[i] = *qd[i]; p.l1_d[i] = *ld[i]; }
+    p.aux = aux; p.auxl = al; p.status = la.status;
+    for (int w = 0; w < 3; ++w)
+        for (int kd = 0; kd < 10; ++kd) p.out[w][kd] = a->d2[10 * w + kd];
+    if (nc == 0) for (int kd = 0; kd < 10; ++kd) p.out[2][kd] = nullptr;
+    const long long threads = B * (long long)p.npairs;
+    int block = s->block;
+    const size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
+    long long grid = (threads + block - 1) / block;
+    WsStridedT<HD> w = s->wsl_hd;
+    w.base = nullptr; w.stride = 0;
+    if (!s->ks->specialized) {
+        long long resident = (long long)s->sms * s->bps_d2;
+        if (grid > resident) grid = resident;
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t per_cta = (size_t)s->ws_hd_elems * sizeof(HD) * block;
+        const size_t budget = (free_b + s->ws_hd.cap) / 4;
+        if ((size_t)grid * per_cta > budget) grid = (long long)(budget / per_cta);
+        if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the second-derivative workspace");
+        CU(s->ws_hd.ensure((size_t)grid * per_cta));
+        w.base = (HD*)s->ws_hd.p;
+    } else if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
+    LaunchCfg c;
+    c.grid = (int)grid; c.block = block; c.smem = smem; c.stream = stream;
+    c.sys = s->ks->specialized ? nullptr : &s->dview;
+    c.dblob = s->dblob; c.blob_bytes = s->blob_bytes; c.ws = s->wsl;
+    Timed t(s, stream);
+    CU(s->ks->d2(c, w, p));
     return TREPB_OK;
 }
 
@@ -385,7 +482,7 @@ namespace {
 struct Stager {
     trepb_system* s;
     int k = 0;
-    struct Out { void* host; void* dev; size_t bytes; } outs[24];
+    struct Out { void* host; void* dev; size_t bytes; } outs[64];
     int nout = 0;
     int err = 0;
     explicit Stager(trepb_system* s_) : s(s_) {}
@@ -459,28 +556,58 @@ int trepb_calc_p2_batch(trepb_system* s, int64_t batch, double dt, const double*
     return st.finish();
 }
 
+}  // extern "C"
+namespace {
+void stage_lin(Stager& st, const trepb_system* s, const trepb_lin_args* a, trepb_lin_args* d) {
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
+    const size_t nX = 2 * nq, nU = nu + nk;
+    *d = *a;
+    d->t1 = st.in(a->t1, B); d->t2 = st.in(a->t2, B);
+    d->q1 = st.in(a->q1, B * nq); d->p1 = st.in(a->p1, B * nd); d->u1 = st.in(a->u1, B * nu); d->k2 = st.in(a->k2, B * nk);
+    d->q2_guess = st.in(a->q2_guess, B * nd); d->lambda_guess = st.in(a->lambda_guess, B * nc);
+    d->q2 = st.out(a->q2, B * nq); d->p2 = st.out(a->p2, B * nd); d->lambda1 = st.out(a->lambda1, B * nc);
+    d->iters = st.out(a->iters, B); d->status = st.out(a->status, B);
+    d->A = st.out(a->A, B * nX * nX); d->B = st.out(a->B, B * nX * nU);
+    d->q2_dq1 = st.out(a->q2_dq1, B * nq * nd); d->q2_dp1 = st.out(a->q2_dp1, B * nd * nd);
+    d->q2_du1 = st.out(a->q2_du1, B * nu * nd); d->q2_dk2 = st.out(a->q2_dk2, B * nk * nd);
+    d->p2_dq1 = st.out(a->p2_dq1, B * nq * nd); d->p2_dp1 = st.out(a->p2_dp1, B * nd * nd);
+    d->p2_du1 = st.out(a->p2_du1, B * nu * nd); d->p2_dk2 = st.out(a->p2_dk2, B * nk * nd);
+    d->l1_dq1 = st.out(a->l1_dq1, B * nq * nc); d->l1_dp1 = st.out(a->l1_dp1, B * nd * nc);
+    d->l1_du1 = st.out(a->l1_du1, B * nu * nc); d->l1_dk2 = st.out(a->l1_dk2, B * nk * nc);
+}
+}  // namespace
+extern "C" {
+
+int trepb_deriv2_batch(trepb_system* s, const trepb_d2_args* a) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (a->lin.batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->lin.batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    trepb_d2_args d = *a;
+    stage_lin(st, s, &a->lin, &d.lin);
+    const size_t cnt[4] = {nq, nd, nu, nk};
+    static const int ka[10] = {0, 0, 0, 0, 1, 1, 1, 2, 2, 3}, kb[10] = {0, 1, 2, 3, 1, 2, 3, 2, 3, 3};
+    for (int w = 0; w < 3; ++w)
+        for (int kd = 0; kd < 10; ++kd)
+            d.d2[10 * w + kd] = st.out(a->d2[10 * w + kd], B * cnt[ka[kd]] * cnt[kb[kd]] * (w == 2 ? nc : nd));
+    if (st.err) return st.err;
+    int rc = trepb_deriv2_batch_dev(s, &d, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
 int trepb_linearize_batch(trepb_system* s, const trepb_lin_args* a) {
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
-    const RtSys& ps = s->P.proto;
-    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
-    const size_t nX = 2 * nq, nU = nu + nk;
     CU(cudaSetDevice(s->device));
     Stager st(s);
-    trepb_lin_args d = *a;
-    d.t1 = st.in(a->t1, B); d.t2 = st.in(a->t2, B);
-    d.q1 = st.in(a->q1, B * nq); d.p1 = st.in(a->p1, B * nd); d.u1 = st.in(a->u1, B * nu); d.k2 = st.in(a->k2, B * nk);
-    d.q2_guess = st.in(a->q2_guess, B * nd); d.lambda_guess = st.in(a->lambda_guess, B * nc);
-    d.q2 = st.out(a->q2, B * nq); d.p2 = st.out(a->p2, B * nd); d.lambda1 = st.out(a->lambda1, B * nc);
-    d.iters = st.out(a->iters, B); d.status = st.out(a->status, B);
-    d.A = st.out(a->A, B * nX * nX); d.B = st.out(a->B, B * nX * nU);
-    d.q2_dq1 = st.out(a->q2_dq1, B * nq * nd); d.q2_dp1 = st.out(a->q2_dp1, B * nd * nd);
-    d.q2_du1 = st.out(a->q2_du1, B * nu * nd); d.q2_dk2 = st.out(a->q2_dk2, B * nk * nd);
-    d.p2_dq1 = st.out(a->p2_dq1, B * nq * nd); d.p2_dp1 = st.out(a->p2_dp1, B * nd * nd);
-    d.p2_du1 = st.out(a->p2_du1, B * nu * nd); d.p2_dk2 = st.out(a->p2_dk2, B * nk * nd);
-    d.l1_dq1 = st.out(a->l1_dq1, B * nq * nc); d.l1_dp1 = st.out(a->l1_dp1, B * nd * nc);
-    d.l1_du1 = st.out(a->l1_du1, B * nu * nc); d.l1_dk2 = st.out(a->l1_dk2, B * nk * nc);
+    trepb_lin_args d;
+    stage_lin(st, s, a, &d);
     if (st.err) return st.err;
     int rc = trepb_linearize_batch_dev(s, &d, nullptr);
     if (rc) return rc;

@@ -15,6 +15,8 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <type_traits>
+#include "trepb_hd.h"
 #include "trepb_math.cuh"
 
 namespace trepb {
@@ -48,7 +50,41 @@ struct LinParams {
     double *A, *B;
     double* raw[12];  // q2_dq1 q2_dp1 q2_du1 q2_dk2 p2_d* l1_d*
     int stage;        // 1: stage A/B through shared memory for coalesced stores
+    double* aux;      // [B][AuxLayout::size] factorizations for the second-derivative kernel, or null
+    int aux_size;
 };
+
+// per-instance data exported by the linearize kernel for this kernel
+struct AuxLayout {
+    int o_m2, o_m2p, o_pj, o_pjp, o_dh1, o_dh2, o_t22, size;
+    TREPB_HD void set(int nd, int nc) {
+        int o = 0;
+        o_m2 = o; o += nd * nd;
+        o_m2p = o; o += nd;
+        o_pj = o; o += nc * nc;
+        o_pjp = o; o += nc;
+        o_dh1 = o; o += nc * nd;
+        o_dh2 = o; o += nc * nd;
+        o_t22 = o; o += nd * nd;
+        size = o;
+    }
+};
+
+struct D2Params {
+    long long batch;
+    int nx, npairs;
+    double t1s, dts;
+    const double *t1, *t2;
+    const double *q1, *u1;          // inputs of the step            [B][nq], [B][nu]
+    const double *q2, *lam;         // converged step                [B][nq], [B][nc]
+    const double* q2_d[4];          // deriv1, [B][wrt][nd]   (dq1, dp1, du1, dk2)
+    const double* l1_d[4];          // deriv1, [B][wrt][nc]
+    const double* aux;              // [B][aux.size]
+    AuxLayout auxl;
+    const int* status;              // instances whose step/deriv1 failed are skipped
+    double* out[3][10];             // q2 / p2 / l1  x  pair kind ; any may be null
+};
+
 
 // What a kernel launch needs besides its parameters.
 struct LaunchCfg {
@@ -76,7 +112,37 @@ struct KernelSet {
     cudaError_t (*lin)(const LaunchCfg&, const LinParams&);
     // which: 0 step, 1 p2, 2 lin.  blocks_per_sm at (block, smem).
     cudaError_t (*occupancy)(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
+    cudaError_t (*d2)(const LaunchCfg&, const WsStridedT<HD>&, const D2Params&);
+    cudaError_t (*d2_occupancy)(int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
 };
+
+// factorizations and tables of deriv1 that the second-derivative kernel reuses (AuxLayout)
+template <class Sys, class Ws>
+TREPB_HD void export_aux(const Sys& sys, Ws& ws, double* ax) {
+    const int nd = sys.ND(), nc = sys.NC();
+    AuxLayout al;
+    al.set(nd, nc);
+    TREPB_UNROLL_SYS
+    for (int i = 0; i < nd; ++i) {
+        ax[al.o_m2p + i] = ws.M2p(i);
+        TREPB_UNROLL_SYS
+        for (int j = 0; j < nd; ++j) {
+            ax[al.o_m2 + i * nd + j] = ws.M2(i, j);
+            ax[al.o_t22 + i * nd + j] = ws.T22(i, j);
+        }
+    }
+    TREPB_UNROLL_SYS
+    for (int cc = 0; cc < nc; ++cc) {
+        ax[al.o_pjp + cc] = ws.PJp(cc);
+        TREPB_UNROLL_SYS
+        for (int c2 = 0; c2 < nc; ++c2) ax[al.o_pj + cc * nc + c2] = ws.PJ(cc, c2);
+        TREPB_UNROLL_SYS
+        for (int j = 0; j < nd; ++j) {
+            ax[al.o_dh1 + cc * nd + j] = ws.Dh1(cc, j);
+            ax[al.o_dh2 + cc * nd + j] = ws.Dh2(cc, j);
+        }
+    }
+}
 
 // registry of ahead-of-time specialised systems (filled by static initialisers of gen/*.cu)
 struct SpecRegistry {
@@ -290,6 +356,7 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
             const int r = deriv1(sys, ws, t1, t2, o, true);
             if (r < 0) status = r;
         }
+        if (live && status == ST_OK && p.aux) export_aux(sys, ws, p.aux + b * (long)p.aux_size);
         if (live) {
             if (p.iters) p.iters[b] = it;
             p.status[b] = status;
@@ -367,6 +434,12 @@ struct Launchers {
     }
 };
 
+#endif  // __CUDACC__
+}  // namespace trepb
+#include "trepb_d2.cuh"
+namespace trepb {
+#if defined(__CUDACC__)
+
 template <class Sys>
 KernelSet make_kernelset(const char* name, unsigned long long hash, int specialized, int nX, int nU) {
     KernelSet k;
@@ -375,6 +448,8 @@ KernelSet make_kernelset(const char* name, unsigned long long hash, int speciali
     k.p2 = &Launchers<Sys>::p2;
     k.lin = &Launchers<Sys>::lin;
     k.occupancy = &Launchers<Sys>::occupancy;
+    k.d2 = &LaunchersD2<Sys>::run;
+    k.d2_occupancy = &LaunchersD2<Sys>::occupancy;
     return k;
 }
 #endif  // __CUDACC__

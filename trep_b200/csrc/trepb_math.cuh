@@ -69,23 +69,28 @@ TREPB_HD Axis axis_of(int kind) {
 TREPB_HD int symi(int r, int s) {  // index into (00,11,22,01,02,12)
     return r == s ? r : (r + s + 2);
 }
-TREPB_HD void cross3(const double* x, const double* y, double* o) {
+template <class T>
+TREPB_HD void cross3(const T* x, const T* y, T* o) {
     o[0] = x[1] * y[2] - x[2] * y[1];
     o[1] = x[2] * y[0] - x[0] * y[2];
     o[2] = x[0] * y[1] - x[1] * y[0];
 }
-TREPB_HD double dot3(const double* x, const double* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; }
-TREPB_HD double dot6(const double* x, const double* y) {
+template <class T>
+TREPB_HD T dot3(const T* x, const T* y) { return x[0] * y[0] + x[1] * y[1] + x[2] * y[2]; }
+template <class T>
+TREPB_HD T dot6(const T* x, const T* y) {
     return x[0] * y[0] + x[1] * y[1] + x[2] * y[2] + x[3] * y[3] + x[4] * y[4] + x[5] * y[5];
 }
 // planar rotation of components (b,c):  R^T x  (parent->child)  and  R x  (child->parent)
-TREPB_HD void rotT(double* x, int b, int c, double cs, double sn) {
-    double xb = x[b], xc = x[c];
+template <class T>
+TREPB_HD void rotT(T* x, int b, int c, T cs, T sn) {
+    T xb = x[b], xc = x[c];
     x[b] = cs * xb + sn * xc;
     x[c] = -sn * xb + cs * xc;
 }
-TREPB_HD void rotF(double* x, int b, int c, double cs, double sn) {
-    double xb = x[b], xc = x[c];
+template <class T>
+TREPB_HD void rotF(T* x, int b, int c, T cs, T sn) {
+    T xb = x[b], xc = x[c];
     x[b] = cs * xb - sn * xc;
     x[c] = sn * xb + cs * xc;
 }
@@ -97,6 +102,8 @@ TREPB_HD void sincos_(double x, double* s, double* c) {
     *c = cos(x);
 #endif
 }
+TREPB_HD bool isnan_(double x) { return isnan(x); }
+TREPB_HD double sqrt_(double x) { return sqrt(x); }
 
 // ---------------------------------------------------------------------------------------------
 // pass 1: root -> leaf.  Inputs ws.qe (evaluation configuration) and ws.dq.
@@ -105,14 +112,15 @@ TREPB_HD void sincos_(double x, double* s, double* c) {
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
+    using Real = typename Ws::Real;
     TREPB_UNROLL_SYS
     for (int f = 1; f < sys.NF(); ++f) {
         const int par = sys.parent(f), kind = sys.kind(f), cfg = sys.config(f);
         const bool vel = with_vel && sys.mass_below(f);
         const bool wrl = with_world && sys.need_world(f);
         if (!vel && !wrl) continue;
-        const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
-        double g[3], V[6], R[9], p[3];
+        const Real x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+        Real g[3], V[6], R[9], p[3];
         if (vel) {
             if (par == 0) {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = sys.gravity(k);
@@ -132,13 +140,13 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
             }
         }
         if (kind == K_CONST_SE3) {
-            double lR[9], lp[3];
+            Real lR[9], lp[3];
             TREPB_UNROLL for (int r = 0; r < 3; ++r) {
                 TREPB_UNROLL for (int c = 0; c < 3; ++c) lR[r * 3 + c] = sys.se3(f, r * 4 + c);
                 lp[r] = sys.se3(f, r * 4 + 3);
             }
             if (vel) {
-                double t[3], u[3];
+                Real t[3], u[3];
                 // v' = R^T (v + w x p), w' = R^T w, g' = R^T g
                 cross3(V + 3, lp, t);
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) t[k] += V[k];
@@ -149,7 +157,7 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = u[k];
             }
             if (wrl) {
-                double Rn[9];
+                Real Rn[9];
                 TREPB_UNROLL for (int r = 0; r < 3; ++r) {
                     p[r] += R[r * 3] * lp[0] + R[r * 3 + 1] * lp[1] + R[r * 3 + 2] * lp[2];
                 }
@@ -161,7 +169,7 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
         } else {
             const Axis ax = axis_of(kind);
             if (ax.rot) {
-                double sn, cs;
+                Real sn, cs;
                 sincos_(x, &sn, &cs);
                 if (vel) {
                     // kept for pass 2 (force transforms); world-only passes at q1/q2 must not
@@ -174,7 +182,7 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
                 }
                 if (wrl) {
                     TREPB_UNROLL for (int r = 0; r < 3; ++r) {
-                        double rb = R[r * 3 + ax.b], rc = R[r * 3 + ax.c];
+                        Real rb = R[r * 3 + ax.b], rc = R[r * 3 + ax.c];
                         R[r * 3 + ax.b] = cs * rb + sn * rc;
                         R[r * 3 + ax.c] = -sn * rb + cs * rc;
                     }
@@ -191,7 +199,7 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
             }
             if (vel && cfg >= 0) {
                 // W = [S, s] with S the velocity carried in from the parent
-                double W[6];
+                Real W[6];
                 TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = 0.0;
                 if (ax.rot) {
                     W[ax.b] = V[ax.c];          // v_S x e_a
@@ -220,10 +228,11 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
 
 // force-vector transform child -> parent through frame f:  f' = R f, n' = R n + p x (R f)
 template <class Sys, class Ws>
-TREPB_HD void force_up(const Sys& sys, Ws& ws, int f, double* F) {
+TREPB_HD void force_up(const Sys& sys, Ws& ws, int f, typename Ws::Real* F) {
+    using Real = typename Ws::Real;
     const int kind = sys.kind(f);
     if (kind == K_CONST_SE3) {
-        double a[3], b[3], lp[3], t[3];
+        Real a[3], b[3], lp[3], t[3];
         TREPB_UNROLL for (int r = 0; r < 3; ++r) {
             a[r] = sys.se3(f, r * 4) * F[0] + sys.se3(f, r * 4 + 1) * F[1] + sys.se3(f, r * 4 + 2) * F[2];
             b[r] = sys.se3(f, r * 4) * F[3] + sys.se3(f, r * 4 + 1) * F[4] + sys.se3(f, r * 4 + 2) * F[5];
@@ -234,12 +243,12 @@ TREPB_HD void force_up(const Sys& sys, Ws& ws, int f, double* F) {
     } else {
         const Axis ax = axis_of(kind);
         if (ax.rot) {
-            const double cs = ws.cs(f, 0), sn = ws.cs(f, 1);
+            const Real cs = ws.cs(f, 0), sn = ws.cs(f, 1);
             rotF(F, ax.b, ax.c, cs, sn);
             rotF(F + 3, ax.b, ax.c, cs, sn);
         } else {
             const int cfg = sys.config(f);
-            const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+            const Real x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
             F[3 + ax.b] -= x * F[ax.c];
             F[3 + ax.c] += x * F[ax.b];
         }
@@ -247,10 +256,11 @@ TREPB_HD void force_up(const Sys& sys, Ws& ws, int f, double* F) {
 }
 // free-vector transform child -> parent
 template <class Sys, class Ws>
-TREPB_HD void vec_up(const Sys& sys, Ws& ws, int f, double* N) {
+TREPB_HD void vec_up(const Sys& sys, Ws& ws, int f, typename Ws::Real* N) {
+    using Real = typename Ws::Real;
     const int kind = sys.kind(f);
     if (kind == K_CONST_SE3) {
-        double a[3];
+        Real a[3];
         TREPB_UNROLL for (int r = 0; r < 3; ++r)
             a[r] = sys.se3(f, r * 4) * N[0] + sys.se3(f, r * 4 + 1) * N[1] + sys.se3(f, r * 4 + 2) * N[2];
         TREPB_UNROLL for (int k = 0; k < 3; ++k) N[k] = a[k];
@@ -261,8 +271,9 @@ TREPB_HD void vec_up(const Sys& sys, Ws& ws, int f, double* N) {
 }
 
 // (f, n) = I (v, w) for I = (m, h, Isym6):  f = m v + w x h ,  n = Ibar w + h x v
-TREPB_HD void inertia_apply(double m, const double* h, const double* I, const double* X, double* F) {
-    double t[3];
+template <class Real>
+TREPB_HD void inertia_apply(Real m, const Real* h, const Real* I, const Real* X, Real* F) {
+    Real t[3];
     cross3(X + 3, h, t);
     TREPB_UNROLL for (int k = 0; k < 3; ++k) F[k] = m * X[k] + t[k];
     cross3(h, X, t);
@@ -277,6 +288,7 @@ TREPB_HD void inertia_apply(double m, const double* h, const double* I, const do
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
+    using Real = typename Ws::Real;
     const int nq = sys.NQ();
     TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) {
         ws.Lq(i) = 0.0;
@@ -316,22 +328,22 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
     for (int f = sys.NF() - 1; f >= 1; --f) {
         if (!sys.mass_below(f)) continue;
         const int kind = sys.kind(f), cfg = sys.config(f), par = sys.parent(f);
-        double m = ws.Im(f), h[3], I[6], mu[6], g[3];
+        Real m = ws.Im(f), h[3], I[6], mu[6], g[3];
         TREPB_UNROLL for (int k = 0; k < 3; ++k) { h[k] = ws.Ih(f, k); g[k] = ws.gf(f, k); }
         TREPB_UNROLL for (int k = 0; k < 6; ++k) mu[k] = ws.mu(f, k);
         if (order >= 2) { TREPB_UNROLL for (int k = 0; k < 6; ++k) I[k] = ws.II(f, k); }
 
         if (cfg >= 0) {
             const Axis ax = axis_of(kind);
-            double W[6];
+            Real W[6];
             TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = ws.W(f, k);
             // first order: L_ddq = s.mu ; L_dq = W.mu + g.(m v_s + w_s x h)
-            double hxg[3];
+            Real hxg[3];
             cross3(h, g, hxg);
             ws.Lv(cfg) = ax.rot ? mu[3 + ax.a] : mu[ax.a];
             ws.Lq(cfg) = dot6(W, mu) + (sys.gravity_on() ? (ax.rot ? hxg[ax.a] : m * g[ax.a]) : 0.0);
             if (order >= 2) {
-                double H[6], G[6], N[3], P[3], t[3];
+                Real H[6], G[6], N[3], P[3], t[3];
                 // H = Ic s
                 TREPB_UNROLL for (int k = 0; k < 6; ++k) H[k] = 0.0;
                 if (ax.rot) {
@@ -373,11 +385,11 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                     const int ci = sys.config(cur);
                     if (ci >= 0) {
                         const Axis ai = axis_of(sys.kind(cur));
-                        const double sH = ai.rot ? H[3 + ai.a] : H[ai.a];
-                        const double sG = ai.rot ? G[3 + ai.a] : G[ai.a];
-                        double Wi[6];
+                        const Real sH = ai.rot ? H[3 + ai.a] : H[ai.a];
+                        const Real sG = ai.rot ? G[3 + ai.a] : G[ai.a];
+                        Real Wi[6];
                         TREPB_UNROLL for (int k = 0; k < 6; ++k) Wi[k] = ws.W(cur, k);
-                        double WG = dot6(Wi, G);
+                        Real WG = dot6(Wi, G);
                         if (sys.gravity_on() && ai.rot) WG += N[ai.a];
                         if (ci == cfg) {
                             ws.Lvv(cfg, cfg) = sH;
@@ -406,7 +418,7 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
         force_up(sys, ws, f, mu);
         TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.mu(par, k) += mu[k];
         if (kind == K_CONST_SE3) {
-            double R[9], lp[3], hr[3];
+            Real R[9], lp[3], hr[3];
             TREPB_UNROLL for (int r = 0; r < 3; ++r) {
                 TREPB_UNROLL for (int c = 0; c < 3; ++c) R[r * 3 + c] = sys.se3(f, r * 4 + c);
                 lp[r] = sys.se3(f, r * 4 + 3);
@@ -414,16 +426,16 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
             TREPB_UNROLL for (int r = 0; r < 3; ++r) hr[r] = R[r * 3] * h[0] + R[r * 3 + 1] * h[1] + R[r * 3 + 2] * h[2];
             if (order >= 2) {
                 // Ibar' = R Ibar R^T + 2(hr.p)1 - hr p^T - p hr^T + m(|p|^2 1 - p p^T)
-                double M[9], T[9];
+                Real M[9], T[9];
                 M[0] = I[0]; M[4] = I[1]; M[8] = I[2];
                 M[1] = M[3] = I[3]; M[2] = M[6] = I[4]; M[5] = M[7] = I[5];
                 TREPB_UNROLL for (int r = 0; r < 3; ++r)
                     TREPB_UNROLL for (int c = 0; c < 3; ++c)
                         T[r * 3 + c] = R[r * 3] * M[c] + R[r * 3 + 1] * M[3 + c] + R[r * 3 + 2] * M[6 + c];
-                const double hp = dot3(hr, lp), pp = dot3(lp, lp);
+                const Real hp = dot3(hr, lp), pp = dot3(lp, lp);
                 TREPB_UNROLL for (int r = 0; r < 3; ++r)
                     TREPB_UNROLL for (int c = r; c < 3; ++c) {
-                        double v = T[r * 3] * R[c * 3] + T[r * 3 + 1] * R[c * 3 + 1] + T[r * 3 + 2] * R[c * 3 + 2];
+                        Real v = T[r * 3] * R[c * 3] + T[r * 3 + 1] * R[c * 3 + 1] + T[r * 3 + 2] * R[c * 3 + 2];
                         v += -hr[r] * lp[c] - lp[r] * hr[c] - m * lp[r] * lp[c];
                         if (r == c) v += 2.0 * hp + m * pp;
                         ws.II(par, symi(r, c)) += v;
@@ -434,11 +446,11 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
         } else {
             const Axis ax = axis_of(kind);
             if (ax.rot) {
-                const double cs = ws.cs(f, 0), sn = ws.cs(f, 1);
+                const Real cs = ws.cs(f, 0), sn = ws.cs(f, 1);
                 if (order >= 2) {
                     const int iaa = symi(ax.a, ax.a), ibb = symi(ax.b, ax.b), icc = symi(ax.c, ax.c);
                     const int iab = symi(ax.a, ax.b), iac = symi(ax.a, ax.c), ibc = symi(ax.b, ax.c);
-                    const double c2 = cs * cs, s2 = sn * sn, sc = sn * cs;
+                    const Real c2 = cs * cs, s2 = sn * sn, sc = sn * cs;
                     ws.II(par, iaa) += I[iaa];
                     ws.II(par, iab) += cs * I[iab] - sn * I[iac];
                     ws.II(par, iac) += sn * I[iab] + cs * I[iac];
@@ -450,11 +462,11 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.Ih(par, k) += h[k];
                 ws.Im(par) += m;
             } else {
-                const double x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
+                const Real x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
                 if (order >= 2) {
                     const int ibb = symi(ax.b, ax.b), icc = symi(ax.c, ax.c);
                     const int iab = symi(ax.a, ax.b), iac = symi(ax.a, ax.c);
-                    const double d = 2.0 * h[ax.a] * x + m * x * x;
+                    const Real d = 2.0 * h[ax.a] * x + m * x * x;
                     TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.II(par, k) += I[k];
                     ws.II(par, ibb) += d;
                     ws.II(par, icc) += d;
@@ -473,7 +485,8 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
 // world-frame point kinematics
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
-TREPB_HD void joint_axis_w(const Sys& sys, Ws& ws, int j, double* aw, bool* rot, int* fj) {
+TREPB_HD void joint_axis_w(const Sys& sys, Ws& ws, int j, typename Ws::Real* aw, bool* rot, int* fj) {
+    using Real = typename Ws::Real;
     const int f = sys.cfg_frame(j);
     const Axis ax = axis_of(sys.kind(f));
     TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = ws.Rw(f, r * 3 + ax.a);
@@ -481,21 +494,23 @@ TREPB_HD void joint_axis_w(const Sys& sys, Ws& ws, int j, double* aw, bool* rot,
     *fj = f;
 }
 template <class Sys, class Ws>
-TREPB_HD void frame_pos(const Sys& sys, Ws& ws, int F, double* p) {
+TREPB_HD void frame_pos(const Sys& sys, Ws& ws, int F, typename Ws::Real* p) {
+    using Real = typename Ws::Real;
     if (F == 0) { p[0] = p[1] = p[2] = 0.0; }
     else { TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k] = ws.pw(F, k); }
 }
 // d p_F / d q_j   (zero when F does not depend on q_j; trep/_trep/frame.c:2247-2262)
 template <class Sys, class Ws>
-TREPB_HD void dpoint(const Sys& sys, Ws& ws, int F, int j, double* out) {
+TREPB_HD void dpoint(const Sys& sys, Ws& ws, int F, int j, typename Ws::Real* out) {
+    using Real = typename Ws::Real;
     out[0] = out[1] = out[2] = 0.0;
     if (F == 0 || sys.cfg_frame(j) < 0 || !sys.dep(F, j)) return;
-    double aw[3];
+    Real aw[3];
     bool rot;
     int fj;
     joint_axis_w(sys, ws, j, aw, &rot, &fj);
     if (rot) {
-        double r[3];
+        Real r[3];
         TREPB_UNROLL for (int k = 0; k < 3; ++k) r[k] = ws.pw(F, k) - ws.pw(fj, k);
         cross3(aw, r, out);
     } else {
@@ -504,14 +519,15 @@ TREPB_HD void dpoint(const Sys& sys, Ws& ws, int F, int j, double* out) {
 }
 // d2 p_F / d q_i d q_j
 template <class Sys, class Ws>
-TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, double* out) {
+TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, typename Ws::Real* out) {
+    using Real = typename Ws::Real;
     out[0] = out[1] = out[2] = 0.0;
     if (F == 0 || sys.cfg_frame(i) < 0 || sys.cfg_frame(j) < 0) return;
     if (!sys.dep(F, i) || !sys.dep(F, j)) return;
     // the upper joint's axis crosses the lower joint's first derivative
     int up = i, lo = j;
     if (!sys.dep(sys.cfg_frame(j), i)) { up = j; lo = i; }
-    double aw[3], d[3];
+    Real aw[3], d[3];
     bool rot;
     int fu;
     joint_axis_w(sys, ws, up, aw, &rot, &fu);
@@ -522,22 +538,24 @@ TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, double* out) 
 
 // v = pA - pB and dv_j = d(pA-pB)/dq_j for all configs into ws.dv
 template <class Sys, class Ws>
-TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, double* v) {
-    double pa[3], pb[3];
+TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, typename Ws::Real* v) {
+    using Real = typename Ws::Real;
+    Real pa[3], pb[3];
     frame_pos(sys, ws, A, pa);
     frame_pos(sys, ws, B, pb);
     TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
     TREPB_UNROLL_SYS
     for (int j = 0; j < sys.NQ(); ++j) {
-        double da[3], db[3];
+        Real da[3], db[3];
         dpoint(sys, ws, A, j, da);
         dpoint(sys, ws, B, j, db);
         TREPB_UNROLL for (int k = 0; k < 3; ++k) ws.dv(j, k) = da[k] - db[k];
     }
 }
 template <class Sys, class Ws>
-TREPB_HD void pair_second(const Sys& sys, Ws& ws, int A, int B, int i, int j, double* ddv) {
-    double a[3], b[3];
+TREPB_HD void pair_second(const Sys& sys, Ws& ws, int A, int B, int i, int j, typename Ws::Real* ddv) {
+    using Real = typename Ws::Real;
+    Real a[3], b[3];
     ddpoint(sys, ws, A, i, j, a);
     ddpoint(sys, ws, B, i, j, b);
     TREPB_UNROLL for (int k = 0; k < 3; ++k) ddv[k] = a[k] - b[k];
@@ -550,6 +568,7 @@ TREPB_HD void pair_second(const Sys& sys, Ws& ws, int A, int B, int i, int j, do
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
+    using Real = typename Ws::Real;
     const int nq = sys.NQ();
     if (mode & 4) {
         TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i)
@@ -559,15 +578,15 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
     for (int c = 0; c < sys.NC(); ++c) {
         const int kind = sys.con_kind(c);
         const int A = sys.con_i(c, 0), B = sys.con_i(c, 1), third = sys.con_i(c, 2);
-        double v[3];
+        Real v[3];
         pair_first(sys, ws, A, B, v);
         if (kind == C_DISTANCE) {
-            const double d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
+            const Real d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
             if (mode & 1) ws.hc(c) = dot3(v, v) - d * d;
             if (mode & 2) {
                 TREPB_UNROLL_SYS
                 for (int j = 0; j < nq; ++j) {
-                    double val = 0.0;
+                    Real val = 0.0;
                     if (sys.dep(A, j) || sys.dep(B, j) || third == j) {
                         val = v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2);
                         if (third == j) val -= d;
@@ -577,16 +596,16 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
                 }
             }
             if (mode & 4) {
-                const double lam = ws.lam(c);
+                const Real lam = ws.lam(c);
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i) {
                     if (!(sys.dep(A, i) || sys.dep(B, i) || third == i)) continue;
                     TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
                         if (!(sys.dep(A, j) || sys.dep(B, j) || third == j)) continue;
-                        double ddv[3];
+                        Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
-                        double val = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2)
+                        Real val = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2)
                                    + v[0] * ddv[0] + v[1] * ddv[1] + v[2] * ddv[2];
                         if (third == i && third == j) val -= 1.0;
                         val *= 2.0 * lam;
@@ -601,19 +620,19 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
             if (mode & 2) {
                 TREPB_UNROLL_SYS
                 for (int j = 0; j < nq; ++j) {
-                    const double val = ws.dv(j, comp);
+                    const Real val = ws.dv(j, comp);
                     if (which_dh == 1) ws.Dh1(c, j) = val; else ws.Dh2(c, j) = val;
                 }
             }
             if (mode & 4) {
-                const double lam = ws.lam(c);
+                const Real lam = ws.lam(c);
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
                     TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
-                        double ddv[3];
+                        Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
-                        const double val = lam * ddv[comp];
+                        const Real val = lam * ddv[comp];
                         ws.DDhl(i, j) += val;
                         if (j != i) ws.DDhl(j, i) += val;
                     }
@@ -628,6 +647,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
+    using Real = typename Ws::Real;
     const int nq = sys.NQ();
     TREPB_UNROLL_SYS
     for (int p = 0; p < sys.NPOT(); ++p) {
@@ -640,15 +660,15 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
         } else if (kind == P_LINEAR_SPRING) {
             const int A = sys.pot_i(p, 0), B = sys.pot_i(p, 1);
             const double k = sys.pot_d(p, 0), x0 = sys.pot_d(p, 1);
-            double v[3];
+            Real v[3];
             pair_first(sys, ws, A, B, v);
-            const double x = sqrt(dot3(v, v));
+            const Real x = sqrt_(dot3(v, v));
             TREPB_UNROLL_SYS
             for (int j = 0; j < nq; ++j) {
-                double dx = (1.0 / x) * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
+                Real dx = (1.0 / x) * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
                 ws.dxs(j) = dx;
-                double val = k * (x - x0) * dx;
-                if (isnan(dx) && x0 == 0.0) val = 0.0;
+                Real val = k * (x - x0) * dx;
+                if (isnan_(dx) && x0 == 0.0) val = 0.0;
                 ws.Lq(j) -= val;
             }
             if (order >= 2) {
@@ -657,13 +677,13 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
                     TREPB_UNROLL_SYS
                     for (int j = i; j < nq; ++j) {
                         if (!(sys.dep(A, i) || sys.dep(B, i)) || !(sys.dep(A, j) || sys.dep(B, j))) continue;
-                        double ddv[3];
+                        Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
-                        const double vdi = v[0] * ws.dv(i, 0) + v[1] * ws.dv(i, 1) + v[2] * ws.dv(i, 2);
-                        const double didj = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2);
-                        const double dix = ws.dxs(i), djx = ws.dxs(j);
-                        const double ddx = -djx / (x * x) * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
-                        const double val = k * dix * djx + k * (x - x0) * ddx;
+                        const Real vdi = v[0] * ws.dv(i, 0) + v[1] * ws.dv(i, 1) + v[2] * ws.dv(i, 2);
+                        const Real didj = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2);
+                        const Real dix = ws.dxs(i), djx = ws.dxs(j);
+                        const Real ddx = -djx / (x * x) * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
+                        const Real val = k * dix * djx + k * (x - x0) * ddx;
                         ws.Lqq(i, j) -= val;
                         if (j != i) ws.Lqq(j, i) -= val;
                     }
@@ -678,6 +698,7 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
+    using Real = typename Ws::Real;
     const int nq = sys.NQ(), nd = sys.ND();
     TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.Fo(j) = 0.0;
     if (order >= 2) {
@@ -708,14 +729,14 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
             const int off = sys.force_i(fo, 0);
             const int A = sys.ipool(off), B = sys.ipool(off + 1);
             const double cdamp = sys.force_d(fo, 0);
-            double v[3];
+            Real v[3];
             pair_first(sys, ws, A, B, v);
-            const double x = sqrt(dot3(v, v));
-            double vel = 0.0;
+            const Real x = sqrt_(dot3(v, v));
+            Real vel = 0.0;
             // dx_j only where exactly one end depends on q_j (tapemeasure.py:97-110)
             TREPB_UNROLL_SYS
             for (int j = 0; j < nq; ++j) {
-                double dx = 0.0;
+                Real dx = 0.0;
                 if (sys.dep(A, j) != sys.dep(B, j))
                     dx = 1.0 / x * (v[0] * ws.dv(j, 0) + v[1] * ws.dv(j, 1) + v[2] * ws.dv(j, 2));
                 ws.dxs(j) = dx;
@@ -731,15 +752,15 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i) {
                     if (sys.dep(A, i) == sys.dep(B, i)) continue;
-                    double veldq = 0.0;
+                    Real veldq = 0.0;
                     TREPB_UNROLL_SYS
                     for (int k = 0; k < nq; ++k) {
-                        double ddx = 0.0;
+                        Real ddx = 0.0;
                         if (sys.dep(A, k) != sys.dep(B, k)) {
-                            double ddv[3];
+                            Real ddv[3];
                             pair_second(sys, ws, A, B, k, i, ddv);
-                            const double dkdi = ws.dv(k, 0) * ws.dv(i, 0) + ws.dv(k, 1) * ws.dv(i, 1) + ws.dv(k, 2) * ws.dv(i, 2);
-                            double t = ws.dxs(k) * ws.dxs(i) - dkdi - dot3(v, ddv);
+                            const Real dkdi = ws.dv(k, 0) * ws.dv(i, 0) + ws.dv(k, 1) * ws.dv(i, 1) + ws.dv(k, 2) * ws.dv(i, 2);
+                            Real t = ws.dxs(k) * ws.dxs(i) - dkdi - dot3(v, ddv);
                             ddx = -1.0 / x * t;
                         }
                         veldq += ddx * ws.dq(k);
@@ -888,9 +909,10 @@ template <class Ws> struct AccTdcCol {  // column k of Tdc (nd x nc)
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
 TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, double dt) {  // 0 = midpoint, 1 = q1, 2 = q2
+    using Real = typename Ws::Real;
     TREPB_UNROLL_SYS
     for (int i = 0; i < sys.NQ(); ++i) {
-        const double a = ws.q1(i), b = ws.q2(i);
+        const Real a = ws.q1(i), b = ws.q2(i);
         ws.qe(i) = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
         ws.dq(i) = (b - a) / dt;
     }
@@ -899,6 +921,7 @@ TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, double dt) {  // 0 = 
 // Lagrangian + forces at the midpoint.  order 1: residual terms.  order 2: Jacobian terms too.
 template <class Sys, class Ws>
 TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
+    using Real = typename Ws::Real;
     set_point(sys, ws, 0, dt);
     pass1(sys, ws, true, sys.pairs_on());
     pass2(sys, ws, order);

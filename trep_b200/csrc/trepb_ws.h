@@ -1,71 +1,79 @@
 // Per-instance workspace for the MidpointVI math (trepb_math.cuh).
 //
 // The same array list is instantiated two ways:
-//   WsStatic<Sys>  - fixed-size member arrays (compile-time system): after unrolling, every index
-//                    is a constant and the arrays live in registers.
-//   WsStrided      - one slab of global memory shared by the whole batch, element e of instance t
-//                    at base[e * stride + t]  (structure-of-arrays across instances, so a warp
-//                    executing the same line touches 32 consecutive doubles = coalesced).
+//   WsStatic<Sys, Real>  - fixed-size member arrays (compile-time system): after unrolling, every
+//                          index is a constant and the arrays live in registers.
+//   WsStridedT<Real>     - one slab of global memory shared by the whole grid, element e of thread t
+//                          at base[e * stride + t]  (structure-of-arrays across threads, so a warp
+//                          executing the same line touches 32 consecutive elements = coalesced).
+// Real is double for the step / first-derivative kernels and a hyper-dual number (trepb_hd.h) for
+// the second-derivative kernel, which only evaluates the first-order residual path and therefore
+// lays out only the arrays flagged `ad`.
 #pragma once
 #include "trepb_sys.h"
 
 namespace trepb {
 
-// X(name, rows, cols) ; sizes use NF NQ ND NU NC NR (= ND+NC)
+// X(name, rows, cols, ad) ; sizes use NF NQ ND NU NC NR (= ND+NC)
 #define TREPB_WS_ARRAYS(X)                                                                     \
     /* integrator state */                                                                     \
-    X(q1, NQ, 1) X(q2, NQ, 1) X(p1, ND, 1) X(p2, ND, 1) X(u1, NU, 1) X(lam, NC, 1)             \
-    X(qe, NQ, 1) X(dq, NQ, 1)                                                                  \
+    X(q1, NQ, 1, 1) X(q2, NQ, 1, 1) X(p1, ND, 1, 0) X(p2, ND, 1, 1) X(u1, NU, 1, 1) X(lam, NC, 1, 1) \
+    X(qe, NQ, 1, 1) X(dq, NQ, 1, 1)                                                            \
     /* frame pass 1 */                                                                         \
-    X(cs, NF, 2) X(gf, NF, 3) X(V, NF, 6) X(W, NF, 6) X(Rw, NF, 9) X(pw, NF, 3)                \
+    X(cs, NF, 2, 1) X(gf, NF, 3, 1) X(V, NF, 6, 1) X(W, NF, 6, 1) X(Rw, NF, 9, 1) X(pw, NF, 3, 1) \
     /* frame pass 2: composite inertia (m, h, I sym6) and momentum */                          \
-    X(Im, NF, 1) X(Ih, NF, 3) X(II, NF, 6) X(mu, NF, 6)                                        \
+    X(Im, NF, 1, 1) X(Ih, NF, 3, 1) X(II, NF, 6, 0) X(mu, NF, 6, 1)                            \
     /* Lagrangian tables */                                                                    \
-    X(Lq, NQ, 1) X(Lv, NQ, 1) X(Lqq, NQ, NQ) X(Lvq, NQ, NQ) X(Lvv, NQ, NQ)                     \
+    X(Lq, NQ, 1, 1) X(Lv, NQ, 1, 1) X(Lqq, NQ, NQ, 0) X(Lvq, NQ, NQ, 0) X(Lvv, NQ, NQ, 0)      \
     /* forces */                                                                               \
-    X(Fo, ND, 1) X(Fq, ND, NQ) X(Fv, ND, NQ) X(Fu, ND, NU)                                     \
+    X(Fo, ND, 1, 1) X(Fq, ND, NQ, 0) X(Fv, ND, NQ, 0) X(Fu, ND, NU, 0)                         \
     /* constraints */                                                                          \
-    X(hc, NC, 1) X(Dh1, NC, NQ) X(Dh2, NC, NQ) X(DDhl, NQ, NQ)                                 \
+    X(hc, NC, 1, 1) X(Dh1, NC, NQ, 1) X(Dh2, NC, NQ, 0) X(DDhl, NQ, NQ, 0)                     \
     /* point-pair scratch: d(pA-pB)/dq_j for every config */                                   \
-    X(dv, NQ, 3) X(dxs, NQ, 1)                                                                 \
+    X(dv, NQ, 3, 1) X(dxs, NQ, 1, 1)                                                           \
     /* Newton */                                                                               \
-    X(fr, NR, 1) X(Df, NR, NR) X(piv, NR, 1) X(lus, NR, 1) X(lux, NR, 1)                       \
+    X(fr, NR, 1, 1) X(Df, NR, NR, 0) X(piv, NR, 1, 0) X(lus, NR, 1, 0) X(lux, NR, 1, 0)        \
     /* first-derivative tables and solves */                                                   \
-    X(T11, NQ, ND) X(T21, NQ, ND) X(T12, NQ, ND) X(T22, NQ, ND) X(T3, NU, ND)                  \
-    X(M2, ND, ND) X(M2p, ND, 1) X(PJ, NC, NC) X(PJp, NC, 1) X(tnd, ND, 1) X(tnc, NC, 1)        \
-    X(Tdc, ND, NC) X(col, ND, 1)
+    X(T11, NQ, ND, 0) X(T21, NQ, ND, 0) X(T12, NQ, ND, 0) X(T22, NQ, ND, 0) X(T3, NU, ND, 0)   \
+    X(M2, ND, ND, 0) X(M2p, ND, 1, 0) X(PJ, NC, NC, 0) X(PJp, NC, 1, 0) X(tnd, ND, 1, 0) X(tnc, NC, 1, 0) \
+    X(Tdc, ND, NC, 0) X(col, ND, 1, 0)
 
-template <class Sys>
+template <class Sys, class RealT = double>
 struct WsStatic {
+    using Real = RealT;
     static constexpr int NF = Sys::kNF, NQ = Sys::kNQ, ND = Sys::kND, NU = Sys::kNU,
                          NC = Sys::kNC, NR = Sys::kND + Sys::kNC;
-#define X(name, rows, cols)                                     \
-    double name##_[((rows) * (cols)) > 0 ? (rows) * (cols) : 1]; \
-    TREPB_HD double& name(int i, int j = 0) { return name##_[i * (cols) + j]; }
+#define X(name, rows, cols, ad)                               \
+    Real name##_[((rows) * (cols)) > 0 ? (rows) * (cols) : 1]; \
+    TREPB_HD Real& name(int i, int j = 0) { return name##_[i * (cols) + j]; }
     TREPB_WS_ARRAYS(X)
 #undef X
 };
 
-struct WsStrided {
-    double* base;
+template <class RealT>
+struct WsStridedT {
+    using Real = RealT;
+    Real* base;
     long stride;
     int NF, NQ, ND, NU, NC, NR;
-#define X(name, rows, cols) int o_##name; int ld_##name;
+#define X(name, rows, cols, ad) int o_##name; int ld_##name;
     TREPB_WS_ARRAYS(X)
 #undef X
-#define X(name, rows, cols) \
-    TREPB_HD double& name(int i, int j = 0) { return base[(long)(o_##name + i * ld_##name + j) * stride]; }
+#define X(name, rows, cols, ad) \
+    TREPB_HD Real& name(int i, int j = 0) { return base[(long)(o_##name + i * ld_##name + j) * stride]; }
     TREPB_WS_ARRAYS(X)
 #undef X
-    // returns number of doubles per instance
-    TREPB_HD int layout(int nf, int nd, int nk, int nu, int nc) {
+    // returns number of elements per thread; ad_only: lay out only the arrays of the residual path
+    TREPB_HD int layout(int nf, int nd, int nk, int nu, int nc, bool ad_only = false) {
         NF = nf; ND = nd; NQ = nd + nk; NU = nu; NC = nc; NR = nd + nc;
         int off = 0;
-#define X(name, rows, cols) o_##name = off; ld_##name = (cols); off += (rows) * (cols);
+#define X(name, rows, cols, ad) \
+        o_##name = off; ld_##name = (cols); if (!ad_only || (ad)) off += (rows) * (cols);
         TREPB_WS_ARRAYS(X)
 #undef X
         return off;
     }
 };
+using WsStrided = WsStridedT<double>;
 
 }  // namespace trepb

@@ -50,6 +50,14 @@ class LinArgs(C.Structure):
                 + [(n, C.c_void_p) for n in RAW])
 
 
+D2_KINDS = ["dq1dq1", "dq1dp1", "dq1du1", "dq1dk2", "dp1dp1", "dp1du1", "dp1dk2", "du1du1", "du1dk2", "dk2dk2"]
+D2_WHICH = ["q2", "p2", "l1"]
+
+
+class D2Args(C.Structure):
+    _fields_ = [("lin", LinArgs), ("d2", C.c_void_p * 30)]
+
+
 _lib.trepb_last_error.restype = C.c_char_p
 _lib.trepb_system_kernel_name.restype = C.c_char_p
 _lib.trepb_specialized_name.restype = C.c_char_p
@@ -63,6 +71,8 @@ _lib.trepb_step_batch.argtypes = [C.c_void_p, C.POINTER(StepArgs)]
 _lib.trepb_step_batch_dev.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
 _lib.trepb_linearize_batch.argtypes = [C.c_void_p, C.POINTER(LinArgs)]
 _lib.trepb_linearize_batch_dev.argtypes = [C.c_void_p, C.POINTER(LinArgs), C.c_void_p]
+_lib.trepb_deriv2_batch.argtypes = [C.c_void_p, C.POINTER(D2Args)]
+_lib.trepb_deriv2_batch_dev.argtypes = [C.c_void_p, C.POINTER(D2Args), C.c_void_p]
 _lib.trepb_calc_p2_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.trepb_calc_p2_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
@@ -83,7 +93,7 @@ EXPORTS = [
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_linearize_batch",
-    "trepb_linearize_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
+    "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
     "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
 ]
@@ -253,10 +263,10 @@ class System:
         else:
             _check(_lib.trepb_step_batch(self._h, C.byref(a)))
 
-    def linearize_raw(self, on_device, batch, q1, p1, u1, k2, status, t1=None, t2=None,
-                      t1_scalar=0.0, dt_scalar=0.0, q2_guess=None, lambda_guess=None, q2=None,
-                      p2=None, lambda1=None, iters=None, A=None, B=None, raw=None,
-                      tolerance=1e-10, max_iterations=200, stream=None):
+    @staticmethod
+    def _lin_args(batch, q1, p1, u1, k2, status, t1=None, t2=None, t1_scalar=0.0, dt_scalar=0.0,
+                  q2_guess=None, lambda_guess=None, q2=None, p2=None, lambda1=None, iters=None,
+                  A=None, B=None, raw=None, tolerance=1e-10, max_iterations=200):
         a = LinArgs(batch=batch, max_iterations=max_iterations, tolerance=tolerance, t1=_ptr(t1),
                     t2=_ptr(t2), t1_scalar=t1_scalar, dt_scalar=dt_scalar, q1=_ptr(q1), p1=_ptr(p1),
                     u1=_ptr(u1), k2=_ptr(k2), q2_guess=_ptr(q2_guess),
@@ -264,10 +274,26 @@ class System:
                     lambda1=_ptr(lambda1), iters=_ptr(iters), status=_ptr(status), A=_ptr(A), B=_ptr(B))
         for n, v in (raw or {}).items():
             setattr(a, n, _ptr(v))
+        return a
+
+    def linearize_raw(self, on_device, batch, q1, p1, u1, k2, status, stream=None, **kw):
+        a = self._lin_args(batch, q1, p1, u1, k2, status, **kw)
         if on_device:
             _check(_lib.trepb_linearize_batch_dev(self._h, C.byref(a), stream))
         else:
             _check(_lib.trepb_linearize_batch(self._h, C.byref(a)))
+
+    def deriv2_raw(self, on_device, batch, q1, p1, u1, k2, status, d2, stream=None, **kw):
+        """d2: {"q2_dq1dq1": array, ...} any subset of D2_WHICH x D2_KINDS."""
+        a = D2Args()
+        a.lin = self._lin_args(batch, q1, p1, u1, k2, status, **kw)
+        for n, v in d2.items():
+            w, kd = n.split("_")
+            a.d2[10 * D2_WHICH.index(w) + D2_KINDS.index(kd)] = _ptr(v)
+        if on_device:
+            _check(_lib.trepb_deriv2_batch_dev(self._h, C.byref(a), stream))
+        else:
+            _check(_lib.trepb_deriv2_batch(self._h, C.byref(a)))
 
     def calc_p2_raw(self, on_device, batch, dt, q0, q1, p, stream=None):
         if on_device:
@@ -351,4 +377,42 @@ class System:
                            A=out["A"], B=out["B"] if self.nU else None,
                            raw={k: v for k, v in rawbufs.items() if v.size},
                            tolerance=tolerance, max_iterations=max_iterations)
+        return out
+
+    def d2_shapes(self, B):
+        cnt = {"dq1": self.nq, "dp1": self.nd, "du1": self.nu, "dk2": self.nk}
+        out = {}
+        for w in D2_WHICH:
+            for kd in D2_KINDS:
+                a, b = kd[:3], kd[3:]
+                out[w + "_" + kd] = (B, cnt[a], cnt[b], self.nc if w == "l1" else self.nd)
+        return out
+
+    def deriv2(self, q1, p1, u1=None, k2=None, t1=0.0, t2=None, dt=None, q2_guess=None,
+               lambda_guess=None, tolerance=1e-10, max_iterations=200):
+        """solve + first derivatives + every second-derivative tensor (reference layout
+        [B][wrt A][wrt B][out]); returns the dict of `linearize(want_raw=True)` plus the tensors."""
+        q1 = np.atleast_2d(np.asarray(q1, float))
+        B = q1.shape[0]
+        q1, p1 = self._f(q1, (B, self.nq)), self._f(p1, (B, self.nd))
+        u1 = self._f(u1 if u1 is not None else np.zeros((B, self.nu)), (B, self.nu))
+        k2 = self._f(k2 if k2 is not None else np.zeros((B, self.nk)), (B, self.nk))
+        q2g = None if q2_guess is None else self._f(q2_guess, (B, self.nd))
+        lg = None if (lambda_guess is None or self.nc == 0) else self._f(lambda_guess, (B, self.nc))
+        t1a = self._f(np.broadcast_to(t1, (B,)), (B,))
+        t2a = self._f(np.broadcast_to(t1a + dt if t2 is None else t2, (B,)), (B,))
+        out = dict(q2=np.empty((B, self.nq)), p2=np.empty((B, self.nd)), lambda1=np.zeros((B, self.nc)),
+                   iters=np.zeros(B, np.int32), status=np.zeros(B, np.int32),
+                   A=np.empty((B, self.nX, self.nX)), B=np.zeros((B, self.nX, self.nU)))
+        wrt = {"dq1": self.nq, "dp1": self.nd, "du1": self.nu, "dk2": self.nk}
+        rawbufs = {n: np.zeros((B, wrt[n[3:]], self.nc if n.startswith("l1") else self.nd)) for n in RAW}
+        d2 = {n: np.zeros(sh) for n, sh in self.d2_shapes(B).items()}
+        self.deriv2_raw(False, B, q1, p1, u1 if self.nu else None, k2 if self.nk else None, out["status"],
+                        {n: v for n, v in d2.items() if v.size}, t1=t1a, t2=t2a, q2_guess=q2g,
+                        lambda_guess=lg, q2=out["q2"], p2=out["p2"],
+                        lambda1=out["lambda1"] if self.nc else None, iters=out["iters"], A=out["A"],
+                        B=out["B"] if self.nU else None, raw={k: v for k, v in rawbufs.items() if v.size},
+                        tolerance=tolerance, max_iterations=max_iterations)
+        out.update(rawbufs)
+        out.update(d2)
         return out
