@@ -38,6 +38,19 @@ struct DevBuf {
 };
 }  // namespace
 
+#if defined(TREPB_PHASE_TIMING)
+namespace trepb { __device__ unsigned long long g_phase_ticks[32]; }
+extern "C" int trepb_phase_ticks(unsigned long long* out, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, trepb::g_phase_ticks, sizeof(unsigned long long) * 32);
+    if (e != cudaSuccess) return TREPB_ERR_CUDA;
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(trepb::g_phase_ticks, z, sizeof(z));
+    }
+    return TREPB_OK;
+}
+#endif
+
 namespace trepb {
 SpecRegistry& spec_registry() {
     static SpecRegistry r = {{nullptr}, 0};

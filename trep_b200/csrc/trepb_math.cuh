@@ -50,6 +50,17 @@ namespace trepb {
 #define TREPB_UNROLL_SYS
 #endif
 
+// Optional phase timing (development builds only: -DTREPB_PHASE_TIMING): clock64 deltas of one
+// lane per warp accumulated into a device array, read back through trepb_phase_ticks().
+#if defined(TREPB_PHASE_TIMING) && defined(__CUDA_ARCH__)
+extern __device__ unsigned long long g_phase_ticks[32];
+#define TREPB_TICK_INIT long long tick_ = clock64();
+#define TREPB_TICK(i) do { const long long now_ = clock64(); if ((threadIdx.x & 31) == 0) atomicAdd(&g_phase_ticks[i], (unsigned long long)(now_ - tick_)); tick_ = clock64(); } while (0)
+#else
+#define TREPB_TICK_INIT
+#define TREPB_TICK(i)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // small helpers
 // ---------------------------------------------------------------------------------------------
@@ -801,23 +812,63 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol
     }
     TREPB_UNROLL_SYS
     for (int j = 0; j < n; ++j) {
-        TREPB_UNROLL_SYS
-        for (int i = 0; i < j; ++i) {
-            double a = A(i, j);
-            TREPB_UNROLL_SYS
-            for (int k = 0; k < i; ++k) a -= A(i, k) * A(k, j);
-            A(i, j) = a;
-        }
         double pv = -1.0;
         int pi = 0;
-        TREPB_UNROLL_SYS
-        for (int i = j; i < n; ++i) {
-            double a = A(i, j);
+        if constexpr (Sys::kStatic) {
             TREPB_UNROLL_SYS
-            for (int k = 0; k < j; ++k) a -= A(i, k) * A(k, j);
-            A(i, j) = a;
-            const double t = fabs(a * scales(i));
-            if (t > pv) { pv = t; pi = i; }
+            for (int i = 0; i < j; ++i) {
+                double a = A(i, j);
+                TREPB_UNROLL_SYS
+                for (int k = 0; k < i; ++k) a -= A(i, k) * A(k, j);
+                A(i, j) = a;
+            }
+            TREPB_UNROLL_SYS
+            for (int i = j; i < n; ++i) {
+                double a = A(i, j);
+                TREPB_UNROLL_SYS
+                for (int k = 0; k < j; ++k) a -= A(i, k) * A(k, j);
+                A(i, j) = a;
+                const double t = fabs(a * scales(i));
+                if (t > pv) { pv = t; pi = i; }
+            }
+        } else {
+            // Same inner products in the same order, four rows at a time: each element of column
+            // j is fetched once per four rows (the matrix lives in the strided global workspace,
+            // the fetches are what bounds this loop).
+            constexpr int kR = 4;
+            for (int i0 = 0; i0 < j; i0 += kR) {
+                double a[kR];
+                TREPB_UNROLL for (int g = 0; g < kR; ++g) a[g] = (i0 + g < j) ? A(i0 + g, j) : 0.0;
+                // rows above i0 are final; within the block row i0+g also needs rows i0..i0+g-1
+                for (int k = 0; k < i0; ++k) {
+                    const double b = A(k, j);
+                    TREPB_UNROLL for (int g = 0; g < kR; ++g) if (i0 + g < j) a[g] -= A(i0 + g, k) * b;
+                }
+                TREPB_UNROLL
+                for (int g = 0; g < kR; ++g) {
+                    if (i0 + g < j) {
+                        TREPB_UNROLL
+                        for (int h = 0; h < g; ++h) a[g] -= A(i0 + g, i0 + h) * a[h];
+                        A(i0 + g, j) = a[g];
+                    }
+                }
+            }
+            for (int i0 = j; i0 < n; i0 += kR) {
+                double a[kR];
+                TREPB_UNROLL for (int g = 0; g < kR; ++g) a[g] = (i0 + g < n) ? A(i0 + g, j) : 0.0;
+                for (int k = 0; k < j; ++k) {
+                    const double b = A(k, j);
+                    TREPB_UNROLL for (int g = 0; g < kR; ++g) if (i0 + g < n) a[g] -= A(i0 + g, k) * b;
+                }
+                TREPB_UNROLL
+                for (int g = 0; g < kR; ++g) {
+                    if (i0 + g < n) {
+                        A(i0 + g, j) = a[g];
+                        const double t = fabs(a[g] * scales(i0 + g));
+                        if (t > pv) { pv = t; pi = i0 + g; }
+                    }
+                }
+            }
         }
         if (pv <= tol) return false;
         if (pi != j) {
@@ -955,14 +1006,17 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
     const int nd = sys.ND(), nc = sys.NC(), nr = nd + nc;
     const double dt = t2 - t1;
     int iterations = 0;
+    TREPB_TICK_INIT
     if (nc > 0) {
         set_point(sys, ws, 1, dt);
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2, 1);  // Dh1 = Dh(q1)
     }
+    TREPB_TICK(0);
     for (;;) {
         // ---- calc_f (midpointvi.c:533-565)
         eval_mid(sys, ws, dt, 1);
+        TREPB_TICK(1);
         TREPB_UNROLL_SYS
         for (int j = 0; j < nd; ++j) {
             double f = ws.p1(j) + (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
@@ -975,6 +1029,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             constraints_eval(sys, ws, 1, 2);
             TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
         }
+        TREPB_TICK(2);
         // ---- DEL_solved (midpointvi.c:672-689)
         double nrm = 0.0;
         TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) nrm += ws.fr(j) * ws.fr(j);
@@ -984,28 +1039,16 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
         if (solved) break;
         if (iterations > max_it) return ST_NOT_CONVERGED;
 
-        // ---- Jacobian (midpointvi.c:577-670), same accumulation order as the reference
+        // ---- Jacobian (midpointvi.c:577-670): Df_11 entry by entry (the reference fills it with a
+        // symmetric/antisymmetric split, :603-627, i.e. the same terms in a different order)
         eval_mid_again(sys, ws, dt);
-        TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k)
-            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
-                ws.Df(k, i) = 0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i);
+        TREPB_TICK(3);
         TREPB_UNROLL_SYS
         for (int k = 0; k < nd; ++k) {
-            ws.Df(k, k) += 0.25 * dt * ws.Lqq(k, k);
-            ws.Df(k, k) -= 1.0 / dt * ws.Lvv(k, k);
-            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) {
-                const double val = 0.5 * ws.Lvq(i, k);
-                ws.Df(k, i) += val;
-                ws.Df(i, k) -= val;
-            }
-            TREPB_UNROLL_SYS for (int i = 0; i < k; ++i) {
-                double val = 0.25 * dt * ws.Lqq(k, i);
-                ws.Df(k, i) += val;
-                ws.Df(i, k) += val;
-                val = 1.0 / dt * ws.Lvv(k, i);
-                ws.Df(k, i) -= val;
-                ws.Df(i, k) -= val;
-            }
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nd; ++i)
+                ws.Df(k, i) = (0.25 * dt * ws.Lqq(k, i) - 1.0 / dt * ws.Lvv(k, i)) + 0.5 * ws.Lvq(i, k)
+                            - 0.5 * ws.Lvq(k, i) + (0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i));
         }
         if (nc > 0) {
             set_point(sys, ws, 2, dt);
@@ -1019,6 +1062,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             TREPB_UNROLL_SYS for (int a = 0; a < nc; ++a)
                 TREPB_UNROLL_SYS for (int b = 0; b < nc; ++b) ws.Df(nd + a, nd + b) = 0.0;
         }
+        TREPB_TICK(4);
         if (nr == 1) {
             // 1x1: the reference's LU reduces to a scaled-pivot test and one division
             const double a = ws.Df(0, 0);
@@ -1028,6 +1072,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             if (!lu_decomp<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
             lu_solve<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws});
         }
+        TREPB_TICK(5);
         TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k) ws.q2(k) -= ws.fr(k);
         TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.lam(c) -= ws.fr(nd + c);
         iterations++;
@@ -1064,6 +1109,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nc = sys.NC(), nu = sys.NU();
     const double dt = t2 - t1;
     const int nX = 2 * nq, nU = nu + nk;
+    TREPB_TICK_INIT
     // ---- constraint derivatives at q1 and q2
     if (nc > 0) {
         set_point(sys, ws, 1, dt);
@@ -1073,7 +1119,8 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2, 2);      // Dh2
     }
-    // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861), same accumulation order.
+    TREPB_TICK(8);
+    // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861).
     // mid_valid: the workspace still holds pass 1 of the converged midpoint (solve_del just ran)
     if (mid_valid) {
         if (nc == 0) set_point(sys, ws, 0, dt);
@@ -1081,67 +1128,27 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     } else {
         eval_mid(sys, ws, dt, 2);
     }
-    TREPB_UNROLL_SYS for (int i1 = 0; i1 < nq; ++i1)
-        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
-            const double v1 = 0.5 * dt * ws.Fq(i2, i1), v2 = ws.Fv(i2, i1);
-            ws.T11(i1, i2) = v1 - v2;
-            ws.T21(i1, i2) = v1 + v2;
-            ws.T12(i1, i2) = 0.0;
-            ws.T22(i1, i2) = 0.0;
-        }
+    TREPB_TICK(9);
+    // Entry by entry; the reference fills the same four tables with a
+    // symmetric i<j pass plus a separate L_ddqdq pass (midpointvi.c:771-858), which only changes
+    // the order of the six-term sums.
     TREPB_UNROLL_SYS
-    for (int i1 = 0; i1 < nd; ++i1) {
-        double v1 = 0.25 * dt * ws.Lqq(i1, i1), v2 = 1.0 / dt * ws.Lvv(i1, i1);
-        ws.T11(i1, i1) += v1 + v2;
-        ws.T21(i1, i1) += v1 - v2;
-        ws.T12(i1, i1) += v1 - v2;
-        ws.T22(i1, i1) += v1 + v2;
-        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nq; ++i2) {
-            v1 = 0.5 * ws.Lvq(i1, i2);
-            ws.T11(i2, i1) -= v1;
-            ws.T21(i2, i1) -= v1;
-            ws.T12(i2, i1) += v1;
-            ws.T22(i2, i1) += v1;
-            if (i2 < nd) {
-                ws.T11(i1, i2) -= v1;
-                ws.T21(i1, i2) += v1;
-                ws.T12(i1, i2) -= v1;
-                ws.T22(i1, i2) += v1;
-            }
-        }
-        TREPB_UNROLL_SYS for (int i2 = 0; i2 < i1; ++i2) {
-            v1 = 0.25 * dt * ws.Lqq(i1, i2);
-            v2 = 1.0 / dt * ws.Lvv(i1, i2);
-            ws.T11(i2, i1) += v1 + v2;
-            ws.T21(i2, i1) += v1 - v2;
-            ws.T12(i2, i1) += v1 - v2;
-            ws.T22(i2, i1) += v1 + v2;
-            ws.T11(i1, i2) += v1 + v2;   // i2 < i1 < nd always holds here
-            ws.T21(i1, i2) += v1 - v2;
-            ws.T12(i1, i2) += v1 - v2;
-            ws.T22(i1, i2) += v1 + v2;
-        }
-    }
-    TREPB_UNROLL_SYS
-    for (int i1 = nd; i1 < nq; ++i1) {
-        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
-            const double v1 = 0.5 * ws.Lvq(i1, i2);
-            ws.T11(i1, i2) -= v1;
-            ws.T21(i1, i2) += v1;
-            ws.T12(i1, i2) -= v1;
-            ws.T22(i1, i2) += v1;
-        }
-        TREPB_UNROLL_SYS for (int i2 = 0; i2 < nd; ++i2) {
-            const double v1 = 0.25 * dt * ws.Lqq(i1, i2), v2 = 1.0 / dt * ws.Lvv(i1, i2);
-            ws.T11(i1, i2) += v1 + v2;
-            ws.T21(i1, i2) += v1 - v2;
-            ws.T12(i1, i2) += v1 - v2;
-            ws.T22(i1, i2) += v1 + v2;
+    for (int a = 0; a < nq; ++a) {
+        TREPB_UNROLL_SYS
+        for (int b = 0; b < nd; ++b) {
+            const double qq = 0.25 * dt * ws.Lqq(a, b), vv = 1.0 / dt * ws.Lvv(a, b);
+            const double vab = 0.5 * ws.Lvq(a, b), vba = 0.5 * ws.Lvq(b, a);
+            const double fq = 0.5 * dt * ws.Fq(b, a), fv = ws.Fv(b, a);
+            ws.T11(a, b) = (qq + vv) - vab - vba + (fq - fv);
+            ws.T21(a, b) = (qq - vv) + vab - vba + (fq + fv);
+            ws.T12(a, b) = (qq - vv) - vab + vba;
+            ws.T22(a, b) = (qq + vv) + vab + vba;
         }
     }
     TREPB_UNROLL_SYS for (int u = 0; u < nu; ++u)
         TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.T3(u, j) = dt * ws.Fu(j, u);
 
+    TREPB_TICK(10);
     // ---- calc_M2 (midpointvi.c:891-908)
     TREPB_UNROLL_SYS for (int a = 0; a < nd; ++a)
         TREPB_UNROLL_SYS for (int b = 0; b < nd; ++b) ws.M2(a, b) = ws.T21(b, a);
@@ -1165,80 +1172,235 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
         if (!lu_decomp<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
     }
 
+    TREPB_TICK(11);
     // ---- calc_deriv1 (midpointvi.c:929-1098): one right-hand side per wrt-variable
     // kind 0: q1_i   1: p1_i   2: u1_i   3: k2_i
     const long es = o.es;
-    TREPB_UNROLL_SYS
-    for (int kindv = 0; kindv < 4; ++kindv) {
-        const int count = kindv == 0 ? nq : (kindv == 1 ? nd : (kindv == 2 ? nu : nk));
+    if constexpr (Sys::kStatic) {
         TREPB_UNROLL_SYS
-        for (int i = 0; i < count; ++i) {
-            // explicit part c
+        for (int kindv = 0; kindv < 4; ++kindv) {
+            const int count = kindv == 0 ? nq : (kindv == 1 ? nd : (kindv == 2 ? nu : nk));
             TREPB_UNROLL_SYS
-            for (int j = 0; j < nd; ++j) {
-                double c;
-                if (kindv == 0) {
-                    c = -ws.T11(i, j);
-                    if (nc > 0) c += ws.DDhl(i, j);
-                } else if (kindv == 1) {
-                    c = (j == i) ? -1.0 : 0.0;
-                } else if (kindv == 2) {
-                    c = -ws.T3(i, j);
-                } else {
-                    c = -ws.T21(nd + i, j);
-                }
-                ws.tnd(j) = c;
-                ws.col(j) = c;
-            }
-            if (nc > 0) {
-                lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
-                TREPB_UNROLL_SYS
-                for (int c = 0; c < nc; ++c) {
-                    double s = 0.0;
-                    TREPB_UNROLL_SYS
-                    for (int j = 0; j < nd; ++j) s += ws.Dh2(c, j) * ws.tnd(j);
-                    if (kindv == 3) s += ws.Dh2(c, nd + i);
-                    ws.tnc(c) = s;
-                }
-                lu_solve<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+            for (int i = 0; i < count; ++i) {
+                // explicit part c
                 TREPB_UNROLL_SYS
                 for (int j = 0; j < nd; ++j) {
-                    double s = ws.col(j);
+                    double c;
+                    if (kindv == 0) {
+                        c = -ws.T11(i, j);
+                        if (nc > 0) c += ws.DDhl(i, j);
+                    } else if (kindv == 1) {
+                        c = (j == i) ? -1.0 : 0.0;
+                    } else if (kindv == 2) {
+                        c = -ws.T3(i, j);
+                    } else {
+                        c = -ws.T21(nd + i, j);
+                    }
+                    ws.tnd(j) = c;
+                    ws.col(j) = c;
+                }
+                if (nc > 0) {
+                    lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
                     TREPB_UNROLL_SYS
-                    for (int c = 0; c < nc; ++c) s += ws.Dh1(c, j) * ws.tnc(c);
-                    ws.col(j) = s;
+                    for (int c = 0; c < nc; ++c) {
+                        double s = 0.0;
+                        TREPB_UNROLL_SYS
+                        for (int j = 0; j < nd; ++j) s += ws.Dh2(c, j) * ws.tnd(j);
+                        if (kindv == 3) s += ws.Dh2(c, nd + i);
+                        ws.tnc(c) = s;
+                    }
+                    lu_solve<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+                    TREPB_UNROLL_SYS
+                    for (int j = 0; j < nd; ++j) {
+                        double s = ws.col(j);
+                        TREPB_UNROLL_SYS
+                        for (int c = 0; c < nc; ++c) s += ws.Dh1(c, j) * ws.tnc(c);
+                        ws.col(j) = s;
+                    }
+                }
+                lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
+                // p2 derivative row
+                double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
+                double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+                double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+                TREPB_UNROLL_SYS
+                for (int j = 0; j < nd; ++j) {
+                    double pv = kindv == 0 ? ws.T12(i, j) : (kindv == 3 ? ws.T22(nd + i, j) : 0.0);
+                    TREPB_UNROLL_SYS
+                    for (int k = 0; k < nd; ++k) pv += ws.T22(k, j) * ws.col(k);
+                    const double qv = ws.col(j);
+                    if (q2o) q2o[(long)(i * nd + j) * es] = qv;
+                    if (p2o) p2o[(long)(i * nd + j) * es] = pv;
+                    // A / B blocks
+                    if (kindv == 0) {
+                        if (o.A) { o.A[(long)(j * nX + i) * es] = qv; o.A[(long)((nq + j) * nX + i) * es] = pv; }
+                    } else if (kindv == 1) {
+                        if (o.A) { o.A[(long)(j * nX + nq + i) * es] = qv; o.A[(long)((nq + j) * nX + nq + i) * es] = pv; }
+                    } else if (kindv == 2) {
+                        if (o.B) { o.B[(long)(j * nU + i) * es] = qv; o.B[(long)((nq + j) * nU + i) * es] = pv; }
+                    } else {
+                        if (o.B) { o.B[(long)(j * nU + nu + i) * es] = qv; o.B[(long)((nq + j) * nU + nu + i) * es] = pv; }
+                    }
+                }
+                if (l1o) {
+                    TREPB_UNROLL_SYS
+                    for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c);
                 }
             }
-            lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
-            // p2 derivative row
-            double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
-            double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
-            double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
-            TREPB_UNROLL_SYS
+        }
+    } else {
+        // Table-driven flavour: the right-hand sides are processed kG at a time so that every
+        // element of the M2 factors and of D2D2L2 is fetched once per group, not once per
+        // column (these fetches are what the kernel is bound by for a system of this size), and
+        // the second M2 back-substitution of the reference (q2_s = M2^-1 (c + Dh1^T l_s)) is
+        // replaced by  M2^-1 c + (M2^-1 Dh1^T) l_s  with the nd x nc matrix calc_proj_inv already
+        // formed.  Same mathematics; rounding differs at the 1e-16 level.
+        constexpr int kG = 4;
+        const int nrhs = nq + nd + nu + nk;
+        for (int r0 = 0; r0 < nrhs; r0 += kG) {
+            const int ng = nrhs - r0 < kG ? nrhs - r0 : kG;
+            int kv[kG], iv[kG];
+            TREPB_UNROLL
+            for (int g = 0; g < kG; ++g) {
+                const int r = r0 + (g < ng ? g : 0);
+                kv[g] = r < nq ? 0 : (r < nq + nd ? 1 : (r < nq + nd + nu ? 2 : 3));
+                iv[g] = r < nq ? r : (r < nq + nd ? r - nq : (r < nq + nd + nu ? r - nq - nd : r - nq - nd - nu));
+            }
             for (int j = 0; j < nd; ++j) {
-                double pv = kindv == 0 ? ws.T12(i, j) : (kindv == 3 ? ws.T22(nd + i, j) : 0.0);
-                TREPB_UNROLL_SYS
-                for (int k = 0; k < nd; ++k) pv += ws.T22(k, j) * ws.col(k);
-                const double qv = ws.col(j);
-                if (q2o) q2o[(long)(i * nd + j) * es] = qv;
-                if (p2o) p2o[(long)(i * nd + j) * es] = pv;
-                // A / B blocks
-                if (kindv == 0) {
-                    if (o.A) { o.A[(long)(j * nX + i) * es] = qv; o.A[(long)((nq + j) * nX + i) * es] = pv; }
-                } else if (kindv == 1) {
-                    if (o.A) { o.A[(long)(j * nX + nq + i) * es] = qv; o.A[(long)((nq + j) * nX + nq + i) * es] = pv; }
-                } else if (kindv == 2) {
-                    if (o.B) { o.B[(long)(j * nU + i) * es] = qv; o.B[(long)((nq + j) * nU + i) * es] = pv; }
-                } else {
-                    if (o.B) { o.B[(long)(j * nU + nu + i) * es] = qv; o.B[(long)((nq + j) * nU + nu + i) * es] = pv; }
+                TREPB_UNROLL
+                for (int g = 0; g < kG; ++g) {
+                    const int kindv = kv[g], i = iv[g];
+                    double c;
+                    if (kindv == 0) {
+                        c = -ws.T11(i, j);
+                        if (nc > 0) c += ws.DDhl(i, j);
+                    } else if (kindv == 1) {
+                        c = (j == i) ? -1.0 : 0.0;
+                    } else if (kindv == 2) {
+                        c = -ws.T3(i, j);
+                    } else {
+                        c = -ws.T21(nd + i, j);
+                    }
+                    ws.tnd(j, g) = c;
                 }
             }
-            if (l1o) {
-                TREPB_UNROLL_SYS
-                for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c);
+            // tnd <- M2^-1 c   (forward / back substitution, kG columns at once)
+            for (int i = 0; i < nd; ++i) {
+                double t[kG];
+                const int src = (int)ws.M2p(i);
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] = ws.tnd(src, g);
+                for (int j = 0; j < i; ++j) {
+                    const double a = ws.M2(i, j);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
+                }
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.lux(i, g) = t[g];
+            }
+            for (int i = nd - 1; i >= 0; --i) {
+                double t[kG];
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] = ws.lux(i, g);
+                for (int j = i + 1; j < nd; ++j) {
+                    const double a = ws.M2(i, j);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
+                }
+                const double dg = ws.M2(i, i);
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = t[g] / dg; ws.lux(i, g) = t[g]; }
+            }
+            for (int i = 0; i < nd; ++i) {
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.tnd(i, g) = ws.lux(i, g);
+            }
+            if (nc > 0) {
+                for (int c = 0; c < nc; ++c) {
+                    double sacc[kG];
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) sacc[g] = 0.0;
+                    for (int j = 0; j < nd; ++j) {
+                        const double a = ws.Dh2(c, j);
+                        TREPB_UNROLL for (int g = 0; g < kG; ++g) sacc[g] += a * ws.tnd(j, g);
+                    }
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) {
+                        if (kv[g] == 3) sacc[g] += ws.Dh2(c, nd + iv[g]);
+                        ws.tnc(c, g) = sacc[g];
+                    }
+                }
+                // tnc <- proj^-1 tnc
+                for (int i = 0; i < nc; ++i) {
+                    double t[kG];
+                    const int src = (int)ws.PJp(i);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] = ws.tnc(src, g);
+                    for (int j = 0; j < i; ++j) {
+                        const double a = ws.PJ(i, j);
+                        TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
+                    }
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.lux(i, g) = t[g];
+                }
+                for (int i = nc - 1; i >= 0; --i) {
+                    double t[kG];
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] = ws.lux(i, g);
+                    for (int j = i + 1; j < nc; ++j) {
+                        const double a = ws.PJ(i, j);
+                        TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
+                    }
+                    const double dg = ws.PJ(i, i);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = t[g] / dg; ws.lux(i, g) = t[g]; }
+                }
+                for (int i = 0; i < nc; ++i) {
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.tnc(i, g) = ws.lux(i, g);
+                }
+                // col = M2^-1 c + (M2^-1 Dh1^T) lambda_s
+                for (int j = 0; j < nd; ++j) {
+                    double t[kG];
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] = ws.tnd(j, g);
+                    for (int c = 0; c < nc; ++c) {
+                        const double a = ws.Tdc(j, c);
+                        TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] += a * ws.tnc(c, g);
+                    }
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.col(j, g) = t[g];
+                }
+            } else {
+                for (int j = 0; j < nd; ++j) {
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.col(j, g) = ws.tnd(j, g);
+                }
+            }
+            // outputs: q2_s = col, p2_s = explicit + D2D2L2^T col
+            for (int j = 0; j < nd; ++j) {
+                double pv[kG];
+                TREPB_UNROLL for (int g = 0; g < kG; ++g)
+                    pv[g] = kv[g] == 0 ? ws.T12(iv[g], j) : (kv[g] == 3 ? ws.T22(nd + iv[g], j) : 0.0);
+                for (int k = 0; k < nd; ++k) {
+                    const double a = ws.T22(k, j);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) pv[g] += a * ws.col(k, g);
+                }
+                TREPB_UNROLL
+                for (int g = 0; g < kG; ++g) {
+                    if (g >= ng) continue;
+                    const int kindv = kv[g], i = iv[g];
+                    const double qv = ws.col(j, g);
+                    double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
+                    double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+                    if (q2o) q2o[(long)(i * nd + j) * es] = qv;
+                    if (p2o) p2o[(long)(i * nd + j) * es] = pv[g];
+                    if (kindv == 0) {
+                        if (o.A) { o.A[(long)(j * nX + i) * es] = qv; o.A[(long)((nq + j) * nX + i) * es] = pv[g]; }
+                    } else if (kindv == 1) {
+                        if (o.A) { o.A[(long)(j * nX + nq + i) * es] = qv; o.A[(long)((nq + j) * nX + nq + i) * es] = pv[g]; }
+                    } else if (kindv == 2) {
+                        if (o.B) { o.B[(long)(j * nU + i) * es] = qv; o.B[(long)((nq + j) * nU + i) * es] = pv[g]; }
+                    } else {
+                        if (o.B) { o.B[(long)(j * nU + nu + i) * es] = qv; o.B[(long)((nq + j) * nU + nu + i) * es] = pv[g]; }
+                    }
+                }
+            }
+            TREPB_UNROLL
+            for (int g = 0; g < kG; ++g) {
+                if (g >= ng) continue;
+                const int kindv = kv[g], i = iv[g];
+                double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+                if (l1o) {
+                    for (int c = 0; c < nc; ++c) l1o[(long)(i * nc + c) * es] = ws.tnc(c, g);
+                }
             }
         }
     }
+    TREPB_TICK(12);
     // constant blocks of A and B
     if (o.A) {
         TREPB_UNROLL_SYS
@@ -1265,6 +1427,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 o.B[(long)(r * nU + c) * es] = v;
             }
     }
+    TREPB_TICK(13);
     return ST_OK;
 }
 

@@ -13,7 +13,7 @@ import numpy as np
 from . import desc as D
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIBPATH = os.path.join(HERE, "libtrepb.so")
+LIBPATH = os.environ.get("TREPB_LIBPATH") or os.path.join(HERE, "libtrepb.so")
 
 if not os.path.exists(LIBPATH):
     raise ImportError("trep_b200/libtrepb.so is missing: build it with `python -m trep_b200.build` "
