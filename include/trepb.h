@@ -198,6 +198,15 @@ int trepb_linearize_batch_dev(trepb_system* sys, const trepb_lin_args* args, voi
 typedef struct trepb_d2_args {
     trepb_lin_args lin;
     double* d2[30];
+    /* Optional z-contracted forms, what DSystem.fdxdx(z) / fdxdu(z) / fdudu(z) return
+     * (trep/discopt/dsystem.py:320-386): sum over outputs of z_Qd * q2_dAdB + z_p * p2_dAdB,
+     * assembled in the DSystem state/input layout.  z: [B][nX] (only its Qd and p parts are read);
+     * fdxdx: [B][nX][nX], fdxdu: [B][nX][nU], fdudu: [B][nU][nU]; all NULL to skip.  This is the
+     * form the optimizer consumes (65 KB instead of 1.76 MB per marionette instance). */
+    const double* z;
+    double* fdxdx;
+    double* fdxdu;
+    double* fdudu;
 } trepb_d2_args;
 
 int trepb_deriv2_batch(trepb_system* sys, const trepb_d2_args* args);

@@ -151,6 +151,7 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     p.q1 = q1; p.u1 = uu.data(); p.q2 = q2.data(); p.lam = lam.data();
     for (int i = 0; i < 4; ++i) { p.q2_d[i] = qd[i].data(); p.l1_d[i] = ld[i].data(); }
     p.aux = aux.data(); p.auxl = al; p.status = nullptr;
+    p.z = nullptr; p.zxx = p.zxu = p.zuu = nullptr;
     for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
     for (int a = 0; a < p.nx; ++a)
         for (int b = a; b < p.nx; ++b) deriv2_pair(s, wh, p, 0, a, b);

@@ -81,7 +81,7 @@ struct trepb_system {
     DevBuf d2s[12];
     int bps_d2 = 1;
     // staging for the host-pointer entry points
-    DevBuf hb[64];
+    DevBuf hb[72];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     std::mutex mu;       // serialises launches on this handle
@@ -412,6 +412,14 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
     for (int w = 0; w < 3; ++w)
         for (int kd = 0; kd < 10; ++kd) p.out[w][kd] = a->d2[10 * w + kd];
     if (nc == 0) for (int kd = 0; kd < 10; ++kd) p.out[2][kd] = nullptr;
+    {
+        const size_t nX = 2 * (size_t)nq, nU = (size_t)(nu + nk);
+        p.z = a->z; p.zxx = a->z ? a->fdxdx : nullptr; p.zxu = a->z ? a->fdxdu : nullptr; p.zuu = a->z ? a->fdudu : nullptr;
+        if (p.zxx) CU(cudaMemsetAsync(p.zxx, 0, (size_t)B * nX * nX * sizeof(double), stream));
+        if (p.zxu && nU) CU(cudaMemsetAsync(p.zxu, 0, (size_t)B * nX * nU * sizeof(double), stream));
+        if (p.zuu && nU) CU(cudaMemsetAsync(p.zuu, 0, (size_t)B * nU * nU * sizeof(double), stream));
+        if (nU == 0) { p.zxu = nullptr; p.zuu = nullptr; }
+    }
     const long long threads = B * (long long)p.npairs;
     int block = s->block;
     const size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
@@ -495,7 +503,7 @@ namespace {
 struct Stager {
     trepb_system* s;
     int k = 0;
-    struct Out { void* host; void* dev; size_t bytes; } outs[64];
+    struct Out { void* host; void* dev; size_t bytes; } outs[72];
     int nout = 0;
     int err = 0;
     explicit Stager(trepb_system* s_) : s(s_) {}
@@ -607,6 +615,13 @@ int trepb_deriv2_batch(trepb_system* s, const trepb_d2_args* a) {
     for (int w = 0; w < 3; ++w)
         for (int kd = 0; kd < 10; ++kd)
             d.d2[10 * w + kd] = st.out(a->d2[10 * w + kd], B * cnt[ka[kd]] * cnt[kb[kd]] * (w == 2 ? nc : nd));
+    {
+        const size_t nX = 2 * nq, nU = nu + nk;
+        d.z = st.in(a->z, B * nX);
+        d.fdxdx = st.out(a->fdxdx, B * nX * nX);
+        d.fdxdu = st.out(a->fdxdu, B * nX * nU);
+        d.fdudu = st.out(a->fdudu, B * nU * nU);
+    }
     if (st.err) return st.err;
     int rc = trepb_deriv2_batch_dev(s, &d, nullptr);
     if (rc) return rc;

@@ -146,6 +146,29 @@ TREPB_HD void deriv2_pair(const Sys& sys, Ws& ws, const D2Params& p, long b, int
             if (mirror) op[((base_q + (long)it * cnt_t + is)) * nd + j] = pv;
         }
     }
+    if (p.z) {
+        // z-contraction in the DSystem layout: X = [Q; p; v], U = [u; rho]  (dsystem.py:320-386)
+        const int nX = 2 * nq, nU = nu + nk;
+        const double* z = p.z + (long)b * nX;
+        double acc = 0.0;
+        TREPB_UNROLL_SYS
+        for (int j = 0; j < nd; ++j) {
+            double pv = ws.p2(j).v;
+            TREPB_UNROLL_SYS
+            for (int k = 0; k < nd; ++k) pv += T22(k, j) * ws.fr(k).b;
+            acc += z[j] * ws.fr(j).b + z[nq + j] * pv;
+        }
+        const bool sx = ts < 2, tx = tt < 2;
+        const int xs = ts == 0 ? is : (ts == 1 ? nq + is : (ts == 2 ? is : nu + is));
+        const int xt = tt == 0 ? it : (tt == 1 ? nq + it : (tt == 2 ? it : nu + it));
+        if (sx && tx) {
+            if (p.zxx) { p.zxx[((long)b * nX + xs) * nX + xt] = acc; p.zxx[((long)b * nX + xt) * nX + xs] = acc; }
+        } else if (sx) {
+            if (p.zxu) p.zxu[((long)b * nX + xs) * nU + xt] = acc;
+        } else {
+            if (p.zuu) { p.zuu[((long)b * nU + xs) * nU + xt] = acc; p.zuu[((long)b * nU + xt) * nU + xs] = acc; }
+        }
+    }
     if (ol) {
         TREPB_UNROLL_SYS
         for (int cc = 0; cc < nc; ++cc) {

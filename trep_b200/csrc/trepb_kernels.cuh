@@ -83,6 +83,8 @@ struct D2Params {
     AuxLayout auxl;
     const int* status;              // instances whose step/deriv1 failed are skipped
     double* out[3][10];             // q2 / p2 / l1  x  pair kind ; any may be null
+    const double* z;                // [B][nX] or null: z-contracted outputs (DSystem.fdxdx(z) ...)
+    double *zxx, *zxu, *zuu;        // [B][nX][nX], [B][nX][nU], [B][nU][nU] (pre-zeroed)
 };
 
 

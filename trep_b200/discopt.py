@@ -119,6 +119,24 @@ class DSystem:
                                         tolerance=self.varint.tolerance)
         return out["A"], out["B"], out["status"]
 
+    def second_derivatives(self, X, U, Z, t1, t2, X_hint=None):
+        """z-contracted second derivatives of f for every instance: what the reference's
+        fdxdx(z), fdxdu(z), fdudu(z) (dsystem.py:320-386) return after set(X[i], U[i], k).
+        X [n,nX], U [n,nU], Z [n,nX], t1/t2 [n].  Returns (fdxdx [n,nX,nX], fdxdu [n,nX,nU],
+        fdudu [n,nU,nU]); the full 30 tensors are never materialised."""
+        X, U, Z = np.asarray(X, float), np.asarray(U, float), np.asarray(Z, float)
+        n = X.shape[0]
+        q1, p1, _ = self.split_state(X)
+        u1, rho2 = self.split_input(U)
+        hint = None if X_hint is None else np.asarray(X_hint, float)[:, :self._np]
+        out = self.varint.sys.deriv2(q1, p1, u1, rho2, t1=np.broadcast_to(np.asarray(t1, float), (n,)),
+                                     t2=np.broadcast_to(np.asarray(t2, float), (n,)), q2_guess=hint,
+                                     tolerance=self.varint.tolerance, z=Z, tensors=False)
+        bad = np.flatnonzero(out["status"] != 0)
+        if bad.size:
+            raise ConvergenceError("%d of %d instances failed" % (bad.size, n), out["status"])
+        return out["fdxdx"], out["fdxdu"], out["fdudu"]
+
     def linearize_trajectory(self, X, U, dist=None, compute=None):
         """Linearization about a trajectory (dsystem.py:406-423).  X [K+1, nX], U [K, nU] for one
         trajectory or X [R, K+1, nX], U [R, K, nU] for R rollouts sharing `time`.

@@ -55,7 +55,8 @@ D2_WHICH = ["q2", "p2", "l1"]
 
 
 class D2Args(C.Structure):
-    _fields_ = [("lin", LinArgs), ("d2", C.c_void_p * 30)]
+    _fields_ = [("lin", LinArgs), ("d2", C.c_void_p * 30), ("z", C.c_void_p), ("fdxdx", C.c_void_p),
+                ("fdxdu", C.c_void_p), ("fdudu", C.c_void_p)]
 
 
 _lib.trepb_last_error.restype = C.c_char_p
@@ -283,10 +284,13 @@ class System:
         else:
             _check(_lib.trepb_linearize_batch(self._h, C.byref(a)))
 
-    def deriv2_raw(self, on_device, batch, q1, p1, u1, k2, status, d2, stream=None, **kw):
-        """d2: {"q2_dq1dq1": array, ...} any subset of D2_WHICH x D2_KINDS."""
+    def deriv2_raw(self, on_device, batch, q1, p1, u1, k2, status, d2, stream=None, z=None,
+                   fdxdx=None, fdxdu=None, fdudu=None, **kw):
+        """d2: {"q2_dq1dq1": array, ...} any subset of D2_WHICH x D2_KINDS; z + fdxdx/fdxdu/fdudu:
+        the z-contracted forms of DSystem.fdxdx(z) / fdxdu(z) / fdudu(z)."""
         a = D2Args()
         a.lin = self._lin_args(batch, q1, p1, u1, k2, status, **kw)
+        a.z, a.fdxdx, a.fdxdu, a.fdudu = _ptr(z), _ptr(fdxdx), _ptr(fdxdu), _ptr(fdudu)
         for n, v in d2.items():
             w, kd = n.split("_")
             a.d2[10 * D2_WHICH.index(w) + D2_KINDS.index(kd)] = _ptr(v)
@@ -389,7 +393,7 @@ class System:
         return out
 
     def deriv2(self, q1, p1, u1=None, k2=None, t1=0.0, t2=None, dt=None, q2_guess=None,
-               lambda_guess=None, tolerance=1e-10, max_iterations=200):
+               lambda_guess=None, tolerance=1e-10, max_iterations=200, z=None, tensors=True):
         """solve + first derivatives + every second-derivative tensor (reference layout
         [B][wrt A][wrt B][out]); returns the dict of `linearize(want_raw=True)` plus the tensors."""
         q1 = np.atleast_2d(np.asarray(q1, float))
@@ -406,9 +410,16 @@ class System:
                    A=np.empty((B, self.nX, self.nX)), B=np.zeros((B, self.nX, self.nU)))
         wrt = {"dq1": self.nq, "dp1": self.nd, "du1": self.nu, "dk2": self.nk}
         rawbufs = {n: np.zeros((B, wrt[n[3:]], self.nc if n.startswith("l1") else self.nd)) for n in RAW}
-        d2 = {n: np.zeros(sh) for n, sh in self.d2_shapes(B).items()}
+        d2 = {n: np.zeros(sh) for n, sh in self.d2_shapes(B).items()} if tensors else {}
+        zk = {}
+        if z is not None:
+            zk = dict(z=self._f(z, (B, self.nX)), fdxdx=np.zeros((B, self.nX, self.nX)),
+                      fdxdu=np.zeros((B, self.nX, self.nU)), fdudu=np.zeros((B, self.nU, self.nU)))
+            out.update({k: v for k, v in zk.items() if k != "z"})
+            if not self.nU:
+                zk["fdxdu"] = zk["fdudu"] = None
         self.deriv2_raw(False, B, q1, p1, u1 if self.nu else None, k2 if self.nk else None, out["status"],
-                        {n: v for n, v in d2.items() if v.size}, t1=t1a, t2=t2a, q2_guess=q2g,
+                        {n: v for n, v in d2.items() if v.size}, **zk, t1=t1a, t2=t2a, q2_guess=q2g,
                         lambda_guess=lg, q2=out["q2"], p2=out["p2"],
                         lambda1=out["lambda1"] if self.nc else None, iters=out["iters"], A=out["A"],
                         B=out["B"] if self.nU else None, raw={k: v for k, v in rawbufs.items() if v.size},
