@@ -189,11 +189,75 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     for b in (dq, dp, du, q2, p2, it, st, A, Bm):
         b.free()
     s.close()
+    # ---- W3 pipeline on the device: 4096 rollouts x 10000 steps by the step kernel (trajectory
+    #      captured in HBM), then every (X[k], U[k], hint X[k+1]) linearized in one launch: the
+    #      exact-hint case of DSystem.linearize_trajectory (0 Newton iterations)
+    d = systems.named_desc("pend_on_cart1")
+    s = lib.System(d, device=device)
+    R, K = 4096, 10000
+    tt = DT * np.arange(K)
+    amp = rng.uniform(0, 2, (R, 1)); om = rng.uniform(0.5, 3, (R, 1))
+    U = (amp * np.sin(om * tt[None, :]))[:, :, None]
+    q0 = np.zeros((R, 2)); q0[:, 1] = rng.uniform(-0.5, 0.5, R)
+    du = up(U); dq0 = up(q0); dp0 = up(np.zeros((R, 2)))
+    tq = lib.DeviceBuffer(device, (R, K, 2)); tp = lib.DeviceBuffer(device, (R, K, 2))
+    q2 = lib.DeviceBuffer(device, (R, 2)); p2 = lib.DeviceBuffer(device, (R, 2))
+    itr = lib.DeviceBuffer(device, (R,), np.int32); sr = lib.DeviceBuffer(device, (R,), np.int32)
+    s.step_raw(True, R, K, 0.0, DT, dq0, dp0, du, None, None, None, q2, p2, None, itr, sr, sample_every=1, traj_q=tq, traj_p=tp)
+    lib.synchronize(device)
+    roll_ms = s.last_kernel_ms()
+
+    class Off:
+        def __init__(self, buf, off_bytes): self.p = buf.data_ptr() + off_bytes
+        def data_ptr(self): return self.p
+    n = R * K - 1
+    A = lib.DeviceBuffer(device, (n, 4, 4)); Bm = lib.DeviceBuffer(device, (n, 4, 1))
+    it = lib.DeviceBuffer(device, (n,), np.int32); st = lib.DeviceBuffer(device, (n,), np.int32)
+    ms = []
+    for rep in range(4):
+        s.linearize_raw(True, n, tq, tp, Off(du, 8), None, st, t1_scalar=0.0, dt_scalar=DT, q2_guess=Off(tq, 16),
+                        iters=it, A=A, B=Bm)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    t = float(np.mean(ms))
+    byt = 16 + 16 + 8 + 16 + 160 + 8      # q1, p1, u1, hint in; A, B, iters, status out
+    out.append({"metric": "linearizations/s (W3: pend-on-cart linearize_trajectory, 4096 rollouts x 10000 steps, exact hints)",
+                "value": n / t * 1e3, "unit": "linearizations/s", "batch": n, "ms": t,
+                "newton_iters_mean": float(it.download().mean()), "ok_fraction": float((st.download() == 0).mean()),
+                "rollout_kernel_ms": roll_ms, "rollout_steps_per_s": R * K / roll_ms * 1e3,
+                "roofline": {"bound": "hbm", "achieved": n * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": n * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt}})
+    for b in (du, dq0, dp0, tq, tp, q2, p2, itr, sr, A, Bm, it, st):
+        b.free()
+    s.close()
+    # ---- W4-shaped: dual pendulums (LinearSpring + LinearDamper), 2^22 instances x 100 steps
+    d = systems.named_desc("dual_pendulums")
+    s = lib.System(d, device=device)
+    B = 1 << 22
+    q = rng.uniform(-np.pi, np.pi, (B, 2))
+    dq = up(q); dp = lib.DeviceBuffer(device, (B, 2))
+    s.calc_p2_raw(True, B, DT, dq, dq, dp)
+    q2 = lib.DeviceBuffer(device, (B, 2)); p2 = lib.DeviceBuffer(device, (B, 2))
+    it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+    ms = []
+    for rep in range(3):
+        s.step_raw(True, B, 100, DT, DT, dq, dp, None, None, None, None, q2, p2, None, it, st)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    t = float(np.mean(ms))
+    out.append({"metric": "DEL steps/s (W4: dual pendulums Monte-Carlo sweep, 2^22 instances x 100 steps)", "value": B * 100 / t * 1e3,
+                "unit": "DEL steps/s", "batch": B, "ms": t, "newton_iters_per_step": float(it.download().mean()) / 100,
+                "ok_fraction": float((st.download() == 0).mean())})
+    for b in (dq, dp, q2, p2, it, st):
+        b.free()
+    s.close()
     # ---- marionette
     d = systems.named_desc("puppet")
     g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
     s = lib.System(d, device=device)
-    B = 32768
+    B = 65536
     idx = rng.integers(1, 58, B)
     q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
     q1[:, :d.nd] += rng.normal(0, 0.02, (B, d.nd)); p1 += rng.normal(0, 0.02, (B, d.nd))
@@ -209,10 +273,33 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         if rep >= 1:
             ms.append(s.last_kernel_ms())
     t = float(np.mean(ms))
-    out.append({"metric": "linearizations/s (marionette nd22/nk18/nc6, solve + deriv1 -> A,B)", "value": B / t * 1e3,
-                "unit": "linearizations/s", "batch": B, "ms": t, "newton_iters_mean": float(it.download().mean()),
-                "ok_fraction": float((st.download() == 0).mean())})
-    for b in (dq, dp, dk, dl, q2, p2, l2, it, st, A, Bm):
+    entry = {"metric": "linearizations/s (W5: marionette nd22/nk18/nc6, solve + deriv1 -> A,B)", "value": B / t * 1e3,
+             "unit": "linearizations/s", "batch": B, "ms": t, "newton_iters_mean": float(it.download().mean()),
+             "ok_fraction": float((st.download() == 0).mean())}
+    fj = os.path.join(ROOT, "profiles", "flops.json")
+    if os.path.exists(fj):
+        fl = json.load(open(fj)).get("puppet_lin_flops_per_linearization")
+        if fl:
+            ach = fl * B / (t * 1e-3) / 1e12
+            entry["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                                 "traffic": None, "flops_per_unit": fl,
+                                 "note": "latency/L2-bound table-driven kernel; see DESIGN.md section 6"}
+    out.append(entry)
+    # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
+    Bd = 1024
+    z = up(rng.normal(0, 1, (Bd, d.nX)))
+    xx = lib.DeviceBuffer(device, (Bd, d.nX, d.nX)); xu = lib.DeviceBuffer(device, (Bd, d.nX, d.nU)); uu = lib.DeviceBuffer(device, (Bd, d.nU, d.nU))
+    ms = []
+    for rep in range(2):
+        s.deriv2_raw(True, Bd, dq, dp, None, dk, st, {}, z=z, fdxdx=xx, fdxdu=xu, fdudu=uu, t1_scalar=0.0, dt_scalar=DT,
+                     lambda_guess=dl)
+        lib.synchronize(device)
+        ms.append(s.last_kernel_ms())
+    t = float(ms[-1])
+    out.append({"metric": "second-derivative evaluations/s (W5: marionette, 3240 parameter pairs, z-contracted fdxdx/fdxdu/fdudu)",
+                "value": Bd / t * 1e3, "unit": "evaluations/s", "batch": Bd, "ms": t,
+                "note": "d2 kernel only (the preceding linearize launch is the line above)"})
+    for b in (dq, dp, dk, dl, q2, p2, l2, it, st, A, Bm, z, xx, xu, uu):
         b.free()
     s.close()
     return out

@@ -132,12 +132,18 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
         if (!vel && !wrl) continue;
         const Real x = cfg >= 0 ? ws.qe(cfg) : sys.value(f);
         Real g[3], V[6], R[9], p[3];
+        // vz: no variable joint above f, so the velocity carried in from the parent is exactly zero
+        // and every operation on it can be dropped without changing a single bit of the result
+        const bool vz = sys.vzero(f);
         if (vel) {
             if (par == 0) {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = sys.gravity(k);
-                TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k] = 0.0;
             } else {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = ws.gf(par, k);
+            }
+            if (vz) {
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k] = 0.0;
+            } else {
                 TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k] = ws.V(par, k);
             }
         }
@@ -159,11 +165,13 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
             if (vel) {
                 Real t[3], u[3];
                 // v' = R^T (v + w x p), w' = R^T w, g' = R^T g
-                cross3(V + 3, lp, t);
-                TREPB_UNROLL for (int k = 0; k < 3; ++k) t[k] += V[k];
-                TREPB_UNROLL for (int c = 0; c < 3; ++c) u[c] = lR[c] * t[0] + lR[3 + c] * t[1] + lR[6 + c] * t[2];
-                TREPB_UNROLL for (int c = 0; c < 3; ++c) t[c] = lR[c] * V[3] + lR[3 + c] * V[4] + lR[6 + c] * V[5];
-                TREPB_UNROLL for (int k = 0; k < 3; ++k) { V[k] = u[k]; V[3 + k] = t[k]; }
+                if (!vz) {
+                    cross3(V + 3, lp, t);
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) t[k] += V[k];
+                    TREPB_UNROLL for (int c = 0; c < 3; ++c) u[c] = lR[c] * t[0] + lR[3 + c] * t[1] + lR[6 + c] * t[2];
+                    TREPB_UNROLL for (int c = 0; c < 3; ++c) t[c] = lR[c] * V[3] + lR[3 + c] * V[4] + lR[6 + c] * V[5];
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { V[k] = u[k]; V[3 + k] = t[k]; }
+                }
                 TREPB_UNROLL for (int c = 0; c < 3; ++c) u[c] = lR[c] * g[0] + lR[3 + c] * g[1] + lR[6 + c] * g[2];
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) g[k] = u[k];
             }
@@ -188,8 +196,10 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
                     ws.cs(f, 0) = cs;
                     ws.cs(f, 1) = sn;
                     rotT(g, ax.b, ax.c, cs, sn);
-                    rotT(V, ax.b, ax.c, cs, sn);
-                    rotT(V + 3, ax.b, ax.c, cs, sn);
+                    if (!vz) {
+                        rotT(V, ax.b, ax.c, cs, sn);
+                        rotT(V + 3, ax.b, ax.c, cs, sn);
+                    }
                 }
                 if (wrl) {
                     TREPB_UNROLL for (int r = 0; r < 3; ++r) {
@@ -199,7 +209,7 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
                     }
                 }
             } else {
-                if (vel) {
+                if (vel && !vz) {
                     // v' = v + w x (x e_a)
                     V[ax.b] += x * V[3 + ax.c];
                     V[ax.c] -= x * V[3 + ax.b];
@@ -210,20 +220,23 @@ TREPB_HD void pass1(const Sys& sys, Ws& ws, bool with_vel, bool with_world) {
             }
             if (vel && cfg >= 0) {
                 // W = [S, s] with S the velocity carried in from the parent
-                Real W[6];
-                TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = 0.0;
-                if (ax.rot) {
-                    W[ax.b] = V[ax.c];          // v_S x e_a
-                    W[ax.c] = -V[ax.b];
-                    W[3 + ax.b] = V[3 + ax.c];  // w_S x e_a
-                    W[3 + ax.c] = -V[3 + ax.b];
-                    V[3 + ax.a] += ws.dq(cfg);
-                } else {
-                    W[ax.b] = V[3 + ax.c];      // w_S x e_a
-                    W[ax.c] = -V[3 + ax.b];
-                    V[ax.a] += ws.dq(cfg);
+                // (W is identically zero when vz: neither stored here nor read in pass 2)
+                if (!vz) {
+                    Real W[6];
+                    TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = 0.0;
+                    if (ax.rot) {
+                        W[ax.b] = V[ax.c];          // v_S x e_a
+                        W[ax.c] = -V[ax.b];
+                        W[3 + ax.b] = V[3 + ax.c];  // w_S x e_a
+                        W[3 + ax.c] = -V[3 + ax.b];
+                    } else {
+                        W[ax.b] = V[3 + ax.c];      // w_S x e_a
+                        W[ax.c] = -V[3 + ax.b];
+                    }
+                    TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.W(f, k) = W[k];
                 }
-                TREPB_UNROLL for (int k = 0; k < 6; ++k) ws.W(f, k) = W[k];
+                if (ax.rot) V[3 + ax.a] += ws.dq(cfg);
+                else V[ax.a] += ws.dq(cfg);
             }
         }
         if (vel) {
@@ -346,13 +359,17 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
 
         if (cfg >= 0) {
             const Axis ax = axis_of(kind);
+            const bool wz = sys.vzero(f);   // W_f == 0 identically (first variable joint of its chain)
             Real W[6];
-            TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = ws.W(f, k);
+            if (wz) { TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = 0.0; }
+            else { TREPB_UNROLL for (int k = 0; k < 6; ++k) W[k] = ws.W(f, k); }
             // first order: L_ddq = s.mu ; L_dq = W.mu + g.(m v_s + w_s x h)
             Real hxg[3];
             cross3(h, g, hxg);
             ws.Lv(cfg) = ax.rot ? mu[3 + ax.a] : mu[ax.a];
-            ws.Lq(cfg) = dot6(W, mu) + (sys.gravity_on() ? (ax.rot ? hxg[ax.a] : m * g[ax.a]) : 0.0);
+            const Real grav1 = sys.gravity_on() ? (ax.rot ? hxg[ax.a] : m * g[ax.a]) : Real(0.0);
+            if (wz) ws.Lq(cfg) = grav1;
+            else ws.Lq(cfg) = dot6(W, mu) + grav1;
             if (order >= 2) {
                 Real H[6], G[6], N[3], P[3], t[3];
                 // H = Ic s
@@ -369,7 +386,8 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                     H[3 + ax.c] = -h[ax.b];
                 }
                 // G = Ic W - ad*_s mu ;  ad*_s mu = (f x w_s, n x w_s + f x v_s)
-                inertia_apply(m, h, I, W, G);
+                if (wz) { TREPB_UNROLL for (int k = 0; k < 6; ++k) G[k] = 0.0; }
+                else inertia_apply(m, h, I, W, G);
                 if (ax.rot) {
                     G[ax.b] -= mu[ax.c];
                     G[ax.c] += mu[ax.b];
@@ -398,9 +416,11 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                         const Axis ai = axis_of(sys.kind(cur));
                         const Real sH = ai.rot ? H[3 + ai.a] : H[ai.a];
                         const Real sG = ai.rot ? G[3 + ai.a] : G[ai.a];
+                        const bool wzi = sys.vzero(cur);
                         Real Wi[6];
-                        TREPB_UNROLL for (int k = 0; k < 6; ++k) Wi[k] = ws.W(cur, k);
-                        Real WG = dot6(Wi, G);
+                        if (wzi) { TREPB_UNROLL for (int k = 0; k < 6; ++k) Wi[k] = 0.0; }
+                        else { TREPB_UNROLL for (int k = 0; k < 6; ++k) Wi[k] = ws.W(cur, k); }
+                        Real WG = wzi ? Real(0.0) : dot6(Wi, G);
                         if (sys.gravity_on() && ai.rot) WG += N[ai.a];
                         if (ci == cfg) {
                             ws.Lvv(cfg, cfg) = sH;
@@ -410,7 +430,7 @@ TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
                             ws.Lvv(ci, cfg) = sH;
                             ws.Lvv(cfg, ci) = sH;
                             ws.Lvq(ci, cfg) = sG;
-                            ws.Lvq(cfg, ci) = dot6(Wi, H);
+                            ws.Lvq(cfg, ci) = wzi ? Real(0.0) : dot6(Wi, H);
                             ws.Lqq(ci, cfg) = WG;
                             ws.Lqq(cfg, ci) = WG;
                         }

@@ -17,7 +17,7 @@ struct PackedSys {
     size_t off[32];
     int nf, nq;
     std::vector<int32_t> cfg_frame;
-    std::vector<uint8_t> dep, mass_below, need_world;
+    std::vector<uint8_t> dep, mass_below, need_world, vzero;
 
     RtSys view(const char* base) const {
         RtSys s = proto;
@@ -43,6 +43,7 @@ struct PackedSys {
         s.dep_ = (const uint8_t*)(base + off[k++]);
         s.mass_below_ = (const uint8_t*)(base + off[k++]);
         s.need_world_ = (const uint8_t*)(base + off[k++]);
+        s.vzero_ = (const uint8_t*)(base + off[k++]);
         return s;
     }
 };
@@ -87,6 +88,11 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
         const double* m = d->frame_mass + 4 * f;
         if (m[0] != 0.0 || m[1] != 0.0 || m[2] != 0.0 || m[3] != 0.0) mass_below[f] = 1;
         if (mass_below[f]) mass_below[d->frame_parent[f]] = 1;
+    }
+    std::vector<uint8_t> vzero(nf, 1);
+    for (int f = 1; f < nf; ++f) {
+        const int p = d->frame_parent[f];
+        vzero[f] = (p == 0) ? 1 : (vzero[p] && d->frame_config[p] < 0 ? 1 : 0);
     }
     auto mark_world = [&](int f) {
         while (f > 0 && !need_world[f]) { need_world[f] = 1; f = d->frame_parent[f]; }
@@ -137,7 +143,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
     // ---- pack
     PackedSys& P = *out;
     P.nf = nf; P.nq = nq;
-    P.cfg_frame = cfg_frame; P.dep = dep; P.mass_below = mass_below; P.need_world = need_world;
+    P.cfg_frame = cfg_frame; P.dep = dep; P.mass_below = mass_below; P.need_world = need_world; P.vzero = vzero;
     memset(&P.proto, 0, sizeof(P.proto));
     P.proto.nf = nf; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
     P.proto.npot = np; P.proto.nforce = nfo; P.proto.max_depth = max_depth;
@@ -172,6 +178,7 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
     put(dep.data(), dep.size());
     put(mass_below.data(), mass_below.size());
     put(need_world.data(), need_world.size());
+    put(vzero.data(), vzero.size());
     return true;
 }
 

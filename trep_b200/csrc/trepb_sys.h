@@ -42,6 +42,7 @@ struct RtSys {
     const uint8_t* dep_;        // [nf][nq]  frame f depends on config c
     const uint8_t* mass_below_; // [nf]  subtree of f (incl. f) carries mass
     const uint8_t* need_world_; // [nf]  world pose needed (point-pair consumer below)
+    const uint8_t* vzero_;      // [nf]  no variable joint above f: velocity carried into f is exactly 0
     const int32_t* pot_kind_;  const int32_t* pot_i_;  const double* pot_d_;
     const int32_t* force_kind_; const int32_t* force_i_; const double* force_d_;
     const int32_t* con_kind_;  const int32_t* con_i_;  const double* con_d_;
@@ -72,6 +73,7 @@ struct RtSys {
     TREPB_HD bool dep(int f, int c) const { return dep_[f * (nd + nk) + c] != 0; }
     TREPB_HD bool mass_below(int f) const { return mass_below_[f] != 0; }
     TREPB_HD bool need_world(int f) const { return need_world_[f] != 0; }
+    TREPB_HD bool vzero(int f) const { return vzero_[f] != 0; }
     TREPB_HD bool has_mass(int f) const {
         return mass(f, 0) != 0.0 || mass(f, 1) != 0.0 || mass(f, 2) != 0.0 || mass(f, 3) != 0.0;
     }
@@ -98,7 +100,7 @@ struct RtSys {
         TREPB_RB(int32_t, frame_parent) TREPB_RB(int32_t, frame_kind) TREPB_RB(int32_t, frame_config)
         TREPB_RB(double, frame_value) TREPB_RB(double, frame_se3) TREPB_RB(double, frame_mass)
         TREPB_RB(int32_t, cfg_frame_) TREPB_RB(uint8_t, dep_) TREPB_RB(uint8_t, mass_below_)
-        TREPB_RB(uint8_t, need_world_)
+        TREPB_RB(uint8_t, need_world_) TREPB_RB(uint8_t, vzero_)
         TREPB_RB(int32_t, pot_kind_) TREPB_RB(int32_t, pot_i_) TREPB_RB(double, pot_d_)
         TREPB_RB(int32_t, force_kind_) TREPB_RB(int32_t, force_i_) TREPB_RB(double, force_d_)
         TREPB_RB(int32_t, con_kind_) TREPB_RB(int32_t, con_i_) TREPB_RB(double, con_d_)
