@@ -1,5 +1,5 @@
 """One short launch of each hot kernel, for ncu (development/profiling aid).
-usage: python tools/profile_step.py [step|lin|puppet|all]"""
+usage: python tools/profile_step.py [step|lin|puppet|d2|all]"""
 import os, sys
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -51,3 +51,19 @@ if mode in ("puppet", "all"):
                         lambda1=l2, iters=it, A=A, B=Bm)
     lib.synchronize(0)
     print("puppet lin: B=%d ms=%.3f iters=%.2f" % (B, s.last_kernel_ms(), it.download().mean()))
+
+if mode in ("d2", "all"):
+    B = int(os.environ.get("D2_B", "128"))
+    d = systems.named_desc("puppet"); s = lib.System(d)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
+    idx = rng.integers(1, 58, B)
+    q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
+    q1[:, :d.nd] += rng.normal(0, 0.02, (B, d.nd)); p1 += rng.normal(0, 0.02, (B, d.nd))
+    dq, dp, dk, dl = up(q1), up(p1), up(g["roll_k2"][idx]), up(g["roll_lambda"][idx - 1])
+    st = lib.DeviceBuffer(0, (B,), np.int32)
+    z = up(rng.normal(0, 1, (B, d.nX)))
+    xx = lib.DeviceBuffer(0, (B, d.nX, d.nX)); xu = lib.DeviceBuffer(0, (B, d.nX, d.nU)); uu = lib.DeviceBuffer(0, (B, d.nU, d.nU))
+    for _ in range(2):
+        s.deriv2_raw(True, B, dq, dp, None, dk, st, {}, z=z, fdxdx=xx, fdxdu=xu, fdudu=uu, t1_scalar=0.0, dt_scalar=0.01, lambda_guess=dl)
+    lib.synchronize(0)
+    print("puppet d2: B=%d ms=%.3f" % (B, s.last_kernel_ms()))

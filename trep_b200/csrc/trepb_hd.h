@@ -16,7 +16,7 @@ namespace trepb {
 
 struct HD {
     double v, a, b, ab;
-    TREPB_HD HD() {}
+    HD() = default;
     TREPB_HD HD(double x) : v(x), a(0.0), b(0.0), ab(0.0) {}
     TREPB_HD HD(double v_, double a_, double b_, double ab_) : v(v_), a(a_), b(b_), ab(ab_) {}
 };
@@ -45,12 +45,12 @@ TREPB_HD HD hd_inv(const HD& y) {
 TREPB_HD HD operator/(const HD& x, const HD& y) { return x * hd_inv(y); }
 TREPB_HD HD operator/(double x, const HD& y) { return x * hd_inv(y); }
 TREPB_HD HD operator/(const HD& x, double y) { return x * (1.0 / y); }
-TREPB_HD HD& operator+=(HD& x, const HD& y) { x = x + y; return x; }
-TREPB_HD HD& operator-=(HD& x, const HD& y) { x = x - y; return x; }
+TREPB_HD HD& operator+=(HD& x, const HD& y) { x.v += y.v; x.a += y.a; x.b += y.b; x.ab += y.ab; return x; }
+TREPB_HD HD& operator-=(HD& x, const HD& y) { x.v -= y.v; x.a -= y.a; x.b -= y.b; x.ab -= y.ab; return x; }
 TREPB_HD HD& operator*=(HD& x, const HD& y) { x = x * y; return x; }
 TREPB_HD HD& operator+=(HD& x, double y) { x.v += y; return x; }
 TREPB_HD HD& operator-=(HD& x, double y) { x.v -= y; return x; }
-TREPB_HD HD& operator*=(HD& x, double y) { x = x * y; return x; }
+TREPB_HD HD& operator*=(HD& x, double y) { x.v *= y; x.a *= y; x.b *= y; x.ab *= y; return x; }
 
 TREPB_HD void sincos_(const HD& x, HD* s, HD* c) {
     double sn, cs;
