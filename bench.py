@@ -257,7 +257,7 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     d = systems.named_desc("puppet")
     g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
     s = lib.System(d, device=device)
-    B = 65536
+    B = 131072          # >= 148 SMs x 16 resident warps x 32 lanes, so the table-driven kernel fills the GPU
     idx = rng.integers(1, 58, B)
     q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
     q1[:, :d.nd] += rng.normal(0, 0.02, (B, d.nd)); p1 += rng.normal(0, 0.02, (B, d.nd))
@@ -278,12 +278,19 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
              "ok_fraction": float((st.download() == 0).mean())}
     fj = os.path.join(ROOT, "profiles", "flops.json")
     if os.path.exists(fj):
-        fl = json.load(open(fj)).get("puppet_lin_flops_per_linearization")
+        prof = json.load(open(fj))
+        fl = prof.get("puppet_lin_flops_per_linearization")
+        tb = prof.get("puppet_lin_dram_bytes_per_linearization")
+        alg = 8 * (d.nq + d.nd + d.nk + d.nc) + 8 * (d.nX * d.nX + d.nX * d.nU + d.nq + d.nd + d.nc) + 8
         if fl:
             ach = fl * B / (t * 1e-3) / 1e12
-            entry["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
-                                 "traffic": None, "flops_per_unit": fl,
-                                 "note": "latency/L2-bound table-driven kernel; see DESIGN.md section 6"}
+            entry["roofline"] = {"bound": "hbm", "achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg,
+                                 "traffic": tb * B if tb else None,
+                                 "fp64": {"achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "flops_per_unit": fl},
+                                 "note": "neither roofline is approached: one thread per instance with a ~144 KB strided global "
+                                         "workspace; measured DRAM traffic per linearization (ncu, profiles/r01c_puppet_raw.txt) is ~20x "
+                                         "the algorithmic bytes - the workspace traffic is what bounds it (DESIGN.md section 6)"}
     out.append(entry)
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
     Bd = 1024
@@ -419,8 +426,11 @@ def main():
         if os.path.exists(fj):
             flops_per_step = json.load(open(fj)).get("damped_pendulum_step_flops_per_del_step")
         kms = total_ms / args.steps
-        roof = {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s", "traffic": None,
+        roof = {"bound": "fp64", "peak": fp64_peak, "unit": "TFLOP/s", "traffic": BATCH * 40,
                 "peak_source": "in-run DFMA micro-benchmark (trepb_measure_fp64_peak); MEASURED_PEAKS.json has no fp64 entry",
+                "traffic_note": "algorithmic HBM bytes per launch (16 B in + 24 B out per rollout of 1000 steps); ncu "
+                                "dram__bytes of a 50-step launch: 16.8 MB read, <1 KB written back before the kernel ends "
+                                "(profiles/r01c_step_raw.txt) - the kernel is on-chip",
                 "kernel": "step_kernel<damped_pendulum>", "kernel_ms": kms}
         if flops_per_step:
             ach = flops_per_step * BATCH * NSTEPS / (kms * 1e-3) / 1e12

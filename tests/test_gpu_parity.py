@@ -272,3 +272,16 @@ def test_second_derivatives_by_finite_differences_where_the_reference_has_none(l
         assert np.max(np.abs(fd[0] - out["q2_dq1dq1"][0, a])) < 2e-6 * max(1.0, np.max(np.abs(fd)))
         fd = (lp["p2_dp1"] - lm["p2_dp1"]) / (2 * eps)
         assert np.max(np.abs(fd[0] - out["p2_dq1dp1"][0, a])) < 2e-6 * max(1.0, np.max(np.abs(fd)))
+
+
+def test_singular_jacobian_status(lib):
+    """A massless dynamic joint makes the DEL Jacobian singular: the reference raises ValueError from
+    LU_decomp (math-code.c:393-398) -> ConvergenceError (midpointvi.py:198-201); here status -2."""
+    from trep_b200 import model as M
+    s = M.System()
+    s.import_frames([M.rx("a"), [M.tz(-1.0)]])
+    M.Gravity(s)
+    h = lib.System(s.describe())
+    out = h.step(np.array([[0.1], [0.2]]), np.array([[1.0], [0.0]]), 0.0, 0.01)
+    assert out["status"][0] == -2
+    assert out["status"][1] == 0 and out["iters"][1] == 0    # p = 0, no mass: already a solution

@@ -52,3 +52,35 @@ def test_json_round_trip():
     for n in G.ALL:
         d = G.desc(n)
         assert D.SystemDesc.from_json(d.to_json()).equal(d)
+
+
+def test_flatten_of_live_reference_systems_equals_the_mirror():
+    """flatten_trep_system on the reference's own objects (oracle/_ref) gives the description the
+    native model mirror gives - the drop-in route and the script route agree."""
+    import os
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "oracle", "_ref", "trep")):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import ref_systems as R
+    for n in G.ALL:
+        d = M.flatten_trep_system(R.REF_BUILDERS[n](), name=n)
+        assert d.equal(G.desc(n)), n
+
+
+def test_unsupported_plugins_are_refused_not_approximated():
+    import os
+    import sys
+    import pytest
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if not os.path.isdir(os.path.join(root, "oracle", "_ref", "trep")):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    import ref_systems as R
+    trep = R.trep
+    system = R.REF_BUILDERS["pendulum1"]()
+    trep.constraints.PointOnPlane(system, system.world_frame, (0, 0, 1), system.frames[-1])
+    with pytest.raises(TypeError):
+        M.flatten_trep_system(system)

@@ -162,6 +162,11 @@ struct SpecRegistrar {
 const KernelSet* general_kernels();
 
 #if defined(__CUDACC__)
+// minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (128 * N));
+// experiments: -DTREPB_LB_MIN=6 ...
+#ifndef TREPB_LB_MIN
+#define TREPB_LB_MIN 1
+#endif
 // ---------------------------------------------------------------------------------------------
 template <class Sys, bool S = Sys::kStatic>
 struct Ctx;
@@ -196,7 +201,7 @@ struct Ctx<Sys, false> {
 };
 
 template <class Sys>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TREPB_LB_MIN)
 step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const StepParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
@@ -285,7 +290,7 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
 }
 
 template <class Sys>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TREPB_LB_MIN)
 lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
