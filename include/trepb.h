@@ -98,6 +98,9 @@ typedef struct trepb_system trepb_system; /* opaque */
 
 /* flags for trepb_system_create */
 #define TREPB_FLAG_NO_SPECIALIZE 1  /* use the table-driven general kernels even for small systems */
+#define TREPB_FLAG_NO_COOP 2        /* table-driven systems: always one thread per instance */
+#define TREPB_FLAG_FORCE_COOP 4     /* table-driven systems: always the cooperative kernels (one warp per
+                                       instance, workspace in shared memory); fails if they do not apply */
 
 int  trepb_abi_version(void);
 const char* trepb_last_error(void);
@@ -105,7 +108,9 @@ const char* trepb_last_error(void);
 /* Validate + flatten + upload tables to `device`.  If the description's structural hash matches
  * one of the systems specialised ahead of time (generated constexpr system, fully unrolled,
  * register-resident; see trepb_codegen) that kernel set is used, otherwise the table-driven
- * general kernels. */
+ * kernels: one thread per instance for small systems, the cooperative kernels (one warp per
+ * instance, link tables and workspace in shared memory) when the per-instance workspace is too
+ * large to stay on chip (e.g. the marionette). */
 int  trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out);
 void trepb_system_destroy(trepb_system* sys);
 int  trepb_system_dims(const trepb_system* sys, int32_t* nq, int32_t* nd, int32_t* nk,
@@ -113,6 +118,8 @@ int  trepb_system_dims(const trepb_system* sys, int32_t* nq, int32_t* nd, int32_
 /* 1 if a specialised (compile-time frame tree) kernel is in use, 0 if table-driven. */
 int  trepb_system_is_specialized(const trepb_system* sys);
 const char* trepb_system_kernel_name(const trepb_system* sys);
+/* 1 if the cooperative kernels (one warp per instance, shared-memory workspace) are in use. */
+int  trepb_system_is_cooperative(const trepb_system* sys);
 /* Launch facts of kernel `which` (0 step, 1 calc_p2, 2 linearize) for this system. */
 int  trepb_kernel_info(trepb_system* sys, int which, int32_t* regs, int32_t* local_bytes,
                        int32_t* blocks_per_sm, int32_t* block, int32_t* smem_bytes);

@@ -7,6 +7,7 @@
 #include "../include/trepb.h"
 #include "../trep_b200/csrc/trepb_kernels.cuh"
 #include "../trep_b200/csrc/trepb_pack.h"
+#include "../trep_b200/csrc/trepb_coop_math.cuh"
 
 using namespace trepb;
 
@@ -155,6 +156,81 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
     for (int a = 0; a < p.nx; ++a)
         for (int b = a; b < p.nx; ++b) deriv2_pair(s, wh, p, 0, a, b);
+    return 0;
+}
+
+// ---- team-cooperative path (trepb_coop_math.cuh) with a one-lane host team
+// returns -200 when the cooperative path does not apply to this system
+int th_coop_linearize(const trepb_sysdesc* d, int nsteps, double t1, double dt, double tol, int maxit,
+                      const double* q1, const double* p1, const double* u1, const double* k2,
+                      const double* q2_guess, const double* lam_guess, double* q2, double* p2,
+                      double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
+    std::string err;
+    PackedSys chk;
+    if (!pack_system(d, &chk, &err)) return -100;
+    CoopPack P = coop_pack(d);
+    if (!P.ok) return -200;
+    CoopSys S = P.view(P.blob.data());
+    CoopLayout L;
+    L.set(S);
+    std::vector<double> slab(L.total + 8, 0.0);
+    Coop<HostTeam> c(S, L, slab.data(), HostTeam());
+    double* w = slab.data();
+    const int nd = S.nd, nk = S.nk, nq = S.nq, nu = S.nu, nc = S.nc;
+    for (int i = 0; i < nq; ++i) { w[L.q1 + i] = q1[i]; w[L.q2 + i] = q1[i]; }
+    for (int i = 0; i < nd; ++i) { w[L.p1 + i] = p1[i]; if (q2_guess) w[L.q2 + i] = q2_guess[i]; }
+    for (int i = 0; i < nc; ++i) w[L.lam + i] = lam_guess ? lam_guess[i] : 0.0;
+    int total = 0;
+    double ta = t1;
+    for (int st = 0; st < nsteps; ++st) {
+        if (st > 0) {
+            for (int i = 0; i < nq; ++i) w[L.q1 + i] = w[L.q2 + i];
+            for (int i = 0; i < nd; ++i) w[L.p1 + i] = w[L.p2 + i];
+        }
+        for (int i = 0; i < nu; ++i) w[L.u1 + i] = u1 ? u1[st * nu + i] : 0.0;
+        for (int i = 0; i < nk; ++i) w[L.q2 + nd + i] = k2[st * nk + i];
+        const int it = c.solve(ta, ta + dt, tol, maxit);
+        if (it < 0) return it;
+        total += it;
+        ta += dt;
+    }
+    *iters = total;
+    for (int i = 0; i < nq; ++i) q2[i] = w[L.q2 + i];
+    for (int i = 0; i < nd; ++i) p2[i] = w[L.p2 + i];
+    for (int i = 0; i < nc; ++i) lam[i] = w[L.lam + i];
+    if (!raw) return 0;
+    Deriv1Out o;
+    o.q2_dq1 = raw[0]; o.q2_dp1 = raw[1]; o.q2_du1 = raw[2]; o.q2_dk2 = raw[3];
+    o.p2_dq1 = raw[4]; o.p2_dp1 = raw[5]; o.p2_du1 = raw[6]; o.p2_dk2 = raw[7];
+    o.l1_dq1 = raw[8]; o.l1_dp1 = raw[9]; o.l1_du1 = raw[10]; o.l1_dk2 = raw[11];
+    o.A = A; o.B = B; o.es = 1;
+    AuxLayout al;
+    al.set(nd, nc);
+    const int auxo[7] = {al.o_m2, al.o_m2p, al.o_pj, al.o_pjp, al.o_dh1, al.o_dh2, al.o_t22};
+    return c.deriv1(ta - dt, ta, o, aux, auxo);
+}
+
+int th_coop_calc_p2(const trepb_sysdesc* d, double dt, const double* q0, const double* q1, double* p) {
+    CoopPack P = coop_pack(d);
+    if (!P.ok) return -200;
+    CoopSys S = P.view(P.blob.data());
+    CoopLayout L;
+    L.set(S);
+    std::vector<double> slab(L.total + 8, 0.0);
+    Coop<HostTeam> c(S, L, slab.data(), HostTeam());
+    for (int i = 0; i < S.nq; ++i) { slab[L.q1 + i] = q0[i]; slab[L.q2 + i] = q1[i]; }
+    c.calc_p2(dt);
+    for (int i = 0; i < S.nd; ++i) p[i] = slab[L.p2 + i];
+    return 0;
+}
+
+int th_coop_info(const trepb_sysdesc* d, int* out) {
+    CoopPack P = coop_pack(d);
+    if (!P.ok) return -200;
+    CoopSys S = P.view(P.blob.data());
+    CoopLayout L;
+    L.set(S);
+    out[0] = S.nl; out[1] = S.nlevels; out[2] = S.npairs; out[3] = S.np; out[4] = L.total; out[5] = (int)P.blob.size();
     return 0;
 }
 }

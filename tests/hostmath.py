@@ -15,7 +15,7 @@ SO = os.path.join(HERE, "_build", "libhostmath.so")
 SRC = os.path.join(HERE, "host_math_check.cc")
 DEPS = [SRC] + [os.path.join(ROOT, "trep_b200", "csrc", f)
                 for f in ("trepb_math.cuh", "trepb_sys.h", "trepb_ws.h", "trepb_pack.h", "trepb_hd.h",
-                          "trepb_d2.cuh", "trepb_kernels.cuh")]
+                          "trepb_d2.cuh", "trepb_kernels.cuh", "trepb_coop_math.cuh", "trepb_coop_sys.h")]
 
 _lib = None
 
@@ -126,3 +126,48 @@ def deriv2(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-1
     res = {n: b[:int(np.prod(sh))].reshape(sh) for n, (b, sh) in out.items()}
     res["rc"] = rc
     return res
+
+
+def coop_info(desc):
+    lib = load()
+    cd, keep = D.to_c(desc)
+    out = (C.c_int * 8)()
+    rc = lib.th_coop_info(C.byref(cd), out)
+    if rc:
+        return None
+    return dict(nl=out[0], nlevels=out[1], npairs=out[2], npoints=out[3], ws_doubles=out[4], blob_bytes=out[5])
+
+
+def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200,
+                   nsteps=1, derivs=True):
+    """Same call as linearize() through the team-cooperative math (one-lane host team)."""
+    lib = load()
+    cd, keep = D.to_c(desc)
+    q1, p1, u1, k2 = _c(q1), _c(p1), _c(u1), _c(k2)
+    q2g = None if q2_guess is None else _c(q2_guess)
+    lg = None if lam_guess is None else _c(lam_guess)
+    q2, p2, lam = np.zeros(desc.nq), np.zeros(desc.nd), np.zeros(max(desc.nc, 1))
+    it = C.c_int(0)
+    A = np.zeros((desc.nX, desc.nX))
+    B = np.zeros((desc.nX, max(desc.nU, 1)))
+    shapes = raw_shapes(desc)
+    raw = {n: np.zeros(max(int(np.prod(shapes[n])), 1)) for n in RAW}
+    ptrs = (C.POINTER(C.c_double) * 12)(*[_dp(raw[n]) for n in RAW])
+    aux = np.zeros(4 * (desc.nd + desc.nc + 2) ** 2)
+    lib.th_coop_linearize.restype = C.c_int
+    rc = lib.th_coop_linearize(C.byref(cd), C.c_int(nsteps), C.c_double(t1), C.c_double(t2 - t1), C.c_double(tol),
+                               C.c_int(maxit), _dp(q1), _dp(p1), _dp(u1), _dp(k2), _dp(q2g), _dp(lg), _dp(q2),
+                               _dp(p2), _dp(lam), C.byref(it), _dp(A), _dp(B), ptrs if derivs else None, _dp(aux))
+    out = {n: raw[n][:int(np.prod(shapes[n]))].reshape(shapes[n]) for n in RAW}
+    out.update(rc=rc, q2=q2, p2=p2, lambda1=lam[:desc.nc], iters=it.value, A=A, B=B[:, :desc.nU], aux=aux)
+    return out
+
+
+def coop_calc_p2(desc, dt, q0, q1):
+    lib = load()
+    cd, keep = D.to_c(desc)
+    q0, q1 = _c(q0), _c(q1)
+    p = np.zeros(desc.nd)
+    rc = lib.th_coop_calc_p2(C.byref(cd), C.c_double(dt), _dp(q0), _dp(q1), _dp(p))
+    assert rc == 0
+    return p

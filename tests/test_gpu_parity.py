@@ -35,16 +35,23 @@ def ref():
     return R
 
 
+COOP_UNSUPPORTED = {"dual_pendulums"}   # LinearSpring / LinearDamper: thread-per-instance kernels only
+
+
 def _systems(lib, name):
-    """(label, System) for the specialised kernel (if one exists) and the general kernel."""
+    """(label, System) for every kernel flavour that can run the system: the specialised kernel
+    (if one exists), the table-driven thread-per-instance kernel and the cooperative
+    (warp-per-instance, shared-memory workspace) kernel."""
     d = G.desc(name)
     out = []
     s = lib.System(d)
     if s.specialized:
         out.append(("spec", s))
-        out.append(("general", lib.System(d, specialize=False)))
-    else:
-        out.append(("general", s))
+    out.append(("general", lib.System(d, specialize=False, cooperative=False)))
+    if name not in COOP_UNSUPPORTED:
+        c = lib.System(d, cooperative=True)
+        assert c.cooperative and c.kernel_name == "cooperative"
+        out.append(("coop", c))
     return out
 
 
@@ -88,9 +95,11 @@ def test_golden_rollout(lib, name):
         assert abs(int(out["iters"][0]) - int(g["roll_iters"].sum())) <= max(2, nsteps // 100)
 
 
-def test_puppet_rollout(lib):
+@pytest.mark.parametrize("coop", [True, False])
+def test_puppet_rollout(lib, coop):
     g = G.golden("puppet")
-    s = lib.System(G.desc("puppet"))
+    s = lib.System(G.desc("puppet"), cooperative=coop)
+    assert s.cooperative == coop
     dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
     p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
     G.assert_close(p0[0], g["roll_p"][0], "puppet p_init")
@@ -154,13 +163,15 @@ def test_puppet_random_vs_reference(lib, ref):
     t1 = 0.01 * (idx + 1)
     t2 = t1 + 0.01
     want = ref.run_cases(mvi, t1, t2, q1, p1, np.zeros((B, 0)), k2, lambda_guess=lam)
-    s = lib.System(G.desc("puppet"))
-    out = s.linearize(q1, p1, None, k2, t1=t1, t2=t2, lambda_guess=lam)
-    assert np.array_equal(out["status"], want["status"])
-    ok = want["status"] == 0
-    for k in ("q2", "p2", "lambda1", "A", "B"):
-        G.assert_close(out[k][ok], want[k][ok], "puppet " + k)
-    assert np.array_equal(out["iters"][ok], want["iters"][ok])
+    for coop in (True, False):
+        s = lib.System(G.desc("puppet"), cooperative=coop)
+        assert s.cooperative == coop
+        out = s.linearize(q1, p1, None, k2, t1=t1, t2=t2, lambda_guess=lam)
+        assert np.array_equal(out["status"], want["status"])
+        ok = want["status"] == 0
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k][ok], want[k][ok], "puppet[coop=%s] %s" % (coop, k))
+        assert np.array_equal(out["iters"][ok], want["iters"][ok])
 
 
 def test_device_pointer_entry_points_match_host(lib):
@@ -246,13 +257,16 @@ def test_puppet_second_derivatives(lib):
     g = G.golden("puppet")
     g2 = np.load(os.path.join(G.GOLD, "puppet_deriv2.npz"))
     c = int(g2["case_index"][0])
-    s = lib.System(G.desc("puppet"))
     sl = slice(c, c + 1)
-    out = s.deriv2(g["case_q1"][sl], g["case_p1"][sl], None, g["case_k2"][sl], t1=g["case_t1"][sl],
-                   t2=g["case_t2"][sl], q2_guess=g["case_q2_guess"][sl], lambda_guess=g["case_lambda_guess"][sl])
-    assert out["status"][0] == 0
-    for n in s.d2_shapes(1):
-        G.assert_close(out[n], g2["case_" + n], "puppet " + n)
+    # the second-derivative kernel consumes the factorizations the linearize kernel exports:
+    # check both producers (cooperative and thread-per-instance)
+    for coop in (True, False):
+        s = lib.System(G.desc("puppet"), cooperative=coop)
+        out = s.deriv2(g["case_q1"][sl], g["case_p1"][sl], None, g["case_k2"][sl], t1=g["case_t1"][sl],
+                       t2=g["case_t2"][sl], q2_guess=g["case_q2_guess"][sl], lambda_guess=g["case_lambda_guess"][sl])
+        assert out["status"][0] == 0
+        for n in s.d2_shapes(1):
+            G.assert_close(out[n], g2["case_" + n], "puppet[coop=%s] %s" % (coop, n))
 
 
 def test_second_derivatives_by_finite_differences_where_the_reference_has_none(lib):

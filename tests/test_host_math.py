@@ -28,6 +28,48 @@ def test_cases_step_and_deriv1(name):
     assert flips == 0, "Newton iteration counts differ from the reference in %d cases" % flips
 
 
+@pytest.mark.parametrize("name", G.ALL)
+def test_cooperative_math_cases(name):
+    """The team-cooperative formulation (link tables, world-coordinate spatial algebra,
+    right-looking LU; trepb_coop_math.cuh) run with a one-lane host team against the goldens."""
+    g = G.golden(name)
+    d = G.desc(name)
+    if H.coop_info(d) is None:
+        pytest.skip("cooperative path does not apply (LinearSpring / LinearDamper)")
+    flips = 0
+    for c in range(g["case_q1"].shape[0]):
+        out = H.coop_linearize(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c],
+                               g["case_p1"][c], g["case_u1"][c], g["case_k2"][c],
+                               q2_guess=g["case_q2_guess"][c], lam_guess=g["case_lambda_guess"][c])
+        assert out["rc"] == 0
+        flips += int(out["iters"] != int(g["case_iters"][c]))
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+        for k in G.RAW:
+            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+    assert flips == 0
+
+
+def test_cooperative_puppet_rollout_and_tables():
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    info = H.coop_info(d)
+    # 34 variable frames of 86, 10 link levels, and the workspace of one instance fits 7 times
+    # next to the tables in one SM's 227 KB of shared memory
+    assert info["nl"] == 34 and info["nlevels"] == 10
+    assert 7 * info["ws_doubles"] * 8 + info["blob_bytes"] + 16 <= 227 * 1024
+    dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
+    p0 = H.coop_calc_p2(d, dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0, g["roll_p"][0], "puppet p_init")
+    out = H.coop_linearize(d, dt, 2 * dt, g["roll_q1"], p0, np.zeros((nsteps, 0)), g["roll_k2"], nsteps=nsteps,
+                           derivs=False)
+    assert out["rc"] == 0
+    G.assert_close(out["q2"], g["roll_q"][-1], "puppet final q", rtol=1e-8)
+    G.assert_close(out["p2"], g["roll_p"][-1], "puppet final p", rtol=1e-8)
+    G.assert_close(out["lambda1"], g["roll_lambda"][-1], "puppet final lambda", rtol=1e-8)
+    assert out["iters"] == int(g["roll_iters"].sum())
+
+
 @pytest.mark.parametrize("name", G.SMALL)
 def test_rollout(name):
     g = G.golden(name)

@@ -8,7 +8,7 @@ from trep_b200 import lib, systems
 up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(a)
 rng = np.random.default_rng(0)
 B = int(os.environ.get("PUPPET_B", "32768"))
-d = systems.named_desc("puppet"); s = lib.System(d)
+d = systems.named_desc("puppet"); s = lib.System(d, cooperative={"1": True, "0": False}.get(os.environ.get("COOP", ""), None))
 g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
 idx = rng.integers(1, 58, B)
 q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
@@ -21,7 +21,13 @@ ticks = (C.c_ulonglong * 32)()
 names = {0: "solve: Dh(q1)", 1: "solve: residual eval_mid(1)", 2: "solve: h(q2)", 3: "solve: eval_mid_again(2)",
          4: "solve: Jacobian assembly + Dh(q2)", 5: "solve: LU 28x28 + solve", 8: "deriv1: constraints q1 (DDh.lam), q2",
          9: "deriv1: eval_mid_again(2)", 10: "deriv1: table assembly", 11: "deriv1: M2 LU, proj", 12: "deriv1: 80 rhs solves + A/B writes",
-         13: "deriv1: constant blocks of A,B"}
+         13: "deriv1: constant blocks of A,B",
+         16: "coop solve: pose(q1) + Dh1", 17: "coop solve: pose(q2) + h + Dh2", 18: "coop solve: pose(mid) + V",
+         19: "coop solve: dyn_first (inertia, up sweep, Lq/Lv)", 20: "coop solve: residual + test",
+         21: "coop solve: dyn_second (H,G,P + pair tables)", 22: "coop solve: Jacobian assembly",
+         23: "coop solve: LU 28x28(+1)", 24: "coop solve: back substitution + update",
+         25: "coop deriv1: dyn_second", 26: "coop deriv1: pose(q1) + DDh.lambda", 27: "coop deriv1: M2 / T22 assembly",
+         28: "coop deriv1: LU M2(+Dh1^T), proj, aux", 29: "coop deriv1: rhs columns + outputs", 30: "coop deriv1: constant blocks of A,B"}
 for rep in range(2):
     lib.raw().trepb_phase_ticks(ticks, 1)
     s.linearize_raw(True, B, dq, dp, None, dk, st, t1_scalar=0.0, dt_scalar=0.01, lambda_guess=dl, q2=q2, p2=p2,

@@ -11,6 +11,7 @@
 #include "trepb_codegen.h"
 #include "trepb_err.h"
 #include "trepb_kernels.cuh"
+#include "trepb_coop.h"
 #include "trepb_pack.h"
 
 using namespace trepb;
@@ -70,6 +71,14 @@ struct trepb_system {
     int bps[3] = {1, 1, 1};      // resident CTAs per SM for step / p2 / lin
     size_t lin_stage_bytes = 0;  // dynamic smem of the staged linearize kernel (0: no staging)
     int lin_bps_staged = 1;
+    // team-cooperative path (one warp per instance, workspace in shared memory)
+    bool coop = false;
+    CoopPack CP;
+    char* dcoop = nullptr;
+    CoopSys cview;               // base = dcoop
+    CoopLayout clay;
+    int coop_blob_bytes = 0;
+    int coop_warps = 0;          // instances in flight per CTA (= per SM)
     // general path workspace
     WsStrided wsl;               // layout (base filled per launch)
     int ws_doubles = 0;
@@ -142,6 +151,35 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     }
     const RtSys& ps = s->P.proto;
     s->ws_doubles = s->wsl.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc);
+    // Cooperative kernels for table-driven systems whose per-thread workspace is too large to stay
+    // on chip (or when asked for); everything else keeps one thread per instance.
+    if (!s->ks->specialized && !(flags & TREPB_FLAG_NO_COOP)) {
+        s->CP = coop_pack(desc);
+        if (s->CP.ok) {
+            CoopSys hv = s->CP.view(s->CP.blob.data());
+            s->clay.set(hv);
+            s->coop_blob_bytes = (int)s->CP.blob.size();
+            const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
+            const size_t ws_b = (size_t)s->clay.total * 8;
+            const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
+            int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
+            if (warps > 8) warps = 8;
+            const bool wanted = (flags & TREPB_FLAG_FORCE_COOP) || s->ws_doubles > 2048;
+            if (warps >= 1 && wanted) {
+                CUS(cudaMalloc((void**)&s->dcoop, blob_d));
+                CUS(cudaMemset(s->dcoop, 0, blob_d));
+                CUS(cudaMemcpy(s->dcoop, s->CP.blob.data(), s->CP.blob.size(), cudaMemcpyHostToDevice));
+                s->cview = s->CP.view(s->dcoop);
+                s->coop_warps = warps;
+                s->coop = true;
+            }
+        }
+        if ((flags & TREPB_FLAG_FORCE_COOP) && !s->coop) {
+            const std::string why = s->CP.ok ? "workspace does not fit in shared memory" : s->CP.why;
+            trepb_system_destroy(s);
+            return fail(TREPB_ERR_UNSUPPORTED, "cooperative kernels not available for this system: " + why);
+        }
+    }
     const size_t base_smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
     if (base_smem > 200 * 1024) { trepb_system_destroy(s); return fail(TREPB_ERR_UNSUPPORTED, "system description exceeds shared memory"); }
     for (int w = 0; w < 3; ++w) {
@@ -175,6 +213,7 @@ void trepb_system_destroy(trepb_system* s) {
     if (!s) return;
     cudaSetDevice(s->device);
     if (s->dblob) cudaFree(s->dblob);
+    if (s->dcoop) cudaFree(s->dcoop);
     s->ws.release();
     s->ws_hd.release();
     for (auto& b : s->d2s) b.release();
@@ -196,7 +235,8 @@ int trepb_system_dims(const trepb_system* s, int32_t* nq, int32_t* nd, int32_t* 
 }
 
 int trepb_system_is_specialized(const trepb_system* s) { return s && s->ks->specialized; }
-const char* trepb_system_kernel_name(const trepb_system* s) { return s ? s->ks->name : ""; }
+const char* trepb_system_kernel_name(const trepb_system* s) { return s ? (s->coop ? "cooperative" : s->ks->name) : ""; }
+int trepb_system_is_cooperative(const trepb_system* s) { return s && s->coop; }
 
 int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_bytes, int32_t* blocks_per_sm,
                       int32_t* block, int32_t* smem_bytes) {
@@ -204,6 +244,15 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
     CU(cudaSetDevice(s->device));
     KernelInfo ki;
     int b = 0;
+    if (s->coop) {
+        CU(coop_kernel_info(which, &ki));
+        if (regs) *regs = ki.regs;
+        if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
+        if (blocks_per_sm) *blocks_per_sm = 1;
+        if (block) *block = 32 * s->coop_warps;
+        if (smem_bytes) *smem_bytes = (int32_t)((size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)s->coop_warps * s->clay.total * 8);
+        return TREPB_OK;
+    }
     size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
     if (which == 2 && s->lin_stage_bytes) smem = s->lin_stage_bytes;
     CU(s->ks->occupancy(which, s->block, smem, &b, &ki));
@@ -263,6 +312,22 @@ int make_cfg(trepb_system* s, int which, long long batch, int bps, size_t smem, 
     return TREPB_OK;
 }
 
+// persistent grid of the cooperative kernels: one CTA per SM, fewer warps per CTA for small batches
+void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch* c) {
+    int warps = s->coop_warps;
+    const long long per_sm = (batch + s->sms - 1) / s->sms;
+    if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
+    long long grid = (batch + warps - 1) / warps;
+    if (grid > s->sms) grid = s->sms;
+    c->grid = (int)grid;
+    c->warps = warps;
+    c->smem = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)warps * s->clay.total * 8;
+    c->stream = stream;
+    c->sys = s->cview;
+    c->blob_bytes = s->coop_blob_bytes;
+    c->lay = s->clay;
+}
+
 struct Timed {
     trepb_system* s;
     cudaStream_t st;
@@ -294,6 +359,13 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     p.sample_every = a->sample_every;
     p.nsamples = a->sample_every > 0 ? a->nsteps / a->sample_every : 0;
     p.traj_q = a->traj_q; p.traj_p = a->traj_p;
+    if (s->coop) {
+        CoopLaunch cl;
+        make_coop(s, a->batch, (cudaStream_t)stream, &cl);
+        Timed t(s, cl.stream);
+        CU(coop_step(cl, p));
+        return TREPB_OK;
+    }
     LaunchCfg c;
     int rc = make_cfg(s, 0, a->batch, s->bps[0], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
@@ -311,6 +383,13 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
     CU(cudaSetDevice(s->device));
     P2Params p;
     p.batch = batch; p.dt = dt; p.q0 = q0; p.q1 = q1; p.p = pout;
+    if (s->coop) {
+        CoopLaunch cl;
+        make_coop(s, batch, (cudaStream_t)stream, &cl);
+        Timed t(s, cl.stream);
+        CU(coop_p2(cl, p));
+        return TREPB_OK;
+    }
     LaunchCfg c;
     int rc = make_cfg(s, 1, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
@@ -343,6 +422,16 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
                        a->l1_dq1, a->l1_dp1, a->l1_du1, a->l1_dk2};
     for (int i = 0; i < 12; ++i) p.raw[i] = raw[i];
     p.aux = aux; p.aux_size = aux_size;
+    if (s->coop) {
+        p.stage = 0;
+        CoopLaunch cl;
+        make_coop(s, a->batch, stream, &cl);
+        AuxLayout al;
+        al.set(ps.nd, ps.nc);
+        Timed t(s, cl.stream);
+        CU(coop_lin(cl, p, al));
+        return TREPB_OK;
+    }
     const bool stage = s->lin_stage_bytes > 0 && (p.A || p.B);
     p.stage = stage ? 1 : 0;
     LaunchCfg c;

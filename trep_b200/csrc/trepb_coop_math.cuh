@@ -1,0 +1,885 @@
+// Team-cooperative MidpointVI math: ONE instance is worked on by a team of lanes (a warp on the
+// device, a single "lane" on the host for CPU checks) with the whole per-instance workspace in
+// shared memory.  Same quantities as trepb_math.cuh / the reference
+// (trep/_trep/midpointvi.c:391-1120 on top of system.c:129-742, frame.c:839-2081 and
+// math-code.c:337-461), evaluated on the link-level tables of trepb_coop_sys.h in WORLD (spatial)
+// coordinates so that every phase is either a short level-by-level sweep of the link tree or a
+// flat loop the lanes of the team share:
+//
+//   pose sweep (root->leaf, one step per tree level)
+//       T_l = T_parent Xc_l J_l(q_l)            pose of link l
+//       s_l = (o_l x a_l, a_l) | (a_l, 0)       joint twist about the world origin (revolute | prismatic)
+//       V_l = V_parent + s_l dq_l               spatial velocity
+//   per link      I_l^w (m, h = m c, Ibar about the world origin),  mu_l = I_l^w V_l
+//   up sweep      composite Ic_l, mu_l = sums over the subtree (plain additions in world coordinates)
+//   per link      W_l = [V_parent, s_l] (= d vb / d q_l),  L_ddq = s.mu,  L_dq = W.mu + g.P,
+//                 H = Ic s,  G = Ic W - ad*_s mu,  P = m v_s + w_s x h
+//   per chain pair (i above-or-equal j)
+//                 L_ddqddq(i,j) = s_i.H_j   L_ddqdq(i,j) = s_i.G_j   L_ddqdq(j,i) = W_i.H_j
+//                 L_dqdq(i,j) = W_i.G_j + a_i.(P_j x g)
+//   constraints   world points p = o_l + R_l r ; dp/dq_j = a_j x (p - o_j) | a_j ;
+//                 d2p/dq_i dq_j = a_up x dp/dq_lo
+//   linear algebra  right-looking LU with the reference's implicit-scaling pivot rule
+//                 (math-code.c:337-432), lanes over columns; right-hand sides ride along as extra
+//                 columns or are solved one column per lane.
+//
+// Nothing here is a transcription of frame.c: there are no per-frame derivative caches at all.
+#pragma once
+#include <math.h>
+#include "trepb_coop_sys.h"
+#include "trepb_math.cuh"   // cross3 / dot3 / Deriv1Out / Status
+
+namespace trepb {
+
+// ---------------------------------------------------------------------------------------------
+// teams
+// ---------------------------------------------------------------------------------------------
+struct HostTeam {
+    static constexpr int kSize = 1;
+    TREPB_HD int lane() const { return 0; }
+    TREPB_HD void sync() const {}
+    TREPB_HD void argmax(double&, int&) const {}
+    TREPB_HD bool any(bool p) const { return p; }
+};
+#if defined(__CUDACC__)
+struct WarpTeam {
+    static constexpr int kSize = 32;
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+    // largest value wins, ties go to the lowest index; every lane gets the result
+    __device__ __forceinline__ void argmax(double& v, int& i) const {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+            const int oi = __shfl_xor_sync(0xffffffffu, i, o);
+            if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+        }
+    }
+    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
+};
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// workspace layout (offsets in doubles from the instance's base)
+// ---------------------------------------------------------------------------------------------
+struct CoopLayout {
+    int nls, ldf, ldm, ldp, ldy;
+    int q1, q2, qe, dq, p1, p2, u1, lam;
+    int cs, R, p, V, comp, pts;      // link region
+    int M2, T22;                     // first-derivative factors; alias the link region
+    int Lq, Lv, VV, QQ, UP, DN;
+    int Dh1, Dh2, hc;
+    int N;                           // Newton augmented matrix [nr][ldf]  /  right-hand sides Y [nd][ldy]
+    int Z, PJ;
+    int fr, scl, rdM, rdP;
+    int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc]  (int32)
+    int total;
+
+    TREPB_HD static int odd(int n) { return n | 1; }
+    TREPB_HD void set(const CoopSys& s) {
+        const int nq = s.nq, nd = s.nd, nc = s.nc, nu = s.nu, nr = nd + nc;
+        nls = s.nl;
+        ldf = odd(nr + 1);
+        ldm = odd(nd + nc);
+        ldp = odd(nc > 0 ? nc : 1);
+        ldy = nq + nu;
+        int o = 0;
+        auto take = [&](int n) { int r = o; o += n; return r; };
+        q1 = take(nq); q2 = take(nq); qe = take(nq); dq = take(nq);
+        p1 = take(nd); p2 = take(nd); u1 = take(nu); lam = take(nc);
+        const int link0 = o;
+        cs = take(2 * nls); R = take(9 * nls); p = take(3 * nls); V = take(6 * nls); comp = take(16 * nls);
+        pts = take(3 * s.np);
+        const int need = nd * ldm + nd * nd;
+        if (o - link0 < need) o = link0 + need;
+        M2 = link0; T22 = link0 + nd * ldm;
+        Lq = take(nq); Lv = take(nq);
+        VV = take(s.npairs); QQ = take(s.npairs); UP = take(s.npairs); DN = take(s.npairs);
+        Dh1 = take(nc * nd); Dh2 = take(nc * nq); hc = take(nc);
+        const int nN = nr * ldf, nY = nd * ldy;
+        N = take(nN > nY ? nN : nY);
+        Z = take(nc * ldy); PJ = take(nc * ldp);
+        fr = take(nr); scl = take(nr); rdM = take(nr); rdP = take(nc);
+        ints = take((2 * nr + 2 * nc + 1) / 2 + 1);
+        total = (o + 1) & ~1;
+    }
+};
+
+// ---------------------------------------------------------------------------------------------
+// cooperative dense helpers
+// ---------------------------------------------------------------------------------------------
+// In-place LU of the leading n x n block of A (row-major, leading dimension ld) with the
+// reference's pivot rule (math-code.c:337-432: implicit row scaling, first strict maximum, whole
+// row swap, scales[pivot] = scales[j]); the same row operations are applied to nx extra columns
+// (right-hand sides), which therefore leave forward-eliminated.  piv[] is the composed permutation
+// of LU_decomp (x[i] = b[piv[i]]), swp[k] the row exchanged with k at step k, rd[k] = 1/U(k,k).
+// Returns false when the scaled pivot is <= tol (the reference's "singular" ValueError).
+template <class Team>
+TREPB_HD bool team_lu(const Team& t, double* A, int ld, int n, int nx, int* piv, int* swp, double* scl,
+                      double* rd, double tol) {
+    const int lane = t.lane();
+    for (int i = lane; i < n; i += Team::kSize) {
+        double s = -1.0;
+        for (int j = 0; j < n; ++j) {
+            const double a = fabs(A[i * ld + j]);
+            if (a > s) s = a;
+        }
+        scl[i] = 1.0 / s;
+        piv[i] = i;
+    }
+    t.sync();
+    for (int k = 0; k < n; ++k) {
+        double best = -1.0;
+        int bi = k;
+        for (int i = k + lane; i < n; i += Team::kSize) {
+            const double v = fabs(A[i * ld + k] * scl[i]);
+            if (v > best) { best = v; bi = i; }
+        }
+        t.argmax(best, bi);
+        if (!(best > tol)) return false;
+        t.sync();   // every lane has read scl / column k before rows move
+        if (bi != k) {
+            for (int j = lane; j < n + nx; j += Team::kSize) {
+                const double a = A[k * ld + j];
+                A[k * ld + j] = A[bi * ld + j];
+                A[bi * ld + j] = a;
+            }
+            if (lane == 0) {
+                const int pk = piv[k];
+                piv[k] = piv[bi];
+                piv[bi] = pk;
+                scl[bi] = scl[k];
+            }
+        }
+        if (lane == 0) swp[k] = bi;
+        t.sync();
+        const double d = A[k * ld + k];
+        for (int i = k + 1 + lane; i < n; i += Team::kSize) A[i * ld + k] /= d;
+        if (lane == 0) rd[k] = 1.0 / d;
+        t.sync();
+        for (int j = k + 1 + lane; j < n + nx; j += Team::kSize) {
+            const double akj = A[k * ld + j];
+            for (int i = k + 1; i < n; ++i) A[i * ld + j] -= A[i * ld + k] * akj;
+        }
+        t.sync();
+    }
+    return true;
+}
+
+// Back substitution of ONE forward-eliminated column (column index c of A) by the whole team.
+template <class Team>
+TREPB_HD void team_backsolve_vec(const Team& t, double* A, int ld, int n, int c, const double* rd, double* x) {
+    const int lane = t.lane();
+    for (int i = n - 1; i >= 0; --i) {
+        const double xi = A[i * ld + c] * rd[i];
+        for (int r = lane; r < i; r += Team::kSize) A[r * ld + c] -= A[r * ld + i] * xi;
+        if (lane == 0) x[i] = xi;
+        t.sync();
+    }
+}
+
+// One column per lane: y (stride ldy) <- U^-1 y for an already forward-eliminated column
+TREPB_HD void col_backsolve(const double* A, int ld, int n, const double* rd, double* y, int ldy) {
+    for (int i = n - 1; i >= 0; --i) {
+        double v = y[i * ldy];
+        for (int j = i + 1; j < n; ++j) v -= A[i * ld + j] * y[j * ldy];
+        y[i * ldy] = v * rd[i];
+    }
+}
+// One column per lane: y <- (LU)^-1 P y
+TREPB_HD void col_solve(const double* A, int ld, int n, const int* swp, const double* rd, double* y, int ldy) {
+    for (int k = 0; k < n; ++k) {
+        const int p = swp[k];
+        if (p != k) {
+            const double a = y[k * ldy];
+            y[k * ldy] = y[p * ldy];
+            y[p * ldy] = a;
+        }
+    }
+    for (int i = 1; i < n; ++i) {
+        double v = y[i * ldy];
+        for (int j = 0; j < i; ++j) v -= A[i * ld + j] * y[j * ldy];
+        y[i * ldy] = v;
+    }
+    col_backsolve(A, ld, n, rd, y, ldy);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the per-instance context
+// ---------------------------------------------------------------------------------------------
+template <class Team>
+struct Coop {
+    const CoopSys& S;
+    const CoopLayout& L;
+    double* w;      // workspace base of this instance
+    Team t;
+
+    TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team) : S(s), L(l), w(base), t(team) {}
+
+    TREPB_HD int* ipivM() const { return (int*)(w + L.ints); }
+    TREPB_HD int* iswpM() const { return ipivM() + (S.nd + S.nc); }
+    TREPB_HD int* ipivP() const { return iswpM() + (S.nd + S.nc); }
+    TREPB_HD int* iswpP() const { return ipivP() + S.nc; }
+
+    // ---- evaluation point: which = 0 midpoint, 1 q1, 2 q2 (midpointvi.c:401-457)
+    TREPB_HD void set_point(int which, double dt) {
+        for (int i = t.lane(); i < S.nq; i += Team::kSize) {
+            const double a = w[L.q1 + i], b = w[L.q2 + i];
+            w[L.qe + i] = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
+            w[L.dq + i] = (b - a) / dt;
+        }
+        t.sync();
+    }
+
+    // ---- pose sweep.  vel: links that carry mass, also V.  !vel: links that carry points.
+    TREPB_HD void pose_sweep(bool vel) {
+        const int nls = L.nls, lane = t.lane();
+        double* cs = w + L.cs; double* R = w + L.R; double* p = w + L.p; double* V = w + L.V;
+        for (int l = lane; l < S.nl; l += Team::kSize) {
+            if (!(vel ? S.dyn(l) : S.wrl(l)) || !S.rot(l)) continue;
+            double sn, c;
+            sincos_(w[L.qe + S.l_cfg()[l]], &sn, &c);
+            cs[l] = c;
+            cs[nls + l] = sn;
+        }
+        t.sync();
+        for (int lev = 0; lev < S.nlevels; ++lev) {
+            for (int l = S.lvl_off()[lev] + lane; l < S.lvl_off()[lev + 1]; l += Team::kSize) {
+                if (!(vel ? S.dyn(l) : S.wrl(l))) continue;
+                const int par = S.l_par()[l], a = S.axis(l), b = (a + 1) % 3, c = (a + 2) % 3;
+                const int cfg = S.l_cfg()[l];
+                double Rb[9], pb[3];
+                if (par < 0) {
+                    if (S.has_xc(l)) {
+                        for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
+                        for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
+                    } else {
+                        for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                        pb[0] = pb[1] = pb[2] = 0.0;
+                    }
+                } else {
+                    double Rp[9], pp[3];
+                    for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
+                    for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
+                    if (S.has_xc(l)) {
+                        const double* Rc = S.l_Rc() + 9 * l;
+                        const double* pc = S.l_pc() + 3 * l;
+                        for (int r = 0; r < 3; ++r) {
+                            for (int q = 0; q < 3; ++q)
+                                Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
+                            pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
+                        }
+                    } else {
+                        for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
+                        for (int k = 0; k < 3; ++k) pb[k] = pp[k];
+                    }
+                }
+                const double x = w[L.qe + cfg];
+                if (S.rot(l)) {
+                    const double c_ = cs[l], s_ = cs[nls + l];
+                    for (int r = 0; r < 3; ++r) {
+                        const double rb = Rb[r * 3 + b], rc = Rb[r * 3 + c];
+                        Rb[r * 3 + b] = c_ * rb + s_ * rc;
+                        Rb[r * 3 + c] = -s_ * rb + c_ * rc;
+                    }
+                } else {
+                    for (int r = 0; r < 3; ++r) pb[r] += x * Rb[r * 3 + a];
+                }
+                for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
+                for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
+                if (vel) {
+                    double s6[6], Vp[6];
+                    twist(Rb, pb, a, S.rot(l), s6);
+                    if (par < 0) { for (int k = 0; k < 6; ++k) Vp[k] = 0.0; }
+                    else { for (int k = 0; k < 6; ++k) Vp[k] = V[k * nls + par]; }
+                    const double d = w[L.dq + cfg];
+                    for (int k = 0; k < 6; ++k) V[k * nls + l] = Vp[k] + s6[k] * d;
+                }
+            }
+            t.sync();
+        }
+    }
+
+    // joint twist (v_O, w) in world coordinates about the world origin
+    TREPB_HD static void twist(const double* Rl, const double* pl, int a, bool rot, double* s6) {
+        const double aw[3] = {Rl[a], Rl[3 + a], Rl[6 + a]};
+        if (rot) {
+            cross3(pl, aw, s6);
+            s6[3] = aw[0]; s6[4] = aw[1]; s6[5] = aw[2];
+        } else {
+            s6[0] = aw[0]; s6[1] = aw[1]; s6[2] = aw[2];
+            s6[3] = s6[4] = s6[5] = 0.0;
+        }
+    }
+    // Lie bracket [X, Y] of two twists (v, w):  (w_X x v_Y + v_X x w_Y , w_X x w_Y)
+    TREPB_HD static void bracket(const double* X, const double* Y, double* o) {
+        double a[3], b[3];
+        cross3(X + 3, Y, a);
+        cross3(X, Y + 3, b);
+        o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2];
+        cross3(X + 3, Y + 3, o + 3);
+    }
+    TREPB_HD void load_link_twists(int l, double* s6, double* W6, double* aw) const {
+        const int nls = L.nls, a = S.axis(l), par = S.l_par()[l];
+        double Rl[9], pl[3];
+        // only column a of R is needed
+        for (int r = 0; r < 3; ++r) { Rl[r * 3 + a] = w[L.R + (r * 3 + a) * nls + l]; pl[r] = w[L.p + r * nls + l]; }
+        twist(Rl, pl, a, S.rot(l), s6);
+        aw[0] = Rl[a]; aw[1] = Rl[3 + a]; aw[2] = Rl[6 + a];
+        if (par < 0) { for (int k = 0; k < 6; ++k) W6[k] = 0.0; }
+        else {
+            double Vp[6];
+            for (int k = 0; k < 6; ++k) Vp[k] = w[L.V + k * nls + par];
+            bracket(Vp, s6, W6);
+        }
+    }
+
+    // ---- first-order dynamics at the midpoint: composite inertia/momentum, Lq, Lv
+    // (system.c:129-168 L_dq, :270-300 L_ddq, gravity.c:30-50)
+    TREPB_HD void dyn_first() {
+        const int nls = L.nls, lane = t.lane();
+        double* comp = w + L.comp;
+        for (int i = lane; i < S.nq; i += Team::kSize) { w[L.Lq + i] = 0.0; w[L.Lv + i] = 0.0; }
+        for (int l = lane; l < S.nl; l += Team::kSize) {
+            if (!S.dyn(l)) continue;
+            double Rl[9], pl[3], Vl[6];
+            for (int k = 0; k < 9; ++k) Rl[k] = w[L.R + k * nls + l];
+            for (int k = 0; k < 3; ++k) pl[k] = w[L.p + k * nls + l];
+            for (int k = 0; k < 6; ++k) Vl[k] = w[L.V + k * nls + l];
+            const double* in = S.l_in() + 10 * l;
+            const double m = in[0];
+            double hr[3], hw[3], I[6];
+            for (int r = 0; r < 3; ++r) {
+                hr[r] = Rl[r * 3] * in[1] + Rl[r * 3 + 1] * in[2] + Rl[r * 3 + 2] * in[3];
+                hw[r] = hr[r] + m * pl[r];
+            }
+            // Ibar^w = R Ibar R^T + 2 (hr.p) 1 - hr p^T - p hr^T + m (|p|^2 1 - p p^T)
+            {
+                double M[9], T[9];
+                M[0] = in[4]; M[4] = in[5]; M[8] = in[6];
+                M[1] = M[3] = in[7]; M[2] = M[6] = in[8]; M[5] = M[7] = in[9];
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c)
+                        T[r * 3 + c] = Rl[r * 3] * M[c] + Rl[r * 3 + 1] * M[3 + c] + Rl[r * 3 + 2] * M[6 + c];
+                const double hp = dot3(hr, pl), pp = dot3(pl, pl);
+                for (int r = 0; r < 3; ++r)
+                    for (int c = r; c < 3; ++c) {
+                        double v = T[r * 3] * Rl[c * 3] + T[r * 3 + 1] * Rl[c * 3 + 1] + T[r * 3 + 2] * Rl[c * 3 + 2];
+                        v += -hr[r] * pl[c] - pl[r] * hr[c] - m * pl[r] * pl[c];
+                        if (r == c) v += 2.0 * hp + m * pp;
+                        I[symi(r, c)] = v;
+                    }
+            }
+            double mu[6];
+            inertia_apply(m, hw, I, Vl, mu);
+            comp[0 * nls + l] = m;
+            for (int k = 0; k < 3; ++k) comp[(1 + k) * nls + l] = hw[k];
+            for (int k = 0; k < 6; ++k) comp[(4 + k) * nls + l] = I[k];
+            for (int k = 0; k < 6; ++k) comp[(10 + k) * nls + l] = mu[k];
+        }
+        t.sync();
+        // up sweep: a parent gathers its children (plain sums in world coordinates)
+        for (int lev = S.nlevels - 1; lev >= 1; --lev) {
+            const int lo = S.lvl_off()[lev - 1], cnt = S.lvl_off()[lev] - lo;
+            for (int e = lane; e < cnt * 16; e += Team::kSize) {
+                const int l = lo + e / 16, k = e % 16;
+                if (!S.dyn(l)) continue;
+                const int c0 = S.l_child0()[l], nch = S.l_nchild()[l];
+                double acc = comp[k * nls + l];
+                for (int ch = c0; ch < c0 + nch; ++ch)
+                    if (S.dyn(ch)) acc += comp[k * nls + ch];
+                comp[k * nls + l] = acc;
+            }
+            t.sync();
+        }
+        for (int l = lane; l < S.nl; l += Team::kSize) {
+            if (!S.dyn(l)) continue;
+            double s6[6], W6[6], aw[3], mu[6], h[3];
+            load_link_twists(l, s6, W6, aw);
+            const double m = comp[l];
+            for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
+            for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
+            const int cfg = S.l_cfg()[l];
+            w[L.Lv + cfg] = dot6(s6, mu);
+            double lq = dot6(W6, mu);
+            if (S.has_gravity) {
+                double P[3], t3[3];
+                cross3(s6 + 3, h, t3);
+                for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
+                lq += dot3(S.grav, P);
+            }
+            w[L.Lq + cfg] = lq;
+        }
+        t.sync();
+        // ConfigSpring (configspring.c:22-30)
+        for (int i = lane; i < S.nq; i += Team::kSize)
+            if (S.ks()[i] != 0.0) w[L.Lq + i] -= S.ks()[i] * w[L.qe + i] - S.kq0()[i];
+        t.sync();
+    }
+
+    // ---- second-order tables on the chain pairs (system.c:170-268, 302-393, 479-512)
+    TREPB_HD void dyn_second() {
+        const int nls = L.nls, lane = t.lane();
+        double* comp = w + L.comp;
+        for (int l = lane; l < S.nl; l += Team::kSize) {
+            if (!S.dyn(l)) continue;
+            double s6[6], W6[6], aw[3], mu[6], h[3], I[6], H[6], G[6], P[3], t3[3];
+            load_link_twists(l, s6, W6, aw);
+            const double m = comp[l];
+            for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
+            for (int k = 0; k < 6; ++k) I[k] = comp[(4 + k) * nls + l];
+            for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
+            inertia_apply(m, h, I, s6, H);
+            inertia_apply(m, h, I, W6, G);
+            // G -= ad*_s mu = (f x w_s , n x w_s + f x v_s)
+            cross3(mu, s6 + 3, t3);
+            for (int k = 0; k < 3; ++k) G[k] -= t3[k];
+            cross3(mu + 3, s6 + 3, t3);
+            for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
+            cross3(mu, s6, t3);
+            for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
+            cross3(s6 + 3, h, t3);
+            for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
+            for (int k = 0; k < 6; ++k) comp[k * nls + l] = H[k];
+            for (int k = 0; k < 6; ++k) comp[(6 + k) * nls + l] = G[k];
+            for (int k = 0; k < 3; ++k) comp[(12 + k) * nls + l] = P[k];
+        }
+        t.sync();
+        for (int e = lane; e < S.npairs; e += Team::kSize) {
+            const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
+            double s6[6], W6[6], aw[3], H[6], G[6];
+            load_link_twists(i, s6, W6, aw);
+            for (int k = 0; k < 6; ++k) { H[k] = comp[k * nls + j]; G[k] = comp[(6 + k) * nls + j]; }
+            const double sG = dot6(s6, G);
+            double WG = dot6(W6, G);
+            if (S.has_gravity && S.rot(i)) {
+                double P[3], N[3];
+                for (int k = 0; k < 3; ++k) P[k] = comp[(12 + k) * nls + j];
+                cross3(P, S.grav, N);
+                WG += dot3(aw, N);
+            }
+            w[L.VV + e] = dot6(s6, H);
+            w[L.UP + e] = sG;
+            w[L.DN + e] = i == j ? sG : dot6(W6, H);
+            w[L.QQ + e] = WG;
+        }
+        t.sync();
+    }
+
+    // table terms for the config pair (a, b):  qq = L_dqdq(a,b), vv = L_ddqddq(a,b),
+    // vab = L_ddqdq(a,b), vba = L_ddqdq(b,a)   (first index of L_ddqdq is the velocity slot)
+    TREPB_HD void tab(int a, int b, double& qq, double& vv, double& vab, double& vba) const {
+        const int m = S.pm()[a * S.nq + b];
+        if (m > 0) {
+            qq = w[L.QQ + m - 1]; vv = w[L.VV + m - 1]; vab = w[L.UP + m - 1]; vba = w[L.DN + m - 1];
+        } else if (m < 0) {
+            qq = w[L.QQ - m - 1]; vv = w[L.VV - m - 1]; vab = w[L.DN - m - 1]; vba = w[L.UP - m - 1];
+        } else {
+            qq = vv = vab = vba = 0.0;
+        }
+        if (a == b) qq -= S.ks()[a];
+    }
+
+    // ---- world points of the constraints at the current pose
+    TREPB_HD void points() {
+        const int nls = L.nls;
+        for (int q = t.lane(); q < S.np; q += Team::kSize) {
+            const int l = S.pt_link()[q];
+            const double* r = S.pt_r() + 3 * q;
+            for (int k = 0; k < 3; ++k) {
+                double v = r[k];
+                if (l >= 0)
+                    v = w[L.p + k * nls + l] + (w[L.R + (k * 3) * nls + l] * r[0] + w[L.R + (k * 3 + 1) * nls + l] * r[1] +
+                                                w[L.R + (k * 3 + 2) * nls + l] * r[2]);
+                w[L.pts + k * S.np + q] = v;
+            }
+        }
+        t.sync();
+    }
+    TREPB_HD void point(int q, double* o) const { for (int k = 0; k < 3; ++k) o[k] = w[L.pts + k * S.np + q]; }
+    TREPB_HD bool pdep(int q, int lj) const {
+        const int l = S.pt_link()[q];
+        return l >= 0 && lj >= 0 && ((S.l_anc()[l] >> lj) & 1ull) != 0;
+    }
+    // d p_q / d q_j for the link lj driven by config j  (zero unless the point hangs below lj)
+    TREPB_HD void dpoint(int q, int lj, double* o) const {
+        o[0] = o[1] = o[2] = 0.0;
+        if (!pdep(q, lj)) return;
+        const int nls = L.nls, a = S.axis(lj);
+        const double aw[3] = {w[L.R + a * nls + lj], w[L.R + (3 + a) * nls + lj], w[L.R + (6 + a) * nls + lj]};
+        if (S.rot(lj)) {
+            double r[3];
+            for (int k = 0; k < 3; ++k) r[k] = w[L.pts + k * S.np + q] - w[L.p + k * nls + lj];
+            cross3(aw, r, o);
+        } else {
+            o[0] = aw[0]; o[1] = aw[1]; o[2] = aw[2];
+        }
+    }
+    TREPB_HD void ddpoint(int q, int li, int lj, double* o) const {
+        o[0] = o[1] = o[2] = 0.0;
+        if (!pdep(q, li) || !pdep(q, lj)) return;
+        int up = li, lo = lj;
+        if (!((S.l_anc()[lj] >> li) & 1ull)) { up = lj; lo = li; }
+        if (!S.rot(up)) return;
+        const int nls = L.nls, a = S.axis(up);
+        const double aw[3] = {w[L.R + a * nls + up], w[L.R + (3 + a) * nls + up], w[L.R + (6 + a) * nls + up]};
+        double d[3];
+        dpoint(q, lo, d);
+        cross3(aw, d, o);
+    }
+
+    // ---- constraints at the current pose (distance.c:16-100, point.c:16-46)
+    //   want_h: hc ;  dh: 0 none, 1 -> Dh1 [nc][nd], 2 -> Dh2 [nc][nq]
+    TREPB_HD void constraints(bool want_h, int dh) {
+        const int lane = t.lane(), nq = S.nq, nd = S.nd;
+        if (want_h) {
+            for (int c = lane; c < S.nc; c += Team::kSize) {
+                double pa[3], pb[3], v[3];
+                point(S.con_a()[c], pa); point(S.con_b()[c], pb);
+                for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                if (S.con_kind()[c] == C_DISTANCE) {
+                    const int third = S.con_third()[c];
+                    const double d = third >= 0 ? w[L.qe + third] : S.con_dist()[c];
+                    w[L.hc + c] = dot3(v, v) - d * d;
+                } else {
+                    w[L.hc + c] = v[S.con_third()[c]];
+                }
+            }
+        }
+        if (dh) {
+            const int ncol = dh == 1 ? nd : nq;
+            double* D = w + (dh == 1 ? L.Dh1 : L.Dh2);
+            for (int e = lane; e < S.nc * ncol; e += Team::kSize) {
+                const int c = e / ncol, j = e % ncol;
+                double val = 0.0;
+                if ((S.con_dep()[c] >> j) & 1ull) {
+                    const int A = S.con_a()[c], B = S.con_b()[c], lj = S.cfg_link()[j];
+                    double da[3], db[3], dv[3];
+                    dpoint(A, lj, da); dpoint(B, lj, db);
+                    for (int k = 0; k < 3; ++k) dv[k] = da[k] - db[k];
+                    if (S.con_kind()[c] == C_DISTANCE) {
+                        double pa[3], pb[3], v[3];
+                        point(A, pa); point(B, pb);
+                        for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                        const int third = S.con_third()[c];
+                        val = dot3(v, dv);
+                        if (third == j) val -= w[L.qe + third];
+                        val *= 2.0;
+                    } else {
+                        val = dv[S.con_third()[c]];
+                    }
+                }
+                D[e] = val;
+            }
+        }
+        t.sync();
+    }
+
+    // Y[j][i] = sum_c lam_c d2h_c/dq_i dq_j   for i < nq, j < nd   (midpointvi.c:864-889)
+    TREPB_HD void ddh_lambda(double* Y, int ldy) {
+        const int lane = t.lane(), nq = S.nq, nd = S.nd;
+        for (int e = lane; e < nd * nq; e += Team::kSize) {
+            const int j = e / nq, i = e % nq;
+            double acc = 0.0;
+            for (int c = 0; c < S.nc; ++c) {
+                const uint64_t dep = S.con_dep()[c];
+                if (!((dep >> i) & 1ull) || !((dep >> j) & 1ull)) continue;
+                const int A = S.con_a()[c], B = S.con_b()[c], li = S.cfg_link()[i], lj = S.cfg_link()[j];
+                double a3[3], b3[3], ddv[3];
+                ddpoint(A, li, lj, a3); ddpoint(B, li, lj, b3);
+                for (int k = 0; k < 3; ++k) ddv[k] = a3[k] - b3[k];
+                const double lam = w[L.lam + c];
+                if (S.con_kind()[c] == C_DISTANCE) {
+                    double pa[3], pb[3], v[3], di[3], dj[3];
+                    point(A, pa); point(B, pb);
+                    for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                    dpoint(A, li, a3); dpoint(B, li, b3);
+                    for (int k = 0; k < 3; ++k) di[k] = a3[k] - b3[k];
+                    dpoint(A, lj, a3); dpoint(B, lj, b3);
+                    for (int k = 0; k < 3; ++k) dj[k] = a3[k] - b3[k];
+                    double val = dot3(di, dj) + dot3(v, ddv);
+                    const int third = S.con_third()[c];
+                    if (third == i && third == j) val -= 1.0;
+                    acc += 2.0 * lam * val;
+                } else {
+                    acc += lam * ddv[S.con_third()[c]];
+                }
+            }
+            Y[j * ldy + i] = acc;
+        }
+        t.sync();
+    }
+
+    // ---- MidpointVI_solve_DEL (midpointvi.c:691-747).  In: q1, p1, u1, q2 (start / k2), lam.
+    // Out: q2, lam, p2.  Returns the iteration count or a negative Status.  On return the
+    // workspace holds the first-order midpoint data of the converged step and (nc > 0) Dh1, Dh2.
+    TREPB_HD int solve(double t1, double t2, double tol, int max_it) {
+        const int nd = S.nd, nc = S.nc, nr = nd + nc, nq = S.nq, lane = t.lane();
+        const double dt = t2 - t1;
+        int iterations = 0;
+        TREPB_TICK_INIT
+        if (nc > 0) {
+            set_point(1, dt);
+            pose_sweep(false);
+            points();
+            constraints(false, 1);
+        }
+        TREPB_TICK(16);
+        for (;;) {
+            if (nc > 0) {
+                set_point(2, dt);
+                pose_sweep(false);
+                points();
+                constraints(true, 2);
+            }
+            TREPB_TICK(17);
+            set_point(0, dt);
+            pose_sweep(true);
+            TREPB_TICK(18);
+            dyn_first();
+            TREPB_TICK(19);
+            // residual (midpointvi.c:533-565); forces: Damping (damping.c:13-22), ConfigForce (configforce.c:13-22)
+            for (int j = lane; j < nd; j += Team::kSize) {
+                double fo = -S.damp()[j] * w[L.dq + j];
+                for (int u = 0; u < S.nu; ++u) fo += S.Fu()[j * S.nu + u] * w[L.u1 + u];
+                double f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
+                for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
+                w[L.fr + j] = f;
+            }
+            for (int c = lane; c < nc; c += Team::kSize) w[L.fr + nd + c] = w[L.hc + c];
+            t.sync();
+            // DEL_solved (midpointvi.c:672-689): every lane evaluates the same test
+            double nrm = 0.0;
+            for (int j = 0; j < nd; ++j) nrm += w[L.fr + j] * w[L.fr + j];
+            bool solved = !(sqrt(nrm) > tol);
+            for (int c = 0; c < nc; ++c)
+                if (fabs(w[L.fr + nd + c]) > S.con_tol()[c]) solved = false;
+            TREPB_TICK(20);
+            if (solved) break;
+            if (iterations > max_it) return ST_NOT_CONVERGED;
+            // Jacobian (midpointvi.c:577-670) with the residual as an extra column
+            dyn_second();
+            TREPB_TICK(21);
+            double* A = w + L.N;
+            const int ld = L.ldf;
+            for (int e = lane; e < nr * (nr + 1); e += Team::kSize) {
+                const int k = e / (nr + 1), i = e % (nr + 1);
+                double v;
+                if (i == nr) v = w[L.fr + k];
+                else if (k < nd && i < nd) {
+                    double qq, vv, vab, vba;
+                    tab(k, i, qq, vv, vab, vba);
+                    v = (0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vba - 0.5 * vab;
+                    if (k == i) v += -S.damp()[k];
+                } else if (k < nd) v = -w[L.Dh1 + (i - nd) * nd + k];
+                else if (i < nd) v = w[L.Dh2 + (k - nd) * nq + i];
+                else v = 0.0;
+                A[k * ld + i] = v;
+            }
+            t.sync();
+            TREPB_TICK(22);
+            if (!team_lu(t, A, ld, nr, 1, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+            TREPB_TICK(23);
+            team_backsolve_vec(t, A, ld, nr, nr, w + L.rdM, w + L.fr);
+            for (int k = lane; k < nd; k += Team::kSize) w[L.q2 + k] -= w[L.fr + k];
+            for (int c = lane; c < nc; c += Team::kSize) w[L.lam + c] -= w[L.fr + nd + c];
+            t.sync();
+            TREPB_TICK(24);
+            iterations++;
+        }
+        for (int j = lane; j < nd; j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
+        t.sync();
+        return iterations;
+    }
+
+    // calc_p2 alone (midpointvi.c:2702-2708)
+    TREPB_HD void calc_p2(double dt) {
+        set_point(0, dt);
+        pose_sweep(true);
+        dyn_first();
+        for (int j = t.lane(); j < S.nd; j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
+        t.sync();
+    }
+
+    // ---- MidpointVI_calc_deriv1 (midpointvi.c:749-1120) right after solve() on the same workspace.
+    // Output layout as trepb_math.cuh::deriv1.  aux: optional export for the second-derivative
+    // kernel (AuxLayout of trepb_kernels.cuh: M2 LU, M2 piv, PJ LU, PJ piv, Dh1, Dh2, T22).
+    TREPB_HD int deriv1(double t1, double t2, const Deriv1Out& o, double* aux, const int* auxo) {
+        const int nd = S.nd, nk = S.nk, nq = S.nq, nc = S.nc, nu = S.nu, lane = t.lane();
+        const int nX = 2 * nq, nU = nu + nk;
+        const double dt = t2 - t1;
+        double* Y = w + L.N;
+        const int ldy = L.ldy;
+        TREPB_TICK_INIT
+        dyn_second();   // tables at the converged midpoint
+        TREPB_TICK(25);
+        if (nc > 0) {
+            set_point(1, dt);
+            pose_sweep(false);
+            points();
+            ddh_lambda(Y, ldy);
+        }
+        TREPB_TICK(26);
+        // M2 = (D2D1L2 + D2fm2)^T on the dynamic block, with Dh1^T as extra columns; D2D2L2 dynamic block
+        double* M2 = w + L.M2;
+        double* T22 = w + L.T22;
+        const int ldm = L.ldm;
+        for (int e = lane; e < nd * nd; e += Team::kSize) {
+            const int a = e / nd, b = e % nd;
+            double qq, vv, vab, vba;
+            tab(b, a, qq, vv, vab, vba);   // T21(b, a)
+            qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
+            const double fv = a == b ? -S.damp()[a] : 0.0;
+            M2[a * ldm + b] = (qq - vv) + vab - vba + fv;
+            // T22(a, b): symmetric in the table terms -> same lookup transposed
+            T22[b * nd + a] = (qq + vv) + vab + vba;
+        }
+        for (int e = lane; e < nd * nc; e += Team::kSize) {
+            const int a = e / nc, c = e % nc;
+            M2[a * ldm + nd + c] = w[L.Dh1 + c * nd + a];
+        }
+        t.sync();
+        TREPB_TICK(27);
+        if (!team_lu(t, M2, ldm, nd, nc, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+        double* PJ = w + L.PJ;
+        const int ldp = L.ldp;
+        if (nc > 0) {
+            for (int c = lane; c < nc; c += Team::kSize) col_backsolve(M2, ldm, nd, w + L.rdM, M2 + nd + c, ldm);
+            t.sync();
+            // proj = -Dh2_d M2^-1 Dh1^T  (midpointvi.c:910-927)
+            for (int e = lane; e < nc * nc; e += Team::kSize) {
+                const int a = e / nc, b = e % nc;
+                double s = 0.0;
+                for (int k = 0; k < nd; ++k) s += w[L.Dh2 + a * nq + k] * M2[k * ldm + nd + b];
+                PJ[a * ldp + b] = -s;
+            }
+            t.sync();
+            if (!team_lu(t, PJ, ldp, nc, 0, ipivP(), iswpP(), w + L.scl, w + L.rdP, 1e-20)) return ST_SINGULAR;
+        }
+        if (aux) {
+            // auxo: o_m2, o_m2p, o_pj, o_pjp, o_dh1, o_dh2, o_t22
+            for (int e = lane; e < nd * nd; e += Team::kSize) {
+                aux[auxo[0] + e] = M2[(e / nd) * ldm + e % nd];
+                aux[auxo[6] + e] = T22[e];
+            }
+            for (int i = lane; i < nd; i += Team::kSize) aux[auxo[1] + i] = (double)ipivM()[i];
+            for (int e = lane; e < nc * nc; e += Team::kSize) aux[auxo[2] + e] = PJ[(e / nc) * ldp + e % nc];
+            for (int i = lane; i < nc; i += Team::kSize) aux[auxo[3] + i] = (double)ipivP()[i];
+            for (int e = lane; e < nc * nd; e += Team::kSize) {
+                aux[auxo[4] + e] = w[L.Dh1 + e];
+                aux[auxo[5] + e] = w[L.Dh2 + (e / nd) * nq + e % nd];
+            }
+        }
+        TREPB_TICK(28);
+        // ---- right-hand sides, one column per lane.  group 0: q1 columns.  group 1: p1 | u1 | k2.
+        for (int grp = 0; grp < 2; ++grp) {
+            const int ncols = grp == 0 ? nq : nd + nu + nk;
+            // explicit part c (midpointvi.c:929-1098)
+            for (int e = lane; e < nd * ncols; e += Team::kSize) {
+                const int j = e / ncols, col = e % ncols;
+                double c;
+                if (grp == 0) {
+                    double qq, vv, vab, vba;
+                    tab(col, j, qq, vv, vab, vba);   // T11(col, j)
+                    const double fv = col == j ? -S.damp()[j] : 0.0;
+                    c = -((0.25 * dt * qq + 1.0 / dt * vv) - 0.5 * vab - 0.5 * vba - fv);
+                    if (nc > 0) c += Y[j * ldy + col];
+                } else if (col < nd) {
+                    c = col == j ? -1.0 : 0.0;
+                } else if (col < nd + nu) {
+                    c = -dt * S.Fu()[j * nu + (col - nd)];
+                } else {
+                    const int a = nd + (col - nd - nu);
+                    double qq, vv, vab, vba;
+                    tab(a, j, qq, vv, vab, vba);     // T21(a, j), a kinematic
+                    c = -((0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vab - 0.5 * vba);
+                }
+                Y[j * ldy + col] = c;
+            }
+            t.sync();
+            double* Z = w + L.Z;
+            for (int col = lane; col < ncols; col += Team::kSize) {
+                double* y = Y + col;
+                col_solve(M2, ldm, nd, iswpM(), w + L.rdM, y, ldy);
+                if (nc > 0) {
+                    double* z = Z + col;
+                    for (int c = 0; c < nc; ++c) {
+                        double s = 0.0;
+                        for (int j = 0; j < nd; ++j) s += w[L.Dh2 + c * nq + j] * y[j * ldy];
+                        if (grp == 1 && col >= nd + nu) s += w[L.Dh2 + c * nq + nd + (col - nd - nu)];
+                        z[c * ldy] = s;
+                    }
+                    col_solve(PJ, ldp, nc, iswpP(), w + L.rdP, z, ldy);
+                    for (int j = 0; j < nd; ++j) {
+                        double s = y[j * ldy];
+                        for (int c = 0; c < nc; ++c) s += M2[j * ldm + nd + c] * z[c * ldy];
+                        y[j * ldy] = s;
+                    }
+                }
+                // outputs of this column
+                int kindv, i;
+                if (grp == 0) { kindv = 0; i = col; }
+                else if (col < nd) { kindv = 1; i = col; }
+                else if (col < nd + nu) { kindv = 2; i = col - nd; }
+                else { kindv = 3; i = col - nd - nu; }
+                double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
+                double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+                double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+                for (int j = 0; j < nd; ++j) {
+                    double pv = 0.0;
+                    if (kindv == 0 || kindv == 3) {
+                        const int a = kindv == 0 ? i : nd + i;
+                        double qq, vv, vab, vba;
+                        tab(a, j, qq, vv, vab, vba);
+                        qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
+                        pv = kindv == 0 ? (qq - vv) - vab + vba      // T12(i, j)
+                                        : (qq + vv) + vab + vba;     // T22(nd+i, j)
+                    }
+                    for (int k = 0; k < nd; ++k) pv += T22[k * nd + j] * y[k * ldy];
+                    const double qv = y[j * ldy];
+                    if (q2o) q2o[i * nd + j] = qv;
+                    if (p2o) p2o[i * nd + j] = pv;
+                    if (kindv == 0) {
+                        if (o.A) { o.A[j * nX + i] = qv; o.A[(nq + j) * nX + i] = pv; }
+                    } else if (kindv == 1) {
+                        if (o.A) { o.A[j * nX + nq + i] = qv; o.A[(nq + j) * nX + nq + i] = pv; }
+                    } else if (kindv == 2) {
+                        if (o.B) { o.B[j * nU + i] = qv; o.B[(nq + j) * nU + i] = pv; }
+                    } else {
+                        if (o.B) { o.B[j * nU + nu + i] = qv; o.B[(nq + j) * nU + nu + i] = pv; }
+                    }
+                }
+                if (l1o) for (int c = 0; c < nc; ++c) l1o[i * nc + c] = Z[c * ldy + col];
+            }
+            t.sync();
+        }
+        TREPB_TICK(29);
+        // constant blocks of A and B (dsystem.py:284-317)
+        if (o.A) {
+            for (int e = lane; e < nX * nX; e += Team::kSize) {
+                const int r = e / nX, c = e % nX;
+                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
+                if (dyn_row && c < nq + nd) continue;
+                double v = 0.0;
+                if (r >= nq + nd && c >= nd && c < nq && (r - nq - nd) == (c - nd)) v = -1.0 / dt;
+                o.A[e] = v;
+            }
+        }
+        if (o.B) {
+            for (int e = lane; e < nX * nU; e += Team::kSize) {
+                const int r = e / nU, c = e % nU;
+                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
+                if (dyn_row) continue;
+                double v = 0.0;
+                if (r >= nd && r < nq && c >= nu && (r - nd) == (c - nu)) v = 1.0;
+                if (r >= nq + nd && c >= nu && (r - nq - nd) == (c - nu)) v = 1.0 / dt;
+                o.B[e] = v;
+            }
+        }
+        t.sync();
+        TREPB_TICK(30);
+        return ST_OK;
+    }
+};
+
+}  // namespace trepb

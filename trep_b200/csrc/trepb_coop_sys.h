@@ -1,0 +1,396 @@
+// Link-level ("articulated body") view of a flattened system for the team-cooperative kernels
+// (trepb_coop_math.cuh): one warp works on one instance, its workspace lives in shared memory.
+//
+// The frame tree of the description (trep/system.py:733-771, trep/frame.py:658-721) is condensed
+// on the host, once per system:
+//   * every frame driven by a config becomes a LINK; the constant frames between two links are
+//     multiplied into one constant pre-transform (Rc, pc) of the lower link;
+//   * the masses that hang off a link through constant frames are summed into one rigid-body
+//     inertia (m, h = m c, Ibar about the link origin) of that link;
+//   * the frames used by constraints become POINTS: a link index and a constant offset;
+//   * links are numbered level by level (all links with k variable ancestors before those with
+//     k+1), so one tree level is a contiguous index range and the children of a link are
+//     contiguous too;
+//   * the (ancestor, descendant) link pairs that carry non-zero entries of the second-order
+//     Lagrangian tables (system.c:129-557: L_dqdq, L_ddqdq, L_ddqddq are zero unless both configs
+//     lie on one chain) are enumerated, with a config x config map into that list.
+//
+// The arithmetic built on these tables is the same mathematics as the reference's frame caches,
+// evaluated in world ("spatial") coordinates - see trepb_coop_math.cuh.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "../../include/trepb.h"
+#include "trepb_sys.h"
+
+namespace trepb {
+
+struct CoopSys {
+    int nl, nq, nd, nk, nu, nc, np, npairs, nlevels;
+    int has_gravity;
+    double grav[3];
+    // Tables live in one relocatable blob (host memory, device memory or a shared-memory copy):
+    // `base` + byte offsets, so that moving the view is one pointer.
+    //   links [nl]    l_par (parent link or -1), l_cfg (driving config), l_kind (bit0-1 axis, bit2
+    //                 revolute, bit3 has pre-transform, bit4 carries mass below, bit5 carries a point
+    //                 below), l_child0 / l_nchild (children are contiguous), l_Rc [nl][9], l_pc [nl][3],
+    //                 l_in [nl][10] = m, h[3], Ibar (xx yy zz xy xz yz), l_anc (ancestor-or-self mask)
+    //   lvl_off [nlevels+1]
+    //   configs [nq]  cfg_link (link driven by the config or -1), damp [nd] (sum of Damping
+    //                 coefficients), ks / kq0 [nq] (sum of ConfigSpring k, k*q0), Fu [nd][nu]
+    //   pairs         pair_ij [npairs] = i | j << 8 (i ancestor-or-self of j); pm [nq][nq] = +idx+1 when
+    //                 the row config is the ancestor(-or-self), -(idx+1) when it is the descendant, 0
+    //   points [np]   pt_link (-1: fixed in the world), pt_r [np][3]
+    //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask)
+    const char* base;
+    int o_l_par;
+    int o_l_cfg;
+    int o_l_kind;
+    int o_l_child0;
+    int o_l_nchild;
+    int o_l_Rc;
+    int o_l_pc;
+    int o_l_in;
+    int o_l_anc;
+    int o_lvl_off;
+    int o_cfg_link;
+    int o_damp;
+    int o_ks;
+    int o_kq0;
+    int o_Fu;
+    int o_pair_ij;
+    int o_pm;
+    int o_pt_link;
+    int o_pt_r;
+    int o_con_kind;
+    int o_con_a;
+    int o_con_b;
+    int o_con_third;
+    int o_con_dist;
+    int o_con_tol;
+    int o_con_dep;
+    TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
+    TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
+    TREPB_HD const int32_t* l_kind() const { return (const int32_t*)(base + o_l_kind); }
+    TREPB_HD const int32_t* l_child0() const { return (const int32_t*)(base + o_l_child0); }
+    TREPB_HD const int32_t* l_nchild() const { return (const int32_t*)(base + o_l_nchild); }
+    TREPB_HD const double* l_Rc() const { return (const double*)(base + o_l_Rc); }
+    TREPB_HD const double* l_pc() const { return (const double*)(base + o_l_pc); }
+    TREPB_HD const double* l_in() const { return (const double*)(base + o_l_in); }
+    TREPB_HD const uint64_t* l_anc() const { return (const uint64_t*)(base + o_l_anc); }
+    TREPB_HD const int32_t* lvl_off() const { return (const int32_t*)(base + o_lvl_off); }
+    TREPB_HD const int32_t* cfg_link() const { return (const int32_t*)(base + o_cfg_link); }
+    TREPB_HD const double* damp() const { return (const double*)(base + o_damp); }
+    TREPB_HD const double* ks() const { return (const double*)(base + o_ks); }
+    TREPB_HD const double* kq0() const { return (const double*)(base + o_kq0); }
+    TREPB_HD const double* Fu() const { return (const double*)(base + o_Fu); }
+    TREPB_HD const int32_t* pair_ij() const { return (const int32_t*)(base + o_pair_ij); }
+    TREPB_HD const int16_t* pm() const { return (const int16_t*)(base + o_pm); }
+    TREPB_HD const int32_t* pt_link() const { return (const int32_t*)(base + o_pt_link); }
+    TREPB_HD const double* pt_r() const { return (const double*)(base + o_pt_r); }
+    TREPB_HD const int32_t* con_kind() const { return (const int32_t*)(base + o_con_kind); }
+    TREPB_HD const int32_t* con_a() const { return (const int32_t*)(base + o_con_a); }
+    TREPB_HD const int32_t* con_b() const { return (const int32_t*)(base + o_con_b); }
+    TREPB_HD const int32_t* con_third() const { return (const int32_t*)(base + o_con_third); }
+    TREPB_HD const double* con_dist() const { return (const double*)(base + o_con_dist); }
+    TREPB_HD const double* con_tol() const { return (const double*)(base + o_con_tol); }
+    TREPB_HD const uint64_t* con_dep() const { return (const uint64_t*)(base + o_con_dep); }
+    TREPB_HD int axis(int l) const { return l_kind()[l] & 3; }
+    TREPB_HD bool rot(int l) const { return (l_kind()[l] & 4) != 0; }
+    TREPB_HD bool has_xc(int l) const { return (l_kind()[l] & 8) != 0; }
+    TREPB_HD bool dyn(int l) const { return (l_kind()[l] & 16) != 0; }
+    TREPB_HD bool wrl(int l) const { return (l_kind()[l] & 32) != 0; }
+};
+
+struct CoopPack {
+    bool ok = false;
+    std::string why;          // why the cooperative path does not apply
+    std::vector<char> blob;
+    CoopSys proto;
+    size_t off[40];
+
+    CoopSys view(const char* base) const {
+        CoopSys s = proto;
+        s.base = base;
+        int k = 0;
+        s.o_l_par = (int)off[k++];
+        s.o_l_cfg = (int)off[k++];
+        s.o_l_kind = (int)off[k++];
+        s.o_l_child0 = (int)off[k++];
+        s.o_l_nchild = (int)off[k++];
+        s.o_l_Rc = (int)off[k++];
+        s.o_l_pc = (int)off[k++];
+        s.o_l_in = (int)off[k++];
+        s.o_l_anc = (int)off[k++];
+        s.o_lvl_off = (int)off[k++];
+        s.o_cfg_link = (int)off[k++];
+        s.o_damp = (int)off[k++];
+        s.o_ks = (int)off[k++];
+        s.o_kq0 = (int)off[k++];
+        s.o_Fu = (int)off[k++];
+        s.o_pair_ij = (int)off[k++];
+        s.o_pm = (int)off[k++];
+        s.o_pt_link = (int)off[k++];
+        s.o_pt_r = (int)off[k++];
+        s.o_con_kind = (int)off[k++];
+        s.o_con_a = (int)off[k++];
+        s.o_con_b = (int)off[k++];
+        s.o_con_third = (int)off[k++];
+        s.o_con_dist = (int)off[k++];
+        s.o_con_tol = (int)off[k++];
+        s.o_con_dep = (int)off[k++];
+        return s;
+    }
+};
+
+namespace coop_detail {
+struct Se3 {
+    double R[9], p[3];
+};
+inline Se3 se3_identity() {
+    Se3 x;
+    for (int k = 0; k < 9; ++k) x.R[k] = (k % 4 == 0) ? 1.0 : 0.0;
+    x.p[0] = x.p[1] = x.p[2] = 0.0;
+    return x;
+}
+inline Se3 se3_mul(const Se3& a, const Se3& b) {  // a then b (b expressed in a's frame)
+    Se3 o;
+    for (int r = 0; r < 3; ++r) {
+        for (int c = 0; c < 3; ++c)
+            o.R[r * 3 + c] = a.R[r * 3] * b.R[c] + a.R[r * 3 + 1] * b.R[3 + c] + a.R[r * 3 + 2] * b.R[6 + c];
+        o.p[r] = a.p[r] + a.R[r * 3] * b.p[0] + a.R[r * 3 + 1] * b.p[1] + a.R[r * 3 + 2] * b.p[2];
+    }
+    return o;
+}
+// local transform of a constant frame (trep/_trep/frame.c:839-1076)
+inline Se3 se3_const_frame(int kind, double value, const double* se3) {
+    Se3 x = se3_identity();
+    if (kind == K_CONST_SE3) {
+        for (int r = 0; r < 3; ++r) {
+            for (int c = 0; c < 3; ++c) x.R[r * 3 + c] = se3[r * 4 + c];
+            x.p[r] = se3[r * 4 + 3];
+        }
+    } else if (kind >= K_TX && kind <= K_TZ) {
+        x.p[kind - K_TX] = value;
+    } else if (kind >= K_RX && kind <= K_RZ) {
+        const int a = kind - K_RX, b = (a + 1) % 3, c = (a + 2) % 3;
+        const double cs = cos(value), sn = sin(value);
+        x.R[b * 3 + b] = cs; x.R[b * 3 + c] = -sn;
+        x.R[c * 3 + b] = sn; x.R[c * 3 + c] = cs;
+    }
+    return x;
+}
+inline bool se3_is_identity(const Se3& x) {
+    for (int k = 0; k < 9; ++k) if (x.R[k] != ((k % 4 == 0) ? 1.0 : 0.0)) return false;
+    return x.p[0] == 0.0 && x.p[1] == 0.0 && x.p[2] == 0.0;
+}
+}  // namespace coop_detail
+
+// Builds the link-level tables.  Returns a pack with ok == false (and `why`) when the system uses
+// something the cooperative kernels do not implement (the thread-per-instance general kernels do).
+inline CoopPack coop_pack(const trepb_sysdesc* d) {
+    using namespace coop_detail;
+    CoopPack P;
+    const int nf = d->n_frames, nd = d->nd, nk = d->nk, nq = nd + nk, nu = d->nu, nc = d->n_constraints;
+    if (nq > 64) { P.why = "more than 64 configs"; return P; }
+    for (int i = 0; i < d->n_potentials; ++i)
+        if (d->pot_kind[i] == TREPB_POT_LINEAR_SPRING) { P.why = "LinearSpring potential"; return P; }
+    for (int i = 0; i < d->n_forces; ++i)
+        if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
+
+    // ---- frames -> links
+    std::vector<int> flink(nf, -1);      // frame -> frame index of the link it belongs to (-1: world)
+    std::vector<Se3> fx(nf);             // frame pose in its link's coordinates (world coordinates when flink == -1)
+    std::vector<int> lframes;            // variable frames in pre-order
+    fx[0] = se3_identity();
+    for (int f = 1; f < nf; ++f) {
+        const int par = d->frame_parent[f];
+        if (d->frame_config[f] >= 0) {
+            flink[f] = f;
+            fx[f] = se3_identity();
+            lframes.push_back(f);
+        } else {
+            flink[f] = flink[par];
+            fx[f] = se3_mul(fx[par], se3_const_frame(d->frame_kind[f], d->frame_value[f], d->frame_se3 + 12 * f));
+        }
+    }
+    const int nl = (int)lframes.size();
+    if (nl < 1) { P.why = "no variable frame"; return P; }
+    if (nl > 64) { P.why = "more than 64 variable frames"; return P; }
+    // parent link (as frame index) and level of every variable frame
+    std::vector<int> fpl(nf, -1), flevel(nf, 0);
+    int nlevels = 0;
+    for (int f : lframes) {
+        fpl[f] = flink[d->frame_parent[f]];
+        flevel[f] = fpl[f] < 0 ? 0 : flevel[fpl[f]] + 1;
+        if (flevel[f] + 1 > nlevels) nlevels = flevel[f] + 1;
+    }
+    // level order; within a level, ordered by (parent's new index, pre-order) so children are contiguous
+    std::vector<int> order;              // new link index -> frame
+    std::vector<int> newidx(nf, -1);
+    std::vector<int32_t> lvl_off(nlevels + 1, 0);
+    for (int L = 0; L < nlevels; ++L) {
+        lvl_off[L] = (int32_t)order.size();
+        if (L == 0) {
+            for (int f : lframes) if (flevel[f] == 0) { newidx[f] = (int)order.size(); order.push_back(f); }
+        } else {
+            const int lo = lvl_off[L - 1], hi = (int)order.size();
+            for (int pi = lo; pi < hi; ++pi)
+                for (int f : lframes)
+                    if (flevel[f] == L && fpl[f] == order[pi]) { newidx[f] = (int)order.size(); order.push_back(f); }
+        }
+    }
+    lvl_off[nlevels] = (int32_t)order.size();
+
+    std::vector<int32_t> l_par(nl), l_cfg(nl), l_kind(nl), l_child0(nl, 0), l_nchild(nl, 0);
+    std::vector<double> l_Rc(9 * nl), l_pc(3 * nl), l_in(10 * nl, 0.0);
+    std::vector<uint64_t> l_anc(nl, 0);
+    std::vector<int32_t> cfg_link(nq > 0 ? nq : 1, -1);
+    for (int l = 0; l < nl; ++l) {
+        const int f = order[l];
+        const int kind = d->frame_kind[f];
+        l_par[l] = fpl[f] < 0 ? -1 : newidx[fpl[f]];
+        l_cfg[l] = d->frame_config[f];
+        cfg_link[l_cfg[l]] = l;
+        const Se3 xc = fx[d->frame_parent[f]];
+        int kbits = (kind >= K_RX ? (kind - K_RX) | 4 : (kind - K_TX));
+        if (!se3_is_identity(xc)) kbits |= 8;
+        l_kind[l] = kbits;
+        for (int k = 0; k < 9; ++k) l_Rc[9 * l + k] = xc.R[k];
+        for (int k = 0; k < 3; ++k) l_pc[3 * l + k] = xc.p[k];
+        l_anc[l] = (l_par[l] < 0 ? 0ull : l_anc[l_par[l]]) | (1ull << l);
+    }
+    for (int l = nl - 1; l >= 0; --l)
+        if (l_par[l] >= 0) { l_child0[l_par[l]] = l; l_nchild[l_par[l]]++; }
+
+    // ---- masses -> link inertia (about the link origin, link axes)
+    for (int f = 1; f < nf; ++f) {
+        const double* mm = d->frame_mass + 4 * f;
+        if (mm[0] == 0.0 && mm[1] == 0.0 && mm[2] == 0.0 && mm[3] == 0.0) continue;
+        if (flink[f] < 0) continue;  // fixed in the world: contributes nothing to the dynamics
+        const int l = newidx[flink[f]];
+        const Se3& x = fx[f];
+        double* I = &l_in[10 * l];
+        const double m = mm[0];
+        I[0] += m;
+        for (int k = 0; k < 3; ++k) I[1 + k] += m * x.p[k];
+        // R diag(Ixx,Iyy,Izz) R^T + m (|p|^2 1 - p p^T)
+        const double pp = x.p[0] * x.p[0] + x.p[1] * x.p[1] + x.p[2] * x.p[2];
+        const int rr[6] = {0, 1, 2, 0, 0, 1}, cc[6] = {0, 1, 2, 1, 2, 2};
+        for (int e = 0; e < 6; ++e) {
+            const int r = rr[e], c = cc[e];
+            double v = 0.0;
+            for (int k = 0; k < 3; ++k) v += x.R[r * 3 + k] * mm[1 + k] * x.R[c * 3 + k];
+            v += -m * x.p[r] * x.p[c];
+            if (r == c) v += m * pp;
+            I[4 + e] += v;
+        }
+        for (int a = l; a >= 0; a = l_par[a]) l_kind[a] |= 16;
+    }
+
+    // ---- constraint end points
+    std::vector<int32_t> pt_link;
+    std::vector<double> pt_r;
+    std::vector<int> pt_frame;
+    auto point_of = [&](int f) {
+        for (size_t i = 0; i < pt_frame.size(); ++i) if (pt_frame[i] == f) return (int)i;
+        pt_frame.push_back(f);
+        const int l = flink[f] < 0 ? -1 : newidx[flink[f]];
+        pt_link.push_back(l);
+        for (int k = 0; k < 3; ++k) pt_r.push_back(fx[f].p[k]);
+        for (int a = l; a >= 0; a = l_par[a]) l_kind[a] |= 32;
+        return (int)pt_frame.size() - 1;
+    };
+    std::vector<int32_t> con_kind(nc > 0 ? nc : 1), con_a(nc > 0 ? nc : 1), con_b(nc > 0 ? nc : 1), con_third(nc > 0 ? nc : 1);
+    std::vector<double> con_dist(nc > 0 ? nc : 1), con_tol(nc > 0 ? nc : 1);
+    std::vector<uint64_t> con_dep(nc > 0 ? nc : 1, 0);
+    for (int c = 0; c < nc; ++c) {
+        const int32_t* ii = d->con_i + 4 * c;
+        con_kind[c] = d->con_kind[c];
+        con_a[c] = point_of(ii[0]);
+        con_b[c] = point_of(ii[1]);
+        con_third[c] = ii[2];
+        con_dist[c] = d->con_d[4 * c];
+        con_tol[c] = d->con_d[4 * c + 1];
+        uint64_t m = 0;
+        for (int e = 0; e < 2; ++e) {
+            const int l = pt_link[e == 0 ? con_a[c] : con_b[c]];
+            if (l < 0) continue;
+            for (int a = l; a >= 0; a = l_par[a]) m |= 1ull << l_cfg[a];
+        }
+        if (con_kind[c] == TREPB_CON_DISTANCE && ii[2] >= 0) m |= 1ull << ii[2];
+        con_dep[c] = m;
+    }
+    const int np = (int)pt_link.size();
+
+    // ---- chain pairs (only links that carry mass below)
+    std::vector<int32_t> pair_ij;
+    std::vector<int16_t> pm((size_t)(nq > 0 ? nq * nq : 1), 0);
+    for (int j = 0; j < nl; ++j) {
+        if (!(l_kind[j] & 16)) continue;
+        for (int i = j; i >= 0; i = l_par[i]) {
+            const int idx = (int)pair_ij.size();
+            pair_ij.push_back(i | (j << 8));
+            const int ci = l_cfg[i], cj = l_cfg[j];
+            pm[(size_t)ci * nq + cj] = (int16_t)(idx + 1);
+            if (i != j) pm[(size_t)cj * nq + ci] = (int16_t)(-(idx + 1));
+        }
+    }
+    const int npairs = (int)pair_ij.size();
+    if (npairs > 30000) { P.why = "too many chain pairs"; return P; }
+
+    // ---- potentials / forces folded into per-config constants
+    std::vector<double> damp(nd > 0 ? nd : 1, 0.0), ks(nq > 0 ? nq : 1, 0.0), kq0(nq > 0 ? nq : 1, 0.0), Fu((size_t)(nd * nu > 0 ? nd * nu : 1), 0.0);
+    double grav[3] = {0, 0, 0};
+    int has_grav = 0;
+    for (int i = 0; i < d->n_potentials; ++i) {
+        if (d->pot_kind[i] == TREPB_POT_GRAVITY) {
+            for (int k = 0; k < 3; ++k) grav[k] += d->pot_d[4 * i + k];
+            has_grav = 1;
+        } else if (d->pot_kind[i] == TREPB_POT_CONFIG_SPRING) {
+            const int c = d->pot_i[4 * i];
+            ks[c] += d->pot_d[4 * i];
+            kq0[c] += d->pot_d[4 * i] * d->pot_d[4 * i + 1];
+        }
+    }
+    for (int i = 0; i < d->n_forces; ++i) {
+        if (d->force_kind[i] == TREPB_FORCE_DAMPING) {
+            for (int j = 0; j < nd; ++j) damp[j] += d->dpool[d->force_i[4 * i] + j];
+        } else if (d->force_kind[i] == TREPB_FORCE_CONFIG) {
+            const int c = d->force_i[4 * i], u = d->force_i[4 * i + 1];
+            if (c < nd) Fu[(size_t)c * nu + u] += 1.0;
+        }
+    }
+
+    // ---- pack
+    memset(&P.proto, 0, sizeof(P.proto));
+    P.proto.nl = nl; P.proto.nq = nq; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
+    P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
+    P.proto.has_gravity = has_grav;
+    for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
+    int k = 0;
+    auto put = [&](const void* src, size_t bytes) {
+        size_t o = (P.blob.size() + 15) & ~size_t(15);
+        P.blob.resize(o + (bytes ? bytes : 16), 0);
+        if (bytes && src) memcpy(P.blob.data() + o, src, bytes);
+        P.off[k++] = o;
+    };
+    put(l_par.data(), 4 * nl); put(l_cfg.data(), 4 * nl); put(l_kind.data(), 4 * nl);
+    put(l_child0.data(), 4 * nl); put(l_nchild.data(), 4 * nl);
+    put(l_Rc.data(), 8 * 9 * nl); put(l_pc.data(), 8 * 3 * nl); put(l_in.data(), 8 * 10 * nl);
+    put(l_anc.data(), 8 * nl); put(lvl_off.data(), 4 * (nlevels + 1));
+    put(cfg_link.data(), 4 * nq); put(damp.data(), 8 * nd); put(ks.data(), 8 * nq); put(kq0.data(), 8 * nq);
+    put(Fu.data(), 8 * (size_t)nd * nu);
+    put(pair_ij.data(), 4 * (size_t)npairs); put(pm.data(), 2 * (size_t)nq * nq);
+    put(pt_link.data(), 4 * (size_t)np); put(pt_r.data(), 8 * 3 * (size_t)np);
+    put(con_kind.data(), 4 * nc); put(con_a.data(), 4 * nc); put(con_b.data(), 4 * nc); put(con_third.data(), 4 * nc);
+    put(con_dist.data(), 8 * nc); put(con_tol.data(), 8 * nc); put(con_dep.data(), 8 * nc);
+    P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
+    P.ok = true;
+    return P;
+}
+
+}  // namespace trepb

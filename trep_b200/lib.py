@@ -67,6 +67,7 @@ _lib.trepb_system_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c
 _lib.trepb_system_destroy.argtypes = [C.c_void_p]
 _lib.trepb_system_destroy.restype = None
 _lib.trepb_system_is_specialized.argtypes = [C.c_void_p]
+_lib.trepb_system_is_cooperative.argtypes = [C.c_void_p]
 _lib.trepb_system_kernel_name.argtypes = [C.c_void_p]
 _lib.trepb_step_batch.argtypes = [C.c_void_p, C.POINTER(StepArgs)]
 _lib.trepb_step_batch_dev.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
@@ -90,7 +91,7 @@ _lib.trepb_measure_fp64_peak.argtypes = [C.c_int, _dp]
 
 EXPORTS = [
     "trepb_abi_version", "trepb_last_error", "trepb_system_create", "trepb_system_destroy",
-    "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_kernel_name",
+    "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_linearize_batch",
@@ -210,12 +211,20 @@ def _ptr(x):
 class System:
     """Handle of a flattened system resident on one GPU (trepb_system)."""
 
-    def __init__(self, desc: D.SystemDesc, device=0, specialize=True):
+    def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None):
+        """specialize=False: skip the ahead-of-time specialised kernels.  cooperative: None = let
+        the library choose between one thread and one warp per instance for a table-driven system,
+        False = always one thread, True = always the cooperative kernels (implies specialize=False)."""
         self.desc = desc
         self.device = device
         cd, self._keep = D.to_c(desc)
         h = C.c_void_p()
-        _check(_lib.trepb_system_create(C.byref(cd), device, 0 if specialize else 1, C.byref(h)))
+        flags = 0 if (specialize and cooperative is not True) else 1
+        if cooperative is False:
+            flags |= 2
+        elif cooperative is True:
+            flags |= 4
+        _check(_lib.trepb_system_create(C.byref(cd), device, flags, C.byref(h)))
         self._h = h
         self.nq, self.nd, self.nk, self.nu, self.nc = desc.nq, desc.nd, desc.nk, desc.nu, desc.nc
         self.nX, self.nU = desc.nX, desc.nU
@@ -223,6 +232,10 @@ class System:
     @property
     def specialized(self):
         return bool(_lib.trepb_system_is_specialized(self._h))
+
+    @property
+    def cooperative(self):
+        return bool(_lib.trepb_system_is_cooperative(self._h))
 
     @property
     def kernel_name(self):
