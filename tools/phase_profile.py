@@ -8,7 +8,7 @@ from trep_b200 import lib, systems
 up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(a)
 rng = np.random.default_rng(0)
 B = int(os.environ.get("PUPPET_B", "32768"))
-d = systems.named_desc("puppet"); s = lib.System(d, cooperative={"1": True, "0": False}.get(os.environ.get("COOP", ""), None))
+d = systems.named_desc("puppet"); s = lib.System(d, specialize=os.environ.get("SPEC", "1") == "1", cooperative={"1": True, "0": False}.get(os.environ.get("COOP", ""), None))
 g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
 idx = rng.integers(1, 58, B)
 q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()

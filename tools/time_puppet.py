@@ -6,7 +6,7 @@ sys.path.insert(0, ROOT)
 from trep_b200 import lib, systems
 up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(a)
 rng = np.random.default_rng(0)
-d = systems.named_desc("puppet"); s = lib.System(d, cooperative={"1": True, "0": False}.get(os.environ.get("COOP", ""), None))
+d = systems.named_desc("puppet"); s = lib.System(d, specialize=os.environ.get("SPEC", "1") == "1", cooperative={"1": True, "0": False}.get(os.environ.get("COOP", ""), None))
 print("kernel:", s.kernel_name)
 g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
 for B in [int(x) for x in os.environ.get("BS", "32768,131072").split(",")]:

@@ -79,6 +79,7 @@ struct trepb_system {
     CoopLayout clay;
     int coop_blob_bytes = 0;
     int coop_warps = 0;          // instances in flight per CTA (= per SM)
+    const CoopKernelSet* cks = nullptr;
     // general path workspace
     WsStrided wsl;               // layout (base filled per launch)
     int ws_doubles = 0;
@@ -143,7 +144,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     s->dview = s->P.view(s->dblob);
     // kernel selection
     s->ks = general_kernels();
-    if (!(flags & TREPB_FLAG_NO_SPECIALIZE)) {
+    if (!(flags & (TREPB_FLAG_NO_SPECIALIZE | TREPB_FLAG_FORCE_COOP))) {
         const unsigned long long h = desc_hash(s->P);
         SpecRegistry& r = spec_registry();
         for (int i = 0; i < r.n; ++i)
@@ -171,6 +172,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
                 CUS(cudaMemcpy(s->dcoop, s->CP.blob.data(), s->CP.blob.size(), cudaMemcpyHostToDevice));
                 s->cview = s->CP.view(s->dcoop);
                 s->coop_warps = warps;
+                s->cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE));
                 s->coop = true;
             }
         }
@@ -235,7 +237,7 @@ int trepb_system_dims(const trepb_system* s, int32_t* nq, int32_t* nd, int32_t* 
 }
 
 int trepb_system_is_specialized(const trepb_system* s) { return s && s->ks->specialized; }
-const char* trepb_system_kernel_name(const trepb_system* s) { return s ? (s->coop ? "cooperative" : s->ks->name) : ""; }
+const char* trepb_system_kernel_name(const trepb_system* s) { return s ? (s->coop ? s->cks->name : s->ks->name) : ""; }
 int trepb_system_is_cooperative(const trepb_system* s) { return s && s->coop; }
 
 int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_bytes, int32_t* blocks_per_sm,
@@ -245,7 +247,7 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
     KernelInfo ki;
     int b = 0;
     if (s->coop) {
-        CU(coop_kernel_info(which, &ki));
+        CU(s->cks->info(which, &ki));
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
         if (blocks_per_sm) *blocks_per_sm = 1;
@@ -363,7 +365,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
         CoopLaunch cl;
         make_coop(s, a->batch, (cudaStream_t)stream, &cl);
         Timed t(s, cl.stream);
-        CU(coop_step(cl, p));
+        CU(s->cks->step(cl, p));
         return TREPB_OK;
     }
     LaunchCfg c;
@@ -387,7 +389,7 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
         CoopLaunch cl;
         make_coop(s, batch, (cudaStream_t)stream, &cl);
         Timed t(s, cl.stream);
-        CU(coop_p2(cl, p));
+        CU(s->cks->p2(cl, p));
         return TREPB_OK;
     }
     LaunchCfg c;
@@ -429,7 +431,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
         AuxLayout al;
         al.set(ps.nd, ps.nc);
         Timed t(s, cl.stream);
-        CU(coop_lin(cl, p, al));
+        CU(s->cks->lin(cl, p, al));
         return TREPB_OK;
     }
     const bool stage = s->lin_stage_bytes > 0 && (p.A || p.B);

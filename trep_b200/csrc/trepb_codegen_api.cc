@@ -6,6 +6,7 @@
 
 #include "../../include/trepb.h"
 #include "trepb_codegen.h"
+#include "trepb_coop_sys.h"
 #include "trepb_err.h"
 #include "trepb_pack.h"
 
@@ -32,6 +33,18 @@ uint64_t trepb_desc_hash(const trepb_sysdesc* desc) {
     std::string err;
     if (!pack_system(desc, &P, &err)) { last_error() = err; return 0; }
     return desc_hash(P);
+}
+
+int trepb_coop_dims(const trepb_sysdesc* desc, int32_t* out) {
+    PackedSys P;
+    std::string err;
+    if (!pack_system(desc, &P, &err)) { last_error() = err; return TREPB_ERR_INVALID; }
+    CoopPack C = coop_pack(desc);
+    if (!C.ok) { last_error() = "cooperative kernels do not apply: " + C.why; return TREPB_ERR_UNSUPPORTED; }
+    const CoopSys& s = C.proto;
+    const int32_t v[8] = {s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, s.nlevels};
+    for (int i = 0; i < 8; ++i) out[i] = v[i];
+    return TREPB_OK;
 }
 
 int trepb_validate(const trepb_sysdesc* desc) {

@@ -1,4 +1,4 @@
-// Launch interface of the team-cooperative kernels (trepb_coop.cu).
+// Launch interface of the team-cooperative kernels (trepb_coop.cu, trepb_coop_kernels.cuh).
 #pragma once
 #include <cuda_runtime.h>
 #include "trepb_kernels.cuh"
@@ -15,9 +15,31 @@ struct CoopLaunch {
     CoopLayout lay;
 };
 
-cudaError_t coop_step(const CoopLaunch& c, const StepParams& p);
-cudaError_t coop_p2(const CoopLaunch& c, const P2Params& p);
-cudaError_t coop_lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al);
-cudaError_t coop_kernel_info(int which, KernelInfo* info);  // 0 step, 1 p2, 2 lin
+// One set per size flavour: run-time sizes ("cooperative") or a CtDims instantiation that serves
+// every system of that shape (e.g. "cooperative/puppet").
+struct CoopKernelSet {
+    const char* name;
+    int specialized;
+    bool (*matches)(const CoopSys&);
+    cudaError_t (*step)(const CoopLaunch&, const StepParams&);
+    cudaError_t (*p2)(const CoopLaunch&, const P2Params&);
+    cudaError_t (*lin)(const CoopLaunch&, const LinParams&, const AuxLayout&);
+    cudaError_t (*info)(int which, KernelInfo*);   // 0 step, 1 p2, 2 lin
+};
+
+struct CoopRegistry {
+    static constexpr int kMax = 32;
+    const CoopKernelSet* sets[kMax];
+    int n;
+};
+CoopRegistry& coop_registry();
+struct CoopRegistrar {
+    explicit CoopRegistrar(const CoopKernelSet* ks) {
+        CoopRegistry& r = coop_registry();
+        if (r.n < CoopRegistry::kMax) r.sets[r.n++] = ks;
+    }
+};
+const CoopKernelSet* coop_general_kernels();
+const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized);
 
 }  // namespace trepb

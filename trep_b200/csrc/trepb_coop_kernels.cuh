@@ -1,0 +1,238 @@
+// Team-cooperative kernel templates: one WARP per instance, the per-instance workspace and the link tables
+// in shared memory (trepb_coop_math.cuh).  Used for systems whose thread-per-instance workspace
+// would not stay on chip (the marionette: 86 frames, nd 22, nk 18, nc 6).
+//
+//   coop_step_kernel   trepb_step_batch*       (MidpointVI.step looped in-kernel)
+//   coop_p2_kernel     trepb_calc_p2_batch*
+//   coop_lin_kernel    trepb_linearize_batch*  (solve_DEL + calc_deriv1 -> A, B, raw arrays, aux)
+//
+// Persistent grid: one CTA per SM, as many warps per CTA as workspaces fit next to the table blob in
+// the SM's shared memory (7 for the marionette: 7 x 30.0 KB + 12.2 KB of tables); every warp
+// walks the batch with stride grid x warps.  All cross-lane traffic goes through shared memory and
+// __syncwarp(), the pivot search of the LU uses warp shuffles.
+#pragma once
+#include <cuda_runtime.h>
+#include "trepb_coop.h"
+
+namespace trepb {
+namespace coopk {
+
+struct Stage {
+    CoopSys S;
+    double* w;
+};
+
+__device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, const CoopLayout& lay) {
+    extern __shared__ double smem_[];
+    const int n8 = (blob_bytes + 7) / 8;
+    const double* src = (const double*)gs.base;
+    for (int i = threadIdx.x; i < n8; i += blockDim.x) smem_[i] = src[i];
+    __syncthreads();
+    Stage st;
+    st.S = gs;
+    st.S.base = (const char*)smem_;
+    st.w = smem_ + ((n8 + 1) & ~1) + (long)(threadIdx.x >> 5) * lay.total;
+    return st;
+}
+
+template <class D>
+__global__ void __launch_bounds__(256, 1)
+coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
+    CoopLayout lay = lay_;
+    if constexpr (D::kStatic) lay = D::layout();
+    Stage st = coop_stage(gs, blob_bytes, lay);
+    const CoopSys& S = st.S;
+    double* w = st.w;
+    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
+    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
+        for (int i = lane; i < nq; i += 32) {
+            const double v = p.q1[b * nq + i];
+            w[lay.q1 + i] = v;
+            w[lay.q2 + i] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < nd; i += 32) {
+            w[lay.p1 + i] = p.p1[b * nd + i];
+            if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
+        }
+        for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
+        int total = 0, status = ST_OK;
+        double t1 = p.t0;
+        for (int s = 0; s < p.nsteps; ++s) {
+            __syncwarp();
+            if (s > 0) {
+                for (int i = lane; i < nq; i += 32) w[lay.q1 + i] = w[lay.q2 + i];
+                for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = w[lay.p2 + i];
+            }
+            for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1 ? p.u1[(b * p.nsteps + s) * nu + i] : 0.0;
+            __syncwarp();
+            for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[(b * p.nsteps + s) * nk + i];
+            __syncwarp();
+            const double t2 = t1 + p.dt;
+            const int it = c.solve(t1, t2, p.tol, p.max_it);
+            if (it < 0) { status = it; break; }
+            total += it;
+            t1 = t2;
+            if (p.sample_every > 0 && (s + 1) % p.sample_every == 0) {
+                const long row = b * p.nsamples + (s + 1) / p.sample_every - 1;
+                if (p.traj_q) for (int i = lane; i < nq; i += 32) p.traj_q[row * nq + i] = w[lay.q2 + i];
+                if (p.traj_p) for (int i = lane; i < nd; i += 32) p.traj_p[row * nd + i] = w[lay.p2 + i];
+            }
+        }
+        __syncwarp();
+        for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
+        for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
+        if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
+        if (lane == 0) {
+            if (p.iters) p.iters[b] = total;
+            p.status[b] = status;
+        }
+        __syncwarp();
+    }
+}
+
+template <class D>
+__global__ void __launch_bounds__(256, 1)
+coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
+    CoopLayout lay = lay_;
+    if constexpr (D::kStatic) lay = D::layout();
+    Stage st = coop_stage(gs, blob_bytes, lay);
+    const CoopSys& S = st.S;
+    double* w = st.w;
+    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int nd = c.ND(), nq = c.NQ();
+    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
+        for (int i = lane; i < nq; i += 32) {
+            w[lay.q1 + i] = p.q0[b * nq + i];
+            w[lay.q2 + i] = p.q1[b * nq + i];
+        }
+        __syncwarp();
+        c.calc_p2(p.dt);
+        for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.p2 + i];
+        __syncwarp();
+    }
+}
+
+template <class D>
+__global__ void __launch_bounds__(256, 1)
+coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
+    CoopLayout lay = lay_;
+    if constexpr (D::kStatic) lay = D::layout();
+    Stage st = coop_stage(gs, blob_bytes, lay);
+    const CoopSys& S = st.S;
+    double* w = st.w;
+    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
+    const long nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
+    const int auxo[7] = {al.o_m2, al.o_m2p, al.o_pj, al.o_pjp, al.o_dh1, al.o_dh2, al.o_t22};
+    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
+        for (int i = lane; i < nq; i += 32) {
+            const double v = p.q1[b * nq + i];
+            w[lay.q1 + i] = v;
+            w[lay.q2 + i] = v;
+        }
+        __syncwarp();
+        for (int i = lane; i < nd; i += 32) {
+            w[lay.p1 + i] = p.p1[b * nd + i];
+            if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
+        }
+        for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[b * nk + i];
+        for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1[b * nu + i];
+        for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
+        __syncwarp();
+        const double t1 = p.t1 ? p.t1[b] : p.t1s;
+        const double t2 = p.t2 ? p.t2[b] : (t1 + p.dts);
+        int it = c.solve(t1, t2, p.tol, p.max_it);
+        int status = ST_OK;
+        if (it < 0) { status = it; it = 0; }
+        __syncwarp();
+        if (p.q2) for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
+        if (p.p2) for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
+        if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
+        if (status == ST_OK) {
+            Deriv1Out o;
+#define TREPB_RAW(idx, member, rows, cols) \
+            o.member = p.raw[idx] ? p.raw[idx] + b * (long)((rows) * (cols)) : nullptr;
+            TREPB_RAW(0, q2_dq1, nq, nd) TREPB_RAW(1, q2_dp1, nd, nd) TREPB_RAW(2, q2_du1, nu, nd) TREPB_RAW(3, q2_dk2, nk, nd)
+            TREPB_RAW(4, p2_dq1, nq, nd) TREPB_RAW(5, p2_dp1, nd, nd) TREPB_RAW(6, p2_du1, nu, nd) TREPB_RAW(7, p2_dk2, nk, nd)
+            TREPB_RAW(8, l1_dq1, nq, nc) TREPB_RAW(9, l1_dp1, nd, nc) TREPB_RAW(10, l1_du1, nu, nc) TREPB_RAW(11, l1_dk2, nk, nc)
+#undef TREPB_RAW
+            o.es = 1;
+            o.A = p.A ? p.A + b * nA : nullptr;
+            o.B = p.B ? p.B + b * nB : nullptr;
+            const int r = c.deriv1(t1, t2, o, p.aux ? p.aux + b * (long)p.aux_size : nullptr, auxo);
+            if (r < 0) status = r;
+        }
+        if (lane == 0) {
+            if (p.iters) p.iters[b] = it;
+            p.status[b] = status;
+        }
+        __syncwarp();
+    }
+}
+
+template <class K>
+cudaError_t prep(K kernel, size_t smem) {
+    if (smem > 48 * 1024)
+        return cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaSuccess;
+}
+
+template <class D>
+struct Launch {
+    static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
+        cudaError_t e = prep(coop_step_kernel<D>, c.smem);
+        if (e != cudaSuccess) return e;
+        coop_step_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        return cudaGetLastError();
+    }
+    static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
+        cudaError_t e = prep(coop_p2_kernel<D>, c.smem);
+        if (e != cudaSuccess) return e;
+        coop_p2_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        return cudaGetLastError();
+    }
+    static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
+        cudaError_t e = prep(coop_lin_kernel<D>, c.smem);
+        if (e != cudaSuccess) return e;
+        coop_lin_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+        return cudaGetLastError();
+    }
+    static cudaError_t info(int which, KernelInfo* ki) {
+        const void* fn = which == 0 ? (const void*)coop_step_kernel<D>
+                       : which == 1 ? (const void*)coop_p2_kernel<D> : (const void*)coop_lin_kernel<D>;
+        cudaFuncAttributes a;
+        cudaError_t e = cudaFuncGetAttributes(&a, fn);
+        if (e != cudaSuccess) return e;
+        ki->regs = a.numRegs;
+        ki->max_threads = a.maxThreadsPerBlock;
+        ki->static_smem = a.sharedSizeBytes;
+        ki->local_bytes = a.localSizeBytes;
+        return cudaSuccess;
+    }
+    static bool matches(const CoopSys& s) {
+        if constexpr (D::kStatic) return D::matches(s);
+        else return true;
+    }
+};
+
+}  // namespace coopk
+
+template <class D>
+CoopKernelSet make_coop_kernelset(const char* name) {
+    CoopKernelSet k;
+    k.name = name;
+    k.specialized = D::kStatic ? 1 : 0;
+    k.matches = &coopk::Launch<D>::matches;
+    k.step = &coopk::Launch<D>::step;
+    k.p2 = &coopk::Launch<D>::p2;
+    k.lin = &coopk::Launch<D>::lin;
+    k.info = &coopk::Launch<D>::info;
+    return k;
+}
+
+}  // namespace trepb

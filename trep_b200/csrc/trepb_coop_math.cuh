@@ -21,13 +21,19 @@
 //                 d2p/dq_i dq_j = a_up x dp/dq_lo
 //   linear algebra  right-looking LU with the reference's implicit-scaling pivot rule
 //                 (math-code.c:337-432), lanes over columns; right-hand sides ride along as extra
-//                 columns or are solved one column per lane.
+//                 columns or are solved one column per lane (in registers when the sizes are
+//                 compile-time constants).
+//
+// Two flavours from one source: D = RtDims (sizes read from the tables at run time: any system) and
+// D = CtDims<...> (sizes are template constants: loops unroll, workspace offsets fold to immediates,
+// the right-hand-side columns live in registers).  The link tables themselves are always run-time
+// data, so one CtDims instantiation serves every system of that shape.
 //
 // Nothing here is a transcription of frame.c: there are no per-frame derivative caches at all.
 #pragma once
 #include <math.h>
 #include "trepb_coop_sys.h"
-#include "trepb_math.cuh"   // cross3 / dot3 / Deriv1Out / Status
+#include "trepb_math.cuh"   // cross3 / dot3 / inertia_apply / Deriv1Out / Status
 
 namespace trepb {
 
@@ -36,14 +42,15 @@ namespace trepb {
 // ---------------------------------------------------------------------------------------------
 struct HostTeam {
     static constexpr int kSize = 1;
+    static constexpr bool kWarp = false;
     TREPB_HD int lane() const { return 0; }
     TREPB_HD void sync() const {}
     TREPB_HD void argmax(double&, int&) const {}
-    TREPB_HD bool any(bool p) const { return p; }
 };
 #if defined(__CUDACC__)
 struct WarpTeam {
     static constexpr int kSize = 32;
+    static constexpr bool kWarp = true;
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     // largest value wins, ties go to the lowest index; every lane gets the result
@@ -55,13 +62,18 @@ struct WarpTeam {
             if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
         }
     }
-    __device__ __forceinline__ bool any(bool p) const { return __any_sync(0xffffffffu, p) != 0; }
 };
 #endif
 
 // ---------------------------------------------------------------------------------------------
-// workspace layout (offsets in doubles from the instance's base)
+// sizes: run-time or compile-time
 // ---------------------------------------------------------------------------------------------
+struct RtDims {
+    static constexpr bool kStatic = false;
+    static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1;
+};
+
+// workspace layout (offsets in doubles from the instance's base)
 struct CoopLayout {
     int nls, ldf, ldm, ldp, ldy;
     int q1, q2, qe, dq, p1, p2, u1, lam;
@@ -75,35 +87,50 @@ struct CoopLayout {
     int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc]  (int32)
     int total;
 
-    TREPB_HD static int odd(int n) { return n | 1; }
-    TREPB_HD void set(const CoopSys& s) {
-        const int nq = s.nq, nd = s.nd, nc = s.nc, nu = s.nu, nr = nd + nc;
-        nls = s.nl;
-        ldf = odd(nr + 1);
-        ldm = odd(nd + nc);
-        ldp = odd(nc > 0 ? nc : 1);
-        ldy = nq + nu;
+    TREPB_HD static constexpr int odd(int n) { return n | 1; }
+    TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs) {
+        CoopLayout L{};
+        const int nq = nd + nk, nr = nd + nc;
+        L.nls = nl;
+        L.ldf = odd(nr + 1);
+        L.ldm = odd(nd + nc);
+        L.ldp = odd(nc > 0 ? nc : 1);
+        L.ldy = nq + nu;
         int o = 0;
-        auto take = [&](int n) { int r = o; o += n; return r; };
-        q1 = take(nq); q2 = take(nq); qe = take(nq); dq = take(nq);
-        p1 = take(nd); p2 = take(nd); u1 = take(nu); lam = take(nc);
+        L.q1 = o; o += nq; L.q2 = o; o += nq; L.qe = o; o += nq; L.dq = o; o += nq;
+        L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc;
         const int link0 = o;
-        cs = take(2 * nls); R = take(9 * nls); p = take(3 * nls); V = take(6 * nls); comp = take(16 * nls);
-        pts = take(3 * s.np);
-        const int need = nd * ldm + nd * nd;
+        L.cs = o; o += 2 * nl; L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
+        L.comp = o; o += 16 * nl; L.pts = o; o += 3 * np;
+        const int need = nd * L.ldm + nd * nd;
         if (o - link0 < need) o = link0 + need;
-        M2 = link0; T22 = link0 + nd * ldm;
-        Lq = take(nq); Lv = take(nq);
-        VV = take(s.npairs); QQ = take(s.npairs); UP = take(s.npairs); DN = take(s.npairs);
-        Dh1 = take(nc * nd); Dh2 = take(nc * nq); hc = take(nc);
-        const int nN = nr * ldf, nY = nd * ldy;
-        N = take(nN > nY ? nN : nY);
-        Z = take(nc * ldy); PJ = take(nc * ldp);
-        fr = take(nr); scl = take(nr); rdM = take(nr); rdP = take(nc);
-        ints = take((2 * nr + 2 * nc + 1) / 2 + 1);
-        total = (o + 1) & ~1;
+        L.M2 = link0; L.T22 = link0 + nd * L.ldm;
+        L.Lq = o; o += nq; L.Lv = o; o += nq;
+        L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += npairs; L.DN = o; o += npairs;
+        L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
+        const int nN = nr * L.ldf, nY = nd * L.ldy;
+        L.N = o; o += nN > nY ? nN : nY;
+        L.Z = o; o += nc * L.ldy; L.PJ = o; o += nc * L.ldp;
+        L.fr = o; o += nr; L.scl = o; o += nr; L.rdM = o; o += nr; L.rdP = o; o += nc;
+        L.ints = o; o += (2 * nr + 2 * nc + 1) / 2 + 1;
+        L.total = (o + 1) & ~1;
+        return L;
+    }
+    TREPB_HD void set(const CoopSys& s) { *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs); }
+};
+
+template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_>
+struct CtDims {
+    static constexpr bool kStatic = true;
+    static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_;
+    TREPB_HD static constexpr CoopLayout layout() { return CoopLayout::make(ND, NK, NU, NC, NL, NP, NPAIRS); }
+    TREPB_HD static bool matches(const CoopSys& s) {
+        return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
+               s.nlevels == NLEVELS;
     }
 };
+
+TREPB_HD double sel3(const double* v, int k) { return k == 0 ? v[0] : (k == 1 ? v[1] : v[2]); }
 
 // ---------------------------------------------------------------------------------------------
 // cooperative dense helpers
@@ -111,9 +138,12 @@ struct CoopLayout {
 // In-place LU of the leading n x n block of A (row-major, leading dimension ld) with the
 // reference's pivot rule (math-code.c:337-432: implicit row scaling, first strict maximum, whole
 // row swap, scales[pivot] = scales[j]); the same row operations are applied to nx extra columns
-// (right-hand sides), which therefore leave forward-eliminated.  piv[] is the composed permutation
-// of LU_decomp (x[i] = b[piv[i]]), swp[k] the row exchanged with k at step k, rd[k] = 1/U(k,k).
-// Returns false when the scaled pivot is <= tol (the reference's "singular" ValueError).
+// (right-hand sides), which therefore leave forward-eliminated.
+// Storage on return: U on and above the diagonal, rd[k] = 1/U(k,k), and BELOW the diagonal the
+// unscaled multipliers m(i,k) = L(i,k) U(k,k)  (the update uses m(i,k) * (rd[k] a(k,j)), one
+// multiplication per column instead of a division per element and no separate scaling phase).
+// piv[] is the composed permutation of LU_decomp (x[i] = b[piv[i]]), swp[k] the row exchanged with k
+// at step k.  Returns false when the scaled pivot is <= tol (the reference's "singular" ValueError).
 template <class Team>
 TREPB_HD bool team_lu(const Team& t, double* A, int ld, int n, int nx, int* piv, int* swp, double* scl,
                       double* rd, double tol) {
@@ -131,11 +161,30 @@ TREPB_HD bool team_lu(const Team& t, double* A, int ld, int n, int nx, int* piv,
     for (int k = 0; k < n; ++k) {
         double best = -1.0;
         int bi = k;
-        for (int i = k + lane; i < n; i += Team::kSize) {
-            const double v = fabs(A[i * ld + k] * scl[i]);
-            if (v > best) { best = v; bi = i; }
+#if defined(__CUDA_ARCH__)
+        if (Team::kWarp && n - k <= 32) {
+            // one candidate per lane; two 32-bit max-reductions over the bit pattern of |a| * scale
+            // (non-negative doubles order like unsigned integers), lowest lane among the maxima wins
+            const int i = k + lane;
+            const bool act = i < n;
+            double v = act ? fabs(A[i * ld + k] * scl[i]) : 0.0;
+            if (!(v == v)) v = 0.0;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+            const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+            const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+            const unsigned cand = __ballot_sync(0xffffffffu, act && hi == mh && lo == ml);
+            bi = k + __ffs(cand) - 1;
+            best = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+        } else
+#endif
+        {
+            for (int i = k + lane; i < n; i += Team::kSize) {
+                const double v = fabs(A[i * ld + k] * scl[i]);
+                if (v > best) { best = v; bi = i; }
+            }
+            t.argmax(best, bi);
         }
-        t.argmax(best, bi);
         if (!(best > tol)) return false;
         t.sync();   // every lane has read scl / column k before rows move
         if (bi != k) {
@@ -153,13 +202,24 @@ TREPB_HD bool team_lu(const Team& t, double* A, int ld, int n, int nx, int* piv,
         }
         if (lane == 0) swp[k] = bi;
         t.sync();
-        const double d = A[k * ld + k];
-        for (int i = k + 1 + lane; i < n; i += Team::kSize) A[i * ld + k] /= d;
-        if (lane == 0) rd[k] = 1.0 / d;
-        t.sync();
+        const double rdk = 1.0 / A[k * ld + k];
+        if (lane == 0) rd[k] = rdk;
         for (int j = k + 1 + lane; j < n + nx; j += Team::kSize) {
-            const double akj = A[k * ld + j];
-            for (int i = k + 1; i < n; ++i) A[i * ld + j] -= A[i * ld + k] * akj;
+            const double akj = A[k * ld + j] * rdk;
+            const double* mk = A + (k + 1) * ld + k;
+            double* aj = A + (k + 1) * ld + j;
+            const int cnt = n - k - 1;
+            for (int i = 0; i < cnt; i += 4) {
+                // four rows at a time; the tail rows are predicated, not looped
+                const bool g1 = i + 1 < cnt, g2 = i + 2 < cnt, g3 = i + 3 < cnt;
+                const double m0 = mk[0], m1 = g1 ? mk[ld] : 0.0, m2 = g2 ? mk[2 * ld] : 0.0, m3 = g3 ? mk[3 * ld] : 0.0;
+                const double a0 = aj[0], a1 = g1 ? aj[ld] : 0.0, a2 = g2 ? aj[2 * ld] : 0.0, a3 = g3 ? aj[3 * ld] : 0.0;
+                aj[0] = a0 - m0 * akj;
+                if (g1) aj[ld] = a1 - m1 * akj;
+                if (g2) aj[2 * ld] = a2 - m2 * akj;
+                if (g3) aj[3 * ld] = a3 - m3 * akj;
+                mk += 4 * ld; aj += 4 * ld;
+            }
         }
         t.sync();
     }
@@ -186,7 +246,7 @@ TREPB_HD void col_backsolve(const double* A, int ld, int n, const double* rd, do
         y[i * ldy] = v * rd[i];
     }
 }
-// One column per lane: y <- (LU)^-1 P y
+// One column per lane: y <- (LU)^-1 P y  with team_lu's storage (unscaled multipliers)
 TREPB_HD void col_solve(const double* A, int ld, int n, const int* swp, const double* rd, double* y, int ldy) {
     for (int k = 0; k < n; ++k) {
         const int p = swp[k];
@@ -196,34 +256,91 @@ TREPB_HD void col_solve(const double* A, int ld, int n, const int* swp, const do
             y[p * ldy] = a;
         }
     }
-    for (int i = 1; i < n; ++i) {
+    // forward: yt_i = (b_i - sum_{j<i} m_ij yt_j) rd_i ; backward: x_i = yt_i - rd_i sum_{j>i} U_ij x_j
+    for (int i = 0; i < n; ++i) {
         double v = y[i * ldy];
         for (int j = 0; j < i; ++j) v -= A[i * ld + j] * y[j * ldy];
-        y[i * ldy] = v;
+        y[i * ldy] = v * rd[i];
     }
-    col_backsolve(A, ld, n, rd, y, ldy);
+    for (int i = n - 2; i >= 0; --i) {
+        double v = 0.0;
+        for (int j = i + 1; j < n; ++j) v += A[i * ld + j] * y[j * ldy];
+        y[i * ldy] -= rd[i] * v;
+    }
+}
+// the same on a register-resident column (N compile-time): y[] indices are constants after
+// unrolling.  Rows are processed four at a time so that four independent accumulation chains are
+// in flight (a single chain of dependent FMAs leaves the FP64 pipe idle most of the time).
+template <int N, int I0>
+TREPB_HD void reg_fwd(const double* A, int ld, const double* rd, double* y) {
+    if constexpr (I0 < N) {
+        constexpr int R = N - I0 < 4 ? N - I0 : 4;
+        double v[R];
+        TREPB_UNROLL for (int r = 0; r < R; ++r) v[r] = y[I0 + r];
+        TREPB_UNROLL
+        for (int j = 0; j < I0; ++j) {
+            TREPB_UNROLL for (int r = 0; r < R; ++r) v[r] -= A[(I0 + r) * ld + j] * y[j];
+        }
+        TREPB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            TREPB_UNROLL for (int q = 0; q < r; ++q) v[r] -= A[(I0 + r) * ld + I0 + q] * y[I0 + q];
+            y[I0 + r] = v[r] * rd[I0 + r];
+        }
+        reg_fwd<N, I0 + R>(A, ld, rd, y);
+    }
+}
+template <int N, int I1>
+TREPB_HD void reg_bwd(const double* A, int ld, const double* rd, double* y) {
+    if constexpr (I1 > 0) {
+        constexpr int R = I1 < 4 ? I1 : 4;      // rows I1-R .. I1-1
+        double v[R];
+        TREPB_UNROLL for (int r = 0; r < R; ++r) v[r] = 0.0;
+        TREPB_UNROLL
+        for (int j = I1; j < N; ++j) {
+            TREPB_UNROLL for (int r = 0; r < R; ++r) v[r] += A[(I1 - 1 - r) * ld + j] * y[j];
+        }
+        TREPB_UNROLL
+        for (int r = 0; r < R; ++r) {
+            TREPB_UNROLL for (int q = 0; q < r; ++q) v[r] += A[(I1 - 1 - r) * ld + I1 - 1 - q] * y[I1 - 1 - q];
+            y[I1 - 1 - r] -= rd[I1 - 1 - r] * v[r];
+        }
+        reg_bwd<N, I1 - R>(A, ld, rd, y);
+    }
+}
+// forward: yt_i = (b_i - sum_{j<i} m_ij yt_j) rd_i ; backward: x_i = yt_i - rd_i sum_{j>i} U_ij x_j
+template <int N>
+TREPB_HD void reg_solve(const double* A, int ld, const double* rd, double* y) {
+    reg_fwd<N, 0>(A, ld, rd, y);
+    reg_bwd<N, N>(A, ld, rd, y);
 }
 
 // ---------------------------------------------------------------------------------------------
 // the per-instance context
 // ---------------------------------------------------------------------------------------------
-template <class Team>
+template <class Team, class D = RtDims>
 struct Coop {
     const CoopSys& S;
-    const CoopLayout& L;
+    const CoopLayout L;
     double* w;      // workspace base of this instance
     Team t;
 
     TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team) : S(s), L(l), w(base), t(team) {}
 
+#define TREPB_DIM(fn, CT, rt) \
+    TREPB_HD int fn() const { if constexpr (D::kStatic) return D::CT; else return S.rt; }
+    TREPB_DIM(ND, ND, nd) TREPB_DIM(NK, NK, nk) TREPB_DIM(NU, NU, nu) TREPB_DIM(NC, NC, nc)
+    TREPB_DIM(NL, NL, nl) TREPB_DIM(NP, NP, np) TREPB_DIM(NPAIRS, NPAIRS, npairs) TREPB_DIM(NLEVELS, NLEVELS, nlevels)
+#undef TREPB_DIM
+    TREPB_HD int NQ() const { return ND() + NK(); }
+
     TREPB_HD int* ipivM() const { return (int*)(w + L.ints); }
-    TREPB_HD int* iswpM() const { return ipivM() + (S.nd + S.nc); }
-    TREPB_HD int* ipivP() const { return iswpM() + (S.nd + S.nc); }
-    TREPB_HD int* iswpP() const { return ipivP() + S.nc; }
+    TREPB_HD int* iswpM() const { return ipivM() + (ND() + NC()); }
+    TREPB_HD int* ipivP() const { return iswpM() + (ND() + NC()); }
+    TREPB_HD int* iswpP() const { return ipivP() + NC(); }
 
     // ---- evaluation point: which = 0 midpoint, 1 q1, 2 q2 (midpointvi.c:401-457)
     TREPB_HD void set_point(int which, double dt) {
-        for (int i = t.lane(); i < S.nq; i += Team::kSize) {
+        for (int i = t.lane(); i < NQ(); i += Team::kSize) {
             const double a = w[L.q1 + i], b = w[L.q2 + i];
             w[L.qe + i] = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
             w[L.dq + i] = (b - a) / dt;
@@ -231,78 +348,18 @@ struct Coop {
         t.sync();
     }
 
-    // ---- pose sweep.  vel: links that carry mass, also V.  !vel: links that carry points.
-    TREPB_HD void pose_sweep(bool vel) {
-        const int nls = L.nls, lane = t.lane();
-        double* cs = w + L.cs; double* R = w + L.R; double* p = w + L.p; double* V = w + L.V;
-        for (int l = lane; l < S.nl; l += Team::kSize) {
-            if (!(vel ? S.dyn(l) : S.wrl(l)) || !S.rot(l)) continue;
-            double sn, c;
-            sincos_(w[L.qe + S.l_cfg()[l]], &sn, &c);
-            cs[l] = c;
-            cs[nls + l] = sn;
-        }
-        t.sync();
-        for (int lev = 0; lev < S.nlevels; ++lev) {
-            for (int l = S.lvl_off()[lev] + lane; l < S.lvl_off()[lev + 1]; l += Team::kSize) {
-                if (!(vel ? S.dyn(l) : S.wrl(l))) continue;
-                const int par = S.l_par()[l], a = S.axis(l), b = (a + 1) % 3, c = (a + 2) % 3;
-                const int cfg = S.l_cfg()[l];
-                double Rb[9], pb[3];
-                if (par < 0) {
-                    if (S.has_xc(l)) {
-                        for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
-                        for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
-                    } else {
-                        for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
-                        pb[0] = pb[1] = pb[2] = 0.0;
-                    }
-                } else {
-                    double Rp[9], pp[3];
-                    for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
-                    for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
-                    if (S.has_xc(l)) {
-                        const double* Rc = S.l_Rc() + 9 * l;
-                        const double* pc = S.l_pc() + 3 * l;
-                        for (int r = 0; r < 3; ++r) {
-                            for (int q = 0; q < 3; ++q)
-                                Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
-                            pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
-                        }
-                    } else {
-                        for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
-                        for (int k = 0; k < 3; ++k) pb[k] = pp[k];
-                    }
-                }
-                const double x = w[L.qe + cfg];
-                if (S.rot(l)) {
-                    const double c_ = cs[l], s_ = cs[nls + l];
-                    for (int r = 0; r < 3; ++r) {
-                        const double rb = Rb[r * 3 + b], rc = Rb[r * 3 + c];
-                        Rb[r * 3 + b] = c_ * rb + s_ * rc;
-                        Rb[r * 3 + c] = -s_ * rb + c_ * rc;
-                    }
-                } else {
-                    for (int r = 0; r < 3; ++r) pb[r] += x * Rb[r * 3 + a];
-                }
-                for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
-                for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
-                if (vel) {
-                    double s6[6], Vp[6];
-                    twist(Rb, pb, a, S.rot(l), s6);
-                    if (par < 0) { for (int k = 0; k < 6; ++k) Vp[k] = 0.0; }
-                    else { for (int k = 0; k < 6; ++k) Vp[k] = V[k * nls + par]; }
-                    const double d = w[L.dq + cfg];
-                    for (int k = 0; k < 6; ++k) V[k * nls + l] = Vp[k] + s6[k] * d;
-                }
-            }
-            t.sync();
+    template <int A_>
+    TREPB_HD static void rot_cols(double* Rb, double c_, double s_) {
+        constexpr int b = (A_ + 1) % 3, c = (A_ + 2) % 3;
+        TREPB_UNROLL
+        for (int r = 0; r < 3; ++r) {
+            const double rb = Rb[r * 3 + b], rc = Rb[r * 3 + c];
+            Rb[r * 3 + b] = c_ * rb + s_ * rc;
+            Rb[r * 3 + c] = -s_ * rb + c_ * rc;
         }
     }
-
-    // joint twist (v_O, w) in world coordinates about the world origin
-    TREPB_HD static void twist(const double* Rl, const double* pl, int a, bool rot, double* s6) {
-        const double aw[3] = {Rl[a], Rl[3 + a], Rl[6 + a]};
+    // joint twist (v_O, w) in world coordinates about the world origin, axis aw through pl
+    TREPB_HD static void twist(const double* aw, const double* pl, bool rot, double* s6) {
         if (rot) {
             cross3(pl, aw, s6);
             s6[3] = aw[0]; s6[4] = aw[1]; s6[5] = aw[2];
@@ -319,17 +376,91 @@ struct Coop {
         o[0] = a[0] + b[0]; o[1] = a[1] + b[1]; o[2] = a[2] + b[2];
         cross3(X + 3, Y + 3, o + 3);
     }
+
+    // ---- pose sweep.  vel: links that carry mass, also V.  !vel: links that carry points.
+    TREPB_HD void pose_sweep(bool vel) {
+        const int nls = L.nls, lane = t.lane();
+        double* cs = w + L.cs; double* R = w + L.R; double* p = w + L.p; double* V = w + L.V;
+        const int flag = vel ? 16 : 32;
+        for (int l = lane; l < NL(); l += Team::kSize) {
+            const int kind = S.l_kind()[l];
+            if ((kind & flag) == 0 || (kind & 4) == 0) continue;
+            double sn, c;
+            sincos_(w[L.qe + S.l_cfg()[l]], &sn, &c);
+            cs[l] = c;
+            cs[nls + l] = sn;
+        }
+        t.sync();
+        for (int lev = 0; lev < NLEVELS(); ++lev) {
+            const int l1 = S.lvl_off()[lev + 1];
+            for (int l = S.lvl_off()[lev] + lane; l < l1; l += Team::kSize) {
+                const int kind = S.l_kind()[l];
+                if ((kind & flag) == 0) continue;
+                const int par = S.l_par()[l], a = kind & 3, cfg = S.l_cfg()[l];
+                const bool rot = (kind & 4) != 0, xc = (kind & 8) != 0;
+                double Rb[9], pb[3];
+                if (par < 0) {
+                    if (xc) {
+                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
+                    } else {
+                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                        pb[0] = pb[1] = pb[2] = 0.0;
+                    }
+                } else {
+                    double Rp[9], pp[3];
+                    TREPB_UNROLL for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
+                    if (xc) {
+                        const double* Rc = S.l_Rc() + 9 * l;
+                        const double* pc = S.l_pc() + 3 * l;
+                        TREPB_UNROLL
+                        for (int r = 0; r < 3; ++r) {
+                            TREPB_UNROLL
+                            for (int q = 0; q < 3; ++q)
+                                Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
+                            pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
+                        }
+                    } else {
+                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = pp[k];
+                    }
+                }
+                if (rot) {
+                    const double c_ = cs[l], s_ = cs[nls + l];
+                    if (a == 0) rot_cols<0>(Rb, c_, s_);
+                    else if (a == 1) rot_cols<1>(Rb, c_, s_);
+                    else rot_cols<2>(Rb, c_, s_);
+                }
+                double aw[3];
+                TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = sel3(Rb + 3 * r, a);
+                if (!rot) {
+                    const double x = w[L.qe + cfg];
+                    TREPB_UNROLL for (int r = 0; r < 3; ++r) pb[r] += x * aw[r];
+                }
+                TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
+                if (vel) {
+                    double s6[6];
+                    twist(aw, pb, rot, s6);
+                    const double d = w[L.dq + cfg];
+                    if (par < 0) { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = s6[k] * d; }
+                    else { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = V[k * nls + par] + s6[k] * d; }
+                }
+            }
+            t.sync();
+        }
+    }
+
     TREPB_HD void load_link_twists(int l, double* s6, double* W6, double* aw) const {
-        const int nls = L.nls, a = S.axis(l), par = S.l_par()[l];
-        double Rl[9], pl[3];
-        // only column a of R is needed
-        for (int r = 0; r < 3; ++r) { Rl[r * 3 + a] = w[L.R + (r * 3 + a) * nls + l]; pl[r] = w[L.p + r * nls + l]; }
-        twist(Rl, pl, a, S.rot(l), s6);
-        aw[0] = Rl[a]; aw[1] = Rl[3 + a]; aw[2] = Rl[6 + a];
-        if (par < 0) { for (int k = 0; k < 6; ++k) W6[k] = 0.0; }
+        const int nls = L.nls, kind = S.l_kind()[l], a = kind & 3, par = S.l_par()[l];
+        double pl[3];
+        TREPB_UNROLL for (int r = 0; r < 3; ++r) { aw[r] = w[L.R + (r * 3 + a) * nls + l]; pl[r] = w[L.p + r * nls + l]; }
+        twist(aw, pl, (kind & 4) != 0, s6);
+        if (par < 0) { TREPB_UNROLL for (int k = 0; k < 6; ++k) W6[k] = 0.0; }
         else {
             double Vp[6];
-            for (int k = 0; k < 6; ++k) Vp[k] = w[L.V + k * nls + par];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) Vp[k] = w[L.V + k * nls + par];
             bracket(Vp, s6, W6);
         }
     }
@@ -339,16 +470,17 @@ struct Coop {
     TREPB_HD void dyn_first() {
         const int nls = L.nls, lane = t.lane();
         double* comp = w + L.comp;
-        for (int i = lane; i < S.nq; i += Team::kSize) { w[L.Lq + i] = 0.0; w[L.Lv + i] = 0.0; }
-        for (int l = lane; l < S.nl; l += Team::kSize) {
+        for (int i = lane; i < NQ(); i += Team::kSize) { w[L.Lq + i] = 0.0; w[L.Lv + i] = 0.0; }
+        for (int l = lane; l < NL(); l += Team::kSize) {
             if (!S.dyn(l)) continue;
             double Rl[9], pl[3], Vl[6];
-            for (int k = 0; k < 9; ++k) Rl[k] = w[L.R + k * nls + l];
-            for (int k = 0; k < 3; ++k) pl[k] = w[L.p + k * nls + l];
-            for (int k = 0; k < 6; ++k) Vl[k] = w[L.V + k * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rl[k] = w[L.R + k * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) pl[k] = w[L.p + k * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) Vl[k] = w[L.V + k * nls + l];
             const double* in = S.l_in() + 10 * l;
             const double m = in[0];
             double hr[3], hw[3], I[6];
+            TREPB_UNROLL
             for (int r = 0; r < 3; ++r) {
                 hr[r] = Rl[r * 3] * in[1] + Rl[r * 3 + 1] * in[2] + Rl[r * 3 + 2] * in[3];
                 hw[r] = hr[r] + m * pl[r];
@@ -358,11 +490,15 @@ struct Coop {
                 double M[9], T[9];
                 M[0] = in[4]; M[4] = in[5]; M[8] = in[6];
                 M[1] = M[3] = in[7]; M[2] = M[6] = in[8]; M[5] = M[7] = in[9];
+                TREPB_UNROLL
                 for (int r = 0; r < 3; ++r)
+                    TREPB_UNROLL
                     for (int c = 0; c < 3; ++c)
                         T[r * 3 + c] = Rl[r * 3] * M[c] + Rl[r * 3 + 1] * M[3 + c] + Rl[r * 3 + 2] * M[6 + c];
                 const double hp = dot3(hr, pl), pp = dot3(pl, pl);
+                TREPB_UNROLL
                 for (int r = 0; r < 3; ++r)
+                    TREPB_UNROLL
                     for (int c = r; c < 3; ++c) {
                         double v = T[r * 3] * Rl[c * 3] + T[r * 3 + 1] * Rl[c * 3 + 1] + T[r * 3 + 2] * Rl[c * 3 + 2];
                         v += -hr[r] * pl[c] - pl[r] * hr[c] - m * pl[r] * pl[c];
@@ -373,16 +509,16 @@ struct Coop {
             double mu[6];
             inertia_apply(m, hw, I, Vl, mu);
             comp[0 * nls + l] = m;
-            for (int k = 0; k < 3; ++k) comp[(1 + k) * nls + l] = hw[k];
-            for (int k = 0; k < 6; ++k) comp[(4 + k) * nls + l] = I[k];
-            for (int k = 0; k < 6; ++k) comp[(10 + k) * nls + l] = mu[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) comp[(1 + k) * nls + l] = hw[k];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) comp[(4 + k) * nls + l] = I[k];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) comp[(10 + k) * nls + l] = mu[k];
         }
         t.sync();
         // up sweep: a parent gathers its children (plain sums in world coordinates)
-        for (int lev = S.nlevels - 1; lev >= 1; --lev) {
+        for (int lev = NLEVELS() - 1; lev >= 1; --lev) {
             const int lo = S.lvl_off()[lev - 1], cnt = S.lvl_off()[lev] - lo;
             for (int e = lane; e < cnt * 16; e += Team::kSize) {
-                const int l = lo + e / 16, k = e % 16;
+                const int l = lo + (e >> 4), k = e & 15;
                 if (!S.dyn(l)) continue;
                 const int c0 = S.l_child0()[l], nch = S.l_nchild()[l];
                 double acc = comp[k * nls + l];
@@ -392,27 +528,27 @@ struct Coop {
             }
             t.sync();
         }
-        for (int l = lane; l < S.nl; l += Team::kSize) {
+        for (int l = lane; l < NL(); l += Team::kSize) {
             if (!S.dyn(l)) continue;
             double s6[6], W6[6], aw[3], mu[6], h[3];
             load_link_twists(l, s6, W6, aw);
             const double m = comp[l];
-            for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
-            for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
             const int cfg = S.l_cfg()[l];
             w[L.Lv + cfg] = dot6(s6, mu);
             double lq = dot6(W6, mu);
             if (S.has_gravity) {
                 double P[3], t3[3];
                 cross3(s6 + 3, h, t3);
-                for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
                 lq += dot3(S.grav, P);
             }
             w[L.Lq + cfg] = lq;
         }
         t.sync();
         // ConfigSpring (configspring.c:22-30)
-        for (int i = lane; i < S.nq; i += Team::kSize)
+        for (int i = lane; i < NQ(); i += Team::kSize)
             if (S.ks()[i] != 0.0) w[L.Lq + i] -= S.ks()[i] * w[L.qe + i] - S.kq0()[i];
         t.sync();
     }
@@ -421,40 +557,40 @@ struct Coop {
     TREPB_HD void dyn_second() {
         const int nls = L.nls, lane = t.lane();
         double* comp = w + L.comp;
-        for (int l = lane; l < S.nl; l += Team::kSize) {
+        for (int l = lane; l < NL(); l += Team::kSize) {
             if (!S.dyn(l)) continue;
             double s6[6], W6[6], aw[3], mu[6], h[3], I[6], H[6], G[6], P[3], t3[3];
             load_link_twists(l, s6, W6, aw);
             const double m = comp[l];
-            for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
-            for (int k = 0; k < 6; ++k) I[k] = comp[(4 + k) * nls + l];
-            for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) h[k] = comp[(1 + k) * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) I[k] = comp[(4 + k) * nls + l];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) mu[k] = comp[(10 + k) * nls + l];
             inertia_apply(m, h, I, s6, H);
             inertia_apply(m, h, I, W6, G);
             // G -= ad*_s mu = (f x w_s , n x w_s + f x v_s)
             cross3(mu, s6 + 3, t3);
-            for (int k = 0; k < 3; ++k) G[k] -= t3[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) G[k] -= t3[k];
             cross3(mu + 3, s6 + 3, t3);
-            for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
             cross3(mu, s6, t3);
-            for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) G[3 + k] -= t3[k];
             cross3(s6 + 3, h, t3);
-            for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
-            for (int k = 0; k < 6; ++k) comp[k * nls + l] = H[k];
-            for (int k = 0; k < 6; ++k) comp[(6 + k) * nls + l] = G[k];
-            for (int k = 0; k < 3; ++k) comp[(12 + k) * nls + l] = P[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) P[k] = m * s6[k] + t3[k];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) comp[k * nls + l] = H[k];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) comp[(6 + k) * nls + l] = G[k];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) comp[(12 + k) * nls + l] = P[k];
         }
         t.sync();
-        for (int e = lane; e < S.npairs; e += Team::kSize) {
+        for (int e = lane; e < NPAIRS(); e += Team::kSize) {
             const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
             double s6[6], W6[6], aw[3], H[6], G[6];
             load_link_twists(i, s6, W6, aw);
-            for (int k = 0; k < 6; ++k) { H[k] = comp[k * nls + j]; G[k] = comp[(6 + k) * nls + j]; }
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) { H[k] = comp[k * nls + j]; G[k] = comp[(6 + k) * nls + j]; }
             const double sG = dot6(s6, G);
             double WG = dot6(W6, G);
             if (S.has_gravity && S.rot(i)) {
                 double P[3], N[3];
-                for (int k = 0; k < 3; ++k) P[k] = comp[(12 + k) * nls + j];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) P[k] = comp[(12 + k) * nls + j];
                 cross3(P, S.grav, N);
                 WG += dot3(aw, N);
             }
@@ -469,7 +605,7 @@ struct Coop {
     // table terms for the config pair (a, b):  qq = L_dqdq(a,b), vv = L_ddqddq(a,b),
     // vab = L_ddqdq(a,b), vba = L_ddqdq(b,a)   (first index of L_ddqdq is the velocity slot)
     TREPB_HD void tab(int a, int b, double& qq, double& vv, double& vab, double& vba) const {
-        const int m = S.pm()[a * S.nq + b];
+        const int m = S.pm()[a * NQ() + b];
         if (m > 0) {
             qq = w[L.QQ + m - 1]; vv = w[L.VV + m - 1]; vab = w[L.UP + m - 1]; vba = w[L.DN + m - 1];
         } else if (m < 0) {
@@ -482,21 +618,22 @@ struct Coop {
 
     // ---- world points of the constraints at the current pose
     TREPB_HD void points() {
-        const int nls = L.nls;
-        for (int q = t.lane(); q < S.np; q += Team::kSize) {
+        const int nls = L.nls, np = NP();
+        for (int q = t.lane(); q < np; q += Team::kSize) {
             const int l = S.pt_link()[q];
             const double* r = S.pt_r() + 3 * q;
+            TREPB_UNROLL
             for (int k = 0; k < 3; ++k) {
                 double v = r[k];
                 if (l >= 0)
                     v = w[L.p + k * nls + l] + (w[L.R + (k * 3) * nls + l] * r[0] + w[L.R + (k * 3 + 1) * nls + l] * r[1] +
                                                 w[L.R + (k * 3 + 2) * nls + l] * r[2]);
-                w[L.pts + k * S.np + q] = v;
+                w[L.pts + k * np + q] = v;
             }
         }
         t.sync();
     }
-    TREPB_HD void point(int q, double* o) const { for (int k = 0; k < 3; ++k) o[k] = w[L.pts + k * S.np + q]; }
+    TREPB_HD void point(int q, double* o) const { TREPB_UNROLL for (int k = 0; k < 3; ++k) o[k] = w[L.pts + k * NP() + q]; }
     TREPB_HD bool pdep(int q, int lj) const {
         const int l = S.pt_link()[q];
         return l >= 0 && lj >= 0 && ((S.l_anc()[l] >> lj) & 1ull) != 0;
@@ -505,107 +642,132 @@ struct Coop {
     TREPB_HD void dpoint(int q, int lj, double* o) const {
         o[0] = o[1] = o[2] = 0.0;
         if (!pdep(q, lj)) return;
-        const int nls = L.nls, a = S.axis(lj);
+        const int nls = L.nls, kind = S.l_kind()[lj], a = kind & 3;
         const double aw[3] = {w[L.R + a * nls + lj], w[L.R + (3 + a) * nls + lj], w[L.R + (6 + a) * nls + lj]};
-        if (S.rot(lj)) {
+        if (kind & 4) {
             double r[3];
-            for (int k = 0; k < 3; ++k) r[k] = w[L.pts + k * S.np + q] - w[L.p + k * nls + lj];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) r[k] = w[L.pts + k * NP() + q] - w[L.p + k * nls + lj];
             cross3(aw, r, o);
         } else {
             o[0] = aw[0]; o[1] = aw[1]; o[2] = aw[2];
         }
     }
-    TREPB_HD void ddpoint(int q, int li, int lj, double* o) const {
-        o[0] = o[1] = o[2] = 0.0;
-        if (!pdep(q, li) || !pdep(q, lj)) return;
-        int up = li, lo = lj;
-        if (!((S.l_anc()[lj] >> li) & 1ull)) { up = lj; lo = li; }
-        if (!S.rot(up)) return;
-        const int nls = L.nls, a = S.axis(up);
-        const double aw[3] = {w[L.R + a * nls + up], w[L.R + (3 + a) * nls + up], w[L.R + (6 + a) * nls + up]};
-        double d[3];
-        dpoint(q, lo, d);
-        cross3(aw, d, o);
-    }
 
     // ---- constraints at the current pose (distance.c:16-100, point.c:16-46)
     //   want_h: hc ;  dh: 0 none, 1 -> Dh1 [nc][nd], 2 -> Dh2 [nc][nq]
     TREPB_HD void constraints(bool want_h, int dh) {
-        const int lane = t.lane(), nq = S.nq, nd = S.nd;
+        const int lane = t.lane(), nq = NQ(), nd = ND(), nc = NC();
         if (want_h) {
-            for (int c = lane; c < S.nc; c += Team::kSize) {
+            for (int c = lane; c < nc; c += Team::kSize) {
                 double pa[3], pb[3], v[3];
                 point(S.con_a()[c], pa); point(S.con_b()[c], pb);
-                for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
                 if (S.con_kind()[c] == C_DISTANCE) {
                     const int third = S.con_third()[c];
                     const double d = third >= 0 ? w[L.qe + third] : S.con_dist()[c];
                     w[L.hc + c] = dot3(v, v) - d * d;
                 } else {
-                    w[L.hc + c] = v[S.con_third()[c]];
+                    w[L.hc + c] = sel3(v, S.con_third()[c]);
                 }
             }
         }
         if (dh) {
             const int ncol = dh == 1 ? nd : nq;
-            double* D = w + (dh == 1 ? L.Dh1 : L.Dh2);
-            for (int e = lane; e < S.nc * ncol; e += Team::kSize) {
-                const int c = e / ncol, j = e % ncol;
+            double* Dm = w + (dh == 1 ? L.Dh1 : L.Dh2);
+            for (int e = lane; e < nc * ncol; e += Team::kSize) {
+                const int c = e / ncol, j = e - c * ncol;
                 double val = 0.0;
                 if ((S.con_dep()[c] >> j) & 1ull) {
                     const int A = S.con_a()[c], B = S.con_b()[c], lj = S.cfg_link()[j];
                     double da[3], db[3], dv[3];
                     dpoint(A, lj, da); dpoint(B, lj, db);
-                    for (int k = 0; k < 3; ++k) dv[k] = da[k] - db[k];
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) dv[k] = da[k] - db[k];
                     if (S.con_kind()[c] == C_DISTANCE) {
                         double pa[3], pb[3], v[3];
                         point(A, pa); point(B, pb);
-                        for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
                         const int third = S.con_third()[c];
                         val = dot3(v, dv);
                         if (third == j) val -= w[L.qe + third];
                         val *= 2.0;
                     } else {
-                        val = dv[S.con_third()[c]];
+                        val = sel3(dv, S.con_third()[c]);
                     }
                 }
-                D[e] = val;
+                Dm[e] = val;
             }
         }
         t.sync();
     }
 
-    // Y[j][i] = sum_c lam_c d2h_c/dq_i dq_j   for i < nq, j < nd   (midpointvi.c:864-889)
+    // Y[j][i] = sum_c lam_c d2h_c/dq_i dq_j   for i < nq, j < nd   (midpointvi.c:864-889).
+    // Per constraint: first dA_i, dB_i (the two end points' first derivatives) for the configs the
+    // constraint depends on, then the dependent (i, j) pairs only.  Scratch: the comp region.
     TREPB_HD void ddh_lambda(double* Y, int ldy) {
-        const int lane = t.lane(), nq = S.nq, nd = S.nd;
+        const int lane = t.lane(), nq = NQ(), nd = ND(), nls = L.nls;
         for (int e = lane; e < nd * nq; e += Team::kSize) {
-            const int j = e / nq, i = e % nq;
-            double acc = 0.0;
-            for (int c = 0; c < S.nc; ++c) {
-                const uint64_t dep = S.con_dep()[c];
-                if (!((dep >> i) & 1ull) || !((dep >> j) & 1ull)) continue;
-                const int A = S.con_a()[c], B = S.con_b()[c], li = S.cfg_link()[i], lj = S.cfg_link()[j];
-                double a3[3], b3[3], ddv[3];
-                ddpoint(A, li, lj, a3); ddpoint(B, li, lj, b3);
-                for (int k = 0; k < 3; ++k) ddv[k] = a3[k] - b3[k];
-                const double lam = w[L.lam + c];
-                if (S.con_kind()[c] == C_DISTANCE) {
-                    double pa[3], pb[3], v[3], di[3], dj[3];
-                    point(A, pa); point(B, pb);
-                    for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
-                    dpoint(A, li, a3); dpoint(B, li, b3);
-                    for (int k = 0; k < 3; ++k) di[k] = a3[k] - b3[k];
-                    dpoint(A, lj, a3); dpoint(B, lj, b3);
-                    for (int k = 0; k < 3; ++k) dj[k] = a3[k] - b3[k];
-                    double val = dot3(di, dj) + dot3(v, ddv);
-                    const int third = S.con_third()[c];
-                    if (third == i && third == j) val -= 1.0;
-                    acc += 2.0 * lam * val;
-                } else {
-                    acc += lam * ddv[S.con_third()[c]];
-                }
+            const int j = e / nq, i = e - j * nq;
+            Y[j * ldy + i] = 0.0;
+        }
+        double* DA = w + L.comp;
+        for (int c = 0; c < NC(); ++c) {
+            const int off = S.cd_off()[c], m = S.cd_off()[c + 1] - off, md = S.cd_nd()[c];
+            const int* list = S.cd_cfg() + off;
+            const int A = S.con_a()[c], B = S.con_b()[c];
+            double* DB = DA + 3 * m;
+            t.sync();
+            for (int a = lane; a < 2 * m; a += Team::kSize) {
+                const int which = a >= m, ai = which ? a - m : a;
+                double d3[3];
+                dpoint(which ? B : A, S.cfg_link()[list[ai]], d3);
+                double* dst = which ? DB : DA;
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) dst[k * m + ai] = d3[k];
             }
-            Y[j * ldy + i] = acc;
+            t.sync();
+            const bool dist = S.con_kind()[c] == C_DISTANCE;
+            const int third = S.con_third()[c];
+            const double lam = w[L.lam + c];
+            double v[3];
+            {
+                double pa[3], pb[3];
+                point(A, pa); point(B, pb);
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+            }
+            const int lA = S.pt_link()[A], lB = S.pt_link()[B];
+            const unsigned long long ancA = lA >= 0 ? S.l_anc()[lA] : 0ull, ancB = lB >= 0 ? S.l_anc()[lB] : 0ull;
+            for (int e = lane; e < m * md; e += Team::kSize) {
+                const int bj = e / m, ai = e - bj * m;     // j = list[bj] dynamic, i = list[ai]
+                const int i = list[ai], j = list[bj];
+                const int li = S.cfg_link()[i], lj = S.cfg_link()[j];
+                double ddv[3] = {0.0, 0.0, 0.0};
+                if (li >= 0 && lj >= 0) {
+                    // the upper joint's axis crosses the lower joint's first derivative
+                    int up = li, lo_idx = bj;
+                    if (!((S.l_anc()[lj] >> li) & 1ull)) { up = lj; lo_idx = ai; }
+                    const int kup = S.l_kind()[up];
+                    if (kup & 4) {
+                        const int a = kup & 3;
+                        const double aw[3] = {w[L.R + a * nls + up], w[L.R + (3 + a) * nls + up], w[L.R + (6 + a) * nls + up]};
+                        const bool onA = ((ancA >> li) & 1ull) && ((ancA >> lj) & 1ull);
+                        const bool onB = ((ancB >> li) & 1ull) && ((ancB >> lj) & 1ull);
+                        double d3[3] = {0.0, 0.0, 0.0};
+                        if (onA) { TREPB_UNROLL for (int k = 0; k < 3; ++k) d3[k] += DA[k * m + lo_idx]; }
+                        if (onB) { TREPB_UNROLL for (int k = 0; k < 3; ++k) d3[k] -= DB[k * m + lo_idx]; }
+                        cross3(aw, d3, ddv);
+                    }
+                }
+                double val;
+                if (dist) {
+                    double di[3], dj[3];
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { di[k] = DA[k * m + ai] - DB[k * m + ai]; dj[k] = DA[k * m + bj] - DB[k * m + bj]; }
+                    val = dot3(di, dj) + dot3(v, ddv);
+                    if (third == i && third == j) val -= 1.0;
+                    val *= 2.0 * lam;
+                } else {
+                    val = lam * sel3(ddv, third);
+                }
+                Y[j * ldy + i] += val;
+            }
         }
         t.sync();
     }
@@ -614,7 +776,7 @@ struct Coop {
     // Out: q2, lam, p2.  Returns the iteration count or a negative Status.  On return the
     // workspace holds the first-order midpoint data of the converged step and (nc > 0) Dh1, Dh2.
     TREPB_HD int solve(double t1, double t2, double tol, int max_it) {
-        const int nd = S.nd, nc = S.nc, nr = nd + nc, nq = S.nq, lane = t.lane();
+        const int nd = ND(), nc = NC(), nr = nd + nc, nq = NQ(), nu = NU(), lane = t.lane();
         const double dt = t2 - t1;
         int iterations = 0;
         TREPB_TICK_INIT
@@ -641,7 +803,7 @@ struct Coop {
             // residual (midpointvi.c:533-565); forces: Damping (damping.c:13-22), ConfigForce (configforce.c:13-22)
             for (int j = lane; j < nd; j += Team::kSize) {
                 double fo = -S.damp()[j] * w[L.dq + j];
-                for (int u = 0; u < S.nu; ++u) fo += S.Fu()[j * S.nu + u] * w[L.u1 + u];
+                for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
                 double f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
                 for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
                 w[L.fr + j] = f;
@@ -663,7 +825,7 @@ struct Coop {
             double* A = w + L.N;
             const int ld = L.ldf;
             for (int e = lane; e < nr * (nr + 1); e += Team::kSize) {
-                const int k = e / (nr + 1), i = e % (nr + 1);
+                const int k = e / (nr + 1), i = e - k * (nr + 1);
                 double v;
                 if (i == nr) v = w[L.fr + k];
                 else if (k < nd && i < nd) {
@@ -697,15 +859,67 @@ struct Coop {
         set_point(0, dt);
         pose_sweep(true);
         dyn_first();
-        for (int j = t.lane(); j < S.nd; j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
+        for (int j = t.lane(); j < ND(); j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
         t.sync();
+    }
+
+    // explicit right-hand-side entry of column `col` (nq: q1 | nd: p1 | nu: u1 | nk: k2) at
+    // dynamic row j  (midpointvi.c:929-1098: -D1D1L2_D1fm2 + DDh1.lambda | -e | -D3fm2 | -D2D1L2_D2fm2)
+    TREPB_HD double rhs_c(int col, int j, double dt, const double* Y, int ldy) const {
+        const int nq = NQ(), nd = ND(), nu = NU();
+        if (col < nq) {
+            double qq, vv, vab, vba;
+            tab(col, j, qq, vv, vab, vba);   // T11(col, j)
+            const double fv = col == j ? -S.damp()[j] : 0.0;
+            double c = -((0.25 * dt * qq + 1.0 / dt * vv) - 0.5 * vab - 0.5 * vba - fv);
+            if (NC() > 0) c += Y[j * ldy + col];
+            return c;
+        }
+        col -= nq;
+        if (col < nd) return col == j ? -1.0 : 0.0;
+        if (col < nd + nu) return -dt * S.Fu()[j * nu + (col - nd)];
+        double qq, vv, vab, vba;
+        tab(nd + (col - nd - nu), j, qq, vv, vab, vba);     // T21(a, j), a kinematic
+        return -((0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vab - 0.5 * vba);
+    }
+    // explicit part of d p2 / d (column) at dynamic row j: D1D2L2 for q1 columns, D2D2L2 for k2 columns
+    TREPB_HD double rhs_e(int kindv, int i, int j, double dt) const {
+        if (kindv != 0 && kindv != 3) return 0.0;
+        const int a = kindv == 0 ? i : ND() + i;
+        double qq, vv, vab, vba;
+        tab(a, j, qq, vv, vab, vba);
+        qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
+        return kindv == 0 ? (qq - vv) - vab + vba : (qq + vv) + vab + vba;
+    }
+    TREPB_HD void col_kind(int col, int& kindv, int& i) const {
+        const int nq = NQ(), nd = ND(), nu = NU();
+        if (col < nq) { kindv = 0; i = col; }
+        else if (col < nq + nd) { kindv = 1; i = col - nq; }
+        else if (col < nq + nd + nu) { kindv = 2; i = col - nq - nd; }
+        else { kindv = 3; i = col - nq - nd - nu; }
+    }
+    TREPB_HD void store_col(const Deriv1Out& o, int kindv, int i, int j, double qv, double pv) const {
+        const int nq = NQ(), nd = ND(), nu = NU(), nX = 2 * nq, nU = nu + NK();
+        double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
+        double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+        if (q2o) q2o[i * nd + j] = qv;
+        if (p2o) p2o[i * nd + j] = pv;
+        if (kindv == 0) {
+            if (o.A) { o.A[j * nX + i] = qv; o.A[(nq + j) * nX + i] = pv; }
+        } else if (kindv == 1) {
+            if (o.A) { o.A[j * nX + nq + i] = qv; o.A[(nq + j) * nX + nq + i] = pv; }
+        } else if (kindv == 2) {
+            if (o.B) { o.B[j * nU + i] = qv; o.B[(nq + j) * nU + i] = pv; }
+        } else {
+            if (o.B) { o.B[j * nU + nu + i] = qv; o.B[(nq + j) * nU + nu + i] = pv; }
+        }
     }
 
     // ---- MidpointVI_calc_deriv1 (midpointvi.c:749-1120) right after solve() on the same workspace.
     // Output layout as trepb_math.cuh::deriv1.  aux: optional export for the second-derivative
     // kernel (AuxLayout of trepb_kernels.cuh: M2 LU, M2 piv, PJ LU, PJ piv, Dh1, Dh2, T22).
     TREPB_HD int deriv1(double t1, double t2, const Deriv1Out& o, double* aux, const int* auxo) {
-        const int nd = S.nd, nk = S.nk, nq = S.nq, nc = S.nc, nu = S.nu, lane = t.lane();
+        const int nd = ND(), nk = NK(), nq = NQ(), nc = NC(), nu = NU(), lane = t.lane();
         const int nX = 2 * nq, nU = nu + nk;
         const double dt = t2 - t1;
         double* Y = w + L.N;
@@ -725,7 +939,7 @@ struct Coop {
         double* T22 = w + L.T22;
         const int ldm = L.ldm;
         for (int e = lane; e < nd * nd; e += Team::kSize) {
-            const int a = e / nd, b = e % nd;
+            const int a = e / nd, b = e - a * nd;
             double qq, vv, vab, vba;
             tab(b, a, qq, vv, vab, vba);   // T21(b, a)
             qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
@@ -735,7 +949,7 @@ struct Coop {
             T22[b * nd + a] = (qq + vv) + vab + vba;
         }
         for (int e = lane; e < nd * nc; e += Team::kSize) {
-            const int a = e / nc, c = e % nc;
+            const int a = e / nc, c = e - a * nc;
             M2[a * ldm + nd + c] = w[L.Dh1 + c * nd + a];
         }
         t.sync();
@@ -748,7 +962,7 @@ struct Coop {
             t.sync();
             // proj = -Dh2_d M2^-1 Dh1^T  (midpointvi.c:910-927)
             for (int e = lane; e < nc * nc; e += Team::kSize) {
-                const int a = e / nc, b = e % nc;
+                const int a = e / nc, b = e - a * nc;
                 double s = 0.0;
                 for (int k = 0; k < nd; ++k) s += w[L.Dh2 + a * nq + k] * M2[k * ldm + nd + b];
                 PJ[a * ldp + b] = -s;
@@ -757,13 +971,22 @@ struct Coop {
             if (!team_lu(t, PJ, ldp, nc, 0, ipivP(), iswpP(), w + L.scl, w + L.rdP, 1e-20)) return ST_SINGULAR;
         }
         if (aux) {
-            // auxo: o_m2, o_m2p, o_pj, o_pjp, o_dh1, o_dh2, o_t22
+            // auxo: o_m2, o_m2p, o_pj, o_pjp, o_dh1, o_dh2, o_t22 ; factors in LU_decomp's convention
+            // (unit lower triangle holds the scaled multipliers)
             for (int e = lane; e < nd * nd; e += Team::kSize) {
-                aux[auxo[0] + e] = M2[(e / nd) * ldm + e % nd];
+                const int i = e / nd, j = e - i * nd;
+                double v = M2[i * ldm + j];
+                if (i > j) v *= w[L.rdM + j];
+                aux[auxo[0] + e] = v;
                 aux[auxo[6] + e] = T22[e];
             }
             for (int i = lane; i < nd; i += Team::kSize) aux[auxo[1] + i] = (double)ipivM()[i];
-            for (int e = lane; e < nc * nc; e += Team::kSize) aux[auxo[2] + e] = PJ[(e / nc) * ldp + e % nc];
+            for (int e = lane; e < nc * nc; e += Team::kSize) {
+                const int i = e / nc, j = e - i * nc;
+                double v = PJ[i * ldp + j];
+                if (i > j) v *= w[L.rdP + j];
+                aux[auxo[2] + e] = v;
+            }
             for (int i = lane; i < nc; i += Team::kSize) aux[auxo[3] + i] = (double)ipivP()[i];
             for (int e = lane; e < nc * nd; e += Team::kSize) {
                 aux[auxo[4] + e] = w[L.Dh1 + e];
@@ -771,93 +994,98 @@ struct Coop {
             }
         }
         TREPB_TICK(28);
-        // ---- right-hand sides, one column per lane.  group 0: q1 columns.  group 1: p1 | u1 | k2.
-        for (int grp = 0; grp < 2; ++grp) {
-            const int ncols = grp == 0 ? nq : nd + nu + nk;
-            // explicit part c (midpointvi.c:929-1098)
-            for (int e = lane; e < nd * ncols; e += Team::kSize) {
-                const int j = e / ncols, col = e % ncols;
-                double c;
-                if (grp == 0) {
-                    double qq, vv, vab, vba;
-                    tab(col, j, qq, vv, vab, vba);   // T11(col, j)
-                    const double fv = col == j ? -S.damp()[j] : 0.0;
-                    c = -((0.25 * dt * qq + 1.0 / dt * vv) - 0.5 * vab - 0.5 * vba - fv);
-                    if (nc > 0) c += Y[j * ldy + col];
-                } else if (col < nd) {
-                    c = col == j ? -1.0 : 0.0;
-                } else if (col < nd + nu) {
-                    c = -dt * S.Fu()[j * nu + (col - nd)];
-                } else {
-                    const int a = nd + (col - nd - nu);
-                    double qq, vv, vab, vba;
-                    tab(a, j, qq, vv, vab, vba);     // T21(a, j), a kinematic
-                    c = -((0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vab - 0.5 * vba);
-                }
-                Y[j * ldy + col] = c;
-            }
-            t.sync();
-            double* Z = w + L.Z;
+        // ---- right-hand sides, one column per lane: q1 (nq) | p1 (nd) | u1 (nu) | k2 (nk)
+        const int ncols = nq + nd + nu + nk;
+        if constexpr (D::kStatic) {
+            // register-resident columns: the permuted explicit part is built directly
+            // (y[i] = c[piv[i]]), everything else is constant-index arithmetic
+            constexpr int N = D::ND, C = D::NC > 0 ? D::NC : 1;
+            const int* pivM = ipivM();
+            const int* pivP = ipivP();
             for (int col = lane; col < ncols; col += Team::kSize) {
-                double* y = Y + col;
-                col_solve(M2, ldm, nd, iswpM(), w + L.rdM, y, ldy);
-                if (nc > 0) {
-                    double* z = Z + col;
-                    for (int c = 0; c < nc; ++c) {
-                        double s = 0.0;
-                        for (int j = 0; j < nd; ++j) s += w[L.Dh2 + c * nq + j] * y[j * ldy];
-                        if (grp == 1 && col >= nd + nu) s += w[L.Dh2 + c * nq + nd + (col - nd - nu)];
-                        z[c * ldy] = s;
+                int kindv, ci;
+                col_kind(col, kindv, ci);
+                double y[N];
+                TREPB_UNROLL for (int i = 0; i < N; ++i) y[i] = rhs_c(col, pivM[i], dt, Y, ldy);
+                reg_solve<N>(M2, ldm, w + L.rdM, y);
+                double z[C];
+                if (D::NC > 0) {
+                    double zz[C];
+                    TREPB_UNROLL
+                    for (int c = 0; c < C; ++c) zz[c] = kindv == 3 ? w[L.Dh2 + c * nq + nd + ci] : 0.0;
+                    TREPB_UNROLL
+                    for (int j = 0; j < N; ++j) {
+                        TREPB_UNROLL for (int c = 0; c < C; ++c) zz[c] += w[L.Dh2 + c * nq + j] * y[j];
                     }
-                    col_solve(PJ, ldp, nc, iswpP(), w + L.rdP, z, ldy);
-                    for (int j = 0; j < nd; ++j) {
-                        double s = y[j * ldy];
-                        for (int c = 0; c < nc; ++c) s += M2[j * ldm + nd + c] * z[c * ldy];
-                        y[j * ldy] = s;
+                    TREPB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        const int src = pivP[c];
+                        double v = 0.0;
+                        TREPB_UNROLL for (int k = 0; k < C; ++k) v = src == k ? zz[k] : v;
+                        z[c] = v;
+                    }
+                    reg_solve<C>(PJ, ldp, w + L.rdP, z);
+                    TREPB_UNROLL
+                    for (int c = 0; c < C; ++c) {
+                        TREPB_UNROLL for (int j = 0; j < N; ++j) y[j] += M2[j * ldm + nd + c] * z[c];
                     }
                 }
-                // outputs of this column
-                int kindv, i;
-                if (grp == 0) { kindv = 0; i = col; }
-                else if (col < nd) { kindv = 1; i = col; }
-                else if (col < nd + nu) { kindv = 2; i = col - nd; }
-                else { kindv = 3; i = col - nd - nu; }
-                double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
-                double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
+                double pv[N];
+                TREPB_UNROLL for (int j = 0; j < N; ++j) pv[j] = rhs_e(kindv, ci, j, dt);
+                TREPB_UNROLL
+                for (int k = 0; k < N; ++k) {
+                    TREPB_UNROLL for (int j = 0; j < N; ++j) pv[j] += T22[k * nd + j] * y[k];
+                }
+                TREPB_UNROLL for (int j = 0; j < N; ++j) store_col(o, kindv, ci, j, y[j], pv[j]);
                 double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
-                for (int j = 0; j < nd; ++j) {
-                    double pv = 0.0;
-                    if (kindv == 0 || kindv == 3) {
-                        const int a = kindv == 0 ? i : nd + i;
-                        double qq, vv, vab, vba;
-                        tab(a, j, qq, vv, vab, vba);
-                        qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
-                        pv = kindv == 0 ? (qq - vv) - vab + vba      // T12(i, j)
-                                        : (qq + vv) + vab + vba;     // T22(nd+i, j)
-                    }
-                    for (int k = 0; k < nd; ++k) pv += T22[k * nd + j] * y[k * ldy];
-                    const double qv = y[j * ldy];
-                    if (q2o) q2o[i * nd + j] = qv;
-                    if (p2o) p2o[i * nd + j] = pv;
-                    if (kindv == 0) {
-                        if (o.A) { o.A[j * nX + i] = qv; o.A[(nq + j) * nX + i] = pv; }
-                    } else if (kindv == 1) {
-                        if (o.A) { o.A[j * nX + nq + i] = qv; o.A[(nq + j) * nX + nq + i] = pv; }
-                    } else if (kindv == 2) {
-                        if (o.B) { o.B[j * nU + i] = qv; o.B[(nq + j) * nU + i] = pv; }
-                    } else {
-                        if (o.B) { o.B[j * nU + nu + i] = qv; o.B[(nq + j) * nU + nu + i] = pv; }
-                    }
-                }
-                if (l1o) for (int c = 0; c < nc; ++c) l1o[i * nc + c] = Z[c * ldy + col];
+                if (D::NC > 0 && l1o) { TREPB_UNROLL for (int c = 0; c < C; ++c) l1o[ci * nc + c] = z[c]; }
             }
-            t.sync();
+        } else {
+            // run-time sizes: columns staged in shared memory, two groups sharing the Y block
+            double* Z = w + L.Z;
+            for (int grp = 0; grp < 2; ++grp) {
+                const int c0 = grp == 0 ? 0 : nq, gcols = grp == 0 ? nq : ncols - nq;
+                for (int e = lane; e < nd * gcols; e += Team::kSize) {
+                    const int j = e / gcols, col = e - j * gcols;
+                    Y[j * ldy + col] = rhs_c(c0 + col, j, dt, Y, ldy);
+                }
+                t.sync();
+                for (int col = lane; col < gcols; col += Team::kSize) {
+                    int kindv, ci;
+                    col_kind(c0 + col, kindv, ci);
+                    double* y = Y + col;
+                    col_solve(M2, ldm, nd, iswpM(), w + L.rdM, y, ldy);
+                    double* z = Z + col;
+                    if (nc > 0) {
+                        for (int c = 0; c < nc; ++c) {
+                            double s = 0.0;
+                            for (int j = 0; j < nd; ++j) s += w[L.Dh2 + c * nq + j] * y[j * ldy];
+                            if (kindv == 3) s += w[L.Dh2 + c * nq + nd + ci];
+                            z[c * ldy] = s;
+                        }
+                        col_solve(PJ, ldp, nc, iswpP(), w + L.rdP, z, ldy);
+                        for (int j = 0; j < nd; ++j) {
+                            double s = y[j * ldy];
+                            for (int c = 0; c < nc; ++c) s += M2[j * ldm + nd + c] * z[c * ldy];
+                            y[j * ldy] = s;
+                        }
+                    }
+                    for (int j = 0; j < nd; ++j) {
+                        double pv = rhs_e(kindv, ci, j, dt);
+                        for (int k = 0; k < nd; ++k) pv += T22[k * nd + j] * y[k * ldy];
+                        store_col(o, kindv, ci, j, y[j * ldy], pv);
+                    }
+                    double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
+                    if (l1o) for (int c = 0; c < nc; ++c) l1o[ci * nc + c] = z[c * ldy];
+                }
+                t.sync();
+            }
         }
         TREPB_TICK(29);
         // constant blocks of A and B (dsystem.py:284-317)
         if (o.A) {
             for (int e = lane; e < nX * nX; e += Team::kSize) {
-                const int r = e / nX, c = e % nX;
+                const int r = e / nX, c = e - r * nX;
                 const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
                 if (dyn_row && c < nq + nd) continue;
                 double v = 0.0;
@@ -867,7 +1095,7 @@ struct Coop {
         }
         if (o.B) {
             for (int e = lane; e < nX * nU; e += Team::kSize) {
-                const int r = e / nU, c = e % nU;
+                const int r = e / nU, c = e - r * nU;
                 const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
                 if (dyn_row) continue;
                 double v = 0.0;

@@ -44,7 +44,9 @@ struct CoopSys {
     //   pairs         pair_ij [npairs] = i | j << 8 (i ancestor-or-self of j); pm [nq][nq] = +idx+1 when
     //                 the row config is the ancestor(-or-self), -(idx+1) when it is the descendant, 0
     //   points [np]   pt_link (-1: fixed in the world), pt_r [np][3]
-    //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask)
+    //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask),
+    //                 cd_off [nc+1] / cd_cfg: the configs each constraint depends on, ascending (the
+    //                 first cd_nd[c] of them are dynamic)
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -72,6 +74,9 @@ struct CoopSys {
     int o_con_dist;
     int o_con_tol;
     int o_con_dep;
+    int o_cd_off;
+    int o_cd_cfg;
+    int o_cd_nd;
     TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
     TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
     TREPB_HD const int32_t* l_kind() const { return (const int32_t*)(base + o_l_kind); }
@@ -98,6 +103,9 @@ struct CoopSys {
     TREPB_HD const double* con_dist() const { return (const double*)(base + o_con_dist); }
     TREPB_HD const double* con_tol() const { return (const double*)(base + o_con_tol); }
     TREPB_HD const uint64_t* con_dep() const { return (const uint64_t*)(base + o_con_dep); }
+    TREPB_HD const int32_t* cd_off() const { return (const int32_t*)(base + o_cd_off); }
+    TREPB_HD const int32_t* cd_cfg() const { return (const int32_t*)(base + o_cd_cfg); }
+    TREPB_HD const int32_t* cd_nd() const { return (const int32_t*)(base + o_cd_nd); }
     TREPB_HD int axis(int l) const { return l_kind()[l] & 3; }
     TREPB_HD bool rot(int l) const { return (l_kind()[l] & 4) != 0; }
     TREPB_HD bool has_xc(int l) const { return (l_kind()[l] & 8) != 0; }
@@ -142,6 +150,9 @@ struct CoopPack {
         s.o_con_dist = (int)off[k++];
         s.o_con_tol = (int)off[k++];
         s.o_con_dep = (int)off[k++];
+        s.o_cd_off = (int)off[k++];
+        s.o_cd_cfg = (int)off[k++];
+        s.o_cd_nd = (int)off[k++];
         return s;
     }
 };
@@ -325,6 +336,13 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
         con_dep[c] = m;
     }
     const int np = (int)pt_link.size();
+    std::vector<int32_t> cd_off(nc + 1, 0), cd_cfg, cd_nd(nc > 0 ? nc : 1, 0);
+    for (int c = 0; c < nc; ++c) {
+        cd_off[c] = (int32_t)cd_cfg.size();
+        for (int j = 0; j < nq; ++j)
+            if ((con_dep[c] >> j) & 1ull) { cd_cfg.push_back(j); if (j < nd) cd_nd[c]++; }
+    }
+    cd_off[nc] = (int32_t)cd_cfg.size();
 
     // ---- chain pairs (only links that carry mass below)
     std::vector<int32_t> pair_ij;
@@ -388,6 +406,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(pt_link.data(), 4 * (size_t)np); put(pt_r.data(), 8 * 3 * (size_t)np);
     put(con_kind.data(), 4 * nc); put(con_a.data(), 4 * nc); put(con_b.data(), 4 * nc); put(con_third.data(), 4 * nc);
     put(con_dist.data(), 8 * nc); put(con_tol.data(), 8 * nc); put(con_dep.data(), 8 * nc);
+    put(cd_off.data(), 4 * (nc + 1)); put(cd_cfg.data(), 4 * cd_cfg.size()); put(cd_nd.data(), 4 * nc);
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;

@@ -92,7 +92,7 @@ _lib.trepb_measure_fp64_peak.argtypes = [C.c_int, _dp]
 EXPORTS = [
     "trepb_abi_version", "trepb_last_error", "trepb_system_create", "trepb_system_destroy",
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
-    "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash",
+    "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
@@ -214,12 +214,13 @@ class System:
     def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None):
         """specialize=False: skip the ahead-of-time specialised kernels.  cooperative: None = let
         the library choose between one thread and one warp per instance for a table-driven system,
-        False = always one thread, True = always the cooperative kernels (implies specialize=False)."""
+        False = always one thread, True = always the cooperative kernels (their compile-time-size
+        flavour when one was built for this shape, unless specialize=False)."""
         self.desc = desc
         self.device = device
         cd, self._keep = D.to_c(desc)
         h = C.c_void_p()
-        flags = 0 if (specialize and cooperative is not True) else 1
+        flags = 0 if specialize else 1
         if cooperative is False:
             flags |= 2
         elif cooperative is True:
