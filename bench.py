@@ -275,23 +275,54 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     t = float(np.mean(ms))
     entry = {"metric": "linearizations/s (W5: marionette nd22/nk18/nc6, solve + deriv1 -> A,B)", "value": B / t * 1e3,
              "unit": "linearizations/s", "batch": B, "ms": t, "newton_iters_mean": float(it.download().mean()),
-             "ok_fraction": float((st.download() == 0).mean())}
+             "ok_fraction": float((st.download() == 0).mean()), "kernel": s.kernel_name,
+             "kernel_info": s.kernel_info(2)}
     fj = os.path.join(ROOT, "profiles", "flops.json")
     if os.path.exists(fj):
         prof = json.load(open(fj))
-        fl = prof.get("puppet_lin_flops_per_linearization")
-        tb = prof.get("puppet_lin_dram_bytes_per_linearization")
+        fl = prof.get("puppet_coop_lin_flops_per_linearization")
+        tb = prof.get("puppet_coop_lin_dram_bytes_per_linearization")
         alg = 8 * (d.nq + d.nd + d.nk + d.nc) + 8 * (d.nX * d.nX + d.nX * d.nU + d.nq + d.nd + d.nc) + 8
         if fl:
             ach = fl * B / (t * 1e-3) / 1e12
-            entry["roofline"] = {"bound": "hbm", "achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg,
-                                 "traffic": tb * B if tb else None,
-                                 "fp64": {"achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak, "flops_per_unit": fl},
-                                 "note": "neither roofline is approached: one thread per instance with a ~144 KB strided global "
-                                         "workspace; measured DRAM traffic per linearization (ncu, profiles/r01c_puppet_raw.txt) is ~20x "
-                                         "the algorithmic bytes - the workspace traffic is what bounds it (DESIGN.md section 6)"}
+            entry["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                                 "flops_per_unit": fl, "traffic": tb * B if tb else None,
+                                 "hbm": {"achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                         "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg},
+                                 "note": "cooperative kernel: one warp per instance, link tables + 30 KB workspace per instance in shared "
+                                         "memory (7 instances per SM); DRAM traffic is the A/B output only. Issue-bound: fp64 "
+                                         "instructions are ~1/5 of the issued instructions and 7 warps per SM cannot hide the "
+                                         "dependent-issue latency (ncu: profiles/r01d_coop_lin_raw.txt; DESIGN.md section 6)"}
     out.append(entry)
+    # the same batch through the thread-per-instance table-driven kernel (the round's starting point)
+    s_thr = lib.System(d, device=device, cooperative=False)
+    ms = []
+    for rep in range(3):
+        s_thr.linearize_raw(True, B, dq, dp, None, dk, st, t1_scalar=0.0, dt_scalar=DT, lambda_guess=dl, q2=q2, p2=p2,
+                            lambda1=l2, iters=it, A=A, B=Bm)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s_thr.last_kernel_ms())
+    tt = float(np.mean(ms))
+    out.append({"metric": "linearizations/s (W5 marionette, thread-per-instance kernel with the workspace in HBM, for comparison)",
+                "value": B / tt * 1e3, "unit": "linearizations/s", "batch": B, "ms": tt, "kernel": s_thr.kernel_name})
+    s_thr.close()
+    # marionette DEL steps (trepb_step_batch): 16 steps per instance in-kernel
+    Bs, ns = 32768, 16
+    k2s = np.repeat(g["roll_k2"][idx[:Bs]][:, None, :], ns, axis=1)
+    dks = up(np.ascontiguousarray(k2s))
+    ms = []
+    for rep in range(3):
+        s.step_raw(True, Bs, ns, 0.0, DT, dq, dp, None, dks, None, dl, q2, p2, l2, it, st)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    ts = float(np.mean(ms))
+    out.append({"metric": "DEL steps/s (W5 marionette, %d steps per instance in-kernel, kinematic strings held)" % ns,
+                "value": Bs * ns / ts * 1e3, "unit": "DEL steps/s", "batch": Bs, "ms": ts,
+                "newton_iters_per_step": float(it.download().mean()) / ns, "ok_fraction": float((st.download() == 0).mean()),
+                "kernel": s.kernel_name})
+    dks.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
     Bd = 1024
     z = up(rng.normal(0, 1, (Bd, d.nX)))

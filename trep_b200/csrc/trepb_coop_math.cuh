@@ -208,16 +208,21 @@ TREPB_HD bool team_lu(const Team& t, double* A, int ld, int n, int nx, int* piv,
             const double akj = A[k * ld + j] * rdk;
             const double* mk = A + (k + 1) * ld + k;
             double* aj = A + (k + 1) * ld + j;
-            const int cnt = n - k - 1;
-            for (int i = 0; i < cnt; i += 4) {
-                // four rows at a time; the tail rows are predicated, not looped
-                const bool g1 = i + 1 < cnt, g2 = i + 2 < cnt, g3 = i + 3 < cnt;
-                const double m0 = mk[0], m1 = g1 ? mk[ld] : 0.0, m2 = g2 ? mk[2 * ld] : 0.0, m3 = g3 ? mk[3 * ld] : 0.0;
-                const double a0 = aj[0], a1 = g1 ? aj[ld] : 0.0, a2 = g2 ? aj[2 * ld] : 0.0, a3 = g3 ? aj[3 * ld] : 0.0;
+            const int cnt = n - k - 1, head = cnt & 3;
+            if (head) {
+                // 1-3 leading rows, predicated; the rest goes four rows at a time without guards
+                const bool g1 = head > 1, g2 = head > 2;
+                const double m0 = mk[0], m1 = g1 ? mk[ld] : 0.0, m2 = g2 ? mk[2 * ld] : 0.0;
+                const double a0 = aj[0], a1 = g1 ? aj[ld] : 0.0, a2 = g2 ? aj[2 * ld] : 0.0;
                 aj[0] = a0 - m0 * akj;
                 if (g1) aj[ld] = a1 - m1 * akj;
                 if (g2) aj[2 * ld] = a2 - m2 * akj;
-                if (g3) aj[3 * ld] = a3 - m3 * akj;
+                mk += head * ld; aj += head * ld;
+            }
+            for (int i = head; i < cnt; i += 4) {
+                const double m0 = mk[0], m1 = mk[ld], m2 = mk[2 * ld], m3 = mk[3 * ld];
+                const double a0 = aj[0], a1 = aj[ld], a2 = aj[2 * ld], a3 = aj[3 * ld];
+                aj[0] = a0 - m0 * akj; aj[ld] = a1 - m1 * akj; aj[2 * ld] = a2 - m2 * akj; aj[3 * ld] = a3 - m3 * akj;
                 mk += 4 * ld; aj += 4 * ld;
             }
         }
@@ -324,7 +329,9 @@ struct Coop {
     double* w;      // workspace base of this instance
     Team t;
 
-    TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team) : S(s), L(l), w(base), t(team) {}
+    TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team) : S(s), L(l), w(base), t(team) {
+        use_pose(false);
+    }
 
 #define TREPB_DIM(fn, CT, rt) \
     TREPB_HD int fn() const { if constexpr (D::kStatic) return D::CT; else return S.rt; }
@@ -377,79 +384,114 @@ struct Coop {
         cross3(X + 3, Y + 3, o + 3);
     }
 
-    // ---- pose sweep.  vel: links that carry mass, also V.  !vel: links that carry points.
-    TREPB_HD void pose_sweep(bool vel) {
+    // ---- pose sweep, one step per tree level.
+    //   mode 0: links that carry mass, at qe, with spatial velocities V          -> R, p, V
+    //   mode 1: links that carry constraint points, at qe                        -> R, p
+    //   mode 2: both at once on the two halves of the team: half 0 as mode 0 (the midpoint, qe),
+    //           half 1 as mode 1 but at q2 into a second pose set (R2, p2) that lives in the comp
+    //           region until dyn_first() overwrites it.  (The link tree is narrow - at most a few
+    //           links per level - so a full team per sweep would leave most lanes idle.)
+    TREPB_HD void pose_sweep(int mode) {
         const int nls = L.nls, lane = t.lane();
-        double* cs = w + L.cs; double* R = w + L.R; double* p = w + L.p; double* V = w + L.V;
-        const int flag = vel ? 16 : 32;
-        for (int l = lane; l < NL(); l += Team::kSize) {
-            const int kind = S.l_kind()[l];
-            if ((kind & flag) == 0 || (kind & 4) == 0) continue;
-            double sn, c;
-            sincos_(w[L.qe + S.l_cfg()[l]], &sn, &c);
-            cs[l] = c;
-            cs[nls + l] = sn;
+        constexpr int TS = Team::kSize;
+        const int npass = (mode == 2 && TS == 1) ? 2 : 1;
+        for (int pass = 0; pass < npass; ++pass) {
+            int half, sub, stride;
+            if (mode != 2) { half = mode; sub = lane; stride = TS; }
+            else if (TS == 1) { half = pass; sub = 0; stride = 1; }
+            else { half = lane / (TS / 2); sub = lane % (TS / 2); stride = TS / 2; }
+            const bool second = mode == 2 && half == 1;
+            const int flag = half == 0 ? 16 : 32, qoff = second ? L.q2 : L.qe;
+            double* cs = w + (second ? L.comp : L.cs);
+            for (int l = sub; l < NL(); l += stride) {
+                const int kind = S.l_kind()[l];
+                if ((kind & flag) == 0 || (kind & 4) == 0) continue;
+                double sn, c;
+                sincos_(w[qoff + S.l_cfg()[l]], &sn, &c);
+                cs[l] = c;
+                cs[nls + l] = sn;
+            }
         }
         t.sync();
         for (int lev = 0; lev < NLEVELS(); ++lev) {
-            const int l1 = S.lvl_off()[lev + 1];
-            for (int l = S.lvl_off()[lev] + lane; l < l1; l += Team::kSize) {
-                const int kind = S.l_kind()[l];
-                if ((kind & flag) == 0) continue;
-                const int par = S.l_par()[l], a = kind & 3, cfg = S.l_cfg()[l];
-                const bool rot = (kind & 4) != 0, xc = (kind & 8) != 0;
-                double Rb[9], pb[3];
-                if (par < 0) {
-                    if (xc) {
-                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
-                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
-                    } else {
-                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
-                        pb[0] = pb[1] = pb[2] = 0.0;
-                    }
-                } else {
-                    double Rp[9], pp[3];
-                    TREPB_UNROLL for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
-                    TREPB_UNROLL for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
-                    if (xc) {
-                        const double* Rc = S.l_Rc() + 9 * l;
-                        const double* pc = S.l_pc() + 3 * l;
-                        TREPB_UNROLL
-                        for (int r = 0; r < 3; ++r) {
-                            TREPB_UNROLL
-                            for (int q = 0; q < 3; ++q)
-                                Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
-                            pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
+            const int l0 = S.lvl_off()[lev], l1 = S.lvl_off()[lev + 1];
+            for (int pass = 0; pass < npass; ++pass) {
+                int half, sub, stride;
+                if (mode != 2) { half = mode; sub = lane; stride = TS; }
+                else if (TS == 1) { half = pass; sub = 0; stride = 1; }
+                else { half = lane / (TS / 2); sub = lane % (TS / 2); stride = TS / 2; }
+                const bool second = mode == 2 && half == 1, vel = half == 0;
+                const int flag = vel ? 16 : 32, qoff = second ? L.q2 : L.qe;
+                double* cs = w + (second ? L.comp : L.cs);
+                double* R = w + (second ? L.comp + 2 * nls : L.R);
+                double* p = w + (second ? L.comp + 11 * nls : L.p);
+                double* V = w + L.V;
+                for (int l = l0 + sub; l < l1; l += stride) {
+                    const int kind = S.l_kind()[l];
+                    if ((kind & flag) == 0) continue;
+                    const int par = S.l_par()[l], a = kind & 3, cfg = S.l_cfg()[l];
+                    const bool rot = (kind & 4) != 0, xc = (kind & 8) != 0;
+                    double Rb[9], pb[3];
+                    if (par < 0) {
+                        if (xc) {
+                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
+                        } else {
+                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
+                            pb[0] = pb[1] = pb[2] = 0.0;
                         }
                     } else {
-                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
-                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = pp[k];
+                        double Rp[9], pp[3];
+                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
+                        if (xc) {
+                            const double* Rc = S.l_Rc() + 9 * l;
+                            const double* pc = S.l_pc() + 3 * l;
+                            TREPB_UNROLL
+                            for (int r = 0; r < 3; ++r) {
+                                TREPB_UNROLL
+                                for (int q = 0; q < 3; ++q)
+                                    Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
+                                pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
+                            }
+                        } else {
+                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = pp[k];
+                        }
                     }
-                }
-                if (rot) {
-                    const double c_ = cs[l], s_ = cs[nls + l];
-                    if (a == 0) rot_cols<0>(Rb, c_, s_);
-                    else if (a == 1) rot_cols<1>(Rb, c_, s_);
-                    else rot_cols<2>(Rb, c_, s_);
-                }
-                double aw[3];
-                TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = sel3(Rb + 3 * r, a);
-                if (!rot) {
-                    const double x = w[L.qe + cfg];
-                    TREPB_UNROLL for (int r = 0; r < 3; ++r) pb[r] += x * aw[r];
-                }
-                TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
-                TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
-                if (vel) {
-                    double s6[6];
-                    twist(aw, pb, rot, s6);
-                    const double d = w[L.dq + cfg];
-                    if (par < 0) { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = s6[k] * d; }
-                    else { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = V[k * nls + par] + s6[k] * d; }
+                    if (rot) {
+                        const double c_ = cs[l], s_ = cs[nls + l];
+                        if (a == 0) rot_cols<0>(Rb, c_, s_);
+                        else if (a == 1) rot_cols<1>(Rb, c_, s_);
+                        else rot_cols<2>(Rb, c_, s_);
+                    }
+                    double aw[3];
+                    TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = sel3(Rb + 3 * r, a);
+                    if (!rot) {
+                        const double x = w[qoff + cfg];
+                        TREPB_UNROLL for (int r = 0; r < 3; ++r) pb[r] += x * aw[r];
+                    }
+                    TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
+                    if (vel) {
+                        double s6[6];
+                        twist(aw, pb, rot, s6);
+                        const double d = w[L.dq + cfg];
+                        if (par < 0) { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = s6[k] * d; }
+                        else { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = V[k * nls + par] + s6[k] * d; }
+                    }
                 }
             }
             t.sync();
         }
+    }
+    // which pose set / configuration the constraint routines read: the primary one (R, p at qe) or
+    // the second one of a dual sweep (R2, p2 at q2)
+    int oR, oP, oQ;
+    TREPB_HD void use_pose(bool second) {
+        oR = second ? L.comp + 2 * L.nls : L.R;
+        oP = second ? L.comp + 11 * L.nls : L.p;
+        oQ = second ? L.q2 : L.qe;
     }
 
     TREPB_HD void load_link_twists(int l, double* s6, double* W6, double* aw) const {
@@ -626,8 +668,8 @@ struct Coop {
             for (int k = 0; k < 3; ++k) {
                 double v = r[k];
                 if (l >= 0)
-                    v = w[L.p + k * nls + l] + (w[L.R + (k * 3) * nls + l] * r[0] + w[L.R + (k * 3 + 1) * nls + l] * r[1] +
-                                                w[L.R + (k * 3 + 2) * nls + l] * r[2]);
+                    v = w[oP + k * nls + l] + (w[oR + (k * 3) * nls + l] * r[0] + w[oR + (k * 3 + 1) * nls + l] * r[1] +
+                                             w[oR + (k * 3 + 2) * nls + l] * r[2]);
                 w[L.pts + k * np + q] = v;
             }
         }
@@ -643,10 +685,10 @@ struct Coop {
         o[0] = o[1] = o[2] = 0.0;
         if (!pdep(q, lj)) return;
         const int nls = L.nls, kind = S.l_kind()[lj], a = kind & 3;
-        const double aw[3] = {w[L.R + a * nls + lj], w[L.R + (3 + a) * nls + lj], w[L.R + (6 + a) * nls + lj]};
+        const double aw[3] = {w[oR + a * nls + lj], w[oR + (3 + a) * nls + lj], w[oR + (6 + a) * nls + lj]};
         if (kind & 4) {
             double r[3];
-            TREPB_UNROLL for (int k = 0; k < 3; ++k) r[k] = w[L.pts + k * NP() + q] - w[L.p + k * nls + lj];
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) r[k] = w[L.pts + k * NP() + q] - w[oP + k * nls + lj];
             cross3(aw, r, o);
         } else {
             o[0] = aw[0]; o[1] = aw[1]; o[2] = aw[2];
@@ -664,7 +706,7 @@ struct Coop {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
                 if (S.con_kind()[c] == C_DISTANCE) {
                     const int third = S.con_third()[c];
-                    const double d = third >= 0 ? w[L.qe + third] : S.con_dist()[c];
+                    const double d = third >= 0 ? w[oQ + third] : S.con_dist()[c];
                     w[L.hc + c] = dot3(v, v) - d * d;
                 } else {
                     w[L.hc + c] = sel3(v, S.con_third()[c]);
@@ -688,7 +730,7 @@ struct Coop {
                         TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
                         const int third = S.con_third()[c];
                         val = dot3(v, dv);
-                        if (third == j) val -= w[L.qe + third];
+                        if (third == j) val -= w[oQ + third];
                         val *= 2.0;
                     } else {
                         val = sel3(dv, S.con_third()[c]);
@@ -747,7 +789,7 @@ struct Coop {
                     const int kup = S.l_kind()[up];
                     if (kup & 4) {
                         const int a = kup & 3;
-                        const double aw[3] = {w[L.R + a * nls + up], w[L.R + (3 + a) * nls + up], w[L.R + (6 + a) * nls + up]};
+                        const double aw[3] = {w[oR + a * nls + up], w[oR + (3 + a) * nls + up], w[oR + (6 + a) * nls + up]};
                         const bool onA = ((ancA >> li) & 1ull) && ((ancA >> lj) & 1ull);
                         const bool onB = ((ancB >> li) & 1ull) && ((ancB >> lj) & 1ull);
                         double d3[3] = {0.0, 0.0, 0.0};
@@ -782,22 +824,26 @@ struct Coop {
         TREPB_TICK_INIT
         if (nc > 0) {
             set_point(1, dt);
-            pose_sweep(false);
+            pose_sweep(1);
             points();
             constraints(false, 1);
         }
         TREPB_TICK(16);
         for (;;) {
+            set_point(0, dt);
             if (nc > 0) {
-                set_point(2, dt);
-                pose_sweep(false);
+                // midpoint pose + velocities and the q2 pose of the constraint links in one sweep
+                pose_sweep(2);
+                TREPB_TICK(18);
+                use_pose(true);
                 points();
                 constraints(true, 2);
+                use_pose(false);
+                TREPB_TICK(17);
+            } else {
+                pose_sweep(0);
+                TREPB_TICK(18);
             }
-            TREPB_TICK(17);
-            set_point(0, dt);
-            pose_sweep(true);
-            TREPB_TICK(18);
             dyn_first();
             TREPB_TICK(19);
             // residual (midpointvi.c:533-565); forces: Damping (damping.c:13-22), ConfigForce (configforce.c:13-22)
@@ -857,7 +903,7 @@ struct Coop {
     // calc_p2 alone (midpointvi.c:2702-2708)
     TREPB_HD void calc_p2(double dt) {
         set_point(0, dt);
-        pose_sweep(true);
+        pose_sweep(0);
         dyn_first();
         for (int j = t.lane(); j < ND(); j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
         t.sync();
@@ -898,21 +944,30 @@ struct Coop {
         else if (col < nq + nd + nu) { kindv = 2; i = col - nq - nd; }
         else { kindv = 3; i = col - nq - nd - nu; }
     }
-    TREPB_HD void store_col(const Deriv1Out& o, int kindv, int i, int j, double qv, double pv) const {
+    // where the results of one right-hand-side column go: raw arrays [wrt][out] and the A / B blocks
+    // of DSystem.fdx / fdu (dsystem.py:284-317); resolved once per column
+    struct ColOut {
+        double *q2o, *p2o, *mq, *mp;   // raw q2_d*, p2_d* rows ; matrix (A or B) entries of the q2 / p2 rows
+        int ms;                        // row stride of the matrix
+    };
+    TREPB_HD ColOut col_out(const Deriv1Out& o, int kindv, int i) const {
         const int nq = NQ(), nd = ND(), nu = NU(), nX = 2 * nq, nU = nu + NK();
         double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
         double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
-        if (q2o) q2o[i * nd + j] = qv;
-        if (p2o) p2o[i * nd + j] = pv;
-        if (kindv == 0) {
-            if (o.A) { o.A[j * nX + i] = qv; o.A[(nq + j) * nX + i] = pv; }
-        } else if (kindv == 1) {
-            if (o.A) { o.A[j * nX + nq + i] = qv; o.A[(nq + j) * nX + nq + i] = pv; }
-        } else if (kindv == 2) {
-            if (o.B) { o.B[j * nU + i] = qv; o.B[(nq + j) * nU + i] = pv; }
-        } else {
-            if (o.B) { o.B[j * nU + nu + i] = qv; o.B[(nq + j) * nU + nu + i] = pv; }
-        }
+        ColOut c;
+        c.q2o = q2o ? q2o + i * nd : nullptr;
+        c.p2o = p2o ? p2o + i * nd : nullptr;
+        double* M = kindv < 2 ? o.A : o.B;
+        c.ms = kindv < 2 ? nX : nU;
+        const int colm = kindv == 0 ? i : (kindv == 1 ? nq + i : (kindv == 2 ? i : nu + i));
+        c.mq = M ? M + colm : nullptr;
+        c.mp = M ? M + nq * c.ms + colm : nullptr;
+        return c;
+    }
+    TREPB_HD static void store_col(const ColOut& c, int j, double qv, double pv) {
+        if (c.q2o) c.q2o[j] = qv;
+        if (c.p2o) c.p2o[j] = pv;
+        if (c.mq) { c.mq[j * c.ms] = qv; c.mp[j * c.ms] = pv; }
     }
 
     // ---- MidpointVI_calc_deriv1 (midpointvi.c:749-1120) right after solve() on the same workspace.
@@ -929,7 +984,7 @@ struct Coop {
         TREPB_TICK(25);
         if (nc > 0) {
             set_point(1, dt);
-            pose_sweep(false);
+            pose_sweep(1);
             points();
             ddh_lambda(Y, ldy);
         }
@@ -1036,7 +1091,8 @@ struct Coop {
                 for (int k = 0; k < N; ++k) {
                     TREPB_UNROLL for (int j = 0; j < N; ++j) pv[j] += T22[k * nd + j] * y[k];
                 }
-                TREPB_UNROLL for (int j = 0; j < N; ++j) store_col(o, kindv, ci, j, y[j], pv[j]);
+                const ColOut co = col_out(o, kindv, ci);
+                TREPB_UNROLL for (int j = 0; j < N; ++j) store_col(co, j, y[j], pv[j]);
                 double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
                 if (D::NC > 0 && l1o) { TREPB_UNROLL for (int c = 0; c < C; ++c) l1o[ci * nc + c] = z[c]; }
             }
@@ -1070,10 +1126,11 @@ struct Coop {
                             y[j * ldy] = s;
                         }
                     }
+                    const ColOut co = col_out(o, kindv, ci);
                     for (int j = 0; j < nd; ++j) {
                         double pv = rhs_e(kindv, ci, j, dt);
                         for (int k = 0; k < nd; ++k) pv += T22[k * nd + j] * y[k * ldy];
-                        store_col(o, kindv, ci, j, y[j * ldy], pv);
+                        store_col(co, j, y[j * ldy], pv);
                     }
                     double* l1o = kindv == 0 ? o.l1_dq1 : (kindv == 1 ? o.l1_dp1 : (kindv == 2 ? o.l1_du1 : o.l1_dk2));
                     if (l1o) for (int c = 0; c < nc; ++c) l1o[ci * nc + c] = z[c * ldy];
