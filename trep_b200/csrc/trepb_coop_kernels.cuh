@@ -46,22 +46,28 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
     Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
     const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
-    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
-        for (int i = lane; i < nq; i += 32) {
-            const double v = p.q1[b * nq + i];
-            w[lay.q1 + i] = v;
-            w[lay.q2 + i] = v;
+    // the warps of a CTA take every step together (see coop_lin_kernel)
+    for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
+        const long b = b0 + (threadIdx.x >> 5);
+        const bool live = b < p.batch;
+        if (live) {
+            for (int i = lane; i < nq; i += 32) {
+                const double v = p.q1[b * nq + i];
+                w[lay.q1 + i] = v;
+                w[lay.q2 + i] = v;
+            }
+            __syncwarp();
+            for (int i = lane; i < nd; i += 32) {
+                w[lay.p1 + i] = p.p1[b * nd + i];
+                if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
+            }
+            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
         }
-        __syncwarp();
-        for (int i = lane; i < nd; i += 32) {
-            w[lay.p1 + i] = p.p1[b * nd + i];
-            if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
-        }
-        for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
         int total = 0, status = ST_OK;
         double t1 = p.t0;
         for (int s = 0; s < p.nsteps; ++s) {
-            __syncwarp();
+            __syncthreads();
+            if (!live || status != ST_OK) continue;
             if (s > 0) {
                 for (int i = lane; i < nq; i += 32) w[lay.q1 + i] = w[lay.q2 + i];
                 for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = w[lay.p2 + i];
@@ -72,7 +78,7 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
             __syncwarp();
             const double t2 = t1 + p.dt;
             const int it = c.solve(t1, t2, p.tol, p.max_it);
-            if (it < 0) { status = it; break; }
+            if (it < 0) { status = it; continue; }
             total += it;
             t1 = t2;
             if (p.sample_every > 0 && (s + 1) % p.sample_every == 0) {
@@ -82,12 +88,14 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
             }
         }
         __syncwarp();
-        for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
-        for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
-        if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
-        if (lane == 0) {
-            if (p.iters) p.iters[b] = total;
-            p.status[b] = status;
+        if (live) {
+            for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
+            if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
+            if (lane == 0) {
+                if (p.iters) p.iters[b] = total;
+                p.status[b] = status;
+            }
         }
         __syncwarp();
     }
@@ -129,7 +137,13 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const long nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
     const int auxo[7] = {al.o_m2, al.o_m2p, al.o_pj, al.o_pjp, al.o_dh1, al.o_dh2, al.o_t22};
-    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
+    // The warps of a CTA start every instance together (one __syncthreads per round): the kernel is
+    // ~200 KB of SASS, and seven warps drifting through different phases of it miss the instruction
+    // cache a third of the time (ncu: "no instruction" stalls 31 % free-running vs 5 % in step); the
+    // wait for the slowest Newton iteration count of the round costs less than that.
+    for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc, __syncthreads()) {
+        const long b = b0 + (threadIdx.x >> 5);
+        if (b >= p.batch) continue;
         for (int i = lane; i < nq; i += 32) {
             const double v = p.q1[b * nq + i];
             w[lay.q1 + i] = v;

@@ -944,6 +944,21 @@ struct Coop {
         else if (col < nq + nd + nu) { kindv = 2; i = col - nq - nd; }
         else { kindv = 3; i = col - nq - nd - nu; }
     }
+    // n doubles of zeros to global memory, 16 bytes per store when the block is 16-byte aligned
+    TREPB_HD void fill_zero(double* dst, int n) const {
+        const int lane = t.lane();
+#if defined(__CUDA_ARCH__)
+        if ((((unsigned long long)dst) & 15ull) == 0ull) {
+            double2* d2 = (double2*)dst;
+            const int n2 = n >> 1;
+            for (int e = lane; e < n2; e += Team::kSize) d2[e] = make_double2(0.0, 0.0);
+            if ((n & 1) && lane == 0) dst[n - 1] = 0.0;
+            return;
+        }
+#endif
+        for (int e = lane; e < n; e += Team::kSize) dst[e] = 0.0;
+    }
+
     // where the results of one right-hand-side column go: raw arrays [wrt][out] and the A / B blocks
     // of DSystem.fdx / fdu (dsystem.py:284-317); resolved once per column
     struct ColOut {
@@ -1049,6 +1064,16 @@ struct Coop {
             }
         }
         TREPB_TICK(28);
+        // ---- constant blocks of A and B (dsystem.py:284-317): zero everything with wide stores, then the
+        // few non-zero constants; the computed columns are written afterwards by the column loop
+        if (o.A) fill_zero(o.A, nX * nX);
+        if (o.B) fill_zero(o.B, nX * nU);
+        t.sync();
+        for (int i = lane; i < nk; i += Team::kSize) {
+            if (o.A) o.A[(nq + nd + i) * nX + nd + i] = -1.0 / dt;
+            if (o.B) { o.B[(nd + i) * nU + nu + i] = 1.0; o.B[(nq + nd + i) * nU + nu + i] = 1.0 / dt; }
+        }
+        TREPB_TICK(30);
         // ---- right-hand sides, one column per lane: q1 (nq) | p1 (nd) | u1 (nu) | k2 (nk)
         const int ncols = nq + nd + nu + nk;
         if constexpr (D::kStatic) {
@@ -1139,28 +1164,6 @@ struct Coop {
             }
         }
         TREPB_TICK(29);
-        // constant blocks of A and B (dsystem.py:284-317)
-        if (o.A) {
-            for (int e = lane; e < nX * nX; e += Team::kSize) {
-                const int r = e / nX, c = e - r * nX;
-                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
-                if (dyn_row && c < nq + nd) continue;
-                double v = 0.0;
-                if (r >= nq + nd && c >= nd && c < nq && (r - nq - nd) == (c - nd)) v = -1.0 / dt;
-                o.A[e] = v;
-            }
-        }
-        if (o.B) {
-            for (int e = lane; e < nX * nU; e += Team::kSize) {
-                const int r = e / nU, c = e - r * nU;
-                const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
-                if (dyn_row) continue;
-                double v = 0.0;
-                if (r >= nd && r < nq && c >= nu && (r - nd) == (c - nu)) v = 1.0;
-                if (r >= nq + nd && c >= nu && (r - nq - nd) == (c - nu)) v = 1.0 / dt;
-                o.B[e] = v;
-            }
-        }
         t.sync();
         TREPB_TICK(30);
         return ST_OK;
