@@ -129,8 +129,9 @@ int  trepb_kernel_info(trepb_system* sys, int which, int32_t* regs, int32_t* loc
 int  trepb_validate(const trepb_sysdesc* desc);
 int  trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap);
 uint64_t trepb_desc_hash(const trepb_sysdesc* desc);
-/* Host-only: the shape the cooperative kernels see for this system, out[8] = nd, nk, nu, nc,
- * links (variable frames), constraint end points, chain pairs, link-tree levels.  A cooperative
+/* Host-only: the shape the cooperative kernels see for this system, out[10] = nd, nk, nu, nc,
+ * links (variable frames), constraint end points, chain pairs, link-tree levels, dynamic configs
+ * and configs that some constraint depends on.  A cooperative
  * kernel instantiated for these sizes serves every system of that shape (the link tables stay
  * run-time data).  TREPB_ERR_UNSUPPORTED when the cooperative kernels do not apply. */
 int  trepb_coop_dims(const trepb_sysdesc* desc, int32_t* out);

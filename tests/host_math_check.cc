@@ -170,7 +170,7 @@ int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double to
                    const double* q2_guess, const double* lam_guess, double* q2, double* p2,
                    double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
     CoopLayout L;
-    L.set(S);
+    L.set(S, D::kStatic);
     std::vector<double> slab(L.total + 8, 0.0);
     Coop<HostTeam, D> c(S, L, slab.data(), HostTeam());
     double* w = slab.data();
@@ -208,7 +208,7 @@ int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double to
     return c.deriv1(ta - dt, ta, o, aux, auxo);
 }
 // the shapes the build specialises ahead of time (trep_b200/build.py COOP_AOT_SYSTEMS)
-using PuppetDims = CtDims<22, 18, 0, 6, 34, 12, 157, 10>;
+using PuppetDims = CtDims<22, 18, 0, 6, 34, 12, 157, 10, 20, 38>;
 }  // namespace
 extern "C" {
 int th_coop_linearize(const trepb_sysdesc* d, int static_dims, int nsteps, double t1, double dt, double tol, int maxit,
@@ -251,6 +251,9 @@ int th_coop_info(const trepb_sysdesc* d, int* out) {
     CoopLayout L;
     L.set(S);
     out[0] = S.nl; out[1] = S.nlevels; out[2] = S.npairs; out[3] = S.np; out[4] = L.total; out[5] = (int)P.blob.size();
+    CoopLayout Ls;
+    Ls.set(S, true);
+    out[6] = Ls.total;
     return 0;
 }
 }

@@ -135,7 +135,8 @@ def coop_info(desc):
     rc = lib.th_coop_info(C.byref(cd), out)
     if rc:
         return None
-    return dict(nl=out[0], nlevels=out[1], npairs=out[2], npoints=out[3], ws_doubles=out[4], blob_bytes=out[5])
+    return dict(nl=out[0], nlevels=out[1], npairs=out[2], npoints=out[3], ws_doubles=out[4], blob_bytes=out[5],
+                ws_doubles_static=out[6])
 
 
 def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200,

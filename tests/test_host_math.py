@@ -82,10 +82,11 @@ def test_cooperative_puppet_rollout_and_tables():
     g = G.golden("puppet")
     d = G.desc("puppet")
     info = H.coop_info(d)
-    # 34 variable frames of 86, 10 link levels, and the workspace of one instance fits 7 times
-    # next to the tables in one SM's 227 KB of shared memory
+    # 34 variable frames of 86, 10 link levels; the workspace of one instance fits 7 times (run-time
+    # sizes) / 8 times (compile-time sizes) next to the tables in one SM's 227 KB of shared memory
     assert info["nl"] == 34 and info["nlevels"] == 10
     assert 7 * info["ws_doubles"] * 8 + info["blob_bytes"] + 16 <= 227 * 1024
+    assert 8 * info["ws_doubles_static"] * 8 + info["blob_bytes"] + 16 <= 227 * 1024
     dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
     p0 = H.coop_calc_p2(d, dt, g["roll_q0"], g["roll_q1"])
     G.assert_close(p0, g["roll_p"][0], "puppet p_init")

@@ -158,7 +158,8 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         s->CP = coop_pack(desc);
         if (s->CP.ok) {
             CoopSys hv = s->CP.view(s->CP.blob.data());
-            s->clay.set(hv);
+            const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE));
+            s->clay.set(hv, cks->specialized != 0);
             s->coop_blob_bytes = (int)s->CP.blob.size();
             const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
             const size_t ws_b = (size_t)s->clay.total * 8;
@@ -172,7 +173,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
                 CUS(cudaMemcpy(s->dcoop, s->CP.blob.data(), s->CP.blob.size(), cudaMemcpyHostToDevice));
                 s->cview = s->CP.view(s->dcoop);
                 s->coop_warps = warps;
-                s->cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE));
+                s->cks = cks;
                 s->coop = true;
             }
         }

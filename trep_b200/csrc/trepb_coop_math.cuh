@@ -70,12 +70,12 @@ struct WarpTeam {
 // ---------------------------------------------------------------------------------------------
 struct RtDims {
     static constexpr bool kStatic = false;
-    static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1;
+    static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1, NDC = 0, NQC = 0;
 };
 
 // workspace layout (offsets in doubles from the instance's base)
 struct CoopLayout {
-    int nls, ldf, ldm, ldp, ldy;
+    int nls, ldf, ldm, ldp, ldy, ldd;
     int q1, q2, qe, dq, p1, p2, u1, lam;
     int cs, R, p, V, comp, pts;      // link region
     int M2, T22;                     // first-derivative factors; alias the link region
@@ -88,7 +88,13 @@ struct CoopLayout {
     int total;
 
     TREPB_HD static constexpr int odd(int n) { return n | 1; }
-    TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs) {
+    // stat: the compile-time-size flavour (right-hand-side columns in registers: no Z block, the
+    // DDh.lambda block compacted to the ndc x nqc configs some constraint depends on).
+    // Aliases: cs (sin/cos of the sweep) sits in the tail of comp, which the sweeps never touch;
+    // fr / scl reuse Lq / Lv, which are dead once the residual and p2 have been formed; M2 / T22
+    // reuse the link region, N holds the Newton matrix during the solve and DDh.lambda after it.
+    TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
+                                              bool stat = false, int ndc = 0, int nqc = 0) {
         CoopLayout L{};
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
@@ -96,37 +102,42 @@ struct CoopLayout {
         L.ldm = odd(nd + nc);
         L.ldp = odd(nc > 0 ? nc : 1);
         L.ldy = nq + nu;
+        L.ldd = stat ? nqc : L.ldy;
         int o = 0;
         L.q1 = o; o += nq; L.q2 = o; o += nq; L.qe = o; o += nq; L.dq = o; o += nq;
         L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc;
         const int link0 = o;
-        L.cs = o; o += 2 * nl; L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
-        L.comp = o; o += 16 * nl; L.pts = o; o += 3 * np;
+        L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
+        L.comp = o; o += 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
         const int need = nd * L.ldm + nd * nd;
         if (o - link0 < need) o = link0 + need;
         L.M2 = link0; L.T22 = link0 + nd * L.ldm;
-        L.Lq = o; o += nq; L.Lv = o; o += nq;
+        const int nlq = nq > nr ? nq : nr;
+        L.Lq = o; o += nlq; L.Lv = o; o += nlq;
+        L.fr = L.Lq; L.scl = L.Lv;
         L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += npairs; L.DN = o; o += npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
-        const int nN = nr * L.ldf, nY = nd * L.ldy;
+        const int nN = nr * L.ldf, nY = stat ? ndc * nqc : nd * L.ldy;
         L.N = o; o += nN > nY ? nN : nY;
-        L.Z = o; o += nc * L.ldy; L.PJ = o; o += nc * L.ldp;
-        L.fr = o; o += nr; L.scl = o; o += nr; L.rdM = o; o += nr; L.rdP = o; o += nc;
+        L.Z = o; o += stat ? 0 : nc * L.ldy;
+        L.PJ = o; o += nc * L.ldp;
+        L.rdM = o; o += nr; L.rdP = o; o += nc;
         L.ints = o; o += (2 * nr + 2 * nc + 1) / 2 + 1;
         L.total = (o + 1) & ~1;
         return L;
     }
-    TREPB_HD void set(const CoopSys& s) { *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs); }
+    TREPB_HD void set(const CoopSys& s, bool stat = false) { *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc); }
 };
 
-template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_>
+template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_, int NDC_, int NQC_>
 struct CtDims {
     static constexpr bool kStatic = true;
-    static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_;
-    TREPB_HD static constexpr CoopLayout layout() { return CoopLayout::make(ND, NK, NU, NC, NL, NP, NPAIRS); }
+    static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_,
+                         NDC = NDC_, NQC = NQC_;
+    TREPB_HD static constexpr CoopLayout layout() { return CoopLayout::make(ND, NK, NU, NC, NL, NP, NPAIRS, true, NDC, NQC); }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
-               s.nlevels == NLEVELS;
+               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC;
     }
 };
 
@@ -747,9 +758,13 @@ struct Coop {
     // constraint depends on, then the dependent (i, j) pairs only.  Scratch: the comp region.
     TREPB_HD void ddh_lambda(double* Y, int ldy) {
         const int lane = t.lane(), nq = NQ(), nd = ND(), nls = L.nls;
-        for (int e = lane; e < nd * nq; e += Team::kSize) {
-            const int j = e / nq, i = e - j * nq;
-            Y[j * ldy + i] = 0.0;
+        if constexpr (D::kStatic) {
+            for (int e = lane; e < D::NDC * D::NQC; e += Team::kSize) Y[e] = 0.0;
+        } else {
+            for (int e = lane; e < nd * nq; e += Team::kSize) {
+                const int j = e / nq, i = e - j * nq;
+                Y[j * ldy + i] = 0.0;
+            }
         }
         double* DA = w + L.comp;
         for (int c = 0; c < NC(); ++c) {
@@ -808,7 +823,8 @@ struct Coop {
                 } else {
                     val = lam * sel3(ddv, third);
                 }
-                Y[j * ldy + i] += val;
+                if constexpr (D::kStatic) Y[S.dd_row()[j] * ldy + S.dd_col()[i]] += val;
+                else Y[j * ldy + i] += val;
             }
         }
         t.sync();
@@ -852,6 +868,9 @@ struct Coop {
                 for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
                 double f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
                 for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
+                // p2 = D2L2 of this midpoint (midpointvi.c:742-743, 491-504): the value of the last
+                // (converged) evaluation is the step's result; fr aliases Lq, so form it here
+                w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
                 w[L.fr + j] = f;
             }
             for (int c = lane; c < nc; c += Team::kSize) w[L.fr + nd + c] = w[L.hc + c];
@@ -895,8 +914,6 @@ struct Coop {
             TREPB_TICK(24);
             iterations++;
         }
-        for (int j = lane; j < nd; j += Team::kSize) w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
-        t.sync();
         return iterations;
     }
 
@@ -918,7 +935,14 @@ struct Coop {
             tab(col, j, qq, vv, vab, vba);   // T11(col, j)
             const double fv = col == j ? -S.damp()[j] : 0.0;
             double c = -((0.25 * dt * qq + 1.0 / dt * vv) - 0.5 * vab - 0.5 * vba - fv);
-            if (NC() > 0) c += Y[j * ldy + col];
+            if (NC() > 0) {
+                if constexpr (D::kStatic) {
+                    const int r = S.dd_row()[j], cc = S.dd_col()[col];
+                    if (r >= 0 && cc >= 0) c += Y[r * ldy + cc];
+                } else {
+                    c += Y[j * ldy + col];
+                }
+            }
             return c;
         }
         col -= nq;
@@ -993,7 +1017,7 @@ struct Coop {
         const int nX = 2 * nq, nU = nu + nk;
         const double dt = t2 - t1;
         double* Y = w + L.N;
-        const int ldy = L.ldy;
+        const int ldy = L.ldd;   // leading dimension of the DDh.lambda block (== L.ldy for run-time sizes)
         TREPB_TICK_INIT
         dyn_second();   // tables at the converged midpoint
         TREPB_TICK(25);

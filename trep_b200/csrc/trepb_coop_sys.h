@@ -30,6 +30,7 @@ namespace trepb {
 
 struct CoopSys {
     int nl, nq, nd, nk, nu, nc, np, npairs, nlevels;
+    int ndc, nqc;   // dynamic configs / configs that any constraint depends on (compact DDh.lambda block)
     int has_gravity;
     double grav[3];
     // Tables live in one relocatable blob (host memory, device memory or a shared-memory copy):
@@ -46,7 +47,8 @@ struct CoopSys {
     //   points [np]   pt_link (-1: fixed in the world), pt_r [np][3]
     //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask),
     //                 cd_off [nc+1] / cd_cfg: the configs each constraint depends on, ascending (the
-    //                 first cd_nd[c] of them are dynamic)
+    //                 first cd_nd[c] of them are dynamic); dd_row [nd] / dd_col [nq]: compact row / column
+    //                 of a config in the block of sum_c lambda_c d2h_c (-1: no constraint depends on it)
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -77,6 +79,8 @@ struct CoopSys {
     int o_cd_off;
     int o_cd_cfg;
     int o_cd_nd;
+    int o_dd_row;
+    int o_dd_col;
     TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
     TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
     TREPB_HD const int32_t* l_kind() const { return (const int32_t*)(base + o_l_kind); }
@@ -106,6 +110,8 @@ struct CoopSys {
     TREPB_HD const int32_t* cd_off() const { return (const int32_t*)(base + o_cd_off); }
     TREPB_HD const int32_t* cd_cfg() const { return (const int32_t*)(base + o_cd_cfg); }
     TREPB_HD const int32_t* cd_nd() const { return (const int32_t*)(base + o_cd_nd); }
+    TREPB_HD const int32_t* dd_row() const { return (const int32_t*)(base + o_dd_row); }
+    TREPB_HD const int32_t* dd_col() const { return (const int32_t*)(base + o_dd_col); }
     TREPB_HD int axis(int l) const { return l_kind()[l] & 3; }
     TREPB_HD bool rot(int l) const { return (l_kind()[l] & 4) != 0; }
     TREPB_HD bool has_xc(int l) const { return (l_kind()[l] & 8) != 0; }
@@ -153,6 +159,8 @@ struct CoopPack {
         s.o_cd_off = (int)off[k++];
         s.o_cd_cfg = (int)off[k++];
         s.o_cd_nd = (int)off[k++];
+        s.o_dd_row = (int)off[k++];
+        s.o_dd_col = (int)off[k++];
         return s;
     }
 };
@@ -343,6 +351,14 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
             if ((con_dep[c] >> j) & 1ull) { cd_cfg.push_back(j); if (j < nd) cd_nd[c]++; }
     }
     cd_off[nc] = (int32_t)cd_cfg.size();
+    std::vector<int32_t> dd_row(nd > 0 ? nd : 1, -1), dd_col(nq > 0 ? nq : 1, -1);
+    int ndc = 0, nqc = 0;
+    {
+        uint64_t any = 0;
+        for (int c = 0; c < nc; ++c) any |= con_dep[c];
+        for (int j = 0; j < nq; ++j)
+            if ((any >> j) & 1ull) { dd_col[j] = nqc++; if (j < nd) dd_row[j] = ndc++; }
+    }
 
     // ---- chain pairs (only links that carry mass below)
     std::vector<int32_t> pair_ij;
@@ -387,6 +403,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     memset(&P.proto, 0, sizeof(P.proto));
     P.proto.nl = nl; P.proto.nq = nq; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
     P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
+    P.proto.ndc = ndc; P.proto.nqc = nqc;
     P.proto.has_gravity = has_grav;
     for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
     int k = 0;
@@ -407,6 +424,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(con_kind.data(), 4 * nc); put(con_a.data(), 4 * nc); put(con_b.data(), 4 * nc); put(con_third.data(), 4 * nc);
     put(con_dist.data(), 8 * nc); put(con_tol.data(), 8 * nc); put(con_dep.data(), 8 * nc);
     put(cd_off.data(), 4 * (nc + 1)); put(cd_cfg.data(), 4 * cd_cfg.size()); put(cd_nd.data(), 4 * nc);
+    put(dd_row.data(), 4 * nd); put(dd_col.data(), 4 * nq);
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;
