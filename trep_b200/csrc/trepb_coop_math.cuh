@@ -424,8 +424,10 @@ struct Coop {
             }
         }
         t.sync();
-        for (int lev = 0; lev < NLEVELS(); ++lev) {
-            const int l0 = S.lvl_off()[lev], l1 = S.lvl_off()[lev + 1];
+        // one step per super level: a lane takes the head of a chain (a run of single-child links)
+        // and follows it with the pose and velocity in registers
+        for (int sl = 0; sl < S.nsl; ++sl) {
+            const int h0 = S.sl_off()[sl], h1 = S.sl_off()[sl + 1];
             for (int pass = 0; pass < npass; ++pass) {
                 int half, sub, stride;
                 if (mode != 2) { half = mode; sub = lane; stride = TS; }
@@ -437,59 +439,65 @@ struct Coop {
                 double* R = w + (second ? L.comp + 2 * nls : L.R);
                 double* p = w + (second ? L.comp + 11 * nls : L.p);
                 double* V = w + L.V;
-                for (int l = l0 + sub; l < l1; l += stride) {
-                    const int kind = S.l_kind()[l];
+                for (int h = h0 + sub; h < h1; h += stride) {
+                    int l = S.sl_head()[h];
+                    int kind = S.l_kind()[l];
                     if ((kind & flag) == 0) continue;
-                    const int par = S.l_par()[l], a = kind & 3, cfg = S.l_cfg()[l];
-                    const bool rot = (kind & 4) != 0, xc = (kind & 8) != 0;
-                    double Rb[9], pb[3];
-                    if (par < 0) {
-                        if (xc) {
-                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = S.l_Rc()[9 * l + k];
-                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = S.l_pc()[3 * l + k];
-                        } else {
+                    double Rb[9], pb[3], Vl[6];
+                    {
+                        const int par = S.l_par()[l];
+                        if (par < 0) {
                             TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = (k % 4 == 0) ? 1.0 : 0.0;
-                            pb[0] = pb[1] = pb[2] = 0.0;
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = 0.0;
+                            TREPB_UNROLL for (int k = 0; k < 6; ++k) Vl[k] = 0.0;
+                        } else {
+                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = R[k * nls + par];
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = p[k * nls + par];
+                            if (vel) { TREPB_UNROLL for (int k = 0; k < 6; ++k) Vl[k] = V[k * nls + par]; }
                         }
-                    } else {
-                        double Rp[9], pp[3];
-                        TREPB_UNROLL for (int k = 0; k < 9; ++k) Rp[k] = R[k * nls + par];
-                        TREPB_UNROLL for (int k = 0; k < 3; ++k) pp[k] = p[k * nls + par];
-                        if (xc) {
+                    }
+                    for (;;) {
+                        const int a = kind & 3, cfg = S.l_cfg()[l];
+                        const bool rot = (kind & 4) != 0;
+                        if (kind & 8) {
                             const double* Rc = S.l_Rc() + 9 * l;
                             const double* pc = S.l_pc() + 3 * l;
+                            double Rn[9];
                             TREPB_UNROLL
                             for (int r = 0; r < 3; ++r) {
                                 TREPB_UNROLL
                                 for (int q = 0; q < 3; ++q)
-                                    Rb[r * 3 + q] = Rp[r * 3] * Rc[q] + Rp[r * 3 + 1] * Rc[3 + q] + Rp[r * 3 + 2] * Rc[6 + q];
-                                pb[r] = pp[r] + (Rp[r * 3] * pc[0] + Rp[r * 3 + 1] * pc[1] + Rp[r * 3 + 2] * pc[2]);
+                                    Rn[r * 3 + q] = Rb[r * 3] * Rc[q] + Rb[r * 3 + 1] * Rc[3 + q] + Rb[r * 3 + 2] * Rc[6 + q];
+                                pb[r] += Rb[r * 3] * pc[0] + Rb[r * 3 + 1] * pc[1] + Rb[r * 3 + 2] * pc[2];
                             }
-                        } else {
-                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = Rp[k];
-                            TREPB_UNROLL for (int k = 0; k < 3; ++k) pb[k] = pp[k];
+                            TREPB_UNROLL for (int k = 0; k < 9; ++k) Rb[k] = Rn[k];
                         }
-                    }
-                    if (rot) {
-                        const double c_ = cs[l], s_ = cs[nls + l];
-                        if (a == 0) rot_cols<0>(Rb, c_, s_);
-                        else if (a == 1) rot_cols<1>(Rb, c_, s_);
-                        else rot_cols<2>(Rb, c_, s_);
-                    }
-                    double aw[3];
-                    TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = sel3(Rb + 3 * r, a);
-                    if (!rot) {
-                        const double x = w[qoff + cfg];
-                        TREPB_UNROLL for (int r = 0; r < 3; ++r) pb[r] += x * aw[r];
-                    }
-                    TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
-                    TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
-                    if (vel) {
-                        double s6[6];
-                        twist(aw, pb, rot, s6);
-                        const double d = w[L.dq + cfg];
-                        if (par < 0) { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = s6[k] * d; }
-                        else { TREPB_UNROLL for (int k = 0; k < 6; ++k) V[k * nls + l] = V[k * nls + par] + s6[k] * d; }
+                        if (rot) {
+                            const double c_ = cs[l], s_ = cs[nls + l];
+                            if (a == 0) rot_cols<0>(Rb, c_, s_);
+                            else if (a == 1) rot_cols<1>(Rb, c_, s_);
+                            else rot_cols<2>(Rb, c_, s_);
+                        }
+                        double aw[3];
+                        TREPB_UNROLL for (int r = 0; r < 3; ++r) aw[r] = sel3(Rb + 3 * r, a);
+                        if (!rot) {
+                            const double x = w[qoff + cfg];
+                            TREPB_UNROLL for (int r = 0; r < 3; ++r) pb[r] += x * aw[r];
+                        }
+                        TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k * nls + l] = Rb[k];
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) p[k * nls + l] = pb[k];
+                        if (vel) {
+                            double s6[6];
+                            twist(aw, pb, rot, s6);
+                            const double d = w[L.dq + cfg];
+                            TREPB_UNROLL for (int k = 0; k < 6; ++k) { Vl[k] += s6[k] * d; V[k * nls + l] = Vl[k]; }
+                        }
+                        const int nx = S.l_next()[l];
+                        if (nx < 0) break;
+                        const int knx = S.l_kind()[nx];
+                        if ((knx & flag) == 0) break;
+                        l = nx;
+                        kind = knx;
                     }
                 }
             }

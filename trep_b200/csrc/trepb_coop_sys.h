@@ -30,6 +30,7 @@ namespace trepb {
 
 struct CoopSys {
     int nl, nq, nd, nk, nu, nc, np, npairs, nlevels;
+    int nsl;        // super levels of the pose sweep: one per run of single-child links (chain)
     int ndc, nqc;   // dynamic configs / configs that any constraint depends on (compact DDh.lambda block)
     int has_gravity;
     double grav[3];
@@ -40,6 +41,8 @@ struct CoopSys {
     //                 below), l_child0 / l_nchild (children are contiguous), l_Rc [nl][9], l_pc [nl][3],
     //                 l_in [nl][10] = m, h[3], Ibar (xx yy zz xy xz yz), l_anc (ancestor-or-self mask)
     //   lvl_off [nlevels+1]
+    //   chains        l_next [nl] (the only child of a link, or -1), sl_off [nsl+1] / sl_head: the heads of
+    //                 the chains (runs of single-child links) grouped by their depth in the tree of chains
     //   configs [nq]  cfg_link (link driven by the config or -1), damp [nd] (sum of Damping
     //                 coefficients), ks / kq0 [nq] (sum of ConfigSpring k, k*q0), Fu [nd][nu]
     //   pairs         pair_ij [npairs] = i | j << 8 (i ancestor-or-self of j); pm [nq][nq] = +idx+1 when
@@ -81,6 +84,9 @@ struct CoopSys {
     int o_cd_nd;
     int o_dd_row;
     int o_dd_col;
+    int o_l_next;
+    int o_sl_off;
+    int o_sl_head;
     TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
     TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
     TREPB_HD const int32_t* l_kind() const { return (const int32_t*)(base + o_l_kind); }
@@ -112,6 +118,9 @@ struct CoopSys {
     TREPB_HD const int32_t* cd_nd() const { return (const int32_t*)(base + o_cd_nd); }
     TREPB_HD const int32_t* dd_row() const { return (const int32_t*)(base + o_dd_row); }
     TREPB_HD const int32_t* dd_col() const { return (const int32_t*)(base + o_dd_col); }
+    TREPB_HD const int32_t* l_next() const { return (const int32_t*)(base + o_l_next); }
+    TREPB_HD const int32_t* sl_off() const { return (const int32_t*)(base + o_sl_off); }
+    TREPB_HD const int32_t* sl_head() const { return (const int32_t*)(base + o_sl_head); }
     TREPB_HD int axis(int l) const { return l_kind()[l] & 3; }
     TREPB_HD bool rot(int l) const { return (l_kind()[l] & 4) != 0; }
     TREPB_HD bool has_xc(int l) const { return (l_kind()[l] & 8) != 0; }
@@ -161,6 +170,9 @@ struct CoopPack {
         s.o_cd_nd = (int)off[k++];
         s.o_dd_row = (int)off[k++];
         s.o_dd_col = (int)off[k++];
+        s.o_l_next = (int)off[k++];
+        s.o_sl_off = (int)off[k++];
+        s.o_sl_head = (int)off[k++];
         return s;
     }
 };
@@ -285,6 +297,31 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     for (int l = nl - 1; l >= 0; --l)
         if (l_par[l] >= 0) { l_child0[l_par[l]] = l; l_nchild[l_par[l]]++; }
 
+    // ---- chains: a lane of the pose sweep follows a run of single-child links without going through
+    // shared memory; the heads of the chains are grouped by their depth in the tree of chains
+    std::vector<int32_t> l_next(nl, -1), sl_off, sl_head;
+    int nsl = 0;
+    {
+        for (int l = 0; l < nl; ++l) if (l_nchild[l] == 1) l_next[l] = l_child0[l];
+        std::vector<int> cdepth(nl, 0);
+        std::vector<std::vector<int32_t>> by_depth;
+        for (int l = 0; l < nl; ++l) {
+            const int par = l_par[l];
+            const bool head = par < 0 || l_nchild[par] != 1;
+            cdepth[l] = par < 0 ? 0 : cdepth[par] + (head ? 1 : 0);
+            if (head) {
+                if ((int)by_depth.size() <= cdepth[l]) by_depth.resize(cdepth[l] + 1);
+                by_depth[cdepth[l]].push_back(l);
+            }
+        }
+        nsl = (int)by_depth.size();
+        for (int dth = 0; dth < nsl; ++dth) {
+            sl_off.push_back((int32_t)sl_head.size());
+            for (int32_t l : by_depth[dth]) sl_head.push_back(l);
+        }
+        sl_off.push_back((int32_t)sl_head.size());
+    }
+
     // ---- masses -> link inertia (about the link origin, link axes)
     for (int f = 1; f < nf; ++f) {
         const double* mm = d->frame_mass + 4 * f;
@@ -403,7 +440,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     memset(&P.proto, 0, sizeof(P.proto));
     P.proto.nl = nl; P.proto.nq = nq; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
     P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
-    P.proto.ndc = ndc; P.proto.nqc = nqc;
+    P.proto.ndc = ndc; P.proto.nqc = nqc; P.proto.nsl = nsl;
     P.proto.has_gravity = has_grav;
     for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
     int k = 0;
@@ -425,6 +462,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(con_dist.data(), 8 * nc); put(con_tol.data(), 8 * nc); put(con_dep.data(), 8 * nc);
     put(cd_off.data(), 4 * (nc + 1)); put(cd_cfg.data(), 4 * cd_cfg.size()); put(cd_nd.data(), 4 * nc);
     put(dd_row.data(), 4 * nd); put(dd_col.data(), 4 * nq);
+    put(l_next.data(), 4 * nl); put(sl_off.data(), 4 * sl_off.size()); put(sl_head.data(), 4 * sl_head.size());
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;
