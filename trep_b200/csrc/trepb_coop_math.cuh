@@ -897,19 +897,29 @@ struct Coop {
             TREPB_TICK(21);
             double* A = w + L.N;
             const int ld = L.ldf;
+            // constant / constraint parts entry by entry, then the Lagrangian terms scattered from the
+            // chain pairs (each (k, i) of the dynamic block receives at most one pair)
             for (int e = lane; e < nr * (nr + 1); e += Team::kSize) {
                 const int k = e / (nr + 1), i = e - k * (nr + 1);
-                double v;
+                double v = 0.0;
                 if (i == nr) v = w[L.fr + k];
-                else if (k < nd && i < nd) {
-                    double qq, vv, vab, vba;
-                    tab(k, i, qq, vv, vab, vba);
-                    v = (0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vba - 0.5 * vab;
-                    if (k == i) v += -S.damp()[k];
-                } else if (k < nd) v = -w[L.Dh1 + (i - nd) * nd + k];
+                else if (k < nd && i < nd) { if (k == i) v = -S.damp()[k] - 0.25 * dt * S.ks()[k]; }
+                else if (k < nd) v = -w[L.Dh1 + (i - nd) * nd + k];
                 else if (i < nd) v = w[L.Dh2 + (k - nd) * nq + i];
-                else v = 0.0;
                 A[k * ld + i] = v;
+            }
+            t.sync();
+            for (int e = lane; e < NPAIRS(); e += Team::kSize) {
+                const int ij = S.pair_ij()[e];
+                const int ci = S.l_cfg()[ij & 255], cj = S.l_cfg()[ij >> 8];   // ci above-or-equal cj
+                if (ci >= nd || cj >= nd) continue;
+                const double base = 0.25 * dt * w[L.QQ + e] - 1.0 / dt * w[L.VV + e];
+                if (ci == cj) A[ci * ld + ci] += base;
+                else {
+                    const double asym = 0.5 * w[L.DN + e] - 0.5 * w[L.UP + e];   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
+                    A[ci * ld + cj] += base + asym;
+                    A[cj * ld + ci] += base - asym;
+                }
             }
             t.sync();
             TREPB_TICK(22);
