@@ -156,7 +156,7 @@ def test_puppet_random_vs_reference(lib, ref):
     rng = np.random.default_rng(7)
     system, mvi = ref.make_mvi("puppet")
     nd = mvi.nd
-    B = 12
+    B = 45          # ragged: not a multiple of the 8 instances a CTA of the cooperative kernel takes per round
     idx = rng.integers(1, 58, B)
     q1 = g["roll_q"][idx].copy()
     p1 = g["roll_p"][idx].copy()

@@ -60,6 +60,21 @@ def test_specialised_registry_and_codegen():
     assert lib.desc_hash(s.describe()) != h
 
 
+def test_cooperative_shapes_and_generated_instantiation():
+    """trepb_coop_dims: the link-level shape of a system; the build instantiates the
+    compile-time-size cooperative kernels for exactly that shape."""
+    assert lib.coop_dims(G.desc("puppet")) == (22, 18, 0, 6, 34, 12, 157, 10, 20, 38)
+    assert lib.coop_dims(G.desc("pendulum5")) == (5, 0, 0, 0, 5, 0, 15, 5, 0, 0)
+    assert lib.coop_dims(G.desc("dual_pendulums")) is None      # LinearSpring / LinearDamper
+    for name in build.COOP_AOT_SYSTEMS:
+        text = open(os.path.join(build.GEN, "coop_%s.cu" % name)).read()
+        dims = ", ".join(str(v) for v in lib.coop_dims(G.desc(name)))
+        assert "CtDims<%s>" % dims in text
+    # tests/host_math_check.cc runs the same instantiation on the CPU
+    assert "CtDims<%s>" % ", ".join(str(v) for v in lib.coop_dims(G.desc("puppet"))) in \
+        open(os.path.join(ROOT, "tests", "host_math_check.cc")).read()
+
+
 def test_invalid_descriptions_are_refused():
     d = G.desc("damped_pendulum")
     bad = D.SystemDesc.from_json(d.to_json())

@@ -123,6 +123,16 @@ def device_count():
     return n.value if rc == 0 else 0
 
 
+def coop_dims(desc):
+    """Shape the cooperative kernels see: (nd, nk, nu, nc, links, points, chain pairs, levels,
+    constrained dynamic configs, constrained configs), or None when they do not apply."""
+    cd, keep = D.to_c(desc)
+    out = (C.c_int32 * 10)()
+    if _lib.trepb_coop_dims(C.byref(cd), out) != 0:
+        return None
+    return tuple(out)
+
+
 def specialized_names():
     return [_lib.trepb_specialized_name(i).decode() for i in range(_lib.trepb_num_specialized())]
 
