@@ -19,6 +19,8 @@
  *                            i.e. MidpointVI.initialize_from_configs (midpointvi.py:155-172).
  *   trepb_deriv2_batch*      _MidpointVI._calc_deriv2 (trep/_trep/midpointvi.c:2516-2545): the
  *                            second-derivative tensors q2/p2/lambda1 _d{q1,p1,u1,k2}d{q1,p1,u1,k2}.
+ *   trepb_project_batch*     DSystem.project / DOptimizer.armijo_simulate: closed-loop rollouts
+ *                            (trep/discopt/dsystem.py:426-457, doptimizer.py:405-428).
  *   trepb_linearize_batch*   DSystem.set + fdx + fdu for every k of
  *                            DSystem.linearize_trajectory (trep/discopt/dsystem.py:229-250,
  *                            284-317, 406-423) == solve_DEL + MidpointVI_calc_deriv1
@@ -168,6 +170,34 @@ typedef struct trepb_step_args {
 
 int trepb_step_batch(trepb_system* sys, const trepb_step_args* args);                   /* host pointers   */
 int trepb_step_batch_dev(trepb_system* sys, const trepb_step_args* args, void* stream); /* device pointers */
+
+/* Closed-loop rollouts with an affine feedback inside the time loop: DSystem.project
+ * (trep/discopt/dsystem.py:426-457) and DOptimizer.armijo_simulate (trep/discopt/doptimizer.py:405-428),
+ * for a batch of (bX, bU) candidates - e.g. every Armijo step size of one line search at once:
+ *     X[0] = bX[0];   U[k] = bU[k] - K[k] (X[k] - bX[k]);   X[k+1] = f(X[k], U[k], k)
+ * in the DSystem layout  X = [Q(nq); p(nd); v(nk)],  U = [u(nu); rho(nk)]  (dsystem.py:19-66);
+ * f is one MidpointVI step (set() for k = 0: lambda starts from 0; step() afterwards: lambda carried). */
+typedef struct trepb_project_args {
+    int64_t batch;          /* B candidates                                                     */
+    int32_t nsteps;         /* K steps; bX / X hold K+1 states                                  */
+    int32_t max_iterations;
+    double  t0, dt, tolerance;
+    const double* bX;       /* [B][K+1][nX]                                                     */
+    const double* bU;       /* [B][K][nU]                                                       */
+    const double* Kfb;      /* [K][nU][nX] shared by the batch, or [B][K][nU][nX]               */
+    int32_t k_per_instance; /* 0: Kfb shared, 1: one gain sequence per candidate                */
+    int32_t use_hint;       /* 1: Newton start of step k = dynamic configs of bX[k+1] (project's
+                               xk_hint); 0: = current configuration (armijo_simulate)           */
+    double* X;              /* [B][K+1][nX] out                                                 */
+    double* U;              /* [B][K][nU]   out                                                 */
+    int32_t* iters;         /* [B] Newton iterations summed over the steps; may be NULL         */
+    int32_t* status;        /* [B] 0 ok, -1 not converged, -2 singular                          */
+    int32_t* fail_step;     /* [B] first failed step (K if none): armijo_simulate returns the
+                               partial trajectory X[:k], U[:k]; may be NULL                     */
+} trepb_project_args;
+
+int trepb_project_batch(trepb_system* sys, const trepb_project_args* args);
+int trepb_project_batch_dev(trepb_system* sys, const trepb_project_args* args, void* stream);
 
 /* p2 from two consecutive configurations (initialize_from_configs). q0,q1: [B][nq] -> p: [B][nd] */
 int trepb_calc_p2_batch(trepb_system* sys, int64_t batch, double dt,

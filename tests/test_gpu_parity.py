@@ -303,3 +303,91 @@ def test_singular_jacobian_status(lib):
     out = h.step(np.array([[0.1], [0.2]]), np.array([[1.0], [0.0]]), 0.0, 0.01)
     assert out["status"][0] == -2
     assert out["status"][1] == 0 and out["iters"][1] == 0    # p = 0, no mass: already a solution
+
+
+def _ref_project(ref, name, t, bX, bU, K):
+    """Reference DSystem.project (trep/discopt/dsystem.py:426-457) for one candidate."""
+    system, mvi = ref.make_mvi(name)
+    dsys = ref.discopt.DSystem(mvi, t)
+    return dsys.project(bX, bU, K)
+
+
+@pytest.mark.parametrize("name", ["pend_on_cart1", "pend_on_cart2"])
+def test_project_matches_reference(lib, ref, name):
+    """Closed-loop rollouts (trepb_project_batch) against the reference's DSystem.project: a batch of
+    perturbed candidates around one trajectory, one shared gain sequence, every kernel flavour."""
+    rng = np.random.default_rng(5)
+    dt, K, R = 0.01, 40, 5
+    t = dt * np.arange(K + 1)
+    system, mvi = ref.make_mvi(name)
+    dsys = ref.discopt.DSystem(mvi, t)
+    nX, nU = dsys.nX, dsys.nU
+    # a feasible trajectory to perturb
+    X0 = np.zeros(nX); X0[1] = 0.3
+    U0 = 0.5 * np.sin(3 * t[:K])[:, None] * np.ones((1, nU))
+    mvi.initialize_from_state(0.0, X0[:2], X0[2:4])
+    X = np.zeros((K + 1, nX)); X[0] = X0
+    for k in range(K):
+        dsys.set(X[k], U0[k], k) if k == 0 else dsys.step(U0[k])
+        X[k + 1] = dsys.f()
+    Kfb = rng.normal(0, 0.5, (K, nU, nX))
+    bX = X[None] + rng.normal(0, 1e-2, (R, K + 1, nX))
+    bU = U0[None] + rng.normal(0, 1e-2, (R, K, nU))
+    want = [_ref_project(ref, name, t, bX[r], bU[r], Kfb) for r in range(R)]
+    for label, s in _systems(lib, name):
+        out = s.project(bX, bU, Kfb, 0.0, dt)
+        assert np.all(out["status"] == 0) and np.all(out["fail_step"] == K), label
+        for r in range(R):
+            G.assert_close(out["X"][r], want[r].X, "%s[%s] X of candidate %d" % (name, label, r), rtol=1e-9)
+            G.assert_close(out["U"][r], want[r].U, "%s[%s] U of candidate %d" % (name, label, r), rtol=1e-9)
+    # the DSystem mirror: same call as the reference's, batch or single candidate
+    from trep_b200 import midpointvi as MV, discopt as DO
+    d = DO.DSystem(MV.MidpointVI(G.desc(name)), t)
+    got = d.project(bX[0], bU[0], Kfb)
+    G.assert_close(got.X, want[0].X, name + " DSystem.project X", rtol=1e-9)
+    G.assert_close(got.U, want[0].U, name + " DSystem.project U", rtol=1e-9)
+    # armijo_simulate's variant (no hint) gives the same trajectory (to the Newton tolerance)
+    nohint = lib.System(G.desc(name)).project(bX, bU, Kfb, 0.0, dt, use_hint=False)
+    G.assert_close(nohint["X"], np.stack([w.X for w in want]), name + " no-hint X", rtol=1e-7)
+
+
+def test_project_puppet_kinematic_feedback(lib, ref):
+    """Marionette: the inputs are the kinematic string configs (rho), so the feedback moves the
+    strings.  Both table-driven flavours against the reference, and a failing candidate reports
+    its first failed step instead of aborting the batch."""
+    g = G.golden("puppet")
+    rng = np.random.default_rng(9)
+    dt, K = float(g["roll_dt"]), 10
+    t = dt * (1 + np.arange(K + 1))
+    system, mvi = ref.make_mvi("puppet")
+    dsys = ref.discopt.DSystem(mvi, t)
+    nX, nU, nq, nd = dsys.nX, dsys.nU, mvi.nq, mvi.nd
+    # golden rollout as the nominal trajectory: X = [Q; p; v]
+    Q, P = g["roll_q"], g["roll_p"]
+    X = np.zeros((K + 1, nX))
+    X[:, :nq] = Q[:K + 1]; X[:, nq:nq + nd] = P[:K + 1]
+    X[1:, nq + nd:] = (Q[1:K + 1, nd:] - Q[:K, nd:]) / dt
+    U = g["roll_k2"][:K].copy()              # rho[k] = kinematic configs at k+1
+    # gains on the dynamic-configuration error only, and small: a string moved by eps in one step
+    # changes the momenta by ~ m eps / dt, random gains on p or v make the closed loop blow up
+    Kfb = np.zeros((K, nU, nX)); Kfb[:, :, :nd] = rng.normal(0, 2e-3, (K, nU, nd))
+    R = 3
+    bX = np.repeat(X[None], R, axis=0)
+    tt = dt * np.arange(K)[None, :, None]
+    bU = U[None] + 2e-4 * np.sin(40 * tt + rng.uniform(0, 6, (R, 1, nU)))   # candidates: wiggled strings
+    want = [dsys.project(bX[r], bU[r], Kfb) for r in range(R)]
+    for coop in (True, False):
+        s = lib.System(G.desc("puppet"), cooperative=coop)
+        out = s.project(bX, bU, Kfb, t[0], dt)
+        assert np.all(out["status"] == 0)
+        for r in range(R):
+            G.assert_close(out["X"][r], want[r].X, "puppet[coop=%s] X %d" % (coop, r), rtol=1e-7)
+            G.assert_close(out["U"][r], want[r].U, "puppet[coop=%s] U %d" % (coop, r), rtol=1e-7)
+            assert np.max(np.abs(out["U"][r] - bU[r])) > 1e-6      # the feedback did something
+    # a candidate that cannot be solved (strings pulled far away at step 5) fails alone
+    bad = bU.copy()
+    bad[1, 5] += 50.0
+    out = lib.System(G.desc("puppet")).project(bX, bad, Kfb, t[0], dt, max_iterations=30)
+    assert out["status"][1] != 0 and out["fail_step"][1] == 5
+    assert out["status"][0] == 0 and out["status"][2] == 0
+    G.assert_close(out["X"][0], want[0].X, "puppet X next to a failing candidate", rtol=1e-7)

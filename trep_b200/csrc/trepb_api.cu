@@ -68,7 +68,7 @@ struct trepb_system {
     const KernelSet* ks = nullptr;
     int sms = 0;
     int block = 128;
-    int bps[3] = {1, 1, 1};      // resident CTAs per SM for step / p2 / lin
+    int bps[4] = {1, 1, 1, 1};   // resident CTAs per SM for step / p2 / lin / project
     size_t lin_stage_bytes = 0;  // dynamic smem of the staged linearize kernel (0: no staging)
     int lin_bps_staged = 1;
     // team-cooperative path (one warp per instance, workspace in shared memory)
@@ -185,7 +185,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     }
     const size_t base_smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
     if (base_smem > 200 * 1024) { trepb_system_destroy(s); return fail(TREPB_ERR_UNSUPPORTED, "system description exceeds shared memory"); }
-    for (int w = 0; w < 3; ++w) {
+    for (int w = 0; w < 4; ++w) {
         int b = 0;
         CUS(s->ks->occupancy(w, s->block, base_smem, &b, nullptr));
         s->bps[w] = b > 0 ? b : 1;
@@ -243,7 +243,7 @@ int trepb_system_is_cooperative(const trepb_system* s) { return s && s->coop; }
 
 int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_bytes, int32_t* blocks_per_sm,
                       int32_t* block, int32_t* smem_bytes) {
-    if (!s || which < 0 || which > 2) return fail(TREPB_ERR_INVALID, "bad arguments");
+    if (!s || which < 0 || which > 3) return fail(TREPB_ERR_INVALID, "bad arguments");
     CU(cudaSetDevice(s->device));
     KernelInfo ki;
     int b = 0;
@@ -374,6 +374,37 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     if (rc) return rc;
     Timed t(s, c.stream);
     CU(s->ks->step(c, p));
+    return TREPB_OK;
+}
+
+int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* stream) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
+    if (!a->bX || !a->bU || !a->Kfb || !a->X || !a->U || !a->status)
+        return fail(TREPB_ERR_INVALID, "bX, bU, Kfb, X, U and status are required");
+    if (!(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    const RtSys& ps = s->P.proto;
+    if (ps.nu + ps.nk == 0) return fail(TREPB_ERR_INVALID, "the system has no inputs to feed back");
+    if (a->batch == 0) return TREPB_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
+    CU(cudaSetDevice(s->device));
+    ProjParams p;
+    p.batch = a->batch; p.nsteps = a->nsteps; p.max_it = a->max_iterations;
+    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance;
+    p.bX = a->bX; p.bU = a->bU; p.K = a->Kfb; p.k_per_instance = a->k_per_instance; p.use_hint = a->use_hint;
+    p.X = a->X; p.U = a->U; p.iters = a->iters; p.status = a->status; p.fail_step = a->fail_step;
+    if (s->coop) {
+        CoopLaunch cl;
+        make_coop(s, a->batch, (cudaStream_t)stream, &cl);
+        Timed t(s, cl.stream);
+        CU(s->cks->proj(cl, p));
+        return TREPB_OK;
+    }
+    LaunchCfg c;
+    int rc = make_cfg(s, 3, a->batch, s->bps[3], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    if (rc) return rc;
+    Timed t(s, c.stream);
+    CU(s->ks->proj(c, p));
     return TREPB_OK;
 }
 
@@ -648,6 +679,25 @@ int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
     d.traj_q = st.out(a->traj_q, B * ns * nq); d.traj_p = st.out(a->traj_p, B * ns * nd);
     if (st.err) return st.err;
     int rc = trepb_step_batch_dev(s, &d, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
+int trepb_project_batch(trepb_system* s, const trepb_project_args* a) {
+    if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, K = (size_t)a->nsteps, nX = 2 * (size_t)(ps.nd + ps.nk), nU = (size_t)(ps.nu + ps.nk);
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    trepb_project_args d = *a;
+    d.bX = st.in(a->bX, B * (K + 1) * nX); d.bU = st.in(a->bU, B * K * nU);
+    d.Kfb = st.in(a->Kfb, (a->k_per_instance ? B : 1) * K * nU * nX);
+    d.X = st.out(a->X, B * (K + 1) * nX); d.U = st.out(a->U, B * K * nU);
+    d.iters = st.out(a->iters, B); d.status = st.out(a->status, B); d.fail_step = st.out(a->fail_step, B);
+    if (st.err) return st.err;
+    int rc = trepb_project_batch_dev(s, &d, nullptr);
     if (rc) return rc;
     return st.finish();
 }

@@ -24,7 +24,8 @@ struct CoopKernelSet {
     cudaError_t (*step)(const CoopLaunch&, const StepParams&);
     cudaError_t (*p2)(const CoopLaunch&, const P2Params&);
     cudaError_t (*lin)(const CoopLaunch&, const LinParams&, const AuxLayout&);
-    cudaError_t (*info)(int which, KernelInfo*);   // 0 step, 1 p2, 2 lin
+    cudaError_t (*proj)(const CoopLaunch&, const ProjParams&);
+    cudaError_t (*info)(int which, KernelInfo*);   // 0 step, 1 p2, 2 lin, 3 project
 };
 
 struct CoopRegistry {

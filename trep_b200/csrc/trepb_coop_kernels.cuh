@@ -101,6 +101,81 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
     }
 }
 
+// DSystem.project / armijo_simulate (trep/discopt/dsystem.py:426-457): closed-loop rollouts, one warp per
+// candidate, the affine feedback U[k] = bU[k] - K[k](X[k] - bX[k]) evaluated by the lanes (one input
+// component each) inside the time loop.
+template <class D>
+__global__ void __launch_bounds__(256, 1)
+coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
+    CoopLayout lay = lay_;
+    if constexpr (D::kStatic) lay = D::layout();
+    Stage st = coop_stage(gs, blob_bytes, lay);
+    const CoopSys& S = st.S;
+    double* w = st.w;
+    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
+    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
+    const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
+    for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
+        const long b = b0 + (threadIdx.x >> 5);
+        const bool live = b < p.batch;
+        const double* bX = p.bX + b * (long)(K + 1) * nX;
+        const double* bU = p.bU + b * (long)K * nU;
+        const double* Kf = p.K + (p.k_per_instance ? b * (long)K * nU * nX : 0);
+        double* Xo = p.X + b * (long)(K + 1) * nX;
+        double* Uo = p.U + b * (long)K * nU;
+        if (live) {
+            for (int i = lane; i < nq; i += 32) { const double v = bX[i]; w[lay.q2 + i] = v; Xo[i] = v; }
+            for (int i = lane; i < nd; i += 32) { const double v = bX[nq + i]; w[lay.p2 + i] = v; Xo[nq + i] = v; }
+            for (int i = lane; i < nk; i += 32) { const double v = bX[nq + nd + i]; w[lay.vk + i] = v; Xo[nq + nd + i] = v; }
+            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = 0.0;
+        }
+        int total = 0, status = ST_OK, fail = K;
+        double t1 = p.t0;
+        for (int s = 0; s < K; ++s) {
+            __syncthreads();   // the warps of a CTA take every step together (see coop_lin_kernel)
+            if (!live || status != ST_OK) continue;
+            for (int i = lane; i < nq; i += 32) w[lay.q1 + i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = w[lay.p2 + i];
+            __syncwarp();
+            const double* bx = bX + (long)s * nX;
+            const double* Ks = Kf + (long)s * nU * nX;
+            for (int cc = lane; cc < nU; cc += 32) {
+                double acc = 0.0;
+                for (int x = 0; x < nq; ++x) acc += Ks[cc * nX + x] * (w[lay.q1 + x] - bx[x]);
+                for (int x = 0; x < nd; ++x) acc += Ks[cc * nX + nq + x] * (w[lay.p1 + x] - bx[nq + x]);
+                for (int x = 0; x < nk; ++x) acc += Ks[cc * nX + nq + nd + x] * (w[lay.vk + x] - bx[nq + nd + x]);
+                const double u = bU[(long)s * nU + cc] - acc;
+                Uo[(long)s * nU + cc] = u;
+                if (cc < nu) w[lay.u1 + cc] = u;
+                else w[lay.q2 + nd + cc - nu] = u;
+            }
+            if (p.use_hint) for (int i = lane; i < nd; i += 32) w[lay.q2 + i] = bX[(long)(s + 1) * nX + i];
+            __syncwarp();
+            const double t2 = t1 + p.dt;
+            const int it = c.solve(t1, t2, p.tol, p.max_it);
+            if (it < 0) { status = it; fail = s; continue; }
+            total += it;
+            t1 = t2;
+            double* xo = Xo + (long)(s + 1) * nX;
+            for (int i = lane; i < nq; i += 32) xo[i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += 32) xo[nq + i] = w[lay.p2 + i];
+            for (int i = lane; i < nk; i += 32) {
+                const double v = (w[lay.q2 + nd + i] - w[lay.q1 + nd + i]) / p.dt;
+                w[lay.vk + i] = v;
+                xo[nq + nd + i] = v;
+            }
+            __syncwarp();
+        }
+        if (live && lane == 0) {
+            if (p.iters) p.iters[b] = total;
+            p.status[b] = status;
+            if (p.fail_step) p.fail_step[b] = fail;
+        }
+        __syncwarp();
+    }
+}
+
 template <class D>
 __global__ void __launch_bounds__(256, 1)
 coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
@@ -216,9 +291,16 @@ struct Launch {
         coop_lin_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
         return cudaGetLastError();
     }
+    static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
+        cudaError_t e = prep(coop_project_kernel<D>, c.smem);
+        if (e != cudaSuccess) return e;
+        coop_project_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        return cudaGetLastError();
+    }
     static cudaError_t info(int which, KernelInfo* ki) {
         const void* fn = which == 0 ? (const void*)coop_step_kernel<D>
-                       : which == 1 ? (const void*)coop_p2_kernel<D> : (const void*)coop_lin_kernel<D>;
+                       : which == 1 ? (const void*)coop_p2_kernel<D>
+                       : which == 2 ? (const void*)coop_lin_kernel<D> : (const void*)coop_project_kernel<D>;
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
         if (e != cudaSuccess) return e;
@@ -245,6 +327,7 @@ CoopKernelSet make_coop_kernelset(const char* name) {
     k.step = &coopk::Launch<D>::step;
     k.p2 = &coopk::Launch<D>::p2;
     k.lin = &coopk::Launch<D>::lin;
+    k.proj = &coopk::Launch<D>::proj;
     k.info = &coopk::Launch<D>::info;
     return k;
 }

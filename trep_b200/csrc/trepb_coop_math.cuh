@@ -76,7 +76,7 @@ struct RtDims {
 // workspace layout (offsets in doubles from the instance's base)
 struct CoopLayout {
     int nls, ldf, ldm, ldp, ldy, ldd;
-    int q1, q2, qe, dq, p1, p2, u1, lam;
+    int q1, q2, qe, dq, p1, p2, u1, lam, vk;
     int cs, R, p, V, comp, pts;      // link region
     int M2, T22;                     // first-derivative factors; alias the link region
     int Lq, Lv, VV, QQ, UP, DN;
@@ -105,7 +105,7 @@ struct CoopLayout {
         L.ldd = stat ? nqc : L.ldy;
         int o = 0;
         L.q1 = o; o += nq; L.q2 = o; o += nq; L.qe = o; o += nq; L.dq = o; o += nq;
-        L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc;
+        L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc; L.vk = o; o += nk;
         const int link0 = o;
         L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
         L.comp = o; o += 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
@@ -666,7 +666,7 @@ struct Coop {
     // table terms for the config pair (a, b):  qq = L_dqdq(a,b), vv = L_ddqddq(a,b),
     // vab = L_ddqdq(a,b), vba = L_ddqdq(b,a)   (first index of L_ddqdq is the velocity slot)
     TREPB_HD void tab(int a, int b, double& qq, double& vv, double& vab, double& vba) const {
-        const int m = S.pm()[a * NQ() + b];
+        const int m = S.pm()[a * ND() + b];   // b is a dynamic config
         if (m > 0) {
             qq = w[L.QQ + m - 1]; vv = w[L.VV + m - 1]; vab = w[L.UP + m - 1]; vba = w[L.DN + m - 1];
         } else if (m < 0) {

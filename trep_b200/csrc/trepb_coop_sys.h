@@ -45,7 +45,7 @@ struct CoopSys {
     //                 the chains (runs of single-child links) grouped by their depth in the tree of chains
     //   configs [nq]  cfg_link (link driven by the config or -1), damp [nd] (sum of Damping
     //                 coefficients), ks / kq0 [nq] (sum of ConfigSpring k, k*q0), Fu [nd][nu]
-    //   pairs         pair_ij [npairs] = i | j << 8 (i ancestor-or-self of j); pm [nq][nq] = +idx+1 when
+    //   pairs         pair_ij [npairs] = i | j << 8 (i ancestor-or-self of j); pm [nq][nd] = +idx+1 when
     //                 the row config is the ancestor(-or-self), -(idx+1) when it is the descendant, 0
     //   points [np]   pt_link (-1: fixed in the world), pt_r [np][3]
     //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask),
@@ -399,15 +399,15 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
 
     // ---- chain pairs (only links that carry mass below)
     std::vector<int32_t> pair_ij;
-    std::vector<int16_t> pm((size_t)(nq > 0 ? nq * nq : 1), 0);
+    std::vector<int16_t> pm((size_t)(nq * nd > 0 ? nq * nd : 1), 0);   // [nq][nd]: the column config is always dynamic
     for (int j = 0; j < nl; ++j) {
         if (!(l_kind[j] & 16)) continue;
         for (int i = j; i >= 0; i = l_par[i]) {
             const int idx = (int)pair_ij.size();
             pair_ij.push_back(i | (j << 8));
             const int ci = l_cfg[i], cj = l_cfg[j];
-            pm[(size_t)ci * nq + cj] = (int16_t)(idx + 1);
-            if (i != j) pm[(size_t)cj * nq + ci] = (int16_t)(-(idx + 1));
+            if (cj < nd) pm[(size_t)ci * nd + cj] = (int16_t)(idx + 1);
+            if (i != j && ci < nd) pm[(size_t)cj * nd + ci] = (int16_t)(-(idx + 1));
         }
     }
     const int npairs = (int)pair_ij.size();
@@ -456,7 +456,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(l_anc.data(), 8 * nl); put(lvl_off.data(), 4 * (nlevels + 1));
     put(cfg_link.data(), 4 * nq); put(damp.data(), 8 * nd); put(ks.data(), 8 * nq); put(kq0.data(), 8 * nq);
     put(Fu.data(), 8 * (size_t)nd * nu);
-    put(pair_ij.data(), 4 * (size_t)npairs); put(pm.data(), 2 * (size_t)nq * nq);
+    put(pair_ij.data(), 4 * (size_t)npairs); put(pm.data(), 2 * (size_t)nq * nd);
     put(pt_link.data(), 4 * (size_t)np); put(pt_r.data(), 8 * 3 * (size_t)np);
     put(con_kind.data(), 4 * nc); put(con_a.data(), 4 * nc); put(con_b.data(), 4 * nc); put(con_third.data(), 4 * nc);
     put(con_dist.data(), 8 * nc); put(con_tol.data(), 8 * nc); put(con_dep.data(), 8 * nc);

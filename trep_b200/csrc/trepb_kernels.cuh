@@ -32,6 +32,17 @@ struct StepParams {
     double *traj_q, *traj_p;
 };
 
+// closed-loop rollouts (trepb_project_batch*)
+struct ProjParams {
+    long long batch;
+    int nsteps, max_it;
+    double t0, dt, tol;
+    const double *bX, *bU, *K;
+    int k_per_instance, use_hint;
+    double *X, *U;
+    int *iters, *status, *fail_step;
+};
+
 struct P2Params {
     long long batch;
     double dt;
@@ -112,6 +123,7 @@ struct KernelSet {
     cudaError_t (*step)(const LaunchCfg&, const StepParams&);
     cudaError_t (*p2)(const LaunchCfg&, const P2Params&);
     cudaError_t (*lin)(const LaunchCfg&, const LinParams&);
+    cudaError_t (*proj)(const LaunchCfg&, const ProjParams&);
     // which: 0 step, 1 p2, 2 lin.  blocks_per_sm at (block, smem).
     cudaError_t (*occupancy)(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
     cudaError_t (*d2)(const LaunchCfg&, const WsStridedT<HD>&, const D2Params&);
@@ -263,6 +275,68 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
         }
         if (p.iters) p.iters[b] = total;
         p.status[b] = status;
+    }
+}
+
+// DSystem.project / armijo_simulate: X[0] = bX[0]; U[k] = bU[k] - K[k](X[k] - bX[k]); X[k+1] = f(X[k],U[k])
+// (trep/discopt/dsystem.py:426-457), one thread per candidate, the feedback inside the time loop.
+template <class Sys>
+__global__ void __launch_bounds__(128, TREPB_LB_MIN)
+project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const ProjParams p) {
+    const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long nth = (long)gridDim.x * blockDim.x;
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    auto& sys = c.sys;
+    auto& ws = c.ws;
+    const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
+    for (long b = tid; b < p.batch; b += nth) {
+        const double* bX = p.bX + b * (long)(K + 1) * nX;
+        const double* bU = p.bU + b * (long)K * nU;
+        const double* Kf = p.K + (p.k_per_instance ? b * (long)K * nU * nX : 0);
+        double* Xo = p.X + b * (long)(K + 1) * nX;
+        double* Uo = p.U + b * (long)K * nU;
+        TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) { const double v = bX[i]; ws.q2(i) = v; Xo[i] = v; }
+        TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) { const double v = bX[nq + i]; ws.p2(i) = v; Xo[nq + i] = v; }
+        TREPB_UNROLL_SYS for (int i = 0; i < nk; ++i) { const double v = bX[nq + nd + i]; ws.vk(i) = v; Xo[nq + nd + i] = v; }
+        TREPB_UNROLL_SYS for (int i = 0; i < nc; ++i) ws.lam(i) = 0.0;   // set(): initialize_from_state zeroes lambda
+        int total = 0, status = ST_OK, fail = K;
+        double t1 = p.t0;
+        for (int s = 0; s < K; ++s) {
+            TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) ws.q1(i) = ws.q2(i);
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) ws.p1(i) = ws.p2(i);
+            const double* bx = bX + (long)s * nX;
+            const double* Ks = Kf + (long)s * nU * nX;
+            TREPB_UNROLL_SYS
+            for (int cc = 0; cc < nU; ++cc) {
+                double acc = 0.0;
+                TREPB_UNROLL_SYS for (int x = 0; x < nq; ++x) acc += Ks[cc * nX + x] * (ws.q1(x) - bx[x]);
+                TREPB_UNROLL_SYS for (int x = 0; x < nd; ++x) acc += Ks[cc * nX + nq + x] * (ws.p1(x) - bx[nq + x]);
+                TREPB_UNROLL_SYS for (int x = 0; x < nk; ++x) acc += Ks[cc * nX + nq + nd + x] * (ws.vk(x) - bx[nq + nd + x]);
+                const double u = bU[(long)s * nU + cc] - acc;
+                Uo[(long)s * nU + cc] = u;
+                if (cc < nu) ws.u1(cc) = u;
+                else ws.q2(nd + cc - nu) = u;
+            }
+            if (p.use_hint) { TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) ws.q2(i) = bX[(long)(s + 1) * nX + i]; }
+            const double t2 = t1 + p.dt;
+            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            if (it < 0) { status = it; fail = s; break; }
+            total += it;
+            t1 = t2;
+            double* xo = Xo + (long)(s + 1) * nX;
+            TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) xo[i] = ws.q2(i);
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) xo[nq + i] = ws.p2(i);
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nk; ++i) {
+                const double v = (ws.q2(nd + i) - ws.q1(nd + i)) / p.dt;
+                ws.vk(i) = v;
+                xo[nq + nd + i] = v;
+            }
+        }
+        if (p.iters) p.iters[b] = total;
+        p.status[b] = status;
+        if (p.fail_step) p.fail_step[b] = fail;
     }
 }
 
@@ -423,9 +497,19 @@ struct Launchers {
         lin_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
         return cudaGetLastError();
     }
+    static cudaError_t proj(const LaunchCfg& c, const ProjParams& p) {
+        RtSys rs{};
+        if (c.sys) rs = *c.sys;
+        cudaError_t e = prep((const void*)project_kernel<Sys>, c.smem);
+        if (e != cudaSuccess) return e;
+        project_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        return cudaGetLastError();
+    }
+    // which: 0 step, 1 p2, 2 lin, 3 project
     static cudaError_t occupancy(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info) {
         const void* fn = which == 0 ? (const void*)step_kernel<Sys>
-                       : which == 1 ? (const void*)p2_kernel<Sys> : (const void*)lin_kernel<Sys>;
+                       : which == 1 ? (const void*)p2_kernel<Sys>
+                       : which == 2 ? (const void*)lin_kernel<Sys> : (const void*)project_kernel<Sys>;
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
         if (e != cudaSuccess) return e;
@@ -454,6 +538,7 @@ KernelSet make_kernelset(const char* name, unsigned long long hash, int speciali
     k.step = &Launchers<Sys>::step;
     k.p2 = &Launchers<Sys>::p2;
     k.lin = &Launchers<Sys>::lin;
+    k.proj = &Launchers<Sys>::proj;
     k.occupancy = &Launchers<Sys>::occupancy;
     k.d2 = &LaunchersD2<Sys>::run;
     k.d2_occupancy = &LaunchersD2<Sys>::occupancy;

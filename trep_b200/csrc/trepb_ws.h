@@ -18,7 +18,7 @@ namespace trepb {
 #define TREPB_WS_ARRAYS(X)                                                                     \
     /* integrator state */                                                                     \
     X(q1, NQ, 1, 1) X(q2, NQ, 1, 1) X(p1, ND, 1, 0) X(p2, ND, 1, 1) X(u1, NU, 1, 1) X(lam, NC, 1, 1) \
-    X(qe, NQ, 1, 1) X(dq, NQ, 1, 1)                                                            \
+    X(qe, NQ, 1, 1) X(dq, NQ, 1, 1) X(vk, NQ, 1, 0)                                            \
     /* frame pass 1 */                                                                         \
     X(cs, NF, 2, 1) X(gf, NF, 3, 1) X(V, NF, 6, 1) X(W, NF, 6, 1) X(Rw, NF, 9, 1) X(pw, NF, 3, 1) \
     /* frame pass 2: composite inertia (m, h, I sym6) and momentum */                          \

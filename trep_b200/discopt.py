@@ -157,6 +157,33 @@ class DSystem:
             A, B = A[0], B[0]
         return self.linearization_return(A, B)
 
+    def project(self, bX, bU, Kproj, use_hint=True):
+        """DSystem.project (dsystem.py:426-457) for one candidate or a batch of candidates in one
+        launch: X[0] = bX[0]; U[k] = bU[k] - Kproj[k] (X[k] - bX[k]); X[k+1] = f(X[k], U[k], k).
+        bX [K+1,nX] / [R,K+1,nX], bU [K,nU] / [R,K,nU], Kproj [K,nU,nX] shared or [R,K,nU,nX].
+        use_hint=False is DOptimizer.armijo_simulate's variant (no xk_hint, doptimizer.py:405-428): pass
+        every Armijo step size's (X + lam dX, U + lam dU) as one batch.  Raises ConvergenceError with
+        the per-candidate status / first failed step attached when a candidate fails (the reference
+        returns the partial trajectory nX[:k], nU[:k] in that case)."""
+        bX, bU = np.asarray(bX, float), np.asarray(bU, float)
+        single = bX.ndim == 2
+        if single:
+            bX, bU = bX[None], bU[None]
+        K = bX.shape[1] - 1
+        dts = np.diff(self._time[:K + 1])
+        assert np.allclose(dts, dts[0], rtol=1e-9, atol=0), "the in-kernel time loop needs a uniform time grid"
+        out = self.varint.sys.project(bX, bU[:, :K], np.asarray(Kproj, float), self._time[0], float(dts[0]),
+                                      use_hint=use_hint, tolerance=self.varint.tolerance)
+        self.last_project = out
+        bad = np.flatnonzero(out["status"] != 0)
+        if bad.size:
+            raise ConvergenceError("%d of %d closed-loop rollouts failed (first: candidate %d at step %d)"
+                                   % (bad.size, bX.shape[0], bad[0], out["fail_step"][bad[0]]), out["status"])
+        X, U = out["X"], out["U"]
+        if single:
+            X, U = X[0], U[0]
+        return self.trajectory_return(X, U)
+
     def simulate(self, X0, U):
         """Rollouts X[k+1] = f(X[k], U[k], k) from X0 [R, nX] with U [R, K, nU] in one launch
         (what repeated DSystem.step calls do, dsystem.py:253-281).  Returns X [R, K+1, nX]."""

@@ -35,6 +35,15 @@ class StepArgs(C.Structure):
                 ("traj_q", C.c_void_p), ("traj_p", C.c_void_p)]
 
 
+class ProjectArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("nsteps", C.c_int32), ("max_iterations", C.c_int32),
+                ("t0", C.c_double), ("dt", C.c_double), ("tolerance", C.c_double),
+                ("bX", C.c_void_p), ("bU", C.c_void_p), ("Kfb", C.c_void_p),
+                ("k_per_instance", C.c_int32), ("use_hint", C.c_int32),
+                ("X", C.c_void_p), ("U", C.c_void_p),
+                ("iters", C.c_void_p), ("status", C.c_void_p), ("fail_step", C.c_void_p)]
+
+
 RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2_dk2",
        "l1_dq1", "l1_dp1", "l1_du1", "l1_dk2"]
 
@@ -71,6 +80,8 @@ _lib.trepb_system_is_cooperative.argtypes = [C.c_void_p]
 _lib.trepb_system_kernel_name.argtypes = [C.c_void_p]
 _lib.trepb_step_batch.argtypes = [C.c_void_p, C.POINTER(StepArgs)]
 _lib.trepb_step_batch_dev.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
+_lib.trepb_project_batch.argtypes = [C.c_void_p, C.POINTER(ProjectArgs)]
+_lib.trepb_project_batch_dev.argtypes = [C.c_void_p, C.POINTER(ProjectArgs), C.c_void_p]
 _lib.trepb_linearize_batch.argtypes = [C.c_void_p, C.POINTER(LinArgs)]
 _lib.trepb_linearize_batch_dev.argtypes = [C.c_void_p, C.POINTER(LinArgs), C.c_void_p]
 _lib.trepb_deriv2_batch.argtypes = [C.c_void_p, C.POINTER(D2Args)]
@@ -94,7 +105,7 @@ EXPORTS = [
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
-    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_linearize_batch",
+    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
     "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
@@ -323,6 +334,17 @@ class System:
         else:
             _check(_lib.trepb_deriv2_batch(self._h, C.byref(a)))
 
+    def project_raw(self, on_device, batch, nsteps, t0, dt, bX, bU, Kfb, X, U, status, k_per_instance=False,
+                    use_hint=True, iters=None, fail_step=None, tolerance=1e-10, max_iterations=200, stream=None):
+        a = ProjectArgs(batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt, tolerance=tolerance,
+                        bX=_ptr(bX), bU=_ptr(bU), Kfb=_ptr(Kfb), k_per_instance=1 if k_per_instance else 0,
+                        use_hint=1 if use_hint else 0, X=_ptr(X), U=_ptr(U), iters=_ptr(iters), status=_ptr(status),
+                        fail_step=_ptr(fail_step))
+        if on_device:
+            _check(_lib.trepb_project_batch_dev(self._h, C.byref(a), stream))
+        else:
+            _check(_lib.trepb_project_batch(self._h, C.byref(a)))
+
     def calc_p2_raw(self, on_device, batch, dt, q0, q1, p, stream=None):
         if on_device:
             _check(_lib.trepb_calc_p2_batch_dev(self._h, batch, dt, _ptr(q0), _ptr(q1), _ptr(p), stream))
@@ -366,6 +388,26 @@ class System:
         self.step_raw(False, B, nsteps, float(t0), float(dt), q1, p1, u1, k2, q2g, lg, out["q2"],
                       out["p2"], out["lambda1"] if self.nc else None, out["iters"], out["status"],
                       tolerance, max_iterations, sample_every, out.get("traj_q"), out.get("traj_p"))
+        return out
+
+    def project(self, bX, bU, Kfb, t0, dt, use_hint=True, tolerance=1e-10, max_iterations=200):
+        """Closed-loop rollouts X[0] = bX[0], U[k] = bU[k] - K[k](X[k] - bX[k]), X[k+1] = f(X[k], U[k])
+        (DSystem.project / DOptimizer.armijo_simulate) for a batch of candidates.
+        bX [B,K+1,nX], bU [B,K,nU], Kfb [K,nU,nX] (shared) or [B,K,nU,nX]."""
+        bX = np.ascontiguousarray(np.asarray(bX, float))
+        if bX.ndim == 2:
+            bX = bX[None]
+        B, K = bX.shape[0], bX.shape[1] - 1
+        bX = self._f(bX, (B, K + 1, self.nX))
+        bU = self._f(bU, (B, K, self.nU))
+        Kfb = np.ascontiguousarray(np.asarray(Kfb, float))
+        per = Kfb.ndim == 4
+        Kfb = self._f(Kfb, (B, K, self.nU, self.nX) if per else (K, self.nU, self.nX))
+        out = dict(X=np.zeros((B, K + 1, self.nX)), U=np.zeros((B, K, self.nU)), iters=np.zeros(B, np.int32),
+                   status=np.zeros(B, np.int32), fail_step=np.zeros(B, np.int32))
+        self.project_raw(False, B, K, float(t0), float(dt), bX, bU, Kfb, out["X"], out["U"], out["status"],
+                         k_per_instance=per, use_hint=use_hint, iters=out["iters"], fail_step=out["fail_step"],
+                         tolerance=tolerance, max_iterations=max_iterations)
         return out
 
     def linearize(self, q1, p1, u1=None, k2=None, t1=0.0, t2=None, dt=None, q2_guess=None,
