@@ -323,6 +323,31 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                 "newton_iters_per_step": float(it.download().mean()) / ns, "ok_fraction": float((st.download() == 0).mean()),
                 "kernel": s.kernel_name})
     dks.free()
+    # closed-loop rollouts (DSystem.project / armijo_simulate as one batch), marionette: nominal
+    # golden rollout, wiggled strings, small gains on the configuration error
+    Bp, Kp = 8192, 10
+    nX, nU, nq, nd = d.nX, d.nU, d.nq, d.nd
+    Xn = np.zeros((Kp + 1, nX)); Xn[:, :nq] = g["roll_q"][:Kp + 1]; Xn[:, nq:nq + nd] = g["roll_p"][:Kp + 1]
+    Xn[1:, nq + nd:] = (g["roll_q"][1:Kp + 1, nd:] - g["roll_q"][:Kp, nd:]) / DT
+    Kfb = np.zeros((Kp, nU, nX)); Kfb[:, :, :nd] = rng.normal(0, 2e-3, (Kp, nU, nd))
+    tt = DT * np.arange(Kp)[None, :, None]
+    bUp = g["roll_k2"][:Kp][None] + 2e-4 * np.sin(40 * tt + rng.uniform(0, 6, (Bp, 1, nU)))
+    dbX = up(np.ascontiguousarray(np.repeat(Xn[None], Bp, axis=0))); dbU = up(np.ascontiguousarray(bUp)); dK = up(Kfb)
+    oX = lib.DeviceBuffer(device, (Bp, Kp + 1, nX)); oU = lib.DeviceBuffer(device, (Bp, Kp, nU))
+    pit = lib.DeviceBuffer(device, (Bp,), np.int32); pst = lib.DeviceBuffer(device, (Bp,), np.int32)
+    ms = []
+    for rep in range(3):
+        s.project_raw(True, Bp, Kp, DT, DT, dbX, dbU, dK, oX, oU, pst, iters=pit)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    tp = float(np.mean(ms))
+    out.append({"metric": "closed-loop DEL steps/s (W5 marionette, DSystem.project / armijo_simulate as one batch: %d candidates x %d steps)" % (Bp, Kp),
+                "value": Bp * Kp / tp * 1e3, "unit": "DEL steps/s", "batch": Bp, "ms": tp,
+                "newton_iters_per_step": float(pit.download().mean()) / Kp, "ok_fraction": float((pst.download() == 0).mean()),
+                "kernel": s.kernel_name})
+    for b_ in (dbX, dbU, dK, oX, oU, pit, pst):
+        b_.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
     Bd = 1024
     z = up(rng.normal(0, 1, (Bd, d.nX)))
