@@ -141,9 +141,11 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     std::vector<double> aux(al.size + 1);
     export_aux(s, ws, aux.data());
     // hyper-dual workspace
-    WsStridedT<HD> wh;
+    // several directions per residual evaluation (the kernels use HDG, trepb_hd.h; the host check
+    // exercises the N-direction arithmetic with N = 7)
+    WsStridedT<HDn<7>> wh;
     const int n = wh.layout(s.nf, nd, nk, nu, nc, true);
-    std::vector<HD> slab(n + 1);
+    std::vector<HDn<7>> slab(n + 1);
     wh.base = slab.data();
     wh.stride = 1;
     D2Params p;
@@ -155,7 +157,7 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     p.z = nullptr; p.zxx = p.zxu = p.zuu = nullptr;
     for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
     for (int a = 0; a < p.nx; ++a)
-        for (int b = a; b < p.nx; ++b) deriv2_pair(s, wh, p, 0, a, b);
+        for (int b0 = a; b0 < p.nx; b0 += 7) deriv2_block(s, wh, p, 0, a, b0, p.nx - b0 < 7 ? p.nx - b0 : 7);
     return 0;
 }
 

@@ -85,7 +85,7 @@ struct trepb_system {
     int ws_doubles = 0;
     DevBuf ws;
     // second-derivative path: hyper-dual workspace slab + deriv1 scratch (raw arrays, aux, q2, lambda)
-    WsStridedT<HD> wsl_hd;
+    WsStridedT<HDG> wsl_hd;
     int ws_hd_elems = 0;
     DevBuf ws_hd;
     DevBuf d2s[12];
@@ -543,23 +543,24 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         if (p.zuu && nU) CU(cudaMemsetAsync(p.zuu, 0, (size_t)B * nU * nU * sizeof(double), stream));
         if (nU == 0) { p.zxu = nullptr; p.zuu = nullptr; }
     }
-    const long long threads = B * (long long)p.npairs;
+    // one thread per (instance, parameter s, block of kD2Dirs directions t)
+    const long long threads = B * (long long)d2_blocks(p.nx, s->ks->specialized ? 1 : kD2Dirs);
     int block = s->block;
     const size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
     long long grid = (threads + block - 1) / block;
-    WsStridedT<HD> w = s->wsl_hd;
+    WsStridedT<HDG> w = s->wsl_hd;
     w.base = nullptr; w.stride = 0;
     if (!s->ks->specialized) {
         long long resident = (long long)s->sms * s->bps_d2;
         if (grid > resident) grid = resident;
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
-        const size_t per_cta = (size_t)s->ws_hd_elems * sizeof(HD) * block;
+        const size_t per_cta = (size_t)s->ws_hd_elems * sizeof(HDG) * block;
         const size_t budget = (free_b + s->ws_hd.cap) / 4;
         if ((size_t)grid * per_cta > budget) grid = (long long)(budget / per_cta);
         if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the second-derivative workspace");
         CU(s->ws_hd.ensure((size_t)grid * per_cta));
-        w.base = (HD*)s->ws_hd.p;
+        w.base = (HDG*)s->ws_hd.p;
     } else if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     LaunchCfg c;
     c.grid = (int)grid; c.block = block; c.smem = smem; c.stream = stream;

@@ -27,12 +27,11 @@ struct AuxVec {
     const double* p;
     TREPB_HD double operator()(int i) const { return p[i]; }
 };
-// scratch vectors live in the components of hyper-dual workspace slots that are free after the
-// residual evaluation
+// scratch vectors live in the v / a / b[0] components of hyper-dual workspace slots whose e1 e2k
+// components hold the right-hand sides of the block (those are left untouched)
 template <class Ws> struct FrV  { Ws* w; TREPB_HD double& operator()(int i) const { return w->fr(i).v; } };
 template <class Ws> struct FrA  { Ws* w; TREPB_HD double& operator()(int i) const { return w->fr(i).a; } };
-template <class Ws> struct FrB  { Ws* w; TREPB_HD double& operator()(int i) const { return w->fr(i).b; } };
-template <class Ws> struct FrAB { Ws* w; TREPB_HD double& operator()(int i) const { return w->fr(i).ab; } };
+template <class Ws> struct FrB  { Ws* w; TREPB_HD double& operator()(int i) const { return w->fr(i).b[0]; } };
 template <class Ws> struct HcV  { Ws* w; TREPB_HD double& operator()(int i) const { return w->hc(i).v; } };
 template <class Ws> struct HcA  { Ws* w; TREPB_HD double& operator()(int i) const { return w->hc(i).a; } };
 
@@ -43,38 +42,69 @@ TREPB_HD void split_param(int s, int nq, int nd, int nu, int* type, int* idx) {
     else if (s < nq + nd + nu) { *type = 2; *idx = s - nq - nd; }
     else { *type = 3; *idx = s - nq - nd - nu; }
 }
+// number of direction blocks of an instance: for every s the parameters t = s .. nx-1 in blocks of N
+TREPB_HD int d2_blocks(int nx, int N) {
+    int n = 0;
+    for (int s = 0; s < nx; ++s) n += (nx - s + N - 1) / N;
+    return n;
+}
 
-// One (instance b, parameter pair s <= t): evaluates the residual on hyper-duals, solves, stores.
+// One (instance b, parameter s, block of nt <= N parameters t0 .. t0+nt-1 >= s): evaluates the residual
+// once on hyper-duals carrying xi_s in e1 and xi_t in e2k, then solves and stores per pair.
 template <class Sys, class Ws>
-TREPB_HD void deriv2_pair(const Sys& sys, Ws& ws, const D2Params& p, long b, int s, int t) {
+TREPB_HD void deriv2_block(const Sys& sys, Ws& ws, const D2Params& p, long b, int s, int t0, int nt) {
+    using Real = typename Ws::Real;
+    constexpr int N = (int)(sizeof(Real) / sizeof(double) - 2) / 2;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
-    int ts, is, tt, it;
+    int ts, is;
     split_param(s, nq, nd, nu, &ts, &is);
-    split_param(t, nq, nd, nu, &tt, &it);
     const int cnt_s = ts == 0 ? nq : (ts == 1 ? nd : (ts == 2 ? nu : nk));
-    const int cnt_t = tt == 0 ? nq : (tt == 1 ? nd : (tt == 2 ? nu : nk));
     const double* zs = p.q2_d[ts] + ((long)b * cnt_s + is) * nd;   // d q2_dyn / d s
-    const double* zt = p.q2_d[tt] + ((long)b * cnt_t + it) * nd;
     const double* ls = nc ? p.l1_d[ts] + ((long)b * cnt_s + is) * nc : nullptr;
-    const double* lt = nc ? p.l1_d[tt] + ((long)b * cnt_t + it) * nc : nullptr;
-    // ---- point z + e1 xi_s + e2 xi_t
+    int tt[N], it[N], cnt_t[N];
+    const double* zt[N];
+    const double* lt[N];
+    TREPB_HDU
+    for (int k = 0; k < N; ++k) {
+        const int t = t0 + (k < nt ? k : 0);
+        split_param(t, nq, nd, nu, &tt[k], &it[k]);
+        cnt_t[k] = tt[k] == 0 ? nq : (tt[k] == 1 ? nd : (tt[k] == 2 ? nu : nk));
+        zt[k] = p.q2_d[tt[k]] + ((long)b * cnt_t[k] + it[k]) * nd;
+        lt[k] = nc ? p.l1_d[tt[k]] + ((long)b * cnt_t[k] + it[k]) * nc : nullptr;
+    }
+    // ---- point z + e1 xi_s + sum_k e2k xi_tk   (unused directions k >= nt carry zero tangents)
     TREPB_UNROLL_SYS
     for (int i = 0; i < nq; ++i) {
-        ws.q1(i) = HD(p.q1[b * nq + i], (ts == 0 && is == i) ? 1.0 : 0.0, (tt == 0 && it == i) ? 1.0 : 0.0, 0.0);
-        double a, bb;
-        if (i < nd) { a = zs[i]; bb = zt[i]; }
-        else { a = (ts == 3 && is == i - nd) ? 1.0 : 0.0; bb = (tt == 3 && it == i - nd) ? 1.0 : 0.0; }
-        ws.q2(i) = HD(p.q2[b * nq + i], a, bb, 0.0);
+        Real x1(p.q1[b * nq + i]), x2(p.q2[b * nq + i]);
+        x1.a = (ts == 0 && is == i) ? 1.0 : 0.0;
+        x2.a = i < nd ? zs[i] : ((ts == 3 && is == i - nd) ? 1.0 : 0.0);
+        TREPB_HDU
+        for (int k = 0; k < N; ++k) {
+            const bool on = k < nt;
+            x1.b[k] = (on && tt[k] == 0 && it[k] == i) ? 1.0 : 0.0;
+            x2.b[k] = !on ? 0.0 : (i < nd ? zt[k][i] : ((tt[k] == 3 && it[k] == i - nd) ? 1.0 : 0.0));
+        }
+        ws.q1(i) = x1;
+        ws.q2(i) = x2;
     }
     TREPB_UNROLL_SYS
-    for (int i = 0; i < nu; ++i)
-        ws.u1(i) = HD(p.u1[b * nu + i], (ts == 2 && is == i) ? 1.0 : 0.0, (tt == 2 && it == i) ? 1.0 : 0.0, 0.0);
+    for (int i = 0; i < nu; ++i) {
+        Real x(p.u1[b * nu + i]);
+        x.a = (ts == 2 && is == i) ? 1.0 : 0.0;
+        TREPB_HDU for (int k = 0; k < N; ++k) x.b[k] = (k < nt && tt[k] == 2 && it[k] == i) ? 1.0 : 0.0;
+        ws.u1(i) = x;
+    }
     TREPB_UNROLL_SYS
-    for (int i = 0; i < nc; ++i) ws.lam(i) = HD(p.lam[b * nc + i], ls[i], lt[i], 0.0);
+    for (int i = 0; i < nc; ++i) {
+        Real x(p.lam[b * nc + i]);
+        x.a = ls[i];
+        TREPB_HDU for (int k = 0; k < N; ++k) x.b[k] = k < nt ? lt[k][i] : 0.0;
+        ws.lam(i) = x;
+    }
     const double t1 = p.t1 ? p.t1[b] : p.t1s;
     const double t2 = p.t2 ? p.t2[b] : (t1 + p.dts);
     const double dt = t2 - t1;
-    // ---- residual along the two tangents (same call sequence as calc_f, midpointvi.c:533-565)
+    // ---- residual along the tangents (same call sequence as calc_f, midpointvi.c:533-565)
     if (nc > 0) {
         set_point(sys, ws, 1, dt);
         pass1(sys, ws, false, true);
@@ -83,98 +113,95 @@ TREPB_HD void deriv2_pair(const Sys& sys, Ws& ws, const D2Params& p, long b, int
     eval_mid(sys, ws, dt, 1);
     TREPB_UNROLL_SYS
     for (int j = 0; j < nd; ++j) {
-        HD f = (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
+        Real f = (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
         TREPB_UNROLL_SYS
         for (int cc = 0; cc < nc; ++cc) f -= ws.Dh1(cc, j) * ws.lam(cc);
-        const HD h2 = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
-        ws.fr(j).v = -f.ab;    // c = -R1
-        ws.p2(j).v = h2.ab;    // D^2 H [xi_s, xi_t]
+        const Real h2 = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
+        ws.fr(j) = f;      // .ab[k] = R1 of pair k
+        ws.p2(j) = h2;     // .ab[k] = D^2 H [xi_s, xi_tk]
     }
     if (nc > 0) {
         set_point(sys, ws, 2, dt);
         pass1(sys, ws, false, true);
-        constraints_eval(sys, ws, 1, 2);
-        TREPB_UNROLL_SYS
-        for (int cc = 0; cc < nc; ++cc) ws.hc(cc).v = ws.hc(cc).ab;   // R2
+        constraints_eval(sys, ws, 1, 2);   // hc(cc).ab[k] = R2 of pair k
     }
-    // ---- solve (calc_deriv1's scheme): lambda_st = proj^-1 (Dh2 M2^-1 c + R2),
+    // ---- per pair: solve (calc_deriv1's scheme): lambda_st = proj^-1 (Dh2 M2^-1 c + R2),
     //      q2_st = M2^-1 (c + Dh1^T lambda_st),  p2_st = D^2H + D2D2L2^T q2_st
     const double* aux = p.aux + (long)b * p.auxl.size;
     const AuxMat M2{aux + p.auxl.o_m2, nd}, PJ{aux + p.auxl.o_pj, nc}, T22{aux + p.auxl.o_t22, nd};
     const AuxMat Dh1{aux + p.auxl.o_dh1, nd}, Dh2{aux + p.auxl.o_dh2, nd};
     const AuxVec M2p{aux + p.auxl.o_m2p}, PJp{aux + p.auxl.o_pjp};
-    TREPB_UNROLL_SYS
-    for (int j = 0; j < nd; ++j) { ws.fr(j).a = ws.fr(j).v; ws.fr(j).b = ws.fr(j).v; }   // tnd = col = c
-    if (nc > 0) {
-        lu_solve<Sys>(M2, nd, M2p, FrA<Ws>{&ws}, FrAB<Ws>{&ws});
+    TREPB_HDU
+    for (int k = 0; k < N; ++k) {
+        if (k >= nt) continue;
         TREPB_UNROLL_SYS
-        for (int cc = 0; cc < nc; ++cc) {
-            double sacc = 0.0;
+        for (int j = 0; j < nd; ++j) { const double c = -ws.fr(j).ab[k]; ws.fr(j).v = c; ws.fr(j).a = c; }   // tnd = col = c = -R1
+        if (nc > 0) {
+            lu_solve<Sys>(M2, nd, M2p, FrV<Ws>{&ws}, FrB<Ws>{&ws});
             TREPB_UNROLL_SYS
-            for (int j = 0; j < nd; ++j) sacc += Dh2(cc, j) * ws.fr(j).a;
-            ws.hc(cc).v = sacc + ws.hc(cc).v;
-        }
-        lu_solve<Sys>(PJ, nc, PJp, HcV<Ws>{&ws}, HcA<Ws>{&ws});
-        TREPB_UNROLL_SYS
-        for (int j = 0; j < nd; ++j) {
-            double sacc = ws.fr(j).b;
+            for (int cc = 0; cc < nc; ++cc) {
+                double sacc = 0.0;
+                TREPB_UNROLL_SYS
+                for (int j = 0; j < nd; ++j) sacc += Dh2(cc, j) * ws.fr(j).v;
+                ws.hc(cc).v = sacc + ws.hc(cc).ab[k];
+            }
+            lu_solve<Sys>(PJ, nc, PJp, HcV<Ws>{&ws}, HcA<Ws>{&ws});
             TREPB_UNROLL_SYS
-            for (int cc = 0; cc < nc; ++cc) sacc += Dh1(cc, j) * ws.hc(cc).v;
-            ws.fr(j).b = sacc;
+            for (int j = 0; j < nd; ++j) {
+                double sacc = ws.fr(j).a;
+                TREPB_UNROLL_SYS
+                for (int cc = 0; cc < nc; ++cc) sacc += Dh1(cc, j) * ws.hc(cc).v;
+                ws.fr(j).a = sacc;
+            }
         }
-    }
-    lu_solve<Sys>(M2, nd, M2p, FrB<Ws>{&ws}, FrAB<Ws>{&ws});
-    // ---- store: kind index of (type s <= type t)
-    const int kind = ts == 0 ? tt : (ts == 1 ? 3 + tt : (ts == 2 ? 5 + tt : 9));
-    const bool mirror = (ts == tt) && (is != it);
-    double* oq = p.out[0][kind];
-    double* op = p.out[1][kind];
-    double* ol = p.out[2][kind];
-    const long base_q = (long)b * cnt_s * cnt_t;
-    TREPB_UNROLL_SYS
-    for (int j = 0; j < nd; ++j) {
-        const double qv = ws.fr(j).b;
-        double pv = ws.p2(j).v;
-        TREPB_UNROLL_SYS
-        for (int k = 0; k < nd; ++k) pv += T22(k, j) * ws.fr(k).b;
-        if (oq) {
-            oq[((base_q + (long)is * cnt_t + it)) * nd + j] = qv;
-            if (mirror) oq[((base_q + (long)it * cnt_t + is)) * nd + j] = qv;
-        }
-        if (op) {
-            op[((base_q + (long)is * cnt_t + it)) * nd + j] = pv;
-            if (mirror) op[((base_q + (long)it * cnt_t + is)) * nd + j] = pv;
-        }
-    }
-    if (p.z) {
-        // z-contraction in the DSystem layout: X = [Q; p; v], U = [u; rho]  (dsystem.py:320-386)
-        const int nX = 2 * nq, nU = nu + nk;
-        const double* z = p.z + (long)b * nX;
+        lu_solve<Sys>(M2, nd, M2p, FrA<Ws>{&ws}, FrB<Ws>{&ws});
+        // ---- store: kind index of (type s <= type t)
+        const int kind = ts == 0 ? tt[k] : (ts == 1 ? 3 + tt[k] : (ts == 2 ? 5 + tt[k] : 9));
+        const bool mirror = (ts == tt[k]) && (is != it[k]);
+        double* oq = p.out[0][kind];
+        double* op = p.out[1][kind];
+        double* ol = p.out[2][kind];
+        const long base_q = (long)b * cnt_s * cnt_t[k];
+        const long e1 = base_q + (long)is * cnt_t[k] + it[k], e2 = base_q + (long)it[k] * cnt_t[k] + is;
         double acc = 0.0;
+        const double* z = p.z ? p.z + (long)b * 2 * nq : nullptr;
         TREPB_UNROLL_SYS
         for (int j = 0; j < nd; ++j) {
-            double pv = ws.p2(j).v;
+            const double qv = ws.fr(j).a;
+            double pv = ws.p2(j).ab[k];
             TREPB_UNROLL_SYS
-            for (int k = 0; k < nd; ++k) pv += T22(k, j) * ws.fr(k).b;
-            acc += z[j] * ws.fr(j).b + z[nq + j] * pv;
+            for (int kk = 0; kk < nd; ++kk) pv += T22(kk, j) * ws.fr(kk).a;
+            if (oq) {
+                oq[e1 * nd + j] = qv;
+                if (mirror) oq[e2 * nd + j] = qv;
+            }
+            if (op) {
+                op[e1 * nd + j] = pv;
+                if (mirror) op[e2 * nd + j] = pv;
+            }
+            if (z) acc += z[j] * qv + z[nq + j] * pv;
         }
-        const bool sx = ts < 2, tx = tt < 2;
-        const int xs = ts == 0 ? is : (ts == 1 ? nq + is : (ts == 2 ? is : nu + is));
-        const int xt = tt == 0 ? it : (tt == 1 ? nq + it : (tt == 2 ? it : nu + it));
-        if (sx && tx) {
-            if (p.zxx) { p.zxx[((long)b * nX + xs) * nX + xt] = acc; p.zxx[((long)b * nX + xt) * nX + xs] = acc; }
-        } else if (sx) {
-            if (p.zxu) p.zxu[((long)b * nX + xs) * nU + xt] = acc;
-        } else {
-            if (p.zuu) { p.zuu[((long)b * nU + xs) * nU + xt] = acc; p.zuu[((long)b * nU + xt) * nU + xs] = acc; }
+        if (z) {
+            // z-contraction in the DSystem layout: X = [Q; p; v], U = [u; rho]  (dsystem.py:320-386)
+            const int nX = 2 * nq, nU = nu + nk;
+            const bool sx = ts < 2, tx = tt[k] < 2;
+            const int xs = ts == 0 ? is : (ts == 1 ? nq + is : (ts == 2 ? is : nu + is));
+            const int xt = tt[k] == 0 ? it[k] : (tt[k] == 1 ? nq + it[k] : (tt[k] == 2 ? it[k] : nu + it[k]));
+            if (sx && tx) {
+                if (p.zxx) { p.zxx[((long)b * nX + xs) * nX + xt] = acc; p.zxx[((long)b * nX + xt) * nX + xs] = acc; }
+            } else if (sx) {
+                if (p.zxu) p.zxu[((long)b * nX + xs) * nU + xt] = acc;
+            } else {
+                if (p.zuu) { p.zuu[((long)b * nU + xs) * nU + xt] = acc; p.zuu[((long)b * nU + xt) * nU + xs] = acc; }
+            }
         }
-    }
-    if (ol) {
-        TREPB_UNROLL_SYS
-        for (int cc = 0; cc < nc; ++cc) {
-            const double lv = ws.hc(cc).v;
-            ol[((base_q + (long)is * cnt_t + it)) * nc + cc] = lv;
-            if (mirror) ol[((base_q + (long)it * cnt_t + is)) * nc + cc] = lv;
+        if (ol) {
+            TREPB_UNROLL_SYS
+            for (int cc = 0; cc < nc; ++cc) {
+                const double lv = ws.hc(cc).v;
+                ol[e1 * nc + cc] = lv;
+                if (mirror) ol[e2 * nc + cc] = lv;
+            }
         }
     }
 }
@@ -186,13 +213,13 @@ template <class Sys>
 struct CtxHD<Sys, true> {
     Sys sys;
     WsStatic<Sys, HD> ws;
-    __device__ __forceinline__ CtxHD(const RtSys&, const char*, int, const WsStridedT<HD>&, long, long) {}
+    __device__ __forceinline__ CtxHD(const RtSys&, const char*, int, const WsStridedT<HDG>&, long, long) {}
 };
 template <class Sys>
 struct CtxHD<Sys, false> {
     RtSys sys;
-    WsStridedT<HD> ws;
-    __device__ __forceinline__ CtxHD(const RtSys& s, const char* dblob, int blob_bytes, const WsStridedT<HD>& w,
+    WsStridedT<HDG> ws;
+    __device__ __forceinline__ CtxHD(const RtSys& s, const char* dblob, int blob_bytes, const WsStridedT<HDG>& w,
                                      long tid, long nthreads) {
         extern __shared__ double smem_[];
         const int n8 = (blob_bytes + 7) / 8;
@@ -208,7 +235,7 @@ struct CtxHD<Sys, false> {
 
 template <class Sys>
 __global__ void __launch_bounds__(128)
-d2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<HD> wsp, const D2Params p) {
+d2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<HDG> wsp, const D2Params p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
     CtxHD<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
@@ -216,19 +243,30 @@ d2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<
     auto& ws = c.ws;
     using Ws = typename std::remove_reference<decltype(ws)>::type;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
-    const long total = p.batch * (long)p.npairs;
+    // work item = (instance, parameter s, block of N parameters t >= s); N = directions per hyper-dual
+    // number of this kernel's workspace type (trepb_hd.h)
+    constexpr int N = (int)(sizeof(typename Ws::Real) / sizeof(double) - 2) / 2;
+    const int nblk = d2_blocks(p.nx, N);
+    const long total = p.batch * (long)nblk;
     for (long g = tid; g < total; g += nth) {
-        const long b = g / p.npairs;
+        const long b = g / nblk;
         if (p.status && p.status[b] != 0) continue;
-        int pr = (int)(g - b * p.npairs), s = 0;
-        while (pr >= p.nx - s) { pr -= p.nx - s; ++s; }
-        deriv2_pair(sys, ws, p, b, s, s + pr);
+        int pr = (int)(g - b * nblk), s = 0;
+        for (;;) {
+            const int nb = (p.nx - s + N - 1) / N;
+            if (pr < nb) break;
+            pr -= nb;
+            ++s;
+        }
+        const int t0 = s + pr * N;
+        const int nt = p.nx - t0 < N ? p.nx - t0 : N;
+        deriv2_block(sys, ws, p, b, s, t0, nt);
     }
 }
 
 template <class Sys>
 struct LaunchersD2 {
-    static cudaError_t run(const LaunchCfg& c, const WsStridedT<HD>& w, const D2Params& p) {
+    static cudaError_t run(const LaunchCfg& c, const WsStridedT<HDG>& w, const D2Params& p) {
         RtSys rs{};
         if (c.sys) rs = *c.sys;
         if (c.smem > 48 * 1024) {

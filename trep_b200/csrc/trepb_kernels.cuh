@@ -126,7 +126,7 @@ struct KernelSet {
     cudaError_t (*proj)(const LaunchCfg&, const ProjParams&);
     // which: 0 step, 1 p2, 2 lin.  blocks_per_sm at (block, smem).
     cudaError_t (*occupancy)(int which, int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
-    cudaError_t (*d2)(const LaunchCfg&, const WsStridedT<HD>&, const D2Params&);
+    cudaError_t (*d2)(const LaunchCfg&, const WsStridedT<HDG>&, const D2Params&);
     cudaError_t (*d2_occupancy)(int block, size_t smem, int* blocks_per_sm, KernelInfo* info);
 };
 
