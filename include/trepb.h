@@ -21,6 +21,8 @@
  *                            second-derivative tensors q2/p2/lambda1 _d{q1,p1,u1,k2}d{q1,p1,u1,k2}.
  *   trepb_project_batch*     DSystem.project / DOptimizer.armijo_simulate: closed-loop rollouts
  *                            (trep/discopt/dsystem.py:426-457, doptimizer.py:405-428).
+ *   trepb_lqr_batch*         discopt.dlqr.solve_tv_lqr (trep/discopt/dlqr.py:9-38), the Riccati sweep of
+ *                            DSystem.calc_feedback_controller (trep/discopt/dsystem.py:474-494).
  *   trepb_linearize_batch*   DSystem.set + fdx + fdu for every k of
  *                            DSystem.linearize_trajectory (trep/discopt/dsystem.py:229-250,
  *                            284-317, 406-423) == solve_DEL + MidpointVI_calc_deriv1
@@ -198,6 +200,32 @@ typedef struct trepb_project_args {
 
 int trepb_project_batch(trepb_system* sys, const trepb_project_args* args);
 int trepb_project_batch_dev(trepb_system* sys, const trepb_project_args* args, void* stream);
+
+/* Time-varying discrete LQR, batched over rollouts: trep.discopt.dlqr.solve_tv_lqr
+ * (trep/discopt/dlqr.py:9-38), the Riccati sweep behind DSystem.calc_feedback_controller
+ * (trep/discopt/dsystem.py:474-494).  It consumes the A / B slabs trepb_linearize_batch_dev wrote
+ * ([rollout][k] order) and produces the gains in the per-candidate layout trepb_project_batch reads,
+ * so linearize -> LQR -> project runs without leaving the GPU.  No system handle is needed.
+ *     P = Q(K);  for k = K-1..0:  gamma = R(k) + B^T P B,  Kp = B^T P A,  K[k] = gamma^-1 Kp,
+ *                                 P = Q(k) + A^T P A - Kp^T K[k],  P = (P + P^T)/2                  */
+typedef struct trepb_lqr_args {
+    int64_t batch;        /* rollouts                                                   */
+    int32_t nsteps;       /* K                                                          */
+    int32_t nX, nU;
+    int32_t q_per_step;   /* 0: Q is one [nX][nX] matrix, 1: Q is [K+1][nX][nX]         */
+    int32_t r_per_step;   /* 0: R is one [nU][nU] matrix, 1: R is [K][nU][nU]           */
+    int32_t _pad;
+    const double* A;      /* [batch][K][nX][nX]                                         */
+    const double* B;      /* [batch][K][nX][nU]                                         */
+    const double* Q;
+    const double* R;
+    double* Kfb;          /* [batch][K][nU][nX] out                                     */
+    double* P0;           /* [batch][nX][nX] out (P at k = 0), may be NULL              */
+    int32_t* status;      /* [batch] 0 ok, -2 singular gamma                            */
+} trepb_lqr_args;
+
+int trepb_lqr_batch(int device, const trepb_lqr_args* args);                   /* host pointers   */
+int trepb_lqr_batch_dev(int device, const trepb_lqr_args* args, void* stream); /* device pointers */
 
 /* p2 from two consecutive configurations (initialize_from_configs). q0,q1: [B][nq] -> p: [B][nd] */
 int trepb_calc_p2_batch(trepb_system* sys, int64_t batch, double dt,

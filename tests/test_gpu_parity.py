@@ -391,3 +391,54 @@ def test_project_puppet_kinematic_feedback(lib, ref):
     assert out["status"][1] != 0 and out["fail_step"][1] == 5
     assert out["status"][0] == 0 and out["status"][2] == 0
     G.assert_close(out["X"][0], want[0].X, "puppet X next to a failing candidate", rtol=1e-7)
+
+
+def test_lqr_sweep_matches_reference(lib, ref):
+    """trepb_lqr_batch against the reference's discopt.dlqr.solve_tv_lqr (dlqr.py:9-38): random
+    stabilisable problems of the marionette's size and of pend-on-cart's, constant and per-step
+    weights, several rollouts in one launch."""
+    from trep.discopt import dlqr
+    rng = np.random.default_rng(21)
+    for nX, nU, K, R_, per_step in ((4, 1, 60, 3, False), (80, 18, 25, 2, True), (7, 3, 40, 5, True)):
+        A = np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (R_, K, nX, nX))
+        B = rng.normal(0, 1.0, (R_, K, nX, nU))
+        if per_step:
+            Qs = np.stack([np.eye(nX) * (1 + 0.1 * k) for k in range(K + 1)])
+            Rs = np.stack([np.eye(nU) * (2 + 0.05 * k) for k in range(K)])
+            Qf, Rf = (lambda k: Qs[k]), (lambda k: Rs[k])
+        else:
+            M = rng.normal(0, 1, (nX, nX)); Qs = M @ M.T + np.eye(nX)
+            Rs = np.eye(nU) * 0.5
+            Qf, Rf = (lambda k: Qs), (lambda k: Rs)
+        Kg, Pg = lib.solve_tv_lqr(A, B, Qs, Rs)
+        for r in range(R_):
+            want = dlqr.solve_tv_lqr(list(A[r]), list(B[r]), Qf, Rf)
+            G.assert_close(Kg[r], np.stack(want.K), "lqr gains nX=%d rollout %d" % (nX, r), rtol=1e-9)
+            G.assert_close(Pg[r], want.P, "lqr P0 nX=%d rollout %d" % (nX, r), rtol=1e-9)
+
+
+def test_feedback_controller_pipeline(lib, ref):
+    """DSystem.calc_feedback_controller + project (dsystem.py:426-457, 474-494) end to end on the GPU
+    (linearize_trajectory -> Riccati sweep -> closed-loop rollout) against the reference doing the
+    same on the host, pend-on-cart."""
+    from trep_b200 import midpointvi as MV, discopt as DO
+    name = "pend_on_cart1"
+    dt, K = 0.01, 50
+    t = dt * np.arange(K + 1)
+    system, mvi = ref.make_mvi(name)
+    rd = ref.discopt.DSystem(mvi, t)
+    X0 = np.zeros(rd.nX); X0[1] = 0.2
+    U0 = 0.3 * np.sin(2 * t[:K])[:, None]
+    X = np.zeros((K + 1, rd.nX)); X[0] = X0
+    for k in range(K):
+        rd.set(X[k], U0[k], k) if k == 0 else rd.step(U0[k])
+        X[k + 1] = rd.f()
+    Kref = rd.calc_feedback_controller(X, U0)
+    d = DO.DSystem(MV.MidpointVI(G.desc(name)), t)
+    Kgpu = d.calc_feedback_controller(X, U0)
+    G.assert_close(Kgpu, np.stack(Kref), "feedback gains", rtol=1e-8)
+    bX = X + np.random.default_rng(2).normal(0, 1e-2, X.shape)
+    want = rd.project(bX, U0, Kref)
+    got = d.project(bX, U0, Kgpu)
+    G.assert_close(got.X, want.X, "projected X", rtol=1e-8)
+    G.assert_close(got.U, want.U, "projected U", rtol=1e-8)

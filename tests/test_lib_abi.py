@@ -34,6 +34,7 @@ def test_ctypes_struct_layout_matches_header():
     # field order/size of the argument structs as declared in include/trepb.h (LP64)
     assert C.sizeof(lib.StepArgs) == 8 + 4 + 4 + 3 * 8 + 11 * 8 + 4 + 4 + 2 * 8
     assert C.sizeof(lib.LinArgs) == 8 + 4 + 4 + 8 + 2 * 8 + 2 * 8 + 6 * 8 + 5 * 8 + 2 * 8 + 12 * 8
+    assert C.sizeof(lib.LqrArgs) == 8 + 6 * 4 + 7 * 8
     assert C.sizeof(lib.ProjectArgs) == 8 + 4 + 4 + 3 * 8 + 3 * 8 + 4 + 4 + 5 * 8
     assert C.sizeof(D.CSysDesc) == 10 * 4 + 17 * 8
 

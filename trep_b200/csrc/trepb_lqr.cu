@@ -1,0 +1,247 @@
+// Time-varying discrete LQR on the device: trep.discopt.dlqr.solve_tv_lqr (trep/discopt/dlqr.py:9-38),
+// the backward Riccati sweep behind DSystem.calc_feedback_controller (trep/discopt/dsystem.py:474-494):
+//
+//     P = Q(K)
+//     for k = K-1 .. 0:   gamma = R(k) + B^T P B ;  Kp = B^T P A ;  K[k] = gamma^-1 Kp
+//                         P = Q(k) + A^T P A - Kp^T K[k] ;  P = (P + P^T) / 2
+//
+// One CTA per rollout (the sweep is sequential in k, rollouts are independent), P, P A and A[k] in
+// shared memory (3 x nX^2 doubles: 154 KB for the marionette's nX = 80), A[k] / B[k] streamed from the
+// slabs the linearize kernel wrote, so the linearization never leaves the GPU; K[k] goes straight into
+// the layout trepb_project_batch reads (per-rollout gains).  Every product has the form
+// C = X^T Y with both operands read along rows (P is symmetric), 4 x 4 register tiles per thread;
+// the nU x nU solve reuses the cooperative LU (trepb_coop_math.cuh) on warp 0 with Kp riding along
+// as extra columns.
+#include <cuda_runtime.h>
+#include <string>
+#include "../../include/trepb.h"
+#include "trepb_coop_math.cuh"
+#include "trepb_err.h"
+
+namespace trepb {
+namespace {
+
+struct LqrParams {
+    long long batch;
+    int K, nX, nU;
+    const double *A, *B, *Q, *R;
+    int q_per_step, r_per_step;
+    double *Kfb, *P0;
+    int* status;
+};
+
+// C[i][j] (op)= sum_m Xt[m][i] * Y[m][j]   for i < M, j < N, m < Kd ; 4 x 4 tiles over the CTA.
+//   mode 0: C = acc   1: C += acc   2: C -= acc
+__device__ __forceinline__ void gemm_tn(double* C, int ldc, const double* Xt, int ldx, const double* Y, int ldy,
+                                        int M, int N, int Kd, int mode) {
+    const int ti = (M + 3) / 4, tj = (N + 3) / 4;
+    for (int tile = threadIdx.x; tile < ti * tj; tile += blockDim.x) {
+        const int i0 = (tile / tj) * 4, j0 = (tile % tj) * 4;
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        const bool full = i0 + 4 <= M && j0 + 4 <= N;
+        if (full) {
+            for (int m = 0; m < Kd; ++m) {
+                double x[4], y[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) { x[a] = Xt[m * ldx + i0 + a]; y[a] = Y[m * ldy + j0 + a]; }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
+            }
+        } else {
+            for (int m = 0; m < Kd; ++m) {
+                double x[4], y[4];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) {
+                    x[a] = i0 + a < M ? Xt[m * ldx + i0 + a] : 0.0;
+                    y[a] = j0 + a < N ? Y[m * ldy + j0 + a] : 0.0;
+                }
+#pragma unroll
+                for (int a = 0; a < 4; ++a)
+#pragma unroll
+                    for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
+            }
+        }
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                if (i0 + a < M && j0 + b < N) {
+                    double* c = C + (i0 + a) * ldc + j0 + b;
+                    if (mode == 0) *c = acc[a][b];
+                    else if (mode == 1) *c += acc[a][b];
+                    else *c -= acc[a][b];
+                }
+            }
+    }
+}
+
+__global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
+    extern __shared__ double sm[];
+    const int nX = p.nX, nU = p.nU, K = p.K;
+    const int ldg = (nU + nX) | 1;                 // [gamma | Kp] augmented, odd leading dimension
+    double* P = sm;                                // [nX][nX]
+    double* T = P + nX * nX;                       // P A, then scratch
+    double* As = T + nX * nX;                      // A[k]
+    double* Bs = As + nX * nX;                     // B[k]            [nX][nU]
+    double* W = Bs + nX * nU;                      // P B             [nX][nU]
+    double* G = W + nX * nU;                       // [gamma | Kp]    [nU][ldg]  -> [LU | K[k]]
+    double* Kp = G + nU * ldg;                     // Kp              [nU][nX]
+    double* scl = Kp + nU * nX;                    // [nU]
+    double* rd = scl + nU;                         // [nU]
+    int* piv = (int*)(rd + nU);                    // [nU] + swp [nU]
+    int* swp = piv + nU;
+    __shared__ int s_fail;
+    for (long r = blockIdx.x; r < p.batch; r += gridDim.x) {
+        const double* Ar = p.A + r * (long)K * nX * nX;
+        const double* Br = p.B + r * (long)K * nX * nU;
+        double* Kr = p.Kfb + r * (long)K * nU * nX;
+        if (threadIdx.x == 0) s_fail = 0;
+        {
+            const double* Qf = p.Q + (p.q_per_step ? (long)K * nX * nX : 0);
+            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) P[e] = Qf[e];
+        }
+        __syncthreads();
+        for (int k = K - 1; k >= 0; --k) {
+            const double* Ak = Ar + (long)k * nX * nX;
+            const double* Bk = Br + (long)k * nX * nU;
+            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) As[e] = Ak[e];
+            for (int e = threadIdx.x; e < nX * nU; e += blockDim.x) Bs[e] = Bk[e];
+            __syncthreads();
+            gemm_tn(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
+            gemm_tn(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
+            __syncthreads();
+            // gamma = R + B^T W ;  Kp = B^T T   into the augmented matrix and a copy of Kp
+            {
+                const double* Rk = p.R + (p.r_per_step ? (long)k * nU * nU : 0);
+                for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rk[e];
+            }
+            __syncthreads();
+            gemm_tn(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1);
+            gemm_tn(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0);
+            __syncthreads();
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) G[(e / nX) * ldg + nU + e % nX] = Kp[e];
+            __syncthreads();
+            // K[k] = gamma^-1 Kp on warp 0 (LU with the right-hand sides riding along, then one column per lane)
+            if (threadIdx.x < 32) {
+                WarpTeam t;
+                const bool ok = team_lu(t, G, ldg, nU, nX, piv, swp, scl, rd, 1e-300);
+                if (!ok) { if (threadIdx.x == 0) s_fail = 1; }
+                else {
+                    for (int c = threadIdx.x; c < nX; c += 32) col_backsolve(G, ldg, nU, rd, G + nU + c, ldg);
+                }
+            }
+            __syncthreads();
+            if (s_fail) break;
+            double* Kk = Kr + (long)k * nU * nX;
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) {
+                const double v = G[(e / nX) * ldg + nU + e % nX];
+                Kk[e] = v;
+                W[e] = v;          // K[k] as [nU][nX] (W is free now: nU * nX doubles)
+            }
+            // P <- Q(k) + A^T T - Kp^T K[k]   (P itself is dead: T and W carried it)
+            {
+                const double* Qk = p.Q + (p.q_per_step ? (long)k * nX * nX : 0);
+                for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) P[e] = Qk[e];
+            }
+            __syncthreads();
+            gemm_tn(P, nX, As, nX, T, nX, nX, nX, nX, 1);
+            __syncthreads();
+            gemm_tn(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);
+            __syncthreads();
+            // P = (P + P^T) / 2
+            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) {
+                const int i = e / nX, j = e % nX;
+                if (i < j) {
+                    const double v = (P[i * nX + j] + P[j * nX + i]) / 2.0;
+                    P[i * nX + j] = v;
+                    P[j * nX + i] = v;
+                }
+            }
+            __syncthreads();
+        }
+        if (p.P0) {
+            double* Pr = p.P0 + r * (long)nX * nX;
+            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) Pr[e] = P[e];
+        }
+        if (threadIdx.x == 0) p.status[r] = s_fail ? ST_SINGULAR : ST_OK;
+        __syncthreads();
+    }
+}
+
+int lqr_fail(int code, const std::string& m) { last_error() = m; return code; }
+
+}  // namespace
+}  // namespace trepb
+
+using namespace trepb;
+
+extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* stream) {
+    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    if (!a->A || !a->B || !a->Q || !a->R || !a->Kfb || !a->status) return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, Kfb and status are required");
+    if (a->batch == 0) return TREPB_OK;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    const int nX = a->nX, nU = a->nU, ldg = (nU + nX) | 1;
+    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * ldg + 4 * (size_t)nU + 8;
+    const size_t smem = doubles * sizeof(double);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+        return lqr_fail(TREPB_ERR_UNSUPPORTED, "state dimension too large for the shared-memory Riccati sweep");
+    e = cudaFuncSetAttribute((const void*)lqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    LqrParams p;
+    p.batch = a->batch; p.K = a->nsteps; p.nX = nX; p.nU = nU;
+    p.A = a->A; p.B = a->B; p.Q = a->Q; p.R = a->R; p.q_per_step = a->q_per_step; p.r_per_step = a->r_per_step;
+    p.Kfb = a->Kfb; p.P0 = a->P0; p.status = a->status;
+    const int tiles = ((nX + 3) / 4) * ((nX + 3) / 4);
+    int block = ((tiles + 31) / 32) * 32;
+    if (block > 512) block = 512;
+    if (block < 64) block = 64;
+    long long grid = a->batch < prop.multiProcessorCount ? a->batch : prop.multiProcessorCount;
+    lqr_kernel<<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    return TREPB_OK;
+}
+
+extern "C" int trepb_lqr_batch(int device, const trepb_lqr_args* a) {
+    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    const size_t R = (size_t)a->batch, K = (size_t)a->nsteps, nX = (size_t)a->nX, nU = (size_t)a->nU;
+    const size_t nA = R * K * nX * nX, nB = R * K * nX * nU, nQ = (a->q_per_step ? K + 1 : 1) * nX * nX,
+                 nR = (a->r_per_step ? K : 1) * nU * nU, nK = R * K * nU * nX, nP = R * nX * nX;
+    double *dA = nullptr, *dB = nullptr, *dQ = nullptr, *dR = nullptr, *dK = nullptr, *dP = nullptr;
+    int* dS = nullptr;
+    int rc = TREPB_OK;
+#define LQ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess && rc == TREPB_OK) rc = lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e_)); } while (0)
+    LQ(cudaMalloc(&dA, nA * 8)); LQ(cudaMalloc(&dB, nB * 8)); LQ(cudaMalloc(&dQ, nQ * 8)); LQ(cudaMalloc(&dR, nR * 8));
+    LQ(cudaMalloc(&dK, nK * 8)); LQ(cudaMalloc(&dP, nP * 8)); LQ(cudaMalloc(&dS, (R ? R : 1) * 4));
+    if (rc == TREPB_OK) {
+        LQ(cudaMemcpy(dA, a->A, nA * 8, cudaMemcpyHostToDevice)); LQ(cudaMemcpy(dB, a->B, nB * 8, cudaMemcpyHostToDevice));
+        LQ(cudaMemcpy(dQ, a->Q, nQ * 8, cudaMemcpyHostToDevice)); LQ(cudaMemcpy(dR, a->R, nR * 8, cudaMemcpyHostToDevice));
+    }
+    if (rc == TREPB_OK) {
+        trepb_lqr_args d = *a;
+        d.A = dA; d.B = dB; d.Q = dQ; d.R = dR; d.Kfb = dK; d.P0 = a->P0 ? dP : nullptr; d.status = dS;
+        rc = trepb_lqr_batch_dev(device, &d, nullptr);
+    }
+    if (rc == TREPB_OK) {
+        LQ(cudaMemcpy(a->Kfb, dK, nK * 8, cudaMemcpyDeviceToHost));
+        if (a->P0) LQ(cudaMemcpy(a->P0, dP, nP * 8, cudaMemcpyDeviceToHost));
+        LQ(cudaMemcpy(a->status, dS, R * 4, cudaMemcpyDeviceToHost));
+    }
+#undef LQ
+    cudaFree(dA); cudaFree(dB); cudaFree(dQ); cudaFree(dR); cudaFree(dK); cudaFree(dP); cudaFree(dS);
+    return rc;
+}

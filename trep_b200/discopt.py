@@ -157,6 +157,20 @@ class DSystem:
             A, B = A[0], B[0]
         return self.linearization_return(A, B)
 
+    def calc_feedback_controller(self, X, U, Q=None, R=None, return_linearization=False):
+        """DSystem.calc_feedback_controller (dsystem.py:474-494): linearize about (X, U), then the
+        time-varying LQR gains (discopt.dlqr.solve_tv_lqr, dlqr.py:9-38) - both on the GPU, for one
+        trajectory or a batch of rollouts.  Q / R: constant matrices or per-step stacks
+        [K+1,nX,nX] / [K,nU,nU] (the reference takes functions Q(k), R(k)); identity by default."""
+        from . import lib
+        A, B = self.linearize_trajectory(X, U)
+        Q = np.eye(self._nX) if Q is None else (np.stack([Q(k) for k in range(A.shape[-3] + 1)]) if callable(Q) else Q)
+        R = np.eye(self._nU) if R is None else (np.stack([R(k) for k in range(A.shape[-3])]) if callable(R) else R)
+        K, _ = lib.solve_tv_lqr(A, B, Q, R, device=self.varint.sys.device)
+        if return_linearization:
+            return K, A, B
+        return K
+
     def project(self, bX, bU, Kproj, use_hint=True):
         """DSystem.project (dsystem.py:426-457) for one candidate or a batch of candidates in one
         launch: X[0] = bX[0]; U[k] = bU[k] - Kproj[k] (X[k] - bX[k]); X[k+1] = f(X[k], U[k], k).

@@ -44,6 +44,13 @@ class ProjectArgs(C.Structure):
                 ("iters", C.c_void_p), ("status", C.c_void_p), ("fail_step", C.c_void_p)]
 
 
+class LqrArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("nsteps", C.c_int32), ("nX", C.c_int32), ("nU", C.c_int32),
+                ("q_per_step", C.c_int32), ("r_per_step", C.c_int32), ("_pad", C.c_int32),
+                ("A", C.c_void_p), ("B", C.c_void_p), ("Q", C.c_void_p), ("R", C.c_void_p),
+                ("Kfb", C.c_void_p), ("P0", C.c_void_p), ("status", C.c_void_p)]
+
+
 RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2_dk2",
        "l1_dq1", "l1_dp1", "l1_du1", "l1_dk2"]
 
@@ -82,6 +89,8 @@ _lib.trepb_step_batch.argtypes = [C.c_void_p, C.POINTER(StepArgs)]
 _lib.trepb_step_batch_dev.argtypes = [C.c_void_p, C.POINTER(StepArgs), C.c_void_p]
 _lib.trepb_project_batch.argtypes = [C.c_void_p, C.POINTER(ProjectArgs)]
 _lib.trepb_project_batch_dev.argtypes = [C.c_void_p, C.POINTER(ProjectArgs), C.c_void_p]
+_lib.trepb_lqr_batch.argtypes = [C.c_int, C.POINTER(LqrArgs)]
+_lib.trepb_lqr_batch_dev.argtypes = [C.c_int, C.POINTER(LqrArgs), C.c_void_p]
 _lib.trepb_linearize_batch.argtypes = [C.c_void_p, C.POINTER(LinArgs)]
 _lib.trepb_linearize_batch_dev.argtypes = [C.c_void_p, C.POINTER(LinArgs), C.c_void_p]
 _lib.trepb_deriv2_batch.argtypes = [C.c_void_p, C.POINTER(D2Args)]
@@ -105,7 +114,7 @@ EXPORTS = [
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
-    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_linearize_batch",
+    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
     "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
@@ -142,6 +151,35 @@ def coop_dims(desc):
     if _lib.trepb_coop_dims(C.byref(cd), out) != 0:
         return None
     return tuple(out)
+
+
+def lqr_raw(on_device, device, batch, nsteps, nX, nU, A, B, Q, R, Kfb, status, P0=None, q_per_step=False,
+            r_per_step=False, stream=None):
+    a = LqrArgs(batch=batch, nsteps=nsteps, nX=nX, nU=nU, q_per_step=1 if q_per_step else 0,
+                r_per_step=1 if r_per_step else 0, A=_ptr(A), B=_ptr(B), Q=_ptr(Q), R=_ptr(R), Kfb=_ptr(Kfb),
+                P0=_ptr(P0), status=_ptr(status))
+    if on_device:
+        _check(_lib.trepb_lqr_batch_dev(device, C.byref(a), stream))
+    else:
+        _check(_lib.trepb_lqr_batch(device, C.byref(a)))
+
+
+def solve_tv_lqr(A, B, Q, R, device=0):
+    """Batched discopt.dlqr.solve_tv_lqr (trep/discopt/dlqr.py:9-38) on the GPU.
+    A [R,K,nX,nX] or [K,nX,nX]; B likewise; Q [nX,nX] or [K+1,nX,nX]; R [nU,nU] or [K,nU,nU].
+    Returns (K [..,K,nU,nX], P0 [..,nX,nX])."""
+    A = np.ascontiguousarray(np.asarray(A, float)); B = np.ascontiguousarray(np.asarray(B, float))
+    single = A.ndim == 3
+    if single:
+        A, B = A[None], B[None]
+    Rn, K, nX = A.shape[0], A.shape[1], A.shape[2]
+    nU = B.shape[3]
+    Q = np.ascontiguousarray(np.asarray(Q, float)); R = np.ascontiguousarray(np.asarray(R, float))
+    Kfb = np.zeros((Rn, K, nU, nX)); P0 = np.zeros((Rn, nX, nX)); status = np.zeros(Rn, np.int32)
+    lqr_raw(False, device, Rn, K, nX, nU, A, B, Q, R, Kfb, status, P0=P0, q_per_step=Q.ndim == 3, r_per_step=R.ndim == 3)
+    if np.any(status != 0):
+        raise TrepbError(0, "singular gamma in the Riccati sweep of rollout(s) %s" % np.flatnonzero(status != 0)[:8])
+    return (Kfb[0], P0[0]) if single else (Kfb, P0)
 
 
 def specialized_names():
