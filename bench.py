@@ -348,6 +348,30 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                 "kernel": s.kernel_name})
     for b_ in (dbX, dbU, dK, oX, oU, pit, pst):
         b_.free()
+    # Riccati sweep (discopt.dlqr.solve_tv_lqr) at the marionette's size, one CTA per rollout
+    Rl, Kl = 296, 64
+    Al = up(np.eye(nX)[None, None] + rng.normal(0, 0.03, (Rl, Kl, nX, nX)))
+    Bl = up(rng.normal(0, 1.0, (Rl, Kl, nX, nU)))
+    Ql, Rr = up(np.eye(nX)), up(np.eye(nU))
+    Kl_out = lib.DeviceBuffer(device, (Rl, Kl, nU, nX)); lst = lib.DeviceBuffer(device, (Rl,), np.int32)
+    import time as _t
+    lib.lqr_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Rr, Kl_out, lst)
+    lib.synchronize(device)
+    t0_ = _t.perf_counter()
+    for rep in range(3):
+        lib.lqr_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Rr, Kl_out, lst)
+    lib.synchronize(device)
+    tl = (_t.perf_counter() - t0_) / 3 * 1e3
+    fl_step = 2.0 * (2 * nX ** 3 + 3 * nX * nX * nU + nU * nU * nX) + 2.0 * nU * nU * (nU / 3.0 + nX)
+    out.append({"metric": "Riccati steps/s (discopt.dlqr.solve_tv_lqr at the marionette's size nX=%d nU=%d, %d rollouts x %d steps)" % (nX, nU, Rl, Kl),
+                "value": Rl * Kl / tl * 1e3, "unit": "Riccati steps/s", "batch": Rl, "ms": tl,
+                "ok_fraction": float((lst.download() == 0).mean()),
+                "roofline": {"bound": "fp64", "achieved": fl_step * Rl * Kl / (tl * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": fl_step * Rl * Kl / (tl * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": fl_step,
+                             "note": "host-timed over 3 launches (the call has no system handle to carry CUDA events); "
+                                     "flops counted from the matrix shapes"}})
+    for b_ in (Al, Bl, Ql, Rr, Kl_out, lst):
+        b_.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
     Bd = 1024
     z = up(rng.normal(0, 1, (Bd, d.nX)))

@@ -10,8 +10,9 @@
 // slabs the linearize kernel wrote, so the linearization never leaves the GPU; K[k] goes straight into
 // the layout trepb_project_batch reads (per-rollout gains).  Every product has the form
 // C = X^T Y with both operands read along rows (P is symmetric), 4 x 4 register tiles per thread;
-// the nU x nU solve reuses the cooperative LU (trepb_coop_math.cuh) on warp 0 with Kp riding along
-// as extra columns.
+// the nU x nU factorization reuses the cooperative LU (trepb_coop_math.cuh) on warp 0, the nX
+// right-hand sides are then solved one per thread; A[k-1], B[k-1] and Q(k) are fetched with cp.async
+// while the current step is still multiplying.
 #include <cuda_runtime.h>
 #include <string>
 #include "../../include/trepb.h"
@@ -32,10 +33,17 @@ struct LqrParams {
 
 // C[i][j] (op)= sum_m Xt[m][i] * Y[m][j]   for i < M, j < N, m < Kd ; 4 x 4 tiles over the CTA.
 //   mode 0: C = acc   1: C += acc   2: C -= acc
+// VEC: ldx, ldy even and both operands 16-byte aligned -> the four operand values of a tile row come
+// in as two 128-bit shared-memory loads each.
+template <bool VEC>
 __device__ __forceinline__ void gemm_tn(double* C, int ldc, const double* Xt, int ldx, const double* Y, int ldy,
-                                        int M, int N, int Kd, int mode) {
+                                        int M, int N, int Kd, int mode, int t0 = 0, int nt = 0) {
+    // threads t0 .. t0+nt-1 of the CTA share the tiles (default: the whole CTA)
+    if (nt == 0) nt = blockDim.x;
+    const int me = (int)threadIdx.x - t0;
+    if (me < 0 || me >= nt) return;
     const int ti = (M + 3) / 4, tj = (N + 3) / 4;
-    for (int tile = threadIdx.x; tile < ti * tj; tile += blockDim.x) {
+    for (int tile = me; tile < ti * tj; tile += nt) {
         const int i0 = (tile / tj) * 4, j0 = (tile % tj) * 4;
         double acc[4][4];
 #pragma unroll
@@ -44,14 +52,25 @@ __device__ __forceinline__ void gemm_tn(double* C, int ldc, const double* Xt, in
             for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
         const bool full = i0 + 4 <= M && j0 + 4 <= N;
         if (full) {
+            const double* xp = Xt + i0;
+            const double* yp = Y + j0;
+#pragma unroll 4
             for (int m = 0; m < Kd; ++m) {
                 double x[4], y[4];
+                if (VEC) {
+                    const double2 x01 = *reinterpret_cast<const double2*>(xp), x23 = *reinterpret_cast<const double2*>(xp + 2);
+                    const double2 y01 = *reinterpret_cast<const double2*>(yp), y23 = *reinterpret_cast<const double2*>(yp + 2);
+                    x[0] = x01.x; x[1] = x01.y; x[2] = x23.x; x[3] = x23.y;
+                    y[0] = y01.x; y[1] = y01.y; y[2] = y23.x; y[3] = y23.y;
+                } else {
 #pragma unroll
-                for (int a = 0; a < 4; ++a) { x[a] = Xt[m * ldx + i0 + a]; y[a] = Y[m * ldy + j0 + a]; }
+                    for (int a = 0; a < 4; ++a) { x[a] = xp[a]; y[a] = yp[a]; }
+                }
 #pragma unroll
                 for (int a = 0; a < 4; ++a)
 #pragma unroll
                     for (int b = 0; b < 4; ++b) acc[a][b] += x[a] * y[b];
+                xp += ldx; yp += ldy;
             }
         } else {
             for (int m = 0; m < Kd; ++m) {
@@ -81,18 +100,35 @@ __device__ __forceinline__ void gemm_tn(double* C, int ldc, const double* Xt, in
     }
 }
 
+// global -> shared copy that does not pass through registers (cp.async): issued early, waited for late,
+// so the next step's A[k], B[k] and Q(k) arrive while the current step is still multiplying
+__device__ __forceinline__ void async_copy(double* dst, const double* src, int n) {
+    const unsigned d0 = (unsigned)__cvta_generic_to_shared(dst);
+    if ((((unsigned long long)src | (unsigned long long)d0) & 15ull) == 0ull && (n & 1) == 0) {
+        for (int e = threadIdx.x; e < n / 2; e += blockDim.x)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d0 + 16u * e), "l"(src + 2 * e) : "memory");
+    } else {
+        for (int e = threadIdx.x; e < n; e += blockDim.x)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d0 + 8u * e), "l"(src + e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <bool VEC>
 __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
-    extern __shared__ double sm[];
+    extern __shared__ __align__(16) double sm[];
     const int nX = p.nX, nU = p.nU, K = p.K;
-    const int ldg = (nU + nX) | 1;                 // [gamma | Kp] augmented, odd leading dimension
+    const int ldg = nU | 1;                        // gamma, odd leading dimension (LU row accesses)
     double* P = sm;                                // [nX][nX]
-    double* T = P + nX * nX;                       // P A, then scratch
+    double* T = P + nX * nX;                       // P A
     double* As = T + nX * nX;                      // A[k]
     double* Bs = As + nX * nX;                     // B[k]            [nX][nU]
-    double* W = Bs + nX * nU;                      // P B             [nX][nU]
-    double* G = W + nX * nU;                       // [gamma | Kp]    [nU][ldg]  -> [LU | K[k]]
-    double* Kp = G + nU * ldg;                     // Kp              [nU][nX]
-    double* scl = Kp + nU * nX;                    // [nU]
+    double* W = Bs + nX * nU;                      // P B [nX][nU], then K[k] [nU][nX]
+    double* Kp = W + nX * nU;                      // Kp = B^T P A    [nU][nX]
+    double* Rs = Kp + nU * nX;                     // R(k)            [nU][nU]
+    double* G = Rs + ((nU * nU + 1) & ~1);         // gamma -> its LU [nU][ldg]
+    double* scl = G + ((nU * ldg + 1) & ~1);       // [nU]
     double* rd = scl + nU;                         // [nU]
     int* piv = (int*)(rd + nU);                    // [nU] + swp [nU]
     int* swp = piv + nU;
@@ -102,69 +138,60 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
         const double* Br = p.B + r * (long)K * nX * nU;
         double* Kr = p.Kfb + r * (long)K * nU * nX;
         if (threadIdx.x == 0) s_fail = 0;
-        {
-            const double* Qf = p.Q + (p.q_per_step ? (long)K * nX * nX : 0);
-            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) P[e] = Qf[e];
-        }
-        __syncthreads();
+        async_copy(P, p.Q + (p.q_per_step ? (long)K * nX * nX : 0), nX * nX);     // P = Q(K)
+        async_copy(As, Ar + (long)(K - 1) * nX * nX, nX * nX);
+        async_copy(Bs, Br + (long)(K - 1) * nX * nU, nX * nU);
+        async_copy(Rs, p.R + (p.r_per_step ? (long)(K - 1) * nU * nU : 0), nU * nU);
         for (int k = K - 1; k >= 0; --k) {
-            const double* Ak = Ar + (long)k * nX * nX;
-            const double* Bk = Br + (long)k * nX * nU;
-            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) As[e] = Ak[e];
-            for (int e = threadIdx.x; e < nX * nU; e += blockDim.x) Bs[e] = Bk[e];
+            async_wait();                                          // A[k], B[k], R(k) (and P) have landed
             __syncthreads();
-            gemm_tn(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
-            gemm_tn(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
+            gemm_tn<VEC>(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
+            gemm_tn<VEC>(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
+            for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rs[e];
             __syncthreads();
-            // gamma = R + B^T W ;  Kp = B^T T   into the augmented matrix and a copy of Kp
-            {
-                const double* Rk = p.R + (p.r_per_step ? (long)k * nU * nU : 0);
-                for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rk[e];
-            }
-            __syncthreads();
-            gemm_tn(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1);
-            gemm_tn(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0);
-            __syncthreads();
-            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) G[(e / nX) * ldg + nU + e % nX] = Kp[e];
-            __syncthreads();
-            // K[k] = gamma^-1 Kp on warp 0 (LU with the right-hand sides riding along, then one column per lane)
+            async_copy(P, p.Q + (p.q_per_step ? (long)k * nX * nX : 0), nX * nX);   // P is dead: start P <- Q(k)
+            // warp 0: gamma = R + B^T P B and its LU;  the other warps meanwhile: Kp = B^T P A
             if (threadIdx.x < 32) {
+                gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 32);
+                __syncwarp();
                 WarpTeam t;
-                const bool ok = team_lu(t, G, ldg, nU, nX, piv, swp, scl, rd, 1e-300);
-                if (!ok) { if (threadIdx.x == 0) s_fail = 1; }
-                else {
-                    for (int c = threadIdx.x; c < nX; c += 32) col_backsolve(G, ldg, nU, rd, G + nU + c, ldg);
-                }
+                if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && threadIdx.x == 0) s_fail = 1;
+            } else {
+                gemm_tn<VEC>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 32, (int)blockDim.x - 32);
             }
             __syncthreads();
             if (s_fail) break;
+            // K[k] = gamma^-1 Kp, one right-hand side per thread (W is free: it becomes K[k], [nU][nX])
+            for (int c = threadIdx.x; c < nX; c += blockDim.x) {
+                for (int i = 0; i < nU; ++i) W[i * nX + c] = Kp[i * nX + c];
+                col_solve(G, ldg, nU, swp, rd, W + c, nX);
+            }
+            __syncthreads();
             double* Kk = Kr + (long)k * nU * nX;
-            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) {
-                const double v = G[(e / nX) * ldg + nU + e % nX];
-                Kk[e] = v;
-                W[e] = v;          // K[k] as [nU][nX] (W is free now: nU * nX doubles)
-            }
-            // P <- Q(k) + A^T T - Kp^T K[k]   (P itself is dead: T and W carried it)
-            {
-                const double* Qk = p.Q + (p.q_per_step ? (long)k * nX * nX : 0);
-                for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) P[e] = Qk[e];
-            }
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) Kk[e] = W[e];
+            async_wait();                                          // Q(k) is in P
             __syncthreads();
-            gemm_tn(P, nX, As, nX, T, nX, nX, nX, nX, 1);
+            gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);     // P += A^T (P A)
             __syncthreads();
-            gemm_tn(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);
+            if (k > 0) {                                           // A, B are dead: fetch the next step's
+                async_copy(As, Ar + (long)(k - 1) * nX * nX, nX * nX);
+                async_copy(Bs, Br + (long)(k - 1) * nX * nU, nX * nU);
+                if (p.r_per_step) async_copy(Rs, p.R + (long)(k - 1) * nU * nU, nU * nU);
+            }
+            gemm_tn<VEC>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);     // P -= Kp^T K[k]
             __syncthreads();
             // P = (P + P^T) / 2
             for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) {
-                const int i = e / nX, j = e % nX;
+                const int i = e / nX, j = e - i * nX;
                 if (i < j) {
                     const double v = (P[i * nX + j] + P[j * nX + i]) / 2.0;
                     P[i * nX + j] = v;
                     P[j * nX + i] = v;
                 }
             }
-            __syncthreads();
         }
+        async_wait();
+        __syncthreads();
         if (p.P0) {
             double* Pr = p.P0 + r * (long)nX * nX;
             for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) Pr[e] = P[e];
@@ -188,15 +215,18 @@ extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* st
     if (a->batch == 0) return TREPB_OK;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
-    const int nX = a->nX, nU = a->nU, ldg = (nU + nX) | 1;
-    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * ldg + 4 * (size_t)nU + 8;
+    const int nX = a->nX, nU = a->nU, ldg = nU | 1;
+    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * nU + (size_t)nU * ldg + 4 * (size_t)nU + 16;
     const size_t smem = doubles * sizeof(double);
-    cudaDeviceProp prop;
-    e = cudaGetDeviceProperties(&prop, device);
+    int smem_optin = 0, sms = 0;
+    e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
-    if (smem > (size_t)prop.sharedMemPerBlockOptin)
+    if (smem > (size_t)smem_optin)
         return lqr_fail(TREPB_ERR_UNSUPPORTED, "state dimension too large for the shared-memory Riccati sweep");
-    e = cudaFuncSetAttribute((const void*)lqr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const bool vec = nX % 2 == 0 && nU % 2 == 0;   // every operand block then starts 16-byte aligned with an even row length
+    const void* fn = vec ? (const void*)lqr_kernel<true> : (const void*)lqr_kernel<false>;
+    e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     LqrParams p;
     p.batch = a->batch; p.K = a->nsteps; p.nX = nX; p.nU = nU;
@@ -206,8 +236,9 @@ extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* st
     int block = ((tiles + 31) / 32) * 32;
     if (block > 512) block = 512;
     if (block < 64) block = 64;
-    long long grid = a->batch < prop.multiProcessorCount ? a->batch : prop.multiProcessorCount;
-    lqr_kernel<<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
+    const long long grid = a->batch < sms ? a->batch : sms;
+    if (vec) lqr_kernel<true><<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
+    else lqr_kernel<false><<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     return TREPB_OK;
