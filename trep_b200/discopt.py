@@ -163,13 +163,51 @@ class DSystem:
         trajectory or a batch of rollouts.  Q / R: constant matrices or per-step stacks
         [K+1,nX,nX] / [K,nU,nU] (the reference takes functions Q(k), R(k)); identity by default."""
         from . import lib
-        A, B = self.linearize_trajectory(X, U)
-        Q = np.eye(self._nX) if Q is None else (np.stack([Q(k) for k in range(A.shape[-3] + 1)]) if callable(Q) else Q)
-        R = np.eye(self._nU) if R is None else (np.stack([R(k) for k in range(A.shape[-3])]) if callable(R) else R)
-        K, _ = lib.solve_tv_lqr(A, B, Q, R, device=self.varint.sys.device)
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        single = X.ndim == 2
+        Xb, Ub = (X[None], U[None]) if single else (X, U)
+        Rn, K = Xb.shape[0], Xb.shape[1] - 1
+        Q = np.eye(self._nX) if Q is None else (np.stack([Q(k) for k in range(K + 1)]) if callable(Q) else np.asarray(Q, float))
+        R = np.eye(self._nU) if R is None else (np.stack([R(k) for k in range(K)]) if callable(R) else np.asarray(R, float))
+        sys_, dev = self.varint.sys, self.varint.sys.device
+        nX, nU, nq, nd = self._nX, self._nU, self._nQ, self._np
+        n = Rn * K
+        up = lambda a, dt=np.float64: lib.DeviceBuffer(dev, a.shape, dt).upload(np.ascontiguousarray(a, dtype=dt))
+        Xk = Xb[:, :K].reshape(n, nX)
+        # inputs of the n = rollouts x steps independent linearizations, resident in HBM
+        dq1, dp1 = up(Xk[:, :nq]), up(Xk[:, nq:nq + nd])
+        du1 = up(Ub[:, :K, :self._nu].reshape(n, -1)) if self._nu else None
+        dk2 = up(Ub[:, :K, self._nu:].reshape(n, -1)) if self._nv else None
+        dhint = up(Xb[:, 1:K + 1, :nd].reshape(n, nd))
+        dt1, dt2 = up(np.tile(self._time[:K], Rn)), up(np.tile(self._time[1:K + 1], Rn))
+        dA, dB = lib.DeviceBuffer(dev, (n, nX, nX)), lib.DeviceBuffer(dev, (n, nX, nU))
+        dst = lib.DeviceBuffer(dev, (n,), np.int32)
+        dQ, dR = up(Q), up(R)
+        dK, dls = lib.DeviceBuffer(dev, (Rn, K, nU, nX)), lib.DeviceBuffer(dev, (Rn,), np.int32)
+        bufs = [b for b in (dq1, dp1, du1, dk2, dhint, dt1, dt2, dA, dB, dst, dQ, dR, dK, dls) if b is not None]
+        try:
+            # linearize -> Riccati sweep without the A / B slabs leaving the GPU
+            sys_.linearize_raw(True, n, dq1, dp1, du1, dk2, dst, t1=dt1, t2=dt2, q2_guess=dhint, A=dA, B=dB,
+                               tolerance=self.varint.tolerance)
+            lib.lqr_raw(True, dev, Rn, K, nX, nU, dA, dB, dQ, dR, dK, dls, q_per_step=Q.ndim == 3, r_per_step=R.ndim == 3)
+            lib.synchronize(dev)
+            status, ls = dst.download(), dls.download()
+            if np.any(status != 0):
+                raise ConvergenceError("%d of %d linearizations failed" % (int(np.sum(status != 0)), n), status)
+            if np.any(ls != 0):
+                raise ConvergenceError("singular gamma in the Riccati sweep", ls)
+            Kfb = dK.download()
+            A = dA.download().reshape(Rn, K, nX, nX) if return_linearization else None
+            B = dB.download().reshape(Rn, K, nX, nU) if return_linearization else None
+        finally:
+            for b in bufs:
+                b.free()
+        if single:
+            Kfb = Kfb[0]
+            A, B = (A[0], B[0]) if return_linearization else (None, None)
         if return_linearization:
-            return K, A, B
-        return K
+            return Kfb, A, B
+        return Kfb
 
     def project(self, bX, bU, Kproj, use_hint=True):
         """DSystem.project (dsystem.py:426-457) for one candidate or a batch of candidates in one
