@@ -105,6 +105,10 @@ typedef struct trepb_system trepb_system; /* opaque */
 #define TREPB_FLAG_NO_COOP 2        /* table-driven systems: always one thread per instance */
 #define TREPB_FLAG_FORCE_COOP 4     /* table-driven systems: always the cooperative kernels (one warp per
                                        instance, workspace in shared memory); fails if they do not apply */
+#define TREPB_FLAG_D2_PAIRWISE 8    /* table-driven systems: second derivatives by one hyper-dual residual
+                                       evaluation per parameter pair (the scheme the small specialised
+                                       systems use) instead of one dual evaluation of the Jacobian tables
+                                       per parameter followed by a contraction */
 
 int  trepb_abi_version(void);
 const char* trepb_last_error(void);

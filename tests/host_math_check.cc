@@ -8,6 +8,7 @@
 #include "../trep_b200/csrc/trepb_kernels.cuh"
 #include "../trep_b200/csrc/trepb_pack.h"
 #include "../trep_b200/csrc/trepb_coop_math.cuh"
+#include "../trep_b200/csrc/trepb_d2jac.cuh"
 
 using namespace trepb;
 
@@ -144,7 +145,7 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     // several directions per residual evaluation (the kernels use HDG, trepb_hd.h; the host check
     // exercises the N-direction arithmetic with N = 7)
     WsStridedT<HDn<7>> wh;
-    const int n = wh.layout(s.nf, nd, nk, nu, nc, true);
+    const int n = wh.layout(s.nf, nd, nk, nu, nc, 1);
     std::vector<HDn<7>> slab(n + 1);
     wh.base = slab.data();
     wh.stride = 1;
@@ -158,6 +159,88 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
     for (int a = 0; a < p.nx; ++a)
         for (int b0 = a; b0 < p.nx; b0 += 7) deriv2_block(s, wh, p, 0, a, b0, p.nx - b0 < 7 ? p.nx - b0 : 7);
+    return 0;
+}
+
+// Second derivatives through the O(nx) formulation (trepb_d2jac.cuh): per parameter s one dual
+// evaluation of the Jacobian tables (pass A), then per pair the same contraction + solve function
+// the d2solve kernel runs (pass B).  method-independent outputs: d2[30] as in trepb_d2_args.
+namespace {
+struct VecSink {
+    std::vector<double>* v;
+    void push(double x) { v->push_back(x); }
+};
+}  // namespace
+int th_deriv2_jac(const trepb_sysdesc* d, double t1, double t2, double tol, int maxit,
+                  const double* q1, const double* p1, const double* u1, const double* k2,
+                  const double* q2_guess, const double* lam_guess, double** d2) {
+    Host h;
+    if (!h.init(d)) return -100;
+    RtSys& s = h.sys;
+    WsStrided& ws = h.ws;
+    const int nd = s.nd, nk = s.nk, nq = nd + nk, nu = s.nu, nc = s.nc;
+    for (int i = 0; i < nq; ++i) { ws.q1(i) = q1[i]; ws.q2(i) = q1[i]; }
+    for (int i = 0; i < nd; ++i) { ws.p1(i) = p1[i]; if (q2_guess) ws.q2(i) = q2_guess[i]; }
+    for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
+    for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
+    for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
+    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    if (it < 0) return it;
+    std::vector<double> q2(nq), lam(nc + 1), uu(nu + 1);
+    for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
+    for (int c = 0; c < nc; ++c) lam[c] = ws.lam(c);
+    for (int i = 0; i < nu; ++i) uu[i] = u1[i];
+    const int cnt[4] = {nq, nd, nu, nk};
+    std::vector<double> qd[4], ld[4], pd[4];
+    for (int i = 0; i < 4; ++i) { qd[i].assign(cnt[i] * nd + 1, 0.0); pd[i].assign(cnt[i] * nd + 1, 0.0); ld[i].assign(cnt[i] * nc + 1, 0.0); }
+    Deriv1Out o;
+    o.q2_dq1 = qd[0].data(); o.q2_dp1 = qd[1].data(); o.q2_du1 = qd[2].data(); o.q2_dk2 = qd[3].data();
+    o.p2_dq1 = pd[0].data(); o.p2_dp1 = pd[1].data(); o.p2_du1 = pd[2].data(); o.p2_dk2 = pd[3].data();
+    o.l1_dq1 = ld[0].data(); o.l1_dp1 = ld[1].data(); o.l1_du1 = ld[2].data(); o.l1_dk2 = ld[3].data();
+    o.A = nullptr; o.B = nullptr; o.es = 1;
+    int rc = deriv1(s, ws, t1, t2, o, true);
+    if (rc) return rc;
+    AuxLayout al;
+    al.set(nd, nc);
+    std::vector<double> aux(al.size + 1);
+    export_aux(s, ws, aux.data());
+    WsStridedT<Dual> wd;
+    const int n = wd.layout(s.nf, nd, nk, nu, nc, 2);
+    std::vector<Dual> slab(n + 1);
+    wd.base = slab.data();
+    wd.stride = 1;
+    D2Params p;
+    p.batch = 1; p.nx = nq + nd + nu + nk; p.npairs = p.nx * (p.nx + 1) / 2;
+    p.t1s = t1; p.dts = t2 - t1; p.t1 = &t1; p.t2 = &t2;
+    p.q1 = q1; p.u1 = uu.data(); p.q2 = q2.data(); p.lam = lam.data();
+    for (int i = 0; i < 4; ++i) { p.q2_d[i] = qd[i].data(); p.l1_d[i] = ld[i].data(); }
+    p.aux = aux.data(); p.auxl = al; p.status = nullptr;
+    p.z = nullptr; p.zxx = p.zxu = p.zuu = nullptr;
+    for (int w = 0; w < 3; ++w) for (int k = 0; k < 10; ++k) p.out[w][k] = d2[10 * w + k];
+    JacLayout jl;
+    jl.set(nd, nk, nu, nc);
+    std::vector<double> G, vec(3 * nd + 3 * nc + 1);
+    std::vector<uint8_t> nzb(NzMaps::bytes(nd, nk) + 8);
+    NzMaps nz;
+    nz.place(nzb.data(), nd, nk);
+    d2jac_build_nz(s, nz, 0, 1);
+    // poison the workspace: entries outside the structure maps must never be read
+    for (auto& e : slab) e = Dual(1e300, -1e300);
+    for (int a = 0; a < p.nx; ++a) {
+        d2jac_eval(s, wd, nz, p, 0, a);
+        G.clear();
+        VecSink sink{&G};
+        d2jac_emit(s, wd, nz, t2 - t1, sink);
+        if ((int)G.size() != jl.size) return -300;
+        D2Pair P;
+        std::vector<double> Jd(nd * nd + 1), Hd(nd * nd + 1);
+        for (int i = 0; i < nd * nd; ++i) { Jd[i] = G[jl.o_q + 4 * i + 1]; Hd[i] = G[jl.o_q + 4 * i + 3]; }
+        P.Jd = Jd.data(); P.Hd = Hd.data(); P.JL = G.data() + jl.o_jl; P.JC = G.data() + jl.o_jc;
+        P.Grow = G.data(); P.aux = aux.data(); P.z = nullptr; P.jl = jl; P.al = al;
+        double* y = vec.data();
+        double *lt = y + nd, *c = lt + nc, *x = c + nd, *hh = x + nd, *hx = hh + nc;
+        for (int b = a; b < p.nx; ++b) d2_pair(P, p, 0, nd, nk, nu, nc, a, b, y, lt, c, x, hh, hx, 1);
+    }
     return 0;
 }
 

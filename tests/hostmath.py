@@ -15,7 +15,7 @@ SO = os.path.join(HERE, "_build", "libhostmath.so")
 SRC = os.path.join(HERE, "host_math_check.cc")
 DEPS = [SRC] + [os.path.join(ROOT, "trep_b200", "csrc", f)
                 for f in ("trepb_math.cuh", "trepb_sys.h", "trepb_ws.h", "trepb_pack.h", "trepb_hd.h",
-                          "trepb_d2.cuh", "trepb_kernels.cuh", "trepb_coop_math.cuh", "trepb_coop_sys.h", "trepb_coop.h")]
+                          "trepb_d2.cuh", "trepb_d2jac.cuh", "trepb_kernels.cuh", "trepb_coop_math.cuh", "trepb_coop_sys.h", "trepb_coop.h")]
 
 _lib = None
 
@@ -105,7 +105,7 @@ D2_KINDS = ["dq1dq1", "dq1dp1", "dq1du1", "dq1dk2", "dp1dp1", "dp1du1", "dp1dk2"
 D2_WHICH = ["q2", "p2", "l1"]
 
 
-def deriv2(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200):
+def deriv2(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-10, maxit=200, method="pair"):
     lib = load()
     cd, keep = D.to_c(desc)
     q1, p1, u1, k2 = _c(q1), _c(p1), _c(u1), _c(k2)
@@ -120,8 +120,9 @@ def deriv2(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, tol=1e-1
             out[w + "_" + kd] = (buf, sh)
             ptrs.append(_dp(buf))
     arr = (C.POINTER(C.c_double) * 30)(*ptrs)
-    lib.th_deriv2.restype = C.c_int
-    rc = lib.th_deriv2(C.byref(cd), C.c_double(t1), C.c_double(t2), C.c_double(tol), C.c_int(maxit),
+    fn = lib.th_deriv2 if method == "pair" else lib.th_deriv2_jac
+    fn.restype = C.c_int
+    rc = fn(C.byref(cd), C.c_double(t1), C.c_double(t2), C.c_double(tol), C.c_int(maxit),
                        _dp(q1), _dp(p1), _dp(u1), _dp(k2), _dp(q2g), _dp(lg), arr)
     res = {n: b[:int(np.prod(sh))].reshape(sh) for n, (b, sh) in out.items()}
     res["rc"] = rc

@@ -247,7 +247,9 @@ D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pen
 def test_golden_second_derivatives(lib, name):
     """Every second-derivative tensor against the reference's _calc_deriv2 (golden cases)."""
     g = G.golden(name)
-    for label, s in _systems(lib, name):
+    flavours = _systems(lib, name) + [("general/pairwise", lib.System(G.desc(name), specialize=False, cooperative=False,
+                                                                     d2_pairwise=True))]
+    for label, s in flavours:
         out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
                        t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
         assert np.all(out["status"] == 0)
@@ -263,14 +265,51 @@ def test_puppet_second_derivatives(lib):
     c = int(g2["case_index"][0])
     sl = slice(c, c + 1)
     # the second-derivative kernel consumes the factorizations the linearize kernel exports:
-    # check both producers (cooperative and thread-per-instance)
-    for coop in (True, False):
-        s = lib.System(G.desc("puppet"), cooperative=coop)
+    # check both producers (cooperative and thread-per-instance) and both second-derivative schemes
+    # (dual Jacobian tables per parameter + contraction; hyper-dual residual per parameter pair)
+    for coop, pairwise in ((True, False), (False, False), (True, True)):
+        s = lib.System(G.desc("puppet"), cooperative=coop, d2_pairwise=pairwise)
         out = s.deriv2(g["case_q1"][sl], g["case_p1"][sl], None, g["case_k2"][sl], t1=g["case_t1"][sl],
                        t2=g["case_t2"][sl], q2_guess=g["case_q2_guess"][sl], lambda_guess=g["case_lambda_guess"][sl])
         assert out["status"][0] == 0
         for n in s.d2_shapes(1):
-            G.assert_close(out[n], g2["case_" + n], "puppet[coop=%s] %s" % (coop, n))
+            G.assert_close(out[n], g2["case_" + n], "puppet[coop=%s pairwise=%s] %s" % (coop, pairwise, n))
+
+
+def test_puppet_second_derivative_schemes_agree_on_a_ragged_batch(lib):
+    """Marionette, ragged batch with one instance that cannot converge (status != 0 must be skipped,
+    not abort the batch): the per-parameter scheme (dual Jacobian tables + contraction) and the
+    per-pair scheme (hyper-dual residual) give the same tensors and the same z-contracted forms."""
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    rng = np.random.default_rng(5)
+    B = 37
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+    q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
+    q1[:, :d.nd] += rng.normal(0, 0.01, (B, d.nd)); p1 += rng.normal(0, 0.01, (B, d.nd))
+    k2 = g["roll_k2"][idx].copy(); lam = g["roll_lambda"][idx - 1].copy()
+    q1[3] = np.nan      # a broken instance
+    z = rng.normal(0, 1, (B, d.nX))
+    outs = []
+    for pairwise in (False, True):
+        s = lib.System(d, d2_pairwise=pairwise)
+        outs.append(s.deriv2(q1, p1, None, k2, t1=0.0, dt=0.01, lambda_guess=lam, z=z))
+    a, b = outs
+    assert np.array_equal(a["status"], b["status"]) and a["status"][3] != 0
+    ok = a["status"] == 0
+    assert ok.sum() == B - 1
+    for n in list(lib.System(d).d2_shapes(1)) + ["fdxdx", "fdxdu", "fdudu"]:
+        x, y = a[n][ok], b[n][ok]
+        if x.size == 0:
+            continue
+        assert np.max(np.abs(x - y)) <= 1e-9 * max(1.0, np.max(np.abs(y))), n
+    # the z-contracted forms are the contraction of the tensors (dsystem.py:320-386)
+    nq, nd = d.nq, d.nd
+    i = int(np.flatnonzero(ok)[0])
+    zz = z[i]
+    want = np.einsum("abj,j->ab", a["q2_dq1dq1"][i], zz[:nd]) + np.einsum("abj,j->ab", a["p2_dq1dq1"][i], zz[nq:nq + nd])
+    got = a["fdxdx"][i][:nq, :nq]
+    assert np.max(np.abs(got - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
 
 
 def test_second_derivatives_by_finite_differences_where_the_reference_has_none(lib):

@@ -139,16 +139,18 @@ def test_puppet_rollout():
 D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"]
 
 
+@pytest.mark.parametrize("method", ["pair", "jac"])
 @pytest.mark.parametrize("name", D2_SYSTEMS)
-def test_second_derivatives(name):
-    """Hyper-dual second derivatives (the per-pair function of the d2 kernel) against the
-    reference's _calc_deriv2 tensors."""
+def test_second_derivatives(name, method):
+    """Second derivatives against the reference's _calc_deriv2 tensors: "pair" = hyper-dual residual
+    per parameter pair (trepb_d2.cuh), "jac" = dual Jacobian tables per parameter + contraction
+    (trepb_d2jac.cuh)."""
     g = G.golden(name)
     d = G.desc(name)
     for c in range(min(4, g["case_q1"].shape[0])):
         out = H.deriv2(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c],
                        g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
-                       lam_guess=g["case_lambda_guess"][c])
+                       lam_guess=g["case_lambda_guess"][c], method=method)
         assert out["rc"] == 0
         for w in H.D2_WHICH:
             for kd in H.D2_KINDS:
@@ -156,7 +158,8 @@ def test_second_derivatives(name):
                 G.assert_close(out[n], g["case_" + n][c], "%s case %d %s" % (name, c, n))
 
 
-def test_puppet_second_derivatives():
+@pytest.mark.parametrize("method", ["pair", "jac"])
+def test_puppet_second_derivatives(method):
     import os
     g = G.golden("puppet")
     g2 = np.load(os.path.join(G.GOLD, "puppet_deriv2.npz"))
@@ -164,7 +167,7 @@ def test_puppet_second_derivatives():
     d = G.desc("puppet")
     out = H.deriv2(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c],
                    g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
-                   lam_guess=g["case_lambda_guess"][c])
+                   lam_guess=g["case_lambda_guess"][c], method=method)
     assert out["rc"] == 0
     for w in H.D2_WHICH:
         for kd in H.D2_KINDS:

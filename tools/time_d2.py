@@ -6,8 +6,11 @@ sys.path.insert(0, ROOT)
 from trep_b200 import lib, systems
 up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(a)
 rng = np.random.default_rng(0)
-for name, B in (("damped_pendulum", 1 << 20), ("pend_on_cart1", 1 << 20), ("puppet", int(os.environ.get("PUPPET_B", "256")))):
-    d = systems.named_desc(name); s = lib.System(d)
+CASES = (("damped_pendulum", 1 << 20), ("pend_on_cart1", 1 << 20), ("puppet", int(os.environ.get("PUPPET_B", "256"))))
+if os.environ.get("ONLY"):
+    CASES = tuple(c for c in CASES if c[0] == os.environ["ONLY"])
+for name, B in CASES:
+    d = systems.named_desc(name); s = lib.System(d, d2_pairwise=bool(int(os.environ.get("PAIRWISE", "0"))))
     if name == "puppet":
         g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
         idx = rng.integers(1, 58, B)

@@ -11,6 +11,7 @@
 #include "trepb_codegen.h"
 #include "trepb_err.h"
 #include "trepb_kernels.cuh"
+#include "trepb_d2jac.cuh"
 #include "trepb_coop.h"
 #include "trepb_pack.h"
 
@@ -90,6 +91,12 @@ struct trepb_system {
     DevBuf ws_hd;
     DevBuf d2s[12];
     int bps_d2 = 1;
+    // O(nx) second-derivative path (trepb_d2jac.cuh): dual workspace slab + Jacobian-table records
+    int flags = 0;
+    WsStridedT<Dual> wsl_du;
+    int ws_du_elems = 0;
+    int bps_d2jac = 1;
+    DevBuf ws_du, d2g;
     // staging for the host-pointer entry points
     DevBuf hb[72];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -132,6 +139,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     }
     if (device < 0 || device >= ndev) { delete s; return fail(TREPB_ERR_INVALID, "device index out of range"); }
     s->device = device;
+    s->flags = flags;
 #define CUS(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { int rc_ = cuda_fail(e_, #call); trepb_system_destroy(s); return rc_; } } while (0)
     CUS(cudaSetDevice(device));
     cudaDeviceProp prop;
@@ -190,11 +198,17 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         CUS(s->ks->occupancy(w, s->block, base_smem, &b, nullptr));
         s->bps[w] = b > 0 ? b : 1;
     }
-    s->ws_hd_elems = s->wsl_hd.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, true);
+    s->ws_hd_elems = s->wsl_hd.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, 1);
     {
         int b = 0;
         CUS(s->ks->d2_occupancy(s->block, base_smem, &b, nullptr));
         s->bps_d2 = b > 0 ? b : 1;
+    }
+    if (!s->ks->specialized) {
+        s->ws_du_elems = s->wsl_du.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, 2);
+        int b = 0;
+        CUS(d2jac_occupancy(s->block, d2jac_smem(s->blob_bytes, s->block, ps.nd, ps.nk), &b, nullptr));
+        s->bps_d2jac = b > 0 ? b : 1;
     }
     if (s->ks->specialized) {
         const int nq = ps.nd + ps.nk, nX = 2 * nq, nU = ps.nu + ps.nk;
@@ -219,6 +233,8 @@ void trepb_system_destroy(trepb_system* s) {
     if (s->dcoop) cudaFree(s->dcoop);
     s->ws.release();
     s->ws_hd.release();
+    s->ws_du.release();
+    s->d2g.release();
     for (auto& b : s->d2s) b.release();
     for (auto& b : s->hb) b.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
@@ -542,6 +558,45 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         if (p.zxu && nU) CU(cudaMemsetAsync(p.zxu, 0, (size_t)B * nX * nU * sizeof(double), stream));
         if (p.zuu && nU) CU(cudaMemsetAsync(p.zuu, 0, (size_t)B * nU * nU * sizeof(double), stream));
         if (nU == 0) { p.zxu = nullptr; p.zuu = nullptr; }
+    }
+    if (!s->ks->specialized && !(s->flags & TREPB_FLAG_D2_PAIRWISE)) {
+        // pass A: one dual evaluation of the Jacobian tables per (instance, parameter);
+        // pass B: contraction + solves per pair (trepb_d2jac.cuh).  The batch is processed in
+        // chunks so that the table records stay within a few GB.
+        JacLayout jl;
+        jl.set(nd, nk, nu, nc);
+        size_t free_b = 0, total_b = 0;
+        CU(cudaMemGetInfo(&free_b, &total_b));
+        const size_t avail = free_b + s->ws_du.cap + s->d2g.cap;
+        const size_t per_inst = (size_t)p.nx * jl.size * sizeof(double);
+        size_t gbudget = avail / 4;
+        if (gbudget > ((size_t)4 << 30)) gbudget = (size_t)4 << 30;
+        long long nb = (long long)(gbudget / per_inst);
+        if (nb < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the second-derivative table records");
+        if (nb > B) nb = B;
+        const int block = s->block;
+        const size_t per_cta = (size_t)s->ws_du_elems * sizeof(Dual) * block;
+        long long grid = (nb * p.nx + block - 1) / block;
+        const long long resident = (long long)s->sms * s->bps_d2jac;
+        if (grid > resident) grid = resident;
+        if ((size_t)grid * per_cta > avail / 4) grid = (long long)((avail / 4) / per_cta);
+        if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the second-derivative workspace");
+        CU(s->ws_du.ensure((size_t)grid * per_cta));
+        CU(s->d2g.ensure((size_t)nb * per_inst));
+        WsStridedT<Dual> wd = s->wsl_du;
+        wd.base = (Dual*)s->ws_du.p; wd.stride = 0;
+        LaunchCfg c;
+        c.block = block; c.smem = d2jac_smem(s->blob_bytes, block, nd, nk); c.stream = stream;
+        c.sys = &s->dview; c.dblob = s->dblob; c.blob_bytes = s->blob_bytes; c.ws = s->wsl;
+        Timed t(s, stream);
+        for (long long b0 = 0; b0 < B; b0 += nb) {
+            const long long cnt_b = B - b0 < nb ? B - b0 : nb;
+            long long g = (cnt_b * p.nx + block - 1) / block;
+            c.grid = (int)(g < grid ? g : grid);
+            CU(d2jac_run(c, wd, p, (double*)s->d2g.p, jl, (long)b0, (long)cnt_b));
+            CU(d2solve_run(stream, p, (const double*)s->d2g.p, jl, nd, nk, nu, nc, (long)b0, (long)cnt_b));
+        }
+        return TREPB_OK;
     }
     // one thread per (instance, parameter s, block of kD2Dirs directions t)
     const long long threads = B * (long long)d2_blocks(p.nx, s->ks->specialized ? 1 : kD2Dirs);

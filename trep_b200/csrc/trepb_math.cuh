@@ -310,15 +310,17 @@ TREPB_HD void inertia_apply(Real m, const Real* h, const Real* I, const Real* X,
 // pass 2: leaf -> root.  order 1: Lq, Lv.  order 2: also Lqq, Lvq, Lvv (all nq x nq).
 // Potentials other than gravity are added by add_potentials().
 // ---------------------------------------------------------------------------------------------
+// zero_tables = false: the caller has already cleared the entries of Lqq / Lvq / Lvv that can be
+// written (trepb_d2jac.cuh clears only the structurally non-zero ones).
 template <class Sys, class Ws>
-TREPB_HD void pass2(const Sys& sys, Ws& ws, int order) {
+TREPB_HD void pass2(const Sys& sys, Ws& ws, int order, bool zero_tables = true) {
     using Real = typename Ws::Real;
     const int nq = sys.NQ();
     TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) {
         ws.Lq(i) = 0.0;
         ws.Lv(i) = 0.0;
     }
-    if (order >= 2) {
+    if (order >= 2 && zero_tables) {
         TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i)
             TREPB_UNROLL_SYS for (int j = 0; j < nq; ++j) {
                 ws.Lqq(i, j) = 0.0;
@@ -598,10 +600,10 @@ TREPB_HD void pair_second(const Sys& sys, Ws& ws, int A, int B, int i, int j, ty
 // World pose must be current (pass1 with_world at the wanted evaluation point).
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
-TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh) {
+TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, bool zero_ddh = true) {
     using Real = typename Ws::Real;
     const int nq = sys.NQ();
-    if (mode & 4) {
+    if ((mode & 4) && zero_ddh) {
         TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i)
             TREPB_UNROLL_SYS for (int j = 0; j < nq; ++j) ws.DDhl(i, j) = 0.0;
     }
@@ -728,11 +730,11 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
 //   order 1: Fo        order 2: also Fq, Fv, Fu
 // ---------------------------------------------------------------------------------------------
 template <class Sys, class Ws>
-TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order) {
+TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order, bool zero_tables = true) {
     using Real = typename Ws::Real;
     const int nq = sys.NQ(), nd = sys.ND();
     TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) ws.Fo(j) = 0.0;
-    if (order >= 2) {
+    if (order >= 2 && zero_tables) {
         TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) {
             TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) { ws.Fq(j, i) = 0.0; ws.Fv(j, i) = 0.0; }
             TREPB_UNROLL_SYS for (int u = 0; u < sys.NU(); ++u) ws.Fu(j, u) = 0.0;

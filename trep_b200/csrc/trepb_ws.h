@@ -6,15 +6,16 @@
 //   WsStridedT<Real>     - one slab of global memory shared by the whole grid, element e of thread t
 //                          at base[e * stride + t]  (structure-of-arrays across threads, so a warp
 //                          executing the same line touches 32 consecutive elements = coalesced).
-// Real is double for the step / first-derivative kernels and a hyper-dual number (trepb_hd.h) for
-// the second-derivative kernel, which only evaluates the first-order residual path and therefore
-// lays out only the arrays flagged `ad`.
+// Real is double for the step / first-derivative kernels, a hyper-dual number (trepb_hd.h) for the
+// per-pair second-derivative kernel, which only evaluates the first-order residual path and therefore
+// lays out only the arrays flagged 1, and a dual number (trepb_d2jac.cuh) for the directional
+// derivative of the Jacobian tables (arrays flagged 1 or 2).
 #pragma once
 #include "trepb_sys.h"
 
 namespace trepb {
 
-// X(name, rows, cols, ad) ; sizes use NF NQ ND NU NC NR (= ND+NC)
+// X(name, rows, cols, ad) ; sizes use NF NQ ND NU NC NR (= ND+NC) ; ad: 1 residual path, 2 second-order tables, 0 solver only
 #define TREPB_WS_ARRAYS(X)                                                                     \
     /* integrator state */                                                                     \
     X(q1, NQ, 1, 1) X(q2, NQ, 1, 1) X(p1, ND, 1, 0) X(p2, ND, 1, 1) X(u1, NU, 1, 1) X(lam, NC, 1, 1) \
@@ -22,13 +23,13 @@ namespace trepb {
     /* frame pass 1 */                                                                         \
     X(cs, NF, 2, 1) X(gf, NF, 3, 1) X(V, NF, 6, 1) X(W, NF, 6, 1) X(Rw, NF, 9, 1) X(pw, NF, 3, 1) \
     /* frame pass 2: composite inertia (m, h, I sym6) and momentum */                          \
-    X(Im, NF, 1, 1) X(Ih, NF, 3, 1) X(II, NF, 6, 0) X(mu, NF, 6, 1)                            \
+    X(Im, NF, 1, 1) X(Ih, NF, 3, 1) X(II, NF, 6, 2) X(mu, NF, 6, 1)                            \
     /* Lagrangian tables */                                                                    \
-    X(Lq, NQ, 1, 1) X(Lv, NQ, 1, 1) X(Lqq, NQ, NQ, 0) X(Lvq, NQ, NQ, 0) X(Lvv, NQ, NQ, 0)      \
+    X(Lq, NQ, 1, 1) X(Lv, NQ, 1, 1) X(Lqq, NQ, NQ, 2) X(Lvq, NQ, NQ, 2) X(Lvv, NQ, NQ, 2)      \
     /* forces */                                                                               \
-    X(Fo, ND, 1, 1) X(Fq, ND, NQ, 0) X(Fv, ND, NQ, 0) X(Fu, ND, NU, 0)                         \
+    X(Fo, ND, 1, 1) X(Fq, ND, NQ, 2) X(Fv, ND, NQ, 2) X(Fu, ND, NU, 2)                         \
     /* constraints */                                                                          \
-    X(hc, NC, 1, 1) X(Dh1, NC, NQ, 1) X(Dh2, NC, NQ, 0) X(DDhl, NQ, NQ, 0)                     \
+    X(hc, NC, 1, 1) X(Dh1, NC, NQ, 1) X(Dh2, NC, NQ, 2) X(DDhl, NQ, NQ, 2)                     \
     /* point-pair scratch: d(pA-pB)/dq_j for every config */                                   \
     X(dv, NQ, 3, 1) X(dxs, NQ, 1, 1)                                                           \
     /* Newton */                                                                               \
@@ -63,12 +64,13 @@ struct WsStridedT {
     TREPB_HD Real& name(int i, int j = 0) { return base[(long)(o_##name + i * ld_##name + j) * stride]; }
     TREPB_WS_ARRAYS(X)
 #undef X
-    // returns number of elements per thread; ad_only: lay out only the arrays of the residual path
-    TREPB_HD int layout(int nf, int nd, int nk, int nu, int nc, bool ad_only = false) {
+    // returns number of elements per thread.  level 0: every array; 1: only the arrays of the residual
+    // path (flag 1); 2: those plus the second-order tables (flags 1 and 2, trepb_d2jac.cuh)
+    TREPB_HD int layout(int nf, int nd, int nk, int nu, int nc, int level = 0) {
         NF = nf; ND = nd; NQ = nd + nk; NU = nu; NC = nc; NR = nd + nc;
         int off = 0;
 #define X(name, rows, cols, ad) \
-        o_##name = off; ld_##name = (cols); if (!ad_only || (ad)) off += (rows) * (cols);
+        o_##name = off; ld_##name = (cols); if (level == 0 || ((ad) != 0 && (ad) <= level)) off += (rows) * (cols);
         TREPB_WS_ARRAYS(X)
 #undef X
         return off;

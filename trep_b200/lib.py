@@ -270,11 +270,13 @@ def _ptr(x):
 class System:
     """Handle of a flattened system resident on one GPU (trepb_system)."""
 
-    def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None):
+    def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None, d2_pairwise=False):
         """specialize=False: skip the ahead-of-time specialised kernels.  cooperative: None = let
         the library choose between one thread and one warp per instance for a table-driven system,
         False = always one thread, True = always the cooperative kernels (their compile-time-size
-        flavour when one was built for this shape, unless specialize=False)."""
+        flavour when one was built for this shape, unless specialize=False).  d2_pairwise: second
+        derivatives of a table-driven system by one hyper-dual residual evaluation per parameter
+        pair instead of one dual evaluation of the Jacobian tables per parameter."""
         self.desc = desc
         self.device = device
         cd, self._keep = D.to_c(desc)
@@ -284,6 +286,8 @@ class System:
             flags |= 2
         elif cooperative is True:
             flags |= 4
+        if d2_pairwise:
+            flags |= 8
         _check(_lib.trepb_system_create(C.byref(cd), device, flags, C.byref(h)))
         self._h = h
         self.nq, self.nd, self.nk, self.nu, self.nc = desc.nq, desc.nd, desc.nk, desc.nu, desc.nc
