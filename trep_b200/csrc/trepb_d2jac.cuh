@@ -194,7 +194,7 @@ TREPB_HD void d2jac_eval(const Sys& sys, Ws& ws, const NzMaps& nz, const D2Param
     }
     // eval_mid(order 2) with the table clearing done above
     set_point(sys, ws, 0, dt);
-    pass1(sys, ws, true, sys.pairs_on());
+    pass1(sys, ws, true, sys.pairs_mid());   // world poses at the midpoint only for springs / dampers
     pass2(sys, ws, 2, false);
     add_potentials(sys, ws, 2);
     forces_eval(sys, ws, 2, false);

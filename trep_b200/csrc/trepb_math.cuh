@@ -570,8 +570,11 @@ TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, typename Ws::
 }
 
 // v = pA - pB and dv_j = d(pA-pB)/dq_j for all configs into ws.dv
+// dep_only: dv_j is left untouched for the configs (other than `also`) neither frame depends on
+// (it is zero there and the caller does not read it)
 template <class Sys, class Ws>
-TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, typename Ws::Real* v) {
+TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, typename Ws::Real* v, bool dep_only = false,
+                         int also = -1) {
     using Real = typename Ws::Real;
     Real pa[3], pb[3];
     frame_pos(sys, ws, A, pa);
@@ -579,6 +582,7 @@ TREPB_HD void pair_first(const Sys& sys, Ws& ws, int A, int B, typename Ws::Real
     TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
     TREPB_UNROLL_SYS
     for (int j = 0; j < sys.NQ(); ++j) {
+        if (dep_only && !(sys.dep(A, j) || sys.dep(B, j) || j == also)) continue;
         Real da[3], db[3];
         dpoint(sys, ws, A, j, da);
         dpoint(sys, ws, B, j, db);
@@ -612,7 +616,8 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
         const int kind = sys.con_kind(c);
         const int A = sys.con_i(c, 0), B = sys.con_i(c, 1), third = sys.con_i(c, 2);
         Real v[3];
-        pair_first(sys, ws, A, B, v);
+        // a distance constraint reads dv only at the configs it depends on
+        pair_first(sys, ws, A, B, v, !Sys::kStatic && kind == C_DISTANCE, third);
         if (kind == C_DISTANCE) {
             const Real d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
             if (mode & 1) ws.hc(c) = dot3(v, v) - d * d;
