@@ -373,7 +373,7 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     for b_ in (Al, Bl, Ql, Rr, Kl_out, lst):
         b_.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
-    Bd = 1024
+    Bd = 4096
     z = up(rng.normal(0, 1, (Bd, d.nX)))
     xx = lib.DeviceBuffer(device, (Bd, d.nX, d.nX)); xu = lib.DeviceBuffer(device, (Bd, d.nX, d.nU)); uu = lib.DeviceBuffer(device, (Bd, d.nU, d.nU))
     ms = []
@@ -383,9 +383,19 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         lib.synchronize(device)
         ms.append(s.last_kernel_ms())
     t = float(ms[-1])
+    d2_flops = 30.7e6      # fp64 flops executed per evaluation, ncu counters (profiles/r01f_d2_launches.csv)
+    d2_dram = 21.0e6       # DRAM bytes per evaluation, ncu (same file): the dual workspace of pass A
     out.append({"metric": "second-derivative evaluations/s (W5: marionette, 3240 parameter pairs, z-contracted fdxdx/fdxdu/fdudu)",
                 "value": Bd / t * 1e3, "unit": "evaluations/s", "batch": Bd, "ms": t,
-                "note": "d2 kernel only (the preceding linearize launch is the line above)"})
+                "scheme": "pass A: one dual-number evaluation of the Jacobian tables per (instance, parameter), 80 per instance; "
+                          "pass B: contraction + LU solves per parameter pair (trepb_d2jac.cuh)",
+                "roofline": {"bound": "hbm", "achieved": d2_dram * Bd / (t * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                             "frac": d2_dram * Bd / (t * 1e-3) / 1e9 / hbm_peak, "bytes_per_unit": d2_dram,
+                             "algorithmic_bytes_per_unit": 8 * (d.nX * d.nX + d.nX * d.nU + d.nU * d.nU + d.nX),
+                             "fp64": {"achieved": d2_flops * Bd / (t * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                                      "frac": d2_flops * Bd / (t * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": d2_flops},
+                             "note": "bytes_per_unit is MEASURED DRAM traffic (pass A keeps its per-thread dual workspace in HBM), "
+                                     "not algorithmic bytes; the time covers both passes, not the preceding linearize launch"}})
     for b in (dq, dp, dk, dl, q2, p2, l2, it, st, A, Bm, z, xx, xu, uu):
         b.free()
     s.close()

@@ -79,6 +79,12 @@ extern "C" {
 #define TREPB_FORCE_LINEAR_DAMPER 2/* i = ipool offset, npath ; d = c    forces/lineardamper.c     */
 #define TREPB_CON_DISTANCE 0       /* i = frame1 frame2 config|-1 ; d = distance tolerance  constraints/distance.c */
 #define TREPB_CON_POINT1D 1        /* i = frame1 frame2 component ; d = - tolerance         constraints/point.c    */
+#define TREPB_CON_PLANE 2          /* i = plane_frame point_frame ; d = n0 tolerance n1 n2  constraints/plane.c    */
+/* wrenches: i = frame, ipool offset of six input indices (-1: constant component), dpool offset of the six
+ * constants                                                         forces/{body,hybrid,spatial}wrench.c */
+#define TREPB_FORCE_BODY_WRENCH 3
+#define TREPB_FORCE_HYBRID_WRENCH 4
+#define TREPB_FORCE_SPATIAL_WRENCH 5
 
 /* Flattened system.  Frame 0 is the world frame; frames are in pre-order (parent before child),
  * configs are [dynamic..., kinematic...].  Arrays are only read during trepb_system_create. */

@@ -82,6 +82,65 @@ def ref_tase_pendulum():
     return system
 
 
+def ref_pccd():
+    """examples/pccd.py:20-66 (PointOnPlane constraints)."""
+    system = trep.System()
+    system.import_frames([
+        rx('J', name='J'), [
+            tz(-0.5, name='I', mass=1),
+            tz(-1), [
+                rx('H', name='H'), [
+                    tz(-1, name='G', mass=1),
+                    tz(-2, name='O2')]]],
+        ty(1.5), [
+            rx('K', name='K'), [
+                tz(-1, name='L', mass=1),
+                tz(-2), [
+                    rx('M', name='M'), [
+                        tz(-0.5, name='N', mass=1),
+                        tz(-1.0, name='O')]]]],
+        ty(-1.5), [
+            rx('A', name='A'), [
+                tz(-1, name='B', mass=1),
+                tz(-2), [
+                    rx('C', name='C'), [
+                        tz(-0.375, name='D', mass=1),
+                        tz(-0.75), [
+                            rx('E', name='E'), [
+                                tz(-0.5, name='F', mass=1),
+                                tz(-1.0, name='G2')]]]]]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.1)
+    trep.constraints.PointOnPlane(system, 'O', (0, 1, 0), 'O2')
+    trep.constraints.PointOnPlane(system, 'O', (0, 0, 1), 'O2')
+    trep.constraints.PointOnPlane(system, 'G', (0, 1, 0), 'G2')
+    trep.constraints.PointOnPlane(system, 'G', (0, 0, 1), 'G2')
+    system.q = {'K': 0.523599, 'M': -1.34537, 'J': -0.523599, 'H': 1.21009, 'A': -0.523599,
+                'C': 1.5385, 'E': 1.22497}
+    system.satisfy_constraints()
+    return system
+
+
+def ref_wrench_arm():
+    """Same script as trep_b200/systems.py:wrench_arm with the reference's own classes."""
+    system = trep.System()
+    system.import_frames([
+        rz('yaw', name='base'), [
+            tz(0.4, name='shoulder', mass=2.0), [
+                ry('pitch', name='upper'), [
+                    tx(0.7, name='elbow', mass=1.5), [
+                        tx('reach', name='slider'), [
+                            trep.const_txyz((0.1, -0.2, 0.3), name='tool', mass=0.5)]]]]]])
+    system.get_frame('shoulder').set_mass(2.0, 0.1, 0.2, 0.3)
+    system.get_frame('tool').set_mass(0.5, 0.02, 0.03, 0.01)
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.05)
+    trep.forces.BodyWrench(system, 'tool', (0.3, 'push', -0.2, 0.0, 0.1, 'twist'))
+    trep.forces.HybridWrench(system, 'elbow', ('lift', 0.4, 0.0, 0.2, 0.0, -0.1))
+    trep.forces.SpatialWrench(system, 'slider', (0.1, -0.3, 'shove', 0.05, 'spin', 0.0))
+    return system
+
+
 def ref_puppet():
     puppet = trep.puppets.Puppet(joint_forces=False, string_forces=False, string_constraints=True)
     puppet.q = {
@@ -97,6 +156,7 @@ REF_BUILDERS = {
     "damped_pendulum": ref_damped_pendulum, "pend_on_cart1": lambda: ref_pend_on_cart(False),
     "pend_on_cart2": lambda: ref_pend_on_cart(True), "dual_pendulums": ref_dual_pendulums,
     "tase_pendulum": ref_tase_pendulum, "puppet": ref_puppet,
+    "pccd": ref_pccd, "wrench_arm": ref_wrench_arm,
 }
 
 

@@ -35,7 +35,8 @@ def ref():
     return R
 
 
-COOP_UNSUPPORTED = {"dual_pendulums"}   # LinearSpring / LinearDamper: thread-per-instance kernels only
+# LinearSpring / LinearDamper, PointOnPlane, wrenches: thread-per-instance kernels only
+COOP_UNSUPPORTED = {"dual_pendulums", "pccd", "wrench_arm"}
 
 
 def _systems(lib, name):
@@ -481,3 +482,94 @@ def test_feedback_controller_pipeline(lib, ref):
     got = d.project(bX, U0, Kgpu)
     G.assert_close(got.X, want.X, "projected X", rtol=1e-8)
     G.assert_close(got.U, want.U, "projected U", rtol=1e-8)
+
+
+# ---- plugin kinds beyond BASELINE.json's configs: PointOnPlane, wrenches ----------
+@pytest.mark.parametrize("name", G.EXTRA)
+def test_extra_plugin_kinds_golden_cases(lib, name):
+    """PointOnPlane constraints (pccd) and Body / Hybrid / Spatial wrenches (wrench_arm): step, every
+    first-derivative array, A / B and the Newton iteration counts against the reference."""
+    g = G.golden(name)
+    s = lib.System(G.desc(name))
+    assert not s.cooperative and not s.specialized
+    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                      t2=g["case_t2"], q2_guess=g["case_q2_guess"],
+                      lambda_guess=g["case_lambda_guess"], want_raw=True)
+    assert np.all(out["status"] == 0)
+    for k in ("q2", "p2", "lambda1", "A", "B"):
+        G.assert_close(out[k], g["case_" + k], "%s %s" % (name, k))
+    for k in G.RAW:
+        G.assert_close(out[k], g["case_" + k], "%s %s" % (name, k))
+    assert np.array_equal(out["iters"], g["case_iters"])
+
+
+@pytest.mark.parametrize("pairwise", [False, True])
+@pytest.mark.parametrize("name", G.EXTRA)
+def test_extra_plugin_kinds_second_derivatives(lib, name, pairwise):
+    g = G.golden(name)
+    s = lib.System(G.desc(name), d2_pairwise=pairwise)
+    out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                   t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
+    assert np.all(out["status"] == 0)
+    for n in s.d2_shapes(1):
+        G.assert_close(out[n], g["case_" + n], "%s[pairwise=%s] %s" % (name, pairwise, n))
+
+
+def test_pccd_rollout(lib):
+    """examples/pccd.py: 300 steps of the closed chain, every step against the reference."""
+    g = G.golden("pccd")
+    s = lib.System(G.desc("pccd"))
+    dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
+    p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0[0], g["roll_p"][0], "pccd p_init")
+    out = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, sample_every=1)
+    assert out["status"][0] == 0
+    G.assert_close(out["traj_q"][0], g["roll_q"][1:], "pccd traj q", rtol=1e-7)
+    G.assert_close(out["traj_p"][0], g["roll_p"][1:], "pccd traj p", rtol=1e-7)
+    assert abs(int(out["iters"][0]) - int(g["roll_iters"].sum())) <= 3
+
+
+def test_wrench_arm_rollout(lib):
+    g = G.golden("wrench_arm")
+    s = lib.System(G.desc("wrench_arm"))
+    dt, nsteps, sample = float(g["roll_dt"]), int(g["roll_nsteps"]), int(g["roll_sample"])
+    p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0[0], g["roll_p_init"], "wrench_arm p_init")
+    t = dt * (1 + np.arange(nsteps))
+    u = np.stack([np.sin(3 * t), 0.5 * np.cos(2 * t), 0.8 * np.sin(t), 0.3 * np.cos(t), -0.6 * np.sin(2 * t)], axis=1)[None]
+    out = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, u1=u, sample_every=sample)
+    assert out["status"][0] == 0
+    ns = nsteps // sample
+    G.assert_close(out["traj_q"][0, :ns], g["roll_q"][1:1 + ns], "wrench_arm traj q", rtol=1e-7)
+    G.assert_close(out["traj_p"][0, :ns], g["roll_p"][1:1 + ns], "wrench_arm traj p", rtol=1e-7)
+    assert abs(int(out["iters"][0]) - int(g["roll_iters"].sum())) <= 4
+
+
+@pytest.mark.parametrize("name", G.EXTRA)
+def test_extra_plugin_kinds_random_vs_reference(lib, ref, name):
+    """Seeded ragged batches against the reference itself run live (oracle/_ref)."""
+    rng = np.random.default_rng(21)
+    system, mvi = ref.make_mvi(name)
+    nq, nd, nu = mvi.nq, mvi.nd, mvi.nu
+    B = 67
+    if name == "pccd":
+        g = G.golden("pccd")
+        idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+        q1 = g["roll_q"][idx] + rng.normal(0, 0.01, (B, nq))
+        p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, nd))
+        lam = g["roll_lambda"][idx - 1]
+    else:
+        q1 = np.stack([rng.uniform(-np.pi, np.pi, B), rng.uniform(-1.2, 1.2, B), rng.uniform(-0.3, 0.5, B)], axis=1)
+        p1 = rng.normal(0, 1.0, (B, nd))
+        lam = None
+    u1 = rng.uniform(-2, 2, (B, nu))
+    k2 = np.zeros((B, 0))
+    t1 = rng.uniform(0, 5, B)
+    t2 = t1 + 0.01
+    want = ref.run_cases(mvi, t1, t2, q1, p1, u1, k2, lambda_guess=lam)
+    s = lib.System(G.desc(name))
+    out = s.linearize(q1, p1, u1, k2, t1=t1, t2=t2, lambda_guess=lam)
+    assert np.array_equal(out["status"], want["status"])
+    for k in ("q2", "p2", "lambda1", "A", "B"):
+        G.assert_close(out[k], want[k], "%s %s" % (name, k))
+    assert int(np.sum(out["iters"] != want["iters"])) <= 1

@@ -9,7 +9,7 @@ import golden_util as G
 import hostmath as H
 
 
-@pytest.mark.parametrize("name", G.ALL)
+@pytest.mark.parametrize("name", G.ALL + G.EXTRA)
 def test_cases_step_and_deriv1(name):
     g = G.golden(name)
     d = G.desc(name)
@@ -136,7 +136,7 @@ def test_puppet_rollout():
     assert iters == int(g["roll_iters"].sum())
 
 
-D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"]
+D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"] + G.EXTRA
 
 
 @pytest.mark.parametrize("method", ["pair", "jac"])

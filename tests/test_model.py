@@ -22,7 +22,8 @@ def test_frame_order_is_preorder_and_configs_dyn_then_kin():
 
 def test_named_small_systems_sizes():
     want = {"pendulum1": (3, 1, 0, 0), "pendulum5": (11, 5, 0, 0), "damped_pendulum": (4, 1, 0, 0),
-            "pend_on_cart1": (4, 2, 0, 1), "pend_on_cart2": (4, 2, 0, 2), "dual_pendulums": (6, 2, 0, 0)}
+            "pend_on_cart1": (4, 2, 0, 1), "pend_on_cart2": (4, 2, 0, 2), "dual_pendulums": (6, 2, 0, 0),
+            "pccd": (24, 7, 0, 0), "wrench_arm": (7, 3, 0, 5)}
     for n, (nf, nd, nk, nu) in want.items():
         d = G.desc(n)
         assert (d.n_frames, d.nd, d.nk, d.nu) == (nf, nd, nk, nu), n
@@ -65,7 +66,7 @@ def test_flatten_of_live_reference_systems_equals_the_mirror():
         pytest.skip("oracle/_ref not built")
     sys.path.insert(0, os.path.join(root, "oracle"))
     import ref_systems as R
-    for n in G.ALL:
+    for n in G.ALL + G.EXTRA:
         d = M.flatten_trep_system(R.REF_BUILDERS[n](), name=n)
         assert d.equal(G.desc(n)), n
 
@@ -81,6 +82,11 @@ def test_unsupported_plugins_are_refused_not_approximated():
     import ref_systems as R
     trep = R.trep
     system = R.REF_BUILDERS["pendulum1"]()
-    trep.constraints.PointOnPlane(system, system.world_frame, (0, 0, 1), system.frames[-1])
+
+    class PythonPotential(trep.Potential):      # a Python-defined plugin: no device implementation
+        def V(self):
+            return 0.0
+
+    PythonPotential(system, "python-potential")
     with pytest.raises(TypeError):
         M.flatten_trep_system(system)

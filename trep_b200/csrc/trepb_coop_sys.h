@@ -231,6 +231,9 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
         if (d->pot_kind[i] == TREPB_POT_LINEAR_SPRING) { P.why = "LinearSpring potential"; return P; }
     for (int i = 0; i < d->n_forces; ++i)
         if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
+        else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }
+    for (int i = 0; i < nc; ++i)
+        if (d->con_kind[i] == TREPB_CON_PLANE) { P.why = "PointOnPlane constraint"; return P; }
 
     // ---- frames -> links
     std::vector<int> flink(nf, -1);      // frame -> frame index of the link it belongs to (-1: world)

@@ -147,6 +147,9 @@ TREPB_HD void d2jac_build_nz(const Sys& sys, const NzMaps& nz, int lane, int nla
                     const int off = sys.force_i(fo, 0);
                     const int A = sys.ipool(off), B = sys.ipool(off + 1);
                     f = f || ((sys.dep(A, i) || sys.dep(B, i)) && (sys.dep(A, j) || sys.dep(B, j)));
+                } else if (kind == F_BODY_WRENCH || kind == F_HYBRID_WRENCH || kind == F_SPATIAL_WRENCH) {
+                    const int A = sys.force_i(fo, 0);
+                    f = f || (sys.dep(A, i) && sys.dep(A, j));
                 }
             }
             nz.F[i * nq + j] = f ? 1 : 0;

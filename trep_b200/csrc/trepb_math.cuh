@@ -569,6 +569,43 @@ TREPB_HD void ddpoint(const Sys& sys, Ws& ws, int F, int i, int j, typename Ws::
     cross3(aw, d, out);
 }
 
+// world orientation of frame F (identity for the world frame)
+template <class Sys, class Ws>
+TREPB_HD void frame_rot(const Sys& sys, Ws& ws, int F, typename Ws::Real* R) {
+    if (F == 0) { TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k] = (k % 4 == 0) ? 1.0 : 0.0; }
+    else { TREPB_UNROLL for (int k = 0; k < 9; ++k) R[k] = ws.Rw(F, k); }
+}
+// d (R_F n) / d q_j = a_j x (R_F n) for a revolute ancestor-or-self joint of F, zero otherwise
+template <class Sys, class Ws>
+TREPB_HD void dnormal(const Sys& sys, Ws& ws, int F, int j, const typename Ws::Real* nw, typename Ws::Real* out) {
+    using Real = typename Ws::Real;
+    out[0] = out[1] = out[2] = 0.0;
+    if (F == 0 || sys.cfg_frame(j) < 0 || !sys.dep(F, j)) return;
+    Real aw[3];
+    bool rot;
+    int fj;
+    joint_axis_w(sys, ws, j, aw, &rot, &fj);
+    if (rot) cross3(aw, nw, out);
+}
+// d2 (R_F n) / d q_i d q_j = a_up x (a_lo x R_F n)
+template <class Sys, class Ws>
+TREPB_HD void ddnormal(const Sys& sys, Ws& ws, int F, int i, int j, const typename Ws::Real* nw, typename Ws::Real* out) {
+    using Real = typename Ws::Real;
+    out[0] = out[1] = out[2] = 0.0;
+    if (F == 0 || sys.cfg_frame(i) < 0 || sys.cfg_frame(j) < 0) return;
+    if (!sys.dep(F, i) || !sys.dep(F, j)) return;
+    int up = i, lo = j;
+    if (!sys.dep(sys.cfg_frame(j), i)) { up = j; lo = i; }
+    Real au[3], al[3], t[3];
+    bool ru, rl;
+    int f;
+    joint_axis_w(sys, ws, up, au, &ru, &f);
+    joint_axis_w(sys, ws, lo, al, &rl, &f);
+    if (!ru || !rl) return;
+    cross3(al, nw, t);
+    cross3(au, t, out);
+}
+
 // v = pA - pB and dv_j = d(pA-pB)/dq_j for all configs into ws.dv
 // dep_only: dv_j is left untouched for the configs (other than `also`) neither frame depends on
 // (it is zero there and the caller does not read it)
@@ -616,8 +653,9 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
         const int kind = sys.con_kind(c);
         const int A = sys.con_i(c, 0), B = sys.con_i(c, 1), third = sys.con_i(c, 2);
         Real v[3];
-        // a distance constraint reads dv only at the configs it depends on
-        pair_first(sys, ws, A, B, v, !Sys::kStatic && kind == C_DISTANCE, third);
+        // distance and plane constraints read dv only at the configs they depend on
+        pair_first(sys, ws, A, B, v, !Sys::kStatic && (kind == C_DISTANCE || kind == C_PLANE),
+                   kind == C_DISTANCE ? third : -1);
         if (kind == C_DISTANCE) {
             const Real d = third >= 0 ? ws.qe(third) : sys.con_d(c, 0);
             if (mode & 1) ws.hc(c) = dot3(v, v) - d * d;
@@ -647,6 +685,49 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
                                    + v[0] * ddv[0] + v[1] * ddv[1] + v[2] * ddv[2];
                         if (third == i && third == j) val -= 1.0;
                         val *= 2.0 * lam;
+                        ws.DDhl(i, j) += val;
+                        if (j != i) ws.DDhl(j, i) += val;
+                    }
+                }
+            }
+        } else if (kind == C_PLANE) {
+            // h = (R_A n) . (p_A - p_B): point B on the plane through frame A's origin with normal
+            // n fixed in frame A (trep/_trep/constraints/plane.c:14-84).  d = (n0, tol, n1, n2).
+            Real RA[9], nw[3];
+            frame_rot(sys, ws, A, RA);
+            const double n0 = sys.con_d(c, 0), n1 = sys.con_d(c, 2), n2 = sys.con_d(c, 3);
+            TREPB_UNROLL for (int r = 0; r < 3; ++r) nw[r] = RA[r * 3] * n0 + RA[r * 3 + 1] * n1 + RA[r * 3 + 2] * n2;
+            if (mode & 1) ws.hc(c) = dot3(nw, v);
+            if (mode & 2) {
+                TREPB_UNROLL_SYS
+                for (int j = 0; j < nq; ++j) {
+                    Real val = 0.0;
+                    if (sys.dep(A, j) || sys.dep(B, j)) {
+                        Real dn[3];
+                        dnormal(sys, ws, A, j, nw, dn);
+                        val = dot3(dn, v) + (nw[0] * ws.dv(j, 0) + nw[1] * ws.dv(j, 1) + nw[2] * ws.dv(j, 2));
+                    }
+                    if (which_dh == 1) ws.Dh1(c, j) = val; else ws.Dh2(c, j) = val;
+                }
+            }
+            if (mode & 4) {
+                const Real lam = ws.lam(c);
+                TREPB_UNROLL_SYS
+                for (int i = 0; i < nq; ++i) {
+                    if (!(sys.dep(A, i) || sys.dep(B, i))) continue;
+                    Real dni[3];
+                    dnormal(sys, ws, A, i, nw, dni);
+                    TREPB_UNROLL_SYS
+                    for (int j = i; j < nq; ++j) {
+                        if (!(sys.dep(A, j) || sys.dep(B, j))) continue;
+                        Real dnj[3], ddn[3], ddv[3];
+                        dnormal(sys, ws, A, j, nw, dnj);
+                        ddnormal(sys, ws, A, i, j, nw, ddn);
+                        pair_second(sys, ws, A, B, i, j, ddv);
+                        Real val = dot3(ddn, v) + dot3(nw, ddv)
+                                   + (dni[0] * ws.dv(j, 0) + dni[1] * ws.dv(j, 1) + dni[2] * ws.dv(j, 2))
+                                   + (dnj[0] * ws.dv(i, 0) + dnj[1] * ws.dv(i, 1) + dnj[2] * ws.dv(i, 2));
+                        val *= lam;
                         ws.DDhl(i, j) += val;
                         if (j != i) ws.DDhl(j, i) += val;
                     }
@@ -761,6 +842,83 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order, bool zero_tables = 
             if (c < nd) {
                 ws.Fo(c) += ws.u1(u);
                 if (order >= 2) ws.Fu(c, u) += 1.0;
+            }
+        } else if (kind == F_BODY_WRENCH || kind == F_HYBRID_WRENCH || kind == F_SPATIAL_WRENCH) {
+            // wrench on frame F (forces/bodywrench.c, hybridwrench.c, spatialwrench.c):
+            //   f_j = J_j . w ,  J_j = unhat(g^-1 g_dq_j)                  body   (R^T dp_j, R^T a_j)
+            //                        = unhat(g_dq_j g^-1)                  spatial (dp_j - a_j x p, a_j)
+            //                        = (dp_j, angular part of the spatial) hybrid (dp_j, a_j)
+            // with dp_j = d p_F / d q_j and a_j the world axis of a revolute joint (0: prismatic).
+            // i = frame, ipool offset of the six input indices (-1: constant), dpool offset of the constants
+            const int F = sys.force_i(fo, 0), io = sys.force_i(fo, 1), dof = sys.force_i(fo, 2);
+            Real wr[6], RF[9], pF[3];
+            TREPB_UNROLL for (int k = 0; k < 6; ++k) {
+                const int in = sys.ipool(io + k);
+                if (in >= 0) wr[k] = ws.u1(in); else wr[k] = sys.dpool(dof + k);
+            }
+            frame_rot(sys, ws, F, RF);
+            frame_pos(sys, ws, F, pF);
+            TREPB_UNROLL_SYS
+            for (int j = 0; j < nd; ++j) {
+                if (F == 0 || !sys.dep(F, j)) continue;
+                Real dp[3], aj[3], J[6];
+                bool rotj;
+                int fj;
+                dpoint(sys, ws, F, j, dp);
+                joint_axis_w(sys, ws, j, aj, &rotj, &fj);
+                if (!rotj) { aj[0] = aj[1] = aj[2] = 0.0; }
+                if (kind == F_HYBRID_WRENCH) {
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { J[k] = dp[k]; J[3 + k] = aj[k]; }
+                } else if (kind == F_SPATIAL_WRENCH) {
+                    Real t[3];
+                    cross3(aj, pF, t);
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { J[k] = dp[k] - t[k]; J[3 + k] = aj[k]; }
+                } else {
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) {
+                        J[k] = RF[k] * dp[0] + RF[3 + k] * dp[1] + RF[6 + k] * dp[2];
+                        J[3 + k] = RF[k] * aj[0] + RF[3 + k] * aj[1] + RF[6 + k] * aj[2];
+                    }
+                }
+                ws.Fo(j) += dot6(J, wr);
+                if (order >= 2) {
+                    TREPB_UNROLL for (int k = 0; k < 6; ++k) {
+                        const int in = sys.ipool(io + k);
+                        if (in >= 0) ws.Fu(j, in) += J[k];
+                    }
+                    TREPB_UNROLL_SYS
+                    for (int i = 0; i < nq; ++i) {
+                        if (!sys.dep(F, i)) continue;
+                        Real ddp[3], ai[3], da[3], dJ[6];
+                        bool roti;
+                        int fi;
+                        ddpoint(sys, ws, F, j, i, ddp);
+                        joint_axis_w(sys, ws, i, ai, &roti, &fi);
+                        if (!roti) { ai[0] = ai[1] = ai[2] = 0.0; }
+                        // d a_j / d q_i = a_i x a_j when joint i is above joint j
+                        if (i != j && sys.dep(fj, i)) cross3(ai, aj, da);
+                        else { da[0] = da[1] = da[2] = 0.0; }
+                        if (kind == F_HYBRID_WRENCH) {
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) { dJ[k] = ddp[k]; dJ[3 + k] = da[k]; }
+                        } else if (kind == F_SPATIAL_WRENCH) {
+                            Real t[3], u[3], dpi[3];
+                            dpoint(sys, ws, F, i, dpi);
+                            cross3(da, pF, t);
+                            cross3(aj, dpi, u);
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) { dJ[k] = ddp[k] - t[k] - u[k]; dJ[3 + k] = da[k]; }
+                        } else {
+                            // d (R^T x) / d q_i = R^T (dx/dq_i - a_i x x)
+                            Real t[3], u[3];
+                            cross3(ai, dp, t);
+                            cross3(ai, aj, u);
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) { t[k] = ddp[k] - t[k]; u[k] = da[k] - u[k]; }
+                            TREPB_UNROLL for (int k = 0; k < 3; ++k) {
+                                dJ[k] = RF[k] * t[0] + RF[3 + k] * t[1] + RF[6 + k] * t[2];
+                                dJ[3 + k] = RF[k] * u[0] + RF[3 + k] * u[1] + RF[6 + k] * u[2];
+                            }
+                        }
+                        ws.Fq(j, i) += dot6(dJ, wr);
+                    }
+                }
             }
         } else if (kind == F_LINEAR_DAMPER) {
             // single-segment tape measure between two frames (forces/lineardamper.py:34)

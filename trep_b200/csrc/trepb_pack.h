@@ -127,13 +127,20 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
                 mark_world(d->ipool[ii[0] + j]);
             }
             has_pairs = 1; has_pairs_mid = 1;
-        } else return fail("unknown force kind (wrench / Python-defined forces have no device implementation)");
+        } else if (k == TREPB_FORCE_BODY_WRENCH || k == TREPB_FORCE_HYBRID_WRENCH || k == TREPB_FORCE_SPATIAL_WRENCH) {
+            if (!frame_ok(ii[0])) return fail("wrench frame index out of range");
+            if (ii[1] < 0 || ii[1] + 6 > d->n_ipool) return fail("wrench input pool out of range");
+            if (ii[2] < 0 || ii[2] + 6 > d->n_dpool) return fail("wrench constant pool out of range");
+            for (int j = 0; j < 6; ++j)
+                if (d->ipool[ii[1] + j] < -1 || d->ipool[ii[1] + j] >= nu) return fail("wrench input index out of range");
+            mark_world(ii[0]); has_pairs = 1; has_pairs_mid = 1;
+        } else return fail("unknown force kind (Python-defined forces have no device implementation)");
     }
     for (int i = 0; i < nc; ++i) {
         const int k = d->con_kind[i];
         const int32_t* ii = d->con_i + 4 * i;
-        if (k != TREPB_CON_DISTANCE && k != TREPB_CON_POINT1D)
-            return fail("unknown constraint kind (plane / Python-defined constraints have no device implementation)");
+        if (k != TREPB_CON_DISTANCE && k != TREPB_CON_POINT1D && k != TREPB_CON_PLANE)
+            return fail("unknown constraint kind (Python-defined constraints have no device implementation)");
         if (!frame_ok(ii[0]) || !frame_ok(ii[1])) return fail("constraint frame index out of range");
         if (k == TREPB_CON_DISTANCE && (ii[2] < -1 || ii[2] >= nq)) return fail("Distance config out of range");
         if (k == TREPB_CON_POINT1D && (ii[2] < 0 || ii[2] > 2)) return fail("PointToPoint component out of range");

@@ -24,8 +24,8 @@ namespace trepb {
 
 enum FrameKind { K_WORLD = 0, K_TX, K_TY, K_TZ, K_RX, K_RY, K_RZ, K_CONST_SE3 };
 enum PotKind { P_GRAVITY = 0, P_LINEAR_SPRING, P_CONFIG_SPRING };
-enum ForceKind { F_DAMPING = 0, F_CONFIG, F_LINEAR_DAMPER };
-enum ConKind { C_DISTANCE = 0, C_POINT1D };
+enum ForceKind { F_DAMPING = 0, F_CONFIG, F_LINEAR_DAMPER, F_BODY_WRENCH, F_HYBRID_WRENCH, F_SPATIAL_WRENCH };
+enum ConKind { C_DISTANCE = 0, C_POINT1D, C_PLANE };
 
 // Status codes written per instance (never abort the batch).
 enum Status { ST_OK = 0, ST_NOT_CONVERGED = -1, ST_SINGULAR = -2 };

@@ -22,9 +22,9 @@ KIND_NAMES = ["WORLD", "TX", "TY", "TZ", "RX", "RY", "RZ", "CONST_SE3"]
 # potential kinds
 POT_GRAVITY, POT_LINEAR_SPRING, POT_CONFIG_SPRING = range(3)
 # force kinds
-FORCE_DAMPING, FORCE_CONFIG, FORCE_LINEAR_DAMPER = range(3)
+FORCE_DAMPING, FORCE_CONFIG, FORCE_LINEAR_DAMPER, FORCE_BODY_WRENCH, FORCE_HYBRID_WRENCH, FORCE_SPATIAL_WRENCH = range(6)
 # constraint kinds
-CON_DISTANCE, CON_POINT1D = range(2)
+CON_DISTANCE, CON_POINT1D, CON_PLANE = range(3)
 
 
 @dataclass
@@ -47,7 +47,7 @@ class SystemDesc:
     force_d: np.ndarray               # f64   [nFo,4]
     con_kind: np.ndarray              # int32 [nc]
     con_i: np.ndarray                 # int32 [nc,4]
-    con_d: np.ndarray                 # f64   [nc,4]   [distance, tolerance, -, -]
+    con_d: np.ndarray                 # f64   [nc,4]   [distance | n0, tolerance, n1, n2]
     ipool: np.ndarray                 # int32 [*]  variable-length int payloads (tape-measure paths)
     dpool: np.ndarray                 # f64   [*]  variable-length double payloads (damping coefficients)
     frame_names: list = field(default_factory=list)

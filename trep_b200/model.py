@@ -311,6 +311,44 @@ class LinearDamper:
         return D.FORCE_LINEAR_DAMPER, _pad4([off, 2], -1), _pad4([self.c], 0.0)
 
 
+class _Wrench:
+    """Wrench on a frame; each of the six components is a constant or the name of an input
+    (trep/forces/bodywrench.py, hybridwrench.py, spatialwrench.py)."""
+    KIND = None
+
+    def __init__(self, system, frame, wrench=tuple(), name=None):
+        self.system, self.name = system, name
+        self.frame = system.get_frame(frame)
+        if self.frame is None:
+            raise ValueError("Could not find frame %r" % (frame,))
+        wrench = (list(wrench) + [0.0] * 6)[:6]
+        self.inputs, self.constants = [None] * 6, [0.0] * 6
+        for i in range(6):
+            if isinstance(wrench[i], str):
+                self.inputs[i] = Input(system, wrench[i])
+            else:
+                self.constants[i] = float(wrench[i])
+        system.forces.append(self)
+
+    def _record(self, fidx, cidx, ipool, dpool):
+        io, do = len(ipool), len(dpool)
+        ipool.extend([-1 if u is None else u.index for u in self.inputs])
+        dpool.extend(self.constants)
+        return self.KIND, [fidx[id(self.frame)], io, do, -1], _pad4([], 0.0)
+
+
+class BodyWrench(_Wrench):
+    KIND = D.FORCE_BODY_WRENCH
+
+
+class HybridWrench(_Wrench):
+    KIND = D.FORCE_HYBRID_WRENCH
+
+
+class SpatialWrench(_Wrench):
+    KIND = D.FORCE_SPATIAL_WRENCH
+
+
 # ---- constraints (trep/constraints/*.py) ---------------------------------------------------
 class Distance:
     def __init__(self, system, frame1, frame2, distance, name=None, tolerance=1e-10):
@@ -342,6 +380,22 @@ class PointToPoint1D:
                 _pad4([0.0, self.tolerance], 0.0))
 
 
+class PointOnPlane:
+    """Point frame stays on the plane through plane_frame's origin with the given normal (fixed in
+    plane_frame) (trep/constraints/plane.py)."""
+    def __init__(self, system, plane_frame, plane_normal, point_frame, name=None, tolerance=1e-10):
+        self.system, self.name, self.tolerance = system, name, float(tolerance)
+        self.plane_frame, self.point_frame = system.get_frame(plane_frame), system.get_frame(point_frame)
+        assert self.plane_frame is not None and self.point_frame is not None
+        self.normal = tuple(float(x) for x in plane_normal)
+        system.constraints.append(self)
+
+    def _record(self, fidx, cidx, ipool, dpool):
+        n = self.normal
+        return (D.CON_PLANE, [fidx[id(self.plane_frame)], fidx[id(self.point_frame)], -1, -1],
+                [n[0], self.tolerance, n[1], n[2]])
+
+
 class PointToPoint2D:
     def __init__(self, system, plane, frame1, frame2, name=None):
         axes = {0: "yz", 1: "xz", 2: "xy"}[{"yz": 0, "zy": 0, "xz": 1, "zx": 1, "xy": 2, "yx": 2}[plane.lower()]]
@@ -363,9 +417,11 @@ potentials = _NS()
 potentials.Gravity, potentials.LinearSpring, potentials.ConfigSpring = Gravity, LinearSpring, ConfigSpring
 forces = _NS()
 forces.Damping, forces.ConfigForce, forces.LinearDamper = Damping, ConfigForce, LinearDamper
+forces.BodyWrench, forces.HybridWrench, forces.SpatialWrench = BodyWrench, HybridWrench, SpatialWrench
 constraints = _NS()
 constraints.Distance, constraints.PointToPoint1D = Distance, PointToPoint1D
 constraints.PointToPoint2D, constraints.PointToPoint3D = PointToPoint2D, PointToPoint3D
+constraints.PointOnPlane = PointOnPlane
 
 
 # ------------------------------------------------------------------------------------------
@@ -375,7 +431,7 @@ def flatten_trep_system(system, name="") -> D.SystemDesc:
     """Build a SystemDesc from a live reference ``trep.System`` without importing trep.
 
     Raises ``TypeError`` for any potential/force/constraint kind that has no device
-    implementation (Python-defined plugins, wrenches, plane constraints, splines): the batched
+    implementation (Python-defined plugins, spline springs): the batched
     path refuses rather than falls back.
     """
     frames = list(system.frames)
@@ -437,6 +493,13 @@ def flatten_trep_system(system, name="") -> D.SystemDesc:
             path = list(f._path._frames)
             ipool.extend([fidx[id(x)] for x in path])
             fk.append(D.FORCE_LINEAR_DAMPER); fi.append([off, len(path), -1, -1]); fd.append([float(f.c), 0, 0, 0])
+        elif cls in ("BodyWrench", "HybridWrench", "SpatialWrench"):
+            io, do = len(ipool), len(dpool)
+            ipool.extend([-1 if u is None else uidx[id(u)] for u in f._wrench_vars])
+            dpool.extend([float(x) for x in f._wrench_cons])
+            wkind = {"BodyWrench": D.FORCE_BODY_WRENCH, "HybridWrench": D.FORCE_HYBRID_WRENCH,
+                     "SpatialWrench": D.FORCE_SPATIAL_WRENCH}[cls]
+            fk.append(wkind); fi.append([fidx[id(f._frame)], io, do, -1]); fd.append([0.0] * 4)
         else:
             raise TypeError("force %s has no batched device implementation" % cls)
     ck, ci, cd = [], [], []
@@ -450,6 +513,10 @@ def flatten_trep_system(system, name="") -> D.SystemDesc:
         elif cls == "PointToPoint1D":
             ck.append(D.CON_POINT1D); ci.append([fidx[id(c.frame1)], fidx[id(c.frame2)], int(c._component), -1])
             cd.append([0.0, float(c.tolerance), 0, 0])
+        elif cls == "PointOnPlane":
+            n = [float(x) for x in c.normal]
+            ck.append(D.CON_PLANE); ci.append([fidx[id(c.plane_frame)], fidx[id(c.point_frame)], -1, -1])
+            cd.append([n[0], float(c.tolerance), n[1], n[2]])
         else:
             raise TypeError("constraint %s has no batched device implementation" % cls)
     return D.make_desc(parent, kind, config, value, se3, mass, system.nQd, system.nQk, system.nu,

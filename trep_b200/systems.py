@@ -76,6 +76,66 @@ def tase_pendulum() -> M.System:
     return s
 
 
+def pccd() -> M.System:
+    """Planar closed-chain device: three open chains closed by four PointOnPlane constraints
+    (examples/pccd.py:20-66).  nd 7, nc 4."""
+    s = M.System(name="pccd")
+    s.import_frames([
+        M.rx("J", name="J"), [
+            M.tz(-0.5, name="I", mass=1),
+            M.tz(-1), [
+                M.rx("H", name="H"), [
+                    M.tz(-1, name="G", mass=1),
+                    M.tz(-2, name="O2")]]],
+        M.ty(1.5), [
+            M.rx("K", name="K"), [
+                M.tz(-1, name="L", mass=1),
+                M.tz(-2), [
+                    M.rx("M", name="M"), [
+                        M.tz(-0.5, name="N", mass=1),
+                        M.tz(-1.0, name="O")]]]],
+        M.ty(-1.5), [
+            M.rx("A", name="A"), [
+                M.tz(-1, name="B", mass=1),
+                M.tz(-2), [
+                    M.rx("C", name="C"), [
+                        M.tz(-0.375, name="D", mass=1),
+                        M.tz(-0.75), [
+                            M.rx("E", name="E"), [
+                                M.tz(-0.5, name="F", mass=1),
+                                M.tz(-1.0, name="G2")]]]]]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.1)
+    M.PointOnPlane(s, "O", (0, 1, 0), "O2")
+    M.PointOnPlane(s, "O", (0, 0, 1), "O2")
+    M.PointOnPlane(s, "G", (0, 1, 0), "G2")
+    M.PointOnPlane(s, "G", (0, 0, 1), "G2")
+    return s
+
+
+def wrench_arm() -> M.System:
+    """Spatial three-joint arm (two revolute joints about different axes and a prismatic one, an
+    offset constant frame) loaded by one wrench of each kind with mixed constant / input components
+    (trep/forces/bodywrench.py, hybridwrench.py, spatialwrench.py; cf. the HybridWrench loads of
+    examples/extensor-tendon-model.py:49-56).  nd 3, nu 5."""
+    s = M.System(name="wrench_arm")
+    s.import_frames([
+        M.rz("yaw", name="base"), [
+            M.tz(0.4, name="shoulder", mass=2.0), [
+                M.ry("pitch", name="upper"), [
+                    M.tx(0.7, name="elbow", mass=1.5), [
+                        M.tx("reach", name="slider"), [
+                            M.const_txyz((0.1, -0.2, 0.3), name="tool", mass=0.5)]]]]]])
+    s.get_frame("shoulder").set_mass(2.0, 0.1, 0.2, 0.3)
+    s.get_frame("tool").set_mass(0.5, 0.02, 0.03, 0.01)
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.05)
+    M.BodyWrench(s, "tool", (0.3, "push", -0.2, 0.0, 0.1, "twist"))
+    M.HybridWrench(s, "elbow", ("lift", 0.4, 0.0, 0.2, 0.0, -0.1))
+    M.SpatialWrench(s, "slider", (0.1, -0.3, "shove", 0.05, "spin", 0.0))
+    return s
+
+
 def puppet_desc() -> SystemDesc:
     """Marionette with string constraints (trep/puppets/puppets.py:220-310,
     examples/puppet-optimization.py:217-218): nd=22, nk=18, nc=6, 86 frames."""
@@ -89,10 +149,12 @@ def named_desc(name) -> SystemDesc:
         "pendulum1": lambda: pendulum(1), "pendulum5": lambda: pendulum(5),
         "damped_pendulum": damped_pendulum, "pend_on_cart1": lambda: pend_on_cart(False),
         "pend_on_cart2": lambda: pend_on_cart(True), "dual_pendulums": dual_pendulums,
-        "tase_pendulum": tase_pendulum,
+        "tase_pendulum": tase_pendulum, "pccd": pccd, "wrench_arm": wrench_arm,
     }
     return table[name]().describe()
 
 
 NAMED = ["pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2",
          "dual_pendulums", "tase_pendulum", "puppet"]
+# systems exercising the plugin kinds beyond BASELINE.json's configs
+EXTRA = ["pccd", "wrench_arm"]
