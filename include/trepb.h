@@ -74,6 +74,8 @@ extern "C" {
 #define TREPB_POT_GRAVITY 0        /* d = gx gy gz                       potentials/gravity.c      */
 #define TREPB_POT_LINEAR_SPRING 1  /* i = frame1 frame2 ; d = k x0       potentials/linearspring.c */
 #define TREPB_POT_CONFIG_SPRING 2  /* i = config        ; d = k q0       potentials/configspring.c */
+#define TREPB_POT_NONLINEAR_CONFIG_SPRING 3 /* i = config, dpool offset, n x-points ; d = m b ; dpool: x[n], coeffs[n-1][6]
+                                             potentials/nonlinear_config_spring.c + spline.c */
 #define TREPB_FORCE_DAMPING 0      /* i = dpool offset, nd ; coefficients per dyn config  forces/damping.c */
 #define TREPB_FORCE_CONFIG 1       /* i = config input                   forces/configforce.c      */
 #define TREPB_FORCE_LINEAR_DAMPER 2/* i = ipool offset, npath ; d = c    forces/lineardamper.c     */

@@ -24,6 +24,12 @@ from trep_b200 import systems as S  # noqa: E402
 
 def main():
     rng = np.random.default_rng(4)
+    # spline tables fitted by the reference's trep.Spline (host side, trep/spline.py) for the mirror
+    import json
+    sp = trep.Spline(S.SPLINE_DATA)
+    with open(os.path.join(ROOT, "trep_b200", "data", "spline_pendulum.json"), "w") as fh:
+        json.dump({"x_points": np.array(sp._x_points).tolist(),
+                   "coefficients": np.array(sp._coefficients).tolist()}, fh)
     for name in S.EXTRA:
         d = M.flatten_trep_system(REF_BUILDERS[name](), name=name)
         assert S.named_desc(name).equal(d), "native model mirror disagrees with the reference for " + name
@@ -78,7 +84,32 @@ def main():
     out["roll_u_desc"] = np.array("u = (sin(3 t), 0.5 cos(2 t), 0.8 sin(t), 0.3 cos(t), -0.6 sin(2 t)), t = t2 of the previous step")
     np.savez_compressed(os.path.join(GG.GOLD, "wrench_arm.npz"), **out)
     print("golden wrench_arm: case iters", [int(c["iters"]) for c in cases])
+    spline_pendulum(np.random.default_rng(5))
+
+
+def spline_pendulum(rng):
+    # NonlinearConfigSpring: the reference's V_dqdqdq has the wrong sign
+    # (nonlinear_config_spring.c:53: "-Spline_ddy * -m * m"), so its second-derivative tensors are not
+    # recorded; the tests check those by finite differences of the first derivatives instead.
+    system = REF_BUILDERS["spline_pendulum"]()
+    mvi = trep.MidpointVI(system, num_threads=1)
+    nq = mvi.nq
+    cases = []
+    for c in range(16):
+        # m q + b sweeps every spline segment, including both extrapolation pieces
+        q1 = np.array([rng.uniform(-2.4, 2.2), rng.uniform(-math.pi, math.pi)])
+        p1 = rng.normal(0, 1.0, nq)
+        hint = None if c % 2 == 0 else q1 + rng.normal(0, 1e-2, nq)
+        cases.append(GG.record_case(mvi, None, 0.01 * c, 0.01 * c + 0.01, q1, p1, np.zeros(0), np.zeros(0), hint,
+                                    None, want_d2=False))
+    out = GG.stack(cases)
+    out.update(GG.rollout(mvi, [1.2, -0.5], [1.2, -0.5], 0.01, 600, sample=100))
+    np.savez_compressed(os.path.join(GG.GOLD, "spline_pendulum.npz"), **out)
+    print("golden spline_pendulum: case iters", [int(c["iters"]) for c in cases])
 
 
 if __name__ == "__main__":
+    if "--spline-only" in sys.argv:
+        spline_pendulum(np.random.default_rng(5))
+        sys.exit(0)
     main()

@@ -141,6 +141,20 @@ def ref_wrench_arm():
     return system
 
 
+def ref_spline_pendulum():
+    """Same script as trep_b200/systems.py:spline_pendulum with the reference's own classes."""
+    from trep_b200.systems import SPLINE_DATA
+    system = trep.System()
+    system.import_frames([
+        rx('theta1'), [tz(-1.0, mass=1.0), [
+            ry('theta2'), [tz(-0.6, mass=0.5)]]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.potentials.NonlinearConfigSpring(system, 'theta1', trep.Spline(SPLINE_DATA), m=1.5, b=0.1)
+    trep.potentials.ConfigSpring(system, 'theta2', k=2.0, q0=0.3)
+    trep.forces.Damping(system, 0.02)
+    return system
+
+
 def ref_puppet():
     puppet = trep.puppets.Puppet(joint_forces=False, string_forces=False, string_constraints=True)
     puppet.q = {
@@ -156,7 +170,7 @@ REF_BUILDERS = {
     "damped_pendulum": ref_damped_pendulum, "pend_on_cart1": lambda: ref_pend_on_cart(False),
     "pend_on_cart2": lambda: ref_pend_on_cart(True), "dual_pendulums": ref_dual_pendulums,
     "tase_pendulum": ref_tase_pendulum, "puppet": ref_puppet,
-    "pccd": ref_pccd, "wrench_arm": ref_wrench_arm,
+    "pccd": ref_pccd, "wrench_arm": ref_wrench_arm, "spline_pendulum": ref_spline_pendulum,
 }
 
 

@@ -36,7 +36,7 @@ def ref():
 
 
 # LinearSpring / LinearDamper, PointOnPlane, wrenches: thread-per-instance kernels only
-COOP_UNSUPPORTED = {"dual_pendulums", "pccd", "wrench_arm"}
+COOP_UNSUPPORTED = {"dual_pendulums", "pccd", "wrench_arm", "spline_pendulum"}
 
 
 def _systems(lib, name):
@@ -504,7 +504,7 @@ def test_extra_plugin_kinds_golden_cases(lib, name):
 
 
 @pytest.mark.parametrize("pairwise", [False, True])
-@pytest.mark.parametrize("name", G.EXTRA)
+@pytest.mark.parametrize("name", G.EXTRA_D2)
 def test_extra_plugin_kinds_second_derivatives(lib, name, pairwise):
     g = G.golden(name)
     s = lib.System(G.desc(name), d2_pairwise=pairwise)
@@ -558,6 +558,10 @@ def test_extra_plugin_kinds_random_vs_reference(lib, ref, name):
         q1 = g["roll_q"][idx] + rng.normal(0, 0.01, (B, nq))
         p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, nd))
         lam = g["roll_lambda"][idx - 1]
+    elif name == "spline_pendulum":
+        q1 = np.stack([rng.uniform(-2.4, 2.2, B), rng.uniform(-np.pi, np.pi, B)], axis=1)
+        p1 = rng.normal(0, 1.0, (B, nd))
+        lam = None
     else:
         q1 = np.stack([rng.uniform(-np.pi, np.pi, B), rng.uniform(-1.2, 1.2, B), rng.uniform(-0.3, 0.5, B)], axis=1)
         p1 = rng.normal(0, 1.0, (B, nd))
@@ -573,3 +577,36 @@ def test_extra_plugin_kinds_random_vs_reference(lib, ref, name):
     for k in ("q2", "p2", "lambda1", "A", "B"):
         G.assert_close(out[k], want[k], "%s %s" % (name, k))
     assert int(np.sum(out["iters"] != want["iters"])) <= 1
+
+
+@pytest.mark.parametrize("pairwise", [False, True])
+def test_spline_spring_second_derivatives_by_finite_differences(lib, pairwise):
+    """NonlinearConfigSpring: the reference's V_dqdqdq has a sign error
+    (potentials/nonlinear_config_spring.c:53), so its second-derivative tensors cannot serve as the
+    oracle for this plugin; both schemes are checked against central differences of this library's own
+    first derivatives (which match the reference) instead."""
+    s = lib.System(G.desc("spline_pendulum"), d2_pairwise=pairwise)
+    rng = np.random.default_rng(3)
+    q1 = np.array([[0.45, -0.3]]); p1 = rng.normal(0, 1, (1, 2))
+    out = s.deriv2(q1, p1, t1=0.0, dt=0.01)
+    eps = 1e-6
+    for a in range(2):
+        dq = np.zeros((1, 2)); dq[0, a] = eps
+        lp = s.linearize(q1 + dq, p1, t1=0.0, dt=0.01, want_raw=True, tolerance=1e-13)
+        lm = s.linearize(q1 - dq, p1, t1=0.0, dt=0.01, want_raw=True, tolerance=1e-13)
+        for raw, tens in (("q2_dq1", "q2_dq1dq1"), ("p2_dq1", "p2_dq1dq1"), ("q2_dp1", "q2_dq1dp1"), ("p2_dp1", "p2_dq1dp1")):
+            fd = (lp[raw] - lm[raw]) / (2 * eps)
+            assert np.max(np.abs(fd[0] - out[tens][0, a])) < 2e-6 * max(1.0, np.max(np.abs(fd))), (tens, a)
+
+
+def test_spline_pendulum_rollout(lib):
+    g = G.golden("spline_pendulum")
+    s = lib.System(G.desc("spline_pendulum"))
+    dt, nsteps, sample = float(g["roll_dt"]), int(g["roll_nsteps"]), int(g["roll_sample"])
+    p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+    G.assert_close(p0[0], g["roll_p_init"], "spline_pendulum p_init")
+    out = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, sample_every=sample)
+    assert out["status"][0] == 0
+    ns = nsteps // sample
+    G.assert_close(out["traj_q"][0, :ns], g["roll_q"][1:1 + ns], "spline_pendulum traj q", rtol=1e-7)
+    G.assert_close(out["traj_p"][0, :ns], g["roll_p"][1:1 + ns], "spline_pendulum traj p", rtol=1e-7)

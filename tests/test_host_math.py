@@ -136,7 +136,7 @@ def test_puppet_rollout():
     assert iters == int(g["roll_iters"].sum())
 
 
-D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"] + G.EXTRA
+D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"] + G.EXTRA_D2
 
 
 @pytest.mark.parametrize("method", ["pair", "jac"])

@@ -23,7 +23,7 @@ def test_frame_order_is_preorder_and_configs_dyn_then_kin():
 def test_named_small_systems_sizes():
     want = {"pendulum1": (3, 1, 0, 0), "pendulum5": (11, 5, 0, 0), "damped_pendulum": (4, 1, 0, 0),
             "pend_on_cart1": (4, 2, 0, 1), "pend_on_cart2": (4, 2, 0, 2), "dual_pendulums": (6, 2, 0, 0),
-            "pccd": (24, 7, 0, 0), "wrench_arm": (7, 3, 0, 5)}
+            "pccd": (24, 7, 0, 0), "wrench_arm": (7, 3, 0, 5), "spline_pendulum": (5, 2, 0, 0)}
     for n, (nf, nd, nk, nu) in want.items():
         d = G.desc(n)
         assert (d.n_frames, d.nd, d.nk, d.nu) == (nf, nd, nk, nu), n

@@ -229,6 +229,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     if (nq > 64) { P.why = "more than 64 configs"; return P; }
     for (int i = 0; i < d->n_potentials; ++i)
         if (d->pot_kind[i] == TREPB_POT_LINEAR_SPRING) { P.why = "LinearSpring potential"; return P; }
+        else if (d->pot_kind[i] == TREPB_POT_NONLINEAR_CONFIG_SPRING) { P.why = "NonlinearConfigSpring potential"; return P; }
     for (int i = 0; i < d->n_forces; ++i)
         if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
         else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }

@@ -124,7 +124,7 @@ TREPB_HD void d2jac_build_nz(const Sys& sys, const NzMaps& nz, int lane, int nla
         bool l = (Fj >= 0 && sys.dep(Fj, i)) || (Fi >= 0 && sys.dep(Fi, j));
         for (int p = 0; p < sys.NPOT(); ++p) {
             const int kind = sys.pot_kind(p);
-            if (kind == P_CONFIG_SPRING) l = l || (i == j && i == sys.pot_i(p, 0));
+            if (kind == P_CONFIG_SPRING || kind == P_NONLINEAR_CONFIG_SPRING) l = l || (i == j && i == sys.pot_i(p, 0));
             else if (kind == P_LINEAR_SPRING) {
                 const int A = sys.pot_i(p, 0), B = sys.pot_i(p, 1);
                 l = l || ((sys.dep(A, i) || sys.dep(B, i)) && (sys.dep(A, j) || sys.dep(B, j)));

@@ -114,6 +114,9 @@ TREPB_HD void sincos_(double x, double* s, double* c) {
 #endif
 }
 TREPB_HD bool isnan_(double x) { return isnan(x); }
+// value part of a (hyper-)dual number / the number itself
+TREPB_HD double val_(double x) { return x; }
+template <class T> TREPB_HD double val_(const T& x) { return x.v; }
 TREPB_HD double sqrt_(double x) { return sqrt(x); }
 
 // ---------------------------------------------------------------------------------------------
@@ -776,6 +779,25 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
             const double k = sys.pot_d(p, 0), q0 = sys.pot_d(p, 1);
             ws.Lq(c) -= k * (ws.qe(c) - q0);
             if (order >= 2) ws.Lqq(c, c) -= k;
+        } else if (kind == P_NONLINEAR_CONFIG_SPRING) {
+            // dV/dq = -y(m q + b) with y a piecewise quintic (potentials/nonlinear_config_spring.c:23-47,
+            // spline.c:7-62).  i = config, dpool offset, number of x points; d = m, b;
+            // dpool: x points [n], then coefficients [n-1][6] (highest power first).
+            const int c = sys.pot_i(p, 0), off = sys.pot_i(p, 1), n = sys.pot_i(p, 2);
+            const double m = sys.pot_d(p, 0), b = sys.pot_d(p, 1);
+            const Real x = m * ws.qe(c) + b;
+            const double xv = val_(x);
+            int seg = 0;                                   // get_index (spline.c:7-22)
+            if (xv >= sys.dpool(off + n - 1)) seg = n - 2;
+            else if (!(xv < sys.dpool(off))) { while (xv >= sys.dpool(off + seg + 1)) ++seg; }
+            const int co = off + n + 6 * seg;
+            const double c0 = sys.dpool(co), c1 = sys.dpool(co + 1), c2 = sys.dpool(co + 2), c3 = sys.dpool(co + 3),
+                         c4 = sys.dpool(co + 4), c5 = sys.dpool(co + 5);
+            const Real dx = x - sys.dpool(off + seg);
+            const Real dx2 = dx * dx, dx3 = dx2 * dx, dx4 = dx3 * dx, dx5 = dx4 * dx;
+            ws.Lq(c) += c0 * dx5 + c1 * dx4 + c2 * dx3 + c3 * dx2 + c4 * dx + c5;
+            if (order >= 2)
+                ws.Lqq(c, c) += (5.0 * c0 * dx4 + 4.0 * c1 * dx3 + 3.0 * c2 * dx2 + 2.0 * c3 * dx + c4) * m;
         } else if (kind == P_LINEAR_SPRING) {
             const int A = sys.pot_i(p, 0), B = sys.pot_i(p, 1);
             const double k = sys.pot_d(p, 0), x0 = sys.pot_d(p, 1);

@@ -110,7 +110,13 @@ inline bool pack_system(const trepb_sysdesc* d, PackedSys* out, std::string* err
             mark_world(ii[0]); mark_world(ii[1]); has_pairs = 1; has_pairs_mid = 1;
         } else if (k == TREPB_POT_CONFIG_SPRING) {
             if (ii[0] < 0 || ii[0] >= nq) return fail("ConfigSpring config index out of range");
-        } else return fail("unknown potential kind (Python-defined / spline potentials have no device implementation)");
+        } else if (k == TREPB_POT_NONLINEAR_CONFIG_SPRING) {
+            if (ii[0] < 0 || ii[0] >= nq) return fail("NonlinearConfigSpring config index out of range");
+            if (ii[2] < 2 || ii[1] < 0 || ii[1] + ii[2] + 6 * (ii[2] - 1) > d->n_dpool)
+                return fail("NonlinearConfigSpring spline pool out of range");
+            for (int j = 1; j < ii[2]; ++j)
+                if (!(d->dpool[ii[1] + j] > d->dpool[ii[1] + j - 1])) return fail("spline x points must increase");
+        } else return fail("unknown potential kind (Python-defined potentials have no device implementation)");
     }
     for (int i = 0; i < nfo; ++i) {
         const int k = d->force_kind[i];

@@ -23,7 +23,7 @@
 namespace trepb {
 
 enum FrameKind { K_WORLD = 0, K_TX, K_TY, K_TZ, K_RX, K_RY, K_RZ, K_CONST_SE3 };
-enum PotKind { P_GRAVITY = 0, P_LINEAR_SPRING, P_CONFIG_SPRING };
+enum PotKind { P_GRAVITY = 0, P_LINEAR_SPRING, P_CONFIG_SPRING, P_NONLINEAR_CONFIG_SPRING };
 enum ForceKind { F_DAMPING = 0, F_CONFIG, F_LINEAR_DAMPER, F_BODY_WRENCH, F_HYBRID_WRENCH, F_SPATIAL_WRENCH };
 enum ConKind { C_DISTANCE = 0, C_POINT1D, C_PLANE };
 

@@ -20,7 +20,7 @@ WORLD, TX, TY, TZ, RX, RY, RZ, CONST_SE3 = range(8)
 KIND_NAMES = ["WORLD", "TX", "TY", "TZ", "RX", "RY", "RZ", "CONST_SE3"]
 
 # potential kinds
-POT_GRAVITY, POT_LINEAR_SPRING, POT_CONFIG_SPRING = range(3)
+POT_GRAVITY, POT_LINEAR_SPRING, POT_CONFIG_SPRING, POT_NONLINEAR_CONFIG_SPRING = range(4)
 # force kinds
 FORCE_DAMPING, FORCE_CONFIG, FORCE_LINEAR_DAMPER, FORCE_BODY_WRENCH, FORCE_HYBRID_WRENCH, FORCE_SPATIAL_WRENCH = range(6)
 # constraint kinds

@@ -264,6 +264,41 @@ class ConfigSpring:
         return D.POT_CONFIG_SPRING, _pad4([cidx[id(self.config)]], -1), _pad4([self.k, self.q0], 0.0)
 
 
+class Spline:
+    """Piecewise quintic y(x) as the reference evaluates it (trep/_trep/spline.c:7-62): x points and,
+    per segment, six coefficients (highest power first) of dx = x - x_i.  The reference fits the
+    coefficients on the host (trep/spline.py, numpy.linalg.solve); the batched path only evaluates,
+    so this mirror takes the fitted tables - from a reference ``trep.Spline`` via
+    ``Spline.from_reference`` or from stored arrays."""
+    def __init__(self, x_points, coefficients):
+        self.x_points = np.ascontiguousarray(x_points, dtype=float)
+        self.coefficients = np.ascontiguousarray(coefficients, dtype=float).reshape(-1, 6)
+        if self.coefficients.shape[0] != self.x_points.shape[0] - 1:
+            raise ValueError("a spline over n x points has n-1 coefficient rows")
+
+    @staticmethod
+    def from_reference(spline):
+        return Spline(np.array(spline._x_points), np.array(spline._coefficients))
+
+
+class NonlinearConfigSpring:
+    """dV/dq = -spline(m q + b) (trep/potentials/nonlinear_config_spring.py)."""
+    def __init__(self, system, config, spline, m=1.0, b=0.0, name=None):
+        self.system, self.name = system, name
+        self.config = system.get_config(config)
+        if self.config is None:
+            raise ValueError("Could not find config %r" % (config,))
+        self.spline, self.m, self.b = spline, float(m), float(b)
+        system.potentials.append(self)
+
+    def _record(self, fidx, cidx, ipool, dpool):
+        off = len(dpool)
+        dpool.extend(self.spline.x_points.tolist())
+        dpool.extend(self.spline.coefficients.reshape(-1).tolist())
+        return (D.POT_NONLINEAR_CONFIG_SPRING, [cidx[id(self.config)], off, len(self.spline.x_points), -1],
+                _pad4([self.m, self.b], 0.0))
+
+
 # ---- forces (trep/forces/*.py) -------------------------------------------------------------
 class Damping:
     def __init__(self, system, default=0.0, coefficients={}, name=None):
@@ -415,6 +450,7 @@ class _NS:
 
 potentials = _NS()
 potentials.Gravity, potentials.LinearSpring, potentials.ConfigSpring = Gravity, LinearSpring, ConfigSpring
+potentials.NonlinearConfigSpring = NonlinearConfigSpring
 forces = _NS()
 forces.Damping, forces.ConfigForce, forces.LinearDamper = Damping, ConfigForce, LinearDamper
 forces.BodyWrench, forces.HybridWrench, forces.SpatialWrench = BodyWrench, HybridWrench, SpatialWrench
@@ -431,7 +467,7 @@ def flatten_trep_system(system, name="") -> D.SystemDesc:
     """Build a SystemDesc from a live reference ``trep.System`` without importing trep.
 
     Raises ``TypeError`` for any potential/force/constraint kind that has no device
-    implementation (Python-defined plugins, spline springs): the batched
+    implementation (Python-defined plugins): the batched
     path refuses rather than falls back.
     """
     frames = list(system.frames)
@@ -477,6 +513,13 @@ def flatten_trep_system(system, name="") -> D.SystemDesc:
         elif cls == "ConfigSpring":
             pk.append(D.POT_CONFIG_SPRING)
             pi.append([cidx[id(p.config)], -1, -1, -1]); pd.append([float(p.k), float(p.q0), 0, 0])
+        elif cls == "NonlinearConfigSpring":
+            off = len(dpool)
+            xs = np.array(p.spline._x_points, dtype=float)
+            dpool.extend(xs.tolist())
+            dpool.extend(np.array(p.spline._coefficients, dtype=float).reshape(-1).tolist())
+            pk.append(D.POT_NONLINEAR_CONFIG_SPRING)
+            pi.append([cidx[id(p.config)], off, len(xs), -1]); pd.append([float(p._m), float(p._b), 0, 0])
         else:
             raise TypeError("potential %s has no batched device implementation" % cls)
     fk, fi, fd = [], [], []

@@ -136,6 +136,28 @@ def wrench_arm() -> M.System:
     return s
 
 
+SPLINE_DATA = [(-2.0, -3.0), (-0.5, -0.4, 1.0), (0.0, 0.0), (0.7, 0.9), (2.0, 1.5, 0.2)]
+
+
+def spline_pendulum() -> M.System:
+    """Two-link pendulum with a spline-defined joint spring on the first joint and a linear one on
+    the second (trep/potentials/nonlinear_config_spring.py; spline data in the style of
+    examples/spline.py).  The quintic coefficients are the ones the reference's trep.Spline fits to
+    SPLINE_DATA on the host; they are stored in data/spline_pendulum.json by oracle/gen_golden_f4.py."""
+    import json
+    with open(os.path.join(_DATA, "spline_pendulum.json")) as fh:
+        tab = json.load(fh)
+    s = M.System(name="spline_pendulum")
+    s.import_frames([
+        M.rx("theta1"), [M.tz(-1.0, mass=1.0), [
+            M.ry("theta2"), [M.tz(-0.6, mass=0.5)]]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.NonlinearConfigSpring(s, "theta1", M.Spline(tab["x_points"], tab["coefficients"]), m=1.5, b=0.1)
+    M.ConfigSpring(s, "theta2", k=2.0, q0=0.3)
+    M.Damping(s, 0.02)
+    return s
+
+
 def puppet_desc() -> SystemDesc:
     """Marionette with string constraints (trep/puppets/puppets.py:220-310,
     examples/puppet-optimization.py:217-218): nd=22, nk=18, nc=6, 86 frames."""
@@ -150,6 +172,7 @@ def named_desc(name) -> SystemDesc:
         "damped_pendulum": damped_pendulum, "pend_on_cart1": lambda: pend_on_cart(False),
         "pend_on_cart2": lambda: pend_on_cart(True), "dual_pendulums": dual_pendulums,
         "tase_pendulum": tase_pendulum, "pccd": pccd, "wrench_arm": wrench_arm,
+        "spline_pendulum": spline_pendulum,
     }
     return table[name]().describe()
 
@@ -157,4 +180,4 @@ def named_desc(name) -> SystemDesc:
 NAMED = ["pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2",
          "dual_pendulums", "tase_pendulum", "puppet"]
 # systems exercising the plugin kinds beyond BASELINE.json's configs
-EXTRA = ["pccd", "wrench_arm"]
+EXTRA = ["pccd", "wrench_arm", "spline_pendulum"]
