@@ -239,6 +239,36 @@ typedef struct trepb_lqr_args {
 int trepb_lqr_batch(int device, const trepb_lqr_args* args);                   /* host pointers   */
 int trepb_lqr_batch_dev(int device, const trepb_lqr_args* args, void* stream); /* device pointers */
 
+/* Time-varying discrete LQ problem with linear and cross cost terms, batched over rollouts:
+ * trep.discopt.dlqr.solve_tv_lq (trep/discopt/dlqr.py:41-81), the solve inside
+ * DOptimizer.calc_descent_direction (trep/discopt/doptimizer.py:228-318).
+ *     P = Q(K), b = q[K];  for k = K-1..0:
+ *         gamma = R(k) + B^T P B,  Kp = B^T P A + S(k)^T,  C[k] = gamma^-1 (B^T b + r[k]),  K[k] = gamma^-1 Kp,
+ *         b = q[k] - K[k]^T r[k] + (A^T - K[k]^T B^T) b,   P = Q(k) + A^T P A - Kp^T K[k],  P = (P + P^T)/2
+ * Same kernel as trepb_lqr_batch (one CTA per rollout, P / P A / A[k] in shared memory); the affine
+ * recursion rides along as one more right-hand side of the gamma factorization.               */
+typedef struct trepb_lq_args {
+    int64_t batch;            /* rollouts                                                          */
+    int32_t nsteps;           /* K                                                                 */
+    int32_t nX, nU;
+    int32_t cost_per_rollout; /* 0: Q, S, R, q, r shared by the batch; 1: one set per rollout      */
+    const double* A;          /* [batch][K][nX][nX]                                                */
+    const double* B;          /* [batch][K][nX][nU]                                                */
+    const double* Q;          /* ([batch])[K+1][nX][nX]                                            */
+    const double* S;          /* ([batch])[K][nX][nU] cross term, NULL = zero                      */
+    const double* R;          /* ([batch])[K][nU][nU]                                              */
+    const double* q;          /* ([batch])[K+1][nX]                                                */
+    const double* r;          /* ([batch])[K][nU]                                                  */
+    double* Kfb;              /* [batch][K][nU][nX] out                                            */
+    double* C;                /* [batch][K][nU] out (affine part of the optimal control)           */
+    double* P0;               /* [batch][nX][nX] out, may be NULL                                  */
+    double* b0;               /* [batch][nX] out, may be NULL                                      */
+    int32_t* status;          /* [batch] 0 ok, -2 singular gamma                                   */
+} trepb_lq_args;
+
+int trepb_lq_batch(int device, const trepb_lq_args* args);                   /* host pointers   */
+int trepb_lq_batch_dev(int device, const trepb_lq_args* args, void* stream); /* device pointers */
+
 /* p2 from two consecutive configurations (initialize_from_configs). q0,q1: [B][nq] -> p: [B][nd] */
 int trepb_calc_p2_batch(trepb_system* sys, int64_t batch, double dt,
                         const double* q0, const double* q1, double* p);

@@ -457,6 +457,32 @@ def test_lqr_sweep_matches_reference(lib, ref):
             G.assert_close(Pg[r], want.P, "lqr P0 nX=%d rollout %d" % (nX, r), rtol=1e-9)
 
 
+def test_lq_sweep_matches_reference(lib, ref):
+    """trepb_lq_batch against the reference's discopt.dlqr.solve_tv_lq (dlqr.py:41-81): linear and
+    cross cost terms, costs shared by the batch and one set per rollout, with and without S."""
+    from trep.discopt import dlqr
+    rng = np.random.default_rng(22)
+    for nX, nU, K, R_, per_rollout, with_s in ((4, 1, 50, 3, False, True), (80, 18, 20, 2, True, True),
+                                               (7, 3, 30, 4, True, False), (5, 2, 10, 1, False, False)):
+        A = np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (R_, K, nX, nX))
+        B = rng.normal(0, 1.0, (R_, K, nX, nU))
+        nc = R_ if per_rollout else 1
+        Qs = np.stack([np.stack([np.eye(nX) * (1 + 0.1 * k + 0.3 * c) for k in range(K + 1)]) for c in range(nc)])
+        Rs = np.stack([np.stack([np.eye(nU) * (2 + 0.05 * k + 0.2 * c) for k in range(K)]) for c in range(nc)])
+        Ss = rng.normal(0, 0.05, (nc, K, nX, nU)) if with_s else None
+        q = rng.normal(0, 1, (nc, K + 1, nX)); r = rng.normal(0, 1, (nc, K, nU))
+        sq = (lambda x: x) if per_rollout else (lambda x: None if x is None else x[0])
+        Kg, Cg, Pg, bg = lib.solve_tv_lq(A, B, sq(q), sq(r), sq(Qs), sq(Ss), sq(Rs))
+        for i in range(R_):
+            c = i if per_rollout else 0
+            Sf = (lambda k: Ss[c][k]) if with_s else (lambda k: np.zeros((nX, nU)))
+            want = dlqr.solve_tv_lq(list(A[i]), list(B[i]), list(q[c]), list(r[c]), lambda k: Qs[c][k], Sf, lambda k: Rs[c][k])
+            G.assert_close(Kg[i], np.stack(want.K), "lq gains nX=%d rollout %d" % (nX, i), rtol=1e-9)
+            G.assert_close(Cg[i], np.stack(want.C), "lq affine term nX=%d rollout %d" % (nX, i), rtol=1e-9)
+            G.assert_close(Pg[i], want.P, "lq P0 nX=%d rollout %d" % (nX, i), rtol=1e-9)
+            G.assert_close(bg[i], want.b, "lq b0 nX=%d rollout %d" % (nX, i), rtol=1e-9)
+
+
 def test_feedback_controller_pipeline(lib, ref):
     """DSystem.calc_feedback_controller + project (dsystem.py:426-457, 474-494) end to end on the GPU
     (linearize_trajectory -> Riccati sweep -> closed-loop rollout) against the reference doing the

@@ -3,7 +3,8 @@ C ABI (include/trepb.h).  The CUDA library is built in-tree by ``python -m trep_
 
     from trep_b200 import MidpointVI, DSystem, systems     # needs libtrepb.so and a GPU to compute
 """
-__all__ = ["MidpointVI", "DSystem", "ConvergenceError", "systems", "model", "desc"]
+__all__ = ["MidpointVI", "DSystem", "ConvergenceError", "systems", "model", "desc", "trajectory",
+           "save_trajectory", "load_trajectory"]
 
 
 def __getattr__(name):
@@ -14,7 +15,10 @@ def __getattr__(name):
     if name == "DSystem":
         from .discopt import DSystem
         return DSystem
-    if name in ("systems", "model", "desc", "lib", "build", "discopt", "midpointvi"):
+    if name in ("save_trajectory", "load_trajectory"):
+        from . import trajectory
+        return getattr(trajectory, name)
+    if name in ("systems", "model", "desc", "lib", "build", "discopt", "midpointvi", "trajectory"):
         import importlib
         return importlib.import_module("." + name, __name__)
     raise AttributeError(name)

@@ -29,6 +29,10 @@ struct LqrParams {
     int q_per_step, r_per_step;
     double *Kfb, *P0;
     int* status;
+    // affine-quadratic extension (solve_tv_lq, dlqr.py:41-81); all null / zero for the plain LQR
+    const double *S, *qv, *rv;         // cross term [K][nX][nU] (may be null), linear costs [K+1][nX], [K][nU]
+    long long Qs, Rs, Ss, qs, rs;      // per-rollout strides of Q, R, S, q, r (0: shared by the batch)
+    double *C, *b0;                    // [batch][K][nU], [batch][nX]
 };
 
 // C[i][j] (op)= sum_m Xt[m][i] * Y[m][j]   for i < M, j < N, m < Kd ; 4 x 4 tiles over the CTA.
@@ -132,24 +136,44 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
     double* rd = scl + nU;                         // [nU]
     int* piv = (int*)(rd + nU);                    // [nU] + swp [nU]
     int* swp = piv + nU;
+    // affine part (solve_tv_lq): b [nX], A^T b [nX], g = B^T b [nU], r(k) + g -> C[k] [nU]
+    double* bv = (double*)(swp + nU);               // 2 nU ints = nU doubles: stays 8-byte aligned
+    double* ab = bv + nX;
+    double* gv = ab + nX;
+    double* cv = gv + nU;
+    const bool affine = p.qv != nullptr;
     __shared__ int s_fail;
     for (long r = blockIdx.x; r < p.batch; r += gridDim.x) {
         const double* Ar = p.A + r * (long)K * nX * nX;
         const double* Br = p.B + r * (long)K * nX * nU;
+        const double* Qr = p.Q + r * p.Qs;
+        const double* Rr = p.R + r * p.Rs;
+        const double* Sr = p.S ? p.S + r * p.Ss : nullptr;
+        const double* qr = affine ? p.qv + r * p.qs : nullptr;
+        const double* rr = affine ? p.rv + r * p.rs : nullptr;
         double* Kr = p.Kfb + r * (long)K * nU * nX;
         if (threadIdx.x == 0) s_fail = 0;
-        async_copy(P, p.Q + (p.q_per_step ? (long)K * nX * nX : 0), nX * nX);     // P = Q(K)
+        async_copy(P, Qr + (p.q_per_step ? (long)K * nX * nX : 0), nX * nX);     // P = Q(K)
         async_copy(As, Ar + (long)(K - 1) * nX * nX, nX * nX);
         async_copy(Bs, Br + (long)(K - 1) * nX * nU, nX * nU);
-        async_copy(Rs, p.R + (p.r_per_step ? (long)(K - 1) * nU * nU : 0), nU * nU);
+        async_copy(Rs, Rr + (p.r_per_step ? (long)(K - 1) * nU * nU : 0), nU * nU);
+        if (affine) for (int c = threadIdx.x; c < nX; c += blockDim.x) bv[c] = qr[(long)K * nX + c];   // b = q[K]
         for (int k = K - 1; k >= 0; --k) {
             async_wait();                                          // A[k], B[k], R(k) (and P) have landed
             __syncthreads();
+            if (affine) {
+                // A^T b and g = B^T b with the old b (columns of A / B, one per thread)
+                for (int c = threadIdx.x; c < nX + nU; c += blockDim.x) {
+                    double acc = 0.0;
+                    if (c < nX) { for (int m = 0; m < nX; ++m) acc += As[m * nX + c] * bv[m]; ab[c] = acc; }
+                    else { const int i = c - nX; for (int m = 0; m < nX; ++m) acc += Bs[m * nU + i] * bv[m]; gv[i] = acc; }
+                }
+            }
             gemm_tn<VEC>(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
             gemm_tn<VEC>(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
             for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rs[e];
             __syncthreads();
-            async_copy(P, p.Q + (p.q_per_step ? (long)k * nX * nX : 0), nX * nX);   // P is dead: start P <- Q(k)
+            async_copy(P, Qr + (p.q_per_step ? (long)k * nX * nX : 0), nX * nX);   // P is dead: start P <- Q(k)
             // warp 0: gamma = R + B^T P B and its LU;  the other warps meanwhile: Kp = B^T P A
             if (threadIdx.x < 32) {
                 gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 32);
@@ -161,14 +185,31 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
             }
             __syncthreads();
             if (s_fail) break;
-            // K[k] = gamma^-1 Kp, one right-hand side per thread (W is free: it becomes K[k], [nU][nX])
-            for (int c = threadIdx.x; c < nX; c += blockDim.x) {
-                for (int i = 0; i < nU; ++i) W[i * nX + c] = Kp[i * nX + c];
-                col_solve(G, ldg, nU, swp, rd, W + c, nX);
+            // K[k] = gamma^-1 Kp, one right-hand side per thread (W is free: it becomes K[k], [nU][nX]);
+            // with a cross term Kp = B^T P A + S(k)^T; the affine right-hand side B^T b + r(k) is one more column
+            for (int c = threadIdx.x; c < nX + (affine ? 1 : 0); c += blockDim.x) {
+                if (c < nX) {
+                    if (Sr) { const double* Sk = Sr + (long)k * nX * nU + c * nU; for (int i = 0; i < nU; ++i) Kp[i * nX + c] += Sk[i]; }
+                    for (int i = 0; i < nU; ++i) W[i * nX + c] = Kp[i * nX + c];
+                    col_solve(G, ldg, nU, swp, rd, W + c, nX);
+                } else {
+                    for (int i = 0; i < nU; ++i) { gv[i] += rr[(long)k * nU + i]; cv[i] = gv[i]; }   // gv = r + B^T b
+                    col_solve(G, ldg, nU, swp, rd, cv, 1);
+                    double* Ck = p.C + (r * (long)K + k) * nU;
+                    for (int i = 0; i < nU; ++i) Ck[i] = cv[i];
+                }
             }
             __syncthreads();
             double* Kk = Kr + (long)k * nU * nX;
             for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) Kk[e] = W[e];
+            if (affine) {
+                // b = q[k] - K^T r + (A^T - K^T B^T) b = q[k] + A^T b - K^T (r + B^T b)
+                for (int c = threadIdx.x; c < nX; c += blockDim.x) {
+                    double acc = qr[(long)k * nX + c] + ab[c];
+                    for (int i = 0; i < nU; ++i) acc -= W[i * nX + c] * gv[i];
+                    bv[c] = acc;
+                }
+            }
             async_wait();                                          // Q(k) is in P
             __syncthreads();
             gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);     // P += A^T (P A)
@@ -176,7 +217,7 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
             if (k > 0) {                                           // A, B are dead: fetch the next step's
                 async_copy(As, Ar + (long)(k - 1) * nX * nX, nX * nX);
                 async_copy(Bs, Br + (long)(k - 1) * nX * nU, nX * nU);
-                if (p.r_per_step) async_copy(Rs, p.R + (long)(k - 1) * nU * nU, nU * nU);
+                if (p.r_per_step) async_copy(Rs, Rr + (long)(k - 1) * nU * nU, nU * nU);
             }
             gemm_tn<VEC>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);     // P -= Kp^T K[k]
             __syncthreads();
@@ -196,6 +237,7 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
             double* Pr = p.P0 + r * (long)nX * nX;
             for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) Pr[e] = P[e];
         }
+        if (affine && p.b0) for (int c = threadIdx.x; c < nX; c += blockDim.x) p.b0[r * (long)nX + c] = bv[c];
         if (threadIdx.x == 0) p.status[r] = s_fail ? ST_SINGULAR : ST_OK;
         __syncthreads();
     }
@@ -208,15 +250,13 @@ int lqr_fail(int code, const std::string& m) { last_error() = m; return code; }
 
 using namespace trepb;
 
-extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* stream) {
-    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
-    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
-    if (!a->A || !a->B || !a->Q || !a->R || !a->Kfb || !a->status) return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, Kfb and status are required");
-    if (a->batch == 0) return TREPB_OK;
+namespace {
+int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
-    const int nX = a->nX, nU = a->nU, ldg = nU | 1;
-    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * nU + (size_t)nU * ldg + 4 * (size_t)nU + 16;
+    const int nX = p.nX, nU = p.nU, ldg = nU | 1;
+    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * nU + (size_t)nU * ldg + 4 * (size_t)nU + 16
+                           + 2 * (size_t)nX + 2 * (size_t)nU + 2;
     const size_t smem = doubles * sizeof(double);
     int smem_optin = 0, sms = 0;
     e = cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
@@ -228,20 +268,85 @@ extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* st
     const void* fn = vec ? (const void*)lqr_kernel<true> : (const void*)lqr_kernel<false>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
-    LqrParams p;
-    p.batch = a->batch; p.K = a->nsteps; p.nX = nX; p.nU = nU;
-    p.A = a->A; p.B = a->B; p.Q = a->Q; p.R = a->R; p.q_per_step = a->q_per_step; p.r_per_step = a->r_per_step;
-    p.Kfb = a->Kfb; p.P0 = a->P0; p.status = a->status;
     const int tiles = ((nX + 3) / 4) * ((nX + 3) / 4);
     int block = ((tiles + 31) / 32) * 32;
     if (block > 512) block = 512;
     if (block < 64) block = 64;
-    const long long grid = a->batch < sms ? a->batch : sms;
-    if (vec) lqr_kernel<true><<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
-    else lqr_kernel<false><<<(int)grid, block, smem, (cudaStream_t)stream>>>(p);
+    const long long grid = p.batch < sms ? p.batch : sms;
+    if (vec) lqr_kernel<true><<<(int)grid, block, smem, stream>>>(p);
+    else lqr_kernel<false><<<(int)grid, block, smem, stream>>>(p);
     e = cudaGetLastError();
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     return TREPB_OK;
+}
+}  // namespace
+
+extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* stream) {
+    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    if (!a->A || !a->B || !a->Q || !a->R || !a->Kfb || !a->status) return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, Kfb and status are required");
+    if (a->batch == 0) return TREPB_OK;
+    LqrParams p{};
+    p.batch = a->batch; p.K = a->nsteps; p.nX = a->nX; p.nU = a->nU;
+    p.A = a->A; p.B = a->B; p.Q = a->Q; p.R = a->R; p.q_per_step = a->q_per_step; p.r_per_step = a->r_per_step;
+    p.Kfb = a->Kfb; p.P0 = a->P0; p.status = a->status;
+    return lqr_launch(device, p, (cudaStream_t)stream);
+}
+
+extern "C" int trepb_lq_batch_dev(int device, const trepb_lq_args* a, void* stream) {
+    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    if (!a->A || !a->B || !a->Q || !a->R || !a->q || !a->r || !a->Kfb || !a->C || !a->status)
+        return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, q, r, Kfb, C and status are required");
+    if (a->batch == 0) return TREPB_OK;
+    const long long K = a->nsteps, nX = a->nX, nU = a->nU, per = a->cost_per_rollout ? 1 : 0;
+    LqrParams p{};
+    p.batch = a->batch; p.K = a->nsteps; p.nX = a->nX; p.nU = a->nU;
+    p.A = a->A; p.B = a->B; p.Q = a->Q; p.R = a->R; p.q_per_step = 1; p.r_per_step = 1;
+    p.S = a->S; p.qv = a->q; p.rv = a->r;
+    p.Qs = per * (K + 1) * nX * nX; p.Rs = per * K * nU * nU; p.Ss = per * K * nX * nU;
+    p.qs = per * (K + 1) * nX; p.rs = per * K * nU;
+    p.Kfb = a->Kfb; p.C = a->C; p.P0 = a->P0; p.b0 = a->b0; p.status = a->status;
+    return lqr_launch(device, p, (cudaStream_t)stream);
+}
+
+extern "C" int trepb_lq_batch(int device, const trepb_lq_args* a) {
+    if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    if (!a->A || !a->B || !a->Q || !a->R || !a->q || !a->r || !a->Kfb || !a->C || !a->status)
+        return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, q, r, Kfb, C and status are required");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    const size_t Rn = (size_t)a->batch, K = (size_t)a->nsteps, nX = (size_t)a->nX, nU = (size_t)a->nU;
+    const size_t cm = a->cost_per_rollout ? Rn : 1;
+    // host -> device staging: {source, bytes} in, {destination, bytes} out
+    const void* in_src[7] = {a->A, a->B, a->Q, a->R, a->S, a->q, a->r};
+    const size_t in_n[7] = {Rn * K * nX * nX, Rn * K * nX * nU, cm * (K + 1) * nX * nX, cm * K * nU * nU,
+                            a->S ? cm * K * nX * nU : 0, cm * (K + 1) * nX, cm * K * nU};
+    void* out_dst[4] = {a->Kfb, a->C, a->P0, a->b0};
+    const size_t out_n[4] = {Rn * K * nU * nX, Rn * K * nU, a->P0 ? Rn * nX * nX : 0, a->b0 ? Rn * nX : 0};
+    double* din[7] = {nullptr}; double* dout[4] = {nullptr};
+    int* dS = nullptr;
+    int rc = TREPB_OK;
+#define LQ(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess && rc == TREPB_OK) rc = lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e_)); } while (0)
+    for (int i = 0; i < 7; ++i) if (in_n[i]) { LQ(cudaMalloc(&din[i], in_n[i] * 8)); if (rc == TREPB_OK) LQ(cudaMemcpy(din[i], in_src[i], in_n[i] * 8, cudaMemcpyHostToDevice)); }
+    for (int i = 0; i < 4; ++i) if (out_n[i]) LQ(cudaMalloc(&dout[i], out_n[i] * 8));
+    LQ(cudaMalloc(&dS, (Rn ? Rn : 1) * 4));
+    if (rc == TREPB_OK && Rn) {
+        trepb_lq_args d = *a;
+        d.A = din[0]; d.B = din[1]; d.Q = din[2]; d.R = din[3]; d.S = din[4]; d.q = din[5]; d.r = din[6];
+        d.Kfb = dout[0]; d.C = dout[1]; d.P0 = dout[2]; d.b0 = dout[3]; d.status = dS;
+        rc = trepb_lq_batch_dev(device, &d, nullptr);
+    }
+    if (rc == TREPB_OK) {
+        for (int i = 0; i < 4; ++i) if (out_n[i]) LQ(cudaMemcpy(out_dst[i], dout[i], out_n[i] * 8, cudaMemcpyDeviceToHost));
+        if (Rn) LQ(cudaMemcpy(a->status, dS, Rn * 4, cudaMemcpyDeviceToHost));
+    }
+#undef LQ
+    for (int i = 0; i < 7; ++i) cudaFree(din[i]);
+    for (int i = 0; i < 4; ++i) cudaFree(dout[i]);
+    cudaFree(dS);
+    return rc;
 }
 
 extern "C" int trepb_lqr_batch(int device, const trepb_lqr_args* a) {

@@ -51,6 +51,14 @@ class LqrArgs(C.Structure):
                 ("Kfb", C.c_void_p), ("P0", C.c_void_p), ("status", C.c_void_p)]
 
 
+class LqArgs(C.Structure):
+    _fields_ = [("batch", C.c_int64), ("nsteps", C.c_int32), ("nX", C.c_int32), ("nU", C.c_int32),
+                ("cost_per_rollout", C.c_int32),
+                ("A", C.c_void_p), ("B", C.c_void_p), ("Q", C.c_void_p), ("S", C.c_void_p), ("R", C.c_void_p),
+                ("q", C.c_void_p), ("r", C.c_void_p), ("Kfb", C.c_void_p), ("C", C.c_void_p), ("P0", C.c_void_p),
+                ("b0", C.c_void_p), ("status", C.c_void_p)]
+
+
 RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2_dk2",
        "l1_dq1", "l1_dp1", "l1_du1", "l1_dk2"]
 
@@ -91,6 +99,8 @@ _lib.trepb_project_batch.argtypes = [C.c_void_p, C.POINTER(ProjectArgs)]
 _lib.trepb_project_batch_dev.argtypes = [C.c_void_p, C.POINTER(ProjectArgs), C.c_void_p]
 _lib.trepb_lqr_batch.argtypes = [C.c_int, C.POINTER(LqrArgs)]
 _lib.trepb_lqr_batch_dev.argtypes = [C.c_int, C.POINTER(LqrArgs), C.c_void_p]
+_lib.trepb_lq_batch.argtypes = [C.c_int, C.POINTER(LqArgs)]
+_lib.trepb_lq_batch_dev.argtypes = [C.c_int, C.POINTER(LqArgs), C.c_void_p]
 _lib.trepb_linearize_batch.argtypes = [C.c_void_p, C.POINTER(LinArgs)]
 _lib.trepb_linearize_batch_dev.argtypes = [C.c_void_p, C.POINTER(LinArgs), C.c_void_p]
 _lib.trepb_deriv2_batch.argtypes = [C.c_void_p, C.POINTER(D2Args)]
@@ -114,7 +124,7 @@ EXPORTS = [
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
-    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_linearize_batch",
+    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
     "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
@@ -180,6 +190,39 @@ def solve_tv_lqr(A, B, Q, R, device=0):
     if np.any(status != 0):
         raise TrepbError(0, "singular gamma in the Riccati sweep of rollout(s) %s" % np.flatnonzero(status != 0)[:8])
     return (Kfb[0], P0[0]) if single else (Kfb, P0)
+
+
+def lq_raw(on_device, device, batch, nsteps, nX, nU, A, B, Q, S, R, q, r, Kfb, Cff, status, P0=None, b0=None,
+           cost_per_rollout=False, stream=None):
+    a = LqArgs(batch=batch, nsteps=nsteps, nX=nX, nU=nU, cost_per_rollout=1 if cost_per_rollout else 0,
+               A=_ptr(A), B=_ptr(B), Q=_ptr(Q), S=_ptr(S), R=_ptr(R), q=_ptr(q), r=_ptr(r), Kfb=_ptr(Kfb),
+               C=_ptr(Cff), P0=_ptr(P0), b0=_ptr(b0), status=_ptr(status))
+    if on_device:
+        _check(_lib.trepb_lq_batch_dev(device, C.byref(a), stream))
+    else:
+        _check(_lib.trepb_lq_batch(device, C.byref(a)))
+
+
+def solve_tv_lq(A, B, q, r, Q, S, R, device=0):
+    """Batched discopt.dlqr.solve_tv_lq (trep/discopt/dlqr.py:41-81) on the GPU.
+    One rollout: A [K,nX,nX], B [K,nX,nU], q [K+1,nX], r [K,nU], Q [K+1,nX,nX], S [K,nX,nU] or None,
+    R [K,nU,nU]; a batch: one more leading axis on A and B, and either the same on every cost array
+    (one cost per rollout) or none (costs shared).  Returns (K, C, P0, b0)."""
+    f = lambda x: np.ascontiguousarray(np.asarray(x, float))
+    A, B, q, r, Q, R = f(A), f(B), f(q), f(r), f(Q), f(R)
+    S = None if S is None else f(S)
+    single = A.ndim == 3
+    if single:
+        A, B = A[None], B[None]
+    Rn, K, nX = A.shape[0], A.shape[1], A.shape[2]
+    nU = B.shape[3]
+    per = Q.ndim == 4
+    Kfb = np.zeros((Rn, K, nU, nX)); Cff = np.zeros((Rn, K, nU)); P0 = np.zeros((Rn, nX, nX)); b0 = np.zeros((Rn, nX))
+    status = np.zeros(Rn, np.int32)
+    lq_raw(False, device, Rn, K, nX, nU, A, B, Q, S, R, q, r, Kfb, Cff, status, P0=P0, b0=b0, cost_per_rollout=per)
+    if np.any(status != 0):
+        raise TrepbError(0, "singular gamma in the Riccati sweep of rollout(s) %s" % np.flatnonzero(status != 0)[:8])
+    return (Kfb[0], Cff[0], P0[0], b0[0]) if single else (Kfb, Cff, P0, b0)
 
 
 def specialized_names():
