@@ -74,3 +74,71 @@ def test_interchange_with_the_reference(tmp_path):
         t, Q, p, v, u, rho = T.load_trajectory(f, target)
         assert np.array_equal(Q, x["Q"]) and np.array_equal(p, x["p"]) and np.array_equal(v, x["v"])
         assert np.array_equal(rho, x["rho"]) and u is None
+
+
+class _FakeVarint:
+    """The trajectory-packing half of the DSystem mirror needs only sizes and names."""
+    def __init__(self, d):
+        self.desc = d
+        self.nq, self.nd, self.nk, self.nu = d.nq, d.nd, d.nk, d.nu
+
+
+def _mirror(name, K):
+    from trep_b200.discopt import DSystem
+    return DSystem(_FakeVarint(G.desc(name)), 0.01 * np.arange(K + 1))
+
+
+def test_dsystem_trajectory_helpers_match_the_reference(tmp_path):
+    """build_trajectory / split_trajectory / save_state_trajectory / load_state_trajectory /
+    convert_trajectory / dproject of the mirror against the reference's DSystem
+    (trep/discopt/dsystem.py:140-226, 388-402, 460-471, 497-534)."""
+    if not os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "trep")):
+        pytest.skip("oracle/_ref not built")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_systems as R
+    trep, discopt = R.trep, R.discopt
+    K = 9
+    t = 0.01 * np.arange(K + 1)
+    rng = np.random.default_rng(3)
+    refs, mirrors = {}, {}
+    for name in ("puppet", "pend_on_cart1", "pend_on_cart2"):
+        system, mvi = R.make_mvi(name)
+        refs[name] = discopt.DSystem(mvi, t)
+        mirrors[name] = _mirror(name, K)
+    ref, mir = refs["puppet"], mirrors["puppet"]
+    d = G.desc("puppet")
+    x = _traj(d, K + 1, rng)
+    Xr, Ur = ref.build_trajectory(x["Q"], x["p"], x["v"], None, x["rho"])
+    Xm, Um = mir.build_trajectory(x["Q"], x["p"], x["v"], None, x["rho"])
+    assert np.array_equal(Xr, Xm) and np.array_equal(Ur, Um)
+    for a, b in zip(ref.split_trajectory(Xr, Ur), mir.split_trajectory(Xm, Um)):
+        assert np.array_equal(a, b)
+    with pytest.raises(ValueError):
+        mir.build_trajectory(Q=x["Q"][:-1])
+    # files: written by the mirror, read by the reference, and back
+    f = str(tmp_path / "state.mat")
+    mir.save_state_trajectory(f, Xm, Um)
+    X2, U2 = ref.load_state_trajectory(f)
+    assert np.array_equal(X2, Xr) and np.array_equal(U2, Ur)
+    ref.save_state_trajectory(f, Xr, Ur)
+    X3, U3 = mir.load_state_trajectory(f)
+    assert np.array_equal(X3, Xr) and np.array_equal(U3, Ur) and np.allclose(mir.time, t)
+    # convert_trajectory between systems that share some names
+    a, b = "pend_on_cart2", "pend_on_cart1"
+    da = G.desc(a)
+    xa = _traj(da, K + 1, rng)
+    Xa, Ua = refs[a].build_trajectory(xa["Q"], xa["p"], None, xa["u"], None)
+    # (the reference's own convert_trajectory indexes with dict views, Python-2 only, so the expectation
+    # is written out: both systems share x, theta and the input x-force; theta-force has no counterpart)
+    got = mirrors[b].convert_trajectory(mirrors[a], Xa, Ua)
+    assert np.array_equal(got.X, Xa) and got.U.shape == (K, 1) and np.array_equal(got.U[:, 0], Ua[:, 0])
+    back = mirrors[a].convert_trajectory(mirrors[b], got.X, got.U)
+    assert np.array_equal(back.X, Xa) and np.array_equal(back.U[:, 0], Ua[:, 0]) and not back.U[:, 1].any()
+    # dproject: one trajectory against the reference, and a batch against the single-trajectory results
+    nX, nU = ref.nX, ref.nU
+    A = rng.normal(0, 0.2, (3, K, nX, nX)); B = rng.normal(0, 0.2, (3, K, nX, nU))
+    Kf = rng.normal(0, 0.1, (3, K, nU, nX)); bdX = rng.normal(size=(3, K + 1, nX)); bdU = rng.normal(size=(3, K, nU))
+    got = mir.dproject(A, B, bdX, bdU, Kf)
+    for i in range(3):
+        want = ref.dproject(A[i], B[i], bdX[i], bdU[i], Kf[i])
+        assert np.allclose(got.dX[i], want.dX, rtol=1e-12, atol=1e-12) and np.allclose(got.dU[i], want.dU, rtol=1e-12, atol=1e-12)

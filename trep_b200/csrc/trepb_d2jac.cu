@@ -29,7 +29,10 @@ struct TileSink {
     }
 };
 
-__global__ void __launch_bounds__(128)
+#ifndef TREPB_D2JAC_MINB
+#define TREPB_D2JAC_MINB 1
+#endif
+__global__ void __launch_bounds__(128, TREPB_D2JAC_MINB)
 d2jac_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<Dual> wsp, const D2Params p,
              double* __restrict__ G, const JacLayout jl, long b0, long nb) {
     extern __shared__ double smem_[];

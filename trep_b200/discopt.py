@@ -89,6 +89,89 @@ class DSystem:
         U = np.asarray(U)
         return U[..., :self._nu], U[..., self._nu:]
 
+    def build_trajectory(self, Q=None, p=None, v=None, u=None, rho=None):
+        """(X, U) from component trajectories (dsystem.py:140-183); one trajectory ([K+1,.] / [K,.]) or
+        a batch with a leading axis.  Unspecified components are zero; lengths are checked against the
+        time base like the reference does."""
+        K1 = len(self._time)
+        lead = ()
+        for name, val, n in (("Q", Q, K1), ("p", p, K1), ("v", v, K1), ("u", u, K1 - 1), ("rho", rho, K1 - 1)):
+            if val is not None:
+                a = np.asarray(val)
+                if a.shape[-2] != n:
+                    raise ValueError("Invalid length for %s (expected %d)" % (name, n))
+                lead = a.shape[:-2]
+        X = np.zeros(lead + (K1, self._nX))
+        U = np.zeros(lead + (K1 - 1, self._nU))
+        if Q is not None: X[..., :self._nQ] = Q
+        if p is not None: X[..., self._nQ:self._nQ + self._np] = p
+        if v is not None: X[..., self._nQ + self._np:] = v
+        if u is not None: U[..., :self._nu] = u
+        if rho is not None: U[..., self._nu:] = rho
+        return self.trajectory_return(X, U)
+
+    def split_trajectory(self, X=None, U=None):
+        """(Q, p, v, u, rho) of a state / input trajectory (dsystem.py:207-226)."""
+        Q = p = v = u = rho = None
+        if X is not None:
+            Q, p, v = self.split_state(X)
+        if U is not None:
+            u, rho = self.split_input(U)
+        return Q, p, v, u, rho
+
+    def save_state_trajectory(self, filename, X=None, U=None):
+        """dsystem.py:388-393: the reference's MATLAB trajectory file (batches get a leading axis)."""
+        from . import trajectory
+        Q, p, v, u, rho = self.split_trajectory(X, U)
+        trajectory.save_trajectory(filename, self.varint.desc, self._time, Q, p, v, u, rho)
+
+    def load_state_trajectory(self, filename):
+        """dsystem.py:396-402: sets the time base from the file and returns (X, U)."""
+        from . import trajectory
+        t, Q, p, v, u, rho = trajectory.load_trajectory(filename, self.varint.desc)
+        self._time = np.array(t, dtype=np.float64).squeeze()
+        return self.build_trajectory(Q, p, v, u, rho)
+
+    def convert_trajectory(self, dsys_a, X, U):
+        """Map a trajectory of ``dsys_a`` onto this system by matching config / input names
+        (dsystem.py:497-534); components without a counterpart stay zero."""
+        a, b = dsys_a.varint.desc, self.varint.desc
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        qa, pa, va, ua, ra = dsys_a.split_trajectory(X, U)
+        nX = np.zeros(X.shape[:-1] + (self._nX,))
+        nU = np.zeros(U.shape[:-1] + (self._nU,))
+        qb, pb, vb = nX[..., :self._nQ], nX[..., self._nQ:self._nQ + self._np], nX[..., self._nQ + self._np:]
+        ub, rb = nU[..., :self._nu], nU[..., self._nu:]
+
+        def copy(dst, src, names_b, names_a):
+            for i, n in enumerate(names_b):
+                if n in names_a:
+                    dst[..., i] = src[..., names_a.index(n)]
+
+        ca, cb = list(a.config_names), list(b.config_names)
+        copy(qb, qa, cb, ca)
+        copy(pb, pa, cb[:b.nd], ca[:a.nd])
+        copy(vb, va, cb[b.nd:], ca[a.nd:])
+        copy(rb, ra, cb[b.nd:], ca[a.nd:])
+        copy(ub, ua, list(b.input_names), list(a.input_names))
+        return self.trajectory_return(nX, nU)
+
+    tangent_trajectory_return = namedtuple("tangent_trajectory", "dX dU")
+
+    def dproject(self, A, B, bdX, bdU, K):
+        """Projection into the tangent trajectory space about a linearization (dsystem.py:460-471):
+        dX[0] = bdX[0]; dU[k] = bdU[k] - K[k](dX[k] - bdX[k]); dX[k+1] = A[k] dX[k] + B[k] dU[k].
+        One trajectory or a batch with a leading axis on every argument (a sequential recursion of
+        matrix-vector products per rollout; evaluated on the host, vectorised over the batch)."""
+        A, B, bdX, bdU, K = (np.asarray(x, float) for x in (A, B, bdX, bdU, K))
+        dX, dU = np.zeros(bdX.shape), np.zeros(bdU.shape)
+        dX[..., 0, :] = bdX[..., 0, :]
+        for k in range(bdX.shape[-2] - 1):
+            dU[..., k, :] = bdU[..., k, :] - np.einsum("...ij,...j->...i", K[..., k, :, :], dX[..., k, :] - bdX[..., k, :])
+            dX[..., k + 1, :] = (np.einsum("...ij,...j->...i", A[..., k, :, :], dX[..., k, :])
+                                 + np.einsum("...ij,...j->...i", B[..., k, :, :], dU[..., k, :]))
+        return self.tangent_trajectory_return(dX, dU)
+
     # ---- the hot path ----------------------------------------------------------------------------------
     def linearize(self, X, U, t1, t2, X_hint=None, dist=None, compute=None):
         """A[i] = fdx, B[i] = fdu of instance i: DSystem.set(X[i], U[i], k, xk_hint=X_hint[i]) +
