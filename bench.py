@@ -383,8 +383,8 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         lib.synchronize(device)
         ms.append(s.last_kernel_ms())
     t = float(ms[-1])
-    d2_flops = 30.7e6      # fp64 flops executed per evaluation, ncu counters (profiles/r01f_d2_launches.csv)
-    d2_dram = 21.0e6       # DRAM bytes per evaluation, ncu (same file): the dual workspace of pass A
+    d2_flops = 26.3e6      # fp64 flops executed per evaluation, ncu counters (profiles/r01f_d2_launches.csv)
+    d2_dram = 24.1e6       # DRAM bytes per evaluation, ncu (same file, all 30 tensors written): mostly the dual workspace of pass A
     out.append({"metric": "second-derivative evaluations/s (W5: marionette, 3240 parameter pairs, z-contracted fdxdx/fdxdu/fdudu)",
                 "value": Bd / t * 1e3, "unit": "evaluations/s", "batch": Bd, "ms": t,
                 "scheme": "pass A: one dual-number evaluation of the Jacobian tables per (instance, parameter), 80 per instance; "
