@@ -30,7 +30,7 @@ struct TileSink {
 };
 
 #ifndef TREPB_D2JAC_MINB
-#define TREPB_D2JAC_MINB 1
+#define TREPB_D2JAC_MINB 4   // measured on the marionette (B200): 4 CTAs per SM at 128 registers (some spills) 40.8 ms per 4096 instances, 3 at 168: 43.3, 5 at 96: 42.2, 2 at 232: 49.0
 #endif
 __global__ void __launch_bounds__(128, TREPB_D2JAC_MINB)
 d2jac_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<Dual> wsp, const D2Params p,
