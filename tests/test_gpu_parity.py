@@ -313,6 +313,28 @@ def test_puppet_second_derivative_schemes_agree_on_a_ragged_batch(lib):
     assert np.max(np.abs(got - want)) <= 1e-10 * max(1.0, np.max(np.abs(want)))
 
 
+def test_puppet_second_derivatives_across_batch_chunks(lib):
+    """The per-parameter scheme processes a large batch in chunks (its table records are bounded to a
+    few GB): replicas of the same instances spread over more than one chunk give identical results."""
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    rng = np.random.default_rng(9)
+    base = 5
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, base)
+    reps = 400                                   # 2000 instances: more than one 4 GB chunk of records
+    til = lambda a: np.tile(a, (reps,) + (1,) * (a.ndim - 1))
+    q1, p1, k2, lam = til(g["roll_q"][idx]), til(g["roll_p"][idx]), til(g["roll_k2"][idx]), til(g["roll_lambda"][idx - 1])
+    z = til(rng.normal(0, 1, (base, d.nX)))
+    s = lib.System(d)
+    out = s.deriv2(q1, p1, None, k2, t1=0.0, dt=0.01, lambda_guess=lam, z=z, tensors=False)
+    assert np.all(out["status"] == 0)
+    for n in ("fdxdx", "fdxdu", "fdudu"):
+        a = out[n].reshape((reps, base) + out[n].shape[1:])
+        assert np.array_equal(a, np.broadcast_to(a[:1], a.shape)), n
+    small = s.deriv2(q1[:base], p1[:base], None, k2[:base], t1=0.0, dt=0.01, lambda_guess=lam[:base], z=z[:base], tensors=False)
+    assert np.array_equal(small["fdxdx"], out["fdxdx"][:base])
+
+
 def test_second_derivatives_by_finite_differences_where_the_reference_has_none(lib):
     """dual_pendulums: the reference cannot run _calc_deriv2 here (LinearSpring has no C V_dqdqdq,
     potentials/linearspring.c); the tensors are checked against central differences of this
