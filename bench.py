@@ -383,8 +383,16 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         lib.synchronize(device)
         ms.append(s.last_kernel_ms())
     t = float(ms[-1])
-    d2_flops = 26.3e6      # fp64 flops executed per evaluation, ncu counters (profiles/r01f_d2_launches.csv)
-    d2_dram = 24.1e6       # DRAM bytes per evaluation, ncu (same file, all 30 tensors written): mostly the dual workspace of pass A
+    # fp64 flops executed and DRAM bytes moved per evaluation: ncu counters (profiles/r01f_d2_launches.csv via
+    # profiles/flops.json; DRAM measured with all 30 tensors written, mostly the dual workspace of pass A)
+    d2_flops, d2_dram = 26.3e6, 24.1e6
+    try:
+        with open(os.path.join(ROOT, "profiles", "flops.json")) as fh:
+            fj_ = json.load(fh)
+        d2_flops = float(fj_.get("puppet_d2_flops_per_evaluation", d2_flops))
+        d2_dram = float(fj_.get("puppet_d2_dram_bytes_per_evaluation", d2_dram))
+    except OSError:
+        pass
     out.append({"metric": "second-derivative evaluations/s (W5: marionette, 3240 parameter pairs, z-contracted fdxdx/fdxdu/fdudu)",
                 "value": Bd / t * 1e3, "unit": "evaluations/s", "batch": Bd, "ms": t,
                 "scheme": "pass A: one dual-number evaluation of the Jacobian tables per (instance, parameter), 80 per instance; "
