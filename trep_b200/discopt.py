@@ -172,6 +172,85 @@ class DSystem:
                                  + np.einsum("...ij,...j->...i", B[..., k, :, :], dU[..., k, :]))
         return self.tangent_trajectory_return(dX, dU)
 
+    # ---- f and the finite-difference self-checks (dsystem.py:253-281, 536-701) -------------------------
+    error_return = namedtuple("derivative_error", "error exact_norm approx_norm")
+
+    def f(self, X, U, k):
+        """X[k+1] = f(X, U, k) for a batch of states / inputs at the time step k (DSystem.set + f,
+        dsystem.py:229-281): X [n,nX], U [n,nU] -> [n,nX] = [q2; p2; (q2_kin - q1_kin)/dt]."""
+        X, U = np.atleast_2d(np.asarray(X, float)), np.atleast_2d(np.asarray(U, float))
+        t1, t2 = float(self._time[k]), float(self._time[k + 1])
+        q1, p1, _ = self.split_state(X)
+        u1, rho = self.split_input(U)
+        out = self.varint.sys.step(q1, p1, t1, t2 - t1, nsteps=1, u1=u1[:, None, :] if self._nu else None,
+                                   k2=rho[:, None, :] if self._nv else None, tolerance=self.varint.tolerance)
+        bad = np.flatnonzero(out["status"] != 0)
+        if bad.size:
+            raise ConvergenceError("%d of %d steps failed" % (bad.size, X.shape[0]), out["status"])
+        v2 = (out["q2"][:, self._np:] - q1[:, self._np:]) / (t2 - t1)
+        return self.build_state(out["q2"], out["p2"], v2)
+
+    def _lin_at(self, X, U, k):
+        n = X.shape[0]
+        return self.linearize(X, U, np.full(n, self._time[k]), np.full(n, self._time[k + 1]))
+
+    def _err(self, exact, approx):
+        return self.error_return(float(np.linalg.norm(exact - approx)), float(np.linalg.norm(exact)),
+                                 float(np.linalg.norm(approx)))
+
+    def _perturbed(self, v, delta):
+        """[2 n, n]: v + delta e_i (rows 0..n-1) and v - delta e_i (rows n..2n-1)."""
+        n = v.shape[0]
+        return np.concatenate([v[None] + delta * np.eye(n), v[None] - delta * np.eye(n)])
+
+    def check_fdx(self, xk, uk, k, delta=1e-5):
+        """f_dx against central differences of f (dsystem.py:536-562); the 2 nX perturbed states are
+        one batch."""
+        xk, uk = np.asarray(xk, float), np.asarray(uk, float)
+        exact = self._lin_at(xk[None], uk[None], k).A[0]
+        F = self.f(self._perturbed(xk, delta), np.tile(uk, (2 * self._nX, 1)), k)
+        approx = ((F[:self._nX] - F[self._nX:]) / (2 * delta)).T
+        return self._err(exact, approx)
+
+    def check_fdu(self, xk, uk, k, delta=1e-5):
+        """f_du against central differences of f (dsystem.py:565-591)."""
+        xk, uk = np.asarray(xk, float), np.asarray(uk, float)
+        exact = self._lin_at(xk[None], uk[None], k).B[0]
+        F = self.f(np.tile(xk, (2 * self._nU, 1)), self._perturbed(uk, delta), k)
+        approx = ((F[:self._nU] - F[self._nU:]) / (2 * delta)).T
+        return self._err(exact, approx)
+
+    def _second(self, xk, uk, k):
+        """fdxdx(e_i), fdxdu(e_i), fdudu(e_i) for every unit vector e_i of the state space: one batch of nX
+        instances of the z-contracted second-derivative kernel."""
+        nX = self._nX
+        t1, t2 = np.full(nX, self._time[k]), np.full(nX, self._time[k + 1])
+        return self.second_derivatives(np.tile(xk, (nX, 1)), np.tile(uk, (nX, 1)), np.eye(nX), t1, t2)
+
+    def check_fdxdx(self, xk, uk, k, delta=1e-5):
+        """f_dxdx against central differences of f_dx (dsystem.py:594-625)."""
+        xk, uk = np.asarray(xk, float), np.asarray(uk, float)
+        exact = self._second(xk, uk, k)[0]                                   # [out i][a][b]
+        A = self._lin_at(self._perturbed(xk, delta), np.tile(uk, (2 * self._nX, 1)), k).A
+        approx = np.transpose((A[:self._nX] - A[self._nX:]) / (2 * delta), (1, 2, 0))   # [i][a][b = perturbed]
+        return self._err(exact, approx)
+
+    def check_fdxdu(self, xk, uk, k, delta=1e-5):
+        """f_dxdu against central differences of f_dx (dsystem.py:628-660)."""
+        xk, uk = np.asarray(xk, float), np.asarray(uk, float)
+        exact = self._second(xk, uk, k)[1]                                   # [i][a][c]
+        A = self._lin_at(np.tile(xk, (2 * self._nU, 1)), self._perturbed(uk, delta), k).A
+        approx = np.transpose((A[:self._nU] - A[self._nU:]) / (2 * delta), (1, 2, 0))
+        return self._err(exact, approx)
+
+    def check_fdudu(self, xk, uk, k, delta=1e-5):
+        """f_dudu against central differences of f_du (dsystem.py:663-701)."""
+        xk, uk = np.asarray(xk, float), np.asarray(uk, float)
+        exact = self._second(xk, uk, k)[2]                                   # [i][c][d]
+        B = self._lin_at(np.tile(xk, (2 * self._nU, 1)), self._perturbed(uk, delta), k).B
+        approx = np.transpose((B[:self._nU] - B[self._nU:]) / (2 * delta), (1, 2, 0))
+        return self._err(exact, approx)
+
     # ---- the hot path ----------------------------------------------------------------------------------
     def linearize(self, X, U, t1, t2, X_hint=None, dist=None, compute=None):
         """A[i] = fdx, B[i] = fdu of instance i: DSystem.set(X[i], U[i], k, xk_hint=X_hint[i]) +
