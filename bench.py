@@ -407,6 +407,85 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     for b in (dq, dp, dk, dl, q2, p2, l2, it, st, A, Bm, z, xx, xu, uu):
         b.free()
     s.close()
+    out += extra_kinds(lib, systems, device, hbm_peak, fp64_peak)
+    return out
+
+
+def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
+    """The rows widened beyond BASELINE.json's configs, measured like the others:
+    linearizations/s of the table-driven thread kernels on systems with PointOnPlane constraints, wrenches
+    and a spline spring, and the affine LQ sweep."""
+    out = []
+    rng = np.random.default_rng(2)
+    up = lambda a: lib.DeviceBuffer(device, a.shape, a.dtype).upload(np.ascontiguousarray(a))
+    for name, B in (("pccd", 1 << 17), ("wrench_arm", 1 << 20), ("spline_pendulum", 1 << 20)):
+        d = systems.named_desc(name)
+        s = lib.System(d, device=device)
+        nq, nd, nu, nc = d.nq, d.nd, d.nu, d.nc
+        lam = None
+        if name == "pccd":
+            g = np.load(os.path.join(ROOT, "tests", "golden", "pccd.npz"))
+            idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+            q1 = g["roll_q"][idx] + rng.normal(0, 0.01, (B, nq)); p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, nd))
+            lam = up(g["roll_lambda"][idx - 1])
+        elif name == "wrench_arm":
+            q1 = np.stack([rng.uniform(-np.pi, np.pi, B), rng.uniform(-1.2, 1.2, B), rng.uniform(-0.3, 0.5, B)], axis=1)
+            p1 = rng.normal(0, 1, (B, nd))
+        else:
+            q1 = np.stack([rng.uniform(-2.4, 2.2, B), rng.uniform(-np.pi, np.pi, B)], axis=1)
+            p1 = rng.normal(0, 1, (B, nd))
+        dq, dp = up(q1), up(p1)
+        du = up(rng.uniform(-2, 2, (B, nu))) if nu else None
+        q2 = lib.DeviceBuffer(device, (B, nq)); p2 = lib.DeviceBuffer(device, (B, nd))
+        l2 = lib.DeviceBuffer(device, (B, nc)) if nc else None
+        it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+        A = lib.DeviceBuffer(device, (B, d.nX, d.nX)); Bm = lib.DeviceBuffer(device, (B, d.nX, d.nU)) if d.nU else None
+        ms = []
+        for rep in range(4):
+            s.linearize_raw(True, B, dq, dp, du, None, st, t1_scalar=0.0, dt_scalar=DT, q2=q2, p2=p2, lambda1=l2, iters=it,
+                            A=A, B=Bm, lambda_guess=lam)
+            lib.synchronize(device)
+            if rep >= 1:
+                ms.append(s.last_kernel_ms())
+        t = float(np.mean(ms))
+        byt = 8 * (nq + nd + nu + nc) + 8 * (d.nX * d.nX + d.nX * d.nU) + 8 * (nq + nd + nc) + 8
+        out.append({"metric": "linearizations/s (%s: %s; solve + deriv1 -> A,B)" % (name, {
+                        "pccd": "examples/pccd.py, 7 DOF closed chain, 4 PointOnPlane constraints",
+                        "wrench_arm": "3 DOF arm with Body / Hybrid / Spatial wrenches, 5 inputs",
+                        "spline_pendulum": "2 DOF, NonlinearConfigSpring over a quintic spline"}[name]),
+                    "value": B / t * 1e3, "unit": "linearizations/s", "batch": B, "ms": t, "kernel": s.kernel_name,
+                    "newton_iters_mean": float(it.download().mean()), "ok_fraction": float((st.download() == 0).mean()),
+                    "roofline": {"bound": "hbm", "achieved": B * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": B * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt,
+                                 "note": "algorithmic bytes (inputs + A, B, q2, p2, lambda, iters, status); the table-driven "
+                                         "thread kernel keeps its per-instance workspace in HBM, so its real traffic is higher"}})
+        for b in (dq, dp, du, lam, q2, p2, l2, it, st, A, Bm):
+            if b is not None:
+                b.free()
+        s.close()
+    # affine LQ sweep (solve_tv_lq) at the marionette's size, one cost set per rollout
+    nX, nU, Rl, Kl = 80, 18, 296, 64
+    Al = up(np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (Rl, Kl, nX, nX)))
+    Bl = up(rng.normal(0, 1.0, (Rl, Kl, nX, nU)))
+    Ql = up(np.broadcast_to(np.eye(nX), (Rl, Kl + 1, nX, nX)).copy()); Rr = up(np.broadcast_to(2.0 * np.eye(nU), (Rl, Kl, nU, nU)).copy())
+    Sl = up(rng.normal(0, 0.02, (Rl, Kl, nX, nU))); ql = up(rng.normal(0, 1, (Rl, Kl + 1, nX))); rl = up(rng.normal(0, 1, (Rl, Kl, nU)))
+    Ko = lib.DeviceBuffer(device, (Rl, Kl, nU, nX)); Co = lib.DeviceBuffer(device, (Rl, Kl, nU)); lst = lib.DeviceBuffer(device, (Rl,), np.int32)
+    lib.lq_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Sl, Rr, ql, rl, Ko, Co, lst, cost_per_rollout=True)
+    lib.synchronize(device)
+    t0_ = time.perf_counter()
+    for rep in range(3):
+        lib.lq_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Sl, Rr, ql, rl, Ko, Co, lst, cost_per_rollout=True)
+    lib.synchronize(device)
+    tl = (time.perf_counter() - t0_) / 3 * 1e3
+    fl_step = 2.0 * (2 * nX ** 3 + 3 * nX * nX * nU + nU * nU * nX) + 2.0 * nU * nU * (nU / 3.0 + nX) + 2.0 * (nX * nX + 3 * nX * nU + nU * nU)
+    out.append({"metric": "Riccati steps/s (discopt.dlqr.solve_tv_lq: cross term + affine recursion, nX=%d nU=%d, %d rollouts x %d steps, one cost set per rollout)" % (nX, nU, Rl, Kl),
+                "value": Rl * Kl / tl * 1e3, "unit": "Riccati steps/s", "batch": Rl, "ms": tl,
+                "ok_fraction": float((lst.download() == 0).mean()),
+                "roofline": {"bound": "fp64", "achieved": fl_step * Rl * Kl / (tl * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                             "frac": fl_step * Rl * Kl / (tl * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": fl_step,
+                             "note": "host-timed over 3 launches; flops counted from the matrix shapes"}})
+    for b_ in (Al, Bl, Ql, Rr, Sl, ql, rl, Ko, Co, lst):
+        b_.free()
     return out
 
 

@@ -538,29 +538,37 @@ def test_extra_plugin_kinds_golden_cases(lib, name):
     """PointOnPlane constraints (pccd) and Body / Hybrid / Spatial wrenches (wrench_arm): step, every
     first-derivative array, A / B and the Newton iteration counts against the reference."""
     g = G.golden(name)
+    # the table-driven kernels, and the register-resident specialised ones where the build made them
+    flavours = [("general", lib.System(G.desc(name), specialize=False))]
     s = lib.System(G.desc(name))
-    assert not s.cooperative and not s.specialized
-    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
-                      t2=g["case_t2"], q2_guess=g["case_q2_guess"],
-                      lambda_guess=g["case_lambda_guess"], want_raw=True)
-    assert np.all(out["status"] == 0)
-    for k in ("q2", "p2", "lambda1", "A", "B"):
-        G.assert_close(out[k], g["case_" + k], "%s %s" % (name, k))
-    for k in G.RAW:
-        G.assert_close(out[k], g["case_" + k], "%s %s" % (name, k))
-    assert np.array_equal(out["iters"], g["case_iters"])
+    assert not s.cooperative
+    if s.specialized:
+        flavours.append(("spec", s))
+    for label, s in flavours:
+        out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                          t2=g["case_t2"], q2_guess=g["case_q2_guess"],
+                          lambda_guess=g["case_lambda_guess"], want_raw=True)
+        assert np.all(out["status"] == 0)
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k], g["case_" + k], "%s[%s] %s" % (name, label, k))
+        for k in G.RAW:
+            G.assert_close(out[k], g["case_" + k], "%s[%s] %s" % (name, label, k))
+        assert np.array_equal(out["iters"], g["case_iters"]), label
 
 
 @pytest.mark.parametrize("pairwise", [False, True])
 @pytest.mark.parametrize("name", G.EXTRA_D2)
 def test_extra_plugin_kinds_second_derivatives(lib, name, pairwise):
     g = G.golden(name)
-    s = lib.System(G.desc(name), d2_pairwise=pairwise)
-    out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
-                   t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
-    assert np.all(out["status"] == 0)
-    for n in s.d2_shapes(1):
-        G.assert_close(out[n], g["case_" + n], "%s[pairwise=%s] %s" % (name, pairwise, n))
+    for spec in (False, True):
+        s = lib.System(G.desc(name), d2_pairwise=pairwise, specialize=spec)
+        if spec and (not s.specialized or not pairwise):
+            continue                      # a specialised system always uses the per-pair scheme
+        out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
+                       t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
+        assert np.all(out["status"] == 0)
+        for n in s.d2_shapes(1):
+            G.assert_close(out[n], g["case_" + n], "%s[pairwise=%s spec=%s] %s" % (name, pairwise, spec, n))
 
 
 def test_pccd_rollout(lib):
@@ -633,7 +641,7 @@ def test_spline_spring_second_derivatives_by_finite_differences(lib, pairwise):
     (potentials/nonlinear_config_spring.c:53), so its second-derivative tensors cannot serve as the
     oracle for this plugin; both schemes are checked against central differences of this library's own
     first derivatives (which match the reference) instead."""
-    s = lib.System(G.desc("spline_pendulum"), d2_pairwise=pairwise)
+    s = lib.System(G.desc("spline_pendulum"), d2_pairwise=pairwise, specialize=False)
     rng = np.random.default_rng(3)
     q1 = np.array([[0.45, -0.3]]); p1 = rng.normal(0, 1, (1, 2))
     out = s.deriv2(q1, p1, t1=0.0, dt=0.01)
