@@ -36,7 +36,7 @@ def ref():
 
 
 # LinearSpring / LinearDamper, PointOnPlane, wrenches: thread-per-instance kernels only
-COOP_UNSUPPORTED = {"dual_pendulums", "pccd", "wrench_arm", "spline_pendulum"}
+COOP_UNSUPPORTED = {"dual_pendulums", "wrench_arm", "spline_pendulum"}
 
 
 def _systems(lib, name):
@@ -539,11 +539,12 @@ def test_extra_plugin_kinds_golden_cases(lib, name):
     first-derivative array, A / B and the Newton iteration counts against the reference."""
     g = G.golden(name)
     # the table-driven kernels, and the register-resident specialised ones where the build made them
-    flavours = [("general", lib.System(G.desc(name), specialize=False))]
-    s = lib.System(G.desc(name))
-    assert not s.cooperative
-    if s.specialized:
-        flavours.append(("spec", s))
+    flavours = [("general", lib.System(G.desc(name), specialize=False, cooperative=False))]
+    s = lib.System(G.desc(name))              # the library's own choice: a specialised thread kernel
+    flavours.append(("default:" + s.kernel_name, s))   # (wrench_arm, spline_pendulum) or cooperative/pccd
+    assert s.kernel_name == {"pccd": "cooperative/pccd"}.get(name, name)
+    if name not in COOP_UNSUPPORTED:          # PointOnPlane is implemented by the cooperative kernels too
+        flavours.append(("coop", lib.System(G.desc(name), specialize=False, cooperative=True)))
     for label, s in flavours:
         out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
                           t2=g["case_t2"], q2_guess=g["case_q2_guess"],
@@ -560,9 +561,14 @@ def test_extra_plugin_kinds_golden_cases(lib, name):
 @pytest.mark.parametrize("name", G.EXTRA_D2)
 def test_extra_plugin_kinds_second_derivatives(lib, name, pairwise):
     g = G.golden(name)
-    for spec in (False, True):
-        s = lib.System(G.desc(name), d2_pairwise=pairwise, specialize=spec)
-        if spec and (not s.specialized or not pairwise):
+    for spec in (False, True, "coop"):
+        if spec == "coop":
+            if name in COOP_UNSUPPORTED:
+                continue                  # the cooperative linearize kernel as producer of the factors
+            s = lib.System(G.desc(name), d2_pairwise=pairwise, specialize=False, cooperative=True)
+        else:
+            s = lib.System(G.desc(name), d2_pairwise=pairwise, specialize=spec, cooperative=False)
+        if spec is True and (not s.specialized or not pairwise):
             continue                      # a specialised system always uses the per-pair scheme
         out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
                        t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])

@@ -714,7 +714,29 @@ struct Coop {
         }
     }
 
-    // ---- constraints at the current pose (distance.c:16-100, point.c:16-46)
+    // PointOnPlane (constraints/plane.c:14-84): world normal n_w = R_l n of constraint c (l = link of the
+    // plane frame, n in link coordinates) and its derivatives d n_w / d q_j = a_j x n_w for a revolute
+    // link lj above-or-equal l,  d2 n_w / d q_i d q_j = a_up x (a_lo x n_w)
+    TREPB_HD void plane_normal(int c, double* nw) const {
+        const int nls = L.nls, l = S.pt_link()[S.con_a()[c]];
+        const double* n = S.con_n() + 3 * c;
+        TREPB_UNROLL
+        for (int k = 0; k < 3; ++k)
+            nw[k] = l < 0 ? n[k] : (w[oR + (k * 3) * nls + l] * n[0] + w[oR + (k * 3 + 1) * nls + l] * n[1] +
+                                    w[oR + (k * 3 + 2) * nls + l] * n[2]);
+    }
+    // world axis of a revolute link lj that carries the plane link l of constraint c, else zero
+    TREPB_HD bool plane_axis(int c, int lj, double* aw) const {
+        aw[0] = aw[1] = aw[2] = 0.0;
+        const int l = S.pt_link()[S.con_a()[c]];
+        if (l < 0 || lj < 0 || !((S.l_anc()[l] >> lj) & 1ull)) return false;
+        const int kind = S.l_kind()[lj], a = kind & 3, nls = L.nls;
+        if (!(kind & 4)) return false;
+        aw[0] = w[oR + a * nls + lj]; aw[1] = w[oR + (3 + a) * nls + lj]; aw[2] = w[oR + (6 + a) * nls + lj];
+        return true;
+    }
+
+    // ---- constraints at the current pose (distance.c:16-100, point.c:16-46, plane.c:14-84)
     //   want_h: hc ;  dh: 0 none, 1 -> Dh1 [nc][nd], 2 -> Dh2 [nc][nq]
     TREPB_HD void constraints(bool want_h, int dh) {
         const int lane = t.lane(), nq = NQ(), nd = ND(), nc = NC();
@@ -727,6 +749,10 @@ struct Coop {
                     const int third = S.con_third()[c];
                     const double d = third >= 0 ? w[oQ + third] : S.con_dist()[c];
                     w[L.hc + c] = dot3(v, v) - d * d;
+                } else if (S.con_kind()[c] == C_PLANE) {
+                    double nw[3];
+                    plane_normal(c, nw);
+                    w[L.hc + c] = dot3(nw, v);
                 } else {
                     w[L.hc + c] = sel3(v, S.con_third()[c]);
                 }
@@ -751,6 +777,14 @@ struct Coop {
                         val = dot3(v, dv);
                         if (third == j) val -= w[oQ + third];
                         val *= 2.0;
+                    } else if (S.con_kind()[c] == C_PLANE) {
+                        double pa[3], pb[3], v[3], nw[3], aw[3], dn[3];
+                        point(A, pa); point(B, pb);
+                        TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+                        plane_normal(c, nw);
+                        plane_axis(c, lj, aw);
+                        cross3(aw, nw, dn);
+                        val = dot3(dn, v) + dot3(nw, dv);
                     } else {
                         val = sel3(dv, S.con_third()[c]);
                     }
@@ -789,9 +823,11 @@ struct Coop {
                 TREPB_UNROLL for (int k = 0; k < 3; ++k) dst[k * m + ai] = d3[k];
             }
             t.sync();
-            const bool dist = S.con_kind()[c] == C_DISTANCE;
+            const bool dist = S.con_kind()[c] == C_DISTANCE, plane = S.con_kind()[c] == C_PLANE;
             const int third = S.con_third()[c];
             const double lam = w[L.lam + c];
+            double nw[3] = {0.0, 0.0, 0.0};
+            if (plane) plane_normal(c, nw);
             double v[3];
             {
                 double pa[3], pb[3];
@@ -828,6 +864,18 @@ struct Coop {
                     val = dot3(di, dj) + dot3(v, ddv);
                     if (third == i && third == j) val -= 1.0;
                     val *= 2.0 * lam;
+                } else if (plane) {
+                    double di[3], dj[3], axi[3], axj[3], dni[3], dnj[3], ddn[3] = {0.0, 0.0, 0.0};
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { di[k] = DA[k * m + ai] - DB[k * m + ai]; dj[k] = DA[k * m + bj] - DB[k * m + bj]; }
+                    const bool ri = plane_axis(c, li, axi), rj = plane_axis(c, lj, axj);
+                    cross3(axi, nw, dni);
+                    cross3(axj, nw, dnj);
+                    if (ri && rj) {
+                        // the upper joint's axis crosses the lower joint's derivative of the normal
+                        const bool i_up = ((S.l_anc()[lj] >> li) & 1ull) != 0;
+                        if (i_up) cross3(axi, dnj, ddn); else cross3(axj, dni, ddn);
+                    }
+                    val = lam * (dot3(ddn, v) + dot3(dni, dj) + dot3(dnj, di) + dot3(nw, ddv));
                 } else {
                     val = lam * sel3(ddv, third);
                 }

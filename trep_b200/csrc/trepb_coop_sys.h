@@ -51,7 +51,8 @@ struct CoopSys {
     //   constraints   con_kind, con_a, con_b (points), con_third, con_dist, con_tol, con_dep (config mask),
     //                 cd_off [nc+1] / cd_cfg: the configs each constraint depends on, ascending (the
     //                 first cd_nd[c] of them are dynamic); dd_row [nd] / dd_col [nq]: compact row / column
-    //                 of a config in the block of sum_c lambda_c d2h_c (-1: no constraint depends on it)
+    //                 of a config in the block of sum_c lambda_c d2h_c (-1: no constraint depends on it);
+    //                 con_n [nc][3]: PointOnPlane normal in the coordinates of the plane frame's link
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -87,6 +88,8 @@ struct CoopSys {
     int o_l_next;
     int o_sl_off;
     int o_sl_head;
+    int o_con_n;
+    TREPB_HD const double* con_n() const { return (const double*)(base + o_con_n); }
     TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
     TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
     TREPB_HD const int32_t* l_kind() const { return (const int32_t*)(base + o_l_kind); }
@@ -173,6 +176,7 @@ struct CoopPack {
         s.o_l_next = (int)off[k++];
         s.o_sl_off = (int)off[k++];
         s.o_sl_head = (int)off[k++];
+        s.o_con_n = (int)off[k++];
         return s;
     }
 };
@@ -233,8 +237,6 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     for (int i = 0; i < d->n_forces; ++i)
         if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
         else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }
-    for (int i = 0; i < nc; ++i)
-        if (d->con_kind[i] == TREPB_CON_PLANE) { P.why = "PointOnPlane constraint"; return P; }
 
     // ---- frames -> links
     std::vector<int> flink(nf, -1);      // frame -> frame index of the link it belongs to (-1: world)
@@ -367,6 +369,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     std::vector<int32_t> con_kind(nc > 0 ? nc : 1), con_a(nc > 0 ? nc : 1), con_b(nc > 0 ? nc : 1), con_third(nc > 0 ? nc : 1);
     std::vector<double> con_dist(nc > 0 ? nc : 1), con_tol(nc > 0 ? nc : 1);
     std::vector<uint64_t> con_dep(nc > 0 ? nc : 1, 0);
+    std::vector<double> con_n(nc > 0 ? 3 * nc : 3, 0.0);
     for (int c = 0; c < nc; ++c) {
         const int32_t* ii = d->con_i + 4 * c;
         con_kind[c] = d->con_kind[c];
@@ -375,6 +378,14 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
         con_third[c] = ii[2];
         con_dist[c] = d->con_d[4 * c];
         con_tol[c] = d->con_d[4 * c + 1];
+        if (con_kind[c] == TREPB_CON_PLANE) {
+            // normal fixed in the plane frame -> coordinates of the link the frame hangs on
+            const double n[3] = {d->con_d[4 * c], d->con_d[4 * c + 2], d->con_d[4 * c + 3]};
+            const Se3& x = fx[ii[0]];
+            for (int r = 0; r < 3; ++r) con_n[3 * c + r] = x.R[r * 3] * n[0] + x.R[r * 3 + 1] * n[1] + x.R[r * 3 + 2] * n[2];
+            con_third[c] = -1;
+            con_dist[c] = 0.0;
+        }
         uint64_t m = 0;
         for (int e = 0; e < 2; ++e) {
             const int l = pt_link[e == 0 ? con_a[c] : con_b[c]];
@@ -467,6 +478,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(cd_off.data(), 4 * (nc + 1)); put(cd_cfg.data(), 4 * cd_cfg.size()); put(cd_nd.data(), 4 * nc);
     put(dd_row.data(), 4 * nd); put(dd_col.data(), 4 * nq);
     put(l_next.data(), 4 * nl); put(sl_off.data(), 4 * sl_off.size()); put(sl_head.data(), 4 * sl_head.size());
+    put(con_n.data(), 8 * 3 * (size_t)nc);
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;
