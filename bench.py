@@ -247,9 +247,18 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         if rep >= 1:
             ms.append(s.last_kernel_ms())
     t = float(np.mean(ms))
-    out.append({"metric": "DEL steps/s (W4: dual pendulums Monte-Carlo sweep, 2^22 instances x 100 steps)", "value": B * 100 / t * 1e3,
-                "unit": "DEL steps/s", "batch": B, "ms": t, "newton_iters_per_step": float(it.download().mean()) / 100,
-                "ok_fraction": float((st.download() == 0).mean())})
+    w4 = {"metric": "DEL steps/s (W4: dual pendulums Monte-Carlo sweep, 2^22 instances x 100 steps)", "value": B * 100 / t * 1e3,
+          "unit": "DEL steps/s", "batch": B, "ms": t, "newton_iters_per_step": float(it.download().mean()) / 100,
+          "ok_fraction": float((st.download() == 0).mean())}
+    try:
+        with open(os.path.join(ROOT, "profiles", "flops.json")) as fh:
+            fl4 = float(json.load(fh)["dual_pendulums_step_flops_per_del_step"])
+        ach = fl4 * B * 100 / (t * 1e-3) / 1e12
+        w4["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                          "flops_per_unit": fl4, "note": "on-chip: 32 B in + 32 B out per rollout of 100 steps"}
+    except (OSError, KeyError):
+        pass
+    out.append(w4)
     for b in (dq, dp, q2, p2, it, st):
         b.free()
     s.close()

@@ -23,6 +23,18 @@ if mode in ("step", "all"):
     lib.synchronize(0)
     print("step: B=%d nsteps=%d ms=%.3f iters/step=%.3f" % (B, nsteps, s.last_kernel_ms(), it.download().mean() / nsteps))
 
+if mode in ("dual", "all"):
+    B, nsteps = 1 << 20, 50
+    d = systems.named_desc("dual_pendulums"); s = lib.System(d)
+    dq = up(rng.uniform(-np.pi, np.pi, (B, 2))); dp = lib.DeviceBuffer(0, (B, 2))
+    s.calc_p2_raw(True, B, 0.01, dq, dq, dp)
+    q2 = lib.DeviceBuffer(0, (B, 2)); p2 = lib.DeviceBuffer(0, (B, 2))
+    it = lib.DeviceBuffer(0, (B,), np.int32); st = lib.DeviceBuffer(0, (B,), np.int32)
+    for _ in range(2):
+        s.step_raw(True, B, nsteps, 0.01, 0.01, dq, dp, None, None, None, None, q2, p2, None, it, st)
+    lib.synchronize(0)
+    print("dual: B=%d nsteps=%d ms=%.3f iters/step=%.3f" % (B, nsteps, s.last_kernel_ms(), it.download().mean() / nsteps))
+
 if mode in ("lin", "all"):
     B = 1 << 22
     d = systems.named_desc("pend_on_cart1"); s = lib.System(d)
