@@ -1181,7 +1181,7 @@ template <class Sys, class Ws>
 TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
     using Real = typename Ws::Real;
     set_point(sys, ws, 0, dt);
-    pass1(sys, ws, true, sys.pairs_on());
+    pass1(sys, ws, true, sys.pairs_mid());   // world poses at the midpoint only for springs / dampers / wrenches
     pass2(sys, ws, order);
     add_potentials(sys, ws, order);
     forces_eval(sys, ws, order);
