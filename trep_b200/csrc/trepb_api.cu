@@ -96,6 +96,7 @@ struct trepb_system {
     WsStridedT<Dual> wsl_du;
     int ws_du_elems = 0;
     int bps_d2jac = 1;
+    bool d2jac_ok = false;       // pass B's per-CTA working set fits in shared memory for this shape
     DevBuf ws_du, d2g;
     // staging for the host-pointer entry points
     DevBuf hb[72];
@@ -209,6 +210,10 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         int b = 0;
         CUS(d2jac_occupancy(s->block, d2jac_smem(s->blob_bytes, s->block, ps.nd, ps.nk), &b, nullptr));
         s->bps_d2jac = b > 0 ? b : 1;
+        AuxLayout al;
+        al.set(ps.nd, ps.nc);
+        const int nx = 2 * (ps.nd + ps.nk) + ps.nu;
+        s->d2jac_ok = nx <= 1024 && d2solve_smem_needed(ps.nd, ps.nk, ps.nc, nx, al.size) <= (size_t)prop.sharedMemPerBlockOptin;
     }
     if (s->ks->specialized) {
         const int nq = ps.nd + ps.nk, nX = 2 * nq, nU = ps.nu + ps.nk;
@@ -559,7 +564,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         if (p.zuu && nU) CU(cudaMemsetAsync(p.zuu, 0, (size_t)B * nU * nU * sizeof(double), stream));
         if (nU == 0) { p.zxu = nullptr; p.zuu = nullptr; }
     }
-    if (!s->ks->specialized && !(s->flags & TREPB_FLAG_D2_PAIRWISE)) {
+    if (!s->ks->specialized && !(s->flags & TREPB_FLAG_D2_PAIRWISE) && s->d2jac_ok) {
         // pass A: one dual evaluation of the Jacobian tables per (instance, parameter);
         // pass B: contraction + solves per pair (trepb_d2jac.cuh).  The batch is processed in
         // chunks so that the table records stay within a few GB.

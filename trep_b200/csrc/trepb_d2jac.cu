@@ -429,6 +429,10 @@ cudaError_t d2jac_run(const LaunchCfg& c, const WsStridedT<Dual>& w, const D2Par
     d2jac_kernel<<<c.grid, c.block, c.smem, c.stream>>>(*c.sys, c.dblob, c.blob_bytes, w, p, G, jl, b0, nb);
     return cudaGetLastError();
 }
+size_t d2solve_smem_needed(int nd, int nk, int nc, int nx, int aux_size) {
+    if (nd == 22 && nc == 6) return D2Ct<22, 6>::smem(nd + nk);
+    return d2solve_smem(nd, nk, nc, aux_size, ((nx + 31) / 32) * 32);
+}
 cudaError_t d2solve_run(cudaStream_t stream, const D2Params& p, const double* G, const JacLayout& jl, int nd, int nk,
                         int nu, int nc, long b0, long nb) {
     // shapes with a compile-time-size pass B (the marionette of BASELINE.json's config 5)

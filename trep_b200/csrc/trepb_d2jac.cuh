@@ -366,6 +366,8 @@ size_t d2jac_smem(int blob_bytes, int block, int nd, int nk);
 cudaError_t d2jac_run(const LaunchCfg& c, const WsStridedT<Dual>& w, const D2Params& p, double* G, const JacLayout& jl,
                       long b0, long nb);
 size_t d2solve_smem(int nd, int nk, int nc, int aux_size, int T);
+// shared memory pass B needs for this shape (compile-time-size flavour where one exists)
+size_t d2solve_smem_needed(int nd, int nk, int nc, int nx, int aux_size);
 cudaError_t d2solve_run(cudaStream_t stream, const D2Params& p, const double* G, const JacLayout& jl, int nd, int nk,
                         int nu, int nc, long b0, long nb);
 #endif
