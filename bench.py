@@ -472,6 +472,30 @@ def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
             if b is not None:
                 b.free()
         s.close()
+    # W1 (BASELINE config 0, examples/pendulum.py): N-link pendulum, a large batch and the latency of ONE rollout
+    for links, B, nsteps in ((1, 1 << 20, 1000), (5, 1 << 18, 200), (1, 1, 1000), (5, 1, 1000)):
+        d = systems.named_desc("pendulum%d" % links)
+        s = lib.System(d, device=device)
+        q0 = np.zeros((B, links)); q0[:, 0] = rng.uniform(-np.pi, np.pi, B) if B > 1 else np.pi / 4
+        dq = up(q0); dp = lib.DeviceBuffer(device, (B, links))
+        s.calc_p2_raw(True, B, DT, dq, dq, dp)
+        q2 = lib.DeviceBuffer(device, (B, links)); p2 = lib.DeviceBuffer(device, (B, links))
+        it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+        ms = []
+        for rep in range(3):
+            s.step_raw(True, B, nsteps, DT, DT, dq, dp, None, None, None, None, q2, p2, None, it, st)
+            lib.synchronize(device)
+            if rep >= 1:
+                ms.append(s.last_kernel_ms())
+        t = float(np.mean(ms))
+        out.append({"metric": "DEL steps/s (W1: %d-link pendulum of examples/pendulum.py, %s)" % (
+                        links, "2^%d rollouts x %d steps" % (int(np.log2(B)), nsteps) if B > 1 else "ONE rollout of %d steps: latency" % nsteps),
+                    "value": B * nsteps / t * 1e3, "unit": "DEL steps/s", "batch": B, "ms": t, "kernel": s.kernel_name,
+                    "us_per_step": t * 1e3 / nsteps if B == 1 else None,
+                    "newton_iters_per_step": float(it.download().mean()) / nsteps, "ok_fraction": float((st.download() == 0).mean())})
+        for b in (dq, dp, q2, p2, it, st):
+            b.free()
+        s.close()
     # affine LQ sweep (solve_tv_lq) at the marionette's size, one cost set per rollout
     nX, nU, Rl, Kl = 80, 18, 296, 64
     Al = up(np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (Rl, Kl, nX, nX)))
