@@ -672,3 +672,27 @@ def test_spline_pendulum_rollout(lib):
     ns = nsteps // sample
     G.assert_close(out["traj_q"][0, :ns], g["roll_q"][1:1 + ns], "spline_pendulum traj q", rtol=1e-7)
     G.assert_close(out["traj_p"][0, :ns], g["roll_p"][1:1 + ns], "spline_pendulum traj p", rtol=1e-7)
+
+
+def test_pccd_iteration_counts_on_a_large_batch(lib, ref):
+    """3000 perturbed points of the pccd rollout through every kernel flavour (table-driven thread kernel,
+    cooperative run-time-size and compile-time-size kernels) against the reference run live: same status,
+    results to 1e-10 and at most a handful of Newton iteration counts differing (measured: none)."""
+    rng = np.random.default_rng(21)
+    system, mvi = ref.make_mvi("pccd")
+    nq, nd = mvi.nq, mvi.nd
+    B = 3000
+    g = G.golden("pccd")
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+    q1 = g["roll_q"][idx] + rng.normal(0, 0.01, (B, nq)); p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, nd))
+    lam = g["roll_lambda"][idx - 1]
+    u1 = np.zeros((B, 0)); k2 = np.zeros((B, 0)); t1 = np.zeros(B); t2 = t1 + 0.01
+    want = ref.run_cases(mvi, t1, t2, q1, p1, u1, k2, lambda_guess=lam, deriv1=False)
+    for kw in (dict(specialize=False, cooperative=False), dict(specialize=False, cooperative=True), {}):
+        s = lib.System(G.desc("pccd"), **kw)
+        out = s.linearize(q1, p1, u1, k2, t1=t1, t2=t2, lambda_guess=lam)
+        assert np.array_equal(out["status"], want["status"]), s.kernel_name
+        ok = want["status"] == 0
+        for k in ("q2", "p2", "lambda1"):
+            G.assert_close(out[k][ok], want[k][ok], "pccd[%s] %s" % (s.kernel_name, k))
+        assert int(np.sum(out["iters"][ok] != want["iters"][ok])) <= 3, s.kernel_name
