@@ -98,3 +98,58 @@ def test_linearize_trajectory_shapes_and_layout():
     # state packing round trip
     Q, p, vv = ds.split_state(X)
     assert np.array_equal(ds.build_state(Q, p, vv), X)
+
+
+# ---- Monte-Carlo sweep (BASELINE config 4): rollouts block-partitioned over ranks, final states gathered
+def _host_sweep(desc, dt, nsteps):
+    import hostmath as H
+
+    def fn(q0, q1, us, ks):
+        n = q0.shape[0]
+        q2 = np.zeros((n, desc.nq)); p2 = np.zeros((n, desc.nd)); it = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+        for i in range(n):
+            p0 = H.calc_p2(desc, dt, q0[i], q1[i])
+            rc, q2[i], p2[i], lam, it[i] = H.step(desc, nsteps, dt, dt, q1[i], p0)
+            st[i] = rc
+        return q2, p2, it, st
+    return fn
+
+
+def _sweep_inputs():
+    return np.random.default_rng(8).uniform(-np.pi, np.pi, (11, 2))      # ragged over 2 ranks: 6 + 5
+
+
+def _sweep_worker(rank, world, port, q):
+    sys.path.insert(0, HERE)
+    sys.path.insert(0, os.path.dirname(HERE))
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from trep_b200.midpointvi import monte_carlo_sweep
+    desc = G.desc("dual_pendulums")
+    out = monte_carlo_sweep(desc, _sweep_inputs(), 0.01, 40, dist=dist, compute=_host_sweep(desc, 0.01, 40))
+    if rank == 0:
+        q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_monte_carlo_sweep_two_ranks_matches_single_process():
+    import torch.multiprocessing as mp
+    from trep_b200.midpointvi import monte_carlo_sweep
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    desc = G.desc("dual_pendulums")
+    want = monte_carlo_sweep(desc, _sweep_inputs(), 0.01, 40, compute=_host_sweep(desc, 0.01, 40))
+    for k in ("q2", "p2", "iters", "status", "hist"):
+        assert np.array_equal(got[k], want[k]), k
+    assert want["status"].tolist() == [0] * 11 and want["hist"].sum() == 11

@@ -45,6 +45,7 @@ class MidpointVI:
         self.q1 = self.q2 = self.p1 = self.p2 = self.u1 = self.lambda1 = None
         self.status = None
         self._lin = None
+        self._d2 = None
 
     # ---- initialisation (midpointvi.py:138-172) --------------------------------------------------
     def _b(self, x, n):
@@ -61,6 +62,7 @@ class MidpointVI:
         B = self.q1.shape[0]
         self.lambda1 = np.zeros((B, self.nc)) if lambda1 is None else self._b(lambda1, self.nc)
         self._lin = None
+        self._d2 = None
 
     def initialize_from_configs(self, t0, q0, t1, q1, lambda1=None):
         q0, q1 = self._b(q0, self.nq), self._b(q1, self.nq)
@@ -71,6 +73,7 @@ class MidpointVI:
         B = q1.shape[0]
         self.lambda1 = np.zeros((B, self.nc)) if lambda1 is None else self._b(lambda1, self.nc)
         self._lin = None
+        self._d2 = None
 
     @property
     def batch(self):
@@ -100,6 +103,7 @@ class MidpointVI:
         self.t2 = float(t2)
         self.q2, self.p2, self.lambda1 = out["q2"], out["p2"], out["lambda1"]
         self._lin = None
+        self._d2 = None
         self._check(out["status"])
         return out["iters"]
 
@@ -118,6 +122,7 @@ class MidpointVI:
         self.t2 = t
         self.q2, self.p2, self.lambda1 = out["q2"], out["p2"], out["lambda1"]
         self._lin = None
+        self._d2 = None
         self._check(out["status"])
         return out
 
@@ -154,3 +159,68 @@ class MidpointVI:
     def lambda1_dp1(self): return self._get("l1_dp1")
     def lambda1_du1(self): return self._get("l1_du1")
     def lambda1_dk2(self): return self._get("l1_dk2")
+
+    # ---- second derivatives (midpointvi.py:422-731): the 30 tensors in the reference's storage layout
+    #      [B][wrt A][wrt B][out]  (trep.h:439-473), e.g. q2_dq1dq1()[b, i, j, :] = d2 q2 / dq1_i dq1_j
+    def _calc_deriv2(self):
+        if getattr(self, "_d2", None) is None or self._lin is None:
+            assert self.q1 is not None and self.p1 is not None, "derivatives need the state before the step"
+            out = self.sys.deriv2(self.q1, self.p1, self.u1, self.q2[:, self.nd:], t1=self.t1, t2=self.t2,
+                                  q2_guess=self.q2[:, :self.nd], lambda_guess=self.lambda1 if self.nc else None,
+                                  tolerance=self.tolerance)
+            self._check(out["status"])
+            self._lin = out
+            self._d2 = out
+        return self._d2
+
+    def __getattr__(self, name):
+        # q2_dq1dq1 ... p2_dk2dk2, lambda1_dq1dq1 ... : getters generated from the tensor names
+        base = name.replace("lambda1_", "l1_", 1)
+        which, _, kind = base.partition("_")
+        if which in ("q2", "p2", "l1") and len(kind) == 6 and kind[:3] in ("dq1", "dp1", "du1", "dk2") \
+                and kind[3:] in ("dq1", "dp1", "du1", "dk2"):
+            def getter():
+                d2 = self._calc_deriv2()
+                if base in d2:
+                    return d2[base]
+                # the mirrored block (e.g. dp1dq1) is the transpose of the stored one (dq1dp1)
+                return np.ascontiguousarray(np.swapaxes(d2[which + "_" + kind[3:] + kind[:3]], 1, 2))
+            return getter
+        raise AttributeError(name)
+
+
+def monte_carlo_sweep(system, q0, dt, nsteps, q1=None, u=None, k=None, tolerance=1e-10, device=0, dist=None,
+                      hist_max=8, compute=None):
+    """Monte-Carlo initial-condition sweep (BASELINE.json config 4): every row of q0 [N, nq] is an
+    independent rollout started with ``initialize_from_configs(0, q0, dt, q1 or q0)`` and stepped
+    ``nsteps`` times inside one kernel launch.  With ``torch.distributed`` initialised (``dist``) the
+    rollouts are block-partitioned over the ranks - no exchange while stepping - and only the final
+    states (q2, p2: 16 (nq + nd) bytes per rollout), the per-rollout iteration totals and status codes
+    are all-gathered.  Returns dict(q2 [N,nq], p2 [N,nd], iters [N], status [N], hist): ``hist[i]`` =
+    number of rollouts whose mean Newton iterations per step rounds to i."""
+    from .discopt import all_gather_blocks, shard_range
+    q0 = np.atleast_2d(np.asarray(q0, float))
+    n = q0.shape[0]
+    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
+    rank = dist.get_rank() if world > 1 else 0
+    lo, hi = shard_range(n, rank, world)
+    sl = slice(lo, hi)
+    q1s = q0[sl] if q1 is None else np.atleast_2d(np.asarray(q1, float))[sl]
+    us = None if u is None else np.asarray(u, float)[sl]
+    ks = None if k is None else np.asarray(k, float)[sl]
+    if compute is None:
+        def compute(q0_, q1_, us_, ks_):
+            mvi = MidpointVI(system, tolerance=tolerance, device=device)
+            if q0_.shape[0] == 0:
+                return np.zeros((0, mvi.nq)), np.zeros((0, mvi.nd)), np.zeros(0, np.int32), np.zeros(0, np.int32)
+            mvi.initialize_from_configs(0.0, q0_, dt, q1_)
+            out = mvi.sys.step(mvi.q2, mvi.p2, mvi.t2, float(dt), nsteps=nsteps, u1=us_, k2=ks_, tolerance=tolerance)
+            return out["q2"], out["p2"], out["iters"], out["status"]
+    q2, p2, iters, status = compute(q0[sl], q1s, us, ks)
+    q2 = all_gather_blocks(np.ascontiguousarray(q2), n, dist)
+    p2 = all_gather_blocks(np.ascontiguousarray(p2), n, dist)
+    iters = all_gather_blocks(np.ascontiguousarray(iters), n, dist)
+    status = all_gather_blocks(np.ascontiguousarray(status), n, dist)
+    mean = np.rint(iters[status == 0] / float(nsteps)).astype(np.int64)
+    hist = np.bincount(np.clip(mean, 0, hist_max), minlength=hist_max + 1)
+    return dict(q2=q2, p2=p2, iters=iters, status=status, hist=hist)
