@@ -97,6 +97,7 @@ struct trepb_system {
     int ws_du_elems = 0;
     int bps_d2jac = 1;
     bool d2jac_ok = false;       // pass B's per-CTA working set fits in shared memory for this shape
+    bool d2_use_jac = false;     // second derivatives by the per-parameter scheme (trepb_d2jac.cuh)
     DevBuf ws_du, d2g;
     // staging for the host-pointer entry points
     DevBuf hb[72];
@@ -200,12 +201,20 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         s->bps[w] = b > 0 ? b : 1;
     }
     s->ws_hd_elems = s->wsl_hd.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, 1);
+    bool d2_spills = false;
     {
         int b = 0;
-        CUS(s->ks->d2_occupancy(s->block, base_smem, &b, nullptr));
+        KernelInfo ki{};
+        CUS(s->ks->d2_occupancy(s->block, base_smem, &b, &ki));
         s->bps_d2 = b > 0 ? b : 1;
+        // a specialised per-pair kernel whose hyper-dual workspace is far beyond the register file loses to
+        // the per-parameter scheme on the tables.  Measured (evaluations/s, per-pair vs per-parameter):
+        // 5-link pendulum (31 KB of local memory per thread) 8.1e6 vs 1.1e7, wrench arm (19 KB) 7.8e6 vs
+        // 1.2e7; dual pendulums (12 KB) 1.05e8 vs 6.8e7, pend-on-cart (10 KB) 1.0e8 vs 6.2e7
+        d2_spills = ki.local_bytes > 16384;
     }
-    if (!s->ks->specialized) {
+    s->d2_use_jac = !s->ks->specialized || d2_spills;
+    if (s->d2_use_jac) {
         s->ws_du_elems = s->wsl_du.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc, 2);
         int b = 0;
         CUS(d2jac_occupancy(s->block, d2jac_smem(s->blob_bytes, s->block, ps.nd, ps.nk), &b, nullptr));
@@ -564,7 +573,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         if (p.zuu && nU) CU(cudaMemsetAsync(p.zuu, 0, (size_t)B * nU * nU * sizeof(double), stream));
         if (nU == 0) { p.zxu = nullptr; p.zuu = nullptr; }
     }
-    if (!s->ks->specialized && !(s->flags & TREPB_FLAG_D2_PAIRWISE) && s->d2jac_ok) {
+    if (s->d2_use_jac && !(s->flags & TREPB_FLAG_D2_PAIRWISE) && s->d2jac_ok) {
         // pass A: one dual evaluation of the Jacobian tables per (instance, parameter);
         // pass B: contraction + solves per pair (trepb_d2jac.cuh).  The batch is processed in
         // chunks so that the table records stay within a few GB.
