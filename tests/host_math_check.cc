@@ -55,7 +55,7 @@ int th_step(const trepb_sysdesc* d, int nsteps, double t0, double dt, double tol
         for (int i = 0; i < nu; ++i) ws.u1(i) = u1 ? u1[st * nu + i] : 0.0;
         for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[st * nk + i];
         const double t2 = t1 + dt;
-        int it = solve_del(s, ws, t1, t2, tol, maxit);
+        int it = solve_del(s, ws, t1, t2, tol, maxit, sqrt_threshold(tol));
         if (it < 0) return it;
         total += it;
         t1 = t2;
@@ -92,7 +92,7 @@ int th_linearize(const trepb_sysdesc* d, double t1, double t2, double tol, int m
     for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
     for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
     for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
-    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    int it = solve_del(s, ws, t1, t2, tol, maxit, sqrt_threshold(tol));
     if (it < 0) return it;
     *iters = it;
     for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
@@ -121,7 +121,7 @@ int th_deriv2(const trepb_sysdesc* d, double t1, double t2, double tol, int maxi
     for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
     for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
     for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
-    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    int it = solve_del(s, ws, t1, t2, tol, maxit, sqrt_threshold(tol));
     if (it < 0) return it;
     std::vector<double> q2(nq), lam(nc + 1), uu(nu + 1);
     for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
@@ -184,7 +184,7 @@ int th_deriv2_jac(const trepb_sysdesc* d, double t1, double t2, double tol, int 
     for (int i = 0; i < nk; ++i) ws.q2(nd + i) = k2[i];
     for (int i = 0; i < nu; ++i) ws.u1(i) = u1[i];
     for (int c = 0; c < nc; ++c) ws.lam(c) = lam_guess ? lam_guess[c] : 0.0;
-    int it = solve_del(s, ws, t1, t2, tol, maxit);
+    int it = solve_del(s, ws, t1, t2, tol, maxit, sqrt_threshold(tol));
     if (it < 0) return it;
     std::vector<double> q2(nq), lam(nc + 1), uu(nu + 1);
     for (int i = 0; i < nq; ++i) q2[i] = ws.q2(i);
@@ -243,6 +243,20 @@ int th_deriv2_jac(const trepb_sysdesc* d, double t1, double t2, double tol, int 
     }
     return 0;
 }
+
+// div_dt against the division it replaces, on n pseudo-random numerators of mixed magnitude
+long th_div_dt_mismatches(double dt, long n) {
+    unsigned long long s = 88172645463325252ull;
+    const Dt d(dt);
+    long bad = 0;
+    for (long i = 0; i < n; ++i) {
+        s ^= s << 13; s ^= s >> 7; s ^= s << 17;
+        const double x = ((double)(s >> 11) / 9007199254740992.0 - 0.5) * ((i & 7) == 0 ? 1e-3 : ((i & 7) == 1 ? 100.0 : 1.0));
+        if (div_dt(x, d) != x / dt) ++bad;
+    }
+    return bad;
+}
+double th_sqrt_threshold(double tol) { return sqrt_threshold(tol); }
 
 // ---- team-cooperative path (trepb_coop_math.cuh) with a one-lane host team
 // returns -200 when the cooperative path does not apply to this system, -201 when the

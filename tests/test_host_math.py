@@ -173,3 +173,17 @@ def test_puppet_second_derivatives(method):
         for kd in H.D2_KINDS:
             n = w + "_" + kd
             G.assert_close(out[n], g2["case_" + n][0], "puppet " + n)
+
+
+def test_division_by_the_time_step_is_exact():
+    """div_dt (x r corrected by two fused multiply-adds) returns the bits of x / dt, and sqrt_threshold(tol)
+    is the exact boundary of sqrt(x) > tol: the two replacements in the Newton loop change no result."""
+    import ctypes as C
+    lib = H.load()
+    lib.th_div_dt_mismatches.restype = C.c_long
+    for dt in (0.01, 0.001, 0.02, 0.0125, 1.0 / 3.0, 0.1):
+        assert lib.th_div_dt_mismatches(C.c_double(dt), C.c_long(2000000)) == 0
+    lib.th_sqrt_threshold.restype = C.c_double
+    for tol in (1e-10, 1e-12, 3.3e-9, 1e-6, 0.0, 1.0):
+        T = lib.th_sqrt_threshold(C.c_double(tol))
+        assert np.sqrt(T) <= tol and (np.sqrt(np.nextafter(T, np.inf)) > tol)

@@ -385,7 +385,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     CU(cudaSetDevice(s->device));
     StepParams p;
     p.batch = a->batch; p.nsteps = a->nsteps; p.max_it = a->max_iterations;
-    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance;
+    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance; p.tolT = sqrt_threshold(a->tolerance);
     p.q1 = a->q1; p.p1 = a->p1; p.u1 = ps.nu ? a->u1 : nullptr; p.k2 = a->k2; p.q2g = a->q2_guess;
     p.lamg = ps.nc ? a->lambda_guess : nullptr;
     p.q2 = a->q2; p.p2 = a->p2; p.lam = ps.nc ? a->lambda1 : nullptr; p.iters = a->iters; p.status = a->status;
@@ -420,7 +420,7 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     CU(cudaSetDevice(s->device));
     ProjParams p;
     p.batch = a->batch; p.nsteps = a->nsteps; p.max_it = a->max_iterations;
-    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance;
+    p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance; p.tolT = sqrt_threshold(a->tolerance);
     p.bX = a->bX; p.bU = a->bU; p.K = a->Kfb; p.k_per_instance = a->k_per_instance; p.use_hint = a->use_hint;
     p.X = a->X; p.U = a->U; p.iters = a->iters; p.status = a->status; p.fail_step = a->fail_step;
     if (s->coop) {
@@ -476,7 +476,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
     if (a->batch == 0) return TREPB_OK;
     CU(cudaSetDevice(s->device));
     LinParams p;
-    p.batch = a->batch; p.max_it = a->max_iterations; p.tol = a->tolerance;
+    p.batch = a->batch; p.max_it = a->max_iterations; p.tol = a->tolerance; p.tolT = sqrt_threshold(a->tolerance);
     p.t1s = a->t1_scalar; p.dts = a->dt_scalar; p.t1 = a->t1; p.t2 = a->t2;
     p.q1 = a->q1; p.p1 = a->p1; p.u1 = a->u1; p.k2 = a->k2; p.q2g = a->q2_guess;
     p.lamg = ps.nc ? a->lambda_guess : nullptr;

@@ -25,6 +25,7 @@ struct StepParams {
     long long batch;
     int nsteps, max_it;
     double t0, dt, tol;
+    double tolT;      // sqrt_threshold(tol), computed on the host
     const double *q1, *p1, *u1, *k2, *q2g, *lamg;
     double *q2, *p2, *lam;
     int *iters, *status;
@@ -37,6 +38,7 @@ struct ProjParams {
     long long batch;
     int nsteps, max_it;
     double t0, dt, tol;
+    double tolT;      // sqrt_threshold(tol), computed on the host
     const double *bX, *bU, *K;
     int k_per_instance, use_hint;
     double *X, *U;
@@ -54,6 +56,7 @@ struct LinParams {
     long long batch;
     int max_it;
     double tol, t1s, dts;
+    double tolT;      // sqrt_threshold(tol), computed on the host
     const double *t1, *t2;
     const double *q1, *p1, *u1, *k2, *q2g, *lamg;
     double *q2, *p2, *lam;
@@ -221,6 +224,7 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    const double tolT = p.tolT;   // the Newton convergence test needs no square root (sqrt_threshold)
     for (long b = tid; b < p.batch; b += nth) {
         TREPB_UNROLL_SYS
         for (int i = 0; i < nq; ++i) {
@@ -249,7 +253,7 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
             TREPB_UNROLL_SYS
             for (int i = 0; i < nk; ++i) ws.q2(nd + i) = p.k2[(b * p.nsteps + st) * nk + i];
             const double t2 = t1 + p.dt;
-            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it, tolT);
             if (it < 0) { status = it; break; }
             total += it;
             t1 = t2;
@@ -289,6 +293,7 @@ project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStri
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    const double tolT = p.tolT;   // the Newton convergence test needs no square root (sqrt_threshold)
     const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
     for (long b = tid; b < p.batch; b += nth) {
         const double* bX = p.bX + b * (long)(K + 1) * nX;
@@ -320,7 +325,7 @@ project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStri
             }
             if (p.use_hint) { TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) ws.q2(i) = bX[(long)(s + 1) * nX + i]; }
             const double t2 = t1 + p.dt;
-            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it, tolT);
             if (it < 0) { status = it; fail = s; break; }
             total += it;
             t1 = t2;
@@ -372,6 +377,7 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
+    const double tolT = p.tolT;   // the Newton convergence test needs no square root (sqrt_threshold)
     const int nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
     extern __shared__ double smem_[];
     // loop bound is uniform per warp so that the staged stores can be warp-cooperative
@@ -401,7 +407,7 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
             for (int i = 0; i < nc; ++i) ws.lam(i) = p.lamg ? p.lamg[b * nc + i] : 0.0;
             t1 = p.t1 ? p.t1[b] : p.t1s;
             t2 = p.t2 ? p.t2[b] : (t1 + p.dts);
-            it = solve_del(sys, ws, t1, t2, p.tol, p.max_it);
+            it = solve_del(sys, ws, t1, t2, p.tol, p.max_it, tolT);
             if (it < 0) { status = it; it = 0; }
             if (p.q2) {
                 TREPB_UNROLL_SYS

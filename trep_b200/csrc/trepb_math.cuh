@@ -1165,20 +1165,52 @@ template <class Ws> struct AccTdcCol {  // column k of Tdc (nd x nc)
 // ---------------------------------------------------------------------------------------------
 // evaluation-point setters (midpointvi.c:401-457)
 // ---------------------------------------------------------------------------------------------
+// The time step and its reciprocal.  x / dt is needed for every configuration at every evaluation point;
+// the double-precision division is an emulated instruction sequence with special-case branches, so it is
+// replaced by  q = x r,  q' = q + r (x - dt q)  with r = RN(1/dt) computed once and two fused
+// multiply-adds: by Markstein's theorem q' is the correctly rounded quotient (no mismatch against x / dt in
+// 10^9 random trials per dt, tests/test_host_math.py::test_division_by_the_time_step_is_exact), i.e. the
+// same bits as the division for finite operands.
+struct Dt {
+    double dt, rdt;
+    TREPB_HD Dt(double d) : dt(d), rdt(1.0 / d) {}
+};
+TREPB_HD double div_dt(double x, const Dt& d) {
+    const double q = x * d.rdt;
+    const double e = fma(-q, d.dt, x);
+    return fma(e, d.rdt, q);
+}
+template <class T> TREPB_HD T div_dt(const T& x, const Dt& d) { return x / d.dt; }   // (hyper-)dual numbers
+
+// sqrt(x) > tol  <=>  x > sqrt_threshold(tol)  for x >= 0 (sqrt is correctly rounded and monotonic): the
+// largest T with sqrt(T) <= tol.  The convergence test of every Newton iteration (midpointvi.c:672-689)
+// then needs no square root.  Host only (the launchers pass it in the kernel parameters).
+inline double sqrt_threshold(double tol) {
+    if (!(tol >= 0.0)) return tol < 0.0 ? -1.0 : tol;      // negative: never converged; NaN: comparison false
+    double T = tol * tol;
+    for (int i = 0; i < 8 && sqrt(T) > tol; ++i) T = nextafter(T, 0.0);
+    for (int i = 0; i < 8; ++i) {
+        const double up = nextafter(T, INFINITY);
+        if (!(sqrt(up) <= tol)) break;
+        T = up;
+    }
+    return T;
+}
+
 template <class Sys, class Ws>
-TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, double dt) {  // 0 = midpoint, 1 = q1, 2 = q2
+TREPB_HD void set_point(const Sys& sys, Ws& ws, int which, const Dt& dt) {  // 0 = midpoint, 1 = q1, 2 = q2
     using Real = typename Ws::Real;
     TREPB_UNROLL_SYS
     for (int i = 0; i < sys.NQ(); ++i) {
         const Real a = ws.q1(i), b = ws.q2(i);
         ws.qe(i) = which == 0 ? 0.5 * (b + a) : (which == 1 ? a : b);
-        ws.dq(i) = (b - a) / dt;
+        ws.dq(i) = div_dt(b - a, dt);
     }
 }
 
 // Lagrangian + forces at the midpoint.  order 1: residual terms.  order 2: Jacobian terms too.
 template <class Sys, class Ws>
-TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
+TREPB_HD void eval_mid(const Sys& sys, Ws& ws, const Dt& dt, int order) {
     using Real = typename Ws::Real;
     set_point(sys, ws, 0, dt);
     pass1(sys, ws, true, sys.pairs_mid());   // world poses at the midpoint only for springs / dampers / wrenches
@@ -1193,7 +1225,7 @@ TREPB_HD void eval_mid(const Sys& sys, Ws& ws, double dt, int order) {
 // have been moved to q1/q2 by the constraint passes in between.  The reference re-walks its
 // whole cache here (set_midpoint clears every cache flag, midpointvi.c:437-457).
 template <class Sys, class Ws>
-TREPB_HD void eval_mid_again(const Sys& sys, Ws& ws, double dt) {
+TREPB_HD void eval_mid_again(const Sys& sys, Ws& ws, const Dt& dt) {
     if (sys.NC() > 0) {
         set_point(sys, ws, 0, dt);
         if (sys.pairs_mid()) pass1(sys, ws, false, true);
@@ -1208,21 +1240,25 @@ TREPB_HD void eval_mid_again(const Sys& sys, Ws& ws, double dt) {
 // start, kin part = k2), lam (start).  Outputs in ws: q2, lam, p2.  Returns the iteration count
 // (>= 0) or ST_NOT_CONVERGED / ST_SINGULAR.
 // ---------------------------------------------------------------------------------------------
+// tolT: sqrt_threshold(tol), computed on the host by the launchers (the convergence test then needs no
+// square root); NaN: test sqrt(|f|^2) > tol as written in the reference
 template <class Sys, class Ws>
-TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol, int max_it) {
+TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol, int max_it, double tolT = NAN) {
     const int nd = sys.ND(), nc = sys.NC(), nr = nd + nc;
     const double dt = t2 - t1;
+    const Dt dtt(dt);
+    const bool thr = tolT == tolT;
     int iterations = 0;
     TREPB_TICK_INIT
     if (nc > 0) {
-        set_point(sys, ws, 1, dt);
+        set_point(sys, ws, 1, dtt);
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2, 1);  // Dh1 = Dh(q1)
     }
     TREPB_TICK(0);
     for (;;) {
         // ---- calc_f (midpointvi.c:533-565)
-        eval_mid(sys, ws, dt, 1);
+        eval_mid(sys, ws, dtt, 1);
         TREPB_TICK(1);
         TREPB_UNROLL_SYS
         for (int j = 0; j < nd; ++j) {
@@ -1231,7 +1267,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             ws.fr(j) = f;
         }
         if (nc > 0) {
-            set_point(sys, ws, 2, dt);
+            set_point(sys, ws, 2, dtt);
             pass1(sys, ws, false, true);
             constraints_eval(sys, ws, 1, 2);
             TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
@@ -1240,7 +1276,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
         // ---- DEL_solved (midpointvi.c:672-689)
         double nrm = 0.0;
         TREPB_UNROLL_SYS for (int j = 0; j < nd; ++j) nrm += ws.fr(j) * ws.fr(j);
-        bool solved = !(sqrt(nrm) > tol);
+        bool solved = thr ? !(nrm > tolT) : !(sqrt(nrm) > tol);      // the same test, see sqrt_threshold
         TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c)
             if (fabs(ws.fr(nd + c)) > sys.con_d(c, 1)) solved = false;
         if (solved) break;
@@ -1248,17 +1284,17 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
 
         // ---- Jacobian (midpointvi.c:577-670): Df_11 entry by entry (the reference fills it with a
         // symmetric/antisymmetric split, :603-627, i.e. the same terms in a different order)
-        eval_mid_again(sys, ws, dt);
+        eval_mid_again(sys, ws, dtt);
         TREPB_TICK(3);
         TREPB_UNROLL_SYS
         for (int k = 0; k < nd; ++k) {
             TREPB_UNROLL_SYS
             for (int i = 0; i < nd; ++i)
-                ws.Df(k, i) = (0.25 * dt * ws.Lqq(k, i) - 1.0 / dt * ws.Lvv(k, i)) + 0.5 * ws.Lvq(i, k)
+                ws.Df(k, i) = (0.25 * dt * ws.Lqq(k, i) - dtt.rdt * ws.Lvv(k, i)) + 0.5 * ws.Lvq(i, k)
                             - 0.5 * ws.Lvq(k, i) + (0.5 * dt * ws.Fq(k, i) + ws.Fv(k, i));
         }
         if (nc > 0) {
-            set_point(sys, ws, 2, dt);
+            set_point(sys, ws, 2, dtt);
             pass1(sys, ws, false, true);
             constraints_eval(sys, ws, 2, 2);  // Dh2 = Dh(q2)
             TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
@@ -1294,7 +1330,7 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
 template <class Sys, class Ws>
 TREPB_HD void calc_p2(const Sys& sys, Ws& ws, double t1, double t2) {
     const double dt = t2 - t1;
-    eval_mid(sys, ws, dt, 1);
+    eval_mid(sys, ws, Dt(dt), 1);
     TREPB_UNROLL_SYS for (int j = 0; j < sys.ND(); ++j) ws.p2(j) = 0.5 * dt * ws.Lq(j) + ws.Lv(j);
 }
 
@@ -1315,14 +1351,15 @@ template <class Sys, class Ws>
 TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Out& o, bool mid_valid = false) {
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nc = sys.NC(), nu = sys.NU();
     const double dt = t2 - t1;
+    const Dt dtt(dt);
     const int nX = 2 * nq, nU = nu + nk;
     TREPB_TICK_INIT
     // ---- constraint derivatives at q1 and q2
     if (nc > 0) {
-        set_point(sys, ws, 1, dt);
+        set_point(sys, ws, 1, dtt);
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2 | 4, 1);  // Dh1, DDhl = sum_c lam_c DDh_c(q1)
-        set_point(sys, ws, 2, dt);
+        set_point(sys, ws, 2, dtt);
         pass1(sys, ws, false, true);
         constraints_eval(sys, ws, 2, 2);      // Dh2
     }
@@ -1330,10 +1367,10 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     // ---- calc_deriv1_cache at the midpoint (midpointvi.c:749-861).
     // mid_valid: the workspace still holds pass 1 of the converged midpoint (solve_del just ran)
     if (mid_valid) {
-        if (nc == 0) set_point(sys, ws, 0, dt);
-        eval_mid_again(sys, ws, dt);
+        if (nc == 0) set_point(sys, ws, 0, dtt);
+        eval_mid_again(sys, ws, dtt);
     } else {
-        eval_mid(sys, ws, dt, 2);
+        eval_mid(sys, ws, dtt, 2);
     }
     TREPB_TICK(9);
     // Entry by entry; the reference fills the same four tables with a
@@ -1343,7 +1380,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     for (int a = 0; a < nq; ++a) {
         TREPB_UNROLL_SYS
         for (int b = 0; b < nd; ++b) {
-            const double qq = 0.25 * dt * ws.Lqq(a, b), vv = 1.0 / dt * ws.Lvv(a, b);
+            const double qq = 0.25 * dt * ws.Lqq(a, b), vv = dtt.rdt * ws.Lvv(a, b);
             const double vab = 0.5 * ws.Lvq(a, b), vba = 0.5 * ws.Lvq(b, a);
             const double fq = 0.5 * dt * ws.Fq(b, a), fv = ws.Fv(b, a);
             ws.T11(a, b) = (qq + vv) - vab - vba + (fq - fv);
@@ -1617,7 +1654,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 const bool dyn_row = r < nd || (r >= nq && r < nq + nd);
                 if (dyn_row && c < nq + nd) continue;  // written above
                 double v = 0.0;
-                if (r >= nq + nd && c >= nd && c < nq && (r - nq - nd) == (c - nd)) v = -1.0 / dt;
+                if (r >= nq + nd && c >= nd && c < nq && (r - nq - nd) == (c - nd)) v = -dtt.rdt;
                 o.A[(long)(r * nX + c) * es] = v;
             }
     }
@@ -1630,7 +1667,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 if (dyn_row) continue;
                 double v = 0.0;
                 if (r >= nd && r < nq && c >= nu && (r - nd) == (c - nu)) v = 1.0;
-                if (r >= nq + nd && c >= nu && (r - nq - nd) == (c - nu)) v = 1.0 / dt;
+                if (r >= nq + nd && c >= nu && (r - nq - nd) == (c - nu)) v = dtt.rdt;
                 o.B[(long)(r * nU + c) * es] = v;
             }
     }
