@@ -105,9 +105,55 @@ TREPB_HD void rotF(T* x, int b, int c, T cs, T sn) {
     x[b] = cs * xb - sn * xc;
     x[c] = sn * xb + cs * xc;
 }
+#if defined(__CUDACC__)
+// sin and cos of one angle for the device.  Same structure as the library routine (Cody-Waite reduction by
+// multiples of pi/2 in three pieces, minimax polynomials in r^2 on [-pi/4, pi/4], quadrant swap), with the
+// coefficients in constant memory: they then reach the FP64 pipe as constant-bank operands of the
+// DFMAs, where the inlined library routine materialised every coefficient with two uniform-register
+// moves in the instruction stream (98 UMOV of the 429 warp instructions of a damped-pendulum DEL step,
+// profiles/r01i_step_raw.txt).  Coefficients: the classical fdlibm kernels (k_sin.c / k_cos.c, |error| < 1 ulp
+// on the reduced argument).  Arguments beyond 1e5 in magnitude take the library routine.
+static __constant__ double kSinCos[16] = {
+    6.36619772367581382433e-01,    //  0  2/pi
+    1.57079632673412561417e+00,    //  1  pi/2, first 33 bits
+    6.07710050630396597660e-11,    //  2  pi/2, next 33 bits
+    2.02226624871116645580e-21,    //  3  pi/2, next 33 bits
+    -1.66666666666666324348e-01,   //  4  S1
+    8.33333333332248946124e-03,    //  5  S2
+    -1.98412698298579493134e-04,   //  6  S3
+    2.75573137070700676789e-06,    //  7  S4
+    -2.50507602534068634195e-08,   //  8  S5
+    1.58969099521155010221e-10,    //  9  S6
+    4.16666666666666019037e-02,    // 10  C1
+    -1.38888888888741095749e-03,   // 11  C2
+    2.48015872894767294178e-05,    // 12  C3
+    -2.75573143513906633035e-07,   // 13  C4
+    2.08757232129817482790e-09,    // 14  C5
+    -1.13596475577881948265e-11};  // 15  C6
+__device__ __forceinline__ void sincos_dev(double x, double* s, double* c) {
+    if (!(fabs(x) <= 1.0e5)) { sincos(x, s, c); return; }
+    const double j = rint(x * kSinCos[0]);
+    double r = fma(-j, kSinCos[1], x);
+    r = fma(-j, kSinCos[2], r);
+    r = fma(-j, kSinCos[3], r);
+    const double z = r * r;
+    double ps = fma(z, kSinCos[9], kSinCos[8]);
+    double pc = fma(z, kSinCos[15], kSinCos[14]);
+    ps = fma(z, ps, kSinCos[7]);  pc = fma(z, pc, kSinCos[13]);
+    ps = fma(z, ps, kSinCos[6]);  pc = fma(z, pc, kSinCos[12]);
+    ps = fma(z, ps, kSinCos[5]);  pc = fma(z, pc, kSinCos[11]);
+    ps = fma(z, ps, kSinCos[4]);  pc = fma(z, pc, kSinCos[10]);
+    const double sr = fma(z * r, ps, r);                       // r + r^3 S(r^2)
+    const double cr = fma(z * z, pc, fma(-0.5, z, 1.0));       // 1 - r^2/2 + r^4 C(r^2)
+    const int q = (int)j;
+    const double a = (q & 1) ? cr : sr, b = (q & 1) ? sr : cr;
+    *s = (q & 2) ? -a : a;
+    *c = ((q + 1) & 2) ? -b : b;
+}
+#endif
 TREPB_HD void sincos_(double x, double* s, double* c) {
 #if defined(__CUDA_ARCH__)
-    sincos(x, s, c);
+    sincos_dev(x, s, c);
 #else
     *s = sin(x);
     *c = cos(x);
