@@ -32,6 +32,7 @@
 // fully-unrolled specialised kernel.
 #pragma once
 #include <math.h>
+#include <type_traits>
 #include "trepb_sys.h"
 #include "trepb_ws.h"
 
@@ -159,6 +160,7 @@ TREPB_HD void sincos_(double x, double* s, double* c) {
     *c = cos(x);
 #endif
 }
+TREPB_HD double div_r(double x, double d, double r);
 TREPB_HD bool isnan_(double x) { return isnan(x); }
 // value part of a (hyper-)dual number / the number itself
 TREPB_HD double val_(double x) { return x; }
@@ -1050,8 +1052,9 @@ TREPB_HD void forces_eval(const Sys& sys, Ws& ws, int order, bool zero_tables = 
 // For a compile-time system (Sys::kStatic) every array index must be a loop counter so that the
 // matrix lives in registers after full unrolling: the row swap and the permuted gather become
 // predicated selects.  Arithmetic and pivot rule are the same in both flavours.
-template <class Sys, class MatAcc, class PivAcc, class ScaleAcc>
-TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol) {
+// rd(j) receives 1 / U(j,j); the divisions by the pivots (and those of lu_solve) go through div_r.
+template <class Sys, class MatAcc, class PivAcc, class ScaleAcc, class RdAcc>
+TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, RdAcc rd, double tol) {
     TREPB_UNROLL_SYS
     for (int i = 0; i < n; ++i) {
         double s = -1.0;
@@ -1149,15 +1152,20 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, double tol
                 scales(pi) = scales(j);
             }
         }
-        const double d = A(j, j);
+        const double d = A(j, j), r = 1.0 / d;
+        rd(j) = r;
         TREPB_UNROLL_SYS
-        for (int i = j + 1; i < n; ++i) A(i, j) /= d;
+        for (int i = j + 1; i < n; ++i) A(i, j) = div_r(A(i, j), d, r);
     }
     return true;
 }
+// the reciprocal-diagonal accessor of a factorization that did not keep them: plain divisions
+struct NoRd {
+    TREPB_HD double operator()(int) const { return 0.0; }
+};
 // solves in place: b <- A^-1 b  (math-code.c:434-461); x is scratch of length n
-template <class Sys, class MatAcc, class PivAcc, class BAcc, class XAcc>
-TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x) {
+template <class Sys, class MatAcc, class PivAcc, class BAcc, class XAcc, class RdAcc = NoRd>
+TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x, RdAcc rd = RdAcc()) {
     TREPB_UNROLL_SYS
     for (int i = 0; i < n; ++i) {
         double t;
@@ -1181,7 +1189,8 @@ TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x) {
         double t = x(i);
         TREPB_UNROLL_SYS
         for (int j = i + 1; j < n; ++j) t -= A(i, j) * x(j);
-        t = t / A(i, i);
+        if constexpr (std::is_same<RdAcc, NoRd>::value) t = t / A(i, i);
+        else t = div_r(t, A(i, i), rd(i));
         x(i) = t;
     }
     TREPB_UNROLL_SYS
@@ -1203,6 +1212,7 @@ TREPB_ACC2(AccDf, Df) TREPB_ACC2(AccM2, M2) TREPB_ACC2(AccPJ, PJ)
 TREPB_ACC1(AccPiv, piv) TREPB_ACC1(AccLus, lus) TREPB_ACC1(AccLux, lux) TREPB_ACC1(AccFr, fr)
 TREPB_ACC1(AccM2p, M2p) TREPB_ACC1(AccPJp, PJp) TREPB_ACC1(AccTnd, tnd) TREPB_ACC1(AccTnc, tnc)
 TREPB_ACC1(AccCol, col)
+TREPB_ACC1(AccDfr, Dfr) TREPB_ACC1(AccM2r, M2r) TREPB_ACC1(AccPJr, PJr)
 template <class Ws> struct AccTdcCol {  // column k of Tdc (nd x nc)
     Ws* w; int k;
     TREPB_HD double& operator()(int i) const { return w->Tdc(i, k); }
@@ -1227,6 +1237,12 @@ TREPB_HD double div_dt(double x, const Dt& d) {
     return fma(e, d.rdt, q);
 }
 template <class T> TREPB_HD T div_dt(const T& x, const Dt& d) { return x / d.dt; }   // (hyper-)dual numbers
+// x / d with r = RN(1/d) at hand (the pivots of an LU factorization divide many numbers): the same correction
+TREPB_HD double div_r(double x, double d, double r) {
+    const double q = x * r;
+    const double e = fma(-q, d, x);
+    return fma(e, r, q);
+}
 
 // sqrt(x) > tol  <=>  x > sqrt_threshold(tol)  for x >= 0 (sqrt is correctly rounded and monotonic): the
 // largest T with sqrt(T) <= tol.  The convergence test of every Newton iteration (midpointvi.c:672-689)
@@ -1358,8 +1374,8 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
             if (!(fabs(a) > 0.0)) return ST_SINGULAR;
             ws.fr(0) = ws.fr(0) / a;
         } else {
-            if (!lu_decomp<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
-            lu_solve<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws});
+            if (!lu_decomp<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccLus<Ws>{&ws}, AccDfr<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+            lu_solve<Sys>(AccDf<Ws>{&ws}, nr, AccPiv<Ws>{&ws}, AccFr<Ws>{&ws}, AccLux<Ws>{&ws}, AccDfr<Ws>{&ws});
         }
         TREPB_TICK(5);
         TREPB_UNROLL_SYS for (int k = 0; k < nd; ++k) ws.q2(k) -= ws.fr(k);
@@ -1442,14 +1458,14 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
     // ---- calc_M2 (midpointvi.c:891-908)
     TREPB_UNROLL_SYS for (int a = 0; a < nd; ++a)
         TREPB_UNROLL_SYS for (int b = 0; b < nd; ++b) ws.M2(a, b) = ws.T21(b, a);
-    if (!lu_decomp<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+    if (!lu_decomp<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccLus<Ws>{&ws}, AccM2r<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
     // ---- calc_proj_inv (midpointvi.c:910-927): proj = -Dh2_d M2^-1 Dh1^T
     if (nc > 0) {
         TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i)
             TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.Tdc(i, c) = ws.Dh1(c, i);
         TREPB_UNROLL_SYS
         for (int c = 0; c < nc; ++c)
-            lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTdcCol<Ws>{&ws, c}, AccLux<Ws>{&ws});
+            lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTdcCol<Ws>{&ws, c}, AccLux<Ws>{&ws}, AccM2r<Ws>{&ws});
         TREPB_UNROLL_SYS
         for (int a = 0; a < nc; ++a)
             TREPB_UNROLL_SYS
@@ -1459,7 +1475,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                 for (int k = 0; k < nd; ++k) s += ws.Dh2(a, k) * ws.Tdc(k, b);
                 ws.PJ(a, b) = -s;
             }
-        if (!lu_decomp<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
+        if (!lu_decomp<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccLus<Ws>{&ws}, AccPJr<Ws>{&ws}, 1e-20)) return ST_SINGULAR;
     }
 
     TREPB_TICK(11);
@@ -1490,7 +1506,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                     ws.col(j) = c;
                 }
                 if (nc > 0) {
-                    lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws});
+                    lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccTnd<Ws>{&ws}, AccLux<Ws>{&ws}, AccM2r<Ws>{&ws});
                     TREPB_UNROLL_SYS
                     for (int c = 0; c < nc; ++c) {
                         double s = 0.0;
@@ -1499,7 +1515,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                         if (kindv == 3) s += ws.Dh2(c, nd + i);
                         ws.tnc(c) = s;
                     }
-                    lu_solve<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws});
+                    lu_solve<Sys>(AccPJ<Ws>{&ws}, nc, AccPJp<Ws>{&ws}, AccTnc<Ws>{&ws}, AccLux<Ws>{&ws}, AccPJr<Ws>{&ws});
                     TREPB_UNROLL_SYS
                     for (int j = 0; j < nd; ++j) {
                         double s = ws.col(j);
@@ -1508,7 +1524,7 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                         ws.col(j) = s;
                     }
                 }
-                lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws});
+                lu_solve<Sys>(AccM2<Ws>{&ws}, nd, AccM2p<Ws>{&ws}, AccCol<Ws>{&ws}, AccLux<Ws>{&ws}, AccM2r<Ws>{&ws});
                 // p2 derivative row
                 double* q2o = kindv == 0 ? o.q2_dq1 : (kindv == 1 ? o.q2_dp1 : (kindv == 2 ? o.q2_du1 : o.q2_dk2));
                 double* p2o = kindv == 0 ? o.p2_dq1 : (kindv == 1 ? o.p2_dp1 : (kindv == 2 ? o.p2_du1 : o.p2_dk2));
@@ -1592,8 +1608,8 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                     const double a = ws.M2(i, j);
                     TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
                 }
-                const double dg = ws.M2(i, i);
-                TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = t[g] / dg; ws.lux(i, g) = t[g]; }
+                const double dg = ws.M2(i, i), rg = ws.M2r(i);
+                TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = div_r(t[g], dg, rg); ws.lux(i, g) = t[g]; }
             }
             for (int i = 0; i < nd; ++i) {
                 TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.tnd(i, g) = ws.lux(i, g);
@@ -1629,8 +1645,8 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
                         const double a = ws.PJ(i, j);
                         TREPB_UNROLL for (int g = 0; g < kG; ++g) t[g] -= a * ws.lux(j, g);
                     }
-                    const double dg = ws.PJ(i, i);
-                    TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = t[g] / dg; ws.lux(i, g) = t[g]; }
+                    const double dg = ws.PJ(i, i), rg = ws.PJr(i);
+                    TREPB_UNROLL for (int g = 0; g < kG; ++g) { t[g] = div_r(t[g], dg, rg); ws.lux(i, g) = t[g]; }
                 }
                 for (int i = 0; i < nc; ++i) {
                     TREPB_UNROLL for (int g = 0; g < kG; ++g) ws.tnc(i, g) = ws.lux(i, g);

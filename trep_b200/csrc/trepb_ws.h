@@ -33,10 +33,12 @@ namespace trepb {
     /* point-pair scratch: d(pA-pB)/dq_j for every config */                                   \
     X(dv, NQ, 3, 1) X(dxs, NQ, 1, 1)                                                           \
     /* Newton */                                                                               \
-    X(fr, NR, 1, 1) X(Df, NR, NR, 0) X(piv, NR, 1, 0) X(lus, NR, 1, 0) X(lux, NR, 4, 0)        \
+    X(fr, NR, 1, 1) X(Df, NR, NR, 0) X(piv, NR, 1, 0) X(lus, NR, 1, 0) X(lux, NR, 4, 0) X(Dfr, NR, 1, 0) \
     /* first-derivative tables and solves (tnd/tnc/col/lux: 4 right-hand sides at a time) */                                                   \
     X(T11, NQ, ND, 0) X(T21, NQ, ND, 0) X(T12, NQ, ND, 0) X(T22, NQ, ND, 0) X(T3, NU, ND, 0)   \
     X(M2, ND, ND, 0) X(M2p, ND, 1, 0) X(PJ, NC, NC, 0) X(PJp, NC, 1, 0) X(tnd, ND, 4, 0) X(tnc, NC, 4, 0) \
+    /* reciprocal diagonals of the three factorizations (divisions by them: div_r) */          \
+    X(M2r, ND, 1, 0) X(PJr, NC, 1, 0)                                                          \
     X(Tdc, ND, NC, 0) X(col, ND, 4, 0)
 
 template <class Sys, class RealT = double>
