@@ -180,8 +180,18 @@ const KernelSet* general_kernels();
 // minimum resident CTAs per SM requested from the compiler (register cap = 65536 / (128 * N));
 // experiments: -DTREPB_LB_MIN=6 ...
 #ifndef TREPB_LB_MIN
-#define TREPB_LB_MIN 1
+#define TREPB_LB_MIN 0
 #endif
+// Small specialised systems (<= 2 configs) are asked for 4 resident CTAs per SM (<= 128 registers): measured on
+// pend-on-cart's linearize kernel 0.410 -> 0.359 ms per 2^22 instances (130 -> 120 registers, no spills; 5 CTAs
+// at 96 registers: 0.369), damped pendulum step 0.746 -> 0.734 ms.  Larger specialised systems keep the whole
+// register file per thread (their workspace lives in registers), the table-driven kernels are unconstrained.
+template <class Sys>
+constexpr int lb_min() {
+    if (TREPB_LB_MIN > 0) return TREPB_LB_MIN;
+    if constexpr (Sys::kStatic) return Sys::kNQ <= 2 ? 4 : 1;
+    else return 1;
+}
 // ---------------------------------------------------------------------------------------------
 template <class Sys, bool S = Sys::kStatic>
 struct Ctx;
@@ -216,7 +226,7 @@ struct Ctx<Sys, false> {
 };
 
 template <class Sys>
-__global__ void __launch_bounds__(128, TREPB_LB_MIN)
+__global__ void __launch_bounds__(128, lb_min<Sys>())
 step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const StepParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
@@ -285,7 +295,7 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
 // DSystem.project / armijo_simulate: X[0] = bX[0]; U[k] = bU[k] - K[k](X[k] - bX[k]); X[k+1] = f(X[k],U[k])
 // (trep/discopt/dsystem.py:426-457), one thread per candidate, the feedback inside the time loop.
 template <class Sys>
-__global__ void __launch_bounds__(128, TREPB_LB_MIN)
+__global__ void __launch_bounds__(128, lb_min<Sys>())
 project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const ProjParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
@@ -369,7 +379,7 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
 }
 
 template <class Sys>
-__global__ void __launch_bounds__(128, TREPB_LB_MIN)
+__global__ void __launch_bounds__(128, lb_min<Sys>())
 lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
