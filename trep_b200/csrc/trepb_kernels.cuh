@@ -186,10 +186,13 @@ const KernelSet* general_kernels();
 // pend-on-cart's linearize kernel 0.410 -> 0.359 ms per 2^22 instances (130 -> 120 registers, no spills; 5 CTAs
 // at 96 registers: 0.369), damped pendulum step 0.746 -> 0.734 ms.  Larger specialised systems keep the whole
 // register file per thread (their workspace lives in registers), the table-driven kernels are unconstrained.
-template <class Sys>
+// The linearize kernel of those systems streams 224+ bytes per instance and gains from one more CTA: along
+// trajectories with exact hints (W3) 1.85e10 linearizations/s at 4 CTAs, 2.04e10 at 5 (96 registers, 44 bytes
+// of spills), 1.96e10 at 6; on random states (2.2 Newton iterations) 1.18e10 / 1.14e10 / 1.12e10.
+template <class Sys, bool kLin = false>
 constexpr int lb_min() {
     if (TREPB_LB_MIN > 0) return TREPB_LB_MIN;
-    if constexpr (Sys::kStatic) return Sys::kNQ <= 2 ? 4 : 1;
+    if constexpr (Sys::kStatic) return Sys::kNQ <= 2 ? (kLin ? 5 : 4) : 1;
     else return 1;
 }
 // ---------------------------------------------------------------------------------------------
@@ -379,7 +382,7 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
 }
 
 template <class Sys>
-__global__ void __launch_bounds__(128, lb_min<Sys>())
+__global__ void __launch_bounds__(128, lb_min<Sys, true>())
 lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
