@@ -57,14 +57,10 @@ TREPB_HD Dual& operator*=(Dual& x, const Dual& y) { x = x * y; return x; }
 TREPB_HD Dual& operator+=(Dual& x, double y) { x.v += y; return x; }
 TREPB_HD Dual& operator-=(Dual& x, double y) { x.v -= y; return x; }
 TREPB_HD Dual& operator*=(Dual& x, double y) { x.v *= y; x.a *= y; return x; }
+TREPB_HD void sincos_(double x, double* s, double* c);   // trepb_math.cuh
 TREPB_HD void sincos_(const Dual& x, Dual* s, Dual* c) {
     double sn, cs;
-#if defined(__CUDA_ARCH__)
-    sincos(x.v, &sn, &cs);
-#else
-    sn = sin(x.v);
-    cs = cos(x.v);
-#endif
+    sincos_(x.v, &sn, &cs);
     *s = Dual(sn, cs * x.a);
     *c = Dual(cs, -sn * x.a);
 }

@@ -92,14 +92,10 @@ template <int N> TREPB_HD HDn<N>& operator+=(HDn<N>& x, double y) { x.v += y; re
 template <int N> TREPB_HD HDn<N>& operator-=(HDn<N>& x, double y) { x.v -= y; return x; }
 template <int N> TREPB_HD HDn<N>& operator*=(HDn<N>& x, double y) { x = x * y; return x; }
 
+TREPB_HD void sincos_(double x, double* s, double* c);   // trepb_math.cuh
 template <int N> TREPB_HD void sincos_(const HDn<N>& x, HDn<N>* s, HDn<N>* c) {
     double sn, cs;
-#if defined(__CUDA_ARCH__)
-    sincos(x.v, &sn, &cs);
-#else
-    sn = sin(x.v);
-    cs = cos(x.v);
-#endif
+    sincos_(x.v, &sn, &cs);
     *s = hd_chain(x, sn, cs, -sn);
     *c = hd_chain(x, cs, -sn, -cs);
 }

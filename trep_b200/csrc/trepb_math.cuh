@@ -1236,7 +1236,7 @@ TREPB_HD double div_dt(double x, const Dt& d) {
     const double e = fma(-q, d.dt, x);
     return fma(e, d.rdt, q);
 }
-template <class T> TREPB_HD T div_dt(const T& x, const Dt& d) { return x / d.dt; }   // (hyper-)dual numbers
+template <class T> TREPB_HD T div_dt(const T& x, const Dt& d) { return x * d.rdt; }   // (hyper-)dual numbers: x * (1 / dt), as their operator/ does
 // x / d with r = RN(1/d) at hand (the pivots of an LU factorization divide many numbers): the same correction
 TREPB_HD double div_r(double x, double d, double r) {
     const double q = x * r;
