@@ -340,6 +340,10 @@ int trepb_synchronize(int device);
 int trepb_last_kernel_ms(trepb_system* sys, float* ms);
 /* FP64 FMA micro-benchmark (roofline denominator): achieved TFLOP/s of a DFMA-saturating kernel. */
 int trepb_measure_fp64_peak(int device, double* tflops);
+/* Diagnostic: sin and cos as the kernels compute them (trep/_trep/frame.c:839-1076 calls libm's sin / cos for
+ * every revolute frame; the kernels use their own routine with the coefficients in constant memory).  Host
+ * pointers, n values.  Used by the tests to bound its error in ulps against libm. */
+int trepb_sincos_batch(int device, int64_t n, const double* x, double* s, double* c);
 
 #ifdef __cplusplus
 }

@@ -696,3 +696,21 @@ def test_pccd_iteration_counts_on_a_large_batch(lib, ref):
         for k in ("q2", "p2", "lambda1"):
             G.assert_close(out[k][ok], want[k][ok], "pccd[%s] %s" % (s.kernel_name, k))
         assert int(np.sum(out["iters"][ok] != want["iters"][ok])) <= 3, s.kernel_name
+
+
+def test_device_sincos_accuracy(lib):
+    """The kernels' own sin / cos (constant-memory coefficients, trepb_math.cuh sincos_dev) against libm:
+    within 2 ulp over the range rollouts visit, exact at 0, library path for huge arguments, NaN for NaN / inf."""
+    rng = np.random.default_rng(0)
+    x = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e5, 1e5, 100000), rng.uniform(-1e-3, 1e-3, 50000),
+                        np.array([0.0, -0.0, np.pi / 2, np.pi, -np.pi, 1e5, -1e5, 3e5, 1e12])])
+    s, c = lib.sincos(x)
+    for got, want in ((s, np.sin(x)), (c, np.cos(x))):
+        ulp = np.spacing(np.maximum(np.abs(want), 1e-300))
+        err = np.abs(got - want) / ulp
+        small = np.abs(want) > 1e-6          # near a zero of sin / cos the absolute error is what matters
+        assert np.max(err[small]) <= 2.0, float(np.max(err[small]))
+        assert np.max(np.abs(got - want)[~small]) <= 1e-21 + 4e-16 * 1e-6
+    assert s[-9] == 0.0 and c[-9] == 1.0
+    bad_s, bad_c = lib.sincos(np.array([np.nan, np.inf, -np.inf]))
+    assert np.all(np.isnan(bad_s)) and np.all(np.isnan(bad_c))

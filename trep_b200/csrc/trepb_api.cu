@@ -897,3 +897,32 @@ extern "C" int trepb_measure_fp64_peak(int device, double* tflops) {
     *tflops = best;
     return TREPB_OK;
 }
+
+// ---- diagnostic: the device sin / cos routine of the kernels (trepb_math.cuh sincos_dev) ----------
+namespace {
+__global__ void sincos_kernel(const double* x, double* s, double* c, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) trepb::sincos_(x[i], s + i, c + i);
+}
+}  // namespace
+
+extern "C" int trepb_sincos_batch(int device, int64_t n, const double* x, double* s, double* c) {
+    if (n < 0 || (n > 0 && (!x || !s || !c))) return fail(TREPB_ERR_INVALID, "null argument");
+    if (n == 0) return TREPB_OK;
+    CU(cudaSetDevice(device));
+    double *dx = nullptr, *ds = nullptr, *dc = nullptr;
+    int rc = TREPB_OK;
+    cudaError_t e = cudaMalloc((void**)&dx, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&ds, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dc, n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpy(dx, x, n * sizeof(double), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        sincos_kernel<<<(unsigned)((n + 255) / 256), 256>>>(dx, ds, dc, n);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpy(s, ds, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess) e = cudaMemcpy(c, dc, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) rc = cuda_fail(e, "trepb_sincos_batch");
+    cudaFree(dx); cudaFree(ds); cudaFree(dc);
+    return rc;
+}

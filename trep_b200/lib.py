@@ -118,6 +118,7 @@ _lib.trepb_memcpy_h2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
 _lib.trepb_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
 _lib.trepb_memset.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64]
 _lib.trepb_measure_fp64_peak.argtypes = [C.c_int, _dp]
+_lib.trepb_sincos_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
 
 EXPORTS = [
     "trepb_abi_version", "trepb_last_error", "trepb_system_create", "trepb_system_destroy",
@@ -127,7 +128,7 @@ EXPORTS = [
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
-    "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak",
+    "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak", "trepb_sincos_batch",
 ]
 
 
@@ -243,6 +244,14 @@ def measure_fp64_peak(device=0):
     v = C.c_double(0)
     _check(_lib.trepb_measure_fp64_peak(device, C.byref(v)))
     return v.value
+
+
+def sincos(x, device=0):
+    """(sin, cos) of an array as the kernels compute them (diagnostic)."""
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    s, c = np.empty_like(x), np.empty_like(x)
+    _check(_lib.trepb_sincos_batch(device, x.size, x.ctypes.data, s.ctypes.data, c.ctypes.data))
+    return s, c
 
 
 def synchronize(device=0):
