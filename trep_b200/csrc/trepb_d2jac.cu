@@ -431,12 +431,14 @@ cudaError_t d2jac_run(const LaunchCfg& c, const WsStridedT<Dual>& w, const D2Par
 }
 size_t d2solve_smem_needed(int nd, int nk, int nc, int nx, int aux_size) {
     if (nd == 22 && nc == 6) return D2Ct<22, 6>::smem(nd + nk);
+    if (nd == 7 && nc == 4) return D2Ct<7, 4>::smem(nd + nk);
     return d2solve_smem(nd, nk, nc, aux_size, ((nx + 31) / 32) * 32);
 }
 cudaError_t d2solve_run(cudaStream_t stream, const D2Params& p, const double* G, const JacLayout& jl, int nd, int nk,
                         int nu, int nc, long b0, long nb) {
     // shapes with a compile-time-size pass B (the marionette of BASELINE.json's config 5)
     if (nd == 22 && nc == 6) return d2solve_ct_run<22, 6>(stream, p, G, jl, nk, nu, b0, nb);
+    if (nd == 7 && nc == 4) return d2solve_ct_run<7, 4>(stream, p, G, jl, nk, nu, b0, nb);   // examples/pccd.py
     const int T = ((p.nx + 31) / 32) * 32;
     const size_t smem = d2solve_smem(nd, nk, nc, p.auxl.size, T);
     if (smem > 48 * 1024) {
