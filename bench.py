@@ -472,6 +472,30 @@ def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
             if b is not None:
                 b.free()
         s.close()
+    # second derivatives of the closed chain (PointOnPlane constraints), z-contracted
+    d = systems.named_desc("pccd")
+    s = lib.System(d, device=device)
+    Bp = 1 << 14
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pccd.npz"))
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, Bp)
+    dq = up(g["roll_q"][idx] + rng.normal(0, 0.01, (Bp, d.nq))); dp = up(g["roll_p"][idx] + rng.normal(0, 0.05, (Bp, d.nd)))
+    lam = up(g["roll_lambda"][idx - 1]); st = lib.DeviceBuffer(device, (Bp,), np.int32)
+    z = up(rng.normal(0, 1, (Bp, d.nX))); xx = lib.DeviceBuffer(device, (Bp, d.nX, d.nX))
+    ms = []
+    for rep in range(3):
+        s.deriv2_raw(True, Bp, dq, dp, None, None, st, {}, z=z, fdxdx=xx, t1_scalar=0.0, dt_scalar=DT, lambda_guess=lam)
+        lib.synchronize(device)
+        if rep >= 1:
+            ms.append(s.last_kernel_ms())
+    t = float(np.mean(ms))
+    out.append({"metric": "second-derivative evaluations/s (pccd: 7 DOF closed chain, 105 parameter pairs, z-contracted fdxdx)",
+                "value": Bp / t * 1e3, "unit": "evaluations/s", "batch": Bp, "ms": t, "kernel": s.kernel_name,
+                "ok_fraction": float((st.download() == 0).mean()),
+                "note": "both second-derivative passes (dual Jacobian tables per parameter, compile-time-size per-pair solves); "
+                        "the preceding cooperative linearize launch is not included"})
+    for b in (dq, dp, lam, st, z, xx):
+        b.free()
+    s.close()
     # W1 (BASELINE config 0, examples/pendulum.py): N-link pendulum, a large batch and the latency of ONE rollout
     for links, B, nsteps in ((1, 1 << 20, 1000), (5, 1 << 18, 200), (1, 1, 1000), (5, 1, 1000)):
         d = systems.named_desc("pendulum%d" % links)
