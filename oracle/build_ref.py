@@ -133,7 +133,17 @@ def patch_py(text, relpath, siblings):
     return text
 
 
-def build(reference, force=False):
+LINEARDAMPER_BUG = "dx_dqdq2 = TapeMeasure_length_dq(self->path, q2);"
+LINEARDAMPER_FIX = "dx_dqdq2 = TapeMeasure_length_dqdq(self->path, q, q2);"
+
+
+def build(reference, force=False, out=None, fix_lineardamper=False):
+    """`out` / `fix_lineardamper`: a SECOND build outside the repo (oracle/gen_golden_r2.py uses a temp dir) with
+    the one-line typo of forces/lineardamper.c:99 corrected (f_ddqdq reads length_dq(q2) where the product rule
+    - and its own f_dqdq at :79 - needs length_dqdq(q, q2)).  It exists only to show that this library's
+    LinearDamper second derivatives equal the reference's once that line is right; oracle/_ref itself is never
+    built with it."""
+    OUT = out or globals()["OUT"]
     src_pkg = os.path.join(reference, "trep")
     so_path = os.path.join(OUT, "trep", "_trep" + sysconfig.get_config_var("EXT_SUFFIX"))
     if os.path.exists(so_path) and not force:
@@ -177,6 +187,9 @@ def build(reference, force=False):
                     p = os.path.join(root, f)
                     with open(p) as fh:
                         text = fh.read()
+                    if fix_lineardamper and f == "lineardamper.c":
+                        assert text.count(LINEARDAMPER_BUG) == 1
+                        text = text.replace(LINEARDAMPER_BUG, LINEARDAMPER_FIX)
                     with open(p, "w") as fh:
                         fh.write(patch_c(text, f))
         incs = ["-I" + sysconfig.get_paths()["include"], "-I" + numpy.get_include(), "-I" + csrc]

@@ -118,3 +118,22 @@ def time_parallel(name, kind, shards, reps=1, procs=None):
     # throughput from the slowest worker's own loop time (excludes process start / system build)
     loop = max(r[1] for r in res)
     return units / loop, procs, wall
+
+
+# ---- multi-process results (parity at scale: tests/test_gpu_parity_r2.py) ------------------------------
+def _rollout_worker(args):
+    name, q, p, nsteps, t0, dt = args
+    return Harness(name).rollouts(q, p, nsteps, t0, dt)
+
+
+def rollouts_parallel(name, q, p, nsteps, t0, dt, procs=None):
+    """Harness.rollouts over all host cores (one reference MidpointVI per process, disjoint shards of the
+    batch): final states, summed Newton iteration counts and status of every rollout."""
+    procs = procs or len(os.sched_getaffinity(0))
+    B = q.shape[0]
+    cuts = np.linspace(0, B, procs + 1).astype(int)
+    jobs = [(name, q[a:b], p[a:b], nsteps, t0, dt) for a, b in zip(cuts[:-1], cuts[1:]) if b > a]
+    ctx = mp.get_context("fork")
+    with ctx.Pool(len(jobs)) as pool:
+        res = pool.map(_rollout_worker, jobs)
+    return {k: np.concatenate([r[k] for r in res]) for k in res[0]}

@@ -155,6 +155,63 @@ def ref_spline_pendulum():
     return system
 
 
+def ref_fourbar():
+    """Planar loop closed by a PointToPoint2D (two PointToPoint1D, constraints/point.c:16-55); one input."""
+    system = trep.System()
+    system.import_frames([
+        rx('a1'), [tz(-1.0, mass=1.0, name='A1'), [rx('a2'), [tz(-1.2, name='tipA', mass=0.7)]]],
+        ty(1.5), [rx('b1'), [tz(-1.4, name='tipB', mass=1.3)]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.05)
+    trep.forces.ConfigForce(system, 'a1', 'torque')
+    trep.constraints.PointToPoint2D(system, 'yz', 'tipA', 'tipB')
+    system.q = {'a1': 0.4, 'a2': 0.9, 'b1': -0.3}
+    system.satisfy_constraints()
+    return system
+
+
+def ref_loop3d():
+    """Spatial loop (joints about all three axes) closed by a PointToPoint3D."""
+    system = trep.System()
+    system.import_frames([
+        rz('a1'), [ry('a2'), [tx(1.0, mass=1.0), [rx('a3'), [tz(-0.8, name='tipA', mass=0.6)]]]],
+        tx(1.2), [ry('b1'), [rz('b2'), [ty(0.9, mass=0.8), [rx('b3'), [tz(-0.5, name='tipB', mass=0.4)]]]]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.1)
+    trep.constraints.PointToPoint3D(system, 'tipA', 'tipB')
+    system.q = {'a1': 0.3, 'a2': -0.2, 'a3': 0.5, 'b1': 0.4, 'b2': 0.8, 'b3': -0.6}
+    system.satisfy_constraints()
+    return system
+
+
+def ref_rod():
+    """Two pendulums joined by a rigid rod: Distance with a FIXED length (constraints/distance.c:16-136,
+    the config == NULL branch); the second pivot rides on a kinematic slide."""
+    system = trep.System()
+    system.import_frames([
+        rx('th1'), [tz(-1.0, name='m1', mass=1.0)],
+        tx('slide', kinematic=True), [ty(1.0), [ry('th2'), [rz('th3'), [tz(-1.5, name='m2', mass=2.0)]]]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.02)
+    trep.constraints.Distance(system, 'm1', 'm2', 1.25)
+    system.q = {'th1': 0.3, 'th2': 0.2, 'th3': -0.1}
+    system.satisfy_constraints()
+    return system
+
+
+def ref_damper_only():
+    """examples/dual_pendulums.py without the LinearSpring (whose missing C V_dqdqdq stops the reference's
+    _calc_deriv2): the LinearDamper's second derivatives (forces/lineardamper.c:60-107) are reachable."""
+    system = trep.System()
+    system.import_frames([
+        rx('theta1'), [tz(2, mass=1, name='pend1')],
+        ty(1), [rx('theta2'), [tz(2, mass=1, name='pend2')]]])
+    trep.forces.LinearDamper(system, 'pend1', 'pend2', c=1)
+    trep.potentials.Gravity(system, name="Gravity")
+    system.q = [3, -3]
+    return system
+
+
 def ref_puppet():
     puppet = trep.puppets.Puppet(joint_forces=False, string_forces=False, string_constraints=True)
     puppet.q = {
@@ -171,6 +228,7 @@ REF_BUILDERS = {
     "pend_on_cart2": lambda: ref_pend_on_cart(True), "dual_pendulums": ref_dual_pendulums,
     "tase_pendulum": ref_tase_pendulum, "puppet": ref_puppet,
     "pccd": ref_pccd, "wrench_arm": ref_wrench_arm, "spline_pendulum": ref_spline_pendulum,
+    "fourbar": ref_fourbar, "loop3d": ref_loop3d, "rod": ref_rod, "damper_only": ref_damper_only,
 }
 
 

@@ -255,8 +255,7 @@ def test_golden_second_derivatives(lib, name):
                        t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
         assert np.all(out["status"] == 0)
         G.assert_close(out["A"], g["case_A"], "%s[%s] A" % (name, label))
-        for n in s.d2_shapes(1):
-            G.assert_close(out[n], g["case_" + n], "%s[%s] %s" % (name, label, n))
+        G.assert_d2_close(out, g, "%s[%s]" % (name, label))
 
 
 def test_puppet_second_derivatives(lib):
@@ -273,8 +272,7 @@ def test_puppet_second_derivatives(lib):
         out = s.deriv2(g["case_q1"][sl], g["case_p1"][sl], None, g["case_k2"][sl], t1=g["case_t1"][sl],
                        t2=g["case_t2"][sl], q2_guess=g["case_q2_guess"][sl], lambda_guess=g["case_lambda_guess"][sl])
         assert out["status"][0] == 0
-        for n in s.d2_shapes(1):
-            G.assert_close(out[n], g2["case_" + n], "puppet[coop=%s pairwise=%s] %s" % (coop, pairwise, n))
+        G.assert_d2_close(out, g2, "puppet[coop=%s pairwise=%s]" % (coop, pairwise))
 
 
 def test_puppet_second_derivative_schemes_agree_on_a_ragged_batch(lib):
@@ -573,8 +571,7 @@ def test_extra_plugin_kinds_second_derivatives(lib, name, pairwise):
         out = s.deriv2(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"],
                        t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"])
         assert np.all(out["status"] == 0)
-        for n in s.d2_shapes(1):
-            G.assert_close(out[n], g["case_" + n], "%s[pairwise=%s spec=%s] %s" % (name, pairwise, spec, n))
+        G.assert_d2_close(out, g, "%s[pairwise=%s spec=%s]" % (name, pairwise, spec))
 
 
 def test_pccd_rollout(lib):

@@ -9,7 +9,7 @@ import golden_util as G
 import hostmath as H
 
 
-@pytest.mark.parametrize("name", G.ALL + G.EXTRA)
+@pytest.mark.parametrize("name", G.ALL + G.EXTRA + G.PARITY)
 def test_cases_step_and_deriv1(name):
     g = G.golden(name)
     d = G.desc(name)
@@ -28,7 +28,7 @@ def test_cases_step_and_deriv1(name):
     assert flips == 0, "Newton iteration counts differ from the reference in %d cases" % flips
 
 
-@pytest.mark.parametrize("name", G.ALL + ["pccd"])
+@pytest.mark.parametrize("name", G.ALL + ["pccd"] + G.PARITY)
 def test_cooperative_math_cases(name):
     """The team-cooperative formulation (link tables, world-coordinate spatial algebra,
     right-looking LU; trepb_coop_math.cuh) run with a one-lane host team against the goldens."""
@@ -136,7 +136,7 @@ def test_puppet_rollout():
     assert iters == int(g["roll_iters"].sum())
 
 
-D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"] + G.EXTRA_D2
+D2_SYSTEMS = ["tase_pendulum", "pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_cart2"] + G.EXTRA_D2 + G.PARITY
 
 
 @pytest.mark.parametrize("method", ["pair", "jac"])
@@ -152,10 +152,10 @@ def test_second_derivatives(name, method):
                        g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
                        lam_guess=g["case_lambda_guess"][c], method=method)
         assert out["rc"] == 0
-        for w in H.D2_WHICH:
-            for kd in H.D2_KINDS:
-                n = w + "_" + kd
-                G.assert_close(out[n], g["case_" + n][c], "%s case %d %s" % (name, c, n))
+        # damper_only: the reference's LinearDamper f_ddqdq has a typo (forces/lineardamper.c:99); the tensors are
+        # compared with the reference built with that one line corrected (casefix_*, oracle/gen_golden_r2.py)
+        G.assert_d2_close(out, g, "%s case %d" % (name, c), index=c,
+                          gold_prefix="casefix_" if name == "damper_only" else "case_")
 
 
 @pytest.mark.parametrize("method", ["pair", "jac"])
@@ -169,10 +169,7 @@ def test_puppet_second_derivatives(method):
                    g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
                    lam_guess=g["case_lambda_guess"][c], method=method)
     assert out["rc"] == 0
-    for w in H.D2_WHICH:
-        for kd in H.D2_KINDS:
-            n = w + "_" + kd
-            G.assert_close(out[n], g2["case_" + n][0], "puppet " + n)
+    G.assert_d2_close(out, g2, "puppet", index=0)
 
 
 def test_division_by_the_time_step_is_exact():

@@ -136,6 +136,58 @@ def wrench_arm() -> M.System:
     return s
 
 
+def fourbar() -> M.System:
+    """Planar loop closed by a PointToPoint2D = two PointToPoint1D (trep/constraints/point.py,
+    trep/_trep/constraints/point.c:16-55), one torque input.  nd 3, nu 1, nc 2."""
+    s = M.System(name="fourbar")
+    s.import_frames([
+        M.rx("a1"), [M.tz(-1.0, mass=1.0, name="A1"), [M.rx("a2"), [M.tz(-1.2, name="tipA", mass=0.7)]]],
+        M.ty(1.5), [M.rx("b1"), [M.tz(-1.4, name="tipB", mass=1.3)]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.05)
+    M.ConfigForce(s, "a1", "torque")
+    M.PointToPoint2D(s, "yz", "tipA", "tipB")
+    return s
+
+
+def loop3d() -> M.System:
+    """Spatial loop (joints about all three axes) closed by a PointToPoint3D.  nd 6, nc 3."""
+    s = M.System(name="loop3d")
+    s.import_frames([
+        M.rz("a1"), [M.ry("a2"), [M.tx(1.0, mass=1.0), [M.rx("a3"), [M.tz(-0.8, name="tipA", mass=0.6)]]]],
+        M.tx(1.2), [M.ry("b1"), [M.rz("b2"), [M.ty(0.9, mass=0.8), [M.rx("b3"), [M.tz(-0.5, name="tipB", mass=0.4)]]]]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.1)
+    M.PointToPoint3D(s, "tipA", "tipB")
+    return s
+
+
+def rod() -> M.System:
+    """Two pendulums joined by a rigid rod: Distance with a fixed length (trep/constraints/distance.py,
+    trep/_trep/constraints/distance.c:16-136 with config == NULL); the second pivot rides on a kinematic
+    slide.  nd 3, nk 1, nc 1."""
+    s = M.System(name="rod")
+    s.import_frames([
+        M.rx("th1"), [M.tz(-1.0, name="m1", mass=1.0)],
+        M.tx("slide", kinematic=True), [M.ty(1.0), [M.ry("th2"), [M.rz("th3"), [M.tz(-1.5, name="m2", mass=2.0)]]]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.02)
+    M.Distance(s, "m1", "m2", 1.25)
+    return s
+
+
+def damper_only() -> M.System:
+    """examples/dual_pendulums.py without the LinearSpring: the one system on which the reference's
+    _calc_deriv2 reaches the LinearDamper second derivatives (forces/lineardamper.c:60-107)."""
+    s = M.System(name="damper_only")
+    s.import_frames([
+        M.rx("theta1"), [M.tz(2, mass=1, name="pend1")],
+        M.ty(1), [M.rx("theta2"), [M.tz(2, mass=1, name="pend2")]]])
+    M.LinearDamper(s, "pend1", "pend2", c=1)
+    M.Gravity(s, name="Gravity")
+    return s
+
+
 SPLINE_DATA = [(-2.0, -3.0), (-0.5, -0.4, 1.0), (0.0, 0.0), (0.7, 0.9), (2.0, 1.5, 0.2)]
 
 
@@ -172,7 +224,8 @@ def named_desc(name) -> SystemDesc:
         "damped_pendulum": damped_pendulum, "pend_on_cart1": lambda: pend_on_cart(False),
         "pend_on_cart2": lambda: pend_on_cart(True), "dual_pendulums": dual_pendulums,
         "tase_pendulum": tase_pendulum, "pccd": pccd, "wrench_arm": wrench_arm,
-        "spline_pendulum": spline_pendulum,
+        "spline_pendulum": spline_pendulum, "fourbar": fourbar, "loop3d": loop3d, "rod": rod,
+        "damper_only": damper_only,
     }
     return table[name]().describe()
 
@@ -181,3 +234,6 @@ NAMED = ["pendulum1", "pendulum5", "damped_pendulum", "pend_on_cart1", "pend_on_
          "dual_pendulums", "tase_pendulum", "puppet"]
 # systems exercising the plugin kinds beyond BASELINE.json's configs
 EXTRA = ["pccd", "wrench_arm", "spline_pendulum"]
+# parity systems for the constraint / force kinds of SURVEY 8a rows a7, a9 that BASELINE.json's configs do not
+# exercise: PointToPoint1D/2D/3D, fixed-length Distance, LinearDamper second derivatives
+PARITY = ["fourbar", "loop3d", "rod", "damper_only"]
