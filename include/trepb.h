@@ -36,6 +36,14 @@
  *
  * `_dev` entry points take DEVICE pointers (inputs already resident in HBM) and enqueue on
  * `stream` (a cudaStream_t passed as void*; NULL = default stream) without synchronizing.
+ * One handle may be used from several host threads and on several streams: launches that need
+ * scratch memory owned by the handle (the table-driven thread kernels' workspace slab, the
+ * second-derivative passes) are ordered on the device behind the previous such launch, whatever
+ * stream that one used; the specialised and the cooperative step / linearize / project kernels own
+ * no scratch and overlap freely.  trepb_last_kernel_ms refers to the handle's most recent launch.
+ * After a failed step of a rollout (status != 0) the `_dev` entry points leave the rows of X / U /
+ * traj_q / traj_p past the failure untouched (the caller's memory); the host-pointer entry points
+ * return zeros there.
  * The un-suffixed entry points take HOST pointers, copy in, run, copy out and synchronize.
  *
  * Every function returns 0 on success, non-zero on failure; trepb_last_error() describes

@@ -105,8 +105,9 @@ def test_lineardamper_second_derivative_deviation_is_the_reference_typo(lib):
     """forces/lineardamper.c:99 reads TapeMeasure_length_dq(q2) where d/dq2 of (dv/ddq1 * dx/dq) needs
     length_dqdq(q, q2) (its own f_dqdq at :79 has it right).  Decision: the library
     computes the correct derivative.  This pins the decision: equal to the corrected reference to 1e-10,
-    and NOT equal to the stock one - the tensors where the typo acts differ by O(1) of their scale, and the
-    ones it cannot reach (anything purely in p1) still agree."""
+    and NOT equal to the stock one (measured on B200: q2/p2_dq1dq1 differ by 1.3 % of their largest entry,
+    the dq1dp1 and dp1dp1 tensors by 104-106 %: every pair of parameters moves both the midpoint configuration
+    and velocity, so f_ddqdq enters all of them).  First derivatives are untouched by the typo."""
     g = G.golden("damper_only")
     s = lib.System(G.desc("damper_only"))
     out = s.deriv2(g["case_q1"], g["case_p1"], t1=g["case_t1"], t2=g["case_t2"], q2_guess=g["case_q2_guess"])
@@ -114,8 +115,7 @@ def test_lineardamper_second_derivative_deviation_is_the_reference_typo(lib):
     dev = {n: float(np.max(np.abs(out[n] - g["case_" + n])) / np.max(np.abs(g["case_" + n])))
            for n in ("q2_dq1dq1", "p2_dq1dq1", "q2_dq1dp1", "p2_dq1dp1", "q2_dp1dp1", "p2_dp1dp1")}
     print("relative deviation from the stock reference:", dev)
-    assert dev["q2_dq1dq1"] > 1e-3 and dev["p2_dq1dq1"] > 1e-3
-    # first derivatives are untouched by the typo
+    assert all(v > 1e-3 for v in dev.values()), dev
     lin = s.linearize(g["case_q1"], g["case_p1"], t1=g["case_t1"], t2=g["case_t2"], q2_guess=g["case_q2_guess"])
     G.assert_close(lin["A"], g["case_A"], "damper_only A")
 
@@ -213,4 +213,7 @@ def test_iteration_count_flip_fraction_at_1e7_steps(lib, cb, name):
     assert np.median(err) <= 1e-12
     assert np.quantile(err, 0.999) <= (1e-10 if name == "damped_pendulum" else 1e-7)
     if (diff > 0).any():
-        assert err[diff > 0].max() <= max(1e-10, np.quantile(err, 0.999))
+        # a rollout whose count differs took one Newton iteration more or less at some step: both iterates
+        # satisfy the 1e-10 residual tolerance, they differ by about that much, and the remaining steps of the
+        # rollout carry (and for the dual pendulums amplify) the difference
+        assert err[diff > 0].max() <= 1e-8

@@ -103,6 +103,11 @@ struct trepb_system {
     DevBuf hb[72];
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
+    // Scratch owned by the handle (the workspace slab of the table-driven thread kernels, the
+    // second-derivative scratch) is shared by every launch: a launch that uses it waits, on the device,
+    // for the previous such launch - whatever stream that one went to (ScratchGuard).
+    cudaEvent_t ev_scratch = nullptr;
+    bool scratch_busy = false;
     std::mutex mu;       // serialises launches on this handle
     std::mutex mu_host;  // serialises the host-pointer entry points (they share staging buffers)
 };
@@ -235,6 +240,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     }
     CUS(cudaEventCreate(&s->ev0));
     CUS(cudaEventCreate(&s->ev1));
+    CUS(cudaEventCreateWithFlags(&s->ev_scratch, cudaEventDisableTiming));
 #undef CUS
     *out = s;
     return TREPB_OK;
@@ -253,6 +259,7 @@ void trepb_system_destroy(trepb_system* s) {
     for (auto& b : s->hb) b.release();
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
+    if (s->ev_scratch) cudaEventDestroy(s->ev_scratch);
     delete s;
 }
 
@@ -361,6 +368,18 @@ void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch
     c->lay = s->clay;
 }
 
+// Orders launches that use the handle's scratch across streams: wait for the previous user before the
+// launch, mark the end of this one after it.  The caller holds s->mu.
+struct ScratchGuard {
+    trepb_system* s;
+    cudaStream_t st;
+    bool on;
+    ScratchGuard(trepb_system* s_, cudaStream_t st_, bool on_) : s(s_), st(st_), on(on_) {
+        if (on && s->scratch_busy) cudaStreamWaitEvent(st, s->ev_scratch, 0);
+    }
+    ~ScratchGuard() { if (on) { cudaEventRecord(s->ev_scratch, st); s->scratch_busy = true; } }
+};
+
 struct Timed {
     trepb_system* s;
     cudaStream_t st;
@@ -400,6 +419,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
         return TREPB_OK;
     }
     LaunchCfg c;
+    ScratchGuard sg(s, (cudaStream_t)stream, !s->ks->specialized);
     int rc = make_cfg(s, 0, a->batch, s->bps[0], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
@@ -431,6 +451,7 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
         return TREPB_OK;
     }
     LaunchCfg c;
+    ScratchGuard sg(s, (cudaStream_t)stream, !s->ks->specialized);
     int rc = make_cfg(s, 3, a->batch, s->bps[3], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
@@ -455,6 +476,7 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
         return TREPB_OK;
     }
     LaunchCfg c;
+    ScratchGuard sg(s, (cudaStream_t)stream, !s->ks->specialized);
     int rc = make_cfg(s, 1, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
@@ -499,6 +521,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
     const bool stage = s->lin_stage_bytes > 0 && (p.A || p.B);
     p.stage = stage ? 1 : 0;
     LaunchCfg c;
+    ScratchGuard sg(s, stream, !s->ks->specialized);
     const size_t smem = s->ks->specialized ? (stage ? s->lin_stage_bytes : 0) : (size_t)s->blob_bytes;
     int rc = make_cfg(s, 2, a->batch, stage ? s->lin_bps_staged : s->bps[2], smem, stream, &c);
     if (rc) return rc;
@@ -531,6 +554,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
     cudaStream_t stream = (cudaStream_t)stream_;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->device));
+    ScratchGuard sg(s, stream, true);   // covers the linearize launch below and both second-derivative passes
     // deriv1 products this kernel consumes: use the caller's arrays where given, scratch otherwise
     trepb_lin_args la = a->lin;
     const size_t cnt[4] = {(size_t)nq, (size_t)nd, (size_t)nu, (size_t)nk};
@@ -716,6 +740,9 @@ struct Stager {
         DevBuf& b = s->hb[k++];
         const size_t bytes = count * sizeof(T);
         cudaError_t e = b.ensure(bytes ? bytes : 8);
+        // the staging buffers are reused between calls: clear, so that what a kernel does not write (the rows
+        // after a failed step of a rollout) reads as zeros, not as an earlier call's data
+        if (e == cudaSuccess && bytes) e = cudaMemsetAsync(b.p, 0, bytes, 0);
         if (e != cudaSuccess) { err = cuda_fail(e, "staging host output"); return nullptr; }
         outs[nout++] = {host, b.p, bytes};
         return (T*)b.p;

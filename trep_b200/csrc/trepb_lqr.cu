@@ -315,6 +315,7 @@ extern "C" int trepb_lq_batch(int device, const trepb_lq_args* a) {
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
     if (!a->A || !a->B || !a->Q || !a->R || !a->q || !a->r || !a->Kfb || !a->C || !a->status)
         return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, q, r, Kfb, C and status are required");
+    if (a->batch == 0) return TREPB_OK;
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     const size_t Rn = (size_t)a->batch, K = (size_t)a->nsteps, nX = (size_t)a->nX, nU = (size_t)a->nU;
@@ -352,6 +353,8 @@ extern "C" int trepb_lq_batch(int device, const trepb_lq_args* a) {
 extern "C" int trepb_lqr_batch(int device, const trepb_lqr_args* a) {
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
+    if (a->batch == 0) return TREPB_OK;
+    if (!a->A || !a->B || !a->Q || !a->R || !a->Kfb || !a->status) return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, Kfb and status are required");
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     const size_t R = (size_t)a->batch, K = (size_t)a->nsteps, nX = (size_t)a->nX, nU = (size_t)a->nU;

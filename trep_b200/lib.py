@@ -467,6 +467,8 @@ class System:
         q1, p1 = self._f(q1, (B, self.nq)), self._f(p1, (B, self.nd))
         u1 = None if (u1 is None or self.nu == 0) else self._f(u1, (B, nsteps, self.nu))
         if self.nk:
+            if k2 is None:
+                raise ValueError("k2 [B][nsteps][nk] is required: the system has %d kinematic configs" % self.nk)
             k2 = self._f(k2, (B, nsteps, self.nk))
         else:
             k2 = None
