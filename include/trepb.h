@@ -59,7 +59,8 @@
 extern "C" {
 #endif
 
-#define TREPB_ABI_VERSION 1
+#define TREPB_ABI_VERSION 2   /* 2: times[] in step / project args, traj_len in lin args, calc_f / discrete_fm2,
+                                   trepb_comm_* / trepb_ipc_* (appended fields and new entry points only) */
 
 /* error codes */
 #define TREPB_OK 0
@@ -188,6 +189,10 @@ typedef struct trepb_step_args {
     int32_t _pad;
     double* traj_q;      /* [B][nsteps/sample_every][nq] */
     double* traj_p;      /* [B][nsteps/sample_every][nd] */
+    /* optional time grid shared by the batch: step s runs from times[s] to times[s+1] (the reference steps
+     * on arbitrary self._time[k], trep/discopt/dsystem.py:229-250, 426-457); NULL: t0 + s dt accumulated
+     * as t2 = t1 + dt.  Device pointer for the _dev entry point. */
+    const double* times; /* [nsteps+1] or NULL */
 } trepb_step_args;
 
 int trepb_step_batch(trepb_system* sys, const trepb_step_args* args);                   /* host pointers   */
@@ -216,6 +221,7 @@ typedef struct trepb_project_args {
     int32_t* status;        /* [B] 0 ok, -1 not converged, -2 singular                          */
     int32_t* fail_step;     /* [B] first failed step (K if none): armijo_simulate returns the
                                partial trajectory X[:k], U[:k]; may be NULL                     */
+    const double* times;    /* [K+1] time grid shared by the batch (DSystem.time), or NULL: t0 + k dt */
 } trepb_project_args;
 
 int trepb_project_batch(trepb_system* sys, const trepb_project_args* args);
@@ -283,13 +289,34 @@ int trepb_calc_p2_batch(trepb_system* sys, int64_t batch, double dt,
 int trepb_calc_p2_batch_dev(trepb_system* sys, int64_t batch, double dt,
                             const double* q0, const double* q1, double* p, void* stream);
 
+/* Residual of the DEL equation at given (q1, q2, p1, u1, lambda1): _MidpointVI._calc_f == MidpointVI_calc_f
+ * (trep/_trep/midpointvi.c:533-575):  f[0:nd] = p1 + D1L2 + fm2 - Dh(q1)^T lambda1,  f[nd:nd+nc] = h(q2).
+ * q1, q2: [B][nq]; p1: [B][nd]; u1: [B][nu] or NULL (zeros); lambda1: [B][nc] or NULL (zeros); f: [B][nd+nc]. */
+int trepb_calc_f_batch(trepb_system* sys, int64_t batch, double t1, double t2, const double* q1, const double* q2,
+                       const double* p1, const double* u1, const double* lambda1, double* f);
+int trepb_calc_f_batch_dev(trepb_system* sys, int64_t batch, double t1, double t2, const double* q1, const double* q2,
+                           const double* p1, const double* u1, const double* lambda1, double* f, void* stream);
+/* Discrete forcing fm2 = (t2 - t1) F(q_mid, dq, u1) on the dynamic configs: _MidpointVI.discrete_fm2
+ * (trep/_trep/midpointvi.c:474-478, 2710-2727).  fm2: [B][nd]. */
+int trepb_discrete_fm2_batch(trepb_system* sys, int64_t batch, double t1, double t2, const double* q1,
+                             const double* q2, const double* u1, double* fm2);
+int trepb_discrete_fm2_batch_dev(trepb_system* sys, int64_t batch, double t1, double t2, const double* q1,
+                                 const double* q2, const double* u1, double* fm2, void* stream);
+
 /* One linearization per instance: solve the step from (q1,p1,u1,k2[,guess]) then first
  * derivatives.  A: [B][nX][nX], B: [B][nX][nU] with nX = 2*nq, nU = nu+nk (DSystem layout).
  * Raw first-derivative arrays in the reference's storage layout [wrt][out] are optional. */
 typedef struct trepb_lin_args {
     int64_t batch;
     int32_t max_iterations;
-    int32_t _pad;
+    /* 0: instance b reads row b of every input array.  L >= 2: the STATE inputs (q1, p1, q2_guess) are
+     * trajectories of L rows, [R][L][..] - DSystem's X, or the trajectory capture of trepb_step_batch - and
+     * instance b = r (L-1) + k linearizes step k -> k+1 of trajectory r: it reads state row r L + k (pass
+     * q2_guess = q1 + nq to use X[k+1] as the Newton start, DSystem.linearize_trajectory's xk_hint).  The
+     * per-STEP inputs (u1, k2, t1, t2, lambda_guess) and every output are packed [R][L-1] (row b), the shape
+     * of DSystem's U and of linearize_trajectory's A[k], B[k] (trep/discopt/dsystem.py:406-423).  The junk
+     * instance that would pair the last state of one trajectory with the first of the next does not exist. */
+    int32_t traj_len;
     double  tolerance;
     const double* t1;    /* [B] or NULL -> use t1_scalar */
     const double* t2;    /* [B] or NULL -> use t1_scalar + dt_scalar */
@@ -333,6 +360,42 @@ typedef struct trepb_d2_args {
 int trepb_deriv2_batch(trepb_system* sys, const trepb_d2_args* args);
 int trepb_deriv2_batch_dev(trepb_system* sys, const trepb_d2_args* args, void* stream);
 
+/* ---- multi-GPU: one process per GPU ---------------------------------------------------------
+ * Instances are independent, so a batch shards over ranks with no exchange during compute (each
+ * rank calls the entry points above on its own contiguous block).  The one exchange of the path is
+ * collecting the A / B slabs of DSystem.linearize_trajectory (trep/discopt/dsystem.py:406-423) where
+ * the sequential Riccati sweep runs (trep/discopt/dlqr.py:9-81).  Device to device over NVLink, two ways:
+ *   (1) NCCL on slabs already in local HBM: trepb_comm_allgather_dev (ncclAllGather) or
+ *       trepb_comm_gather_dev (grouped ncclSend / ncclRecv to `root`).  NCCL is loaded at run time
+ *       (libnccl.so.2: the copy already in the process, else the system one; TREPB_NCCL_LIB overrides).
+ *   (2) fused into the linearize kernel: the root exports its slab (trepb_ipc_export), every rank maps
+ *       it (trepb_ipc_open) and passes mapped + rank offset as the A / B pointers of
+ *       trepb_linearize_batch_dev: the kernel's own stores land in the root's HBM, no second pass.
+ * The 128-byte id of trepb_comm_unique_id (rank 0) and the 64-byte IPC handles travel between the
+ * processes by the host's own means (trep_b200/dist.py: a TCP rendezvous on MASTER_ADDR/MASTER_PORT). */
+#define TREPB_COMM_ID_BYTES 128
+#define TREPB_IPC_HANDLE_BYTES 64
+typedef struct trepb_comm trepb_comm; /* opaque */
+int  trepb_comm_available(int* nccl_version);            /* 0 if NCCL could be loaded */
+int  trepb_comm_unique_id(char* id);                     /* id[TREPB_COMM_ID_BYTES], call on one rank */
+int  trepb_comm_create(int device, int rank, int nranks, const char* id, trepb_comm** out);  /* collective */
+void trepb_comm_destroy(trepb_comm* comm);
+int  trepb_comm_rank(const trepb_comm* comm, int* rank, int* nranks);
+/* recv: [nranks][bytes_per_rank] on every rank (allgather) / on `root` (gather; may be NULL elsewhere);
+ * device pointers, enqueued on `stream`, no synchronization. */
+int  trepb_comm_allgather_dev(trepb_comm* comm, const void* send, void* recv, int64_t bytes_per_rank, void* stream);
+int  trepb_comm_gather_dev(trepb_comm* comm, const void* send, void* recv, int64_t bytes_per_rank, int root, void* stream);
+/* ptr: the BASE of an allocation made by trepb_malloc (cudaMalloc); handle[TREPB_IPC_HANDLE_BYTES]. */
+int  trepb_ipc_export(int device, const void* ptr, char* handle);
+int  trepb_ipc_open(int device, const char* handle, void** ptr);    /* in ANOTHER process than the exporter */
+int  trepb_ipc_close(int device, void* ptr);
+/* CUDA-event timing for hosts without a CUDA binding of their own: record(pair, 0 | 1, stream), then
+ * elapsed_ms synchronizes on the second event. */
+int  trepb_event_pair_create(int device, void** pair);
+int  trepb_event_record(void* pair, int which, void* stream);
+int  trepb_event_elapsed_ms(void* pair, float* ms);
+void trepb_event_pair_destroy(void* pair);
+
 /* Device utilities so that a C host (no torch) can own HBM buffers. */
 int trepb_device_count(int* n);
 int trepb_malloc(int device, int64_t bytes, void** ptr);
@@ -342,6 +405,7 @@ int trepb_host_free(void* ptr);
 int trepb_memset(int device, void* dst, int value, int64_t bytes);
 int trepb_memcpy_h2d(int device, void* dst, const void* src, int64_t bytes);
 int trepb_memcpy_d2h(int device, void* dst, const void* src, int64_t bytes);
+int trepb_memcpy_d2d(int device, void* dst, const void* src, int64_t bytes);   /* also peer-mapped addresses */
 int trepb_synchronize(int device);
 /* Time of the most recent kernel launched by a *_dev / host entry point on this system, in
  * milliseconds, measured with CUDA events on the launching stream (valid after a sync). */

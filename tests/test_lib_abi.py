@@ -27,15 +27,15 @@ def test_every_declared_symbol_is_exported():
     missing = [s for s in syms if not hasattr(raw, s)]
     assert not missing, missing
     assert set(lib.EXPORTS) == set(syms)
-    assert raw.trepb_abi_version() == 1
+    assert raw.trepb_abi_version() == 2
 
 
 def test_ctypes_struct_layout_matches_header():
     # field order/size of the argument structs as declared in include/trepb.h (LP64)
-    assert C.sizeof(lib.StepArgs) == 8 + 4 + 4 + 3 * 8 + 11 * 8 + 4 + 4 + 2 * 8
+    assert C.sizeof(lib.StepArgs) == 8 + 4 + 4 + 3 * 8 + 11 * 8 + 4 + 4 + 2 * 8 + 8
     assert C.sizeof(lib.LinArgs) == 8 + 4 + 4 + 8 + 2 * 8 + 2 * 8 + 6 * 8 + 5 * 8 + 2 * 8 + 12 * 8
     assert C.sizeof(lib.LqrArgs) == 8 + 6 * 4 + 7 * 8
-    assert C.sizeof(lib.ProjectArgs) == 8 + 4 + 4 + 3 * 8 + 3 * 8 + 4 + 4 + 5 * 8
+    assert C.sizeof(lib.ProjectArgs) == 8 + 4 + 4 + 3 * 8 + 3 * 8 + 4 + 4 + 5 * 8 + 8
     assert C.sizeof(D.CSysDesc) == 10 * 4 + 17 * 8
 
 

@@ -397,7 +397,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
     if (!a->q1 || !a->p1 || !a->q2 || !a->p2 || !a->status) return fail(TREPB_ERR_INVALID, "q1, p1, q2, p2 and status are required");
     if (ps.nk > 0 && !a->k2) return fail(TREPB_ERR_INVALID, "k2 is required for a system with kinematic configs");
-    if (!(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    if (!a->times && !(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
     if (a->sample_every < 0) return fail(TREPB_ERR_INVALID, "sample_every must be >= 0");
     if (a->batch == 0) return TREPB_OK;
     std::lock_guard<std::mutex> lk(s->mu);
@@ -411,6 +411,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     p.sample_every = a->sample_every;
     p.nsamples = a->sample_every > 0 ? a->nsteps / a->sample_every : 0;
     p.traj_q = a->traj_q; p.traj_p = a->traj_p;
+    p.times = a->times;
     if (s->coop) {
         CoopLaunch cl;
         make_coop(s, a->batch, (cudaStream_t)stream, &cl);
@@ -432,7 +433,7 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
     if (!a->bX || !a->bU || !a->Kfb || !a->X || !a->U || !a->status)
         return fail(TREPB_ERR_INVALID, "bX, bU, Kfb, X, U and status are required");
-    if (!(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    if (!a->times && !(a->dt != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
     const RtSys& ps = s->P.proto;
     if (ps.nu + ps.nk == 0) return fail(TREPB_ERR_INVALID, "the system has no inputs to feed back");
     if (a->batch == 0) return TREPB_OK;
@@ -443,6 +444,7 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     p.t0 = a->t0; p.dt = a->dt; p.tol = a->tolerance; p.tolT = sqrt_threshold(a->tolerance);
     p.bX = a->bX; p.bU = a->bU; p.K = a->Kfb; p.k_per_instance = a->k_per_instance; p.use_hint = a->use_hint;
     p.X = a->X; p.U = a->U; p.iters = a->iters; p.status = a->status; p.fail_step = a->fail_step;
+    p.times = a->times;
     if (s->coop) {
         CoopLaunch cl;
         make_coop(s, a->batch, (cudaStream_t)stream, &cl);
@@ -459,29 +461,60 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     return TREPB_OK;
 }
 
-int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1,
-                            double* pout, void* stream) {
-    if (!s || !q0 || !q1 || !pout) return fail(TREPB_ERR_INVALID, "null argument");
-    if (batch < 0 || !(dt != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or dt");
-    if (batch == 0) return TREPB_OK;
+}  // extern "C"
+
+namespace {
+// calc_p2 / calc_f / discrete_fm2 share one kernel (P2Params::mode); the caller has validated the pointers
+int eval_launch(trepb_system* s, const P2Params& p, void* stream) {
+    if (p.batch == 0) return TREPB_OK;
     std::lock_guard<std::mutex> lk(s->mu);
     CU(cudaSetDevice(s->device));
-    P2Params p;
-    p.batch = batch; p.dt = dt; p.q0 = q0; p.q1 = q1; p.p = pout;
     if (s->coop) {
         CoopLaunch cl;
-        make_coop(s, batch, (cudaStream_t)stream, &cl);
+        make_coop(s, p.batch, (cudaStream_t)stream, &cl);
         Timed t(s, cl.stream);
         CU(s->cks->p2(cl, p));
         return TREPB_OK;
     }
     LaunchCfg c;
     ScratchGuard sg(s, (cudaStream_t)stream, !s->ks->specialized);
-    int rc = make_cfg(s, 1, batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
+    int rc = make_cfg(s, 1, p.batch, s->bps[1], s->ks->specialized ? 0 : (size_t)s->blob_bytes, (cudaStream_t)stream, &c);
     if (rc) return rc;
     Timed t(s, c.stream);
     CU(s->ks->p2(c, p));
     return TREPB_OK;
+}
+}  // namespace
+
+extern "C" {
+
+int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1,
+                            double* pout, void* stream) {
+    if (!s || !q0 || !q1 || !pout) return fail(TREPB_ERR_INVALID, "null argument");
+    if (batch < 0 || !(dt != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or dt");
+    P2Params p{};
+    p.batch = batch; p.dt = dt; p.q0 = q0; p.q1 = q1; p.p = pout; p.mode = 0;
+    return eval_launch(s, p, stream);
+}
+
+int trepb_calc_f_batch_dev(trepb_system* s, int64_t batch, double t1, double t2, const double* q1, const double* q2,
+                           const double* p1, const double* u1, const double* lambda1, double* f, void* stream) {
+    if (!s || !q1 || !q2 || !p1 || !f) return fail(TREPB_ERR_INVALID, "null argument");
+    if (batch < 0 || !(t2 - t1 != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or t2 == t1");
+    P2Params p{};
+    p.batch = batch; p.dt = t2 - t1; p.q0 = q1; p.q1 = q2; p.p = f; p.mode = 1;
+    p.p1 = p1; p.u1 = s->P.proto.nu ? u1 : nullptr; p.lam = s->P.proto.nc ? lambda1 : nullptr;
+    return eval_launch(s, p, stream);
+}
+
+int trepb_discrete_fm2_batch_dev(trepb_system* s, int64_t batch, double t1, double t2, const double* q1,
+                                 const double* q2, const double* u1, double* fm2, void* stream) {
+    if (!s || !q1 || !q2 || !fm2) return fail(TREPB_ERR_INVALID, "null argument");
+    if (batch < 0 || !(t2 - t1 != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or t2 == t1");
+    P2Params p{};
+    p.batch = batch; p.dt = t2 - t1; p.q0 = q1; p.q1 = q2; p.p = fm2; p.mode = 2;
+    p.u1 = s->P.proto.nu ? u1 : nullptr;
+    return eval_launch(s, p, stream);
 }
 
 }  // extern "C"
@@ -495,6 +528,8 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
     if (ps.nk > 0 && !a->k2) return fail(TREPB_ERR_INVALID, "k2 is required for a system with kinematic configs");
     if (ps.nu > 0 && !a->u1) return fail(TREPB_ERR_INVALID, "u1 is required for a system with inputs");
     if (!a->t2 && !(a->dt_scalar != 0.0)) return fail(TREPB_ERR_INVALID, "dt must be non-zero");
+    if (a->traj_len < 0 || a->traj_len == 1 || (a->traj_len > 1 && a->batch % (a->traj_len - 1) != 0))
+        return fail(TREPB_ERR_INVALID, "traj_len must be 0 or >= 2 with batch a multiple of traj_len - 1");
     if (a->batch == 0) return TREPB_OK;
     CU(cudaSetDevice(s->device));
     LinParams p;
@@ -508,6 +543,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
                        a->l1_dq1, a->l1_dp1, a->l1_du1, a->l1_dk2};
     for (int i = 0; i < 12; ++i) p.raw[i] = raw[i];
     p.aux = aux; p.aux_size = aux_size;
+    p.traj_len = a->traj_len;
     if (s->coop) {
         p.stage = 0;
         CoopLaunch cl;
@@ -702,6 +738,11 @@ int trepb_memcpy_d2h(int device, void* dst, const void* src, int64_t bytes) {
     CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost));
     return TREPB_OK;
 }
+int trepb_memcpy_d2d(int device, void* dst, const void* src, int64_t bytes) {
+    CU(cudaSetDevice(device));
+    CU(cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToDevice));
+    return TREPB_OK;
+}
 int trepb_memset(int device, void* dst, int value, int64_t bytes) {
     CU(cudaSetDevice(device));
     CU(cudaMemset(dst, value, (size_t)bytes));
@@ -774,6 +815,7 @@ int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
     d.iters = st.out(a->iters, B); d.status = st.out(a->status, B);
     const size_t ns = a->sample_every > 0 ? (size_t)(a->nsteps / a->sample_every) : 0;
     d.traj_q = st.out(a->traj_q, B * ns * nq); d.traj_p = st.out(a->traj_p, B * ns * nd);
+    d.times = st.in(a->times, (size_t)a->nsteps + 1);
     if (st.err) return st.err;
     int rc = trepb_step_batch_dev(s, &d, nullptr);
     if (rc) return rc;
@@ -793,6 +835,7 @@ int trepb_project_batch(trepb_system* s, const trepb_project_args* a) {
     d.Kfb = st.in(a->Kfb, (a->k_per_instance ? B : 1) * K * nU * nX);
     d.X = st.out(a->X, B * (K + 1) * nX); d.U = st.out(a->U, B * K * nU);
     d.iters = st.out(a->iters, B); d.status = st.out(a->status, B); d.fail_step = st.out(a->fail_step, B);
+    d.times = st.in(a->times, K + 1);
     if (st.err) return st.err;
     int rc = trepb_project_batch_dev(s, &d, nullptr);
     if (rc) return rc;
@@ -816,16 +859,57 @@ int trepb_calc_p2_batch(trepb_system* s, int64_t batch, double dt, const double*
     return st.finish();
 }
 
+int trepb_calc_f_batch(trepb_system* s, int64_t batch, double t1, double t2, const double* q1, const double* q2,
+                       const double* p1, const double* u1, const double* lambda1, double* f) {
+    if (!s) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)batch, nq = ps.nd + ps.nk;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    const double* dq1 = st.in(q1, B * nq); const double* dq2 = st.in(q2, B * nq); const double* dp1 = st.in(p1, B * ps.nd);
+    const double* du = st.in(u1, B * ps.nu); const double* dl = st.in(lambda1, B * ps.nc);
+    double* df = st.out(f, B * (ps.nd + ps.nc));
+    if (st.err) return st.err;
+    int rc = trepb_calc_f_batch_dev(s, batch, t1, t2, dq1, dq2, dp1, du, dl, df, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
+int trepb_discrete_fm2_batch(trepb_system* s, int64_t batch, double t1, double t2, const double* q1,
+                             const double* q2, const double* u1, double* fm2) {
+    if (!s) return fail(TREPB_ERR_INVALID, "null argument");
+    std::lock_guard<std::mutex> hlk(s->mu_host);
+    if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)batch, nq = ps.nd + ps.nk;
+    CU(cudaSetDevice(s->device));
+    Stager st(s);
+    const double* dq1 = st.in(q1, B * nq); const double* dq2 = st.in(q2, B * nq);
+    const double* du = st.in(u1, B * ps.nu);
+    double* df = st.out(fm2, B * ps.nd);
+    if (st.err) return st.err;
+    int rc = trepb_discrete_fm2_batch_dev(s, batch, t1, t2, dq1, dq2, du, df, nullptr);
+    if (rc) return rc;
+    return st.finish();
+}
+
 }  // extern "C"
 namespace {
 void stage_lin(Stager& st, const trepb_system* s, const trepb_lin_args* a, trepb_lin_args* d) {
     const RtSys& ps = s->P.proto;
     const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
     const size_t nX = 2 * nq, nU = nu + nk;
+    // state rows: [R][L] trajectories when traj_len is set (the caller's q2_guess then has the rows from its
+    // start to the end of the q1 block only when it aliases q1; a separate q2_guess array must hold BS rows)
+    const size_t BS = a->traj_len > 1 ? B / (size_t)(a->traj_len - 1) * (size_t)a->traj_len : B;
     *d = *a;
     d->t1 = st.in(a->t1, B); d->t2 = st.in(a->t2, B);
-    d->q1 = st.in(a->q1, B * nq); d->p1 = st.in(a->p1, B * nd); d->u1 = st.in(a->u1, B * nu); d->k2 = st.in(a->k2, B * nk);
-    d->q2_guess = st.in(a->q2_guess, B * nd); d->lambda_guess = st.in(a->lambda_guess, B * nc);
+    d->q1 = st.in(a->q1, BS * nq); d->p1 = st.in(a->p1, BS * nd); d->u1 = st.in(a->u1, B * nu); d->k2 = st.in(a->k2, B * nk);
+    if (a->traj_len > 1 && a->q2_guess == a->q1 + nq && nd == nq) d->q2_guess = d->q1 + nq;   // X[k+1] as the hint: no second copy
+    else d->q2_guess = st.in(a->q2_guess, BS * nd);
+    d->lambda_guess = st.in(a->lambda_guess, B * nc);
     d->q2 = st.out(a->q2, B * nq); d->p2 = st.out(a->p2, B * nd); d->lambda1 = st.out(a->lambda1, B * nc);
     d->iters = st.out(a->iters, B); d->status = st.out(a->status, B);
     d->A = st.out(a->A, B * nX * nX); d->B = st.out(a->B, B * nX * nU);

@@ -76,7 +76,8 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
             __syncwarp();
             for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[(b * p.nsteps + s) * nk + i];
             __syncwarp();
-            const double t2 = t1 + p.dt;
+            if (p.times) t1 = p.times[s];
+            const double t2 = p.times ? p.times[s + 1] : t1 + p.dt;
             const int it = c.solve(t1, t2, p.tol, p.max_it);
             if (it < 0) { status = it; continue; }
             total += it;
@@ -152,16 +153,18 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
             }
             if (p.use_hint) for (int i = lane; i < nd; i += 32) w[lay.q2 + i] = bX[(long)(s + 1) * nX + i];
             __syncwarp();
-            const double t2 = t1 + p.dt;
+            if (p.times) t1 = p.times[s];
+            const double t2 = p.times ? p.times[s + 1] : t1 + p.dt;
             const int it = c.solve(t1, t2, p.tol, p.max_it);
             if (it < 0) { status = it; fail = s; continue; }
             total += it;
+            const double dts = t2 - t1;
             t1 = t2;
             double* xo = Xo + (long)(s + 1) * nX;
             for (int i = lane; i < nq; i += 32) xo[i] = w[lay.q2 + i];
             for (int i = lane; i < nd; i += 32) xo[nq + i] = w[lay.p2 + i];
             for (int i = lane; i < nk; i += 32) {
-                const double v = (w[lay.q2 + nd + i] - w[lay.q1 + nd + i]) / p.dt;
+                const double v = (w[lay.q2 + nd + i] - w[lay.q1 + nd + i]) / dts;
                 w[lay.vk + i] = v;
                 xo[nq + nd + i] = v;
             }
@@ -186,15 +189,28 @@ coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, co
     double* w = st.w;
     Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
     const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
-    const int nd = c.ND(), nq = c.NQ();
+    const int nd = c.ND(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
         for (int i = lane; i < nq; i += 32) {
             w[lay.q1 + i] = p.q0[b * nq + i];
             w[lay.q2 + i] = p.q1[b * nq + i];
         }
+        for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1 ? p.u1[b * nu + i] : 0.0;
+        if (p.mode == 1) {
+            for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = p.p1[b * nd + i];
+            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lam ? p.lam[b * nc + i] : 0.0;
+        }
         __syncwarp();
-        c.calc_p2(p.dt);
-        for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.p2 + i];
+        if (p.mode == 0) {
+            c.calc_p2(p.dt);
+            for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.p2 + i];
+        } else if (p.mode == 1) {
+            c.calc_f(p.dt);
+            for (int i = lane; i < nd + nc; i += 32) p.p[b * (nd + nc) + i] = w[lay.fr + i];
+        } else {
+            c.calc_fm2(p.dt);
+            for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.fr + i];
+        }
         __syncwarp();
     }
 }
@@ -219,15 +235,16 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc, __syncthreads()) {
         const long b = b0 + (threadIdx.x >> 5);
         if (b >= p.batch) continue;
+        const long r = p.traj_len > 1 ? b + b / (p.traj_len - 1) : b;   // state row (trepb_lin_args.traj_len)
         for (int i = lane; i < nq; i += 32) {
-            const double v = p.q1[b * nq + i];
+            const double v = p.q1[r * nq + i];
             w[lay.q1 + i] = v;
             w[lay.q2 + i] = v;
         }
         __syncwarp();
         for (int i = lane; i < nd; i += 32) {
-            w[lay.p1 + i] = p.p1[b * nd + i];
-            if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
+            w[lay.p1 + i] = p.p1[r * nd + i];
+            if (p.q2g) w[lay.q2 + i] = p.q2g[r * nd + i];
         }
         for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[b * nk + i];
         for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1[b * nu + i];

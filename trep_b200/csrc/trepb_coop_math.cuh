@@ -992,6 +992,50 @@ struct Coop {
         t.sync();
     }
 
+    // MidpointVI_calc_f alone (midpointvi.c:533-575): fr[0:nd] = p1 + D1L2 + fm2 - Dh(q1)^T lam, fr[nd:] = h(q2)
+    TREPB_HD void calc_f(double dt) {
+        const int nd = ND(), nc = NC(), nu = NU(), lane = t.lane();
+        if (nc > 0) {
+            set_point(1, dt);
+            pose_sweep(1);
+            points();
+            constraints(false, 1);
+        }
+        set_point(0, dt);
+        if (nc > 0) {
+            pose_sweep(2);
+            use_pose(true);
+            points();
+            constraints(true, 0);
+            use_pose(false);
+        } else {
+            pose_sweep(0);
+        }
+        dyn_first();
+        double f = 0.0;
+        // fr aliases Lq: every lane forms its entries before any is stored
+        for (int j = lane; j < nd; j += Team::kSize) {
+            double fo = -S.damp()[j] * w[L.dq + j];
+            for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
+            f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
+            for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
+            w[L.fr + j] = f;
+        }
+        for (int c = lane; c < nc; c += Team::kSize) w[L.fr + nd + c] = w[L.hc + c];
+        t.sync();
+    }
+    // discrete_fm2 (midpointvi.c:474-478, 2710-2727): dt F(q_mid, dq, u1) -> fr[0:nd]
+    TREPB_HD void calc_fm2(double dt) {
+        const int nd = ND(), nu = NU();
+        set_point(0, dt);
+        for (int j = t.lane(); j < nd; j += Team::kSize) {
+            double fo = -S.damp()[j] * w[L.dq + j];
+            for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
+            w[L.fr + j] = dt * fo;
+        }
+        t.sync();
+    }
+
     // explicit right-hand-side entry of column `col` (nq: q1 | nd: p1 | nu: u1 | nk: k2) at
     // dynamic row j  (midpointvi.c:929-1098: -D1D1L2_D1fm2 + DDh1.lambda | -e | -D3fm2 | -D2D1L2_D2fm2)
     TREPB_HD double rhs_c(int col, int j, double dt, const double* Y, int ldy) const {

@@ -31,6 +31,7 @@ struct StepParams {
     int *iters, *status;
     int sample_every, nsamples;
     double *traj_q, *traj_p;
+    const double* times;   // [nsteps+1] or null
 };
 
 // closed-loop rollouts (trepb_project_batch*)
@@ -43,6 +44,7 @@ struct ProjParams {
     int k_per_instance, use_hint;
     double *X, *U;
     int *iters, *status, *fail_step;
+    const double* times;   // [nsteps+1] or null
 };
 
 struct P2Params {
@@ -50,6 +52,9 @@ struct P2Params {
     double dt;
     const double *q0, *q1;
     double* p;
+    // mode 0: p2 (calc_p2); 1: residual f [nd+nc] (MidpointVI_calc_f); 2: fm2 [nd] (discrete_fm2)
+    int mode;
+    const double *p1, *u1, *lam;
 };
 
 struct LinParams {
@@ -64,6 +69,7 @@ struct LinParams {
     double *A, *B;
     double* raw[12];  // q2_dq1 q2_dp1 q2_du1 q2_dk2 p2_d* l1_d*
     int stage;        // 1: stage A/B through shared memory for coalesced stores
+    int traj_len;     // 0, or rows per state trajectory (instance b reads state row b + b / (traj_len - 1))
     double* aux;      // [B][AuxLayout::size] factorizations for the second-derivative kernel, or null
     int aux_size;
 };
@@ -265,7 +271,8 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
             for (int i = 0; i < nu; ++i) ws.u1(i) = p.u1 ? p.u1[(b * p.nsteps + st) * nu + i] : 0.0;
             TREPB_UNROLL_SYS
             for (int i = 0; i < nk; ++i) ws.q2(nd + i) = p.k2[(b * p.nsteps + st) * nk + i];
-            const double t2 = t1 + p.dt;
+            if (p.times) t1 = p.times[st];
+            const double t2 = p.times ? p.times[st + 1] : t1 + p.dt;
             const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it, tolT);
             if (it < 0) { status = it; break; }
             total += it;
@@ -337,17 +344,19 @@ project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStri
                 else ws.q2(nd + cc - nu) = u;
             }
             if (p.use_hint) { TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) ws.q2(i) = bX[(long)(s + 1) * nX + i]; }
-            const double t2 = t1 + p.dt;
+            if (p.times) t1 = p.times[s];
+            const double t2 = p.times ? p.times[s + 1] : t1 + p.dt;
             const int it = solve_del(sys, ws, t1, t2, p.tol, p.max_it, tolT);
             if (it < 0) { status = it; fail = s; break; }
             total += it;
+            const double dts = t2 - t1;
             t1 = t2;
             double* xo = Xo + (long)(s + 1) * nX;
             TREPB_UNROLL_SYS for (int i = 0; i < nq; ++i) xo[i] = ws.q2(i);
             TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) xo[nq + i] = ws.p2(i);
             TREPB_UNROLL_SYS
             for (int i = 0; i < nk; ++i) {
-                const double v = (ws.q2(nd + i) - ws.q1(nd + i)) / p.dt;
+                const double v = (ws.q2(nd + i) - ws.q1(nd + i)) / dts;
                 ws.vk(i) = v;
                 xo[nq + nd + i] = v;
             }
@@ -366,7 +375,7 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
     Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
     auto& sys = c.sys;
     auto& ws = c.ws;
-    const int nd = sys.ND(), nq = sys.NQ(), nu = sys.NU();
+    const int nd = sys.ND(), nq = sys.NQ(), nu = sys.NU(), nc = sys.NC();
     for (long b = tid; b < p.batch; b += nth) {
         TREPB_UNROLL_SYS
         for (int i = 0; i < nq; ++i) {
@@ -374,10 +383,22 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
             ws.q2(i) = p.q1[b * nq + i];
         }
         TREPB_UNROLL_SYS
-        for (int i = 0; i < nu; ++i) ws.u1(i) = 0.0;
-        calc_p2(sys, ws, 0.0, p.dt);
-        TREPB_UNROLL_SYS
-        for (int i = 0; i < nd; ++i) p.p[b * nd + i] = ws.p2(i);
+        for (int i = 0; i < nu; ++i) ws.u1(i) = p.u1 ? p.u1[b * nu + i] : 0.0;
+        if (p.mode == 0) {
+            calc_p2(sys, ws, 0.0, p.dt);
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nd; ++i) p.p[b * nd + i] = ws.p2(i);
+        } else if (p.mode == 1) {
+            TREPB_UNROLL_SYS for (int i = 0; i < nd; ++i) ws.p1(i) = p.p1[b * nd + i];
+            TREPB_UNROLL_SYS for (int i = 0; i < nc; ++i) ws.lam(i) = p.lam ? p.lam[b * nc + i] : 0.0;
+            calc_f(sys, ws, 0.0, p.dt);
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nd + nc; ++i) p.p[b * (nd + nc) + i] = ws.fr(i);
+        } else {
+            eval_mid(sys, ws, Dt(p.dt), 1);
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < nd; ++i) p.p[b * nd + i] = p.dt * ws.Fo(i);
+        }
     }
 }
 
@@ -401,16 +422,17 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
         Deriv1Out o;
         double t1 = 0.0, t2 = 0.0;
         if (live) {
+            const long r = p.traj_len > 1 ? b + b / (p.traj_len - 1) : b;   // input row (see trepb_lin_args.traj_len)
             TREPB_UNROLL_SYS
             for (int i = 0; i < nq; ++i) {
-                const double v = p.q1[b * nq + i];
+                const double v = p.q1[r * nq + i];
                 ws.q1(i) = v;
                 ws.q2(i) = v;
             }
             TREPB_UNROLL_SYS
             for (int i = 0; i < nd; ++i) {
-                ws.p1(i) = p.p1[b * nd + i];
-                if (p.q2g) ws.q2(i) = p.q2g[b * nd + i];
+                ws.p1(i) = p.p1[r * nd + i];
+                if (p.q2g) ws.q2(i) = p.q2g[r * nd + i];
             }
             TREPB_UNROLL_SYS
             for (int i = 0; i < nk; ++i) ws.q2(nd + i) = p.k2[b * nk + i];

@@ -1388,6 +1388,33 @@ TREPB_HD int solve_del(const Sys& sys, Ws& ws, double t1, double t2, double tol,
     return iterations;
 }
 
+// MidpointVI_calc_f alone (midpointvi.c:533-575): residual of the DEL equation at the (q1, q2, p1, u1, lam) in
+// the workspace -> fr[0:nd] = p1 + D1L2 + fm2 - Dh(q1)^T lam, fr[nd:nd+nc] = h(q2).
+template <class Sys, class Ws>
+TREPB_HD void calc_f(const Sys& sys, Ws& ws, double t1, double t2) {
+    const int nd = sys.ND(), nc = sys.NC();
+    const double dt = t2 - t1;
+    const Dt dtt(dt);
+    if (nc > 0) {
+        set_point(sys, ws, 1, dtt);
+        pass1(sys, ws, false, true);
+        constraints_eval(sys, ws, 2, 1);  // Dh1 = Dh(q1)
+    }
+    eval_mid(sys, ws, dtt, 1);
+    TREPB_UNROLL_SYS
+    for (int j = 0; j < nd; ++j) {
+        double f = ws.p1(j) + (0.5 * dt * ws.Lq(j) - ws.Lv(j)) + dt * ws.Fo(j);
+        TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) f -= ws.Dh1(c, j) * ws.lam(c);
+        ws.fr(j) = f;
+    }
+    if (nc > 0) {
+        set_point(sys, ws, 2, dtt);
+        pass1(sys, ws, false, true);
+        constraints_eval(sys, ws, 1, 2);
+        TREPB_UNROLL_SYS for (int c = 0; c < nc; ++c) ws.fr(nd + c) = ws.hc(c);
+    }
+}
+
 // calc_p2 alone (midpointvi.c:2702-2708) for initialize_from_configs
 template <class Sys, class Ws>
 TREPB_HD void calc_p2(const Sys& sys, Ws& ws, double t1, double t2) {

@@ -6,9 +6,10 @@ State / input layout is the reference's:  X = [Q(nq); p(nd); v(nk)],  U = [u(nu)
 
 ``linearize_trajectory`` treats every time-step k (and every rollout) as an independent instance -
 exactly what the reference's loop does (it *sets* the state at every k, dsystem.py:413-415) - and
-evaluates all of them in one kernel launch.  With ``torch.distributed`` initialised the instances
-are block-partitioned over the ranks and the A/B slabs are all-gathered (the only exchange this
-path has).
+evaluates all of them in one kernel launch.  With a ``trep_b200.dist.Group`` (one process per GPU) the
+instances are block-partitioned over the ranks and the A / B slabs are collected on rank 0 device to
+device over NVLink - by NCCL, or by the linearize kernel itself writing into rank 0's peer-mapped slab
+(the only exchange this path has).
 """
 from __future__ import annotations
 
@@ -19,29 +20,7 @@ import numpy as np
 from .midpointvi import ConvergenceError, MidpointVI
 
 
-def shard_range(n, rank, world):
-    """Contiguous block partition of n instances: [lo, hi) of `rank`."""
-    base, rem = divmod(n, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
-
-
-def all_gather_blocks(local, n_total, dist=None):
-    """Concatenate per-rank slabs [n_local, ...] -> [n_total, ...] on every rank.  `dist` is
-    torch.distributed (initialised) or None for a single process."""
-    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return local
-    import torch
-    world, rank = dist.get_world_size(), dist.get_rank()
-    counts = [shard_range(n_total, r, world) for r in range(world)]
-    width = max(hi - lo for lo, hi in counts)
-    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
-    pad = np.zeros((width,) + local.shape[1:], dtype=local.dtype)
-    pad[:local.shape[0]] = local
-    mine = torch.from_numpy(pad).to(dev)
-    parts = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(parts, mine)
-    return np.concatenate([p.cpu().numpy()[:hi - lo] for p, (lo, hi) in zip(parts, counts)], axis=0)
+from .dist import shard_range  # noqa: F401  (re-exported: the block partition of the instances)
 
 
 class DSystem:
@@ -252,34 +231,92 @@ class DSystem:
         return self._err(exact, approx)
 
     # ---- the hot path ----------------------------------------------------------------------------------
-    def linearize(self, X, U, t1, t2, X_hint=None, dist=None, compute=None):
+    def linearize(self, X, U, t1, t2, X_hint=None, group=None, gather="nccl", everywhere=False):
         """A[i] = fdx, B[i] = fdu of instance i: DSystem.set(X[i], U[i], k, xk_hint=X_hint[i]) +
-        fdx() + fdu() of the reference.  X [n,nX], U [n,nU], t1/t2 [n]."""
+        fdx() + fdu() of the reference.  X [n,nX], U [n,nU], t1/t2 [n].
+
+        group: a trep_b200.dist.Group (one process per GPU): the instances are block-partitioned over the
+        ranks, every rank linearizes its block, and the A / B slabs are collected on rank 0 (every rank with
+        everywhere=True) device to device: gather="nccl" (ncclSend/Recv or ncclAllGather on the finished
+        slabs) or gather="peer" (rank 0's slab is mapped into every rank and the linearize kernel writes
+        its block straight into it).  Ranks that do not receive the result return None."""
         X, U = np.asarray(X, float), np.asarray(U, float)
         n = X.shape[0]
-        world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
-        rank = dist.get_rank() if world > 1 else 0
+        world = 1 if group is None else group.world
+        rank = 0 if group is None else group.rank
         lo, hi = shard_range(n, rank, world)
         q1, p1, _ = self.split_state(X[lo:hi])
         u1, rho2 = self.split_input(U[lo:hi])
         hint = None if X_hint is None else np.asarray(X_hint, float)[lo:hi, :self._np]
         t1 = np.broadcast_to(np.asarray(t1, float), (n,))[lo:hi]
         t2 = np.broadcast_to(np.asarray(t2, float), (n,))[lo:hi]
-        fn = compute or self._device_linearize
-        A, B, status = fn(q1, p1, u1, rho2, t1, t2, hint)
-        A = all_gather_blocks(A, n, dist)
-        B = all_gather_blocks(B, n, dist)
-        status = all_gather_blocks(status, n, dist)
+        if world == 1:
+            out = self.varint.sys.linearize(q1, p1, u1, rho2, t1=t1, t2=t2, q2_guess=hint, tolerance=self.varint.tolerance)
+            A, B, status = out["A"], out["B"], out["status"]
+        else:
+            A, B, status = self._linearize_sharded(q1, p1, u1, rho2, t1, t2, hint, n, lo, hi, group, gather, everywhere)
+            if A is None:
+                return None
         bad = np.flatnonzero(status != 0)
         if bad.size:
             raise ConvergenceError("%d of %d linearizations failed (first: instance %d, status %d)"
                                    % (bad.size, n, bad[0], status[bad[0]]), status)
         return self.linearization_return(A, B)
 
-    def _device_linearize(self, q1, p1, u1, rho2, t1, t2, hint):
-        out = self.varint.sys.linearize(q1, p1, u1, rho2, t1=t1, t2=t2, q2_guess=hint,
-                                        tolerance=self.varint.tolerance)
-        return out["A"], out["B"], out["status"]
+    def _linearize_sharded(self, q1, p1, u1, rho2, t1, t2, hint, n, lo, hi, group, gather, everywhere):
+        """This rank's block on its GPU, results collected on rank 0 without leaving device memory."""
+        from . import dist, lib
+        sys_, dev = self.varint.sys, self.varint.sys.device
+        nX, nU, cnt = self._nX, self._nU, hi - lo
+        up = lambda a: lib.DeviceBuffer(dev, a.shape, np.float64).upload(np.ascontiguousarray(a, dtype=np.float64))
+        ins = dict(q1=up(q1), p1=up(p1), u1=up(u1) if self._nu else None, k2=up(rho2) if self._nv else None,
+                   t1=up(t1), t2=up(t2), hint=None if hint is None else up(hint))
+        rowA, rowB = nX * nX * 8, nX * nU * 8
+        root = group.rank == 0
+        slabs = []
+        try:
+            if gather == "peer":
+                # rank 0 owns [n] rows of A | B | status; every rank maps it and writes its own rows
+                offB, offS = n * rowA, n * (rowA + rowB)
+                slab = dist.SharedSlab(dev, group.exchange, n * (rowA + rowB + 4))
+                slabs.append(slab)
+                sys_.linearize_raw(True, cnt, ins["q1"], ins["p1"], ins["u1"], ins["k2"], slab.at(offS + lo * 4),
+                                   t1=ins["t1"], t2=ins["t2"], q2_guess=ins["hint"], A=slab.at(lo * rowA),
+                                   B=slab.at(offB + lo * rowB) if nU else None, tolerance=self.varint.tolerance)
+                lib.synchronize(dev)
+                group.barrier()          # every rank's stores have reached rank 0's HBM
+                res = None
+                if root:
+                    raw = slab.local.download()
+                    res = (raw[:offB].view(np.float64).reshape(n, nX, nX).copy(),
+                           raw[offB:offS].view(np.float64).reshape(n, nX, nU).copy(),
+                           raw[offS:offS + 4 * n].view(np.int32).copy())
+                if everywhere:
+                    raise ValueError('gather="peer" delivers to rank 0 only; use gather="nccl" with everywhere=True')
+                group.barrier()          # nobody unmaps before rank 0 has read
+                return res if root else (None, None, None)
+            dA, dB = lib.DeviceBuffer(dev, (max(cnt, 1), nX, nX)), lib.DeviceBuffer(dev, (max(cnt, 1), nX, max(nU, 1)))
+            dS = lib.DeviceBuffer(dev, (max(cnt, 1),), np.int32)
+            slabs += [dA, dB, dS]
+            sys_.linearize_raw(True, cnt, ins["q1"], ins["p1"], ins["u1"], ins["k2"], dS, t1=ins["t1"], t2=ins["t2"],
+                               q2_guess=ins["hint"], A=dA, B=dB if nU else None, tolerance=self.varint.tolerance)
+            out = []
+            for buf, rb, dt, shape in ((dA, rowA, np.float64, (n, nX, nX)), (dB, rowB, np.float64, (n, nX, nU)),
+                                       (dS, 4, np.int32, (n,))):
+                if rb == 0:
+                    out.append(np.zeros(shape, dt))
+                    continue
+                full = dist.gather_rows(buf, cnt, n, rb, group.comm, dev, everywhere=everywhere)
+                if full is None:
+                    out.append(None)
+                else:
+                    out.append(full.download()[:n * rb].view(dt).reshape(shape).copy())
+                    full.free()
+            return tuple(out)
+        finally:
+            for b in list(ins.values()) + slabs:
+                if b is not None:
+                    (b.close if hasattr(b, "close") else b.free)()
 
     def second_derivatives(self, X, U, Z, t1, t2, X_hint=None):
         """z-contracted second derivatives of f for every instance: what the reference's
@@ -299,10 +336,11 @@ class DSystem:
             raise ConvergenceError("%d of %d instances failed" % (bad.size, n), out["status"])
         return out["fdxdx"], out["fdxdu"], out["fdudu"]
 
-    def linearize_trajectory(self, X, U, dist=None, compute=None):
+    def linearize_trajectory(self, X, U, group=None, gather="nccl", everywhere=False):
         """Linearization about a trajectory (dsystem.py:406-423).  X [K+1, nX], U [K, nU] for one
         trajectory or X [R, K+1, nX], U [R, K, nU] for R rollouts sharing `time`.
-        Returns (A, B) with shapes [..., K, nX, nX], [..., K, nX, nU]."""
+        Returns (A, B) with shapes [..., K, nX, nX], [..., K, nX, nU] (None on the ranks of a `group` that
+        do not receive the result, see linearize)."""
         X, U = np.asarray(X, float), np.asarray(U, float)
         single = X.ndim == 2
         if single:
@@ -311,8 +349,11 @@ class DSystem:
         assert U.shape[1] >= K and len(self._time) >= K + 1
         t1 = np.tile(self._time[:K], R)
         t2 = np.tile(self._time[1:K + 1], R)
-        A, B = self.linearize(X[:, :K].reshape(R * K, -1), U[:, :K].reshape(R * K, -1), t1, t2,
-                              X_hint=X[:, 1:K + 1].reshape(R * K, -1), dist=dist, compute=compute)
+        res = self.linearize(X[:, :K].reshape(R * K, -1), U[:, :K].reshape(R * K, -1), t1, t2,
+                             X_hint=X[:, 1:K + 1].reshape(R * K, -1), group=group, gather=gather, everywhere=everywhere)
+        if res is None:
+            return None
+        A, B = res
         A = A.reshape(R, K, self._nX, self._nX)
         B = B.reshape(R, K, self._nX, self._nU)
         if single:
@@ -384,10 +425,12 @@ class DSystem:
         if single:
             bX, bU = bX[None], bU[None]
         K = bX.shape[1] - 1
-        dts = np.diff(self._time[:K + 1])
-        assert np.allclose(dts, dts[0], rtol=1e-9, atol=0), "the in-kernel time loop needs a uniform time grid"
-        out = self.varint.sys.project(bX, bU[:, :K], np.asarray(Kproj, float), self._time[0], float(dts[0]),
-                                      use_hint=use_hint, tolerance=self.varint.tolerance)
+        if len(self._time) < K + 1:
+            raise ValueError("the time base has %d points, the trajectory needs %d" % (len(self._time), K + 1))
+        # the kernel steps on this system's own time grid, uniform or not (dsystem.py:426-457 uses self._time[k])
+        out = self.varint.sys.project(bX, bU[:, :K], np.asarray(Kproj, float), self._time[0],
+                                      float(self._time[1] - self._time[0]), use_hint=use_hint,
+                                      tolerance=self.varint.tolerance, times=self._time[:K + 1])
         self.last_project = out
         bad = np.flatnonzero(out["status"] != 0)
         if bad.size:
@@ -405,13 +448,15 @@ class DSystem:
         if U.ndim == 2:
             U = U[None]
         R, K = U.shape[0], U.shape[1]
+        if len(self._time) < K + 1:
+            raise ValueError("the time base has %d points, the rollout needs %d" % (len(self._time), K + 1))
         dts = np.diff(self._time[:K + 1])
-        assert np.allclose(dts, dts[0], rtol=1e-9, atol=0), "the in-kernel time loop needs a uniform time grid"
         q0, p0, _ = self.split_state(X0)
         u, rho = self.split_input(U)
         v = self.varint
         v.initialize_from_state(self._time[0], q0, p0)
-        out = v.simulate(K, float(dts[0]), u=u if self._nu else None, k=rho if self._nv else None, sample_every=1)
+        out = v.simulate(K, float(dts[0]), u=u if self._nu else None, k=rho if self._nv else None, sample_every=1,
+                         times=self._time[:K + 1])
         Q = np.concatenate([q0[:, None, :], out["traj_q"]], axis=1)
         P = np.concatenate([p0[:, None, :], out["traj_p"]], axis=1)
         X = np.zeros((R, K + 1, self._nX))
@@ -419,5 +464,5 @@ class DSystem:
         X[..., self._nQ:self._nQ + self._np] = P
         if self._nv:
             X[:, 0, self._nQ + self._np:] = X0[:, self._nQ + self._np:]
-            X[:, 1:, self._nQ + self._np:] = (Q[:, 1:, self._np:] - Q[:, :-1, self._np:]) / dts[0]
+            X[:, 1:, self._nQ + self._np:] = (Q[:, 1:, self._np:] - Q[:, :-1, self._np:]) / dts[None, :, None]
         return X

@@ -32,7 +32,7 @@ class StepArgs(C.Structure):
                 ("q2", C.c_void_p), ("p2", C.c_void_p), ("lambda1", C.c_void_p),
                 ("iters", C.c_void_p), ("status", C.c_void_p),
                 ("sample_every", C.c_int32), ("_pad", C.c_int32),
-                ("traj_q", C.c_void_p), ("traj_p", C.c_void_p)]
+                ("traj_q", C.c_void_p), ("traj_p", C.c_void_p), ("times", C.c_void_p)]
 
 
 class ProjectArgs(C.Structure):
@@ -41,7 +41,7 @@ class ProjectArgs(C.Structure):
                 ("bX", C.c_void_p), ("bU", C.c_void_p), ("Kfb", C.c_void_p),
                 ("k_per_instance", C.c_int32), ("use_hint", C.c_int32),
                 ("X", C.c_void_p), ("U", C.c_void_p),
-                ("iters", C.c_void_p), ("status", C.c_void_p), ("fail_step", C.c_void_p)]
+                ("iters", C.c_void_p), ("status", C.c_void_p), ("fail_step", C.c_void_p), ("times", C.c_void_p)]
 
 
 class LqrArgs(C.Structure):
@@ -64,7 +64,7 @@ RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2
 
 
 class LinArgs(C.Structure):
-    _fields_ = ([("batch", C.c_int64), ("max_iterations", C.c_int32), ("_pad", C.c_int32),
+    _fields_ = ([("batch", C.c_int64), ("max_iterations", C.c_int32), ("traj_len", C.c_int32),
                  ("tolerance", C.c_double), ("t1", C.c_void_p), ("t2", C.c_void_p),
                  ("t1_scalar", C.c_double), ("dt_scalar", C.c_double),
                  ("q1", C.c_void_p), ("p1", C.c_void_p), ("u1", C.c_void_p), ("k2", C.c_void_p),
@@ -108,6 +108,10 @@ _lib.trepb_deriv2_batch_dev.argtypes = [C.c_void_p, C.POINTER(D2Args), C.c_void_
 _lib.trepb_calc_p2_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p]
 _lib.trepb_calc_p2_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]
+_lib.trepb_calc_f_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double] + [C.c_void_p] * 6
+_lib.trepb_calc_f_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double] + [C.c_void_p] * 7
+_lib.trepb_discrete_fm2_batch.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double] + [C.c_void_p] * 4
+_lib.trepb_discrete_fm2_batch_dev.argtypes = [C.c_void_p, C.c_int64, C.c_double, C.c_double] + [C.c_void_p] * 5
 _lib.trepb_last_kernel_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
 _lib.trepb_kernel_info.argtypes = [C.c_void_p, C.c_int] + [_ip] * 5
 _lib.trepb_malloc.argtypes = [C.c_int, C.c_int64, C.POINTER(C.c_void_p)]
@@ -117,6 +121,23 @@ _lib.trepb_host_free.argtypes = [C.c_void_p]
 _lib.trepb_memcpy_h2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
 _lib.trepb_memcpy_d2h.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
 _lib.trepb_memset.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int64]
+_lib.trepb_memcpy_d2d.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int64]
+_lib.trepb_comm_available.argtypes = [C.POINTER(C.c_int)]
+_lib.trepb_comm_unique_id.argtypes = [C.c_char_p]
+_lib.trepb_comm_create.argtypes = [C.c_int, C.c_int, C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+_lib.trepb_comm_destroy.argtypes = [C.c_void_p]
+_lib.trepb_comm_destroy.restype = None
+_lib.trepb_comm_rank.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+_lib.trepb_comm_allgather_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
+_lib.trepb_comm_gather_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]
+_lib.trepb_ipc_export.argtypes = [C.c_int, C.c_void_p, C.c_char_p]
+_lib.trepb_ipc_open.argtypes = [C.c_int, C.c_char_p, C.POINTER(C.c_void_p)]
+_lib.trepb_ipc_close.argtypes = [C.c_int, C.c_void_p]
+_lib.trepb_event_pair_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+_lib.trepb_event_record.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+_lib.trepb_event_elapsed_ms.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+_lib.trepb_event_pair_destroy.argtypes = [C.c_void_p]
+_lib.trepb_event_pair_destroy.restype = None
 _lib.trepb_measure_fp64_peak.argtypes = [C.c_int, _dp]
 _lib.trepb_sincos_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p]
 
@@ -125,9 +146,13 @@ EXPORTS = [
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
-    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_linearize_batch",
+    "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_calc_f_batch", "trepb_calc_f_batch_dev",
+    "trepb_discrete_fm2_batch", "trepb_discrete_fm2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
-    "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h",
+    "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h", "trepb_memcpy_d2d",
+    "trepb_comm_available", "trepb_comm_unique_id", "trepb_comm_create", "trepb_comm_destroy", "trepb_comm_rank",
+    "trepb_comm_allgather_dev", "trepb_comm_gather_dev", "trepb_ipc_export", "trepb_ipc_open", "trepb_ipc_close",
+    "trepb_event_pair_create", "trepb_event_record", "trepb_event_elapsed_ms", "trepb_event_pair_destroy",
     "trepb_synchronize", "trepb_last_kernel_ms", "trepb_measure_fp64_peak", "trepb_sincos_batch",
 ]
 
@@ -258,6 +283,35 @@ def synchronize(device=0):
     _check(_lib.trepb_synchronize(device))
 
 
+class EventTimer:
+    """CUDA-event pair on a stream (trepb_event_*): `with EventTimer(dev) as t: ...launches...; t.ms`."""
+
+    def __init__(self, device=0, stream=None):
+        self.device, self.stream = device, stream
+        self._h = C.c_void_p()
+        _check(_lib.trepb_event_pair_create(device, C.byref(self._h)))
+        self.ms = None
+
+    def __enter__(self):
+        _check(_lib.trepb_event_record(self._h, 0, self.stream))
+        return self
+
+    def __exit__(self, *exc):
+        _check(_lib.trepb_event_record(self._h, 1, self.stream))
+        v = C.c_float(0)
+        _check(_lib.trepb_event_elapsed_ms(self._h, C.byref(v)))
+        self.ms = v.value
+        return False
+
+    def __del__(self):
+        try:
+            if self._h:
+                _lib.trepb_event_pair_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+
 class DeviceBuffer:
     """HBM buffer owned through the C ABI (so that a host without torch can drive the library)."""
 
@@ -382,8 +436,8 @@ class System:
     #      anything with data_ptr() => device entry point); the caller owns shapes/dtypes ----------
     def step_raw(self, on_device, batch, nsteps, t0, dt, q1, p1, u1, k2, q2_guess, lambda_guess,
                  q2, p2, lambda1, iters, status, tolerance=1e-10, max_iterations=200,
-                 sample_every=0, traj_q=None, traj_p=None, stream=None):
-        a = StepArgs(batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt,
+                 sample_every=0, traj_q=None, traj_p=None, stream=None, times=None):
+        a = StepArgs(times=_ptr(times), batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt,
                      tolerance=tolerance, q1=_ptr(q1), p1=_ptr(p1), u1=_ptr(u1), k2=_ptr(k2),
                      q2_guess=_ptr(q2_guess), lambda_guess=_ptr(lambda_guess), q2=_ptr(q2),
                      p2=_ptr(p2), lambda1=_ptr(lambda1), iters=_ptr(iters), status=_ptr(status),
@@ -396,8 +450,8 @@ class System:
     @staticmethod
     def _lin_args(batch, q1, p1, u1, k2, status, t1=None, t2=None, t1_scalar=0.0, dt_scalar=0.0,
                   q2_guess=None, lambda_guess=None, q2=None, p2=None, lambda1=None, iters=None,
-                  A=None, B=None, raw=None, tolerance=1e-10, max_iterations=200):
-        a = LinArgs(batch=batch, max_iterations=max_iterations, tolerance=tolerance, t1=_ptr(t1),
+                  A=None, B=None, raw=None, tolerance=1e-10, max_iterations=200, traj_len=0):
+        a = LinArgs(traj_len=traj_len, batch=batch, max_iterations=max_iterations, tolerance=tolerance, t1=_ptr(t1),
                     t2=_ptr(t2), t1_scalar=t1_scalar, dt_scalar=dt_scalar, q1=_ptr(q1), p1=_ptr(p1),
                     u1=_ptr(u1), k2=_ptr(k2), q2_guess=_ptr(q2_guess),
                     lambda_guess=_ptr(lambda_guess), q2=_ptr(q2), p2=_ptr(p2),
@@ -429,8 +483,9 @@ class System:
             _check(_lib.trepb_deriv2_batch(self._h, C.byref(a)))
 
     def project_raw(self, on_device, batch, nsteps, t0, dt, bX, bU, Kfb, X, U, status, k_per_instance=False,
-                    use_hint=True, iters=None, fail_step=None, tolerance=1e-10, max_iterations=200, stream=None):
-        a = ProjectArgs(batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt, tolerance=tolerance,
+                    use_hint=True, iters=None, fail_step=None, tolerance=1e-10, max_iterations=200, stream=None,
+                    times=None):
+        a = ProjectArgs(times=_ptr(times), batch=batch, nsteps=nsteps, max_iterations=max_iterations, t0=t0, dt=dt, tolerance=tolerance,
                         bX=_ptr(bX), bU=_ptr(bU), Kfb=_ptr(Kfb), k_per_instance=1 if k_per_instance else 0,
                         use_hint=1 if use_hint else 0, X=_ptr(X), U=_ptr(U), iters=_ptr(iters), status=_ptr(status),
                         fail_step=_ptr(fail_step))
@@ -445,6 +500,20 @@ class System:
         else:
             _check(_lib.trepb_calc_p2_batch(self._h, batch, dt, _ptr(q0), _ptr(q1), _ptr(p)))
 
+    def calc_f_raw(self, on_device, batch, t1, t2, q1, q2, p1, u1, lambda1, f, stream=None):
+        if on_device:
+            _check(_lib.trepb_calc_f_batch_dev(self._h, batch, t1, t2, _ptr(q1), _ptr(q2), _ptr(p1), _ptr(u1),
+                                               _ptr(lambda1), _ptr(f), stream))
+        else:
+            _check(_lib.trepb_calc_f_batch(self._h, batch, t1, t2, _ptr(q1), _ptr(q2), _ptr(p1), _ptr(u1),
+                                           _ptr(lambda1), _ptr(f)))
+
+    def discrete_fm2_raw(self, on_device, batch, t1, t2, q1, q2, u1, fm2, stream=None):
+        if on_device:
+            _check(_lib.trepb_discrete_fm2_batch_dev(self._h, batch, t1, t2, _ptr(q1), _ptr(q2), _ptr(u1), _ptr(fm2), stream))
+        else:
+            _check(_lib.trepb_discrete_fm2_batch(self._h, batch, t1, t2, _ptr(q1), _ptr(q2), _ptr(u1), _ptr(fm2)))
+
     # ---- numpy convenience (host entry points) ---------------------------------------------------
     def _f(self, x, shape):
         x = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
@@ -458,10 +527,34 @@ class System:
         self.calc_p2_raw(False, B, float(dt), q0, q1, p)
         return p
 
+    def calc_f(self, t1, t2, q1, q2, p1, u1=None, lambda1=None):
+        """Residual of the DEL equation [B][nd+nc] (_MidpointVI._calc_f, midpointvi.c:533-575)."""
+        q1 = np.atleast_2d(np.asarray(q1, float))
+        B = q1.shape[0]
+        q1, q2, p1 = self._f(q1, (B, self.nq)), self._f(q2, (B, self.nq)), self._f(p1, (B, self.nd))
+        u1 = None if (u1 is None or self.nu == 0) else self._f(u1, (B, self.nu))
+        lam = None if (lambda1 is None or self.nc == 0) else self._f(lambda1, (B, self.nc))
+        f = np.empty((B, self.nd + self.nc))
+        self.calc_f_raw(False, B, float(t1), float(t2), q1, q2, p1, u1, lam, f)
+        return f
+
+    def discrete_fm2(self, t1, t2, q1, q2, u1=None):
+        """Discrete forcing (t2 - t1) F(q_mid, dq, u1) [B][nd] (_MidpointVI.discrete_fm2, midpointvi.c:2710-2727)."""
+        q1 = np.atleast_2d(np.asarray(q1, float))
+        B = q1.shape[0]
+        q1, q2 = self._f(q1, (B, self.nq)), self._f(q2, (B, self.nq))
+        u1 = None if (u1 is None or self.nu == 0) else self._f(u1, (B, self.nu))
+        fm2 = np.empty((B, self.nd))
+        self.discrete_fm2_raw(False, B, float(t1), float(t2), q1, q2, u1, fm2)
+        return fm2
+
     def step(self, q1, p1, t0, dt, nsteps=1, u1=None, k2=None, q2_guess=None, lambda_guess=None,
-             tolerance=1e-10, max_iterations=200, sample_every=0):
+             tolerance=1e-10, max_iterations=200, sample_every=0, times=None):
         """`nsteps` consecutive MidpointVI steps for every instance.  Returns a dict with the
-        final q2, p2, lambda1, iters (summed), status and optionally the sampled trajectory."""
+        final q2, p2, lambda1, iters (summed), status and optionally the sampled trajectory.
+        times: optional grid [nsteps+1] shared by the batch (step s runs times[s] -> times[s+1])."""
+        if times is not None:
+            times = self._f(times, (nsteps + 1,))
         q1 = np.atleast_2d(np.asarray(q1, float))
         B = q1.shape[0]
         q1, p1 = self._f(q1, (B, self.nq)), self._f(p1, (B, self.nd))
@@ -483,10 +576,10 @@ class System:
             out["traj_p"] = np.empty((B, ns, self.nd))
         self.step_raw(False, B, nsteps, float(t0), float(dt), q1, p1, u1, k2, q2g, lg, out["q2"],
                       out["p2"], out["lambda1"] if self.nc else None, out["iters"], out["status"],
-                      tolerance, max_iterations, sample_every, out.get("traj_q"), out.get("traj_p"))
+                      tolerance, max_iterations, sample_every, out.get("traj_q"), out.get("traj_p"), times=times)
         return out
 
-    def project(self, bX, bU, Kfb, t0, dt, use_hint=True, tolerance=1e-10, max_iterations=200):
+    def project(self, bX, bU, Kfb, t0, dt, use_hint=True, tolerance=1e-10, max_iterations=200, times=None):
         """Closed-loop rollouts X[0] = bX[0], U[k] = bU[k] - K[k](X[k] - bX[k]), X[k+1] = f(X[k], U[k])
         (DSystem.project / DOptimizer.armijo_simulate) for a batch of candidates.
         bX [B,K+1,nX], bU [B,K,nU], Kfb [K,nU,nX] (shared) or [B,K,nU,nX]."""
@@ -503,7 +596,8 @@ class System:
                    status=np.zeros(B, np.int32), fail_step=np.zeros(B, np.int32))
         self.project_raw(False, B, K, float(t0), float(dt), bX, bU, Kfb, out["X"], out["U"], out["status"],
                          k_per_instance=per, use_hint=use_hint, iters=out["iters"], fail_step=out["fail_step"],
-                         tolerance=tolerance, max_iterations=max_iterations)
+                         tolerance=tolerance, max_iterations=max_iterations,
+                         times=None if times is None else self._f(times, (K + 1,)))
         return out
 
     def linearize(self, q1, p1, u1=None, k2=None, t1=0.0, t2=None, dt=None, q2_guess=None,

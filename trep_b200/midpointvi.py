@@ -107,24 +107,39 @@ class MidpointVI:
         self._check(out["status"])
         return out["iters"]
 
-    def simulate(self, nsteps, dt, u=None, k=None, max_iterations=200, sample_every=0):
-        """`nsteps` steps of length dt inside one kernel launch (the Monte-Carlo / rollout path).
+    def simulate(self, nsteps, dt, u=None, k=None, max_iterations=200, sample_every=0, times=None):
+        """`nsteps` steps inside one kernel launch (the Monte-Carlo / rollout path): of length dt, or on
+        the grid `times` [nsteps+1] (times[0] = the current t2; any spacing).
         u: [B, nsteps, nu], k: [B, nsteps, nk] (kinematic configs at the END of each step).
         Returns dict(iters, traj_q, traj_p) - trajectories only if sample_every > 0."""
         out = self.sys.step(self.q2, self.p2, self.t2, float(dt), nsteps=nsteps, u1=u, k2=k,
                             lambda_guess=self.lambda1 if self.nc else None, tolerance=self.tolerance,
-                            max_iterations=max_iterations, sample_every=sample_every)
+                            max_iterations=max_iterations, sample_every=sample_every, times=times)
         # state before the last step is only known when a trajectory was captured
         self.q1 = self.p1 = None
         t = self.t2
-        for _ in range(nsteps):       # same accumulation as repeated step(t2 + dt) calls
-            self.t1, t = t, t + float(dt)
+        if times is not None:
+            self.t1, t = float(times[-2]), float(times[-1])
+        else:
+            for _ in range(nsteps):       # same accumulation as repeated step(t2 + dt) calls
+                self.t1, t = t, t + float(dt)
         self.t2 = t
         self.q2, self.p2, self.lambda1 = out["q2"], out["p2"], out["lambda1"]
         self._lin = None
         self._d2 = None
         self._check(out["status"])
         return out
+
+    def calc_f(self):
+        """Residual of the DEL equation at the current (q1, q2, p1, u1, lambda1): [B, nd+nc]
+        (_MidpointVI._calc_f, midpointvi.c:567-575)."""
+        assert self.q1 is not None and self.p1 is not None, "calc_f needs the state before the step"
+        return self.sys.calc_f(self.t1, self.t2, self.q1, self.q2, self.p1, self.u1, self.lambda1 if self.nc else None)
+
+    def discrete_fm2(self):
+        """Discrete forcing of the current step [B, nd] (_MidpointVI.discrete_fm2, midpointvi.c:2710-2727)."""
+        assert self.q1 is not None, "discrete_fm2 needs the configuration before the step"
+        return self.sys.discrete_fm2(self.t1, self.t2, self.q1, self.q2, self.u1)
 
     @property
     def v2(self):
@@ -189,38 +204,59 @@ class MidpointVI:
         raise AttributeError(name)
 
 
-def monte_carlo_sweep(system, q0, dt, nsteps, q1=None, u=None, k=None, tolerance=1e-10, device=0, dist=None,
-                      hist_max=8, compute=None):
+def monte_carlo_sweep(system, q0, dt, nsteps, q1=None, u=None, k=None, tolerance=1e-10, device=None, group=None,
+                      hist_max=8):
     """Monte-Carlo initial-condition sweep (BASELINE.json config 4): every row of q0 [N, nq] is an
     independent rollout started with ``initialize_from_configs(0, q0, dt, q1 or q0)`` and stepped
-    ``nsteps`` times inside one kernel launch.  With ``torch.distributed`` initialised (``dist``) the
+    ``nsteps`` times inside one kernel launch.  With a ``trep_b200.dist.Group`` (one process per GPU) the
     rollouts are block-partitioned over the ranks - no exchange while stepping - and only the final
-    states (q2, p2: 16 (nq + nd) bytes per rollout), the per-rollout iteration totals and status codes
-    are all-gathered.  Returns dict(q2 [N,nq], p2 [N,nd], iters [N], status [N], hist): ``hist[i]`` =
-    number of rollouts whose mean Newton iterations per step rounds to i."""
-    from .discopt import all_gather_blocks, shard_range
+    states (q2, p2: 8 (nq + nd) bytes per rollout), the per-rollout iteration totals and status codes
+    are gathered on rank 0, device to device (NCCL).  Returns dict(q2 [N,nq], p2 [N,nd], iters [N],
+    status [N], hist) on rank 0 (None elsewhere): ``hist[i]`` = number of rollouts whose mean Newton
+    iterations per step rounds to i."""
+    from . import dist as D_
     q0 = np.atleast_2d(np.asarray(q0, float))
     n = q0.shape[0]
-    world = dist.get_world_size() if (dist is not None and dist.is_initialized()) else 1
-    rank = dist.get_rank() if world > 1 else 0
-    lo, hi = shard_range(n, rank, world)
+    world = 1 if group is None else group.world
+    rank = 0 if group is None else group.rank
+    if device is None:
+        device = 0 if group is None else group.device
+    lo, hi = D_.shard_range(n, rank, world)
     sl = slice(lo, hi)
     q1s = q0[sl] if q1 is None else np.atleast_2d(np.asarray(q1, float))[sl]
     us = None if u is None else np.asarray(u, float)[sl]
     ks = None if k is None else np.asarray(k, float)[sl]
-    if compute is None:
-        def compute(q0_, q1_, us_, ks_):
-            mvi = MidpointVI(system, tolerance=tolerance, device=device)
-            if q0_.shape[0] == 0:
-                return np.zeros((0, mvi.nq)), np.zeros((0, mvi.nd)), np.zeros(0, np.int32), np.zeros(0, np.int32)
-            mvi.initialize_from_configs(0.0, q0_, dt, q1_)
-            out = mvi.sys.step(mvi.q2, mvi.p2, mvi.t2, float(dt), nsteps=nsteps, u1=us_, k2=ks_, tolerance=tolerance)
-            return out["q2"], out["p2"], out["iters"], out["status"]
-    q2, p2, iters, status = compute(q0[sl], q1s, us, ks)
-    q2 = all_gather_blocks(np.ascontiguousarray(q2), n, dist)
-    p2 = all_gather_blocks(np.ascontiguousarray(p2), n, dist)
-    iters = all_gather_blocks(np.ascontiguousarray(iters), n, dist)
-    status = all_gather_blocks(np.ascontiguousarray(status), n, dist)
+    mvi = MidpointVI(system, tolerance=tolerance, device=device)
+    cnt = hi - lo
+    if world == 1:
+        mvi.initialize_from_configs(0.0, q0[sl], dt, q1s)
+        out = mvi.sys.step(mvi.q2, mvi.p2, mvi.t2, float(dt), nsteps=nsteps, u1=us, k2=ks, tolerance=tolerance)
+        q2, p2, iters, status = out["q2"], out["p2"], out["iters"], out["status"]
+    else:
+        s, nq, nd = mvi.sys, mvi.nq, mvi.nd
+        up = lambda a: lib.DeviceBuffer(device, a.shape, np.float64).upload(np.ascontiguousarray(a, dtype=np.float64))
+        dq0, dq1 = up(q0[sl]), up(q1s)
+        du = None if us is None or not mvi.nu else up(us)
+        dk = None if ks is None or not mvi.nk else up(ks)
+        m = max(cnt, 1)
+        dp = lib.DeviceBuffer(device, (m, nd)); q2d = lib.DeviceBuffer(device, (m, nq)); p2d = lib.DeviceBuffer(device, (m, nd))
+        itd = lib.DeviceBuffer(device, (m,), np.int32); std = lib.DeviceBuffer(device, (m,), np.int32)
+        s.calc_p2_raw(True, cnt, float(dt), dq0, dq1, dp)
+        s.step_raw(True, cnt, nsteps, float(dt), float(dt), dq1, dp, du, dk, None, None, q2d, p2d, None, itd, std,
+                   tolerance=tolerance)
+        res = []
+        for buf, rb, dt_, shape in ((q2d, 8 * nq, np.float64, (n, nq)), (p2d, 8 * nd, np.float64, (n, nd)),
+                                    (itd, 4, np.int32, (n,)), (std, 4, np.int32, (n,))):
+            full = D_.gather_rows(buf, cnt, n, rb, group.comm, device)
+            res.append(None if full is None else full.download()[:n * rb].view(dt_).reshape(shape).copy())
+            if full is not None:
+                full.free()
+        for b in (dq0, dq1, du, dk, dp, q2d, p2d, itd, std):
+            if b is not None:
+                b.free()
+        if rank != 0:
+            return None
+        q2, p2, iters, status = res
     mean = np.rint(iters[status == 0] / float(nsteps)).astype(np.int64)
     hist = np.bincount(np.clip(mean, 0, hist_max), minlength=hist_max + 1)
     return dict(q2=q2, p2=p2, iters=iters, status=status, hist=hist)
