@@ -17,7 +17,11 @@ hot path over that batch = 1.048576e9 DEL steps per GPU.  Metric: DEL steps/s, w
              bounded sample
 
 `--impl reference` times only the reference arm (rank 0; other ranks exit).
-Multi-GPU (torchrun): the batch shards across ranks with no data-path collective (weak scaling).
+Multi-GPU (torchrun): the batch shards across ranks with no data-path collective (weak scaling).  For N > 1 the
+line also carries `secondary` entries measured on all N ranks (max over ranks, device-timed): W3 linearizations/s
+sharded over the ranks plus the gather of the A / B slabs on rank 0 - by NCCL (trepb_comm_gather_dev) and fused
+into the linearize kernel through rank 0's peer-mapped slab - with the achieved NVLink GB/s, W5 marionette
+linearizations/s, and W4 at north_star's size (1.25e7 dual pendulums per GPU x 1000 steps).
 """
 import argparse
 import json
@@ -117,6 +121,34 @@ def dist_setup(ngpus):
     return None, 0, 0, 1
 
 
+def explain_failures(name, kind, **inp):
+    """CHECKER (oracle/_ref, not timed, not part of any measured path): run the reference's own C on the inputs
+    of the instances the GPU reported as not converged / singular and count on how many the reference fails too."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    h = cb.Harness(name)
+    if kind == "rollouts":
+        r = h.rollouts(inp["q"], inp["p"], inp["nsteps"], inp["t0"], inp["dt"])
+    else:
+        r = h.linearize(inp["q1"], inp["p1"], inp.get("u1"), inp.get("k2"), inp.get("t1", 0.0), inp["dt"],
+                        q2_hint=inp.get("hint"), lam_hint=inp.get("lam"))
+    return int(np.sum(r["status"] != 0))
+
+
+def failure_report(name, kind, status, limit=64, **inp):
+    bad = np.flatnonzero(status != 0)
+    rep = {"not_ok": int(bad.size)}
+    if bad.size:
+        pick = bad[:limit]
+        sub = {k: (v[pick] if isinstance(v, np.ndarray) and v.shape[:1] == status.shape else v) for k, v in inp.items()}
+        try:
+            rep["checked"] = int(pick.size)
+            rep["reference_also_fails"] = explain_failures(name, kind, **sub)
+        except Exception as e:      # the checker must never break the measurement
+            rep["checker_error"] = repr(e)[:200]
+    return rep
+
+
 def reference_arm(args, rank, world):
     """Times the reference's own C implementation on the host cores (oracle/_ref)."""
     if rank != 0:
@@ -210,25 +242,57 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     class Off:
         def __init__(self, buf, off_bytes): self.p = buf.data_ptr() + off_bytes
         def data_ptr(self): return self.p
-    n = R * K - 1
+    # R trajectories of K state rows (x_1 .. x_K) -> R (K-1) linearizations (traj_len = K): instance (r, k) has
+    # state x_{k+1}, input U[r][k+1] and hint x_{k+2}; nothing straddles two rollouts (round 1 linearized 4095 such
+    # junk instances: those were its 12 non-converged ones)
+    n = R * (K - 1)
+    du_lin = up(np.ascontiguousarray(U[:, 1:]))
     A = lib.DeviceBuffer(device, (n, 4, 4)); Bm = lib.DeviceBuffer(device, (n, 4, 1))
     it = lib.DeviceBuffer(device, (n,), np.int32); st = lib.DeviceBuffer(device, (n,), np.int32)
     ms = []
     for rep in range(4):
-        s.linearize_raw(True, n, tq, tp, Off(du, 8), None, st, t1_scalar=0.0, dt_scalar=DT, q2_guess=Off(tq, 16),
-                        iters=it, A=A, B=Bm)
+        s.linearize_raw(True, n, tq, tp, du_lin, None, st, t1_scalar=0.0, dt_scalar=DT, q2_guess=Off(tq, 16),
+                        iters=it, A=A, B=Bm, traj_len=K)
         lib.synchronize(device)
         if rep >= 1:
             ms.append(s.last_kernel_ms())
     t = float(np.mean(ms))
     byt = 16 + 16 + 8 + 16 + 160 + 8      # q1, p1, u1, hint in; A, B, iters, status out
-    out.append({"metric": "linearizations/s (W3: pend-on-cart linearize_trajectory, 4096 rollouts x 10000 steps, exact hints)",
-                "value": n / t * 1e3, "unit": "linearizations/s", "batch": n, "ms": t,
-                "newton_iters_mean": float(it.download().mean()), "ok_fraction": float((st.download() == 0).mean()),
-                "rollout_kernel_ms": roll_ms, "rollout_steps_per_s": R * K / roll_ms * 1e3,
-                "roofline": {"bound": "hbm", "achieved": n * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
-                             "frac": n * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt}})
-    for b in (du, dq0, dp0, tq, tp, q2, p2, itr, sr, A, Bm, it, st):
+    st_h = st.download()
+    w3 = {"metric": "linearizations/s (W3: pend-on-cart linearize_trajectory, 4096 rollouts x 10000 steps, exact hints)",
+          "value": n / t * 1e3, "unit": "linearizations/s", "batch": n, "ms": t,
+          "newton_iters_mean": float(it.download().mean()), "ok_fraction": float((st_h == 0).mean()),
+          "rollout_kernel_ms": roll_ms, "rollout_steps_per_s": R * K / roll_ms * 1e3,
+          "rollouts_ok_fraction": float((sr.download() == 0).mean()),
+          "roofline": {"bound": "hbm", "achieved": n * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                       "frac": n * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt}}
+    if (st_h != 0).any():
+        bad = np.flatnonzero(st_h != 0)[:64]
+        rows = bad + bad // (K - 1)
+        tqh, tph = tq.download().reshape(-1, 2), tp.download().reshape(-1, 2)
+        w3["failures"] = failure_report("pend_on_cart1", "linearize", np.ones(bad.size, np.int32), q1=tqh[rows], p1=tph[rows],
+                                        u1=U[:, 1:].reshape(-1, 1)[bad], hint=tqh[rows + 1], dt=DT)
+    out.append(w3)
+    # the same pipeline end to end through the host-pointer call: X, U in pinned host memory, A, B back to the host
+    ne = 1 << 21
+    hq, hp, hu = lib.pinned_empty((ne, 2)), lib.pinned_empty((ne, 2)), lib.pinned_empty((ne, 1))
+    hq[:] = tq.download().reshape(-1, 2)[:ne]; hp[:] = tp.download().reshape(-1, 2)[:ne]; hu[:] = U.reshape(-1, 1)[:ne]
+    hA, hB = lib.pinned_empty((ne, 4, 4)), lib.pinned_empty((ne, 4, 1))
+    hst = lib.pinned_empty((ne,), np.int32)
+    te = []
+    for rep in range(3):
+        t0_ = time.perf_counter()
+        s.linearize_raw(False, ne, hq, hp, hu, None, hst, t1_scalar=0.0, dt_scalar=DT, A=hA, B=hB)
+        te.append((time.perf_counter() - t0_) * 1e3)
+    te = float(np.mean(te[1:]))
+    out.append({"metric": "linearizations/s END TO END (W3-shaped: trepb_linearize_batch with pinned host buffers, 2^21 instances, "
+                          "host-to-device and device-to-host copies inside the timed region)",
+                "value": ne / te * 1e3, "unit": "linearizations/s", "batch": ne, "ms": te,
+                "h2d_bytes": ne * 40, "d2h_bytes": ne * 164, "pcie_GBps": ne * 204 / te / 1e6,
+                "note": "PCIe-bound: 204 bytes cross the bus per linearization against 224 bytes of HBM traffic at 4.6 TB/s on the "
+                        "device-resident path; a caller that needs the gains, not A / B, keeps the slabs on the GPU "
+                        "(trepb_lqr_batch_dev) and moves 8 nU nX bytes per step instead"})
+    for b in (du, du_lin, dq0, dp0, tq, tp, q2, p2, itr, sr, A, Bm, it, st):
         b.free()
     s.close()
     # ---- W4-shaped: dual pendulums (LinearSpring + LinearDamper), 2^22 instances x 100 steps
@@ -247,9 +311,11 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
         if rep >= 1:
             ms.append(s.last_kernel_ms())
     t = float(np.mean(ms))
+    st_h = st.download()
     w4 = {"metric": "DEL steps/s (W4: dual pendulums Monte-Carlo sweep, 2^22 instances x 100 steps)", "value": B * 100 / t * 1e3,
           "unit": "DEL steps/s", "batch": B, "ms": t, "newton_iters_per_step": float(it.download().mean()) / 100,
-          "ok_fraction": float((st.download() == 0).mean())}
+          "ok_fraction": float((st_h == 0).mean()),
+          "failures": failure_report("dual_pendulums", "rollouts", st_h, q=q, p=dp.download(), nsteps=100, t0=DT, dt=DT)}
     try:
         with open(os.path.join(ROOT, "profiles", "flops.json")) as fh:
             fl4 = float(json.load(fh)["dual_pendulums_step_flops_per_del_step"])
@@ -299,7 +365,7 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                                  "hbm": {"achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                          "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg},
                                  "note": "cooperative kernel: one warp per instance, link tables + 30 KB workspace per instance in shared "
-                                         "memory (7 instances per SM); DRAM traffic is the A/B output only. Issue-bound: fp64 "
+                                         "memory (8 instances per SM); DRAM traffic is the A/B output only. Issue-bound: fp64 "
                                          "instructions are ~1/5 of the issued instructions and 7 warps per SM cannot hide the "
                                          "dependent-issue latency (ncu: profiles/r01d_coop_lin_raw.txt; DESIGN.md section 6)"}
     out.append(entry)
@@ -363,22 +429,19 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     Bl = up(rng.normal(0, 1.0, (Rl, Kl, nX, nU)))
     Ql, Rr = up(np.eye(nX)), up(np.eye(nU))
     Kl_out = lib.DeviceBuffer(device, (Rl, Kl, nU, nX)); lst = lib.DeviceBuffer(device, (Rl,), np.int32)
-    import time as _t
     lib.lqr_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Rr, Kl_out, lst)
     lib.synchronize(device)
-    t0_ = _t.perf_counter()
-    for rep in range(3):
-        lib.lqr_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Rr, Kl_out, lst)
-    lib.synchronize(device)
-    tl = (_t.perf_counter() - t0_) / 3 * 1e3
+    with lib.EventTimer(device) as tm:
+        for rep in range(3):
+            lib.lqr_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Rr, Kl_out, lst)
+    tl = tm.ms / 3
     fl_step = 2.0 * (2 * nX ** 3 + 3 * nX * nX * nU + nU * nU * nX) + 2.0 * nU * nU * (nU / 3.0 + nX)
     out.append({"metric": "Riccati steps/s (discopt.dlqr.solve_tv_lqr at the marionette's size nX=%d nU=%d, %d rollouts x %d steps)" % (nX, nU, Rl, Kl),
                 "value": Rl * Kl / tl * 1e3, "unit": "Riccati steps/s", "batch": Rl, "ms": tl,
                 "ok_fraction": float((lst.download() == 0).mean()),
                 "roofline": {"bound": "fp64", "achieved": fl_step * Rl * Kl / (tl * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": fl_step * Rl * Kl / (tl * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": fl_step,
-                             "note": "host-timed over 3 launches (the call has no system handle to carry CUDA events); "
-                                     "flops counted from the matrix shapes"}})
+                             "note": "CUDA events around 3 launches on the launching stream; flops counted from the matrix shapes"}})
     for b_ in (Al, Bl, Ql, Rr, Kl_out, lst):
         b_.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)
@@ -464,10 +527,11 @@ def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
                         "spline_pendulum": "2 DOF, NonlinearConfigSpring over a quintic spline"}[name]),
                     "value": B / t * 1e3, "unit": "linearizations/s", "batch": B, "ms": t, "kernel": s.kernel_name,
                     "newton_iters_mean": float(it.download().mean()), "ok_fraction": float((st.download() == 0).mean()),
+                    "failures": failure_report(name, "linearize", st.download(), q1=q1, p1=p1, u1=du.download() if nu else None,
+                                               lam=lam.download() if lam is not None else None, dt=DT),
                     "roofline": {"bound": "hbm", "achieved": B * byt / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": B * byt / t / 1e6 / hbm_peak, "traffic": None, "bytes_per_unit": byt,
-                                 "note": "algorithmic bytes (inputs + A, B, q2, p2, lambda, iters, status); the table-driven "
-                                         "thread kernel keeps its per-instance workspace in HBM, so its real traffic is higher"}})
+                                 "note": "algorithmic bytes (inputs + A, B, q2, p2, lambda, iters, status)"}})
         for b in (dq, dp, du, lam, q2, p2, l2, it, st, A, Bm):
             if b is not None:
                 b.free()
@@ -529,20 +593,179 @@ def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
     Ko = lib.DeviceBuffer(device, (Rl, Kl, nU, nX)); Co = lib.DeviceBuffer(device, (Rl, Kl, nU)); lst = lib.DeviceBuffer(device, (Rl,), np.int32)
     lib.lq_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Sl, Rr, ql, rl, Ko, Co, lst, cost_per_rollout=True)
     lib.synchronize(device)
-    t0_ = time.perf_counter()
-    for rep in range(3):
-        lib.lq_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Sl, Rr, ql, rl, Ko, Co, lst, cost_per_rollout=True)
-    lib.synchronize(device)
-    tl = (time.perf_counter() - t0_) / 3 * 1e3
+    with lib.EventTimer(device) as tm:
+        for rep in range(3):
+            lib.lq_raw(True, device, Rl, Kl, nX, nU, Al, Bl, Ql, Sl, Rr, ql, rl, Ko, Co, lst, cost_per_rollout=True)
+    tl = tm.ms / 3
     fl_step = 2.0 * (2 * nX ** 3 + 3 * nX * nX * nU + nU * nU * nX) + 2.0 * nU * nU * (nU / 3.0 + nX) + 2.0 * (nX * nX + 3 * nX * nU + nU * nU)
     out.append({"metric": "Riccati steps/s (discopt.dlqr.solve_tv_lq: cross term + affine recursion, nX=%d nU=%d, %d rollouts x %d steps, one cost set per rollout)" % (nX, nU, Rl, Kl),
                 "value": Rl * Kl / tl * 1e3, "unit": "Riccati steps/s", "batch": Rl, "ms": tl,
                 "ok_fraction": float((lst.download() == 0).mean()),
                 "roofline": {"bound": "fp64", "achieved": fl_step * Rl * Kl / (tl * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": fl_step * Rl * Kl / (tl * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": fl_step,
-                             "note": "host-timed over 3 launches; flops counted from the matrix shapes"}})
+                             "note": "CUDA events around 3 launches; flops counted from the matrix shapes"}})
     for b_ in (Al, Bl, Ql, Rr, Sl, ql, rl, Ko, Co, lst):
         b_.free()
+    return out
+
+
+def w4_full(lib, systems, device, world, reduce_max, fp64_peak):
+    """W4 at north_star's size: 1.25e7 dual pendulums per GPU (1e8 on 8 GPUs) x 1000 steps, one launch."""
+    rng = np.random.default_rng(100 + int(os.environ.get("RANK", "0")))
+    d = systems.named_desc("dual_pendulums")
+    s = lib.System(d, device=device)
+    B, ns = 12500000, 1000
+    q = rng.uniform(-np.pi, np.pi, (B, 2))
+    up = lambda a: lib.DeviceBuffer(device, a.shape, a.dtype).upload(a)
+    dq = up(q); dp = lib.DeviceBuffer(device, (B, 2))
+    s.calc_p2_raw(True, B, DT, dq, dq, dp)
+    q2 = lib.DeviceBuffer(device, (B, 2)); p2 = lib.DeviceBuffer(device, (B, 2))
+    it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+    s.step_raw(True, B, 20, DT, DT, dq, dp, None, None, None, None, q2, p2, None, it, st)     # warm-up
+    lib.synchronize(device)
+    s.step_raw(True, B, ns, DT, DT, dq, dp, None, None, None, None, q2, p2, None, it, st)
+    lib.synchronize(device)
+    t = reduce_max(s.last_kernel_ms())
+    st_h = st.download()
+    iters = it.download()
+    hist = np.bincount(np.clip(np.rint(iters[st_h == 0] / float(ns)).astype(np.int64), 0, 8), minlength=9)
+    e = {"metric": "DEL steps/s (W4 at north_star's size: %.3g dual pendulums per GPU x %d steps, %d GPU(s), weak scaling)" % (B, ns, world),
+         "value": float(B) * ns * world / t * 1e3, "unit": "DEL steps/s", "batch_per_gpu": B, "nsteps": ns, "ms": t,
+         "newton_iters_per_step": float(iters.mean()) / ns, "ok_fraction_rank0": float((st_h == 0).mean()),
+         "iteration_histogram_rank0": hist.tolist(),
+         "failures_rank0": failure_report("dual_pendulums", "rollouts", st_h, limit=16, q=q, p=dp.download(), nsteps=ns, t0=DT, dt=DT)}
+    try:
+        with open(os.path.join(ROOT, "profiles", "flops.json")) as fh:
+            fl4 = float(json.load(fh)["dual_pendulums_step_flops_per_del_step"])
+        ach = fl4 * B * ns / (t * 1e-3) / 1e12
+        e["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s per GPU", "frac": ach / fp64_peak,
+                         "flops_per_unit": fl4}
+    except (OSError, KeyError):
+        pass
+    for b in (dq, dp, q2, p2, it, st):
+        b.free()
+    s.close()
+    return e
+
+
+def multi_gpu(lib, systems, group, device, rank, world, reduce_max, fp64_peak, hbm_peak):
+    """N > 1: the BASELINE metric's other half (linearizations/s) on all ranks, and the one exchange of the path -
+    collecting the A / B slabs on rank 0 - measured two ways.  Every time is the max over ranks of a device time."""
+    from trep_b200 import dist as D_
+    out = []
+    up = lambda a, dt=np.float64: lib.DeviceBuffer(device, a.shape, dt).upload(np.ascontiguousarray(a, dtype=dt))
+
+    class Off:
+        def __init__(self, p): self.p = int(p)
+        def data_ptr(self): return self.p
+    # ---- W3, strong scaling: the fixed 4096 rollouts x 10000 steps, block-partitioned by rollout
+    rng = np.random.default_rng(1)
+    d = systems.named_desc("pend_on_cart1")
+    s = lib.System(d, device=device)
+    Rtot, K = 4096, 10000
+    lo, hi = D_.shard_range(Rtot, rank, world)
+    R = hi - lo
+    tt = DT * np.arange(K)
+    amp = rng.uniform(0, 2, (Rtot, 1)); om = rng.uniform(0.5, 3, (Rtot, 1)); th0 = rng.uniform(-0.5, 0.5, Rtot)
+    U = (amp[lo:hi] * np.sin(om[lo:hi] * tt[None, :]))[:, :, None]
+    q0 = np.zeros((R, 2)); q0[:, 1] = th0[lo:hi]
+    du = up(U); du_lin = up(U[:, 1:]); dq0 = up(q0); dp0 = up(np.zeros((R, 2)))
+    tq = lib.DeviceBuffer(device, (R, K, 2)); tp = lib.DeviceBuffer(device, (R, K, 2))
+    q2 = lib.DeviceBuffer(device, (R, 2)); p2 = lib.DeviceBuffer(device, (R, 2))
+    itr = lib.DeviceBuffer(device, (R,), np.int32); sr = lib.DeviceBuffer(device, (R,), np.int32)
+    s.step_raw(True, R, K, 0.0, DT, dq0, dp0, du, None, None, None, q2, p2, None, itr, sr, sample_every=1, traj_q=tq, traj_p=tp)
+    lib.synchronize(device)
+    n, ntot = R * (K - 1), Rtot * (K - 1)
+    rowA, rowB = 128, 32
+    A = lib.DeviceBuffer(device, (n, 4, 4)); Bm = lib.DeviceBuffer(device, (n, 4, 1))
+    it = lib.DeviceBuffer(device, (n,), np.int32); st = lib.DeviceBuffer(device, (n,), np.int32)
+
+    def lin(Ao, Bo):
+        s.linearize_raw(True, n, tq, tp, du_lin, None, st, t1_scalar=0.0, dt_scalar=DT, q2_guess=Off(tq.data_ptr() + 16),
+                        iters=it, A=Ao, B=Bo, traj_len=K)
+        lib.synchronize(device)
+        return s.last_kernel_ms()
+    ms = [lin(A, Bm) for _ in range(3)][1:]
+    group.barrier()
+    t_lin = reduce_max(float(np.mean(ms)))
+    ok = float((st.download() == 0).mean())
+    # (a) NCCL: grouped ncclSend / ncclRecv of the finished slabs to rank 0 (equal blocks: 4096 % world == 0)
+    fullA = lib.DeviceBuffer(device, (ntot, 4, 4)) if rank == 0 else None
+    fullB = lib.DeviceBuffer(device, (ntot, 4, 1)) if rank == 0 else None
+    tg = []
+    for rep in range(3):
+        group.barrier()
+        with lib.EventTimer(device) as tm:
+            group.comm.gather(A, fullA, n * rowA, 0)
+            group.comm.gather(Bm, fullB, n * rowB, 0)
+        tg.append(tm.ms)
+    t_gather = reduce_max(float(np.mean(tg[1:])))
+    check = None
+    if rank == 0:
+        # the first block of the gathered slab is rank 0's own: bitwise equal to its local slab
+        a0 = A.download()[:1000]
+        check = bool(np.array_equal(fullA.download()[:1000], a0))
+    # (b) fused: rank 0's slab mapped into every rank, the linearize kernel stores straight into it
+    if fullA is not None:
+        fullA.free(); fullB.free()
+    slab = D_.SharedSlab(device, group.exchange, ntot * (rowA + rowB))
+    offB = ntot * rowA
+    first = lo * (K - 1)
+    group.barrier()
+    ms = []
+    for rep in range(3):
+        group.barrier()
+        ms.append(lin(slab.at(first * rowA), slab.at(offB + first * rowB)))
+    group.barrier()
+    t_fused = reduce_max(float(np.mean(ms[1:])))
+    fused_ok = None
+    if rank == 0:
+        raw = slab.local.download()
+        fused_ok = bool(np.array_equal(raw[:1000 * rowA].view(np.float64).reshape(1000, 4, 4), a0))
+        last = raw[(ntot - 1) * rowA:ntot * rowA].view(np.float64)
+        fused_ok = fused_ok and bool(np.all(np.isfinite(last)) and np.any(last != 0))
+    group.barrier()
+    slab.close()
+    moved = (rowA + rowB) * float(ntot) * (world - 1) / world      # bytes that cross NVLink into rank 0
+    out.append({"metric": "linearizations/s (W3 sharded over %d GPUs: 4096 rollouts x 10000 steps block-partitioned by rollout, exact hints)" % world,
+                "value": ntot / t_lin * 1e3, "unit": "linearizations/s", "batch_total": ntot, "ms": t_lin, "scaling": "strong",
+                "ok_fraction_rank0": ok,
+                "gather_nccl": {"what": "A / B slabs of every rank collected on rank 0: trepb_comm_gather_dev (grouped ncclSend / ncclRecv), "
+                                        "device to device", "ms": t_gather, "bytes_into_rank0": moved,
+                                "nvlink_GBps_into_rank0": moved / t_gather / 1e6, "first_block_bitwise_equal": check,
+                                "linearize_plus_gather_per_s": ntot / (t_lin + t_gather) * 1e3},
+                "gather_fused": {"what": "rank 0's slab mapped into every rank (trepb_ipc_open); the linearize kernel's own stores deliver "
+                                         "A / B over NVLink - no second pass", "ms": t_fused,
+                                 "linearizations_per_s_delivered_to_rank0": ntot / t_fused * 1e3,
+                                 "nvlink_GBps_into_rank0": moved / t_fused / 1e6, "slab_checked": fused_ok}})
+    for b in (du, du_lin, dq0, dp0, tq, tp, q2, p2, itr, sr, A, Bm, it, st):
+        b.free()
+    s.close()
+    # ---- W5 marionette linearizations/s, weak scaling (131072 instances per GPU)
+    d = systems.named_desc("puppet")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "puppet.npz"))
+    s = lib.System(d, device=device)
+    rng = np.random.default_rng(50 + rank)
+    B = 131072
+    idx = rng.integers(1, 58, B)
+    q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx].copy()
+    q1[:, :d.nd] += rng.normal(0, 0.02, (B, d.nd)); p1 += rng.normal(0, 0.02, (B, d.nd))
+    dq, dp, dk, dl = up(q1), up(p1), up(g["roll_k2"][idx]), up(g["roll_lambda"][idx - 1])
+    it = lib.DeviceBuffer(device, (B,), np.int32); st = lib.DeviceBuffer(device, (B,), np.int32)
+    A = lib.DeviceBuffer(device, (B, d.nX, d.nX)); Bm = lib.DeviceBuffer(device, (B, d.nX, d.nU))
+    ms = []
+    for rep in range(3):
+        s.linearize_raw(True, B, dq, dp, None, dk, st, t1_scalar=0.0, dt_scalar=DT, lambda_guess=dl, iters=it, A=A, B=Bm)
+        lib.synchronize(device)
+        ms.append(s.last_kernel_ms())
+    t = reduce_max(float(np.mean(ms[1:])))
+    out.append({"metric": "linearizations/s (W5 marionette nd22/nk18/nc6 on %d GPUs, %d instances per GPU, weak scaling)" % (world, B),
+                "value": float(B) * world / t * 1e3, "unit": "linearizations/s", "ms": t, "kernel": s.kernel_name,
+                "ok_fraction_rank0": float((st.download() == 0).mean()), "newton_iters_mean": float(it.download().mean())})
+    for b in (dq, dp, dk, dl, it, st, A, Bm):
+        b.free()
+    s.close()
+    out.append(w4_full(lib, systems, device, world, reduce_max, fp64_peak))
     return out
 
 
@@ -612,6 +835,14 @@ def main():
             dist.barrier()
         lib.synchronize(device)
 
+    def reduce_max(x):
+        if dist is None:
+            return float(x)
+        import torch
+        t = torch.tensor([float(x)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
     for _ in range(args.warmup):
         one_step()
     fp64_peak = lib.measure_fp64_peak(device)
@@ -653,6 +884,19 @@ def main():
     units = float(BATCH) * NSTEPS * args.steps * world
     value = units / (total_ms * 1e-3)
     e2e_value = units / (e2e_ms * 1e-3)
+    multi = None
+    if world > 1 and not args.no_secondary:
+        # data plane of the library itself (NCCL / peer-mapped slabs through the C ABI); torch.distributed only
+        # hands round the 128-byte id and the IPC handles
+        from trep_b200 import dist as D_
+        for b in (dq0, dq1, dp, q2, p2, it, st, flush):
+            b.free()
+        group = D_.Group(device=device, exchange=D_.TorchExchange(dist))
+        hbm_peak_ = 6451.2
+        mp_ = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(mp_):
+            hbm_peak_ = json.load(open(mp_)).get("hbm_gbs", hbm_peak_)
+        multi = multi_gpu(lib, systems, group, device, rank, world, reduce_max, fp64_peak, hbm_peak_)
 
     if rank == 0:
         flops_per_step = None
@@ -692,6 +936,9 @@ def main():
         }
         if world == 1 and not args.no_secondary:
             line["secondary"] = secondary(lib, systems, device, fp64_peak, hbm_peak)
+            line["secondary"].append(w4_full(lib, systems, device, 1, float, fp64_peak))
+        if multi is not None:
+            line["secondary"] = multi
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line))
