@@ -336,6 +336,34 @@ class DSystem:
             raise ConvergenceError("%d of %d instances failed" % (bad.size, n), out["status"])
         return out["fdxdx"], out["fdxdu"], out["fdudu"]
 
+    def calc_newton_model(self, X, U, A, B, K, l_dx, l_du, m_dx):
+        """The dynamics' part of DOptimizer.calc_newton_model (doptimizer.py:319-345) for one trajectory or a
+        batch of rollouts sharing `time`: the backward adjoint recursion
+            z[n] = m_dx,   z[k] = l_dx[k] - l_du[k] K[k] + z[k+1] (A[k] - B[k] K[k])
+        (n matrix-vector products per rollout, on the host) and then ONE launch of the z-contracted
+        second-derivative kernel over every step of every rollout (step k contracts with z[k+1]).
+        X [.., n+1, nX], U [.., n, nU], A / B / K per step, l_dx [.., n, nX], l_du [.., n, nU], m_dx [.., nX].
+        Returns (z [.., n+1, nX], fdxdx [.., n, nX, nX], fdxdu [.., n, nX, nU], fdudu [.., n, nU, nU]): add the cost's
+        own second derivatives to obtain Q(k), S(k), R(k)."""
+        X, U = np.asarray(X, float), np.asarray(U, float)
+        single = X.ndim == 2
+        f = (lambda a: np.asarray(a, float)[None]) if single else (lambda a: np.asarray(a, float))
+        X, U, A, B, K, l_dx, l_du, m_dx = (f(a) for a in (X, U, A, B, K, l_dx, l_du, m_dx))
+        R, n = X.shape[0], X.shape[1] - 1
+        Z = np.zeros((R, n + 1, self._nX))
+        Z[:, n] = m_dx
+        for k in reversed(range(n)):
+            Acl = A[:, k] - np.einsum("rxu,ruy->rxy", B[:, k], K[:, k])
+            Z[:, k] = l_dx[:, k] - np.einsum("ru,rux->rx", l_du[:, k], K[:, k]) + np.einsum("rx,rxy->ry", Z[:, k + 1], Acl)
+        t1, t2 = np.tile(self._time[:n], R), np.tile(self._time[1:n + 1], R)
+        xx, xu, uu = self.second_derivatives(X[:, :n].reshape(R * n, -1), U[:, :n].reshape(R * n, -1),
+                                             Z[:, 1:].reshape(R * n, -1), t1, t2, X_hint=X[:, 1:].reshape(R * n, -1))
+        xx = xx.reshape(R, n, self._nX, self._nX); xu = xu.reshape(R, n, self._nX, self._nU)
+        uu = uu.reshape(R, n, self._nU, self._nU)
+        if single:
+            return Z[0], xx[0], xu[0], uu[0]
+        return Z, xx, xu, uu
+
     def linearize_trajectory(self, X, U, group=None, gather="nccl", everywhere=False):
         """Linearization about a trajectory (dsystem.py:406-423).  X [K+1, nX], U [K, nU] for one
         trajectory or X [R, K+1, nX], U [R, K, nU] for R rollouts sharing `time`.
