@@ -127,12 +127,15 @@ typedef struct trepb_system trepb_system; /* opaque */
                                        systems use) instead of one dual evaluation of the Jacobian tables
                                        per parameter followed by a contraction */
 
+#define TREPB_FLAG_NO_LITERAL 16     /* specialised systems: skip an all-literal instantiation built for exactly this
+                                       description and use the run-time-parameter kernel of its structure */
+
 int  trepb_abi_version(void);
 const char* trepb_last_error(void);
 
-/* Validate + flatten + upload tables to `device`.  If the description's structural hash matches
- * one of the systems specialised ahead of time (generated constexpr system, fully unrolled,
- * register-resident; see trepb_codegen) that kernel set is used, otherwise the table-driven
+/* Validate + flatten + upload tables to `device`.  If the description's structure (trepb_struct_hash)
+ * matches one of the systems specialised ahead of time (generated constexpr structure, fully unrolled,
+ * register-resident, parameters at run time; see trepb_codegen) that kernel set is used, otherwise the table-driven
  * kernels: one thread per instance for small systems, the cooperative kernels (one warp per
  * instance, link tables and workspace in shared memory) when the per-instance workspace is too
  * large to stay on chip (e.g. the marionette). */
@@ -153,7 +156,15 @@ int  trepb_kernel_info(trepb_system* sys, int which, int32_t* regs, int32_t* loc
  * invalid description); structural hash used to match specialised kernels. */
 int  trepb_validate(const trepb_sysdesc* desc);
 int  trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap);
-uint64_t trepb_desc_hash(const trepb_sysdesc* desc);
+/* The same with every number of this one description as a literal (no run-time parameters; matched by
+ * trepb_desc_hash): a few percent faster, built for the systems BASELINE.json's configs name exactly. */
+int  trepb_codegen_literal(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap);
+uint64_t trepb_desc_hash(const trepb_sysdesc* desc);     /* the whole description, parameters included */
+/* Hash of the STRUCTURE only: sizes, topology, plugin kinds and index arguments, and which numeric entries are
+ * exactly zero.  Specialised kernels are compiled per structure; masses, inertias, lengths, gravity, spring /
+ * damping constants, tolerances and spline tables are run-time parameters handed to the kernel as an argument
+ * block, so e.g. a damped pendulum with any mass and length runs the kernel built for examples/damped-pendulum.py. */
+uint64_t trepb_struct_hash(const trepb_sysdesc* desc);
 /* Host-only: the shape the cooperative kernels see for this system, out[10] = nd, nk, nu, nc,
  * links (variable frames), constraint end points, chain pairs, link-tree levels, dynamic configs
  * and configs that some constraint depends on.  A cooperative

@@ -205,3 +205,42 @@ def test_one_handle_on_two_streams_keeps_its_scratch_consistent(lib):
         assert np.array_equal(outs[j][0].download(), want["A"])
     for x in st:
         cudart.cudaStreamDestroy(x)
+
+
+def test_specialised_kernels_take_parameters_at_run_time(lib, ref):
+    """Structure is compiled in, numbers are kernel arguments: damped pendulums with other masses, lengths,
+    pivots, gravity and damping run the kernel built for examples/damped-pendulum.py (not the table-driven
+    fallback) and match the reference built with the same numbers."""
+    from trep_b200 import model as M
+    trep = ref.trep
+    rng = np.random.default_rng(77)
+    for m, l, y0, grav, c in ((1.0, 3.0, 3.0, -9.8, 1.2), (2.0, 5.0, 1.0, -9.8, 1.2), (0.3, 0.7, -2.0, -1.62, 0.05),
+                              (7.5, 2.2, 4.0, -24.8, 3.3)):
+        s = M.System(name="damped_pendulum")
+        s.import_frames([M.ty(y0), M.rx("theta"), [M.tz(-l, mass=m)]])
+        M.Gravity(s, (0, 0, grav))
+        M.Damping(s, c)
+        h = lib.System(s.describe())
+        assert h.specialized and h.kernel_name == "damped_pendulum"
+        rs = trep.System()
+        rs.import_frames([trep.ty(y0), trep.rx("theta"), [trep.tz(-l, mass=m)]])
+        trep.potentials.Gravity(rs, (0, 0, grav))
+        trep.forces.Damping(rs, c)
+        mvi = trep.MidpointVI(rs, num_threads=1)
+        B = 64
+        q1 = rng.uniform(-3, 3, (B, 1)); p1 = rng.normal(0, 2 * m * l * l, (B, 1))
+        want = ref.run_cases(mvi, 0.0, 0.01, q1, p1, np.zeros((B, 0)), np.zeros((B, 0)))
+        got = h.linearize(q1, p1, t1=0.0, t2=0.01)
+        assert np.array_equal(got["status"], want["status"]) and np.array_equal(got["iters"], want["iters"])
+        for k in ("q2", "p2", "A"):
+            G.assert_close(got[k], want[k], "m=%g l=%g %s" % (m, l, k))
+        # second derivatives through the specialised per-pair kernel
+        mvi.initialize_from_state(0.0, q1[0], p1[0]); mvi.step(0.01); mvi._calc_deriv2()
+        d2 = h.deriv2(q1[:1], p1[:1], t1=0.0, t2=0.01)
+        G.assert_close(d2["q2_dq1dq1"][0], np.array(mvi._q2_dq1dq1), "m=%g l=%g q2_dq1dq1" % (m, l))
+        G.assert_close(d2["p2_dq1dp1"][0], np.array(mvi._p2_dq1dp1), "m=%g l=%g p2_dq1dp1" % (m, l))
+    # a structural change (a rotational inertia on the bob) is another kernel: table-driven here
+    s = M.System()
+    s.import_frames([M.ty(3), M.rx("theta"), [M.tz(-3, mass=(1.0, 0.2, 0.0, 0.0))]])
+    M.Gravity(s, (0, 0, -9.8)); M.Damping(s, 1.2)
+    assert not lib.System(s.describe()).specialized

@@ -48,6 +48,9 @@ def _systems(lib, name):
     s = lib.System(d)
     if s.specialized:
         out.append(("spec", s))
+        # the instantiation with run-time parameters (for four systems lib.System picks the all-literal one)
+        out.append(("spec-param", lib.System(d, literal=False)))
+        assert out[-1][1].specialized
     out.append(("general", lib.System(d, specialize=False, cooperative=False)))
     if name not in COOP_UNSUPPORTED:
         c = lib.System(d, specialize=False, cooperative=True)

@@ -54,12 +54,18 @@ def test_specialised_registry_and_codegen():
         assert n in names
     text, h = build.codegen(G.desc("pend_on_cart1"))
     assert "struct CtSys" in text and "kND = 2" in text and "kNU = 1" in text
-    assert ("0x%016x" % h) in text
-    assert h == lib.desc_hash(G.desc("pend_on_cart1"))
-    # a parameter change is a different specialisation
+    assert h == lib.struct_hash(G.desc("pend_on_cart1")) and ("0x%016x" % h) in text
+    # structure is compiled in, numbers are run-time parameters (slots of the kernel's argument block):
+    # another cart mass is the SAME specialisation, another description (desc_hash) ...
+    assert "par.v[" in text and "kNPAR" in text and "10.0" not in text
     s = systems.pend_on_cart()
     s.world_frame.children[0].set_mass(11.0)
-    assert lib.desc_hash(s.describe()) != h
+    assert lib.struct_hash(s.describe()) == h
+    assert lib.desc_hash(s.describe()) != lib.desc_hash(G.desc("pend_on_cart1"))
+    # ... while a change of structure is not: a rotational inertia where there was none, one more input
+    s.world_frame.children[0].set_mass(10.0, 0.3, 0.0, 0.0)
+    assert lib.struct_hash(s.describe()) != h
+    assert lib.struct_hash(G.desc("pend_on_cart2")) != h
 
 
 def test_cooperative_shapes_and_generated_instantiation():

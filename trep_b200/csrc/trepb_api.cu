@@ -6,6 +6,7 @@
 #include <string.h>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include "../../include/trepb.h"
 #include "trepb_codegen.h"
@@ -67,6 +68,7 @@ struct trepb_system {
     char* dblob = nullptr;
     int blob_bytes = 0;
     const KernelSet* ks = nullptr;
+    std::vector<double> spec_params;   // run-time parameters of the specialised kernels (param_map order)
     int sms = 0;
     int block = 128;
     int bps[4] = {1, 1, 1, 1};   // resident CTAs per SM for step / p2 / lin / project
@@ -160,10 +162,21 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
     // kernel selection
     s->ks = general_kernels();
     if (!(flags & (TREPB_FLAG_NO_SPECIALIZE | TREPB_FLAG_FORCE_COOP))) {
-        const unsigned long long h = desc_hash(s->P);
+        // an instantiation for exactly this description (every number a literal) if the build made one ...
         SpecRegistry& r = spec_registry();
+        const unsigned long long hd = desc_hash(s->P);
         for (int i = 0; i < r.n; ++i)
-            if (r.sets[i]->hash == h) { s->ks = r.sets[i]; break; }
+            if (r.sets[i]->hash == hd && r.sets[i]->n_params == 0 && !(flags & TREPB_FLAG_NO_LITERAL)) { s->ks = r.sets[i]; break; }
+        // ... else structure picks the kernel and the numbers travel as its run-time parameters
+        const unsigned long long h = struct_hash(s->P);
+        for (int i = 0; i < r.n && !s->ks->specialized; ++i)
+            if (r.sets[i]->hash == h) {
+                ParamMap pm = param_map(s->P);
+                if ((int)pm.values.size() != r.sets[i]->n_params) continue;   // cannot happen for equal structures
+                s->ks = r.sets[i];
+                s->spec_params = std::move(pm.values);
+                break;
+            }
     }
     const RtSys& ps = s->P.proto;
     s->ws_doubles = s->wsl.layout(ps.nf, ps.nd, ps.nk, ps.nu, ps.nc);
@@ -349,6 +362,7 @@ int make_cfg(trepb_system* s, int which, long long batch, int bps, size_t smem, 
     c->ws = s->wsl;
     c->ws.base = (double*)s->ws.p;
     c->ws.stride = 0;
+    c->spec_params = s->spec_params.empty() ? nullptr : s->spec_params.data();
     return TREPB_OK;
 }
 
@@ -660,6 +674,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         WsStridedT<Dual> wd = s->wsl_du;
         wd.base = (Dual*)s->ws_du.p; wd.stride = 0;
         LaunchCfg c;
+        c.spec_params = nullptr;
         c.block = block; c.smem = d2jac_smem(s->blob_bytes, block, nd, nk); c.stream = stream;
         c.sys = &s->dview; c.dblob = s->dblob; c.blob_bytes = s->blob_bytes; c.ws = s->wsl;
         Timed t(s, stream);
@@ -692,6 +707,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         w.base = (HDG*)s->ws_hd.p;
     } else if (grid > 0x7fffffffLL) grid = 0x7fffffffLL;
     LaunchCfg c;
+    c.spec_params = s->spec_params.empty() ? nullptr : s->spec_params.data();
     c.grid = (int)grid; c.block = block; c.smem = smem; c.stream = stream;
     c.sys = s->ks->specialized ? nullptr : &s->dview;
     c.dblob = s->dblob; c.blob_bytes = s->blob_bytes; c.ws = s->wsl;

@@ -14,11 +14,11 @@ using namespace trepb;
 
 extern "C" {
 
-int trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap) {
+static int codegen_impl(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap, bool literal) {
     PackedSys P;
     std::string err;
     if (!pack_system(desc, &P, &err)) { last_error() = err; return -1; }
-    const std::string text = codegen_system(P, struct_name && *struct_name ? struct_name : "CtSys");
+    const std::string text = codegen_system(P, struct_name && *struct_name ? struct_name : "CtSys", literal);
     const int need = (int)text.size() + 1;
     if (buf && cap > 0) {
         const int n = need <= cap ? need - 1 : cap - 1;
@@ -28,11 +28,25 @@ int trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf,
     return need;
 }
 
+int trepb_codegen(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap) {
+    return codegen_impl(desc, struct_name, buf, cap, false);
+}
+int trepb_codegen_literal(const trepb_sysdesc* desc, const char* struct_name, char* buf, int cap) {
+    return codegen_impl(desc, struct_name, buf, cap, true);
+}
+
 uint64_t trepb_desc_hash(const trepb_sysdesc* desc) {
     PackedSys P;
     std::string err;
     if (!pack_system(desc, &P, &err)) { last_error() = err; return 0; }
     return desc_hash(P);
+}
+
+uint64_t trepb_struct_hash(const trepb_sysdesc* desc) {
+    PackedSys P;
+    std::string err;
+    if (!pack_system(desc, &P, &err)) { last_error() = err; return 0; }
+    return struct_hash(P);
 }
 
 int trepb_coop_dims(const trepb_sysdesc* desc, int32_t* out) {

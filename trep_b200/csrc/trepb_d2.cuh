@@ -213,14 +213,15 @@ template <class Sys>
 struct CtxHD<Sys, true> {
     Sys sys;
     WsStatic<Sys, HD> ws;
-    __device__ __forceinline__ CtxHD(const RtSys&, const char*, int, const WsStridedT<HDG>&, long, long) {}
+    __device__ __forceinline__ CtxHD(const RtSys&, const char*, int, const WsStridedT<HDG>&, long, long,
+                                     const typename Sys::Params& par) { sys.par = par; }
 };
 template <class Sys>
 struct CtxHD<Sys, false> {
     RtSys sys;
     WsStridedT<HDG> ws;
     __device__ __forceinline__ CtxHD(const RtSys& s, const char* dblob, int blob_bytes, const WsStridedT<HDG>& w,
-                                     long tid, long nthreads) {
+                                     long tid, long nthreads, const typename Sys::Params&) {
         extern __shared__ double smem_[];
         const int n8 = (blob_bytes + 7) / 8;
         const double* src = (const double*)dblob;
@@ -235,10 +236,11 @@ struct CtxHD<Sys, false> {
 
 template <class Sys>
 __global__ void __launch_bounds__(128)
-d2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<HDG> wsp, const D2Params p) {
+d2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStridedT<HDG> wsp, const D2Params p,
+          const typename Sys::Params par) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
-    CtxHD<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    CtxHD<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth, par);
     auto& sys = c.sys;
     auto& ws = c.ws;
     using Ws = typename std::remove_reference<decltype(ws)>::type;
@@ -273,7 +275,7 @@ struct LaunchersD2 {
             cudaError_t e = cudaFuncSetAttribute((const void*)d2_kernel<Sys>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)c.smem);
             if (e != cudaSuccess) return e;
         }
-        d2_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, w, p);
+        d2_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, w, p, Launchers<Sys>::spec_params(c));
         return cudaGetLastError();
     }
     static cudaError_t occupancy(int block, size_t smem, int* blocks_per_sm, KernelInfo* info) {

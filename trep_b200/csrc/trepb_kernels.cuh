@@ -117,6 +117,7 @@ struct LaunchCfg {
     const char* dblob;      // device address of the packed blob
     int blob_bytes;
     WsStrided ws;           // workspace slab view (general path)
+    const double* spec_params;   // host: run-time parameters of a specialised system (trepb::param_map order)
 };
 
 struct KernelInfo {
@@ -129,6 +130,7 @@ struct KernelSet {
     unsigned long long hash;  // 0: general
     int specialized;
     int nX, nU;
+    int n_params;            // specialised: number of run-time parameters the kernels take (param_map order)
     cudaError_t (*step)(const LaunchCfg&, const StepParams&);
     cudaError_t (*p2)(const LaunchCfg&, const P2Params&);
     cudaError_t (*lin)(const LaunchCfg&, const LinParams&);
@@ -211,7 +213,8 @@ struct Ctx<Sys, true> {
     using WsT = WsStatic<Sys>;
     Sys sys;
     WsT ws;
-    __device__ __forceinline__ Ctx(const RtSys&, const char*, int, const WsStrided&, long, long) {}
+    __device__ __forceinline__ Ctx(const RtSys&, const char*, int, const WsStrided&, long, long,
+                                   const typename Sys::Params& par) { sys.par = par; }
 };
 
 // general: tables staged in shared memory, strided workspace
@@ -221,7 +224,7 @@ struct Ctx<Sys, false> {
     RtSys sys;
     WsT ws;
     __device__ __forceinline__ Ctx(const RtSys& s, const char* dblob, int blob_bytes, const WsStrided& w,
-                                   long tid, long nthreads) {
+                                   long tid, long nthreads, const typename Sys::Params&) {
         extern __shared__ double smem_[];
         const int n8 = (blob_bytes + 7) / 8;
         const double* src = (const double*)dblob;
@@ -236,10 +239,11 @@ struct Ctx<Sys, false> {
 
 template <class Sys>
 __global__ void __launch_bounds__(128, lb_min<Sys>())
-step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const StepParams p) {
+step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const StepParams p,
+            const typename Sys::Params par) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
-    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth, par);
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
@@ -306,10 +310,11 @@ step_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided
 // (trep/discopt/dsystem.py:426-457), one thread per candidate, the feedback inside the time loop.
 template <class Sys>
 __global__ void __launch_bounds__(128, lb_min<Sys>())
-project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const ProjParams p) {
+project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const ProjParams p,
+            const typename Sys::Params par) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
-    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth, par);
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
@@ -369,10 +374,11 @@ project_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStri
 
 template <class Sys>
 __global__ void __launch_bounds__(128)
-p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const P2Params p) {
+p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const P2Params p,
+            const typename Sys::Params par) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
-    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth, par);
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nq = sys.NQ(), nu = sys.NU(), nc = sys.NC();
@@ -404,10 +410,11 @@ p2_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided w
 
 template <class Sys>
 __global__ void __launch_bounds__(128, lb_min<Sys, true>())
-lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p) {
+lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided wsp, const LinParams p,
+            const typename Sys::Params par) {
     const long tid = (long)blockIdx.x * blockDim.x + threadIdx.x;
     const long nth = (long)gridDim.x * blockDim.x;
-    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth);
+    Ctx<Sys> c(rsys, dblob, blob_bytes, wsp, tid, nth, par);
     auto& sys = c.sys;
     auto& ws = c.ws;
     const int nd = sys.ND(), nk = sys.NK(), nq = nd + nk, nu = sys.NU(), nc = sys.NC();
@@ -509,6 +516,12 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
 // ---------------------------------------------------------------------------------------------
 template <class Sys>
 struct Launchers {
+    static typename Sys::Params spec_params(const LaunchCfg& c) {
+        typename Sys::Params P{};
+        if (Sys::kNPAR > 0 && c.spec_params)
+            for (int i = 0; i < Sys::kNPAR; ++i) P.v[i] = c.spec_params[i];
+        return P;
+    }
     static cudaError_t prep(const void* fn, size_t smem) {
         if (smem > 48 * 1024)
             return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -519,7 +532,7 @@ struct Launchers {
         if (c.sys) rs = *c.sys;
         cudaError_t e = prep((const void*)step_kernel<Sys>, c.smem);
         if (e != cudaSuccess) return e;
-        step_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        step_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p, spec_params(c));
         return cudaGetLastError();
     }
     static cudaError_t p2(const LaunchCfg& c, const P2Params& p) {
@@ -527,7 +540,7 @@ struct Launchers {
         if (c.sys) rs = *c.sys;
         cudaError_t e = prep((const void*)p2_kernel<Sys>, c.smem);
         if (e != cudaSuccess) return e;
-        p2_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        p2_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p, spec_params(c));
         return cudaGetLastError();
     }
     static cudaError_t lin(const LaunchCfg& c, const LinParams& p) {
@@ -535,7 +548,7 @@ struct Launchers {
         if (c.sys) rs = *c.sys;
         cudaError_t e = prep((const void*)lin_kernel<Sys>, c.smem);
         if (e != cudaSuccess) return e;
-        lin_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        lin_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p, spec_params(c));
         return cudaGetLastError();
     }
     static cudaError_t proj(const LaunchCfg& c, const ProjParams& p) {
@@ -543,7 +556,7 @@ struct Launchers {
         if (c.sys) rs = *c.sys;
         cudaError_t e = prep((const void*)project_kernel<Sys>, c.smem);
         if (e != cudaSuccess) return e;
-        project_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p);
+        project_kernel<Sys><<<c.grid, c.block, c.smem, c.stream>>>(rs, c.dblob, c.blob_bytes, c.ws, p, spec_params(c));
         return cudaGetLastError();
     }
     // which: 0 step, 1 p2, 2 lin, 3 project
@@ -576,6 +589,7 @@ template <class Sys>
 KernelSet make_kernelset(const char* name, unsigned long long hash, int specialized, int nX, int nU) {
     KernelSet k;
     k.name = name; k.hash = hash; k.specialized = specialized; k.nX = nX; k.nU = nU;
+    k.n_params = Sys::kNPAR;
     k.step = &Launchers<Sys>::step;
     k.p2 = &Launchers<Sys>::p2;
     k.lin = &Launchers<Sys>::lin;

@@ -54,6 +54,8 @@ struct RtSys {
 
     static constexpr bool kStatic = false;
     static constexpr int kUnroll = 1;   // system-sized loops stay rolled (see TREPB_UNROLL_SYS)
+    static constexpr int kNPAR = 0;
+    struct Params { double v[1]; };     // a generated compile-time system takes its parameters here; unused
     TREPB_HD int MAXDEPTH() const { return max_depth; }
     TREPB_HD int NF() const { return nf; }
     TREPB_HD int ND() const { return nd; }

@@ -87,6 +87,7 @@ _lib.trepb_last_error.restype = C.c_char_p
 _lib.trepb_system_kernel_name.restype = C.c_char_p
 _lib.trepb_specialized_name.restype = C.c_char_p
 _lib.trepb_desc_hash.restype = C.c_uint64
+_lib.trepb_struct_hash.restype = C.c_uint64
 _lib.trepb_system_create.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
 _lib.trepb_system_destroy.argtypes = [C.c_void_p]
 _lib.trepb_system_destroy.restype = None
@@ -144,7 +145,7 @@ _lib.trepb_sincos_batch.argtypes = [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, 
 EXPORTS = [
     "trepb_abi_version", "trepb_last_error", "trepb_system_create", "trepb_system_destroy",
     "trepb_system_dims", "trepb_system_is_specialized", "trepb_system_is_cooperative", "trepb_system_kernel_name",
-    "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_desc_hash", "trepb_coop_dims",
+    "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_codegen_literal", "trepb_desc_hash", "trepb_struct_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_calc_f_batch", "trepb_calc_f_batch_dev",
     "trepb_discrete_fm2_batch", "trepb_discrete_fm2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_linearize_batch",
@@ -258,6 +259,12 @@ def specialized_names():
 def desc_hash(desc):
     cd, keep = D.to_c(desc)
     return int(_lib.trepb_desc_hash(C.byref(cd)))
+
+
+def struct_hash(desc):
+    """Hash of the structure only (what a specialised kernel is compiled for); see include/trepb.h."""
+    cd, keep = D.to_c(desc)
+    return int(_lib.trepb_struct_hash(C.byref(cd)))
 
 
 def validate(desc):
@@ -376,7 +383,7 @@ def _ptr(x):
 class System:
     """Handle of a flattened system resident on one GPU (trepb_system)."""
 
-    def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None, d2_pairwise=False):
+    def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None, d2_pairwise=False, literal=True):
         """specialize=False: skip the ahead-of-time specialised kernels.  cooperative: None = let
         the library choose between one thread and one warp per instance for a table-driven system,
         False = always one thread, True = always the cooperative kernels (their compile-time-size
@@ -394,6 +401,8 @@ class System:
             flags |= 4
         if d2_pairwise:
             flags |= 8
+        if not literal:
+            flags |= 16     # skip an all-literal instantiation: the run-time-parameter kernel of the structure
         _check(_lib.trepb_system_create(C.byref(cd), device, flags, C.byref(h)))
         self._h = h
         self.nq, self.nd, self.nk, self.nu, self.nc = desc.nq, desc.nd, desc.nk, desc.nu, desc.nc
