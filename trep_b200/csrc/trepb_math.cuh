@@ -50,6 +50,13 @@ namespace trepb {
 #define TREPB_UNROLL
 #define TREPB_UNROLL_SYS
 #endif
+// for (j = lo; j < n; ++j) with lo depending on an outer loop counter.  The unroller works inner loop
+// first, so at that time such a bound is unknown and a rolled remainder loop stays behind - and with it
+// dynamic indices that push the whole compile-time workspace into local memory.  The compile-time
+// flavour therefore runs over the full range [0, n) and guards the body; the guard folds after unrolling.
+#define TREPB_FOR_FROM(j, lo, n) \
+    TREPB_UNROLL_SYS for (int j = Sys::kStatic ? 0 : (lo); j < (n); ++j) if (!Sys::kStatic || j >= (lo))
+
 
 // Optional phase timing (development builds only: -DTREPB_PHASE_TIMING): clock64 deltas of one
 // lane per warp accumulated into a device array, read back through trepb_phase_ticks().
@@ -727,8 +734,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i) {
                     if (!(sys.dep(A, i) || sys.dep(B, i) || third == i)) continue;
-                    TREPB_UNROLL_SYS
-                    for (int j = i; j < nq; ++j) {
+                    TREPB_FOR_FROM(j, i, nq) {
                         if (!(sys.dep(A, j) || sys.dep(B, j) || third == j)) continue;
                         Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
@@ -768,8 +774,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
                     if (!(sys.dep(A, i) || sys.dep(B, i))) continue;
                     Real dni[3];
                     dnormal(sys, ws, A, i, nw, dni);
-                    TREPB_UNROLL_SYS
-                    for (int j = i; j < nq; ++j) {
+                    TREPB_FOR_FROM(j, i, nq) {
                         if (!(sys.dep(A, j) || sys.dep(B, j))) continue;
                         Real dnj[3], ddn[3], ddv[3];
                         dnormal(sys, ws, A, j, nw, dnj);
@@ -798,8 +803,7 @@ TREPB_HD void constraints_eval(const Sys& sys, Ws& ws, int mode, int which_dh, b
                 const Real lam = ws.lam(c);
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
-                    TREPB_UNROLL_SYS
-                    for (int j = i; j < nq; ++j) {
+                    TREPB_FOR_FROM(j, i, nq) {
                         Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
                         const Real val = lam * ddv[comp];
@@ -863,8 +867,7 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
             if (order >= 2) {
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
-                    TREPB_UNROLL_SYS
-                    for (int j = i; j < nq; ++j) {
+                    TREPB_FOR_FROM(j, i, nq) {
                         if (!(sys.dep(A, i) || sys.dep(B, i)) || !(sys.dep(A, j) || sys.dep(B, j))) continue;
                         Real ddv[3];
                         pair_second(sys, ws, A, B, i, j, ddv);
@@ -1071,18 +1074,23 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, RdAcc rd, 
         double pv = -1.0;
         int pi = 0;
         if constexpr (Sys::kStatic) {
+            // every loop runs over the full compile-time range with the triangle as a guard: a bound that
+            // depends on an outer counter is unknown when the (inner-first) unroller reaches the loop,
+            // which then leaves a rolled remainder loop behind and the matrix in local memory
             TREPB_UNROLL_SYS
-            for (int i = 0; i < j; ++i) {
+            for (int i = 0; i < n; ++i) {
+                if (i >= j) continue;
                 double a = A(i, j);
                 TREPB_UNROLL_SYS
-                for (int k = 0; k < i; ++k) a -= A(i, k) * A(k, j);
+                for (int k = 0; k < n; ++k) if (k < i) a -= A(i, k) * A(k, j);
                 A(i, j) = a;
             }
             TREPB_UNROLL_SYS
-            for (int i = j; i < n; ++i) {
+            for (int i = 0; i < n; ++i) {
+                if (i < j) continue;
                 double a = A(i, j);
                 TREPB_UNROLL_SYS
-                for (int k = 0; k < j; ++k) a -= A(i, k) * A(k, j);
+                for (int k = 0; k < n; ++k) if (k < j) a -= A(i, k) * A(k, j);
                 A(i, j) = a;
                 const double t = fabs(a * scales(i));
                 if (t > pv) { pv = t; pi = i; }
@@ -1132,7 +1140,8 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, RdAcc rd, 
                 // selects with unconditional loads/stores: a branch on (pi == i) would let the
                 // optimiser substitute the dynamic `pi` for the loop counter and index memory
                 TREPB_UNROLL_SYS
-                for (int i = j + 1; i < n; ++i) {
+                for (int i = 0; i < n; ++i) {
+                    if (i <= j) continue;
                     const bool sw = (pi == i);
                     const double pj = piv(j), pi_ = piv(i);
                     piv(j) = sw ? pi_ : pj;
@@ -1154,8 +1163,12 @@ TREPB_HD bool lu_decomp(MatAcc A, int n, PivAcc piv, ScaleAcc scales, RdAcc rd, 
         }
         const double d = A(j, j), r = 1.0 / d;
         rd(j) = r;
-        TREPB_UNROLL_SYS
-        for (int i = j + 1; i < n; ++i) A(i, j) = div_r(A(i, j), d, r);
+        if constexpr (Sys::kStatic) {
+            TREPB_UNROLL_SYS
+            for (int i = 0; i < n; ++i) if (i > j) A(i, j) = div_r(A(i, j), d, r);
+        } else {
+            for (int i = j + 1; i < n; ++i) A(i, j) = div_r(A(i, j), d, r);
+        }
     }
     return true;
 }
@@ -1180,15 +1193,23 @@ TREPB_HD void lu_solve(MatAcc A, int n, PivAcc piv, BAcc b, XAcc x, RdAcc rd = R
         } else {
             t = b((int)piv(i));
         }
-        TREPB_UNROLL_SYS
-        for (int j = 0; j < i; ++j) t -= A(i, j) * x(j);
+        if constexpr (Sys::kStatic) {
+            TREPB_UNROLL_SYS
+            for (int j = 0; j < n; ++j) if (j < i) t -= A(i, j) * x(j);
+        } else {
+            for (int j = 0; j < i; ++j) t -= A(i, j) * x(j);
+        }
         x(i) = t;
     }
     TREPB_UNROLL_SYS
     for (int i = n - 1; i >= 0; --i) {
         double t = x(i);
-        TREPB_UNROLL_SYS
-        for (int j = i + 1; j < n; ++j) t -= A(i, j) * x(j);
+        if constexpr (Sys::kStatic) {
+            TREPB_UNROLL_SYS
+            for (int j = 0; j < n; ++j) if (j > i) t -= A(i, j) * x(j);
+        } else {
+            for (int j = i + 1; j < n; ++j) t -= A(i, j) * x(j);
+        }
         if constexpr (std::is_same<RdAcc, NoRd>::value) t = t / A(i, i);
         else t = div_r(t, A(i, i), rd(i));
         x(i) = t;
