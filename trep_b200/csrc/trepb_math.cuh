@@ -1534,8 +1534,11 @@ TREPB_HD int deriv1(const Sys& sys, Ws& ws, double t1, double t2, const Deriv1Ou
         TREPB_UNROLL_SYS
         for (int kindv = 0; kindv < 4; ++kindv) {
             const int count = kindv == 0 ? nq : (kindv == 1 ? nd : (kindv == 2 ? nu : nk));
+            // full compile-time range + guard (see TREPB_FOR_FROM): count depends on the outer counter
+            const int cmax = nq > nu ? nq : nu;
             TREPB_UNROLL_SYS
-            for (int i = 0; i < count; ++i) {
+            for (int i = 0; i < cmax; ++i) {
+                if (i >= count) continue;
                 // explicit part c
                 TREPB_UNROLL_SYS
                 for (int j = 0; j < nd; ++j) {
