@@ -194,6 +194,10 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
             const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
             int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
             if (warps > 8) warps = 8;
+            if (const char* e = getenv("TREPB_COOP_WARPS")) {   // diagnostic: fewer instances in flight per SM
+                const int w = atoi(e);
+                if (w >= 1 && w < warps) warps = w;
+            }
             const bool wanted = (flags & TREPB_FLAG_FORCE_COOP) || s->ws_doubles > 2048;
             if (warps >= 1 && wanted) {
                 CUS(cudaMalloc((void**)&s->dcoop, blob_d));

@@ -22,6 +22,12 @@ struct Stage {
     double* w;
 };
 
+// The warp's index in its CTA as a value the compiler knows to be the same in all 32 lanes (the result of
+// a broadcast): the workspace base, the instance index and every branch taken on data read from the
+// workspace are then provably warp-uniform, which removes the re-convergence bookkeeping (BSSY / BSYNC,
+// WARPSYNC.COLLECTIVE around every shuffle and reduction) the compiler otherwise emits.
+__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+
 __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, const CoopLayout& lay) {
     extern __shared__ double smem_[];
     const int n8 = (blob_bytes + 7) / 8;
@@ -31,7 +37,7 @@ __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, c
     Stage st;
     st.S = gs;
     st.S.base = (const char*)smem_;
-    st.w = smem_ + ((n8 + 1) & ~1) + (long)(threadIdx.x >> 5) * lay.total;
+    st.w = smem_ + ((n8 + 1) & ~1) + (long)warp_index() * lay.total;
     return st;
 }
 
@@ -48,7 +54,7 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     // the warps of a CTA take every step together (see coop_lin_kernel)
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
-        const long b = b0 + (threadIdx.x >> 5);
+        const long b = b0 + warp_index();
         const bool live = b < p.batch;
         if (live) {
             for (int i = lane; i < nq; i += 32) {
@@ -118,7 +124,7 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
-        const long b = b0 + (threadIdx.x >> 5);
+        const long b = b0 + warp_index();
         const bool live = b < p.batch;
         const double* bX = p.bX + b * (long)(K + 1) * nX;
         const double* bU = p.bU + b * (long)K * nU;
@@ -190,7 +196,7 @@ coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, co
     Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
     const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
     const int nd = c.ND(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
-    for (long b = (long)blockIdx.x * wpc + (threadIdx.x >> 5); b < p.batch; b += (long)gridDim.x * wpc) {
+    for (long b = (long)blockIdx.x * wpc + warp_index(); b < p.batch; b += (long)gridDim.x * wpc) {
         for (int i = lane; i < nq; i += 32) {
             w[lay.q1 + i] = p.q0[b * nq + i];
             w[lay.q2 + i] = p.q1[b * nq + i];
@@ -232,8 +238,9 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     // ~200 KB of SASS, and seven warps drifting through different phases of it miss the instruction
     // cache a third of the time (ncu: "no instruction" stalls 31 % free-running vs 5 % in step); the
     // wait for the slowest Newton iteration count of the round costs less than that.
+#pragma unroll 1
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc, __syncthreads()) {
-        const long b = b0 + (threadIdx.x >> 5);
+        const long b = b0 + warp_index();
         if (b >= p.batch) continue;
         const long r = p.traj_len > 1 ? b + b / (p.traj_len - 1) : b;   // state row (trepb_lin_args.traj_len)
         for (int i = lane; i < nq; i += 32) {

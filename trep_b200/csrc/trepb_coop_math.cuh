@@ -330,6 +330,88 @@ TREPB_HD void reg_solve(const double* A, int ld, const double* rd, double* y) {
     reg_bwd<N, N>(A, ld, rd, y);
 }
 
+#if defined(__CUDACC__)
+// The same factorization as team_lu for compile-time sizes N <= 32, with ONE ROW PER LANE held in
+// registers (N + NX doubles): no shared-memory traffic and no __syncwarp inside the factorization.
+// Rows are never moved: every lane keeps its row, its implicit scale and the POSITION its row would
+// occupy after the reference's row exchanges (math-code.c:337-432); the pivot of step k is the largest
+// |a_ik| scale_i over the rows at positions >= k, ties to the lowest position (= the first strict
+// maximum of the reference's scan), the row that sat at position k takes the pivot row's old position.
+// Step k broadcasts the pivot row by shuffles; arithmetic per element is team_lu's:
+// a_ij -= m_ik (rd_k a_kj) with the unscaled multiplier m_ik left in place.
+template <int N, int NX>
+struct RowLU {
+    static constexpr unsigned kFull = 0xffffffffu;
+    double a[N + NX];
+    double scl, rdp;
+    int pos;
+    __device__ __forceinline__ void load(const double* A, int ld, int lane) {
+        pos = lane < N ? lane : 255;
+        const double* row = A + (lane < N ? lane : 0) * ld;
+        double s = -1.0;
+#pragma unroll
+        for (int j = 0; j < N + NX; ++j) {
+            a[j] = row[j];
+            if (j < N) { const double v = fabs(a[j]); if (v > s) s = v; }
+        }
+        scl = 1.0 / s;
+        rdp = 0.0;
+    }
+    __device__ __forceinline__ bool factor(double tol) {
+#pragma unroll
+        for (int k = 0; k < N; ++k) {
+            const bool act = pos >= k && pos < N;
+            double v = act ? fabs(a[k] * scl) : 0.0;
+            if (!(v == v)) v = 0.0;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+            const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+            const unsigned mh = __reduce_max_sync(kFull, hi);
+            const unsigned ml = __reduce_max_sync(kFull, hi == mh ? lo : 0u);
+            const bool ismax = act && hi == mh && lo == ml;
+            const unsigned bpos = __reduce_min_sync(kFull, ismax ? (unsigned)pos : 255u);
+            const double best = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+            if (!(best > tol)) return false;
+            const bool isp = ismax && (unsigned)pos == bpos;
+            const int pl = __ffs(__ballot_sync(kFull, isp)) - 1;
+            if (pos == k) pos = (int)bpos;
+            if (isp) pos = k;
+            const double rdk = 1.0 / __shfl_sync(kFull, a[k], pl);
+            if (isp) rdp = rdk;
+            // rows already used as pivots (and idle lanes) take a zero multiplier: an unconditional
+            // fused multiply-add instead of a select per updated element
+            const double m = (pos > k && pos < N) ? a[k] : 0.0;
+#pragma unroll
+            for (int j = 0; j < N + NX; ++j) {
+                if (j <= k) continue;
+                const double akj = __shfl_sync(kFull, a[j], pl) * rdk;
+                a[j] -= m * akj;
+            }
+        }
+        return true;
+    }
+    // back substitution of the forward-eliminated column N + c: x[i] = unknown at position i
+    __device__ __forceinline__ void backsolve(int c, double* x, int lane) {
+#pragma unroll
+        for (int i = N - 1; i >= 0; --i) {
+            const int li = __ffs(__ballot_sync(kFull, pos == i)) - 1;
+            const double xi = __shfl_sync(kFull, a[N + c] * rdp, li);
+            a[N + c] -= (pos < i ? a[i] : 0.0) * xi;
+            if (lane == li) x[i] = xi;
+        }
+    }
+    // factors back to shared memory in team_lu's storage (row of position p at row p), rd, composed permutation
+    __device__ __forceinline__ void store(double* A, int ld, double* rd, int* piv, int lane) const {
+        if (pos < N) {
+            double* row = A + pos * ld;
+#pragma unroll
+            for (int j = 0; j < N + NX; ++j) row[j] = a[j];
+            rd[pos] = rdp;
+            piv[pos] = lane;
+        }
+    }
+};
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // the per-instance context
 // ---------------------------------------------------------------------------------------------
@@ -663,18 +745,35 @@ struct Coop {
         t.sync();
     }
 
-    // table terms for the config pair (a, b):  qq = L_dqdq(a,b), vv = L_ddqddq(a,b),
-    // vab = L_ddqdq(a,b), vba = L_ddqdq(b,a)   (first index of L_ddqdq is the velocity slot)
-    TREPB_HD void tab(int a, int b, double& qq, double& vv, double& vab, double& vba) const {
-        const int m = S.pm()[a * ND() + b];   // b is a dynamic config
-        if (m > 0) {
-            qq = w[L.QQ + m - 1]; vv = w[L.VV + m - 1]; vab = w[L.UP + m - 1]; vba = w[L.DN + m - 1];
-        } else if (m < 0) {
-            qq = w[L.QQ - m - 1]; vv = w[L.VV - m - 1]; vab = w[L.DN - m - 1]; vba = w[L.UP - m - 1];
-        } else {
-            qq = vv = vab = vba = 0.0;
+    // ---- first-derivative blocks from the chain-pair tables.  Every block of calc_deriv1
+    // (midpointvi.c:749-861: D1D1L2, D2D1L2, D1D2L2, D2D2L2 with the force terms) is one of four
+    // combinations of  Q = dt/4 L_dqdq,  V = 1/dt L_ddqddq,  U = 1/2 L_ddqdq(i,j),  D = 1/2 L_ddqdq(j,i)
+    // (i above-or-equal j).  pair_combos() replaces the raw tables by the combinations once per pair,
+    //     VV <- (Q+V)+U+D   QQ <- (Q+V)-U-D   UP <- (Q-V)+U-D   DN <- (Q-V)-U+D
+    // (ConfigSpring's -k on the diagonal folded into Q), so that each of the ~4000 block entries deriv1
+    // reads is one lookup instead of four loads and the arithmetic.
+    TREPB_HD void pair_combos(double dt) {
+        for (int e = t.lane(); e < NPAIRS(); e += Team::kSize) {
+            const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
+            double qq = w[L.QQ + e];
+            if (i == j) qq -= S.ks()[S.l_cfg()[i]];
+            const double Q = 0.25 * dt * qq, V = 1.0 / dt * w[L.VV + e], U = 0.5 * w[L.UP + e], Dn = 0.5 * w[L.DN + e];
+            w[L.VV + e] = (Q + V) + U + Dn;
+            w[L.QQ + e] = (Q + V) - U - Dn;
+            w[L.UP + e] = (Q - V) + U - Dn;
+            w[L.DN + e] = (Q - V) - U + Dn;
         }
-        if (a == b) qq -= S.ks()[a];
+        t.sync();
+    }
+    // combination for the config pair (a, b), b dynamic, after pair_combos():
+    //   which 0: (Q+V)+vab+vba   1: (Q+V)-vab-vba   2: (Q-V)+vab-vba   3: (Q-V)-vab+vba
+    // with vab = 1/2 L_ddqdq(a,b), vba = 1/2 L_ddqdq(b,a)  (first index of L_ddqdq is the velocity slot)
+    TREPB_HD double comb(int which, int a, int b, double dt) const {
+        const int m = S.pm()[a * ND() + b];
+        if (m == 0) return a == b ? 0.25 * dt * -S.ks()[a] : 0.0;
+        const int e = (m > 0 ? m : -m) - 1;
+        const int off = which == 0 ? L.VV : (which == 1 ? L.QQ : (((which == 2) == (m > 0)) ? L.UP : L.DN));
+        return w[off + e];
     }
 
     // ---- world points of the constraints at the current pose
@@ -901,6 +1000,9 @@ struct Coop {
             constraints(false, 1);
         }
         TREPB_TICK(16);
+#if defined(__CUDACC__)
+#pragma unroll 1
+#endif
         for (;;) {
             set_point(0, dt);
             if (nc > 0) {
@@ -971,9 +1073,21 @@ struct Coop {
             }
             t.sync();
             TREPB_TICK(22);
-            if (!team_lu(t, A, ld, nr, 1, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
-            TREPB_TICK(23);
-            team_backsolve_vec(t, A, ld, nr, nr, w + L.rdM, w + L.fr);
+#if defined(__CUDACC__)
+            if constexpr (D::kStatic && Team::kWarp && D::ND + D::NC <= 32) {
+                RowLU<D::ND + D::NC, 1> lu;
+                lu.load(A, ld, lane);
+                if (!lu.factor(1e-20)) return ST_SINGULAR;
+                TREPB_TICK(23);
+                lu.backsolve(0, w + L.fr, lane);
+                t.sync();
+            } else
+#endif
+            {
+                if (!team_lu(t, A, ld, nr, 1, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+                TREPB_TICK(23);
+                team_backsolve_vec(t, A, ld, nr, nr, w + L.rdM, w + L.fr);
+            }
             for (int k = lane; k < nd; k += Team::kSize) w[L.q2 + k] -= w[L.fr + k];
             for (int c = lane; c < nc; c += Team::kSize) w[L.lam + c] -= w[L.fr + nd + c];
             t.sync();
@@ -1041,10 +1155,8 @@ struct Coop {
     TREPB_HD double rhs_c(int col, int j, double dt, const double* Y, int ldy) const {
         const int nq = NQ(), nd = ND(), nu = NU();
         if (col < nq) {
-            double qq, vv, vab, vba;
-            tab(col, j, qq, vv, vab, vba);   // T11(col, j)
             const double fv = col == j ? -S.damp()[j] : 0.0;
-            double c = -((0.25 * dt * qq + 1.0 / dt * vv) - 0.5 * vab - 0.5 * vba - fv);
+            double c = -(comb(1, col, j, dt) - fv);   // T11(col, j)
             if (NC() > 0) {
                 if constexpr (D::kStatic) {
                     const int r = S.dd_row()[j], cc = S.dd_col()[col];
@@ -1058,18 +1170,13 @@ struct Coop {
         col -= nq;
         if (col < nd) return col == j ? -1.0 : 0.0;
         if (col < nd + nu) return -dt * S.Fu()[j * nu + (col - nd)];
-        double qq, vv, vab, vba;
-        tab(nd + (col - nd - nu), j, qq, vv, vab, vba);     // T21(a, j), a kinematic
-        return -((0.25 * dt * qq - 1.0 / dt * vv) + 0.5 * vab - 0.5 * vba);
+        return -comb(2, nd + (col - nd - nu), j, dt);     // T21(a, j), a kinematic
     }
     // explicit part of d p2 / d (column) at dynamic row j: D1D2L2 for q1 columns, D2D2L2 for k2 columns
     TREPB_HD double rhs_e(int kindv, int i, int j, double dt) const {
         if (kindv != 0 && kindv != 3) return 0.0;
         const int a = kindv == 0 ? i : ND() + i;
-        double qq, vv, vab, vba;
-        tab(a, j, qq, vv, vab, vba);
-        qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
-        return kindv == 0 ? (qq - vv) - vab + vba : (qq + vv) + vab + vba;
+        return comb(kindv == 0 ? 3 : 0, a, j, dt);
     }
     TREPB_HD void col_kind(int col, int& kindv, int& i) const {
         const int nq = NQ(), nd = ND(), nu = NU();
@@ -1130,6 +1237,7 @@ struct Coop {
         const int ldy = L.ldd;   // leading dimension of the DDh.lambda block (== L.ldy for run-time sizes)
         TREPB_TICK_INIT
         dyn_second();   // tables at the converged midpoint
+        pair_combos(dt);
         TREPB_TICK(25);
         if (nc > 0) {
             set_point(1, dt);
@@ -1144,13 +1252,10 @@ struct Coop {
         const int ldm = L.ldm;
         for (int e = lane; e < nd * nd; e += Team::kSize) {
             const int a = e / nd, b = e - a * nd;
-            double qq, vv, vab, vba;
-            tab(b, a, qq, vv, vab, vba);   // T21(b, a)
-            qq *= 0.25 * dt; vv *= 1.0 / dt; vab *= 0.5; vba *= 0.5;
             const double fv = a == b ? -S.damp()[a] : 0.0;
-            M2[a * ldm + b] = (qq - vv) + vab - vba + fv;
+            M2[a * ldm + b] = comb(2, b, a, dt) + fv;   // T21(b, a)
             // T22(a, b): symmetric in the table terms -> same lookup transposed
-            T22[b * nd + a] = (qq + vv) + vab + vba;
+            T22[b * nd + a] = comb(0, b, a, dt);
         }
         for (int e = lane; e < nd * nc; e += Team::kSize) {
             const int a = e / nc, c = e - a * nc;
@@ -1158,7 +1263,19 @@ struct Coop {
         }
         t.sync();
         TREPB_TICK(27);
-        if (!team_lu(t, M2, ldm, nd, nc, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+#if defined(__CUDACC__)
+        if constexpr (D::kStatic && Team::kWarp && D::ND <= 32) {
+            RowLU<D::ND, D::NC> lu;
+            lu.load(M2, ldm, lane);
+            if (!lu.factor(1e-20)) return ST_SINGULAR;
+            t.sync();   // every lane has read its row before rows are written back in pivot order
+            lu.store(M2, ldm, w + L.rdM, ipivM(), lane);
+            t.sync();
+        } else
+#endif
+        {
+            if (!team_lu(t, M2, ldm, nd, nc, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+        }
         double* PJ = w + L.PJ;
         const int ldp = L.ldp;
         if (nc > 0) {
