@@ -120,13 +120,15 @@ typedef struct trepb_system trepb_system; /* opaque */
 /* flags for trepb_system_create */
 #define TREPB_FLAG_NO_SPECIALIZE 1  /* use the table-driven general kernels even for small systems */
 #define TREPB_FLAG_NO_COOP 2        /* table-driven systems: always one thread per instance */
-#define TREPB_FLAG_FORCE_COOP 4     /* table-driven systems: always the cooperative kernels (one warp per
+#define TREPB_FLAG_FORCE_COOP 4     /* table-driven systems: always the cooperative kernels (one or two warps per
                                        instance, workspace in shared memory); fails if they do not apply */
 #define TREPB_FLAG_D2_PAIRWISE 8    /* table-driven systems: second derivatives by one hyper-dual residual
                                        evaluation per parameter pair (the scheme the small specialised
                                        systems use) instead of one dual evaluation of the Jacobian tables
                                        per parameter followed by a contraction */
 
+#define TREPB_FLAG_COOP_ONE_WARP 32  /* cooperative kernels: one warp per instance even where a two-warps-per-instance
+                                       flavour was built for this shape (the marionette's, which is the default there) */
 #define TREPB_FLAG_NO_LITERAL 16     /* specialised systems: skip an all-literal instantiation built for exactly this
                                        description and use the run-time-parameter kernel of its structure */
 

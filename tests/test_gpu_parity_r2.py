@@ -58,6 +58,10 @@ def flavours(lib, name):
         out.append(("coop", c))
         if name in COOP_STATIC:
             c = lib.System(d, cooperative=True)
+            if c.kernel_name.endswith("/pair"):     # two warps per instance: the default where it was built
+                assert c.kernel_name == "cooperative/" + name + "/pair"
+                out.append(("coop-static-pair", c))
+                c = lib.System(d, cooperative=True, coop_one_warp=True)
             assert c.kernel_name == "cooperative/" + name
             out.append(("coop-static", c))
     return out

@@ -186,7 +186,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         s->CP = coop_pack(desc);
         if (s->CP.ok) {
             CoopSys hv = s->CP.view(s->CP.blob.data());
-            const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE));
+            const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE), (flags & TREPB_FLAG_COOP_ONE_WARP) ? 1 : 0);
             s->clay.set(hv, cks->specialized != 0);
             s->coop_blob_bytes = (int)s->CP.blob.size();
             const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
@@ -306,7 +306,7 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
         if (blocks_per_sm) *blocks_per_sm = 1;
-        if (block) *block = 32 * s->coop_warps;
+        if (block) *block = 32 * s->cks->team_warps * s->coop_warps;
         if (smem_bytes) *smem_bytes = (int32_t)((size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)s->coop_warps * s->clay.total * 8);
         return TREPB_OK;
     }

@@ -1,5 +1,6 @@
 // Team-cooperative kernels, run-time-size flavour (any system the link tables can express) and
 // the registry of compile-time-size flavours (generated gen/coop_<name>.cu files).
+#include <stdlib.h>
 #include "trepb_coop_kernels.cuh"
 
 namespace trepb {
@@ -14,11 +15,20 @@ const CoopKernelSet* coop_general_kernels() {
     return &ks;
 }
 
-const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized) {
+const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized, int team_warps) {
     if (allow_specialized) {
+        // several team sizes may be registered for one shape: the widest team wins unless the caller
+        // (TREPB_FLAG_COOP_ONE_WARP) or TREPB_COOP_TEAM=<warps> (diagnostic) asks for another
         CoopRegistry& r = coop_registry();
-        for (int i = 0; i < r.n; ++i)
-            if (r.sets[i]->matches(s)) return r.sets[i];
+        const char* e = getenv("TREPB_COOP_TEAM");
+        const int want = team_warps > 0 ? team_warps : (e ? atoi(e) : 0);
+        const CoopKernelSet* best = nullptr;
+        for (int i = 0; i < r.n; ++i) {
+            if (!r.sets[i]->matches(s)) continue;
+            if (want > 0 && r.sets[i]->team_warps == want) return r.sets[i];
+            if (!best || r.sets[i]->team_warps > best->team_warps) best = r.sets[i];
+        }
+        if (best) return best;
     }
     return coop_general_kernels();
 }

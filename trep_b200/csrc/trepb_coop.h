@@ -7,7 +7,7 @@
 namespace trepb {
 
 struct CoopLaunch {
-    int grid, warps;        // CTAs, warps (= instances in flight) per CTA
+    int grid, warps;        // CTAs, teams (= instances in flight) per CTA; a team is team_warps warps
     size_t smem;            // table blob + warps x workspace
     cudaStream_t stream;
     CoopSys sys;            // view whose base is the DEVICE copy of the blob
@@ -20,6 +20,7 @@ struct CoopLaunch {
 struct CoopKernelSet {
     const char* name;
     int specialized;
+    int team_warps;         // warps that work on one instance (1: WarpTeam, 2: PairTeam)
     bool (*matches)(const CoopSys&);
     cudaError_t (*step)(const CoopLaunch&, const StepParams&);
     cudaError_t (*p2)(const CoopLaunch&, const P2Params&);
@@ -41,6 +42,6 @@ struct CoopRegistrar {
     }
 };
 const CoopKernelSet* coop_general_kernels();
-const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized);
+const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized, int team_warps = 0);
 
 }  // namespace trepb

@@ -17,17 +17,40 @@
 namespace trepb {
 namespace coopk {
 
+// CTA-wide barrier at the start of every instance / step (see coop_lin_kernel); -DTREPB_COOP_FREERUN
+// lets the teams run free (experiment)
+#if defined(TREPB_COOP_FREERUN)
+#define TREPB_LOCKSTEP() ((void)0)
+#else
+#define TREPB_LOCKSTEP() __syncthreads()
+#endif
+
+
 struct Stage {
     CoopSys S;
     double* w;
 };
 
-// The warp's index in its CTA as a value the compiler knows to be the same in all 32 lanes (the result of
-// a broadcast): the workspace base, the instance index and every branch taken on data read from the
-// workspace are then provably warp-uniform, which removes the re-convergence bookkeeping (BSSY / BSYNC,
-// WARPSYNC.COLLECTIVE around every shuffle and reduction) the compiler otherwise emits.
-__device__ __forceinline__ int warp_index() { return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0); }
+// The team's index in its CTA as a value the compiler knows to be the same in all lanes of a warp (the
+// result of a broadcast): the workspace base, the instance index and every branch taken on data read
+// from the workspace are then provably warp-uniform, which removes the re-convergence bookkeeping (BSSY /
+// BSYNC, WARPSYNC.COLLECTIVE around every shuffle and reduction) the compiler otherwise emits.
+template <class Team>
+__device__ __forceinline__ int team_index() {
+    return __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0) / Team::kWarps;
+}
+template <class Team>
+__device__ __forceinline__ Team make_team() {
+    if constexpr (Team::kWarps > 1) {
+        Team t;
+        t.bar = 1 + team_index<Team>();
+        return t;
+    } else {
+        return Team();
+    }
+}
 
+template <class Team>
 __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, const CoopLayout& lay) {
     extern __shared__ double smem_[];
     const int n8 = (blob_bytes + 7) / 8;
@@ -37,51 +60,53 @@ __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, c
     Stage st;
     st.S = gs;
     st.S.base = (const char*)smem_;
-    st.w = smem_ + ((n8 + 1) & ~1) + (long)warp_index() * lay.total;
+    st.w = smem_ + ((n8 + 1) & ~1) + (long)team_index<Team>() * lay.total;
     return st;
 }
 
-template <class D>
-__global__ void __launch_bounds__(256, 1)
+template <class D, class Team>
+__global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = D::layout();
-    Stage st = coop_stage(gs, blob_bytes, lay);
+    Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
-    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
-    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const Team tm = make_team<Team>();
+    constexpr int TS = Team::kSize;
+    Coop<Team, D> c(S, lay, w, tm);
+    const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     // the warps of a CTA take every step together (see coop_lin_kernel)
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
-        const long b = b0 + warp_index();
+        const long b = b0 + team_index<Team>();
         const bool live = b < p.batch;
         if (live) {
-            for (int i = lane; i < nq; i += 32) {
+            for (int i = lane; i < nq; i += TS) {
                 const double v = p.q1[b * nq + i];
                 w[lay.q1 + i] = v;
                 w[lay.q2 + i] = v;
             }
-            __syncwarp();
-            for (int i = lane; i < nd; i += 32) {
+            tm.sync();
+            for (int i = lane; i < nd; i += TS) {
                 w[lay.p1 + i] = p.p1[b * nd + i];
                 if (p.q2g) w[lay.q2 + i] = p.q2g[b * nd + i];
             }
-            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
+            for (int i = lane; i < nc; i += TS) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
         }
         int total = 0, status = ST_OK;
         double t1 = p.t0;
         for (int s = 0; s < p.nsteps; ++s) {
-            __syncthreads();
+            TREPB_LOCKSTEP();
             if (!live || status != ST_OK) continue;
             if (s > 0) {
-                for (int i = lane; i < nq; i += 32) w[lay.q1 + i] = w[lay.q2 + i];
-                for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = w[lay.p2 + i];
+                for (int i = lane; i < nq; i += TS) w[lay.q1 + i] = w[lay.q2 + i];
+                for (int i = lane; i < nd; i += TS) w[lay.p1 + i] = w[lay.p2 + i];
             }
-            for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1 ? p.u1[(b * p.nsteps + s) * nu + i] : 0.0;
-            __syncwarp();
-            for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[(b * p.nsteps + s) * nk + i];
-            __syncwarp();
+            for (int i = lane; i < nu; i += TS) w[lay.u1 + i] = p.u1 ? p.u1[(b * p.nsteps + s) * nu + i] : 0.0;
+            tm.sync();
+            for (int i = lane; i < nk; i += TS) w[lay.q2 + nd + i] = p.k2[(b * p.nsteps + s) * nk + i];
+            tm.sync();
             if (p.times) t1 = p.times[s];
             const double t2 = p.times ? p.times[s + 1] : t1 + p.dt;
             const int it = c.solve(t1, t2, p.tol, p.max_it);
@@ -90,41 +115,43 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
             t1 = t2;
             if (p.sample_every > 0 && (s + 1) % p.sample_every == 0) {
                 const long row = b * p.nsamples + (s + 1) / p.sample_every - 1;
-                if (p.traj_q) for (int i = lane; i < nq; i += 32) p.traj_q[row * nq + i] = w[lay.q2 + i];
-                if (p.traj_p) for (int i = lane; i < nd; i += 32) p.traj_p[row * nd + i] = w[lay.p2 + i];
+                if (p.traj_q) for (int i = lane; i < nq; i += TS) p.traj_q[row * nq + i] = w[lay.q2 + i];
+                if (p.traj_p) for (int i = lane; i < nd; i += TS) p.traj_p[row * nd + i] = w[lay.p2 + i];
             }
         }
-        __syncwarp();
+        tm.sync();
         if (live) {
-            for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
-            for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
-            if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
+            for (int i = lane; i < nq; i += TS) p.q2[b * nq + i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += TS) p.p2[b * nd + i] = w[lay.p2 + i];
+            if (p.lam) for (int i = lane; i < nc; i += TS) p.lam[b * nc + i] = w[lay.lam + i];
             if (lane == 0) {
                 if (p.iters) p.iters[b] = total;
                 p.status[b] = status;
             }
         }
-        __syncwarp();
+        tm.sync();
     }
 }
 
 // DSystem.project / armijo_simulate (trep/discopt/dsystem.py:426-457): closed-loop rollouts, one warp per
 // candidate, the affine feedback U[k] = bU[k] - K[k](X[k] - bX[k]) evaluated by the lanes (one input
 // component each) inside the time loop.
-template <class D>
-__global__ void __launch_bounds__(256, 1)
+template <class D, class Team>
+__global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = D::layout();
-    Stage st = coop_stage(gs, blob_bytes, lay);
+    Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
-    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
-    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const Team tm = make_team<Team>();
+    constexpr int TS = Team::kSize;
+    Coop<Team, D> c(S, lay, w, tm);
+    const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
     for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc) {
-        const long b = b0 + warp_index();
+        const long b = b0 + team_index<Team>();
         const bool live = b < p.batch;
         const double* bX = p.bX + b * (long)(K + 1) * nX;
         const double* bU = p.bU + b * (long)K * nU;
@@ -132,22 +159,22 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
         double* Xo = p.X + b * (long)(K + 1) * nX;
         double* Uo = p.U + b * (long)K * nU;
         if (live) {
-            for (int i = lane; i < nq; i += 32) { const double v = bX[i]; w[lay.q2 + i] = v; Xo[i] = v; }
-            for (int i = lane; i < nd; i += 32) { const double v = bX[nq + i]; w[lay.p2 + i] = v; Xo[nq + i] = v; }
-            for (int i = lane; i < nk; i += 32) { const double v = bX[nq + nd + i]; w[lay.vk + i] = v; Xo[nq + nd + i] = v; }
-            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = 0.0;
+            for (int i = lane; i < nq; i += TS) { const double v = bX[i]; w[lay.q2 + i] = v; Xo[i] = v; }
+            for (int i = lane; i < nd; i += TS) { const double v = bX[nq + i]; w[lay.p2 + i] = v; Xo[nq + i] = v; }
+            for (int i = lane; i < nk; i += TS) { const double v = bX[nq + nd + i]; w[lay.vk + i] = v; Xo[nq + nd + i] = v; }
+            for (int i = lane; i < nc; i += TS) w[lay.lam + i] = 0.0;
         }
         int total = 0, status = ST_OK, fail = K;
         double t1 = p.t0;
         for (int s = 0; s < K; ++s) {
-            __syncthreads();   // the warps of a CTA take every step together (see coop_lin_kernel)
+            TREPB_LOCKSTEP();   // the warps of a CTA take every step together (see coop_lin_kernel)
             if (!live || status != ST_OK) continue;
-            for (int i = lane; i < nq; i += 32) w[lay.q1 + i] = w[lay.q2 + i];
-            for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = w[lay.p2 + i];
-            __syncwarp();
+            for (int i = lane; i < nq; i += TS) w[lay.q1 + i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += TS) w[lay.p1 + i] = w[lay.p2 + i];
+            tm.sync();
             const double* bx = bX + (long)s * nX;
             const double* Ks = Kf + (long)s * nU * nX;
-            for (int cc = lane; cc < nU; cc += 32) {
+            for (int cc = lane; cc < nU; cc += TS) {
                 double acc = 0.0;
                 for (int x = 0; x < nq; ++x) acc += Ks[cc * nX + x] * (w[lay.q1 + x] - bx[x]);
                 for (int x = 0; x < nd; ++x) acc += Ks[cc * nX + nq + x] * (w[lay.p1 + x] - bx[nq + x]);
@@ -157,8 +184,8 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
                 if (cc < nu) w[lay.u1 + cc] = u;
                 else w[lay.q2 + nd + cc - nu] = u;
             }
-            if (p.use_hint) for (int i = lane; i < nd; i += 32) w[lay.q2 + i] = bX[(long)(s + 1) * nX + i];
-            __syncwarp();
+            if (p.use_hint) for (int i = lane; i < nd; i += TS) w[lay.q2 + i] = bX[(long)(s + 1) * nX + i];
+            tm.sync();
             if (p.times) t1 = p.times[s];
             const double t2 = p.times ? p.times[s + 1] : t1 + p.dt;
             const int it = c.solve(t1, t2, p.tol, p.max_it);
@@ -167,70 +194,74 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
             const double dts = t2 - t1;
             t1 = t2;
             double* xo = Xo + (long)(s + 1) * nX;
-            for (int i = lane; i < nq; i += 32) xo[i] = w[lay.q2 + i];
-            for (int i = lane; i < nd; i += 32) xo[nq + i] = w[lay.p2 + i];
-            for (int i = lane; i < nk; i += 32) {
+            for (int i = lane; i < nq; i += TS) xo[i] = w[lay.q2 + i];
+            for (int i = lane; i < nd; i += TS) xo[nq + i] = w[lay.p2 + i];
+            for (int i = lane; i < nk; i += TS) {
                 const double v = (w[lay.q2 + nd + i] - w[lay.q1 + nd + i]) / dts;
                 w[lay.vk + i] = v;
                 xo[nq + nd + i] = v;
             }
-            __syncwarp();
+            tm.sync();
         }
         if (live && lane == 0) {
             if (p.iters) p.iters[b] = total;
             p.status[b] = status;
             if (p.fail_step) p.fail_step[b] = fail;
         }
-        __syncwarp();
+        tm.sync();
     }
 }
 
-template <class D>
-__global__ void __launch_bounds__(256, 1)
+template <class D, class Team>
+__global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = D::layout();
-    Stage st = coop_stage(gs, blob_bytes, lay);
+    Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
-    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
-    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const Team tm = make_team<Team>();
+    constexpr int TS = Team::kSize;
+    Coop<Team, D> c(S, lay, w, tm);
+    const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
-    for (long b = (long)blockIdx.x * wpc + warp_index(); b < p.batch; b += (long)gridDim.x * wpc) {
-        for (int i = lane; i < nq; i += 32) {
+    for (long b = (long)blockIdx.x * wpc + team_index<Team>(); b < p.batch; b += (long)gridDim.x * wpc) {
+        for (int i = lane; i < nq; i += TS) {
             w[lay.q1 + i] = p.q0[b * nq + i];
             w[lay.q2 + i] = p.q1[b * nq + i];
         }
-        for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1 ? p.u1[b * nu + i] : 0.0;
+        for (int i = lane; i < nu; i += TS) w[lay.u1 + i] = p.u1 ? p.u1[b * nu + i] : 0.0;
         if (p.mode == 1) {
-            for (int i = lane; i < nd; i += 32) w[lay.p1 + i] = p.p1[b * nd + i];
-            for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lam ? p.lam[b * nc + i] : 0.0;
+            for (int i = lane; i < nd; i += TS) w[lay.p1 + i] = p.p1[b * nd + i];
+            for (int i = lane; i < nc; i += TS) w[lay.lam + i] = p.lam ? p.lam[b * nc + i] : 0.0;
         }
-        __syncwarp();
+        tm.sync();
         if (p.mode == 0) {
             c.calc_p2(p.dt);
-            for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.p2 + i];
+            for (int i = lane; i < nd; i += TS) p.p[b * nd + i] = w[lay.p2 + i];
         } else if (p.mode == 1) {
             c.calc_f(p.dt);
-            for (int i = lane; i < nd + nc; i += 32) p.p[b * (nd + nc) + i] = w[lay.fr + i];
+            for (int i = lane; i < nd + nc; i += TS) p.p[b * (nd + nc) + i] = w[lay.fr + i];
         } else {
             c.calc_fm2(p.dt);
-            for (int i = lane; i < nd; i += 32) p.p[b * nd + i] = w[lay.fr + i];
+            for (int i = lane; i < nd; i += TS) p.p[b * nd + i] = w[lay.fr + i];
         }
-        __syncwarp();
+        tm.sync();
     }
 }
 
-template <class D>
-__global__ void __launch_bounds__(256, 1)
+template <class D, class Team>
+__global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = D::layout();
-    Stage st = coop_stage(gs, blob_bytes, lay);
+    Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
-    Coop<WarpTeam, D> c(S, lay, w, WarpTeam());
-    const int lane = threadIdx.x & 31, wpc = blockDim.x >> 5;
+    const Team tm = make_team<Team>();
+    constexpr int TS = Team::kSize;
+    Coop<Team, D> c(S, lay, w, tm);
+    const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const long nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
     const int auxo[7] = {al.o_m2, al.o_m2p, al.o_pj, al.o_pjp, al.o_dh1, al.o_dh2, al.o_t22};
@@ -239,33 +270,33 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     // cache a third of the time (ncu: "no instruction" stalls 31 % free-running vs 5 % in step); the
     // wait for the slowest Newton iteration count of the round costs less than that.
 #pragma unroll 1
-    for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc, __syncthreads()) {
-        const long b = b0 + warp_index();
+    for (long b0 = (long)blockIdx.x * wpc; b0 < p.batch; b0 += (long)gridDim.x * wpc, TREPB_LOCKSTEP()) {
+        const long b = b0 + team_index<Team>();
         if (b >= p.batch) continue;
         const long r = p.traj_len > 1 ? b + b / (p.traj_len - 1) : b;   // state row (trepb_lin_args.traj_len)
-        for (int i = lane; i < nq; i += 32) {
+        for (int i = lane; i < nq; i += TS) {
             const double v = p.q1[r * nq + i];
             w[lay.q1 + i] = v;
             w[lay.q2 + i] = v;
         }
-        __syncwarp();
-        for (int i = lane; i < nd; i += 32) {
+        tm.sync();
+        for (int i = lane; i < nd; i += TS) {
             w[lay.p1 + i] = p.p1[r * nd + i];
             if (p.q2g) w[lay.q2 + i] = p.q2g[r * nd + i];
         }
-        for (int i = lane; i < nk; i += 32) w[lay.q2 + nd + i] = p.k2[b * nk + i];
-        for (int i = lane; i < nu; i += 32) w[lay.u1 + i] = p.u1[b * nu + i];
-        for (int i = lane; i < nc; i += 32) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
-        __syncwarp();
+        for (int i = lane; i < nk; i += TS) w[lay.q2 + nd + i] = p.k2[b * nk + i];
+        for (int i = lane; i < nu; i += TS) w[lay.u1 + i] = p.u1[b * nu + i];
+        for (int i = lane; i < nc; i += TS) w[lay.lam + i] = p.lamg ? p.lamg[b * nc + i] : 0.0;
+        tm.sync();
         const double t1 = p.t1 ? p.t1[b] : p.t1s;
         const double t2 = p.t2 ? p.t2[b] : (t1 + p.dts);
         int it = c.solve(t1, t2, p.tol, p.max_it);
         int status = ST_OK;
         if (it < 0) { status = it; it = 0; }
-        __syncwarp();
-        if (p.q2) for (int i = lane; i < nq; i += 32) p.q2[b * nq + i] = w[lay.q2 + i];
-        if (p.p2) for (int i = lane; i < nd; i += 32) p.p2[b * nd + i] = w[lay.p2 + i];
-        if (p.lam) for (int i = lane; i < nc; i += 32) p.lam[b * nc + i] = w[lay.lam + i];
+        tm.sync();
+        if (p.q2) for (int i = lane; i < nq; i += TS) p.q2[b * nq + i] = w[lay.q2 + i];
+        if (p.p2) for (int i = lane; i < nd; i += TS) p.p2[b * nd + i] = w[lay.p2 + i];
+        if (p.lam) for (int i = lane; i < nc; i += TS) p.lam[b * nc + i] = w[lay.lam + i];
         if (status == ST_OK) {
             Deriv1Out o;
 #define TREPB_RAW(idx, member, rows, cols) \
@@ -284,7 +315,7 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
             if (p.iters) p.iters[b] = it;
             p.status[b] = status;
         }
-        __syncwarp();
+        tm.sync();
     }
 }
 
@@ -295,36 +326,36 @@ cudaError_t prep(K kernel, size_t smem) {
     return cudaSuccess;
 }
 
-template <class D>
+template <class D, class Team>
 struct Launch {
     static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
-        cudaError_t e = prep(coop_step_kernel<D>, c.smem);
+        cudaError_t e = prep(coop_step_kernel<D, Team>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_step_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_step_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
-        cudaError_t e = prep(coop_p2_kernel<D>, c.smem);
+        cudaError_t e = prep(coop_p2_kernel<D, Team>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_p2_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_p2_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
-        cudaError_t e = prep(coop_lin_kernel<D>, c.smem);
+        cudaError_t e = prep(coop_lin_kernel<D, Team>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_lin_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+        coop_lin_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
         return cudaGetLastError();
     }
     static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
-        cudaError_t e = prep(coop_project_kernel<D>, c.smem);
+        cudaError_t e = prep(coop_project_kernel<D, Team>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_project_kernel<D><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_project_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t info(int which, KernelInfo* ki) {
-        const void* fn = which == 0 ? (const void*)coop_step_kernel<D>
-                       : which == 1 ? (const void*)coop_p2_kernel<D>
-                       : which == 2 ? (const void*)coop_lin_kernel<D> : (const void*)coop_project_kernel<D>;
+        const void* fn = which == 0 ? (const void*)coop_step_kernel<D, Team>
+                       : which == 1 ? (const void*)coop_p2_kernel<D, Team>
+                       : which == 2 ? (const void*)coop_lin_kernel<D, Team> : (const void*)coop_project_kernel<D, Team>;
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
         if (e != cudaSuccess) return e;
@@ -342,17 +373,18 @@ struct Launch {
 
 }  // namespace coopk
 
-template <class D>
+template <class D, class Team = WarpTeam>
 CoopKernelSet make_coop_kernelset(const char* name) {
     CoopKernelSet k;
     k.name = name;
     k.specialized = D::kStatic ? 1 : 0;
-    k.matches = &coopk::Launch<D>::matches;
-    k.step = &coopk::Launch<D>::step;
-    k.p2 = &coopk::Launch<D>::p2;
-    k.lin = &coopk::Launch<D>::lin;
-    k.proj = &coopk::Launch<D>::proj;
-    k.info = &coopk::Launch<D>::info;
+    k.team_warps = Team::kWarps;
+    k.matches = &coopk::Launch<D, Team>::matches;
+    k.step = &coopk::Launch<D, Team>::step;
+    k.p2 = &coopk::Launch<D, Team>::p2;
+    k.lin = &coopk::Launch<D, Team>::lin;
+    k.proj = &coopk::Launch<D, Team>::proj;
+    k.info = &coopk::Launch<D, Team>::info;
     return k;
 }
 

@@ -41,17 +41,23 @@ namespace trepb {
 // teams
 // ---------------------------------------------------------------------------------------------
 struct HostTeam {
-    static constexpr int kSize = 1;
+    static constexpr int kSize = 1, kWarps = 1;
     static constexpr bool kWarp = false;
+    using Sub = HostTeam;
     TREPB_HD int lane() const { return 0; }
+    TREPB_HD int warp() const { return 0; }
+    TREPB_HD Sub sub() const { return Sub(); }
     TREPB_HD void sync() const {}
     TREPB_HD void argmax(double&, int&) const {}
 };
 #if defined(__CUDACC__)
 struct WarpTeam {
-    static constexpr int kSize = 32;
+    static constexpr int kSize = 32, kWarps = 1;
     static constexpr bool kWarp = true;
+    using Sub = WarpTeam;
     __device__ __forceinline__ int lane() const { return threadIdx.x & 31; }
+    __device__ __forceinline__ int warp() const { return 0; }
+    __device__ __forceinline__ Sub sub() const { return Sub(); }
     __device__ __forceinline__ void sync() const { __syncwarp(); }
     // largest value wins, ties go to the lowest index; every lane gets the result
     __device__ __forceinline__ void argmax(double& v, int& i) const {
@@ -62,6 +68,22 @@ struct WarpTeam {
             if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
         }
     }
+};
+// Two warps on one instance: the flat phases (pairs, matrix entries, right-hand-side columns, constraint
+// lists) spread over 64 lanes and the midpoint / q2 pose sweeps run on one warp each, which doubles the
+// warps an SM has to hide latencies with while the shared-memory footprint per instance stays the same.
+// Synchronisation is a named barrier per team (bar.sync id, 64); the factorizations, which use warp
+// collectives, run on the team's first warp (Sub).
+struct PairTeam {
+    static constexpr int kSize = 64, kWarps = 2;
+    static constexpr bool kWarp = false;
+    using Sub = WarpTeam;
+    int bar;   // named barrier of this team (1 + team index in the CTA; 0 is __syncthreads)
+    __device__ __forceinline__ int lane() const { return threadIdx.x & 63; }
+    __device__ __forceinline__ int warp() const { return (threadIdx.x >> 5) & 1; }
+    __device__ __forceinline__ Sub sub() const { return Sub(); }
+    __device__ __forceinline__ void sync() const { asm volatile("bar.sync %0, 64;" ::"r"(bar) : "memory"); }
+    __device__ __forceinline__ void argmax(double&, int&) const {}
 };
 #endif
 
@@ -84,7 +106,7 @@ struct CoopLayout {
     int N;                           // Newton augmented matrix [nr][ldf]  /  right-hand sides Y [nd][ldy]
     int Z, PJ;
     int fr, scl, rdM, rdP;
-    int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc]  (int32)
+    int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc] flag  (int32)
     int total;
 
     TREPB_HD static constexpr int odd(int n) { return n | 1; }
@@ -122,7 +144,7 @@ struct CoopLayout {
         L.Z = o; o += stat ? 0 : nc * L.ldy;
         L.PJ = o; o += nc * L.ldp;
         L.rdM = o; o += nr; L.rdP = o; o += nc;
-        L.ints = o; o += (2 * nr + 2 * nc + 1) / 2 + 1;
+        L.ints = o; o += (2 * nr + 2 * nc + 2) / 2 + 1;   // + the first-warp flag
         L.total = (o + 1) & ~1;
         return L;
     }
@@ -437,6 +459,16 @@ struct Coop {
     TREPB_HD int* iswpM() const { return ipivM() + (ND() + NC()); }
     TREPB_HD int* ipivP() const { return iswpM() + (ND() + NC()); }
     TREPB_HD int* iswpP() const { return ipivP() + NC(); }
+    TREPB_HD int* iflag() const { return iswpP() + NC(); }   // result of a first-warp section (teams of several warps)
+    // the outcome of a section only the team's first warp ran, made known to every lane of the team
+    TREPB_HD bool first_warp_result(bool ok) {
+        if constexpr (Team::kWarps > 1) {
+            if (t.lane() == 0) iflag()[0] = ok ? 1 : 0;
+            t.sync();
+            ok = iflag()[0] != 0;
+        }
+        return ok;
+    }
 
     // ---- evaluation point: which = 0 midpoint, 1 q1, 2 q2 (midpointvi.c:401-457)
     TREPB_HD void set_point(int which, double dt) {
@@ -1073,20 +1105,30 @@ struct Coop {
             }
             t.sync();
             TREPB_TICK(22);
-#if defined(__CUDACC__)
-            if constexpr (D::kStatic && Team::kWarp && D::ND + D::NC <= 32) {
-                RowLU<D::ND + D::NC, 1> lu;
-                lu.load(A, ld, lane);
-                if (!lu.factor(1e-20)) return ST_SINGULAR;
-                TREPB_TICK(23);
-                lu.backsolve(0, w + L.fr, lane);
-                t.sync();
-            } else
-#endif
             {
-                if (!team_lu(t, A, ld, nr, 1, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
-                TREPB_TICK(23);
-                team_backsolve_vec(t, A, ld, nr, nr, w + L.rdM, w + L.fr);
+                // factorization + back substitution on the team's first warp (warp collectives)
+                bool ok = true;
+                if (t.warp() == 0) {
+                    bool done = false;
+#if defined(__CUDACC__)
+                    if constexpr (D::kStatic && Team::Sub::kWarp && D::ND + D::NC <= 32) {
+                        RowLU<D::ND + D::NC, 1> lu;
+                        lu.load(A, ld, lane & 31);
+                        ok = lu.factor(1e-20);
+                        TREPB_TICK(23);
+                        if (ok) lu.backsolve(0, w + L.fr, lane & 31);
+                        done = true;
+                    }
+#endif
+                    if (!done) {
+                        ok = team_lu(t.sub(), A, ld, nr, 1, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20);
+                        TREPB_TICK(23);
+                        if (ok) team_backsolve_vec(t.sub(), A, ld, nr, nr, w + L.rdM, w + L.fr);
+                    }
+                }
+                ok = first_warp_result(ok);
+                if (!ok) return ST_SINGULAR;
+                t.sync();
             }
             for (int k = lane; k < nd; k += Team::kSize) w[L.q2 + k] -= w[L.fr + k];
             for (int c = lane; c < nc; c += Team::kSize) w[L.lam + c] -= w[L.fr + nd + c];
@@ -1263,18 +1305,25 @@ struct Coop {
         }
         t.sync();
         TREPB_TICK(27);
-#if defined(__CUDACC__)
-        if constexpr (D::kStatic && Team::kWarp && D::ND <= 32) {
-            RowLU<D::ND, D::NC> lu;
-            lu.load(M2, ldm, lane);
-            if (!lu.factor(1e-20)) return ST_SINGULAR;
-            t.sync();   // every lane has read its row before rows are written back in pivot order
-            lu.store(M2, ldm, w + L.rdM, ipivM(), lane);
-            t.sync();
-        } else
-#endif
         {
-            if (!team_lu(t, M2, ldm, nd, nc, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20)) return ST_SINGULAR;
+            bool ok = true;
+            if (t.warp() == 0) {
+                bool done = false;
+#if defined(__CUDACC__)
+                if constexpr (D::kStatic && Team::Sub::kWarp && D::ND <= 32) {
+                    RowLU<D::ND, D::NC> lu;
+                    lu.load(M2, ldm, lane & 31);
+                    ok = lu.factor(1e-20);
+                    t.sub().sync();   // every lane has read its row before rows are written back in pivot order
+                    if (ok) lu.store(M2, ldm, w + L.rdM, ipivM(), lane & 31);
+                    done = true;
+                }
+#endif
+                if (!done) ok = team_lu(t.sub(), M2, ldm, nd, nc, ipivM(), iswpM(), w + L.scl, w + L.rdM, 1e-20);
+            }
+            ok = first_warp_result(ok);
+            if (!ok) return ST_SINGULAR;
+            t.sync();
         }
         double* PJ = w + L.PJ;
         const int ldp = L.ldp;
@@ -1289,7 +1338,13 @@ struct Coop {
                 PJ[a * ldp + b] = -s;
             }
             t.sync();
-            if (!team_lu(t, PJ, ldp, nc, 0, ipivP(), iswpP(), w + L.scl, w + L.rdP, 1e-20)) return ST_SINGULAR;
+            {
+                bool ok = true;
+                if (t.warp() == 0) ok = team_lu(t.sub(), PJ, ldp, nc, 0, ipivP(), iswpP(), w + L.scl, w + L.rdP, 1e-20);
+                ok = first_warp_result(ok);
+                if (!ok) return ST_SINGULAR;
+                t.sync();
+            }
         }
         if (aux) {
             // auxo: o_m2, o_m2p, o_pj, o_pjp, o_dh1, o_dh2, o_t22 ; factors in LU_decomp's convention
