@@ -15,4 +15,5 @@ for rep in range(3):
     lib.synchronize(0); t0 = time.perf_counter()
     lib.lqr_raw(True, 0, R, K, nX, nU, A, B, Q, Rm, Ko, st)
     lib.synchronize(0); dt = time.perf_counter() - t0
-    print("R=%d K=%d nX=%d nU=%d: %.2f ms, %.1f us per step per rollout-SM, ok=%s" % (R, K, nX, nU, dt * 1e3, dt * 1e6 / K / max(1, (R + 147) // 148), bool(np.all(st.download() == 0))))
+    ms = lib.lqr_last_kernel_ms(0)
+    print("R=%d K=%d nX=%d nU=%d: host %.2f ms, kernel (CUDA events) %.2f ms, %.1f us per step per rollout-SM, ok=%s" % (R, K, nX, nU, dt * 1e3, ms, ms * 1e3 / K / max(1, (R + 147) // 148), bool(np.all(st.download() == 0))))

@@ -14,6 +14,7 @@
 // right-hand sides are then solved one per thread; A[k-1], B[k-1] and Q(k) are fetched with cp.async
 // while the current step is still multiplying.
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <string>
 #include "../../include/trepb.h"
 #include "trepb_coop_math.cuh"
@@ -104,6 +105,65 @@ __device__ __forceinline__ void gemm_tn(double* C, int ldc, const double* Xt, in
     }
 }
 
+// The same product on the FP64 tensor-core path: mma.sync.aligned.m8n8k4 (DMMA), one warp per tile of
+// (8 TI) x (8 TJ) outputs, TI + TJ operand fragments loaded per TI x TJ instructions of 256 fused
+// multiply-adds.  Fragment layout (g = lane / 4, tg = lane % 4): A[g][tg] = Xt[m0 + tg][i + g],
+// B[tg][g] = Y[m0 + tg][j + g], C[g][2 tg + {0, 1}].  Rows / columns beyond M, N, Kd read as zero and are
+// not stored, so any shape works (nU = 18 runs as 24).  Warps w0 .. w0+nw-1 of the CTA share the tiles.
+template <int TI, int TJ>
+__device__ __forceinline__ void gemm_tn_dmma(double* C, int ldc, const double* Xt, int ldx, const double* Y, int ldy,
+                                             int M, int N, int Kd, int mode, int w0, int nw) {
+    const int warp = (int)(threadIdx.x >> 5) - w0, lane = threadIdx.x & 31;
+    if (warp < 0 || warp >= nw) return;
+    const int g = lane >> 2, tg = lane & 3;
+    const int tm = (M + 8 * TI - 1) / (8 * TI), tn = (N + 8 * TJ - 1) / (8 * TJ);
+    for (int tile = warp; tile < tm * tn; tile += nw) {
+        const int i0 = (tile / tn) * 8 * TI, j0 = (tile % tn) * 8 * TJ;
+        double c[TI][TJ][2];
+        bool xin[TI], yin[TJ];
+#pragma unroll
+        for (int a = 0; a < TI; ++a) xin[a] = i0 + 8 * a + g < M;
+#pragma unroll
+        for (int b = 0; b < TJ; ++b) yin[b] = j0 + 8 * b + g < N;
+#pragma unroll
+        for (int a = 0; a < TI; ++a)
+#pragma unroll
+            for (int b = 0; b < TJ; ++b) c[a][b][0] = c[a][b][1] = 0.0;
+        const double* xp = Xt + tg * ldx + i0 + g;
+        const double* yp = Y + tg * ldy + j0 + g;
+        for (int m0 = 0; m0 < Kd; m0 += 4) {
+            const bool in = m0 + tg < Kd;
+            double x[TI], y[TJ];
+#pragma unroll
+            for (int a = 0; a < TI; ++a) x[a] = (in && xin[a]) ? xp[8 * a] : 0.0;
+#pragma unroll
+            for (int b = 0; b < TJ; ++b) y[b] = (in && yin[b]) ? yp[8 * b] : 0.0;
+#pragma unroll
+            for (int a = 0; a < TI; ++a)
+#pragma unroll
+                for (int b = 0; b < TJ; ++b)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(c[a][b][0]), "+d"(c[a][b][1]) : "d"(x[a]), "d"(y[b]));
+            xp += 4 * ldx; yp += 4 * ldy;
+        }
+#pragma unroll
+        for (int a = 0; a < TI; ++a)
+#pragma unroll
+            for (int b = 0; b < TJ; ++b) {
+                const int i = i0 + 8 * a + g, j = j0 + 8 * b + 2 * tg;
+                if (i >= M) continue;
+                double* cp = C + i * ldc + j;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    if (j + h >= N) continue;
+                    if (mode == 0) cp[h] = c[a][b][h];
+                    else if (mode == 1) cp[h] += c[a][b][h];
+                    else cp[h] -= c[a][b][h];
+                }
+            }
+    }
+}
+
 // global -> shared copy that does not pass through registers (cp.async): issued early, waited for late,
 // so the next step's A[k], B[k] and Q(k) arrive while the current step is still multiplying
 __device__ __forceinline__ void async_copy(double* dst, const double* src, int n) {
@@ -119,7 +179,7 @@ __device__ __forceinline__ void async_copy(double* dst, const double* src, int n
 }
 __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-template <bool VEC>
+template <bool VEC, bool MMA>
 __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
     extern __shared__ __align__(16) double sm[];
     const int nX = p.nX, nU = p.nU, K = p.K;
@@ -169,19 +229,40 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
                     else { const int i = c - nX; for (int m = 0; m < nX; ++m) acc += Bs[m * nU + i] * bv[m]; gv[i] = acc; }
                 }
             }
-            gemm_tn<VEC>(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
-            gemm_tn<VEC>(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
+            const int nwarps = blockDim.x >> 5;
+            if (MMA) {
+                // tensor-core schedule (16 warps): T = P A on warps 0-9 next to W = P B on warps 10-14
+                gemm_tn_dmma<2, 5>(T, nX, P, nX, As, nX, nX, nX, nX, 0, 0, 10);
+                gemm_tn_dmma<2, 3>(W, nU, P, nX, Bs, nU, nX, nU, nX, 0, 10, nwarps - 10);
+            } else {
+                gemm_tn<VEC>(T, nX, P, nX, As, nX, nX, nX, nX, 0);     // T = P A      (P symmetric: P^T = P)
+                gemm_tn<VEC>(W, nU, P, nX, Bs, nU, nX, nU, nX, 0);     // W = P B
+            }
             for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rs[e];
             __syncthreads();
             async_copy(P, Qr + (p.q_per_step ? (long)k * nX * nX : 0), nX * nX);   // P is dead: start P <- Q(k)
-            // warp 0: gamma = R + B^T P B and its LU;  the other warps meanwhile: Kp = B^T P A
-            if (threadIdx.x < 32) {
-                gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 32);
-                __syncwarp();
-                WarpTeam t;
-                if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && threadIdx.x == 0) s_fail = 1;
+            if (MMA) {
+                // gamma = R + B^T P B (3 warp tiles) next to Kp = B^T P A (6 warp tiles); then the gamma
+                // factorization on the last warp while warps 0-9 already run P <- Q(k) + A^T (P A)
+                gemm_tn_dmma<1, 3>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 3);
+                gemm_tn_dmma<1, 5>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 3, nwarps - 3);
+                async_wait();                                      // Q(k) is in P
+                __syncthreads();
+                if ((int)(threadIdx.x >> 5) == nwarps - 1) {
+                    WarpTeam t;
+                    if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && (threadIdx.x & 31) == 0) s_fail = 1;
+                }
+                gemm_tn_dmma<2, 5>(P, nX, As, nX, T, nX, nX, nX, nX, 1, 0, 10);   // P += A^T (P A)
             } else {
-                gemm_tn<VEC>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 32, (int)blockDim.x - 32);
+                // warp 0: gamma = R + B^T P B and its LU;  the other warps meanwhile: Kp = B^T P A
+                if (threadIdx.x < 32) {
+                    gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 32);
+                    __syncwarp();
+                    WarpTeam t;
+                    if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && threadIdx.x == 0) s_fail = 1;
+                } else {
+                    gemm_tn<VEC>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 32, (int)blockDim.x - 32);
+                }
             }
             __syncthreads();
             if (s_fail) break;
@@ -210,16 +291,19 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
                     bv[c] = acc;
                 }
             }
-            async_wait();                                          // Q(k) is in P
-            __syncthreads();
-            gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);     // P += A^T (P A)
-            __syncthreads();
+            if (!MMA) {
+                async_wait();                                          // Q(k) is in P
+                __syncthreads();
+                gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);     // P += A^T (P A)
+                __syncthreads();
+            }
             if (k > 0) {                                           // A, B are dead: fetch the next step's
                 async_copy(As, Ar + (long)(k - 1) * nX * nX, nX * nX);
                 async_copy(Bs, Br + (long)(k - 1) * nX * nU, nX * nU);
                 if (p.r_per_step) async_copy(Rs, Rr + (long)(k - 1) * nU * nU, nU * nU);
             }
-            gemm_tn<VEC>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);     // P -= Kp^T K[k]
+            if (MMA) gemm_tn_dmma<2, 5>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2, 0, nwarps);   // P -= Kp^T K[k]
+            else gemm_tn<VEC>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);
             __syncthreads();
             // P = (P + P^T) / 2
             for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) {
@@ -251,6 +335,18 @@ int lqr_fail(int code, const std::string& m) { last_error() = m; return code; }
 using namespace trepb;
 
 namespace {
+// CUDA events around the last Riccati launch of each device (trepb_lqr_last_kernel_ms)
+struct LqrTimer {
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    bool ok = false;
+};
+LqrTimer& lqr_timer(int device) {
+    static LqrTimer t[64];
+    LqrTimer& x = t[device & 63];
+    if (!x.ok) x.ok = cudaEventCreate(&x.e0) == cudaSuccess && cudaEventCreate(&x.e1) == cudaSuccess;
+    return x;
+}
+
 int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
@@ -265,21 +361,42 @@ int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     if (smem > (size_t)smem_optin)
         return lqr_fail(TREPB_ERR_UNSUPPORTED, "state dimension too large for the shared-memory Riccati sweep");
     const bool vec = nX % 2 == 0 && nU % 2 == 0;   // every operand block then starts 16-byte aligned with an even row length
-    const void* fn = vec ? (const void*)lqr_kernel<true> : (const void*)lqr_kernel<false>;
+    // tensor-core schedule for states large enough to fill its warp tiles (TREPB_LQR_NO_MMA=1: scalar tiles, for comparison)
+    const char* no_mma = getenv("TREPB_LQR_NO_MMA");
+    const bool mma = nX >= 32 && !(no_mma && no_mma[0] == '1');
+    const void* fn = mma ? (vec ? (const void*)lqr_kernel<true, true> : (const void*)lqr_kernel<false, true>) : vec ? (const void*)lqr_kernel<true, false> : (const void*)lqr_kernel<false, false>;
     e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     const int tiles = ((nX + 3) / 4) * ((nX + 3) / 4);
     int block = ((tiles + 31) / 32) * 32;
     if (block > 512) block = 512;
     if (block < 64) block = 64;
+    if (mma) block = 512;   // the tensor-core schedule assigns products to warps 0-9, 10-14, 15
     const long long grid = p.batch < sms ? p.batch : sms;
-    if (vec) lqr_kernel<true><<<(int)grid, block, smem, stream>>>(p);
-    else lqr_kernel<false><<<(int)grid, block, smem, stream>>>(p);
+    LqrTimer& tm = lqr_timer(device);
+    if (tm.ok) cudaEventRecord(tm.e0, stream);
+    if (mma && vec) lqr_kernel<true, true><<<(int)grid, block, smem, stream>>>(p);
+    else if (mma) lqr_kernel<false, true><<<(int)grid, block, smem, stream>>>(p);
+    else if (vec) lqr_kernel<true, false><<<(int)grid, block, smem, stream>>>(p);
+    else lqr_kernel<false, false><<<(int)grid, block, smem, stream>>>(p);
+    if (tm.ok) cudaEventRecord(tm.e1, stream);
     e = cudaGetLastError();
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
     return TREPB_OK;
 }
 }  // namespace
+
+extern "C" int trepb_lqr_last_kernel_ms(int device, float* ms) {
+    if (!ms) return lqr_fail(TREPB_ERR_INVALID, "null argument");
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    LqrTimer& tm = lqr_timer(device);
+    if (!tm.ok) return lqr_fail(TREPB_ERR_CUDA, "no events");
+    e = cudaEventSynchronize(tm.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms, tm.e0, tm.e1);
+    if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
+    return TREPB_OK;
+}
 
 extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* stream) {
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
