@@ -441,7 +441,8 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                 "ok_fraction": float((lst.download() == 0).mean()),
                 "roofline": {"bound": "fp64", "achieved": fl_step * Rl * Kl / (tl * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                              "frac": fl_step * Rl * Kl / (tl * 1e-3) / 1e12 / fp64_peak, "flops_per_unit": fl_step,
-                             "note": "CUDA events around 3 launches on the launching stream; flops counted from the matrix shapes"}})
+                             "kernel_ms_last_launch": lib.lqr_last_kernel_ms(device),
+                             "note": "CUDA events around 3 launches on the launching stream (cross-check: the library's own events around the last launch, trepb_lqr_last_kernel_ms); flops counted from the matrix shapes; products on the FP64 tensor cores (mma.sync m8n8k4), gamma solve by a CTA-wide Gauss-Jordan elimination"}})
     for b_ in (Al, Bl, Ql, Rr, Kl_out, lst):
         b_.free()
     # second derivatives, z-contracted output (the form DOptimizer.calc_newton_model consumes)

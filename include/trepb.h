@@ -296,8 +296,9 @@ typedef struct trepb_lq_args {
 int trepb_lq_batch(int device, const trepb_lq_args* args);                   /* host pointers   */
 int trepb_lq_batch_dev(int device, const trepb_lq_args* args, void* stream); /* device pointers */
 /* Device time of the last Riccati kernel launched on `device` by any of the four calls above (CUDA events on the
- * launching stream; waits for that kernel).  The nX x nX products run on the FP64 tensor cores (mma.sync m8n8k4)
- * when nX is a multiple of 80 = lcm of the 16 x 40 warp tile, on 4 x 4 register tiles otherwise.           */
+ * launching stream; waits for that kernel).  For nX >= 32 every product runs on the FP64 tensor cores
+ * (mma.sync m8n8k4, 16 x 40 warp tiles, ragged edges read as zero), below that on 4 x 4 register tiles; the
+ * gamma solve is a Gauss-Jordan elimination by the whole CTA (nU (nU + nX + 1) <= 2048).                  */
 int trepb_lqr_last_kernel_ms(int device, float* ms);
 
 /* p2 from two consecutive configurations (initialize_from_configs). q0,q1: [B][nq] -> p: [B][nd] */

@@ -179,25 +179,94 @@ __device__ __forceinline__ void async_copy(double* dst, const double* src, int n
 }
 __device__ __forceinline__ void async_wait() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// K = gamma^-1 [Kp | c] by Gauss-Jordan elimination with implicitly scaled partial pivoting, the whole CTA
+// on one system M = [gamma | Kp | c] (n rows, nc columns, leading dimension ldt): its elements are dealt
+// out to the threads (at most kGJ each; GjElems holds their offsets, computed once per kernel), every warp
+// finds the pivot of step k on its own (lane = row, two max-reductions over the bit pattern of |a| scale,
+// lowest row among equals), every element outside the pivot row and right of column k takes one fused
+// multiply-add, one __syncthreads per step.  No row is moved: order[k] = pivot row of step k, the solution
+// row k is row order[k] divided by its pivot.  (The sweep is sequential in k and this solve sits on its
+// critical path: a one-warp LU plus one right-hand side per thread took 55 % of a Riccati step.)
+// Returns false if a scaled pivot is <= tol.
+constexpr int kGJ = 4;
+struct GjElems {
+    int off[kGJ];   // i * ldt + j, or -1
+    int row[kGJ];   // i * ldt
+    int col[kGJ];   // j
+};
+__device__ __forceinline__ GjElems gj_elems(int n, int nc, int ldt) {
+    GjElems g;
+#pragma unroll
+    for (int q = 0; q < kGJ; ++q) {
+        const int e = (int)threadIdx.x + q * (int)blockDim.x;
+        const bool in = e < n * nc;
+        const int i = in ? e / nc : 0, j = e - i * nc;
+        g.off[q] = in ? i * ldt + j : -1;
+        g.row[q] = i * ldt;
+        g.col[q] = j;
+    }
+    return g;
+}
+__device__ __forceinline__ bool cta_gauss_jordan(double* M, int ldt, int n, const GjElems& g, double* scl, double* rd,
+                                                 int* order, int* done, double tol) {
+    const int tid = threadIdx.x, lane = tid & 31, nth = blockDim.x;
+    for (int i = tid; i < n; i += nth) {
+        double sm_ = -1.0;
+        for (int j = 0; j < n; ++j) { const double a = fabs(M[i * ldt + j]); if (a > sm_) sm_ = a; }
+        scl[i] = 1.0 / sm_;
+        done[i] = 0;
+    }
+    __syncthreads();
+    for (int k = 0; k < n; ++k) {
+        // pivot of column k among the rows not used yet (every warp computes the same answer)
+        double best = 0.0;
+        int br = 0x7fffffff;
+        for (int r = lane; r < n; r += 32) {
+            double v = done[r] ? 0.0 : fabs(M[r * ldt + k] * scl[r]);
+            if (!(v == v)) v = 0.0;
+            if (v > best) { best = v; br = r; }
+        }
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(best);
+        const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+        const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+        const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+        const int pr = (int)__reduce_min_sync(0xffffffffu, (hi == mh && lo == ml) ? (unsigned)br : 0x7fffffffu);
+        const double bestv = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+        if (!(bestv > tol)) return false;
+        const double* prow = M + pr * ldt;
+        const double rdk = 1.0 / prow[k];
+#pragma unroll
+        for (int q = 0; q < kGJ; ++q) {
+            if (g.off[q] < 0 || g.row[q] == pr * ldt || g.col[q] <= k) continue;
+            M[g.off[q]] -= M[g.row[q] + k] * (rdk * prow[g.col[q]]);
+        }
+        if (tid == 0) { order[k] = pr; rd[k] = rdk; done[pr] = 1; }
+        __syncthreads();
+    }
+    return true;
+}
+
 template <bool VEC, bool MMA>
 __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
     extern __shared__ __align__(16) double sm[];
     const int nX = p.nX, nU = p.nU, K = p.K;
-    const int ldg = nU | 1;                        // gamma, odd leading dimension (LU row accesses)
+    const int nct = nU + nX + 1, ldg = nct | 1;    // columns / (odd) leading dimension of M = [gamma | Kp | c]
+    const GjElems gje = gj_elems(nU, nct, ldg);
     double* P = sm;                                // [nX][nX]
     double* T = P + nX * nX;                       // P A
     double* As = T + nX * nX;                      // A[k]
     double* Bs = As + nX * nX;                     // B[k]            [nX][nU]
-    double* W = Bs + nX * nU;                      // P B [nX][nU], then K[k] [nU][nX]
+    double* W = Bs + nX * nU;                      // P B [nX][nU]
     double* Kp = W + nX * nU;                      // Kp = B^T P A    [nU][nX]
     double* Rs = Kp + nU * nX;                     // R(k)            [nU][nU]
-    double* G = Rs + ((nU * nU + 1) & ~1);         // gamma -> its LU [nU][ldg]
+    double* G = Rs + ((nU * nU + 1) & ~1);         // M = [gamma | Kp | c] [nU][ldt], eliminated in place
     double* scl = G + ((nU * ldg + 1) & ~1);       // [nU]
     double* rd = scl + nU;                         // [nU]
-    int* piv = (int*)(rd + nU);                    // [nU] + swp [nU]
-    int* swp = piv + nU;
+    int* order = (int*)(rd + nU);                  // [nU] pivot row of every elimination step + done [nU]
+    int* done = order + nU;
+    double* Ks = (double*)(done + nU);             // K[k] [nU][nX]   (2 nU ints = nU doubles: stays 8-byte aligned)
     // affine part (solve_tv_lq): b [nX], A^T b [nX], g = B^T b [nU], r(k) + g -> C[k] [nU]
-    double* bv = (double*)(swp + nU);               // 2 nU ints = nU doubles: stays 8-byte aligned
+    double* bv = Ks + nU * nX;
     double* ab = bv + nX;
     double* gv = ab + nX;
     double* cv = gv + nU;
@@ -241,77 +310,71 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
             for (int e = threadIdx.x; e < nU * nU; e += blockDim.x) G[(e / nU) * ldg + e % nU] = Rs[e];
             __syncthreads();
             async_copy(P, Qr + (p.q_per_step ? (long)k * nX * nX : 0), nX * nX);   // P is dead: start P <- Q(k)
+            // gamma = R + B^T P B and Kp = B^T P A (tensor cores: 3 + 6 warp tiles)
             if (MMA) {
-                // gamma = R + B^T P B (3 warp tiles) next to Kp = B^T P A (6 warp tiles); then the gamma
-                // factorization on the last warp while warps 0-9 already run P <- Q(k) + A^T (P A)
                 gemm_tn_dmma<1, 3>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 3);
                 gemm_tn_dmma<1, 5>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 3, nwarps - 3);
-                async_wait();                                      // Q(k) is in P
-                __syncthreads();
-                if ((int)(threadIdx.x >> 5) == nwarps - 1) {
-                    WarpTeam t;
-                    if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && (threadIdx.x & 31) == 0) s_fail = 1;
-                }
-                gemm_tn_dmma<2, 5>(P, nX, As, nX, T, nX, nX, nX, nX, 1, 0, 10);   // P += A^T (P A)
             } else {
-                // warp 0: gamma = R + B^T P B and its LU;  the other warps meanwhile: Kp = B^T P A
-                if (threadIdx.x < 32) {
-                    gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1, 0, 32);
-                    __syncwarp();
-                    WarpTeam t;
-                    if (!team_lu(t, G, ldg, nU, 0, piv, swp, scl, rd, 1e-300) && threadIdx.x == 0) s_fail = 1;
-                } else {
-                    gemm_tn<VEC>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0, 32, (int)blockDim.x - 32);
-                }
+                gemm_tn<VEC>(G, ldg, Bs, nU, W, nU, nU, nU, nX, 1);
+                gemm_tn<VEC>(Kp, nX, Bs, nU, T, nX, nU, nX, nX, 0);
+            }
+            async_wait();                                          // Q(k) is in P
+            __syncthreads();
+            // P += A^T (P A) next to the set-up of the solve: Kp += S(k)^T (cross term), W <- Kp, c = r(k) + B^T b
+            if (MMA) gemm_tn_dmma<2, 5>(P, nX, As, nX, T, nX, nX, nX, nX, 1, 0, 10);
+            else gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) {
+                const int i = e / nX, c = e - i * nX;
+                double v = Kp[e];
+                if (Sr) { v += Sr[(long)k * nX * nU + c * nU + i]; Kp[e] = v; }
+                G[i * ldg + nU + c] = v;
+            }
+            for (int i = threadIdx.x; i < nU; i += blockDim.x) {
+                double c = 0.0;
+                if (affine) { gv[i] += rr[(long)k * nU + i]; c = gv[i]; }   // gv = r + B^T b
+                G[i * ldg + nU + nX] = c;
             }
             __syncthreads();
-            if (s_fail) break;
-            // K[k] = gamma^-1 Kp, one right-hand side per thread (W is free: it becomes K[k], [nU][nX]);
-            // with a cross term Kp = B^T P A + S(k)^T; the affine right-hand side B^T b + r(k) is one more column
-            for (int c = threadIdx.x; c < nX + (affine ? 1 : 0); c += blockDim.x) {
-                if (c < nX) {
-                    if (Sr) { const double* Sk = Sr + (long)k * nX * nU + c * nU; for (int i = 0; i < nU; ++i) Kp[i * nX + c] += Sk[i]; }
-                    for (int i = 0; i < nU; ++i) W[i * nX + c] = Kp[i * nX + c];
-                    col_solve(G, ldg, nU, swp, rd, W + c, nX);
-                } else {
-                    for (int i = 0; i < nU; ++i) { gv[i] += rr[(long)k * nU + i]; cv[i] = gv[i]; }   // gv = r + B^T b
-                    col_solve(G, ldg, nU, swp, rd, cv, 1);
-                    double* Ck = p.C + (r * (long)K + k) * nU;
-                    for (int i = 0; i < nU; ++i) Ck[i] = cv[i];
-                }
+            // K[k] = gamma^-1 Kp and C[k] = gamma^-1 (r + B^T b)
+            if (!cta_gauss_jordan(G, ldg, nU, gje, scl, rd, order, done, 1e-300)) {
+                s_fail = 1;   // every thread takes this branch (the pivots are computed redundantly by every warp)
+                break;
+            }
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) {
+                const int i = e / nX;
+                Ks[e] = G[order[i] * ldg + nU + (e - i * nX)] * rd[i];
+            }
+            if (affine) {
+                double* Ck = p.C + (r * (long)K + k) * nU;
+                for (int i = threadIdx.x; i < nU; i += blockDim.x) Ck[i] = G[order[i] * ldg + nU + nX] * rd[i];
             }
             __syncthreads();
             double* Kk = Kr + (long)k * nU * nX;
-            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) Kk[e] = W[e];
+            for (int e = threadIdx.x; e < nU * nX; e += blockDim.x) Kk[e] = Ks[e];
             if (affine) {
                 // b = q[k] - K^T r + (A^T - K^T B^T) b = q[k] + A^T b - K^T (r + B^T b)
                 for (int c = threadIdx.x; c < nX; c += blockDim.x) {
                     double acc = qr[(long)k * nX + c] + ab[c];
-                    for (int i = 0; i < nU; ++i) acc -= W[i * nX + c] * gv[i];
+                    for (int i = 0; i < nU; ++i) acc -= Ks[i * nX + c] * gv[i];
                     bv[c] = acc;
                 }
-            }
-            if (!MMA) {
-                async_wait();                                          // Q(k) is in P
-                __syncthreads();
-                gemm_tn<VEC>(P, nX, As, nX, T, nX, nX, nX, nX, 1);     // P += A^T (P A)
-                __syncthreads();
             }
             if (k > 0) {                                           // A, B are dead: fetch the next step's
                 async_copy(As, Ar + (long)(k - 1) * nX * nX, nX * nX);
                 async_copy(Bs, Br + (long)(k - 1) * nX * nU, nX * nU);
                 if (p.r_per_step) async_copy(Rs, Rr + (long)(k - 1) * nU * nU, nU * nU);
             }
-            if (MMA) gemm_tn_dmma<2, 5>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2, 0, nwarps);   // P -= Kp^T K[k]
-            else gemm_tn<VEC>(P, nX, Kp, nX, W, nX, nX, nX, nU, 2);
+            if (MMA) gemm_tn_dmma<2, 5>(P, nX, Kp, nX, Ks, nX, nX, nX, nU, 2, 0, nwarps);   // P -= Kp^T K[k]
+            else gemm_tn<VEC>(P, nX, Kp, nX, Ks, nX, nX, nX, nU, 2);
             __syncthreads();
-            // P = (P + P^T) / 2
-            for (int e = threadIdx.x; e < nX * nX; e += blockDim.x) {
-                const int i = e / nX, j = e - i * nX;
-                if (i < j) {
-                    const double v = (P[i * nX + j] + P[j * nX + i]) / 2.0;
-                    P[i * nX + j] = v;
-                    P[j * nX + i] = v;
+            // P = (P + P^T) / 2, one off-diagonal per warp pass: (i, i + d) and its mirror are both read with
+            // stride nX + 1 (a row-by-row sweep reads the mirror with stride nX: a 32-way bank conflict at nX = 80)
+            for (int d = 1 + (int)(threadIdx.x >> 5); d < nX; d += nwarps) {
+                for (int i = threadIdx.x & 31; i + d < nX; i += 32) {
+                    const int a = i * nX + i + d, b = (i + d) * nX + i;
+                    const double v = (P[a] + P[b]) / 2.0;
+                    P[a] = v;
+                    P[b] = v;
                 }
             }
         }
@@ -350,8 +413,8 @@ LqrTimer& lqr_timer(int device) {
 int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return lqr_fail(TREPB_ERR_CUDA, cudaGetErrorString(e));
-    const int nX = p.nX, nU = p.nU, ldg = nU | 1;
-    const size_t doubles = 3 * (size_t)nX * nX + 3 * (size_t)nX * nU + (size_t)nU * nU + (size_t)nU * ldg + 4 * (size_t)nU + 16
+    const int nX = p.nX, nU = p.nU, ldg = (nU + nX + 1) | 1;
+    const size_t doubles = 3 * (size_t)nX * nX + 4 * (size_t)nX * nU + (size_t)nU * nU + (size_t)nU * ldg + 4 * (size_t)nU + 16
                            + 2 * (size_t)nX + 2 * (size_t)nU + 2;
     const size_t smem = doubles * sizeof(double);
     int smem_optin = 0, sms = 0;
@@ -371,8 +434,16 @@ int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     int block = ((tiles + 31) / 32) * 32;
     if (block > 512) block = 512;
     if (block < 64) block = 64;
-    if (mma) block = 512;   // the tensor-core schedule assigns products to warps 0-9, 10-14, 15
-    const long long grid = p.batch < sms ? p.batch : sms;
+    if (mma) block = 512;   // the tensor-core schedule assigns products to warps 0-9 and 10-14
+    // the elimination deals the nU x (nU + nX + 1) elements of [gamma | Kp | c] out to the threads, at most 4 each
+    while (block < 512 && (long long)nU * (nU + nX + 1) > 4LL * block) block += 32;
+    if ((long long)nU * (nU + nX + 1) > 4LL * block)
+        return lqr_fail(TREPB_ERR_UNSUPPORTED, "input dimension too large for the in-kernel gamma solve");
+    // small systems: as many CTAs per SM as registers / shared memory allow (one rollout per CTA)
+    int occ = 1;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, block, smem) != cudaSuccess || occ < 1) occ = 1;
+    const long long slots = (long long)sms * occ;
+    const long long grid = p.batch < slots ? p.batch : slots;
     LqrTimer& tm = lqr_timer(device);
     if (tm.ok) cudaEventRecord(tm.e0, stream);
     if (mma && vec) lqr_kernel<true, true><<<(int)grid, block, smem, stream>>>(p);
