@@ -112,3 +112,16 @@ def test_product_never_imports_the_oracle():
                 assert not pat.search(open(os.path.join(root, f)).read()), f
             if f.endswith((".cu", ".cuh", ".h", ".cc")):
                 assert "oracle" not in open(os.path.join(root, f)).read(), f
+
+
+def test_every_batch_entry_point_opens_an_nvtx_range():
+    """the reference brackets its hot calls with callgrind markers
+    (trep/_trep/midpointvi.c:2674-2738); here every batch entry point of the C ABI opens an NVTX range named
+    after itself (trepb_nvtx.h)."""
+    import re
+    csrc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "trep_b200", "csrc")
+    text = "".join(open(os.path.join(csrc, f)).read() for f in ("trepb_api.cu", "trepb_lqr.cu", "trepb_comm.cu"))
+    marked = set(re.findall(r'TREPB_NVTX\("(trepb_[a-z0-9_]+)"\)', text))
+    from trep_b200 import lib
+    want = {n for n in lib.EXPORTS if n.endswith("_batch") or n.endswith("_batch_dev")}
+    assert want and want <= marked, sorted(want - marked)

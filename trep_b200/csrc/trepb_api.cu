@@ -1,6 +1,7 @@
 // C ABI of libtrepb.so (include/trepb.h): system handles, launch geometry, host<->device staging.
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
+#include "trepb_nvtx.h"
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -134,6 +135,7 @@ const char* trepb_specialized_name(int i) {
 }
 
 int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out) {
+    TREPB_NVTX("trepb_system_create");
     if (!out) return fail(TREPB_ERR_INVALID, "null output handle");
     *out = nullptr;
     trepb_system* s = new trepb_system();
@@ -410,6 +412,7 @@ struct Timed {
 extern "C" {
 
 int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream) {
+    TREPB_NVTX("trepb_step_batch_dev");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     const RtSys& ps = s->P.proto;
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
@@ -447,6 +450,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
 }
 
 int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* stream) {
+    TREPB_NVTX("trepb_project_batch_dev");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
     if (!a->bX || !a->bU || !a->Kfb || !a->X || !a->U || !a->status)
@@ -508,6 +512,7 @@ extern "C" {
 
 int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1,
                             double* pout, void* stream) {
+    TREPB_NVTX("trepb_calc_p2_batch_dev");
     if (!s || !q0 || !q1 || !pout) return fail(TREPB_ERR_INVALID, "null argument");
     if (batch < 0 || !(dt != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or dt");
     P2Params p{};
@@ -517,6 +522,7 @@ int trepb_calc_p2_batch_dev(trepb_system* s, int64_t batch, double dt, const dou
 
 int trepb_calc_f_batch_dev(trepb_system* s, int64_t batch, double t1, double t2, const double* q1, const double* q2,
                            const double* p1, const double* u1, const double* lambda1, double* f, void* stream) {
+    TREPB_NVTX("trepb_calc_f_batch_dev");
     if (!s || !q1 || !q2 || !p1 || !f) return fail(TREPB_ERR_INVALID, "null argument");
     if (batch < 0 || !(t2 - t1 != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or t2 == t1");
     P2Params p{};
@@ -527,6 +533,7 @@ int trepb_calc_f_batch_dev(trepb_system* s, int64_t batch, double t1, double t2,
 
 int trepb_discrete_fm2_batch_dev(trepb_system* s, int64_t batch, double t1, double t2, const double* q1,
                                  const double* q2, const double* u1, double* fm2, void* stream) {
+    TREPB_NVTX("trepb_discrete_fm2_batch_dev");
     if (!s || !q1 || !q2 || !fm2) return fail(TREPB_ERR_INVALID, "null argument");
     if (batch < 0 || !(t2 - t1 != 0.0)) return fail(TREPB_ERR_INVALID, "bad batch or t2 == t1");
     P2Params p{};
@@ -593,12 +600,14 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
 extern "C" {
 
 int trepb_linearize_batch_dev(trepb_system* s, const trepb_lin_args* a, void* stream) {
+    TREPB_NVTX("trepb_linearize_batch_dev");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(s->mu);
     return lin_launch(s, a, (cudaStream_t)stream, nullptr, 0);
 }
 
 int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream_) {
+    TREPB_NVTX("trepb_deriv2_batch_dev");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     const RtSys& ps = s->P.proto;
     const int nd = ps.nd, nk = ps.nk, nq = nd + nk, nu = ps.nu, nc = ps.nc;
@@ -820,6 +829,7 @@ struct Stager {
 extern "C" {
 
 int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
+    TREPB_NVTX("trepb_step_batch");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
@@ -843,6 +853,7 @@ int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
 }
 
 int trepb_project_batch(trepb_system* s, const trepb_project_args* a) {
+    TREPB_NVTX("trepb_project_batch");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->batch < 0 || a->nsteps < 1) return fail(TREPB_ERR_INVALID, "batch must be >= 0 and nsteps >= 1");
@@ -863,6 +874,7 @@ int trepb_project_batch(trepb_system* s, const trepb_project_args* a) {
 }
 
 int trepb_calc_p2_batch(trepb_system* s, int64_t batch, double dt, const double* q0, const double* q1, double* p) {
+    TREPB_NVTX("trepb_calc_p2_batch");
     if (!s) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
@@ -881,6 +893,7 @@ int trepb_calc_p2_batch(trepb_system* s, int64_t batch, double dt, const double*
 
 int trepb_calc_f_batch(trepb_system* s, int64_t batch, double t1, double t2, const double* q1, const double* q2,
                        const double* p1, const double* u1, const double* lambda1, double* f) {
+    TREPB_NVTX("trepb_calc_f_batch");
     if (!s) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
@@ -899,6 +912,7 @@ int trepb_calc_f_batch(trepb_system* s, int64_t batch, double t1, double t2, con
 
 int trepb_discrete_fm2_batch(trepb_system* s, int64_t batch, double t1, double t2, const double* q1,
                              const double* q2, const double* u1, double* fm2) {
+    TREPB_NVTX("trepb_discrete_fm2_batch");
     if (!s) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
@@ -944,6 +958,7 @@ void stage_lin(Stager& st, const trepb_system* s, const trepb_lin_args* a, trepb
 extern "C" {
 
 int trepb_deriv2_batch(trepb_system* s, const trepb_d2_args* a) {
+    TREPB_NVTX("trepb_deriv2_batch");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->lin.batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
@@ -972,6 +987,7 @@ int trepb_deriv2_batch(trepb_system* s, const trepb_d2_args* a) {
 }
 
 int trepb_linearize_batch(trepb_system* s, const trepb_lin_args* a) {
+    TREPB_NVTX("trepb_linearize_batch");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
@@ -1038,6 +1054,7 @@ __global__ void sincos_kernel(const double* x, double* s, double* c, long long n
 }  // namespace
 
 extern "C" int trepb_sincos_batch(int device, int64_t n, const double* x, double* s, double* c) {
+    TREPB_NVTX("trepb_sincos_batch");
     if (n < 0 || (n > 0 && (!x || !s || !c))) return fail(TREPB_ERR_INVALID, "null argument");
     if (n == 0) return TREPB_OK;
     CU(cudaSetDevice(device));

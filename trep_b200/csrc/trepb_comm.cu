@@ -14,6 +14,7 @@
 //       pointers of trepb_linearize_batch_dev and the linearize kernel's own stores land in the root's
 //       HBM - the gather is fused into the kernel, there is no second pass over the data.
 #include <cuda_runtime.h>
+#include "trepb_nvtx.h"
 #include <dlfcn.h>
 #include <nccl.h>   // types and enums only; every function is looked up with dlsym
 #include <stdlib.h>
@@ -82,6 +83,7 @@ struct trepb_comm {
 extern "C" {
 
 int trepb_comm_available(int* version) {
+    TREPB_NVTX("trepb_comm_available");
     Nccl& n = nccl();
     if (!n.h) return cfail(TREPB_ERR_UNSUPPORTED, n.why);
     if (version) { int v = 0; n.GetVersion(&v); *version = v; }
@@ -89,6 +91,7 @@ int trepb_comm_available(int* version) {
 }
 
 int trepb_comm_unique_id(char* id) {
+    TREPB_NVTX("trepb_comm_unique_id");
     static_assert(sizeof(ncclUniqueId) == TREPB_COMM_ID_BYTES, "TREPB_COMM_ID_BYTES must be sizeof(ncclUniqueId)");
     if (!id) return cfail(TREPB_ERR_INVALID, "null argument");
     Nccl& n = nccl();
@@ -100,6 +103,7 @@ int trepb_comm_unique_id(char* id) {
 }
 
 int trepb_comm_create(int device, int rank, int nranks, const char* id, trepb_comm** out) {
+    TREPB_NVTX("trepb_comm_create");
     if (!out || !id) return cfail(TREPB_ERR_INVALID, "null argument");
     *out = nullptr;
     if (nranks < 1 || rank < 0 || rank >= nranks) return cfail(TREPB_ERR_INVALID, "rank must be in [0, nranks)");
@@ -124,6 +128,7 @@ void trepb_comm_destroy(trepb_comm* c) {
 }
 
 int trepb_comm_rank(const trepb_comm* c, int* rank, int* nranks) {
+    TREPB_NVTX("trepb_comm_rank");
     if (!c) return cfail(TREPB_ERR_INVALID, "null communicator");
     if (rank) *rank = c->rank;
     if (nranks) *nranks = c->nranks;
@@ -131,6 +136,7 @@ int trepb_comm_rank(const trepb_comm* c, int* rank, int* nranks) {
 }
 
 int trepb_comm_allgather_dev(trepb_comm* c, const void* send, void* recv, int64_t bytes_per_rank, void* stream) {
+    TREPB_NVTX("trepb_comm_allgather_dev");
     if (!c || !recv || (!send && bytes_per_rank > 0)) return cfail(TREPB_ERR_INVALID, "null argument");
     if (bytes_per_rank < 0) return cfail(TREPB_ERR_INVALID, "bytes_per_rank must be >= 0");
     if (bytes_per_rank == 0) return TREPB_OK;
@@ -143,6 +149,7 @@ int trepb_comm_allgather_dev(trepb_comm* c, const void* send, void* recv, int64_
 }
 
 int trepb_comm_gather_dev(trepb_comm* c, const void* send, void* recv, int64_t bytes_per_rank, int root, void* stream) {
+    TREPB_NVTX("trepb_comm_gather_dev");
     if (!c || (!send && bytes_per_rank > 0)) return cfail(TREPB_ERR_INVALID, "null argument");
     if (root < 0 || root >= c->nranks) return cfail(TREPB_ERR_INVALID, "root out of range");
     if (c->rank == root && !recv) return cfail(TREPB_ERR_INVALID, "the root needs a receive buffer");
@@ -171,6 +178,7 @@ int trepb_comm_gather_dev(trepb_comm* c, const void* send, void* recv, int64_t b
 
 // ---- peer-mapped slabs (CUDA IPC) ---------------------------------------------------------------
 int trepb_ipc_export(int device, const void* ptr, char* handle) {
+    TREPB_NVTX("trepb_ipc_export");
     static_assert(sizeof(cudaIpcMemHandle_t) == TREPB_IPC_HANDLE_BYTES, "TREPB_IPC_HANDLE_BYTES must be sizeof(cudaIpcMemHandle_t)");
     if (!ptr || !handle) return cfail(TREPB_ERR_INVALID, "null argument");
     CUC(cudaSetDevice(device));
@@ -181,6 +189,7 @@ int trepb_ipc_export(int device, const void* ptr, char* handle) {
 }
 
 int trepb_ipc_open(int device, const char* handle, void** ptr) {
+    TREPB_NVTX("trepb_ipc_open");
     if (!handle || !ptr) return cfail(TREPB_ERR_INVALID, "null argument");
     CUC(cudaSetDevice(device));
     cudaIpcMemHandle_t h;
@@ -190,6 +199,7 @@ int trepb_ipc_open(int device, const char* handle, void** ptr) {
 }
 
 int trepb_ipc_close(int device, void* ptr) {
+    TREPB_NVTX("trepb_ipc_close");
     if (!ptr) return TREPB_OK;
     CUC(cudaSetDevice(device));
     CUC(cudaIpcCloseMemHandle(ptr));

@@ -14,6 +14,7 @@
 // right-hand sides are then solved one per thread; A[k-1], B[k-1] and Q(k) are fetched with cp.async
 // while the current step is still multiplying.
 #include <cuda_runtime.h>
+#include "trepb_nvtx.h"
 #include <stdlib.h>
 #include <string>
 #include "../../include/trepb.h"
@@ -470,6 +471,7 @@ extern "C" int trepb_lqr_last_kernel_ms(int device, float* ms) {
 }
 
 extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* stream) {
+    TREPB_NVTX("trepb_lqr_batch_dev");
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
     if (!a->A || !a->B || !a->Q || !a->R || !a->Kfb || !a->status) return lqr_fail(TREPB_ERR_INVALID, "A, B, Q, R, Kfb and status are required");
@@ -482,6 +484,7 @@ extern "C" int trepb_lqr_batch_dev(int device, const trepb_lqr_args* a, void* st
 }
 
 extern "C" int trepb_lq_batch_dev(int device, const trepb_lq_args* a, void* stream) {
+    TREPB_NVTX("trepb_lq_batch_dev");
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
     if (!a->A || !a->B || !a->Q || !a->R || !a->q || !a->r || !a->Kfb || !a->C || !a->status)
@@ -499,6 +502,7 @@ extern "C" int trepb_lq_batch_dev(int device, const trepb_lq_args* a, void* stre
 }
 
 extern "C" int trepb_lq_batch(int device, const trepb_lq_args* a) {
+    TREPB_NVTX("trepb_lq_batch");
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
     if (!a->A || !a->B || !a->Q || !a->R || !a->q || !a->r || !a->Kfb || !a->C || !a->status)
@@ -539,6 +543,7 @@ extern "C" int trepb_lq_batch(int device, const trepb_lq_args* a) {
 }
 
 extern "C" int trepb_lqr_batch(int device, const trepb_lqr_args* a) {
+    TREPB_NVTX("trepb_lqr_batch");
     if (!a) return lqr_fail(TREPB_ERR_INVALID, "null argument");
     if (a->batch < 0 || a->nsteps < 1 || a->nX < 1 || a->nU < 1) return lqr_fail(TREPB_ERR_INVALID, "bad sizes");
     if (a->batch == 0) return TREPB_OK;
