@@ -770,6 +770,29 @@ def multi_gpu(lib, systems, group, device, rank, world, reduce_max, fp64_peak, h
     return out
 
 
+def w1_cpu_reference(lines):
+    """BASELINE config 0 beside the reference: the same N-link pendulum rollout on ONE host core through the
+    reference's own C (oracle/_ref via oracle/ref_harness.c) - its per-core rate and its per-step latency -
+    attached to the W1 lines."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import cpu_baseline as cb
+    for links in (1, 5):
+        h = cb.Harness("pendulum%d" % links)
+        q0 = np.zeros((1, links)); q0[0, 0] = np.pi / 4
+        h.mvi.initialize_from_configs(0.0, q0[0], DT, q0[0])
+        p0 = np.array([h.mvi.p2], float).reshape(1, links)
+        h.rollouts(q0, p0, 200, DT, DT)
+        nsteps, t0 = 4000 if links == 1 else 1000, time.perf_counter()
+        h.rollouts(q0, p0, nsteps, DT, DT)
+        dt_ = time.perf_counter() - t0
+        for m in lines:
+            if m["metric"].startswith("DEL steps/s (W1: %d-link" % links):
+                m["reference_one_core"] = {"steps_per_s": nsteps / dt_, "us_per_step": dt_ * 1e6 / nsteps,
+                                           "sample": "one rollout of %d steps, oracle/_ref in the C loop of oracle/ref_harness.c" % nsteps}
+                if m.get("us_per_step"):
+                    m["latency_vs_reference_core"] = (dt_ * 1e6 / nsteps) / m["us_per_step"]
+
+
 def cpu_baseline_sample():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import cpu_baseline as cb
@@ -942,6 +965,8 @@ def main():
             line["secondary"] = multi
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_sample()
+            if "secondary" in line:
+                w1_cpu_reference(line["secondary"])
         print(json.dumps(line))
     if dist is not None:
         dist.barrier()

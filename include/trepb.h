@@ -132,6 +132,13 @@ typedef struct trepb_system trepb_system; /* opaque */
 #define TREPB_FLAG_NO_LITERAL 16     /* specialised systems: skip an all-literal instantiation built for exactly this
                                        description and use the run-time-parameter kernel of its structure */
 
+/* Loads a plug-in built by trep_b200/build.py:build_plugin from a system description: ahead-of-time specialised
+ * (register-resident) kernels for a structure the library was not built with - the role the reference gives to
+ * compiling a system's own C plugins.  *n_added (may be NULL) receives the number of kernel sets registered;
+ * a library that registers none (not a plug-in, or loaded before) is TREPB_ERR_INVALID.  trepb_system_create
+ * then matches the structure like a built-in one (parameters stay run-time data).                           */
+int  trepb_load_plugin(const char* path, int* n_added);
+
 int  trepb_abi_version(void);
 const char* trepb_last_error(void);
 

@@ -1,0 +1,63 @@
+"""Plug-in kernels (trepb_load_plugin): a user system the library was not built with runs on ahead-of-time
+specialised, register-resident kernels after its structure was compiled into a plug-in.  (Last test module on
+purpose: loading the plug-in changes which kernel later System() calls for that structure pick.)"""
+import os
+import shutil
+
+import numpy as np
+import pytest
+
+import golden_util as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from trep_b200 import lib as L
+    if L.device_count() < 1:
+        pytest.skip("needs a CUDA device")
+    return L
+
+
+def test_plugin_kernel_matches_the_reference(lib):
+    from trep_b200 import build
+    name = "damper_only"
+    d = G.desc(name)
+    g = G.golden(name)
+    before = lib.System(d)
+    assert not before.specialized and before.kernel_name == "general"
+    ref = before.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
+                           q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+    path = os.path.join(os.path.dirname(build.LIB), "libtrepb_plugin_%s.so" % name)
+    if not os.path.exists(path):
+        if shutil.which(build.NVCC) is None:
+            pytest.skip("plug-in not prebuilt and no nvcc on this box")
+        path = build.build_plugin(d, name)
+    assert lib.load_plugin(path) == 1
+    s = lib.System(d)
+    assert s.specialized and s.kernel_name == name
+    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
+                      q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+    assert np.all(out["status"] == 0)
+    for k in ("q2", "p2", "A", "B"):
+        G.assert_close(out[k], g["case_" + k], "plugin %s" % k)
+        G.assert_close(out[k], ref[k], "plugin vs table-driven %s" % k)
+    for k in G.RAW:
+        G.assert_close(out[k], g["case_" + k], "plugin %s" % k)
+    assert np.array_equal(out["iters"], g["case_iters"])
+    # throughput: plug-in against the table-driven kernel on the same batch
+    rng = np.random.default_rng(0)
+    B = 1 << 18
+    q = rng.uniform(-1.0, 1.0, (B, d.nq))
+    p = rng.normal(0, 0.5, (B, d.nd))
+    t = {}
+    for label, sysm in (("general", before), ("plugin", s)):
+        o = sysm.step(q, p, 0.01, 0.01, nsteps=20)
+        t[label] = (o, sysm.last_kernel_ms())
+    ok = (t["general"][0]["status"] == 0) & (t["plugin"][0]["status"] == 0)
+    assert ok.mean() > 0.99
+    G.assert_close(t["plugin"][0]["q2"][ok], t["general"][0]["q2"][ok], "plugin rollout q2", rtol=1e-7)
+    print("damper_only 2^18 x 20 steps: table-driven %.2f ms, plug-in %.2f ms (%.1fx)" % (
+        t["general"][1], t["plugin"][1], t["general"][1] / t["plugin"][1]))
+    assert t["plugin"][1] < t["general"][1]

@@ -125,3 +125,19 @@ def test_every_batch_entry_point_opens_an_nvtx_range():
     from trep_b200 import lib
     want = {n for n in lib.EXPORTS if n.endswith("_batch") or n.endswith("_batch_dev")}
     assert want and want <= marked, sorted(want - marked)
+
+
+def test_plugin_adds_a_specialised_kernel_for_a_user_system():
+    """A system the library was not built with (the LinearDamper pair of tests/golden/damper_only.npz) gets its
+    register-resident kernels from a plug-in: build_plugin generates and compiles the specialisation unit,
+    trepb_load_plugin registers it (no GPU needed for either)."""
+    d = systems.named_desc("damper_only")
+    before = [lib.raw().trepb_specialized_name(i) for i in range(lib.raw().trepb_num_specialized())]
+    assert b"damper_only" not in before
+    path = build.build_plugin(d, "damper_only")
+    assert os.path.exists(path)
+    assert lib.load_plugin(path) == 1
+    names = [lib.raw().trepb_specialized_name(i) for i in range(lib.raw().trepb_num_specialized())]
+    assert b"damper_only" in names
+    with pytest.raises(Exception):
+        lib.load_plugin(path)            # already loaded: registers nothing

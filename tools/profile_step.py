@@ -23,6 +23,19 @@ if mode in ("step", "all"):
     lib.synchronize(0)
     print("step: B=%d nsteps=%d ms=%.3f iters/step=%.3f" % (B, nsteps, s.last_kernel_ms(), it.download().mean() / nsteps))
 
+if mode in ("pend5", "all"):
+    B, nsteps = 1 << 18, 20
+    d = systems.named_desc("pendulum5"); s = lib.System(d)
+    q0 = np.zeros((B, 5)); q0[:, 0] = rng.uniform(-np.pi, np.pi, B)
+    dq = up(q0); dp = lib.DeviceBuffer(0, (B, 5))
+    s.calc_p2_raw(True, B, 0.01, dq, dq, dp)
+    q2 = lib.DeviceBuffer(0, (B, 5)); p2 = lib.DeviceBuffer(0, (B, 5))
+    it = lib.DeviceBuffer(0, (B,), np.int32); st = lib.DeviceBuffer(0, (B,), np.int32)
+    for _ in range(2):
+        s.step_raw(True, B, nsteps, 0.01, 0.01, dq, dp, None, None, None, None, q2, p2, None, it, st)
+    lib.synchronize(0)
+    print("pend5: B=%d nsteps=%d ms=%.3f iters/step=%.3f" % (B, nsteps, s.last_kernel_ms(), it.download().mean() / nsteps))
+
 if mode in ("dual", "all"):
     B, nsteps = 1 << 20, 50
     d = systems.named_desc("dual_pendulums"); s = lib.System(d)

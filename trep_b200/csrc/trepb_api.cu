@@ -2,6 +2,7 @@
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include <cuda_runtime.h>
 #include "trepb_nvtx.h"
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -132,6 +133,25 @@ int trepb_num_specialized(void) { return spec_registry().n; }
 const char* trepb_specialized_name(int i) {
     SpecRegistry& r = spec_registry();
     return (i >= 0 && i < r.n) ? r.sets[i]->name : nullptr;
+}
+
+// A plug-in is a shared library made of generated specialisation units (trep_b200/build.py: build_plugin):
+// loading it runs their static registrars, which add the kernel sets to this library's registries, so that
+// trepb_system_create finds a register-resident kernel for a user's own system structure without the library
+// being rebuilt.  The plug-in stays loaded for the life of the process (the registries point into it).
+int trepb_load_plugin(const char* path, int* n_added) {
+    if (n_added) *n_added = 0;
+    if (!path) return fail(TREPB_ERR_INVALID, "null path");
+    const int before = spec_registry().n + coop_registry().n;
+    void* h = dlopen(path, RTLD_NOW | RTLD_LOCAL);
+    if (!h) {
+        const char* why = dlerror();
+        return fail(TREPB_ERR_INVALID, std::string("cannot load plug-in: ") + (why ? why : path));
+    }
+    const int added = spec_registry().n + coop_registry().n - before;
+    if (added <= 0) return fail(TREPB_ERR_INVALID, "the library registered no kernel set (not a trepb plug-in, loaded before, or the registry is full)");
+    if (n_added) *n_added = added;
+    return TREPB_OK;
 }
 
 int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_system** out) {

@@ -149,7 +149,7 @@ EXPORTS = [
     "trepb_kernel_info", "trepb_validate", "trepb_codegen", "trepb_codegen_literal", "trepb_desc_hash", "trepb_struct_hash", "trepb_coop_dims",
     "trepb_num_specialized", "trepb_specialized_name", "trepb_step_batch", "trepb_step_batch_dev",
     "trepb_calc_p2_batch", "trepb_calc_p2_batch_dev", "trepb_calc_f_batch", "trepb_calc_f_batch_dev",
-    "trepb_discrete_fm2_batch", "trepb_discrete_fm2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_lqr_last_kernel_ms", "trepb_linearize_batch",
+    "trepb_discrete_fm2_batch", "trepb_discrete_fm2_batch_dev", "trepb_project_batch", "trepb_project_batch_dev", "trepb_lqr_batch", "trepb_lqr_batch_dev", "trepb_lq_batch", "trepb_lq_batch_dev", "trepb_lqr_last_kernel_ms", "trepb_load_plugin", "trepb_linearize_batch",
     "trepb_linearize_batch_dev", "trepb_deriv2_batch", "trepb_deriv2_batch_dev", "trepb_device_count", "trepb_malloc", "trepb_free",
     "trepb_host_alloc", "trepb_host_free", "trepb_memset", "trepb_memcpy_h2d", "trepb_memcpy_d2h", "trepb_memcpy_d2d",
     "trepb_comm_available", "trepb_comm_unique_id", "trepb_comm_create", "trepb_comm_destroy", "trepb_comm_rank",
@@ -200,6 +200,14 @@ def lqr_raw(on_device, device, batch, nsteps, nX, nU, A, B, Q, R, Kfb, status, P
         _check(_lib.trepb_lqr_batch_dev(device, C.byref(a), stream))
     else:
         _check(_lib.trepb_lqr_batch(device, C.byref(a)))
+
+
+def load_plugin(path):
+    """Load a plug-in of specialised kernels (trep_b200.build.build_plugin); returns the number of kernel sets it added."""
+    _lib.trepb_load_plugin.argtypes = [C.c_char_p, C.POINTER(C.c_int)]
+    n = C.c_int(0)
+    _check(_lib.trepb_load_plugin(os.fspath(path).encode(), C.byref(n)))
+    return int(n.value)
 
 
 def lqr_last_kernel_ms(device=0):
