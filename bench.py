@@ -364,10 +364,11 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                                  "flops_per_unit": fl, "traffic": tb * B if tb else None,
                                  "hbm": {"achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                          "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg},
-                                 "note": "cooperative kernel: one warp per instance, link tables + 30 KB workspace per instance in shared "
-                                         "memory (8 instances per SM); DRAM traffic is the A/B output only. Issue-bound: fp64 "
-                                         "instructions are ~1/5 of the issued instructions and 7 warps per SM cannot hide the "
-                                         "dependent-issue latency (ncu: profiles/r01d_coop_lin_raw.txt; DESIGN.md section 6)"}
+                                 "note": "cooperative kernel: two warps per instance, link tables + 27 KB workspace per instance in shared "
+                                         "memory (8 instances = 16 warps per SM); DRAM traffic is the A/B output only. Latency-bound on "
+                                         "chip: 65 k warp instructions per linearization at ~6.5 cycles each, fp64 pipe ~15 % active; the "
+                                         "flops are the kernel's executed count (ncu sass counters), so frac is pipe utilisation "
+                                         "(ncu: profiles/r02i_coop_lin_pair_lines.txt; DESIGN.md section 4b)"}
     out.append(entry)
     # the same batch through the thread-per-instance table-driven kernel (the round's starting point)
     s_thr = lib.System(d, device=device, cooperative=False)
@@ -916,7 +917,7 @@ def main():
         for b in (dq0, dq1, dp, q2, p2, it, st, flush):
             b.free()
         group = D_.Group(device=device, exchange=D_.TorchExchange(dist))
-        hbm_peak_ = 6451.2
+        hbm_peak_ = 6525.9
         mp_ = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(mp_):
             hbm_peak_ = json.load(open(mp_)).get("hbm_gbs", hbm_peak_)
@@ -933,13 +934,17 @@ def main():
                 "traffic_note": "algorithmic HBM bytes per launch (16 B in + 24 B out per rollout of 1000 steps); ncu "
                                 "dram__bytes of a 50-step launch: 16.8 MB read, <1 KB written back before the kernel ends "
                                 "(profiles/r01c_step_raw.txt) - the kernel is on-chip",
-                "kernel": "step_kernel<damped_pendulum>", "kernel_ms": kms}
+                "kernel": "step_kernel<damped_pendulum>", "kernel_ms": kms,
+                "flops_kind": "executed fp64 operations per DEL step (fma = 2, add, mul; libdevice-free sincos included) counted by "
+                              "ncu's sass op counters on this kernel (profiles/flops.json), not an operation count of the "
+                              "reference's algorithm: frac is the FP64 pipe's arithmetic utilisation, an upper bound on "
+                              "algorithmic efficiency"}
         if flops_per_step:
             ach = flops_per_step * BATCH * NSTEPS / (kms * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / fp64_peak, flops_per_unit=flops_per_step)
         else:
             roof.update(achieved=None, frac=None)
-        hbm_peak = 6451.2
+        hbm_peak = 6525.9
         mp = os.path.join(ROOT, "MEASURED_PEAKS.json")
         if os.path.exists(mp):
             hbm_peak = json.load(open(mp)).get("hbm_gbs", hbm_peak)
