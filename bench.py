@@ -583,6 +583,16 @@ def extra_kinds(lib, systems, device, hbm_peak, fp64_peak):
                     "value": B * nsteps / t * 1e3, "unit": "DEL steps/s", "batch": B, "ms": t, "kernel": s.kernel_name,
                     "us_per_step": t * 1e3 / nsteps if B == 1 else None,
                     "newton_iters_per_step": float(it.download().mean()) / nsteps, "ok_fraction": float((st.download() == 0).mean())})
+        if links == 5 and B > 1:
+            fj = os.path.join(ROOT, "profiles", "flops.json")
+            fl5 = json.load(open(fj)).get("pendulum5_step_flops_per_del_step") if os.path.exists(fj) else None
+            if fl5:
+                ach = fl5 * B * nsteps / (t * 1e-3) / 1e12
+                out[-1]["roofline"] = {"bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach / fp64_peak,
+                                       "flops_per_unit": fl5, "kernel_info": s.kernel_info(0),
+                                       "note": "register-resident specialised kernel (255 registers, 80 B of stack, one CTA of 256 threads "
+                                               "per SM); executed flops per DEL step from ncu (profiles/r02m_flops_pend5.csv): 53 % of "
+                                               "the 6.0 k warp instructions per step are fp64; on-chip (85 B of DRAM per rollout)"}
         for b in (dq, dp, q2, p2, it, st):
             b.free()
         s.close()
