@@ -215,6 +215,10 @@ typedef struct trepb_step_args {
     const double* times; /* [nsteps+1] or NULL */
 } trepb_step_args;
 
+/* Host-pointer entry points stage through device buffers owned by the handle.  trepb_step_batch and
+ * trepb_linearize_batch cut a batch of >= 2^17 instances into 2 or 4 contiguous chunks that alternate between two
+ * streams, so that the host<->device copies of one chunk overlap the kernel of another (pinned host buffers make the
+ * copies asynchronous); results are bit-identical to one launch over the whole batch.                       */
 int trepb_step_batch(trepb_system* sys, const trepb_step_args* args);                   /* host pointers   */
 int trepb_step_batch_dev(trepb_system* sys, const trepb_step_args* args, void* stream); /* device pointers */
 

@@ -244,3 +244,32 @@ def test_specialised_kernels_take_parameters_at_run_time(lib, ref):
     s.import_frames([M.ty(3), M.rx("theta"), [M.tz(-3, mass=(1.0, 0.2, 0.0, 0.0))]])
     M.Gravity(s, (0, 0, -9.8)); M.Damping(s, 1.2)
     assert not lib.System(s.describe()).specialized
+
+
+def test_large_host_batches_are_pipelined_in_chunks_with_identical_results(lib):
+    """trepb_step_batch / trepb_linearize_batch cut a large host batch into chunks on two streams (copies of one
+    chunk overlap the kernel of another): same bits as the device-resident call on the whole batch, ragged
+    chunk boundaries included."""
+    from trep_b200 import systems
+    rng = np.random.default_rng(5)
+    d = systems.named_desc("pend_on_cart1")
+    s = lib.System(d)
+    B = 4 * 65536 + 1237
+    q1 = rng.uniform(-2, 2, (B, d.nq)); p1 = rng.normal(0, 1, (B, d.nd)); u1 = rng.uniform(-1, 1, (B, 3, d.nu))
+    host = s.step(q1, p1, 0.0, 0.01, nsteps=3, u1=u1, sample_every=1)
+    up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(np.ascontiguousarray(a))
+    dq, dp, du = up(q1), up(p1), up(u1)
+    q2 = lib.DeviceBuffer(0, (B, d.nq)); p2 = lib.DeviceBuffer(0, (B, d.nd))
+    it = lib.DeviceBuffer(0, (B,), np.int32); st = lib.DeviceBuffer(0, (B,), np.int32)
+    tq = lib.DeviceBuffer(0, (B, 3, d.nq)); tp = lib.DeviceBuffer(0, (B, 3, d.nd))
+    s.step_raw(True, B, 3, 0.0, 0.01, dq, dp, du, None, None, None, q2, p2, None, it, st, sample_every=1, traj_q=tq, traj_p=tp)
+    lib.synchronize(0)
+    assert np.array_equal(host["q2"], q2.download()) and np.array_equal(host["p2"], p2.download())
+    assert np.array_equal(host["iters"], it.download()) and np.array_equal(host["status"], st.download())
+    assert np.array_equal(host["traj_q"], tq.download()) and np.array_equal(host["traj_p"], tp.download())
+    lin = s.linearize(q1, p1, u1[:, 0], None, t1=np.zeros(B), t2=np.full(B, 0.01))
+    A = lib.DeviceBuffer(0, (B, d.nX, d.nX)); Bm = lib.DeviceBuffer(0, (B, d.nX, d.nU))
+    s.linearize_raw(True, B, dq, dp, up(u1[:, 0]), None, st, t1_scalar=0.0, dt_scalar=0.01, q2=q2, p2=p2, iters=it, A=A, B=Bm)
+    lib.synchronize(0)
+    assert np.array_equal(lin["A"], A.download()) and np.array_equal(lin["B"], Bm.download())
+    assert np.array_equal(lin["q2"], q2.download()) and np.array_equal(lin["status"], st.download())

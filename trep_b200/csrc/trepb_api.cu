@@ -105,6 +105,7 @@ struct trepb_system {
     DevBuf ws_du, d2g;
     // staging for the host-pointer entry points
     DevBuf hb[72];
+    cudaStream_t hs[2] = {nullptr, nullptr};   // the two streams the chunked host-pointer calls alternate between
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     // Scratch owned by the handle (the workspace slab of the table-driven thread kernels, the
@@ -299,6 +300,7 @@ void trepb_system_destroy(trepb_system* s) {
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     if (s->ev_scratch) cudaEventDestroy(s->ev_scratch);
+    for (int i = 0; i < 2; ++i) if (s->hs[i]) cudaStreamDestroy(s->hs[i]);
     delete s;
 }
 
@@ -844,9 +846,93 @@ struct Stager {
         return TREPB_OK;
     }
 };
+// Chunked variant for large batches: the batch is cut into a few contiguous chunks that alternate between two
+// streams - host-to-device copy, kernel and device-to-host copy of a chunk are ordered on its stream, so the
+// copies of one chunk overlap the kernel of another (and each other: the two directions use different copy
+// engines).  Every per-instance array is registered with its element count per instance; chunk c covers the
+// instances [lo, lo + n).  Host buffers should be pinned for the copies to be asynchronous.
+struct Pipe {
+    trepb_system* s;
+    size_t B;
+    struct Arr { const char* hin; char* hout; char* dev; size_t per; } arr[40];
+    int n = 0, k = 0, err = 0;
+    Pipe(trepb_system* s_, size_t B_) : s(s_), B(B_) {}
+    char* reg(const void* hin, void* hout, size_t per_bytes) {
+        if (err) return nullptr;
+        DevBuf& b = s->hb[k++];
+        cudaError_t e = b.ensure(B * per_bytes ? B * per_bytes : 8);
+        if (e != cudaSuccess) { err = cuda_fail(e, "staging buffers"); return nullptr; }
+        arr[n++] = {(const char*)hin, (char*)hout, (char*)b.p, per_bytes};
+        return (char*)b.p;
+    }
+    template <class T> const T* in(const T* host, size_t per) { return host ? (const T*)reg(host, nullptr, per * sizeof(T)) : nullptr; }
+    template <class T> T* out(T* host, size_t per) { return host ? (T*)reg(nullptr, host, per * sizeof(T)) : nullptr; }
+    static int chunks(size_t B) { return B >= 4 * 65536 ? 4 : (B >= 2 * 65536 ? 2 : 1); }
+    int streams() {
+        for (int i = 0; i < 2; ++i)
+            if (!s->hs[i]) CU(cudaStreamCreateWithFlags(&s->hs[i], cudaStreamNonBlocking));
+        return TREPB_OK;
+    }
+    int upload(size_t lo, size_t cnt, cudaStream_t st) {
+        for (int i = 0; i < n; ++i) {
+            const size_t off = lo * arr[i].per, bytes = cnt * arr[i].per;
+            if (!bytes) continue;
+            if (arr[i].hin) CU(cudaMemcpyAsync(arr[i].dev + off, arr[i].hin + off, bytes, cudaMemcpyHostToDevice, st));
+            else CU(cudaMemsetAsync(arr[i].dev + off, 0, bytes, st));   // see Stager::out
+        }
+        return TREPB_OK;
+    }
+    int download(size_t lo, size_t cnt, cudaStream_t st) {
+        for (int i = 0; i < n; ++i) {
+            const size_t off = lo * arr[i].per, bytes = cnt * arr[i].per;
+            if (arr[i].hout && bytes) CU(cudaMemcpyAsync(arr[i].hout + off, arr[i].dev + off, bytes, cudaMemcpyDeviceToHost, st));
+        }
+        return TREPB_OK;
+    }
+    int finish() {
+        for (int i = 0; i < 2; ++i) CU(cudaStreamSynchronize(s->hs[i]));
+        return TREPB_OK;
+    }
+};
 }  // namespace
 
 extern "C" {
+
+static int step_batch_chunked(trepb_system* s, const trepb_step_args* a, int C_) {
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc, K = (size_t)a->nsteps;
+    const size_t ns = a->sample_every > 0 ? (size_t)(a->nsteps / a->sample_every) : 0;
+    Pipe pp(s, B);
+    trepb_step_args d = *a;
+    d.q1 = pp.in(a->q1, nq); d.p1 = pp.in(a->p1, nd); d.u1 = pp.in(a->u1, K * nu); d.k2 = pp.in(a->k2, K * nk);
+    d.q2_guess = pp.in(a->q2_guess, nd); d.lambda_guess = pp.in(a->lambda_guess, nc);
+    d.q2 = pp.out(a->q2, nq); d.p2 = pp.out(a->p2, nd); d.lambda1 = pp.out(a->lambda1, nc);
+    d.iters = pp.out(a->iters, 1); d.status = pp.out(a->status, 1);
+    d.traj_q = pp.out(a->traj_q, ns * nq); d.traj_p = pp.out(a->traj_p, ns * nd);
+    if (pp.err) return pp.err;
+    int rc = pp.streams();
+    if (rc) return rc;
+    if (a->times) {   // shared by every chunk: up before either stream starts
+        DevBuf& tb = s->hb[pp.k++];
+        CU(tb.ensure((K + 1) * sizeof(double)));
+        CU(cudaMemcpy(tb.p, a->times, (K + 1) * sizeof(double), cudaMemcpyHostToDevice));
+        d.times = (const double*)tb.p;
+    }
+    for (int c = 0; c < C_; ++c) {
+        const size_t lo = B * c / C_, hi = B * (c + 1) / C_, cnt = hi - lo;
+        cudaStream_t st = s->hs[c & 1];
+        if ((rc = pp.upload(lo, cnt, st))) return rc;
+        trepb_step_args e = d;
+        e.batch = (int64_t)cnt;
+#define OFF(f, per) if (e.f) e.f += lo * (per)
+        OFF(q1, nq); OFF(p1, nd); OFF(u1, K * nu); OFF(k2, K * nk); OFF(q2_guess, nd); OFF(lambda_guess, nc);
+        OFF(q2, nq); OFF(p2, nd); OFF(lambda1, nc); OFF(iters, 1); OFF(status, 1); OFF(traj_q, ns * nq); OFF(traj_p, ns * nd);
+#undef OFF
+        if ((rc = trepb_step_batch_dev(s, &e, st))) return rc;
+        if ((rc = pp.download(lo, cnt, st))) return rc;
+    }
+    return pp.finish();
+}
 
 int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
     TREPB_NVTX("trepb_step_batch");
@@ -856,6 +942,7 @@ int trepb_step_batch(trepb_system* s, const trepb_step_args* a) {
     const RtSys& ps = s->P.proto;
     const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
     CU(cudaSetDevice(s->device));
+    if (const int C_ = Pipe::chunks(B); C_ > 1 && a->q1 && a->p1 && a->q2 && a->p2 && a->status) return step_batch_chunked(s, a, C_);
     Stager st(s);
     trepb_step_args d = *a;
     d.q1 = st.in(a->q1, B * nq); d.p1 = st.in(a->p1, B * nd);
@@ -1006,12 +1093,52 @@ int trepb_deriv2_batch(trepb_system* s, const trepb_d2_args* a) {
     return st.finish();
 }
 
+// trepb_linearize_batch for a large plain batch (no trajectory rows): chunks alternating between two streams (Pipe)
+static int lin_batch_chunked(trepb_system* s, const trepb_lin_args* a, int C_) {
+    const RtSys& ps = s->P.proto;
+    const size_t B = (size_t)a->batch, nq = ps.nd + ps.nk, nd = ps.nd, nu = ps.nu, nk = ps.nk, nc = ps.nc;
+    const size_t nX = 2 * nq, nU = nu + nk;
+    Pipe pp(s, B);
+    trepb_lin_args d = *a;
+    // (member, elements per instance): inputs first, then outputs
+#define TREPB_LIN_IN(X) X(t1, 1) X(t2, 1) X(q1, nq) X(p1, nd) X(u1, nu) X(k2, nk) X(q2_guess, nd) X(lambda_guess, nc)
+#define TREPB_LIN_OUT(X) X(q2, nq) X(p2, nd) X(lambda1, nc) X(iters, 1) X(status, 1) X(A, nX * nX) X(B, nX * nU) \
+    X(q2_dq1, nq * nd) X(q2_dp1, nd * nd) X(q2_du1, nu * nd) X(q2_dk2, nk * nd) X(p2_dq1, nq * nd) X(p2_dp1, nd * nd) \
+    X(p2_du1, nu * nd) X(p2_dk2, nk * nd) X(l1_dq1, nq * nc) X(l1_dp1, nd * nc) X(l1_du1, nu * nc) X(l1_dk2, nk * nc)
+#define X(f, per) d.f = pp.in(a->f, (per));
+    TREPB_LIN_IN(X)
+#undef X
+#define X(f, per) d.f = pp.out(a->f, (per));
+    TREPB_LIN_OUT(X)
+#undef X
+    if (pp.err) return pp.err;
+    int rc = pp.streams();
+    if (rc) return rc;
+    for (int c = 0; c < C_; ++c) {
+        const size_t lo = B * c / C_, hi = B * (c + 1) / C_, cnt = hi - lo;
+        cudaStream_t st = s->hs[c & 1];
+        if ((rc = pp.upload(lo, cnt, st))) return rc;
+        trepb_lin_args e = d;
+        e.batch = (int64_t)cnt;
+#define X(f, per) if (e.f) e.f += lo * (per);
+        TREPB_LIN_IN(X) TREPB_LIN_OUT(X)
+#undef X
+#undef TREPB_LIN_IN
+#undef TREPB_LIN_OUT
+        if ((rc = trepb_linearize_batch_dev(s, &e, st))) return rc;
+        if ((rc = pp.download(lo, cnt, st))) return rc;
+    }
+    return pp.finish();
+}
+
 int trepb_linearize_batch(trepb_system* s, const trepb_lin_args* a) {
     TREPB_NVTX("trepb_linearize_batch");
     if (!s || !a) return fail(TREPB_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> hlk(s->mu_host);
     if (a->batch < 0) return fail(TREPB_ERR_INVALID, "batch must be >= 0");
     CU(cudaSetDevice(s->device));
+    if (const int C_ = Pipe::chunks((size_t)a->batch); C_ > 1 && a->traj_len <= 1 && a->q1 && a->p1 && a->status)
+        return lin_batch_chunked(s, a, C_);
     Stager st(s);
     trepb_lin_args d;
     stage_lin(st, s, a, &d);
