@@ -209,21 +209,23 @@ __device__ __forceinline__ GjElems gj_elems(int n, int nc, int ldt) {
     return g;
 }
 __device__ __forceinline__ bool cta_gauss_jordan(double* M, int ldt, int n, const GjElems& g, double* scl, double* rd,
-                                                 int* order, int* done, double tol) {
+                                                 int* order, double tol) {
     const int tid = threadIdx.x, lane = tid & 31, nth = blockDim.x;
     for (int i = tid; i < n; i += nth) {
         double sm_ = -1.0;
         for (int j = 0; j < n; ++j) { const double a = fabs(M[i * ldt + j]); if (a > sm_) sm_ = a; }
         scl[i] = 1.0 / sm_;
-        done[i] = 0;
     }
     __syncthreads();
+    // rows already used as pivots: a bit mask every thread keeps for itself (all threads compute the same pivots);
+    // a flag array in shared memory would be written by one warp while a slower one still searches this step's pivot
+    unsigned long long used = 0ull;
     for (int k = 0; k < n; ++k) {
         // pivot of column k among the rows not used yet (every warp computes the same answer)
         double best = 0.0;
         int br = 0x7fffffff;
         for (int r = lane; r < n; r += 32) {
-            double v = done[r] ? 0.0 : fabs(M[r * ldt + k] * scl[r]);
+            double v = ((used >> r) & 1ull) ? 0.0 : fabs(M[r * ldt + k] * scl[r]);
             if (!(v == v)) v = 0.0;
             if (v > best) { best = v; br = r; }
         }
@@ -241,7 +243,8 @@ __device__ __forceinline__ bool cta_gauss_jordan(double* M, int ldt, int n, cons
             if (g.off[q] < 0 || g.row[q] == pr * ldt || g.col[q] <= k) continue;
             M[g.off[q]] -= M[g.row[q] + k] * (rdk * prow[g.col[q]]);
         }
-        if (tid == 0) { order[k] = pr; rd[k] = rdk; done[pr] = 1; }
+        used |= 1ull << pr;
+        if (tid == 0) { order[k] = pr; rd[k] = rdk; }
         __syncthreads();
     }
     return true;
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
             }
             __syncthreads();
             // K[k] = gamma^-1 Kp and C[k] = gamma^-1 (r + B^T b)
-            if (!cta_gauss_jordan(G, ldg, nU, gje, scl, rd, order, done, 1e-300)) {
+            if (!cta_gauss_jordan(G, ldg, nU, gje, scl, rd, order, 1e-300)) {
                 s_fail = 1;   // every thread takes this branch (the pivots are computed redundantly by every warp)
                 break;
             }
@@ -437,6 +440,7 @@ int lqr_launch(int device, LqrParams& p, cudaStream_t stream) {
     if (block < 64) block = 64;
     if (mma) block = 512;   // the tensor-core schedule assigns products to warps 0-9 and 10-14
     // the elimination deals the nU x (nU + nX + 1) elements of [gamma | Kp | c] out to the threads, at most 4 each
+    if (nU > 64) return lqr_fail(TREPB_ERR_UNSUPPORTED, "more than 64 inputs");
     while (block < 512 && (long long)nU * (nU + nX + 1) > 4LL * block) block += 32;
     if ((long long)nU * (nU + nX + 1) > 4LL * block)
         return lqr_fail(TREPB_ERR_UNSUPPORTED, "input dimension too large for the in-kernel gamma solve");
