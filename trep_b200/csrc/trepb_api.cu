@@ -81,7 +81,9 @@ struct trepb_system {
     CoopPack CP;
     char* dcoop = nullptr;
     CoopSys cview;               // base = dcoop
-    CoopLayout clay;
+    CoopLayout clay;             // linearize kernel
+    CoopLayout clay_solve;       // step / project / p2 kernels (CoopLayout::make, solve_only): smaller, more instances per SM
+    int coop_warps_solve = 0;
     int coop_blob_bytes = 0;
     int coop_warps = 0;          // instances in flight per CTA (= per SM)
     const CoopKernelSet* cks = nullptr;
@@ -211,15 +213,19 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
             CoopSys hv = s->CP.view(s->CP.blob.data());
             const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE), (flags & TREPB_FLAG_COOP_ONE_WARP) ? 1 : 0);
             s->clay.set(hv, cks->specialized != 0);
+            s->clay_solve.set(hv, cks->specialized != 0, true);
             s->coop_blob_bytes = (int)s->CP.blob.size();
             const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
             const size_t ws_b = (size_t)s->clay.total * 8;
             const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
             int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
             if (warps > 8) warps = 8;
+            int warps_solve = cap > blob_d ? (int)((cap - blob_d) / ((size_t)s->clay_solve.total * 8)) : 0;
+            if (warps_solve > coopk::kSolveTeams) warps_solve = coopk::kSolveTeams;
             if (const char* e = getenv("TREPB_COOP_WARPS")) {   // diagnostic: fewer instances in flight per SM
                 const int w = atoi(e);
                 if (w >= 1 && w < warps) warps = w;
+                if (w >= 1 && w < warps_solve) warps_solve = w;
             }
             const bool wanted = (flags & TREPB_FLAG_FORCE_COOP) || s->ws_doubles > 2048;
             if (warps >= 1 && wanted) {
@@ -228,6 +234,7 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
                 CUS(cudaMemcpy(s->dcoop, s->CP.blob.data(), s->CP.blob.size(), cudaMemcpyHostToDevice));
                 s->cview = s->CP.view(s->dcoop);
                 s->coop_warps = warps;
+                s->coop_warps_solve = warps_solve;
                 s->cks = cks;
                 s->coop = true;
             }
@@ -330,8 +337,10 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
         if (blocks_per_sm) *blocks_per_sm = 1;
-        if (block) *block = 32 * s->cks->team_warps * s->coop_warps;
-        if (smem_bytes) *smem_bytes = (int32_t)((size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)s->coop_warps * s->clay.total * 8);
+        const bool lin = which == 2;
+        const int teams = lin ? s->coop_warps : s->coop_warps_solve;
+        if (block) *block = 32 * (lin ? s->cks->team_warps : 1) * teams;
+        if (smem_bytes) *smem_bytes = (int32_t)((size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)teams * (lin ? s->clay : s->clay_solve).total * 8);
         return TREPB_OK;
     }
     size_t smem = s->ks->specialized ? 0 : (size_t)s->blob_bytes;
@@ -395,19 +404,20 @@ int make_cfg(trepb_system* s, int which, long long batch, int bps, size_t smem, 
 }
 
 // persistent grid of the cooperative kernels: one CTA per SM, fewer warps per CTA for small batches
-void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch* c) {
-    int warps = s->coop_warps;
+void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch* c, bool solve_only) {
+    int warps = solve_only ? s->coop_warps_solve : s->coop_warps;
+    const CoopLayout& lay = solve_only ? s->clay_solve : s->clay;
     const long long per_sm = (batch + s->sms - 1) / s->sms;
     if (per_sm < warps) warps = (int)(per_sm < 1 ? 1 : per_sm);
     long long grid = (batch + warps - 1) / warps;
     if (grid > s->sms) grid = s->sms;
     c->grid = (int)grid;
     c->warps = warps;
-    c->smem = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)warps * s->clay.total * 8;
+    c->smem = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)warps * lay.total * 8;
     c->stream = stream;
     c->sys = s->cview;
     c->blob_bytes = s->coop_blob_bytes;
-    c->lay = s->clay;
+    c->lay = lay;
 }
 
 // Orders launches that use the handle's scratch across streams: wait for the previous user before the
@@ -457,7 +467,7 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     p.times = a->times;
     if (s->coop) {
         CoopLaunch cl;
-        make_coop(s, a->batch, (cudaStream_t)stream, &cl);
+        make_coop(s, a->batch, (cudaStream_t)stream, &cl, true);
         Timed t(s, cl.stream);
         CU(s->cks->step(cl, p));
         return TREPB_OK;
@@ -491,7 +501,7 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     p.times = a->times;
     if (s->coop) {
         CoopLaunch cl;
-        make_coop(s, a->batch, (cudaStream_t)stream, &cl);
+        make_coop(s, a->batch, (cudaStream_t)stream, &cl, true);
         Timed t(s, cl.stream);
         CU(s->cks->proj(cl, p));
         return TREPB_OK;
@@ -515,7 +525,7 @@ int eval_launch(trepb_system* s, const P2Params& p, void* stream) {
     CU(cudaSetDevice(s->device));
     if (s->coop) {
         CoopLaunch cl;
-        make_coop(s, p.batch, (cudaStream_t)stream, &cl);
+        make_coop(s, p.batch, (cudaStream_t)stream, &cl, true);
         Timed t(s, cl.stream);
         CU(s->cks->p2(cl, p));
         return TREPB_OK;
@@ -594,7 +604,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
     if (s->coop) {
         p.stage = 0;
         CoopLaunch cl;
-        make_coop(s, a->batch, stream, &cl);
+        make_coop(s, a->batch, stream, &cl, false);
         AuxLayout al;
         al.set(ps.nd, ps.nc);
         Timed t(s, cl.stream);

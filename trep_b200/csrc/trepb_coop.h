@@ -6,6 +6,12 @@
 
 namespace trepb {
 
+namespace coopk {
+// most instances (one warp each) a CTA of the solve-only kernels (step, project, p2 / f) holds: their workspace
+// is smaller than the linearize kernel's (CoopLayout::make, solve_only), 12 x 18.0 KB for the marionette
+constexpr int kSolveTeams = 12;
+}  // namespace coopk
+
 struct CoopLaunch {
     int grid, warps;        // CTAs, teams (= instances in flight) per CTA; a team is team_warps warps
     size_t smem;            // table blob + warps x workspace

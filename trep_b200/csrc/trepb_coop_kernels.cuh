@@ -65,10 +65,10 @@ __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, c
 }
 
 template <class D, class Team>
-__global__ void __launch_bounds__(8 * Team::kSize, 1)
+__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout();
+    if constexpr (D::kStatic) lay = D::layout(true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -137,10 +137,10 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
 // candidate, the affine feedback U[k] = bU[k] - K[k](X[k] - bX[k]) evaluated by the lanes (one input
 // component each) inside the time loop.
 template <class D, class Team>
-__global__ void __launch_bounds__(8 * Team::kSize, 1)
+__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout();
+    if constexpr (D::kStatic) lay = D::layout(true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -213,10 +213,10 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
 }
 
 template <class D, class Team>
-__global__ void __launch_bounds__(8 * Team::kSize, 1)
+__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout();
+    if constexpr (D::kStatic) lay = D::layout(true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -254,7 +254,7 @@ template <class D, class Team>
 __global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout();
+    if constexpr (D::kStatic) lay = D::layout(false);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -329,15 +329,15 @@ cudaError_t prep(K kernel, size_t smem) {
 template <class D, class Team>
 struct Launch {
     static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
-        cudaError_t e = prep(coop_step_kernel<D, Team>, c.smem);
+        cudaError_t e = prep(coop_step_kernel<D, WarpTeam>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_step_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_step_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
-        cudaError_t e = prep(coop_p2_kernel<D, Team>, c.smem);
+        cudaError_t e = prep(coop_p2_kernel<D, WarpTeam>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_p2_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_p2_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
@@ -347,15 +347,15 @@ struct Launch {
         return cudaGetLastError();
     }
     static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
-        cudaError_t e = prep(coop_project_kernel<D, Team>, c.smem);
+        cudaError_t e = prep(coop_project_kernel<D, WarpTeam>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_project_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_project_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t info(int which, KernelInfo* ki) {
-        const void* fn = which == 0 ? (const void*)coop_step_kernel<D, Team>
-                       : which == 1 ? (const void*)coop_p2_kernel<D, Team>
-                       : which == 2 ? (const void*)coop_lin_kernel<D, Team> : (const void*)coop_project_kernel<D, Team>;
+        const void* fn = which == 0 ? (const void*)coop_step_kernel<D, WarpTeam>
+                       : which == 1 ? (const void*)coop_p2_kernel<D, WarpTeam>
+                       : which == 2 ? (const void*)coop_lin_kernel<D, Team> : (const void*)coop_project_kernel<D, WarpTeam>;
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
         if (e != cudaSuccess) return e;

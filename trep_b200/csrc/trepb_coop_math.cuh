@@ -103,7 +103,8 @@ struct CoopLayout {
     int M2, T22;                     // first-derivative factors; alias the link region
     int Lq, Lv, VV, QQ, UP, DN;
     int Dh1, Dh2, hc;
-    int N;                           // Newton augmented matrix [nr][ldf]  /  right-hand sides Y [nd][ldy]
+    int N;                           // Newton augmented matrix [nr][ldf]; aliases the link region
+    int Y;                           // DDh.lambda block / right-hand sides [nd][ldy] (first-derivative kernels only)
     int Z, PJ;
     int fr, scl, rdM, rdP;
     int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc] flag  (int32)
@@ -113,10 +114,15 @@ struct CoopLayout {
     // stat: the compile-time-size flavour (right-hand-side columns in registers: no Z block, the
     // DDh.lambda block compacted to the ndc x nqc configs some constraint depends on).
     // Aliases: cs (sin/cos of the sweep) sits in the tail of comp, which the sweeps never touch;
-    // fr / scl reuse Lq / Lv, which are dead once the residual and p2 have been formed; M2 / T22
-    // reuse the link region, N holds the Newton matrix during the solve and DDh.lambda after it.
+    // fr / scl reuse Lq / Lv, which are dead once the residual and p2 have been formed; M2 / T22 and
+    // the Newton matrix N reuse the link region (poses, velocities, composite inertias are dead from
+    // the moment the pair tables of an iteration exist until the next iteration recomputes them; the
+    // converged iteration leaves before it would assemble N, so deriv1 finds the midpoint data intact).
+    // solve_only: the layout of the kernels that never call deriv1 (step, project, p2 / f): no DDh.lambda
+    // block, no projection factors, two pair arrays instead of four (dyn_second) - 18.0 instead of 27.0 KB
+    // per marionette instance, 12 instead of 8 instances per SM.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
-                                              bool stat = false, int ndc = 0, int nqc = 0) {
+                                              bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false) {
         CoopLayout L{};
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
@@ -131,24 +137,28 @@ struct CoopLayout {
         const int link0 = o;
         L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
         L.comp = o; o += 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
-        const int need = nd * L.ldm + nd * nd;
+        const int nN = nr * L.ldf;
+        const int need = nd * L.ldm + nd * nd > nN ? nd * L.ldm + nd * nd : nN;
         if (o - link0 < need) o = link0 + need;
         L.M2 = link0; L.T22 = link0 + nd * L.ldm;
+        L.N = link0;
         const int nlq = nq > nr ? nq : nr;
         L.Lq = o; o += nlq; L.Lv = o; o += nlq;
         L.fr = L.Lq; L.scl = L.Lv;
-        L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += npairs; L.DN = o; o += npairs;
+        L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
-        const int nN = nr * L.ldf, nY = stat ? ndc * nqc : nd * L.ldy;
-        L.N = o; o += nN > nY ? nN : nY;
-        L.Z = o; o += stat ? 0 : nc * L.ldy;
-        L.PJ = o; o += nc * L.ldp;
-        L.rdM = o; o += nr; L.rdP = o; o += nc;
+        const int nY = stat ? ndc * nqc : nd * L.ldy;
+        L.Y = o; o += solve_only ? 0 : nY;
+        L.Z = o; o += (stat || solve_only) ? 0 : nc * L.ldy;
+        L.PJ = o; o += solve_only ? 0 : nc * L.ldp;
+        L.rdM = o; o += nr; L.rdP = o; o += solve_only ? 0 : nc;
         L.ints = o; o += (2 * nr + 2 * nc + 2) / 2 + 1;   // + the first-warp flag
         L.total = (o + 1) & ~1;
         return L;
     }
-    TREPB_HD void set(const CoopSys& s, bool stat = false) { *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc); }
+    TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
+        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only);
+    }
 };
 
 template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_, int NDC_, int NQC_>
@@ -156,7 +166,9 @@ struct CtDims {
     static constexpr bool kStatic = true;
     static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_,
                          NDC = NDC_, NQC = NQC_;
-    TREPB_HD static constexpr CoopLayout layout() { return CoopLayout::make(ND, NK, NU, NC, NL, NP, NPAIRS, true, NDC, NQC); }
+    TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
+        return CoopLayout::make(ND, NK, NU, NC, NL, NP, NPAIRS, true, NDC, NQC, solve_only);
+    }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
                s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC;
@@ -729,7 +741,10 @@ struct Coop {
     }
 
     // ---- second-order tables on the chain pairs (system.c:170-268, 302-393, 479-512)
-    TREPB_HD void dyn_second() {
+    // newton_dt != 0: called from the Newton iteration, which needs two combinations per pair only - they
+    // are stored instead of the four tables (VV <- dt/4 L_dqdq - 1/dt L_ddqddq, QQ <- the antisymmetric part),
+    // so the solve-only layout carries two pair arrays.
+    TREPB_HD void dyn_second(double newton_dt = 0.0) {
         const int nls = L.nls, lane = t.lane();
         double* comp = w + L.comp;
         for (int l = lane; l < NL(); l += Team::kSize) {
@@ -769,10 +784,16 @@ struct Coop {
                 cross3(P, S.grav, N);
                 WG += dot3(aw, N);
             }
-            w[L.VV + e] = dot6(s6, H);
-            w[L.UP + e] = sG;
-            w[L.DN + e] = i == j ? sG : dot6(W6, H);
-            w[L.QQ + e] = WG;
+            const double vv = dot6(s6, H), dn = i == j ? sG : dot6(W6, H);
+            if (newton_dt != 0.0) {
+                w[L.VV + e] = 0.25 * newton_dt * WG - 1.0 / newton_dt * vv;
+                w[L.QQ + e] = 0.5 * dn - 0.5 * sG;   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
+            } else {
+                w[L.VV + e] = vv;
+                w[L.UP + e] = sG;
+                w[L.DN + e] = dn;
+                w[L.QQ + e] = WG;
+            }
         }
         t.sync();
     }
@@ -1075,7 +1096,7 @@ struct Coop {
             if (solved) break;
             if (iterations > max_it) return ST_NOT_CONVERGED;
             // Jacobian (midpointvi.c:577-670) with the residual as an extra column
-            dyn_second();
+            dyn_second(dt);
             TREPB_TICK(21);
             double* A = w + L.N;
             const int ld = L.ldf;
@@ -1095,10 +1116,10 @@ struct Coop {
                 const int ij = S.pair_ij()[e];
                 const int ci = S.l_cfg()[ij & 255], cj = S.l_cfg()[ij >> 8];   // ci above-or-equal cj
                 if (ci >= nd || cj >= nd) continue;
-                const double base = 0.25 * dt * w[L.QQ + e] - 1.0 / dt * w[L.VV + e];
+                const double base = w[L.VV + e];   // dt/4 L_dqdq - 1/dt L_ddqddq (dyn_second, Newton form)
                 if (ci == cj) A[ci * ld + ci] += base;
                 else {
-                    const double asym = 0.5 * w[L.DN + e] - 0.5 * w[L.UP + e];   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
+                    const double asym = w[L.QQ + e];
                     A[ci * ld + cj] += base + asym;
                     A[cj * ld + ci] += base - asym;
                 }
@@ -1275,7 +1296,7 @@ struct Coop {
         const int nd = ND(), nk = NK(), nq = NQ(), nc = NC(), nu = NU(), lane = t.lane();
         const int nX = 2 * nq, nU = nu + nk;
         const double dt = t2 - t1;
-        double* Y = w + L.N;
+        double* Y = w + L.Y;
         const int ldy = L.ldd;   // leading dimension of the DDh.lambda block (== L.ldy for run-time sizes)
         TREPB_TICK_INIT
         dyn_second();   // tables at the converged midpoint
