@@ -199,6 +199,25 @@ def ref_rod():
     return system
 
 
+def ref_spring_arms():
+    """Same script as trep_b200/systems.py:spring_arms with the reference's own classes."""
+    system = trep.System()
+    system.import_frames([
+        tx(0.3), [tz(1.0, name='anchor')],
+        rz('a1'), [ry('a2'), [tx(1.0, mass=1.0, name='elbowA'), [rx('a3'), [tz(-0.8, name='tipA', mass=0.6)]]]],
+        tx('slide', kinematic=True), [ty(1.1), [ry('b1'), [rz('b2'), [ty(0.9, mass=0.8, name='elbowB'),
+                                                 [rx('b3'), [tz(-0.5, name='tipB', mass=0.4)]]]]]]])
+    trep.potentials.Gravity(system, (0, 0, -9.8))
+    trep.forces.Damping(system, 0.05)
+    trep.forces.ConfigForce(system, 'a1', 'torque')
+    trep.potentials.LinearSpring(system, 'tipA', 'tipB', k=15.0, x0=0.7)
+    trep.potentials.LinearSpring(system, 'elbowA', 'anchor', k=4.0, x0=0.5)
+    trep.constraints.Distance(system, 'elbowA', 'elbowB', 1.6)
+    system.q = {'a1': 0.3, 'a2': -0.2, 'a3': 0.5, 'b1': 0.4, 'b2': 0.6, 'b3': -0.6}
+    system.satisfy_constraints()
+    return system
+
+
 def ref_damper_only():
     """examples/dual_pendulums.py without the LinearSpring (whose missing C V_dqdqdq stops the reference's
     _calc_deriv2): the LinearDamper's second derivatives (forces/lineardamper.c:60-107) are reachable."""
@@ -229,6 +248,7 @@ REF_BUILDERS = {
     "tase_pendulum": ref_tase_pendulum, "puppet": ref_puppet,
     "pccd": ref_pccd, "wrench_arm": ref_wrench_arm, "spline_pendulum": ref_spline_pendulum,
     "fourbar": ref_fourbar, "loop3d": ref_loop3d, "rod": ref_rod, "damper_only": ref_damper_only,
+    "spring_arms": ref_spring_arms,
 }
 
 

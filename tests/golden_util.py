@@ -24,6 +24,9 @@ EXTRA_D2 = ["pccd", "wrench_arm"]
 # (damper_only: the reference's _calc_deriv2 runs there)
 PARITY = ["fourbar", "loop3d", "rod", "damper_only"]
 PARITY_CONSTRAINED = ["fourbar", "loop3d", "rod"]
+# LinearSprings between two arms, a kinematic slide, an input and a distance constraint: the spring terms of the
+# cooperative kernels (no second-derivative goldens: the reference has no C V_dqdqdq for a LinearSpring)
+PARITY_SPRING = ["spring_arms"]
 
 RAW = ["q2_dq1", "q2_dp1", "q2_du1", "q2_dk2", "p2_dq1", "p2_dp1", "p2_du1", "p2_dk2",
        "l1_dq1", "l1_dp1", "l1_du1", "l1_dk2"]

@@ -67,7 +67,7 @@ def flavours(lib, name):
     return out
 
 
-@pytest.mark.parametrize("name", G.PARITY)
+@pytest.mark.parametrize("name", G.PARITY + G.PARITY_SPRING)
 def test_parity_golden_cases(lib, name):
     """Step, every first-derivative array, A / B and the Newton iteration counts on every flavour."""
     g = G.golden(name)
@@ -124,7 +124,7 @@ def test_lineardamper_second_derivative_deviation_is_the_reference_typo(lib):
     G.assert_close(lin["A"], g["case_A"], "damper_only A")
 
 
-@pytest.mark.parametrize("name", G.PARITY_CONSTRAINED)
+@pytest.mark.parametrize("name", G.PARITY_CONSTRAINED + G.PARITY_SPRING)
 def test_parity_rollouts(lib, name):
     """Every step of the recorded closed-loop rollouts (inputs / kinematic configs as recorded)."""
     g = G.golden(name)
@@ -142,7 +142,7 @@ def test_parity_rollouts(lib, name):
         assert abs(int(out["iters"][0]) - int(g["roll_iters"].sum())) <= 3
 
 
-@pytest.mark.parametrize("name", G.PARITY)
+@pytest.mark.parametrize("name", G.PARITY + G.PARITY_SPRING)
 def test_parity_random_vs_reference(lib, ref, name):
     """Ragged seeded batch against the reference itself run live: perturbed points of the recorded rollout for
     the constrained systems (a constraint far from satisfied is not a state the integrator visits)."""

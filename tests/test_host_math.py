@@ -9,7 +9,7 @@ import golden_util as G
 import hostmath as H
 
 
-@pytest.mark.parametrize("name", G.ALL + G.EXTRA + G.PARITY)
+@pytest.mark.parametrize("name", G.ALL + G.EXTRA + G.PARITY + G.PARITY_SPRING)
 def test_cases_step_and_deriv1(name):
     g = G.golden(name)
     d = G.desc(name)
@@ -28,7 +28,7 @@ def test_cases_step_and_deriv1(name):
     assert flips == 0, "Newton iteration counts differ from the reference in %d cases" % flips
 
 
-@pytest.mark.parametrize("name", G.ALL + ["pccd"] + G.PARITY)
+@pytest.mark.parametrize("name", G.ALL + ["pccd"] + G.PARITY + G.PARITY_SPRING)
 def test_cooperative_math_cases(name):
     """The team-cooperative formulation (link tables, world-coordinate spatial algebra,
     right-looking LU; trepb_coop_math.cuh) run with a one-lane host team against the goldens."""

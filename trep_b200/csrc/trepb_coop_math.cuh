@@ -102,6 +102,7 @@ struct CoopLayout {
     int cs, R, p, V, comp, pts;      // link region
     int M2, T22;                     // first-derivative factors; alias the link region
     int Lq, Lv, VV, QQ, UP, DN;
+    int XS;                          // sum of the LinearSpring Hessians d2V / dq dq at the midpoint [nqs][nqs]
     int Dh1, Dh2, hc;
     int N;                           // Newton augmented matrix [nr][ldf]; aliases the link region
     int Y;                           // DDh.lambda block / right-hand sides [nd][ldy] (first-derivative kernels only)
@@ -122,7 +123,8 @@ struct CoopLayout {
     // block, no projection factors, two pair arrays instead of four (dyn_second) - 18.0 instead of 27.0 KB
     // per marionette instance, 12 instead of 8 instances per SM.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
-                                              bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false) {
+                                              bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false,
+                                              int nqs = 0) {
         CoopLayout L{};
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
@@ -136,7 +138,7 @@ struct CoopLayout {
         L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc; L.vk = o; o += nk;
         const int link0 = o;
         L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
-        L.comp = o; o += 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
+        L.comp = o; o += (nqs > 0 && 7 * nq > 16 * nl) ? 7 * nq : 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
         const int nN = nr * L.ldf;
         const int need = nd * L.ldm + nd * nd > nN ? nd * L.ldm + nd * nd : nN;
         if (o - link0 < need) o = link0 + need;
@@ -147,6 +149,7 @@ struct CoopLayout {
         L.fr = L.Lq; L.scl = L.Lv;
         L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
+        L.XS = o; o += nqs * nqs;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
         L.Y = o; o += solve_only ? 0 : nY;
         L.Z = o; o += (stat || solve_only) ? 0 : nc * L.ldy;
@@ -157,7 +160,7 @@ struct CoopLayout {
         return L;
     }
     TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
-        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only);
+        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs);
     }
 };
 
@@ -171,7 +174,7 @@ struct CtDims {
     }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
-               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC;
+               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0;   // springs: run-time-size flavour only
     }
 };
 
@@ -466,6 +469,8 @@ struct Coop {
     TREPB_DIM(NL, NL, nl) TREPB_DIM(NP, NP, np) TREPB_DIM(NPAIRS, NPAIRS, npairs) TREPB_DIM(NLEVELS, NLEVELS, nlevels)
 #undef TREPB_DIM
     TREPB_HD int NQ() const { return ND() + NK(); }
+    // LinearSprings: run-time-size flavour only (CtDims::matches), so the compile-time flavours drop the code
+    TREPB_HD int NS() const { if constexpr (D::kStatic) return 0; else return S.ns; }
 
     TREPB_HD int* ipivM() const { return (int*)(w + L.ints); }
     TREPB_HD int* iswpM() const { return ipivM() + (ND() + NC()); }
@@ -538,7 +543,7 @@ struct Coop {
             else if (TS == 1) { half = pass; sub = 0; stride = 1; }
             else { half = lane / (TS / 2); sub = lane % (TS / 2); stride = TS / 2; }
             const bool second = mode == 2 && half == 1;
-            const int flag = half == 0 ? 16 : 32, qoff = second ? L.q2 : L.qe;
+            const int flag = half == 0 ? (16 | 64) : 32, qoff = second ? L.q2 : L.qe;
             double* cs = w + (second ? L.comp : L.cs);
             for (int l = sub; l < NL(); l += stride) {
                 const int kind = S.l_kind()[l];
@@ -560,7 +565,7 @@ struct Coop {
                 else if (TS == 1) { half = pass; sub = 0; stride = 1; }
                 else { half = lane / (TS / 2); sub = lane % (TS / 2); stride = TS / 2; }
                 const bool second = mode == 2 && half == 1, vel = half == 0;
-                const int flag = vel ? 16 : 32, qoff = second ? L.q2 : L.qe;
+                const int flag = vel ? (16 | 64) : 32, qoff = second ? L.q2 : L.qe;
                 double* cs = w + (second ? L.comp : L.cs);
                 double* R = w + (second ? L.comp + 2 * nls : L.R);
                 double* p = w + (second ? L.comp + 11 * nls : L.p);
@@ -738,6 +743,95 @@ struct Coop {
         for (int i = lane; i < NQ(); i += Team::kSize)
             if (S.ks()[i] != 0.0) w[L.Lq + i] -= S.ks()[i] * w[L.qe + i] - S.kq0()[i];
         t.sync();
+        springs_first();
+    }
+
+    // ---- LinearSpring potentials (potentials/linearspring.c:30-74) at the midpoint pose: V = k/2 (x - x0)^2 with
+    // x = |pA - pB|.  The end points are world points of the primary pose set; d(pA - pB)/dq_j and the second
+    // derivatives come from dpoint() and the axis-cross-derivative rule the constraint Hessians use.
+    TREPB_HD void spring_v(int sp, double* v, double& x) const {
+        double pa[3], pb[3];
+        point(S.sp_a()[sp], pa); point(S.sp_b()[sp], pb);
+        TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+        x = sqrt(dot3(v, v));
+    }
+    // L_dq -= dV/dq (called by dyn_first; the primary pose set is selected)
+    TREPB_HD void springs_first() {
+        if (NS() == 0) return;
+        points(true);
+        for (int j = t.lane(); j < NQ(); j += Team::kSize) {
+            if (S.xs_idx()[j] < 0) continue;
+            const int lj = S.cfg_link()[j];
+            double acc = 0.0;
+            for (int sp = 0; sp < NS(); ++sp) {
+                double v[3], x, da[3], db[3];
+                spring_v(sp, v, x);
+                dpoint(S.sp_a()[sp], lj, da); dpoint(S.sp_b()[sp], lj, db);
+                const double dx = (1.0 / x) * (v[0] * (da[0] - db[0]) + v[1] * (da[1] - db[1]) + v[2] * (da[2] - db[2]));
+                double val = S.sp_k()[sp] * (x - S.sp_x0()[sp]) * dx;
+                if (dx != dx && S.sp_x0()[sp] == 0.0) val = 0.0;      // linearspring.c:41
+                acc += val;
+            }
+            w[L.Lq + j] -= acc;
+        }
+        t.sync();
+    }
+    // XS = sum over springs of d2V / dq_i dq_j on the configs any spring depends on (called by dyn_second once
+    // the pair tables are done: the comp region is free to hold dA_i, dB_i, dx_i of one spring at a time)
+    TREPB_HD void springs_second() {
+        if (NS() == 0) return;
+        const int lane = t.lane(), nqs = S.nqs, nls = L.nls;
+        for (int e = lane; e < nqs * nqs; e += Team::kSize) w[L.XS + e] = 0.0;
+        double* DA = w + L.comp;
+        for (int sp = 0; sp < NS(); ++sp) {
+            const int off = S.sp_off()[sp], m = S.sp_off()[sp + 1] - off;
+            const int* list = S.sp_cfg() + off;
+            const int A = S.sp_a()[sp], B = S.sp_b()[sp];
+            double* DB = DA + 3 * m;
+            double* DX = DB + 3 * m;
+            double v[3], x;
+            spring_v(sp, v, x);
+            const double k = S.sp_k()[sp], x0 = S.sp_x0()[sp];
+            t.sync();
+            for (int a = lane; a < m; a += Team::kSize) {
+                const int lj = S.cfg_link()[list[a]];
+                double da[3], db[3];
+                dpoint(A, lj, da); dpoint(B, lj, db);
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) { DA[c * m + a] = da[c]; DB[c * m + a] = db[c]; }
+                DX[a] = (1.0 / x) * (v[0] * (da[0] - db[0]) + v[1] * (da[1] - db[1]) + v[2] * (da[2] - db[2]));
+            }
+            t.sync();
+            const int lA = S.pt_link()[A], lB = S.pt_link()[B];
+            const unsigned long long ancA = lA >= 0 ? S.l_anc()[lA] : 0ull, ancB = lB >= 0 ? S.l_anc()[lB] : 0ull;
+            for (int e = lane; e < m * m; e += Team::kSize) {
+                const int bj = e / m, ai = e - bj * m;
+                const int i = list[ai], j = list[bj];
+                const int li = S.cfg_link()[i], lj = S.cfg_link()[j];
+                double ddv[3] = {0.0, 0.0, 0.0};
+                if (li >= 0 && lj >= 0) {
+                    // the upper joint's axis crosses the lower joint's first derivative
+                    int up = li, lo_idx = bj;
+                    if (!((S.l_anc()[lj] >> li) & 1ull)) { up = lj; lo_idx = ai; }
+                    const int kup = S.l_kind()[up];
+                    if (kup & 4) {
+                        const int a = kup & 3;
+                        const double aw[3] = {w[oR + a * nls + up], w[oR + (3 + a) * nls + up], w[oR + (6 + a) * nls + up]};
+                        const bool onA = ((ancA >> li) & 1ull) && ((ancA >> lj) & 1ull);
+                        const bool onB = ((ancB >> li) & 1ull) && ((ancB >> lj) & 1ull);
+                        double d3[3] = {0.0, 0.0, 0.0};
+                        if (onA) { TREPB_UNROLL for (int c = 0; c < 3; ++c) d3[c] += DA[c * m + lo_idx]; }
+                        if (onB) { TREPB_UNROLL for (int c = 0; c < 3; ++c) d3[c] -= DB[c * m + lo_idx]; }
+                        cross3(aw, d3, ddv);
+                    }
+                }
+                double di[3], dj[3];
+                TREPB_UNROLL for (int c = 0; c < 3; ++c) { di[c] = DA[c * m + ai] - DB[c * m + ai]; dj[c] = DA[c * m + bj] - DB[c * m + bj]; }
+                const double vdi = dot3(v, di), didj = dot3(di, dj), dix = DX[ai], djx = DX[bj];
+                const double ddx = -djx / (x * x) * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
+                w[L.XS + S.xs_idx()[i] * nqs + S.xs_idx()[j]] += k * dix * djx + k * (x - x0) * ddx;
+            }
+        }
+        t.sync();
     }
 
     // ---- second-order tables on the chain pairs (system.c:170-268, 302-393, 479-512)
@@ -796,6 +890,7 @@ struct Coop {
             }
         }
         t.sync();
+        springs_second();
     }
 
     // ---- first-derivative blocks from the chain-pair tables.  Every block of calc_deriv1
@@ -823,16 +918,26 @@ struct Coop {
     // with vab = 1/2 L_ddqdq(a,b), vba = 1/2 L_ddqdq(b,a)  (first index of L_ddqdq is the velocity slot)
     TREPB_HD double comb(int which, int a, int b, double dt) const {
         const int m = S.pm()[a * ND() + b];
-        if (m == 0) return a == b ? 0.25 * dt * -S.ks()[a] : 0.0;
-        const int e = (m > 0 ? m : -m) - 1;
-        const int off = which == 0 ? L.VV : (which == 1 ? L.QQ : (((which == 2) == (m > 0)) ? L.UP : L.DN));
-        return w[off + e];
+        double val;
+        if (m == 0) val = a == b ? 0.25 * dt * -S.ks()[a] : 0.0;
+        else {
+            const int e = (m > 0 ? m : -m) - 1;
+            const int off = which == 0 ? L.VV : (which == 1 ? L.QQ : (((which == 2) == (m > 0)) ? L.UP : L.DN));
+            val = w[off + e];
+        }
+        if (NS() > 0) {   // Q = dt/4 L_dqdq enters all four combinations with a plus sign; L_dqdq -= d2V/dqdq
+            const int xa = S.xs_idx()[a], xb = S.xs_idx()[b];
+            if (xa >= 0 && xb >= 0) val -= 0.25 * dt * w[L.XS + xa * S.nqs + xb];
+        }
+        return val;
     }
 
     // ---- world points of the constraints at the current pose
-    TREPB_HD void points() {
+    TREPB_HD void points(bool springs = false) {
         const int nls = L.nls, np = NP();
-        for (int q = t.lane(); q < np; q += Team::kSize) {
+        // constraint points [0, npc) at the selected pose; spring ends [npc, np) at the primary (midpoint) pose
+        const int q0 = springs ? S.npc : 0, q1 = springs ? np : S.npc;
+        for (int q = q0 + t.lane(); q < q1; q += Team::kSize) {
             const int l = S.pt_link()[q];
             const double* r = S.pt_r() + 3 * q;
             TREPB_UNROLL
@@ -1125,6 +1230,15 @@ struct Coop {
                 }
             }
             t.sync();
+            if (NS() > 0) {
+                // L_dqdq -= d2V/dqdq of the LinearSprings: cross-chain entries the pair tables do not carry
+                const int nqs = S.nqs;
+                for (int e = lane; e < nqs * nqs; e += Team::kSize) {
+                    const int ca = S.xs_cfg()[e / nqs], cb = S.xs_cfg()[e % nqs];
+                    if (ca < nd && cb < nd) A[ca * ld + cb] -= 0.25 * dt * w[L.XS + e];
+                }
+                t.sync();
+            }
             TREPB_TICK(22);
             {
                 // factorization + back substitution on the team's first warp (warp collectives)

@@ -32,6 +32,8 @@ struct CoopSys {
     int nl, nq, nd, nk, nu, nc, np, npairs, nlevels;
     int nsl;        // super levels of the pose sweep: one per run of single-child links (chain)
     int ndc, nqc;   // dynamic configs / configs that any constraint depends on (compact DDh.lambda block)
+    int ns, nqs;    // LinearSpring potentials / configs that any of them depends on (compact block of their Hessian)
+    int npc;        // points [0, npc) belong to constraints, [npc, np) are spring ends (evaluated at the midpoint)
     int has_gravity;
     double grav[3];
     // Tables live in one relocatable blob (host memory, device memory or a shared-memory copy):
@@ -53,6 +55,11 @@ struct CoopSys {
     //                 first cd_nd[c] of them are dynamic); dd_row [nd] / dd_col [nq]: compact row / column
     //                 of a config in the block of sum_c lambda_c d2h_c (-1: no constraint depends on it);
     //                 con_n [nc][3]: PointOnPlane normal in the coordinates of the plane frame's link
+    //   springs [ns]  LinearSpring (potentials/linearspring.c:30-74): sp_a, sp_b (points), sp_k, sp_x0,
+    //                 sp_off [ns+1] / sp_cfg: the configs each spring depends on, ascending; xs_idx [nq]: compact
+    //                 row = column of a config in the block of sum_s d2V_s / dq dq (-1: no spring depends on
+    //                 it), xs_cfg [nqs] its inverse.  Links that carry a spring end have bit6 of l_kind set
+    //                 (they take part in the midpoint pose sweep even without mass below).
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -89,6 +96,15 @@ struct CoopSys {
     int o_sl_off;
     int o_sl_head;
     int o_con_n;
+    int o_sp_a, o_sp_b, o_sp_k, o_sp_x0, o_sp_off, o_sp_cfg, o_xs_idx, o_xs_cfg;
+    TREPB_HD const int32_t* sp_a() const { return (const int32_t*)(base + o_sp_a); }
+    TREPB_HD const int32_t* sp_b() const { return (const int32_t*)(base + o_sp_b); }
+    TREPB_HD const double* sp_k() const { return (const double*)(base + o_sp_k); }
+    TREPB_HD const double* sp_x0() const { return (const double*)(base + o_sp_x0); }
+    TREPB_HD const int32_t* sp_off() const { return (const int32_t*)(base + o_sp_off); }
+    TREPB_HD const int32_t* sp_cfg() const { return (const int32_t*)(base + o_sp_cfg); }
+    TREPB_HD const int32_t* xs_idx() const { return (const int32_t*)(base + o_xs_idx); }
+    TREPB_HD const int32_t* xs_cfg() const { return (const int32_t*)(base + o_xs_cfg); }
     TREPB_HD const double* con_n() const { return (const double*)(base + o_con_n); }
     TREPB_HD const int32_t* l_par() const { return (const int32_t*)(base + o_l_par); }
     TREPB_HD const int32_t* l_cfg() const { return (const int32_t*)(base + o_l_cfg); }
@@ -136,7 +152,7 @@ struct CoopPack {
     std::string why;          // why the cooperative path does not apply
     std::vector<char> blob;
     CoopSys proto;
-    size_t off[40];
+    size_t off[48];
 
     CoopSys view(const char* base) const {
         CoopSys s = proto;
@@ -177,6 +193,8 @@ struct CoopPack {
         s.o_sl_off = (int)off[k++];
         s.o_sl_head = (int)off[k++];
         s.o_con_n = (int)off[k++];
+        s.o_sp_a = (int)off[k++]; s.o_sp_b = (int)off[k++]; s.o_sp_k = (int)off[k++]; s.o_sp_x0 = (int)off[k++];
+        s.o_sp_off = (int)off[k++]; s.o_sp_cfg = (int)off[k++]; s.o_xs_idx = (int)off[k++]; s.o_xs_cfg = (int)off[k++];
         return s;
     }
 };
@@ -232,8 +250,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     const int nf = d->n_frames, nd = d->nd, nk = d->nk, nq = nd + nk, nu = d->nu, nc = d->n_constraints;
     if (nq > 64) { P.why = "more than 64 configs"; return P; }
     for (int i = 0; i < d->n_potentials; ++i)
-        if (d->pot_kind[i] == TREPB_POT_LINEAR_SPRING) { P.why = "LinearSpring potential"; return P; }
-        else if (d->pot_kind[i] == TREPB_POT_NONLINEAR_CONFIG_SPRING) { P.why = "NonlinearConfigSpring potential"; return P; }
+        if (d->pot_kind[i] == TREPB_POT_NONLINEAR_CONFIG_SPRING) { P.why = "NonlinearConfigSpring potential"; return P; }
     for (int i = 0; i < d->n_forces; ++i)
         if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
         else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }
@@ -357,13 +374,15 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     std::vector<int32_t> pt_link;
     std::vector<double> pt_r;
     std::vector<int> pt_frame;
-    auto point_of = [&](int f) {
-        for (size_t i = 0; i < pt_frame.size(); ++i) if (pt_frame[i] == f) return (int)i;
+    // first: search from this point index (spring ends get their own points even when a constraint uses the
+    // same frame: the two sets are evaluated at different poses); bit: the l_kind flag of the links above it
+    auto point_of = [&](int f, size_t first = 0, int bit = 32) {
+        for (size_t i = first; i < pt_frame.size(); ++i) if (pt_frame[i] == f) return (int)i;
         pt_frame.push_back(f);
         const int l = flink[f] < 0 ? -1 : newidx[flink[f]];
         pt_link.push_back(l);
         for (int k = 0; k < 3; ++k) pt_r.push_back(fx[f].p[k]);
-        for (int a = l; a >= 0; a = l_par[a]) l_kind[a] |= 32;
+        for (int a = l; a >= 0; a = l_par[a]) l_kind[a] |= bit;
         return (int)pt_frame.size() - 1;
     };
     std::vector<int32_t> con_kind(nc > 0 ? nc : 1), con_a(nc > 0 ? nc : 1), con_b(nc > 0 ? nc : 1), con_third(nc > 0 ? nc : 1);
@@ -395,6 +414,30 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
         if (con_kind[c] == TREPB_CON_DISTANCE && ii[2] >= 0) m |= 1ull << ii[2];
         con_dep[c] = m;
     }
+    const int npc = (int)pt_link.size();
+    // ---- LinearSpring end points and dependency lists
+    std::vector<int32_t> sp_a, sp_b, sp_off(1, 0), sp_cfg;
+    std::vector<double> sp_k, sp_x0;
+    std::vector<int32_t> xs_idx(nq > 0 ? nq : 1, -1), xs_cfg;
+    {
+        uint64_t any = 0;
+        for (int i = 0; i < d->n_potentials; ++i) {
+            if (d->pot_kind[i] != TREPB_POT_LINEAR_SPRING) continue;
+            const int a = point_of(d->pot_i[4 * i], (size_t)npc, 64), b = point_of(d->pot_i[4 * i + 1], (size_t)npc, 64);
+            sp_a.push_back(a); sp_b.push_back(b);
+            sp_k.push_back(d->pot_d[4 * i]); sp_x0.push_back(d->pot_d[4 * i + 1]);
+            uint64_t m = 0;
+            for (int e = 0; e < 2; ++e) {
+                const int l = pt_link[e == 0 ? a : b];
+                for (int x = l; x >= 0; x = l_par[x]) m |= 1ull << l_cfg[x];
+            }
+            for (int j = 0; j < nq; ++j) if ((m >> j) & 1ull) sp_cfg.push_back(j);
+            sp_off.push_back((int32_t)sp_cfg.size());
+            any |= m;
+        }
+        for (int j = 0; j < nq; ++j) if ((any >> j) & 1ull) { xs_idx[j] = (int32_t)xs_cfg.size(); xs_cfg.push_back(j); }
+    }
+    const int ns = (int)sp_a.size(), nqs = (int)xs_cfg.size();
     const int np = (int)pt_link.size();
     std::vector<int32_t> cd_off(nc + 1, 0), cd_cfg, cd_nd(nc > 0 ? nc : 1, 0);
     for (int c = 0; c < nc; ++c) {
@@ -456,6 +499,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     P.proto.nl = nl; P.proto.nq = nq; P.proto.nd = nd; P.proto.nk = nk; P.proto.nu = nu; P.proto.nc = nc;
     P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
     P.proto.ndc = ndc; P.proto.nqc = nqc; P.proto.nsl = nsl;
+    P.proto.ns = ns; P.proto.nqs = nqs; P.proto.npc = npc;
     P.proto.has_gravity = has_grav;
     for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
     int k = 0;
@@ -479,6 +523,9 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(dd_row.data(), 4 * nd); put(dd_col.data(), 4 * nq);
     put(l_next.data(), 4 * nl); put(sl_off.data(), 4 * sl_off.size()); put(sl_head.data(), 4 * sl_head.size());
     put(con_n.data(), 8 * 3 * (size_t)nc);
+    put(sp_a.data(), 4 * (size_t)ns); put(sp_b.data(), 4 * (size_t)ns); put(sp_k.data(), 8 * (size_t)ns); put(sp_x0.data(), 8 * (size_t)ns);
+    put(sp_off.data(), 4 * sp_off.size()); put(sp_cfg.data(), 4 * sp_cfg.size());
+    put(xs_idx.data(), 4 * (size_t)nq); put(xs_cfg.data(), 4 * (size_t)nqs);
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;

@@ -176,6 +176,26 @@ def rod() -> M.System:
     return s
 
 
+def spring_arms() -> M.System:
+    """Two spatial arms joined by LinearSprings (tip to tip, and elbow to a point fixed in the world), the second
+    arm's base on a kinematic slide, one torque input, and a distance constraint between the mid links: a
+    mid-size system with springs for the cooperative kernels (potentials/linearspring.c:30-74).  nd 6, nk 1,
+    nu 1, nc 1."""
+    s = M.System(name="spring_arms")
+    s.import_frames([
+        M.tx(0.3), [M.tz(1.0, name="anchor")],
+        M.rz("a1"), [M.ry("a2"), [M.tx(1.0, mass=1.0, name="elbowA"), [M.rx("a3"), [M.tz(-0.8, name="tipA", mass=0.6)]]]],
+        M.tx("slide", kinematic=True), [M.ty(1.1), [M.ry("b1"), [M.rz("b2"), [M.ty(0.9, mass=0.8, name="elbowB"),
+                                                   [M.rx("b3"), [M.tz(-0.5, name="tipB", mass=0.4)]]]]]]])
+    M.Gravity(s, (0, 0, -9.8))
+    M.Damping(s, 0.05)
+    M.ConfigForce(s, "a1", "torque")
+    M.LinearSpring(s, "tipA", "tipB", k=15.0, x0=0.7)
+    M.LinearSpring(s, "elbowA", "anchor", k=4.0, x0=0.5)
+    M.Distance(s, "elbowA", "elbowB", 1.6)
+    return s
+
+
 def damper_only() -> M.System:
     """examples/dual_pendulums.py without the LinearSpring: the one system on which the reference's
     _calc_deriv2 reaches the LinearDamper second derivatives (forces/lineardamper.c:60-107)."""
@@ -225,7 +245,7 @@ def named_desc(name) -> SystemDesc:
         "pend_on_cart2": lambda: pend_on_cart(True), "dual_pendulums": dual_pendulums,
         "tase_pendulum": tase_pendulum, "pccd": pccd, "wrench_arm": wrench_arm,
         "spline_pendulum": spline_pendulum, "fourbar": fourbar, "loop3d": loop3d, "rod": rod,
-        "damper_only": damper_only,
+        "damper_only": damper_only, "spring_arms": spring_arms,
     }
     return table[name]().describe()
 
@@ -237,3 +257,5 @@ EXTRA = ["pccd", "wrench_arm", "spline_pendulum"]
 # parity systems for the constraint / force kinds of SURVEY 8a rows a7, a9 that BASELINE.json's configs do not
 # exercise: PointToPoint1D/2D/3D, fixed-length Distance, LinearDamper second derivatives
 PARITY = ["fourbar", "loop3d", "rod", "damper_only"]
+# a mid-size system with LinearSprings that the cooperative kernels run (round 2)
+PARITY_SPRING = ["spring_arms"]
