@@ -61,3 +61,29 @@ def test_plugin_kernel_matches_the_reference(lib):
     print("damper_only 2^18 x 20 steps: table-driven %.2f ms, plug-in %.2f ms (%.1fx)" % (
         t["general"][1], t["plugin"][1], t["general"][1] / t["plugin"][1]))
     assert t["plugin"][1] < t["general"][1]
+
+
+def test_cooperative_plugin_for_a_user_shape(lib):
+    """kind="coop": the compile-time-size cooperative kernels for a shape the library was not built with (the rod
+    system: fixed-length Distance + a kinematic slide)."""
+    from trep_b200 import build
+    name = "rod"
+    d = G.desc(name)
+    g = G.golden(name)
+    assert lib.System(d, cooperative=True).kernel_name == "cooperative"        # run-time sizes before the plug-in
+    path = os.path.join(os.path.dirname(build.LIB), "libtrepb_plugin_rod_coop.so")
+    if not os.path.exists(path):
+        if shutil.which(build.NVCC) is None:
+            pytest.skip("plug-in not prebuilt and no nvcc on this box")
+        path = build.build_plugin(d, "rod_coop", kind="coop")
+    assert lib.load_plugin(path) == 1
+    s = lib.System(d, cooperative=True)
+    assert s.cooperative and s.kernel_name == "cooperative/rod_coop"
+    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
+                      q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+    assert np.all(out["status"] == 0)
+    for k in ("q2", "p2", "lambda1", "A", "B"):
+        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
+    for k in G.RAW:
+        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
+    assert np.array_equal(out["iters"], g["case_iters"])

@@ -141,3 +141,6 @@ def test_plugin_adds_a_specialised_kernel_for_a_user_system():
     assert b"damper_only" in names
     with pytest.raises(Exception):
         lib.load_plugin(path)            # already loaded: registers nothing
+    # kind="coop": compile-time-size cooperative kernels for a shape the library was not built with
+    path = build.build_plugin(systems.named_desc("rod"), "rod_coop", kind="coop")
+    assert lib.load_plugin(path) == 1
