@@ -466,7 +466,9 @@ def test_lqr_sweep_matches_reference(lib, ref):
     weights, several rollouts in one launch."""
     from trep.discopt import dlqr
     rng = np.random.default_rng(21)
-    for nX, nU, K, R_, per_step in ((4, 1, 60, 3, False), (80, 18, 25, 2, True), (7, 3, 40, 5, True)):
+    # (37, 5): odd sizes on the tensor-core path (every tile ragged, no vector loads); (40, 6): partial 16 x 40 tiles
+    for nX, nU, K, R_, per_step in ((4, 1, 60, 3, False), (80, 18, 25, 2, True), (7, 3, 40, 5, True),
+                                    (37, 5, 12, 2, True), (40, 6, 12, 3, False)):
         A = np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (R_, K, nX, nX))
         B = rng.normal(0, 1.0, (R_, K, nX, nU))
         if per_step:
@@ -490,7 +492,8 @@ def test_lq_sweep_matches_reference(lib, ref):
     from trep.discopt import dlqr
     rng = np.random.default_rng(22)
     for nX, nU, K, R_, per_rollout, with_s in ((4, 1, 50, 3, False, True), (80, 18, 20, 2, True, True),
-                                               (7, 3, 30, 4, True, False), (5, 2, 10, 1, False, False)):
+                                               (7, 3, 30, 4, True, False), (5, 2, 10, 1, False, False),
+                                               (37, 5, 10, 2, True, True)):
         A = np.eye(nX)[None, None] + rng.normal(0, 0.3 / np.sqrt(nX), (R_, K, nX, nX))
         B = rng.normal(0, 1.0, (R_, K, nX, nU))
         nc = R_ if per_rollout else 1
