@@ -497,15 +497,31 @@ lin_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStrided 
             const long b0 = b - lane;
             const long nlive = p.batch - b0 < 32 ? p.batch - b0 : 32;
             const double* tile = smem_ + (long)(threadIdx.x - lane) * (nA + nB);
+            // 16-byte accesses when every row of the tile and of A / B starts 16-byte aligned (even nA, nB)
+            const bool vec2 = Sys::kStatic && nA % 2 == 0 && nB % 2 == 0;
             if (p.A) {
                 double* dstA = p.A + b0 * nA;
-                for (long e = lane; e < nlive * nA; e += 32) dstA[e] = tile[(e / nA) * (nA + nB) + e % nA];
+                if (vec2) {
+                    const int hA = nA / 2, hT = (nA + nB) / 2;
+                    const double2* t2p = reinterpret_cast<const double2*>(tile);
+                    double2* d2p = reinterpret_cast<double2*>(dstA);
+                    for (long e = lane; e < nlive * hA; e += 32) d2p[e] = t2p[(e / hA) * hT + e % hA];
+                } else {
+                    for (long e = lane; e < nlive * nA; e += 32) dstA[e] = tile[(e / nA) * (nA + nB) + e % nA];
+                }
             }
             if constexpr (!Sys::kStatic || (Sys::kStatic && (Sys{}.NU() + Sys{}.NK()) > 0)) {
                 if (p.B && nB > 0) {
                     const int nBs = nB > 0 ? nB : 1;
                     double* dstB = p.B + b0 * nB;
-                    for (long e = lane; e < nlive * nB; e += 32) dstB[e] = tile[(e / nBs) * (nA + nB) + nA + e % nBs];
+                    if (vec2) {
+                        const int hA = nA / 2, hB = nBs / 2, hT = (nA + nB) / 2;
+                        const double2* t2p = reinterpret_cast<const double2*>(tile);
+                        double2* d2p = reinterpret_cast<double2*>(dstB);
+                        for (long e = lane; e < nlive * hB; e += 32) d2p[e] = t2p[(e / hB) * hT + hA + e % hB];
+                    } else {
+                        for (long e = lane; e < nlive * nB; e += 32) dstB[e] = tile[(e / nBs) * (nA + nB) + nA + e % nBs];
+                    }
                 }
             }
             __syncwarp();
