@@ -952,6 +952,10 @@ def main():
         if flops_per_step:
             ach = flops_per_step * BATCH * NSTEPS / (kms * 1e-3) / 1e12
             roof.update(achieved=ach, frac=ach / fp64_peak, flops_per_unit=flops_per_step)
+            # beside the measured denominator: the nominal one (64 DFMA per clock per SM at the maximum SM clock)
+            if clocks.get("sm_max_mhz"):
+                nominal = 148 * 64 * 2 * clocks["sm_max_mhz"] * 1e6 / 1e12
+                roof.update(peak_nominal=nominal, frac_of_nominal=ach / nominal)
         else:
             roof.update(achieved=None, frac=None)
         hbm_peak = 6525.9
