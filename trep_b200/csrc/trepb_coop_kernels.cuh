@@ -1,15 +1,18 @@
-// Team-cooperative kernel templates: one WARP per instance, the per-instance workspace and the link tables
-// in shared memory (trepb_coop_math.cuh).  Used for systems whose thread-per-instance workspace
-// would not stay on chip (the marionette: 86 frames, nd 22, nk 18, nc 6).
+// Team-cooperative kernel templates: one TEAM (one warp, or two for the linearize kernel of shapes built with
+// PairTeam) per instance, the per-instance workspace and the link tables in shared memory
+// (trepb_coop_math.cuh).  Used for systems whose thread-per-instance workspace would not stay on chip (the
+// marionette: 86 frames, nd 22, nk 18, nc 6).
 //
-//   coop_step_kernel   trepb_step_batch*       (MidpointVI.step looped in-kernel)
-//   coop_p2_kernel     trepb_calc_p2_batch*
-//   coop_lin_kernel    trepb_linearize_batch*  (solve_DEL + calc_deriv1 -> A, B, raw arrays, aux)
+//   coop_step_kernel     trepb_step_batch*       (MidpointVI.step looped in-kernel)
+//   coop_project_kernel  trepb_project_batch*    (closed-loop rollouts)
+//   coop_p2_kernel       trepb_calc_p2_batch* / trepb_calc_f_batch* / trepb_discrete_fm2_batch*
+//   coop_lin_kernel      trepb_linearize_batch*  (solve_DEL + calc_deriv1 -> A, B, raw arrays, aux)
 //
-// Persistent grid: one CTA per SM, as many warps per CTA as workspaces fit next to the table blob in
-// the SM's shared memory (7 for the marionette: 7 x 30.0 KB + 12.2 KB of tables); every warp
-// walks the batch with stride grid x warps.  All cross-lane traffic goes through shared memory and
-// __syncwarp(), the pivot search of the LU uses warp shuffles.
+// Persistent grid: one CTA per SM, as many teams per CTA as workspaces fit next to the table blob in the SM's
+// shared memory (marionette: 8 x 26.6 KB for the linearize kernel, 12 x 18.0 KB for the kernels that never
+// call deriv1, + 12.3 KB of tables); every team walks the batch with stride grid x teams.  Cross-lane traffic
+// goes through shared memory and the team's barrier (__syncwarp / a named barrier); the factorizations run on
+// the team's first warp with shuffles and warp reductions.
 #pragma once
 #include <cuda_runtime.h>
 #include "trepb_coop.h"

@@ -9,10 +9,12 @@
 // shared memory (3 x nX^2 doubles: 154 KB for the marionette's nX = 80), A[k] / B[k] streamed from the
 // slabs the linearize kernel wrote, so the linearization never leaves the GPU; K[k] goes straight into
 // the layout trepb_project_batch reads (per-rollout gains).  Every product has the form
-// C = X^T Y with both operands read along rows (P is symmetric), 4 x 4 register tiles per thread;
-// the nU x nU factorization reuses the cooperative LU (trepb_coop_math.cuh) on warp 0, the nX
-// right-hand sides are then solved one per thread; A[k-1], B[k-1] and Q(k) are fetched with cp.async
-// while the current step is still multiplying.
+// C = X^T Y with both operands read along rows (P is symmetric): on the FP64 tensor cores
+// (mma.sync m8n8k4, one warp per 16 x 40 tile, ragged edges read as zero) for nX >= 32, on 4 x 4 register
+// tiles per thread below that; K[k] = gamma^-1 Kp (and the affine term) by a Gauss-Jordan elimination of
+// [gamma | Kp | c] shared by the whole CTA; A[k-1], B[k-1] and Q(k) are fetched with cp.async while the
+// current step is still multiplying.  One CTA of 16 warps per SM at the marionette's size, several smaller
+// CTAs per SM for small states.
 #include <cuda_runtime.h>
 #include "trepb_nvtx.h"
 #include <stdlib.h>
@@ -266,14 +268,12 @@ __global__ void __launch_bounds__(512, 1) lqr_kernel(const LqrParams p) {
     double* G = Rs + ((nU * nU + 1) & ~1);         // M = [gamma | Kp | c] [nU][ldt], eliminated in place
     double* scl = G + ((nU * ldg + 1) & ~1);       // [nU]
     double* rd = scl + nU;                         // [nU]
-    int* order = (int*)(rd + nU);                  // [nU] pivot row of every elimination step + done [nU]
-    int* done = order + nU;
-    double* Ks = (double*)(done + nU);             // K[k] [nU][nX]   (2 nU ints = nU doubles: stays 8-byte aligned)
-    // affine part (solve_tv_lq): b [nX], A^T b [nX], g = B^T b [nU], r(k) + g -> C[k] [nU]
+    int* order = (int*)(rd + nU);                  // [nU] pivot row of every elimination step (+ nU ints of padding)
+    double* Ks = (double*)(order + 2 * nU);        // K[k] [nU][nX]   (2 nU ints = nU doubles: stays 8-byte aligned)
+    // affine part (solve_tv_lq): b [nX], A^T b [nX], g = B^T b [nU] (+ r(k): the last column of M)
     double* bv = Ks + nU * nX;
     double* ab = bv + nX;
     double* gv = ab + nX;
-    double* cv = gv + nU;
     const bool affine = p.qv != nullptr;
     __shared__ int s_fail;
     for (long r = blockIdx.x; r < p.batch; r += gridDim.x) {
