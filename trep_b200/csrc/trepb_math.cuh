@@ -865,6 +865,9 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
                 ws.Lq(j) -= val;
             }
             if (order >= 2) {
+                // 1 / x^2 once per spring: the reference divides by x * x for every pair (linearspring.c:60-74);
+                // one division and a multiplication per pair differ from that by a rounding of one Hessian term
+                const Real rxx = 1.0 / (x * x);
                 TREPB_UNROLL_SYS
                 for (int i = 0; i < nq; ++i)
                     TREPB_FOR_FROM(j, i, nq) {
@@ -874,7 +877,7 @@ TREPB_HD void add_potentials(const Sys& sys, Ws& ws, int order) {
                         const Real vdi = v[0] * ws.dv(i, 0) + v[1] * ws.dv(i, 1) + v[2] * ws.dv(i, 2);
                         const Real didj = ws.dv(i, 0) * ws.dv(j, 0) + ws.dv(i, 1) * ws.dv(j, 1) + ws.dv(i, 2) * ws.dv(j, 2);
                         const Real dix = ws.dxs(i), djx = ws.dxs(j);
-                        const Real ddx = -djx / (x * x) * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
+                        const Real ddx = -djx * rxx * vdi + 1.0 / x * didj + 1.0 / x * dot3(v, ddv);
                         const Real val = k * dix * djx + k * (x - x0) * ddx;
                         ws.Lqq(i, j) -= val;
                         if (j != i) ws.Lqq(j, i) -= val;
