@@ -377,6 +377,7 @@ int make_cfg(trepb_system* s, int which, long long batch, int bps, size_t smem, 
     if (!s->ks->specialized) {
         long long resident = (long long)s->sms * bps;
         if (grid > resident) grid = resident;
+        if (grid > ws_grid_cap(s->ws_doubles, block)) grid = ws_grid_cap(s->ws_doubles, block);
         // keep the slab within a quarter of the free memory
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
@@ -712,6 +713,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
         long long grid = (nb * p.nx + block - 1) / block;
         const long long resident = (long long)s->sms * s->bps_d2jac;
         if (grid > resident) grid = resident;
+        if (grid > ws_grid_cap(s->ws_du_elems, block)) grid = ws_grid_cap(s->ws_du_elems, block);
         if ((size_t)grid * per_cta > avail / 4) grid = (long long)((avail / 4) / per_cta);
         if (grid < 1) return fail(TREPB_ERR_CUDA, "not enough device memory for the second-derivative workspace");
         CU(s->ws_du.ensure((size_t)grid * per_cta));
@@ -742,6 +744,7 @@ int trepb_deriv2_batch_dev(trepb_system* s, const trepb_d2_args* a, void* stream
     if (!s->ks->specialized) {
         long long resident = (long long)s->sms * s->bps_d2;
         if (grid > resident) grid = resident;
+        if (grid > ws_grid_cap(s->ws_hd_elems, block)) grid = ws_grid_cap(s->ws_hd_elems, block);
         size_t free_b = 0, total_b = 0;
         CU(cudaMemGetInfo(&free_b, &total_b));
         const size_t per_cta = (size_t)s->ws_hd_elems * sizeof(HDG) * block;

@@ -230,7 +230,7 @@ struct CtxHD<Sys, false> {
         sys = s.rebased(dblob, (const char*)smem_);
         ws = w;
         ws.base = w.base + tid;
-        ws.stride = nthreads;
+        ws.stride = (unsigned)nthreads;
     }
 };
 

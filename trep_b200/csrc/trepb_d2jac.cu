@@ -47,7 +47,7 @@ d2jac_kernel(const RtSys rsys, const char* dblob, int blob_bytes, const WsStride
     const RtSys sys = rsys.rebased(dblob, (const char*)smem_);
     WsStridedT<Dual> ws = wsp;
     ws.base = wsp.base + tid;
-    ws.stride = nth;
+    ws.stride = (unsigned)nth;
     const int lane = threadIdx.x & 31;
     double* tile = smem_ + n8 + (threadIdx.x >> 5) * (32 * 33);
     NzMaps nz;

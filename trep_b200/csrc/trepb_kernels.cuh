@@ -233,7 +233,7 @@ struct Ctx<Sys, false> {
         sys = s.rebased(dblob, (const char*)smem_);
         ws = w;
         ws.base = w.base + tid;
-        ws.stride = nthreads;
+        ws.stride = (unsigned)nthreads;
     }
 };
 

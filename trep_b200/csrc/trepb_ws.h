@@ -57,13 +57,13 @@ template <class RealT>
 struct WsStridedT {
     using Real = RealT;
     Real* base;
-    long stride;
+    unsigned stride;   // threads of the grid; (elements per thread) x stride < 2^32 (the launchers cap the grid: ws_grid_cap)
     int NF, NQ, ND, NU, NC, NR;
 #define X(name, rows, cols, ad) int o_##name; int ld_##name;
     TREPB_WS_ARRAYS(X)
 #undef X
 #define X(name, rows, cols, ad) \
-    TREPB_HD Real& name(int i, int j = 0) { return base[(long)(o_##name + i * ld_##name + j) * stride]; }
+    TREPB_HD Real& name(int i, int j = 0) { return base[(size_t)((unsigned)(o_##name + i * ld_##name + j) * stride)]; }
     TREPB_WS_ARRAYS(X)
 #undef X
     // returns number of elements per thread.  level 0: every array; 1: only the arrays of the residual
@@ -79,5 +79,14 @@ struct WsStridedT {
     }
 };
 using WsStrided = WsStridedT<double>;
+
+// The strided accessors index with 32-bit arithmetic (one IMAD and one IMAD.WIDE per access instead of a 64-bit
+// multiply: a quarter of the table-driven kernels' instructions is this address arithmetic): the largest grid,
+// in CTAs of `block` threads, for which (elements per thread) x (threads) stays below 2^32
+inline long long ws_grid_cap(long long elems_per_thread, int block) {
+    const long long threads = 0xffffffffLL / (elems_per_thread > 0 ? elems_per_thread : 1);
+    const long long g = threads / block;
+    return g < 1 ? 1 : g;
+}
 
 }  // namespace trepb
