@@ -36,7 +36,7 @@ def ref():
 
 
 # LinearSpring / LinearDamper, PointOnPlane, wrenches: thread-per-instance kernels only
-COOP_UNSUPPORTED = {"dual_pendulums", "wrench_arm", "spline_pendulum"}
+COOP_UNSUPPORTED = {"wrench_arm", "spline_pendulum"}     # wrenches / spline springs: thread kernels only
 
 
 def _systems(lib, name):

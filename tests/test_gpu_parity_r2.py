@@ -52,7 +52,7 @@ def flavours(lib, name):
         s = lib.System(d)
         assert s.specialized and s.kernel_name == name
         out.append(("spec", s))
-    if name != "damper_only":           # a LinearDamper keeps a system on the thread kernels
+    if True:                            # every parity system runs on the cooperative kernels (LinearDamper since round 2)
         c = lib.System(d, specialize=False, cooperative=True)
         assert c.cooperative and c.kernel_name == "cooperative"
         out.append(("coop", c))

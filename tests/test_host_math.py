@@ -35,7 +35,7 @@ def test_cooperative_math_cases(name):
     g = G.golden(name)
     d = G.desc(name)
     if H.coop_info(d) is None:
-        pytest.skip("cooperative path does not apply (LinearSpring / LinearDamper / wrench / spline spring)")
+        pytest.skip("cooperative path does not apply (wrench / spline spring)")
     flips = 0
     # run-time sizes everywhere; the compile-time-size flavour (register-resident right-hand-side
     # columns) for the shape the build specialises

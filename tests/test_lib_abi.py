@@ -73,7 +73,8 @@ def test_cooperative_shapes_and_generated_instantiation():
     compile-time-size cooperative kernels for exactly that shape."""
     assert lib.coop_dims(G.desc("puppet")) == (22, 18, 0, 6, 34, 12, 157, 10, 20, 38)
     assert lib.coop_dims(G.desc("pendulum5")) == (5, 0, 0, 0, 5, 0, 15, 5, 0, 0)
-    assert lib.coop_dims(G.desc("dual_pendulums")) is None      # LinearSpring / LinearDamper
+    assert lib.coop_dims(G.desc("dual_pendulums")) is None      # LinearSpring / LinearDamper: run-time-size flavour only
+    assert lib.coop_dims(G.desc("wrench_arm")) is None          # wrenches: no cooperative kernels at all
     for name in build.COOP_AOT_SYSTEMS:
         text = open(os.path.join(build.GEN, "coop_%s.cu" % name)).read()
         dims = ", ".join(str(v) for v in lib.coop_dims(G.desc(name)))

@@ -61,6 +61,12 @@ SpecRegistry& spec_registry() {
     static SpecRegistry r = {{nullptr}, 0};
     return r;
 }
+bool spec_register(const KernelSet* ks, unsigned abi) {
+    SpecRegistry& r = spec_registry();
+    if (abi != kSpecAbi || r.n >= SpecRegistry::kMax) return false;
+    r.sets[r.n++] = ks;
+    return true;
+}
 }  // namespace trepb
 
 struct trepb_system {
@@ -152,7 +158,7 @@ int trepb_load_plugin(const char* path, int* n_added) {
         return fail(TREPB_ERR_INVALID, std::string("cannot load plug-in: ") + (why ? why : path));
     }
     const int added = spec_registry().n + coop_registry().n - before;
-    if (added <= 0) return fail(TREPB_ERR_INVALID, "the library registered no kernel set (not a trepb plug-in, loaded before, or the registry is full)");
+    if (added <= 0) return fail(TREPB_ERR_INVALID, "the library registered no kernel set (not a trepb plug-in, loaded before, built against other headers than this library, or the registry is full)");
     if (n_added) *n_added = added;
     return TREPB_OK;
 }

@@ -10,6 +10,13 @@ CoopRegistry& coop_registry() {
     return r;
 }
 
+bool coop_register(const CoopKernelSet* ks, unsigned abi) {
+    CoopRegistry& r = coop_registry();
+    if (abi != kCoopAbi || r.n >= CoopRegistry::kMax) return false;
+    r.sets[r.n++] = ks;
+    return true;
+}
+
 const CoopKernelSet* coop_general_kernels() {
     static const CoopKernelSet ks = make_coop_kernelset<RtDims>("cooperative");
     return &ks;

@@ -41,11 +41,13 @@ struct CoopRegistry {
     int n;
 };
 CoopRegistry& coop_registry();
+// layout fingerprint of what a cooperative specialisation unit shares with the library (see kSpecAbi)
+constexpr unsigned kCoopAbi = 0x20000u + (unsigned)(sizeof(CoopSys) * 131 + sizeof(CoopLayout) * 31 + sizeof(CoopLaunch) * 17 +
+                                                    sizeof(CoopKernelSet) * 13 + sizeof(StepParams) * 7 + sizeof(LinParams) * 5 +
+                                                    sizeof(ProjParams) * 3 + sizeof(P2Params));
+bool coop_register(const CoopKernelSet* ks, unsigned abi);
 struct CoopRegistrar {
-    explicit CoopRegistrar(const CoopKernelSet* ks) {
-        CoopRegistry& r = coop_registry();
-        if (r.n < CoopRegistry::kMax) r.sets[r.n++] = ks;
-    }
+    explicit CoopRegistrar(const CoopKernelSet* ks) { coop_register(ks, kCoopAbi); }
 };
 const CoopKernelSet* coop_general_kernels();
 const CoopKernelSet* coop_select(const CoopSys& s, bool allow_specialized, int team_warps = 0);

@@ -103,6 +103,7 @@ struct CoopLayout {
     int M2, T22;                     // first-derivative factors; alias the link region
     int Lq, Lv, VV, QQ, UP, DN;
     int XS;                          // sum of the LinearSpring Hessians d2V / dq dq at the midpoint [nqs][nqs]
+    int FD, FX, FQ, FV;              // LinearDampers: force [nd], dx scratch [nq], f_dq / f_ddq blocks [nqf][nqf]
     int Dh1, Dh2, hc;
     int N;                           // Newton augmented matrix [nr][ldf]; aliases the link region
     int Y;                           // DDh.lambda block / right-hand sides [nd][ldy] (first-derivative kernels only)
@@ -124,7 +125,7 @@ struct CoopLayout {
     // per marionette instance, 12 instead of 8 instances per SM.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
                                               bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false,
-                                              int nqs = 0) {
+                                              int nqs = 0, int nqf = 0) {
         CoopLayout L{};
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
@@ -138,7 +139,7 @@ struct CoopLayout {
         L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc; L.vk = o; o += nk;
         const int link0 = o;
         L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
-        L.comp = o; o += (nqs > 0 && 7 * nq > 16 * nl) ? 7 * nq : 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
+        L.comp = o; o += ((nqs > 0 || nqf > 0) && 7 * nq > 16 * nl) ? 7 * nq : 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
         const int nN = nr * L.ldf;
         const int need = nd * L.ldm + nd * nd > nN ? nd * L.ldm + nd * nd : nN;
         if (o - link0 < need) o = link0 + need;
@@ -150,6 +151,7 @@ struct CoopLayout {
         L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
         L.XS = o; o += nqs * nqs;
+        L.FD = o; o += nqf > 0 ? nd : 0; L.FX = o; o += nqf > 0 ? nq : 0; L.FQ = o; o += nqf * nqf; L.FV = o; o += nqf * nqf;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
         L.Y = o; o += solve_only ? 0 : nY;
         L.Z = o; o += (stat || solve_only) ? 0 : nc * L.ldy;
@@ -160,7 +162,7 @@ struct CoopLayout {
         return L;
     }
     TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
-        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs);
+        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf);
     }
 };
 
@@ -174,7 +176,7 @@ struct CtDims {
     }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
-               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0;   // springs: run-time-size flavour only
+               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0 && s.nfd == 0;   // springs / dampers: run-time-size flavour only
     }
 };
 
@@ -471,6 +473,7 @@ struct Coop {
     TREPB_HD int NQ() const { return ND() + NK(); }
     // LinearSprings: run-time-size flavour only (CtDims::matches), so the compile-time flavours drop the code
     TREPB_HD int NS() const { if constexpr (D::kStatic) return 0; else return S.ns; }
+    TREPB_HD int NFD() const { if constexpr (D::kStatic) return 0; else return S.nfd; }
 
     TREPB_HD int* ipivM() const { return (int*)(w + L.ints); }
     TREPB_HD int* iswpM() const { return ipivM() + (ND() + NC()); }
@@ -757,8 +760,10 @@ struct Coop {
     }
     // L_dq -= dV/dq (called by dyn_first; the primary pose set is selected)
     TREPB_HD void springs_first() {
-        if (NS() == 0) return;
+        if (NS() == 0 && NFD() == 0) return;
         points(true);
+        dampers_first();
+        if (NS() == 0) return;
         for (int j = t.lane(); j < NQ(); j += Team::kSize) {
             if (S.xs_idx()[j] < 0) continue;
             const int lj = S.cfg_link()[j];
@@ -776,6 +781,114 @@ struct Coop {
         }
         t.sync();
     }
+    // ---- LinearDamper forces (forces/lineardamper.c:14-107 over a single-segment TapeMeasure, tapemeasure.c:6-226)
+    // at the midpoint: x = |pA - pB|, dx_j = (v . d(pA - pB)/dq_j) / x for the configs that move exactly one end,
+    // vel = sum_k dx_k dq_k, f_j = -c vel dx_j.   FD [nd] <- sum over the dampers (spring / damper points are valid)
+    TREPB_HD void dampers_first() {
+        if (NFD() == 0) return;
+        const int lane = t.lane();
+        for (int j = lane; j < ND(); j += Team::kSize) w[L.FD + j] = 0.0;
+        for (int f = 0; f < NFD(); ++f) {
+            const int off = S.dp_off()[f], m = S.dp_off()[f + 1] - off;
+            const int* list = S.dp_cfg() + off;
+            const int A = S.da_a()[f], B = S.da_b()[f];
+            double pa[3], pb[3], v[3];
+            point(A, pa); point(B, pb);
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+            const double x = sqrt(dot3(v, v));
+            t.sync();
+            for (int a = lane; a < m; a += Team::kSize) {
+                const int lj = S.cfg_link()[list[a]];
+                double da[3], db[3];
+                dpoint(A, lj, da); dpoint(B, lj, db);
+                w[L.FX + a] = 1.0 / x * (v[0] * (da[0] - db[0]) + v[1] * (da[1] - db[1]) + v[2] * (da[2] - db[2]));
+            }
+            t.sync();
+            double vel = 0.0;
+            for (int a = 0; a < m; ++a) vel += w[L.FX + a] * w[L.dq + list[a]];
+            for (int a = lane; a < m; a += Team::kSize)
+                if (list[a] < ND()) w[L.FD + list[a]] += -S.da_c()[f] * vel * w[L.FX + a];
+        }
+        t.sync();
+    }
+    // FQ (j, i) = sum over dampers of d f_j / d q_i, FV (j, i) = d f_j / d dq_i on the compact block of configs that
+    // move exactly one end of some damper (called by dyn_second: the comp region is free as scratch)
+    TREPB_HD void dampers_second() {
+        if (NFD() == 0) return;
+        const int lane = t.lane(), nqf = S.nqf, nls = L.nls, nd = ND();
+        for (int e = lane; e < nqf * nqf; e += Team::kSize) { w[L.FQ + e] = 0.0; w[L.FV + e] = 0.0; }
+        double* DA = w + L.comp;
+        for (int f = 0; f < NFD(); ++f) {
+            const int off = S.dp_off()[f], m = S.dp_off()[f + 1] - off;
+            const int* list = S.dp_cfg() + off;
+            const int A = S.da_a()[f], B = S.da_b()[f];
+            const double c = S.da_c()[f];
+            double* DB = DA + 3 * m;
+            double* DX = DB + 3 * m;
+            double pa[3], pb[3], v[3];
+            point(A, pa); point(B, pb);
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) v[k] = pa[k] - pb[k];
+            const double x = sqrt(dot3(v, v));
+            t.sync();
+            for (int a = lane; a < m; a += Team::kSize) {
+                const int lj = S.cfg_link()[list[a]];
+                double da[3], db[3];
+                dpoint(A, lj, da); dpoint(B, lj, db);
+                TREPB_UNROLL for (int k = 0; k < 3; ++k) { DA[k * m + a] = da[k]; DB[k * m + a] = db[k]; }
+                DX[a] = 1.0 / x * (v[0] * (da[0] - db[0]) + v[1] * (da[1] - db[1]) + v[2] * (da[2] - db[2]));
+            }
+            t.sync();
+            double vel = 0.0;
+            for (int a = 0; a < m; ++a) vel += DX[a] * w[L.dq + list[a]];
+            const int lA = S.pt_link()[A], lB = S.pt_link()[B];
+            const unsigned long long ancA = lA >= 0 ? S.l_anc()[lA] : 0ull, ancB = lB >= 0 ? S.l_anc()[lB] : 0ull;
+            // one column i per lane: ddx(k, i) = TapeMeasure_length_dqdq, vel_dq(i) = sum_k ddx(k, i) dq_k
+            for (int ai = lane; ai < m; ai += Team::kSize) {
+                const int i = list[ai], li = S.cfg_link()[i], xi = S.xf_idx()[i];
+                double veldq = 0.0;
+                for (int bk = 0; bk < m; ++bk) {
+                    const int kc = list[bk], lk = S.cfg_link()[kc];
+                    double ddv[3] = {0.0, 0.0, 0.0};
+                    if (li >= 0 && lk >= 0) {
+                        int up = lk, lo_idx = ai;
+                        if (!((S.l_anc()[li] >> lk) & 1ull)) { up = li; lo_idx = bk; }
+                        const int kup = S.l_kind()[up];
+                        if (kup & 4) {
+                            const int ax = kup & 3;
+                            const double aw[3] = {w[oR + ax * nls + up], w[oR + (3 + ax) * nls + up], w[oR + (6 + ax) * nls + up]};
+                            const bool onA = ((ancA >> li) & 1ull) && ((ancA >> lk) & 1ull);
+                            const bool onB = ((ancB >> li) & 1ull) && ((ancB >> lk) & 1ull);
+                            double d3[3] = {0.0, 0.0, 0.0};
+                            if (onA) { TREPB_UNROLL for (int q = 0; q < 3; ++q) d3[q] += DA[q * m + lo_idx]; }
+                            if (onB) { TREPB_UNROLL for (int q = 0; q < 3; ++q) d3[q] -= DB[q * m + lo_idx]; }
+                            cross3(aw, d3, ddv);
+                        }
+                    }
+                    double dk[3], di[3];
+                    TREPB_UNROLL for (int q = 0; q < 3; ++q) { dk[q] = DA[q * m + bk] - DB[q * m + bk]; di[q] = DA[q * m + ai] - DB[q * m + ai]; }
+                    const double tt = DX[bk] * DX[ai] - dot3(dk, di) - dot3(v, ddv);
+                    const double ddx = -1.0 / x * tt;
+                    veldq += ddx * w[L.dq + kc];
+                    if (kc < nd) w[L.FQ + S.xf_idx()[kc] * nqf + xi] += -c * vel * ddx;
+                }
+                for (int bj = 0; bj < m; ++bj) {
+                    const int j = list[bj];
+                    if (j >= nd) continue;
+                    w[L.FQ + S.xf_idx()[j] * nqf + xi] += -c * veldq * DX[bj];
+                    w[L.FV + S.xf_idx()[j] * nqf + xi] += -c * DX[ai] * DX[bj];
+                }
+            }
+        }
+        t.sync();
+    }
+    // generalized force on dynamic config j besides the per-config constants: Damping, ConfigForce, LinearDampers
+    TREPB_HD double ext_force(int j) const {
+        double fo = -S.damp()[j] * w[L.dq + j];
+        for (int u = 0; u < NU(); ++u) fo += S.Fu()[j * NU() + u] * w[L.u1 + u];
+        if (NFD() > 0) fo += w[L.FD + j];
+        return fo;
+    }
+
     // XS = sum over springs of d2V / dq_i dq_j on the configs any spring depends on (called by dyn_second once
     // the pair tables are done: the comp region is free to hold dA_i, dB_i, dx_i of one spring at a time)
     TREPB_HD void springs_second() {
@@ -891,6 +1004,7 @@ struct Coop {
         }
         t.sync();
         springs_second();
+        dampers_second();
     }
 
     // ---- first-derivative blocks from the chain-pair tables.  Every block of calc_deriv1
@@ -928,6 +1042,13 @@ struct Coop {
         if (NS() > 0) {   // Q = dt/4 L_dqdq enters all four combinations with a plus sign; L_dqdq -= d2V/dqdq
             const int xa = S.xs_idx()[a], xb = S.xs_idx()[b];
             if (xa >= 0 && xb >= 0) val -= 0.25 * dt * w[L.XS + xa * S.nqs + xb];
+        }
+        if (NFD() > 0 && (which == 1 || which == 2)) {   // D1fm2 = dt/2 f_dq - f_ddq, D2fm2 = dt/2 f_dq + f_ddq (row b, column a)
+            const int xa = S.xf_idx()[a], xb = S.xf_idx()[b];
+            if (xa >= 0 && xb >= 0) {
+                const double fq = 0.5 * dt * w[L.FQ + xb * S.nqf + xa], fv = w[L.FV + xb * S.nqf + xa];
+                val += which == 1 ? fq - fv : fq + fv;
+            }
         }
         return val;
     }
@@ -1180,8 +1301,7 @@ struct Coop {
             TREPB_TICK(19);
             // residual (midpointvi.c:533-565); forces: Damping (damping.c:13-22), ConfigForce (configforce.c:13-22)
             for (int j = lane; j < nd; j += Team::kSize) {
-                double fo = -S.damp()[j] * w[L.dq + j];
-                for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
+                const double fo = ext_force(j);
                 double f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
                 for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
                 // p2 = D2L2 of this midpoint (midpointvi.c:742-743, 491-504): the value of the last
@@ -1230,6 +1350,15 @@ struct Coop {
                 }
             }
             t.sync();
+            if (NFD() > 0) {
+                // dt (1/2 f_dq + 1/dt f_ddq) of the LinearDampers (midpointvi.c:577-670)
+                const int nqf = S.nqf;
+                for (int e = lane; e < nqf * nqf; e += Team::kSize) {
+                    const int ca = S.xf_cfg()[e / nqf], cb = S.xf_cfg()[e % nqf];
+                    if (ca < nd && cb < nd) A[ca * ld + cb] += 0.5 * dt * w[L.FQ + e] + w[L.FV + e];
+                }
+                t.sync();
+            }
             if (NS() > 0) {
                 // L_dqdq -= d2V/dqdq of the LinearSprings: cross-chain entries the pair tables do not carry
                 const int nqs = S.nqs;
@@ -1306,8 +1435,7 @@ struct Coop {
         double f = 0.0;
         // fr aliases Lq: every lane forms its entries before any is stored
         for (int j = lane; j < nd; j += Team::kSize) {
-            double fo = -S.damp()[j] * w[L.dq + j];
-            for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
+            const double fo = ext_force(j);
             f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
             for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
             w[L.fr + j] = f;
@@ -1319,11 +1447,12 @@ struct Coop {
     TREPB_HD void calc_fm2(double dt) {
         const int nd = ND(), nu = NU();
         set_point(0, dt);
-        for (int j = t.lane(); j < nd; j += Team::kSize) {
-            double fo = -S.damp()[j] * w[L.dq + j];
-            for (int u = 0; u < nu; ++u) fo += S.Fu()[j * nu + u] * w[L.u1 + u];
-            w[L.fr + j] = dt * fo;
+        if (NFD() > 0) {       // the dampers need the midpoint pose of their end points
+            pose_sweep(0);
+            points(true);
+            dampers_first();
         }
+        for (int j = t.lane(); j < nd; j += Team::kSize) w[L.fr + j] = dt * ext_force(j);
         t.sync();
     }
 

@@ -33,7 +33,8 @@ struct CoopSys {
     int nsl;        // super levels of the pose sweep: one per run of single-child links (chain)
     int ndc, nqc;   // dynamic configs / configs that any constraint depends on (compact DDh.lambda block)
     int ns, nqs;    // LinearSpring potentials / configs that any of them depends on (compact block of their Hessian)
-    int npc;        // points [0, npc) belong to constraints, [npc, np) are spring ends (evaluated at the midpoint)
+    int npc;        // points [0, npc) belong to constraints, [npc, np) are spring / damper ends (evaluated at the midpoint)
+    int nfd, nqf;   // LinearDamper forces / configs that move exactly one end of any of them (compact f_dq, f_ddq blocks)
     int has_gravity;
     double grav[3];
     // Tables live in one relocatable blob (host memory, device memory or a shared-memory copy):
@@ -60,6 +61,10 @@ struct CoopSys {
     //                 row = column of a config in the block of sum_s d2V_s / dq dq (-1: no spring depends on
     //                 it), xs_cfg [nqs] its inverse.  Links that carry a spring end have bit6 of l_kind set
     //                 (they take part in the midpoint pose sweep even without mass below).
+    //   dampers [nfd] LinearDamper over a single-segment tape measure (forces/lineardamper.c:14-107,
+    //                 tapemeasure.py:97-110): da_a, da_b (points), da_c, dp_off [nfd+1] / dp_cfg: the configs that
+    //                 move exactly ONE end (the only ones the reference's path length depends on), xf_idx [nq] /
+    //                 xf_cfg [nqf]: compact row = column of such a config in the f_dq / f_ddq blocks.
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -97,6 +102,14 @@ struct CoopSys {
     int o_sl_head;
     int o_con_n;
     int o_sp_a, o_sp_b, o_sp_k, o_sp_x0, o_sp_off, o_sp_cfg, o_xs_idx, o_xs_cfg;
+    int o_da_a, o_da_b, o_da_c, o_dp_off, o_dp_cfg, o_xf_idx, o_xf_cfg;
+    TREPB_HD const int32_t* da_a() const { return (const int32_t*)(base + o_da_a); }
+    TREPB_HD const int32_t* da_b() const { return (const int32_t*)(base + o_da_b); }
+    TREPB_HD const double* da_c() const { return (const double*)(base + o_da_c); }
+    TREPB_HD const int32_t* dp_off() const { return (const int32_t*)(base + o_dp_off); }
+    TREPB_HD const int32_t* dp_cfg() const { return (const int32_t*)(base + o_dp_cfg); }
+    TREPB_HD const int32_t* xf_idx() const { return (const int32_t*)(base + o_xf_idx); }
+    TREPB_HD const int32_t* xf_cfg() const { return (const int32_t*)(base + o_xf_cfg); }
     TREPB_HD const int32_t* sp_a() const { return (const int32_t*)(base + o_sp_a); }
     TREPB_HD const int32_t* sp_b() const { return (const int32_t*)(base + o_sp_b); }
     TREPB_HD const double* sp_k() const { return (const double*)(base + o_sp_k); }
@@ -152,7 +165,7 @@ struct CoopPack {
     std::string why;          // why the cooperative path does not apply
     std::vector<char> blob;
     CoopSys proto;
-    size_t off[48];
+    size_t off[56];
 
     CoopSys view(const char* base) const {
         CoopSys s = proto;
@@ -195,6 +208,8 @@ struct CoopPack {
         s.o_con_n = (int)off[k++];
         s.o_sp_a = (int)off[k++]; s.o_sp_b = (int)off[k++]; s.o_sp_k = (int)off[k++]; s.o_sp_x0 = (int)off[k++];
         s.o_sp_off = (int)off[k++]; s.o_sp_cfg = (int)off[k++]; s.o_xs_idx = (int)off[k++]; s.o_xs_cfg = (int)off[k++];
+        s.o_da_a = (int)off[k++]; s.o_da_b = (int)off[k++]; s.o_da_c = (int)off[k++]; s.o_dp_off = (int)off[k++];
+        s.o_dp_cfg = (int)off[k++]; s.o_xf_idx = (int)off[k++]; s.o_xf_cfg = (int)off[k++];
         return s;
     }
 };
@@ -252,7 +267,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     for (int i = 0; i < d->n_potentials; ++i)
         if (d->pot_kind[i] == TREPB_POT_NONLINEAR_CONFIG_SPRING) { P.why = "NonlinearConfigSpring potential"; return P; }
     for (int i = 0; i < d->n_forces; ++i)
-        if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER) { P.why = "LinearDamper force"; return P; }
+        if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER && d->force_i[4 * i + 1] != 2) { P.why = "LinearDamper over more than one segment"; return P; }
         else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }
 
     // ---- frames -> links
@@ -438,6 +453,27 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
         for (int j = 0; j < nq; ++j) if ((any >> j) & 1ull) { xs_idx[j] = (int32_t)xs_cfg.size(); xs_cfg.push_back(j); }
     }
     const int ns = (int)sp_a.size(), nqs = (int)xs_cfg.size();
+    // ---- LinearDamper end points and the configs that move exactly one end
+    std::vector<int32_t> da_a, da_b, dp_off(1, 0), dp_cfg, xf_idx(nq > 0 ? nq : 1, -1), xf_cfg;
+    std::vector<double> da_c;
+    {
+        uint64_t any = 0;
+        for (int i = 0; i < d->n_forces; ++i) {
+            if (d->force_kind[i] != TREPB_FORCE_LINEAR_DAMPER) continue;
+            const int off = d->force_i[4 * i];
+            const int a = point_of(d->ipool[off], (size_t)npc, 64), b = point_of(d->ipool[off + 1], (size_t)npc, 64);
+            da_a.push_back(a); da_b.push_back(b); da_c.push_back(d->force_d[4 * i]);
+            uint64_t ma = 0, mb = 0;
+            for (int x = pt_link[a]; x >= 0; x = l_par[x]) ma |= 1ull << l_cfg[x];
+            for (int x = pt_link[b]; x >= 0; x = l_par[x]) mb |= 1ull << l_cfg[x];
+            const uint64_t m = ma ^ mb;
+            for (int j = 0; j < nq; ++j) if ((m >> j) & 1ull) dp_cfg.push_back(j);
+            dp_off.push_back((int32_t)dp_cfg.size());
+            any |= m;
+        }
+        for (int j = 0; j < nq; ++j) if ((any >> j) & 1ull) { xf_idx[j] = (int32_t)xf_cfg.size(); xf_cfg.push_back(j); }
+    }
+    const int nfd = (int)da_a.size(), nqf = (int)xf_cfg.size();
     const int np = (int)pt_link.size();
     std::vector<int32_t> cd_off(nc + 1, 0), cd_cfg, cd_nd(nc > 0 ? nc : 1, 0);
     for (int c = 0; c < nc; ++c) {
@@ -500,6 +536,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
     P.proto.ndc = ndc; P.proto.nqc = nqc; P.proto.nsl = nsl;
     P.proto.ns = ns; P.proto.nqs = nqs; P.proto.npc = npc;
+    P.proto.nfd = nfd; P.proto.nqf = nqf;
     P.proto.has_gravity = has_grav;
     for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
     int k = 0;
@@ -526,6 +563,9 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(sp_a.data(), 4 * (size_t)ns); put(sp_b.data(), 4 * (size_t)ns); put(sp_k.data(), 8 * (size_t)ns); put(sp_x0.data(), 8 * (size_t)ns);
     put(sp_off.data(), 4 * sp_off.size()); put(sp_cfg.data(), 4 * sp_cfg.size());
     put(xs_idx.data(), 4 * (size_t)nq); put(xs_cfg.data(), 4 * (size_t)nqs);
+    put(da_a.data(), 4 * (size_t)nfd); put(da_b.data(), 4 * (size_t)nfd); put(da_c.data(), 8 * (size_t)nfd);
+    put(dp_off.data(), 4 * dp_off.size()); put(dp_cfg.data(), 4 * dp_cfg.size());
+    put(xf_idx.data(), 4 * (size_t)nq); put(xf_cfg.data(), 4 * (size_t)nqf);
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;

@@ -176,11 +176,15 @@ struct SpecRegistry {
     int n;
 };
 SpecRegistry& spec_registry();
+// Layout fingerprint of everything a specialisation unit shares with the library (kernel parameter structs,
+// the kernel-set table).  A plug-in compiled against other headers registers with another fingerprint and is
+// refused by spec_register (which lives in the library), instead of being called with mismatched structs.
+constexpr unsigned kSpecAbi = 0x20000u + (unsigned)(sizeof(RtSys) * 131 + sizeof(StepParams) * 31 + sizeof(LinParams) * 17 +
+                                                    sizeof(ProjParams) * 13 + sizeof(P2Params) * 7 + sizeof(D2Params) * 5 +
+                                                    sizeof(LaunchCfg) * 3 + sizeof(KernelSet));
+bool spec_register(const KernelSet* ks, unsigned abi);
 struct SpecRegistrar {
-    explicit SpecRegistrar(const KernelSet* ks) {
-        SpecRegistry& r = spec_registry();
-        if (r.n < SpecRegistry::kMax) r.sets[r.n++] = ks;
-    }
+    explicit SpecRegistrar(const KernelSet* ks) { spec_register(ks, kSpecAbi); }
 };
 const KernelSet* general_kernels();
 

@@ -182,8 +182,9 @@ def device_count():
 
 
 def coop_dims(desc):
-    """Shape the cooperative kernels see: (nd, nk, nu, nc, links, points, chain pairs, levels,
-    constrained dynamic configs, constrained configs), or None when they do not apply."""
+    """Shape the compile-time-size cooperative kernels are instantiated for: (nd, nk, nu, nc, links, points,
+    chain pairs, levels, constrained dynamic configs, constrained configs), or None when they do not apply
+    (wrenches / spline springs: no cooperative kernels; LinearSpring / LinearDamper: run-time sizes only)."""
     cd, keep = D.to_c(desc)
     out = (C.c_int32 * 10)()
     if _lib.trepb_coop_dims(C.byref(cd), out) != 0:
