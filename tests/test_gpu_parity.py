@@ -36,7 +36,7 @@ def ref():
 
 
 # LinearSpring / LinearDamper, PointOnPlane, wrenches: thread-per-instance kernels only
-COOP_UNSUPPORTED = {"wrench_arm", "spline_pendulum"}     # wrenches / spline springs: thread kernels only
+COOP_UNSUPPORTED = set()     # every plugin kind runs on the cooperative kernels since round 2
 
 
 def _systems(lib, name):

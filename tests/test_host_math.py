@@ -28,14 +28,14 @@ def test_cases_step_and_deriv1(name):
     assert flips == 0, "Newton iteration counts differ from the reference in %d cases" % flips
 
 
-@pytest.mark.parametrize("name", G.ALL + ["pccd"] + G.PARITY + G.PARITY_SPRING)
+@pytest.mark.parametrize("name", G.ALL + ["pccd", "spline_pendulum", "wrench_arm"] + G.PARITY + G.PARITY_SPRING)
 def test_cooperative_math_cases(name):
     """The team-cooperative formulation (link tables, world-coordinate spatial algebra,
     right-looking LU; trepb_coop_math.cuh) run with a one-lane host team against the goldens."""
     g = G.golden(name)
     d = G.desc(name)
     if H.coop_info(d) is None:
-        pytest.skip("cooperative path does not apply (wrench / spline spring)")
+        pytest.skip("cooperative path does not apply")
     flips = 0
     # run-time sizes everywhere; the compile-time-size flavour (register-resident right-hand-side
     # columns) for the shape the build specialises

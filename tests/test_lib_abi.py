@@ -74,7 +74,7 @@ def test_cooperative_shapes_and_generated_instantiation():
     assert lib.coop_dims(G.desc("puppet")) == (22, 18, 0, 6, 34, 12, 157, 10, 20, 38)
     assert lib.coop_dims(G.desc("pendulum5")) == (5, 0, 0, 0, 5, 0, 15, 5, 0, 0)
     assert lib.coop_dims(G.desc("dual_pendulums")) is None      # LinearSpring / LinearDamper: run-time-size flavour only
-    assert lib.coop_dims(G.desc("wrench_arm")) is None          # wrenches: no cooperative kernels at all
+    assert lib.coop_dims(G.desc("wrench_arm")) is None          # wrenches: run-time-size flavour only
     for name in build.COOP_AOT_SYSTEMS:
         text = open(os.path.join(build.GEN, "coop_%s.cu" % name)).read()
         dims = ", ".join(str(v) for v in lib.coop_dims(G.desc(name)))

@@ -104,6 +104,8 @@ struct CoopLayout {
     int Lq, Lv, VV, QQ, UP, DN;
     int XS;                          // sum of the LinearSpring Hessians d2V / dq dq at the midpoint [nqs][nqs]
     int FD, FX, FQ, FV;              // LinearDampers: force [nd], dx scratch [nq], f_dq / f_ddq blocks [nqf][nqf]
+    int KS;                          // config stiffness at the evaluation point [nq]: ConfigSpring k + spline springs' -d2V/dq2
+    int FUW;                         // wrenches: d f / d u at the evaluation point [nd][nu] (on top of the constant ConfigForce part)
     int Dh1, Dh2, hc;
     int N;                           // Newton augmented matrix [nr][ldf]; aliases the link region
     int Y;                           // DDh.lambda block / right-hand sides [nd][ldy] (first-derivative kernels only)
@@ -125,7 +127,7 @@ struct CoopLayout {
     // per marionette instance, 12 instead of 8 instances per SM.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
                                               bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false,
-                                              int nqs = 0, int nqf = 0) {
+                                              int nqs = 0, int nqf = 0, int nns = 0, int nw = 0) {
         CoopLayout L{};
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
@@ -151,6 +153,8 @@ struct CoopLayout {
         L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
         L.XS = o; o += nqs * nqs;
+        L.KS = o; o += nns > 0 ? nq : 0;
+        L.FUW = o; o += nw > 0 ? nd * nu : 0;
         L.FD = o; o += nqf > 0 ? nd : 0; L.FX = o; o += nqf > 0 ? nq : 0; L.FQ = o; o += nqf * nqf; L.FV = o; o += nqf * nqf;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
         L.Y = o; o += solve_only ? 0 : nY;
@@ -162,7 +166,7 @@ struct CoopLayout {
         return L;
     }
     TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
-        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf);
+        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf, s.nns, s.nw);
     }
 };
 
@@ -176,7 +180,7 @@ struct CtDims {
     }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
-               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0 && s.nfd == 0;   // springs / dampers: run-time-size flavour only
+               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0 && s.nfd == 0 && s.nns == 0 && s.nw == 0;   // springs / dampers / wrenches: run-time-size flavour only
     }
 };
 
@@ -474,6 +478,16 @@ struct Coop {
     // LinearSprings: run-time-size flavour only (CtDims::matches), so the compile-time flavours drop the code
     TREPB_HD int NS() const { if constexpr (D::kStatic) return 0; else return S.ns; }
     TREPB_HD int NFD() const { if constexpr (D::kStatic) return 0; else return S.nfd; }
+    TREPB_HD int NNS() const { if constexpr (D::kStatic) return 0; else return S.nns; }
+    TREPB_HD int NW() const { if constexpr (D::kStatic) return 0; else return S.nw; }
+    TREPB_HD int NPF() const { return NFD() + NW(); }     // forces acting through world points: dampers, wrenches
+    TREPB_HD double fu_eff(int j, int u) const {
+        const double c = S.Fu()[j * NU() + u];
+        return NW() > 0 ? c + w[L.FUW + j * NU() + u] : c;
+    }
+    // stiffness of config i seen by the second-order terms: the ConfigSpring constant, plus -d2V/dq2 of the spline
+    // springs at the last evaluated midpoint (dyn_first)
+    TREPB_HD double ks_eff(int i) const { return NNS() > 0 ? w[L.KS + i] : S.ks()[i]; }
 
     TREPB_HD int* ipivM() const { return (int*)(w + L.ints); }
     TREPB_HD int* iswpM() const { return ipivM() + (ND() + NC()); }
@@ -745,6 +759,31 @@ struct Coop {
         // ConfigSpring (configspring.c:22-30)
         for (int i = lane; i < NQ(); i += Team::kSize)
             if (S.ks()[i] != 0.0) w[L.Lq + i] -= S.ks()[i] * w[L.qe + i] - S.kq0()[i];
+        if (NNS() > 0) {
+            // NonlinearConfigSpring: dV/dq = -y(m q + b), y a piecewise quintic (nonlinear_config_spring.c:23-47,
+            // spline.c:7-62: same segment search, same extrapolation segments)
+            for (int i = lane; i < NQ(); i += Team::kSize) {
+                double ksum = S.ks()[i], lq = 0.0;
+                for (int sp = 0; sp < NNS(); ++sp) {
+                    const int32_t* si = S.nsp_i() + 3 * sp;
+                    if (si[0] != i) continue;
+                    const double* tab = S.nsp_tab() + si[1];
+                    const int n = si[2];
+                    const double m = S.nsp_d()[2 * sp], b = S.nsp_d()[2 * sp + 1];
+                    const double x = m * w[L.qe + i] + b;
+                    int seg = 0;
+                    if (x >= tab[n - 1]) seg = n - 2;
+                    else if (!(x < tab[0])) { while (x >= tab[seg + 1]) ++seg; }
+                    const double* cf = tab + n + 6 * seg;
+                    const double dx = x - tab[seg];
+                    const double dx2 = dx * dx, dx3 = dx2 * dx, dx4 = dx3 * dx, dx5 = dx4 * dx;
+                    lq += cf[0] * dx5 + cf[1] * dx4 + cf[2] * dx3 + cf[3] * dx2 + cf[4] * dx + cf[5];
+                    ksum -= (5.0 * cf[0] * dx4 + 4.0 * cf[1] * dx3 + 3.0 * cf[2] * dx2 + 2.0 * cf[3] * dx + cf[4]) * m;
+                }
+                w[L.Lq + i] += lq;
+                w[L.KS + i] = ksum;
+            }
+        }
         t.sync();
         springs_first();
     }
@@ -760,9 +799,14 @@ struct Coop {
     }
     // L_dq -= dV/dq (called by dyn_first; the primary pose set is selected)
     TREPB_HD void springs_first() {
-        if (NS() == 0 && NFD() == 0) return;
+        if (NS() == 0 && NPF() == 0) return;
         points(true);
-        dampers_first();
+        if (NPF() > 0) {
+            for (int j = t.lane(); j < ND(); j += Team::kSize) w[L.FD + j] = 0.0;
+            t.sync();
+            dampers_first();
+            wrenches_first();
+        }
         if (NS() == 0) return;
         for (int j = t.lane(); j < NQ(); j += Team::kSize) {
             if (S.xs_idx()[j] < 0) continue;
@@ -787,7 +831,6 @@ struct Coop {
     TREPB_HD void dampers_first() {
         if (NFD() == 0) return;
         const int lane = t.lane();
-        for (int j = lane; j < ND(); j += Team::kSize) w[L.FD + j] = 0.0;
         for (int f = 0; f < NFD(); ++f) {
             const int off = S.dp_off()[f], m = S.dp_off()[f + 1] - off;
             const int* list = S.dp_cfg() + off;
@@ -814,7 +857,7 @@ struct Coop {
     // FQ (j, i) = sum over dampers of d f_j / d q_i, FV (j, i) = d f_j / d dq_i on the compact block of configs that
     // move exactly one end of some damper (called by dyn_second: the comp region is free as scratch)
     TREPB_HD void dampers_second() {
-        if (NFD() == 0) return;
+        if (NPF() == 0) return;
         const int lane = t.lane(), nqf = S.nqf, nls = L.nls, nd = ND();
         for (int e = lane; e < nqf * nqf; e += Team::kSize) { w[L.FQ + e] = 0.0; w[L.FV + e] = 0.0; }
         double* DA = w + L.comp;
@@ -880,12 +923,125 @@ struct Coop {
             }
         }
         t.sync();
+        wrenches_second();
+    }
+    // ---- Body / Hybrid / Spatial wrenches (forces/bodywrench.c, hybridwrench.c, spatialwrench.c) on a frame F:
+    // f_j = J_j . w with J_j = (dp_j, a_j) hybrid, (dp_j - a_j x p_F, a_j) spatial, (R_F^T dp_j, R_F^T a_j) body;
+    // dp_j = d p_F / d q_j, a_j the world axis of a revolute joint (0: prismatic); d a_j / d q_i = a_i x a_j for a
+    // joint i above j; each of the six components of w a constant or an input.
+    TREPB_HD void wrench_setup(int wi, double* wr, double* RF, double* pF) const {
+        const int32_t* ii = S.wr_i() + 8 * wi;
+        const double* dd = S.wr_d() + 15 * wi;
+        TREPB_UNROLL for (int k = 0; k < 6; ++k) wr[k] = ii[2 + k] >= 0 ? w[L.u1 + ii[2 + k]] : dd[k];
+        const int pt = ii[1], l = S.pt_link()[pt], nls = L.nls;
+        point(pt, pF);
+        TREPB_UNROLL
+        for (int r = 0; r < 3; ++r)
+            TREPB_UNROLL
+            for (int c = 0; c < 3; ++c)
+                RF[r * 3 + c] = l < 0 ? dd[6 + r * 3 + c]
+                                      : (w[oR + (r * 3) * nls + l] * dd[6 + c] + w[oR + (r * 3 + 1) * nls + l] * dd[9 + c] +
+                                         w[oR + (r * 3 + 2) * nls + l] * dd[12 + c]);
+    }
+    TREPB_HD void link_axis(int lj, double* aj) const {   // world axis of a revolute link, zero otherwise
+        const int kind = S.l_kind()[lj], a = kind & 3, nls = L.nls;
+        if (kind & 4) { aj[0] = w[oR + a * nls + lj]; aj[1] = w[oR + (3 + a) * nls + lj]; aj[2] = w[oR + (6 + a) * nls + lj]; }
+        else { aj[0] = aj[1] = aj[2] = 0.0; }
+    }
+    TREPB_HD void wrench_J(int kind, const double* RF, const double* pF, const double* dp, const double* aj, double* J) const {
+        if (kind == F_HYBRID_WRENCH) {
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) { J[k] = dp[k]; J[3 + k] = aj[k]; }
+        } else if (kind == F_SPATIAL_WRENCH) {
+            double t3[3];
+            cross3(aj, pF, t3);
+            TREPB_UNROLL for (int k = 0; k < 3; ++k) { J[k] = dp[k] - t3[k]; J[3 + k] = aj[k]; }
+        } else {
+            TREPB_UNROLL
+            for (int k = 0; k < 3; ++k) {
+                J[k] = RF[k] * dp[0] + RF[3 + k] * dp[1] + RF[6 + k] * dp[2];
+                J[3 + k] = RF[k] * aj[0] + RF[3 + k] * aj[1] + RF[6 + k] * aj[2];
+            }
+        }
+    }
+    // FD [j] += J_j . w and FUW [j][u] = J_j [k] for the input components (one row j per lane)
+    TREPB_HD void wrenches_first() {
+        if (NW() == 0) return;
+        const int nu = NU();
+        for (int j = t.lane(); j < ND(); j += Team::kSize) {
+            for (int u = 0; u < nu; ++u) w[L.FUW + j * nu + u] = 0.0;
+            const int lj = S.cfg_link()[j];
+            if (S.xf_idx()[j] < 0 || lj < 0) continue;
+            double acc = 0.0;
+            for (int wi = 0; wi < NW(); ++wi) {
+                if (!((S.wr_dep()[wi] >> j) & 1ull)) continue;
+                const int32_t* ii = S.wr_i() + 8 * wi;
+                double wr[6], RF[9], pF[3], dp[3], aj[3], J[6];
+                wrench_setup(wi, wr, RF, pF);
+                dpoint(ii[1], lj, dp);
+                link_axis(lj, aj);
+                wrench_J(ii[0], RF, pF, dp, aj, J);
+                acc += dot6(J, wr);
+                TREPB_UNROLL for (int k = 0; k < 6; ++k) if (ii[2 + k] >= 0) w[L.FUW + j * nu + ii[2 + k]] += J[k];
+            }
+            w[L.FD + j] += acc;
+        }
+        t.sync();
+    }
+    // FQ (j, i) += d J_j / d q_i . w (one entry of the compact block per lane)
+    TREPB_HD void wrenches_second() {
+        if (NW() == 0) return;
+        const int nqf = S.nqf, nd = ND();
+        for (int e = t.lane(); e < nqf * nqf; e += Team::kSize) {
+            const int j = S.xf_cfg()[e / nqf], i = S.xf_cfg()[e % nqf];
+            if (j >= nd) continue;
+            const int lj = S.cfg_link()[j], li = S.cfg_link()[i];
+            if (lj < 0 || li < 0) continue;
+            double acc = 0.0;
+            for (int wi = 0; wi < NW(); ++wi) {
+                const unsigned long long dep = S.wr_dep()[wi];
+                if (!((dep >> j) & 1ull) || !((dep >> i) & 1ull)) continue;
+                const int32_t* ii = S.wr_i() + 8 * wi;
+                const int kind = ii[0], pt = ii[1];
+                double wr[6], RF[9], pF[3], dpj[3], dpi[3], aj[3], ai[3], ddp[3], da[3], dJ[6];
+                wrench_setup(wi, wr, RF, pF);
+                dpoint(pt, lj, dpj); dpoint(pt, li, dpi);
+                link_axis(lj, aj); link_axis(li, ai);
+                // d2 p_F / d q_j d q_i: the upper joint's axis crosses the lower joint's first derivative
+                const bool j_above = ((S.l_anc()[li] >> lj) & 1ull) != 0;
+                if (j_above) cross3(aj, dpi, ddp); else cross3(ai, dpj, ddp);
+                // d a_j / d q_i = a_i x a_j when joint i is strictly above joint j
+                if (i != j && ((S.l_anc()[lj] >> li) & 1ull)) cross3(ai, aj, da);
+                else { da[0] = da[1] = da[2] = 0.0; }
+                if (kind == F_HYBRID_WRENCH) {
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { dJ[k] = ddp[k]; dJ[3 + k] = da[k]; }
+                } else if (kind == F_SPATIAL_WRENCH) {
+                    double t3[3], u3[3];
+                    cross3(da, pF, t3);
+                    cross3(aj, dpi, u3);
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { dJ[k] = ddp[k] - t3[k] - u3[k]; dJ[3 + k] = da[k]; }
+                } else {
+                    // d (R^T x) / d q_i = R^T (dx/dq_i - a_i x x)
+                    double t3[3], u3[3];
+                    cross3(ai, dpj, t3);
+                    cross3(ai, aj, u3);
+                    TREPB_UNROLL for (int k = 0; k < 3; ++k) { t3[k] = ddp[k] - t3[k]; u3[k] = da[k] - u3[k]; }
+                    TREPB_UNROLL
+                    for (int k = 0; k < 3; ++k) {
+                        dJ[k] = RF[k] * t3[0] + RF[3 + k] * t3[1] + RF[6 + k] * t3[2];
+                        dJ[3 + k] = RF[k] * u3[0] + RF[3 + k] * u3[1] + RF[6 + k] * u3[2];
+                    }
+                }
+                acc += dot6(dJ, wr);
+            }
+            w[L.FQ + e] += acc;
+        }
+        t.sync();
     }
     // generalized force on dynamic config j besides the per-config constants: Damping, ConfigForce, LinearDampers
     TREPB_HD double ext_force(int j) const {
         double fo = -S.damp()[j] * w[L.dq + j];
         for (int u = 0; u < NU(); ++u) fo += S.Fu()[j * NU() + u] * w[L.u1 + u];
-        if (NFD() > 0) fo += w[L.FD + j];
+        if (NPF() > 0) fo += w[L.FD + j];
         return fo;
     }
 
@@ -1018,7 +1174,7 @@ struct Coop {
         for (int e = t.lane(); e < NPAIRS(); e += Team::kSize) {
             const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
             double qq = w[L.QQ + e];
-            if (i == j) qq -= S.ks()[S.l_cfg()[i]];
+            if (i == j) qq -= ks_eff(S.l_cfg()[i]);
             const double Q = 0.25 * dt * qq, V = 1.0 / dt * w[L.VV + e], U = 0.5 * w[L.UP + e], Dn = 0.5 * w[L.DN + e];
             w[L.VV + e] = (Q + V) + U + Dn;
             w[L.QQ + e] = (Q + V) - U - Dn;
@@ -1033,7 +1189,7 @@ struct Coop {
     TREPB_HD double comb(int which, int a, int b, double dt) const {
         const int m = S.pm()[a * ND() + b];
         double val;
-        if (m == 0) val = a == b ? 0.25 * dt * -S.ks()[a] : 0.0;
+        if (m == 0) val = a == b ? 0.25 * dt * -ks_eff(a) : 0.0;
         else {
             const int e = (m > 0 ? m : -m) - 1;
             const int off = which == 0 ? L.VV : (which == 1 ? L.QQ : (((which == 2) == (m > 0)) ? L.UP : L.DN));
@@ -1043,7 +1199,7 @@ struct Coop {
             const int xa = S.xs_idx()[a], xb = S.xs_idx()[b];
             if (xa >= 0 && xb >= 0) val -= 0.25 * dt * w[L.XS + xa * S.nqs + xb];
         }
-        if (NFD() > 0 && (which == 1 || which == 2)) {   // D1fm2 = dt/2 f_dq - f_ddq, D2fm2 = dt/2 f_dq + f_ddq (row b, column a)
+        if (NPF() > 0 && (which == 1 || which == 2)) {   // D1fm2 = dt/2 f_dq - f_ddq, D2fm2 = dt/2 f_dq + f_ddq (row b, column a)
             const int xa = S.xf_idx()[a], xb = S.xf_idx()[b];
             if (xa >= 0 && xb >= 0) {
                 const double fq = 0.5 * dt * w[L.FQ + xb * S.nqf + xa], fv = w[L.FV + xb * S.nqf + xa];
@@ -1331,7 +1487,7 @@ struct Coop {
                 const int k = e / (nr + 1), i = e - k * (nr + 1);
                 double v = 0.0;
                 if (i == nr) v = w[L.fr + k];
-                else if (k < nd && i < nd) { if (k == i) v = -S.damp()[k] - 0.25 * dt * S.ks()[k]; }
+                else if (k < nd && i < nd) { if (k == i) v = -S.damp()[k] - 0.25 * dt * ks_eff(k); }
                 else if (k < nd) v = -w[L.Dh1 + (i - nd) * nd + k];
                 else if (i < nd) v = w[L.Dh2 + (k - nd) * nq + i];
                 A[k * ld + i] = v;
@@ -1350,8 +1506,8 @@ struct Coop {
                 }
             }
             t.sync();
-            if (NFD() > 0) {
-                // dt (1/2 f_dq + 1/dt f_ddq) of the LinearDampers (midpointvi.c:577-670)
+            if (NPF() > 0) {
+                // dt (1/2 f_dq + 1/dt f_ddq) of the LinearDampers and wrenches (midpointvi.c:577-670)
                 const int nqf = S.nqf;
                 for (int e = lane; e < nqf * nqf; e += Team::kSize) {
                     const int ca = S.xf_cfg()[e / nqf], cb = S.xf_cfg()[e % nqf];
@@ -1447,10 +1603,13 @@ struct Coop {
     TREPB_HD void calc_fm2(double dt) {
         const int nd = ND(), nu = NU();
         set_point(0, dt);
-        if (NFD() > 0) {       // the dampers need the midpoint pose of their end points
+        if (NPF() > 0) {       // dampers and wrenches need the midpoint pose of their end points
             pose_sweep(0);
             points(true);
+            for (int j = t.lane(); j < nd; j += Team::kSize) w[L.FD + j] = 0.0;
+            t.sync();
             dampers_first();
+            wrenches_first();
         }
         for (int j = t.lane(); j < nd; j += Team::kSize) w[L.fr + j] = dt * ext_force(j);
         t.sync();
@@ -1475,7 +1634,7 @@ struct Coop {
         }
         col -= nq;
         if (col < nd) return col == j ? -1.0 : 0.0;
-        if (col < nd + nu) return -dt * S.Fu()[j * nu + (col - nd)];
+        if (col < nd + nu) return -dt * fu_eff(j, col - nd);
         return -comb(2, nd + (col - nd - nu), j, dt);     // T21(a, j), a kinematic
     }
     // explicit part of d p2 / d (column) at dynamic row j: D1D2L2 for q1 columns, D2D2L2 for k2 columns

@@ -35,6 +35,8 @@ struct CoopSys {
     int ns, nqs;    // LinearSpring potentials / configs that any of them depends on (compact block of their Hessian)
     int npc;        // points [0, npc) belong to constraints, [npc, np) are spring / damper ends (evaluated at the midpoint)
     int nfd, nqf;   // LinearDamper forces / configs that move exactly one end of any of them (compact f_dq, f_ddq blocks)
+    int nns;        // NonlinearConfigSpring potentials (piecewise-quintic splines of one config)
+    int nw;         // Body / Hybrid / Spatial wrench forces
     int has_gravity;
     double grav[3];
     // Tables live in one relocatable blob (host memory, device memory or a shared-memory copy):
@@ -65,6 +67,13 @@ struct CoopSys {
     //                 tapemeasure.py:97-110): da_a, da_b (points), da_c, dp_off [nfd+1] / dp_cfg: the configs that
     //                 move exactly ONE end (the only ones the reference's path length depends on), xf_idx [nq] /
     //                 xf_cfg [nqf]: compact row = column of such a config in the f_dq / f_ddq blocks.
+    //   spline springs [nns]  NonlinearConfigSpring (potentials/nonlinear_config_spring.c:23-47, spline.c:7-62):
+    //                 nsp_i [nns][3] = config, offset into nsp_tab, number of x points; nsp_d [nns][2] = m, b;
+    //                 nsp_tab: per spring x [n] then coefficients [n-1][6] (highest power first).
+    //   wrenches [nw] forces/bodywrench.c, hybridwrench.c, spatialwrench.c: wr_i [nw][8] = kind, point, six input
+    //                 indices (-1: constant component); wr_d [nw][15] = six constants, rotation of the frame in the
+    //                 coordinates of its link (row-major 3x3); wr_dep [nw] config mask.  Their configs share the
+    //                 compact f_dq block of the dampers (xf_idx / xf_cfg).
     const char* base;
     int o_l_par;
     int o_l_cfg;
@@ -103,6 +112,14 @@ struct CoopSys {
     int o_con_n;
     int o_sp_a, o_sp_b, o_sp_k, o_sp_x0, o_sp_off, o_sp_cfg, o_xs_idx, o_xs_cfg;
     int o_da_a, o_da_b, o_da_c, o_dp_off, o_dp_cfg, o_xf_idx, o_xf_cfg;
+    int o_nsp_i, o_nsp_d, o_nsp_tab;
+    int o_wr_i, o_wr_d, o_wr_dep;
+    TREPB_HD const int32_t* wr_i() const { return (const int32_t*)(base + o_wr_i); }
+    TREPB_HD const double* wr_d() const { return (const double*)(base + o_wr_d); }
+    TREPB_HD const uint64_t* wr_dep() const { return (const uint64_t*)(base + o_wr_dep); }
+    TREPB_HD const int32_t* nsp_i() const { return (const int32_t*)(base + o_nsp_i); }
+    TREPB_HD const double* nsp_d() const { return (const double*)(base + o_nsp_d); }
+    TREPB_HD const double* nsp_tab() const { return (const double*)(base + o_nsp_tab); }
     TREPB_HD const int32_t* da_a() const { return (const int32_t*)(base + o_da_a); }
     TREPB_HD const int32_t* da_b() const { return (const int32_t*)(base + o_da_b); }
     TREPB_HD const double* da_c() const { return (const double*)(base + o_da_c); }
@@ -165,7 +182,7 @@ struct CoopPack {
     std::string why;          // why the cooperative path does not apply
     std::vector<char> blob;
     CoopSys proto;
-    size_t off[56];
+    size_t off[72];
 
     CoopSys view(const char* base) const {
         CoopSys s = proto;
@@ -210,6 +227,8 @@ struct CoopPack {
         s.o_sp_off = (int)off[k++]; s.o_sp_cfg = (int)off[k++]; s.o_xs_idx = (int)off[k++]; s.o_xs_cfg = (int)off[k++];
         s.o_da_a = (int)off[k++]; s.o_da_b = (int)off[k++]; s.o_da_c = (int)off[k++]; s.o_dp_off = (int)off[k++];
         s.o_dp_cfg = (int)off[k++]; s.o_xf_idx = (int)off[k++]; s.o_xf_cfg = (int)off[k++];
+        s.o_nsp_i = (int)off[k++]; s.o_nsp_d = (int)off[k++]; s.o_nsp_tab = (int)off[k++];
+        s.o_wr_i = (int)off[k++]; s.o_wr_d = (int)off[k++]; s.o_wr_dep = (int)off[k++];
         return s;
     }
 };
@@ -264,11 +283,8 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     CoopPack P;
     const int nf = d->n_frames, nd = d->nd, nk = d->nk, nq = nd + nk, nu = d->nu, nc = d->n_constraints;
     if (nq > 64) { P.why = "more than 64 configs"; return P; }
-    for (int i = 0; i < d->n_potentials; ++i)
-        if (d->pot_kind[i] == TREPB_POT_NONLINEAR_CONFIG_SPRING) { P.why = "NonlinearConfigSpring potential"; return P; }
     for (int i = 0; i < d->n_forces; ++i)
         if (d->force_kind[i] == TREPB_FORCE_LINEAR_DAMPER && d->force_i[4 * i + 1] != 2) { P.why = "LinearDamper over more than one segment"; return P; }
-        else if (d->force_kind[i] >= TREPB_FORCE_BODY_WRENCH) { P.why = "wrench force"; return P; }
 
     // ---- frames -> links
     std::vector<int> flink(nf, -1);      // frame -> frame index of the link it belongs to (-1: world)
@@ -455,7 +471,9 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     const int ns = (int)sp_a.size(), nqs = (int)xs_cfg.size();
     // ---- LinearDamper end points and the configs that move exactly one end
     std::vector<int32_t> da_a, da_b, dp_off(1, 0), dp_cfg, xf_idx(nq > 0 ? nq : 1, -1), xf_cfg;
-    std::vector<double> da_c;
+    std::vector<double> da_c, wr_d;
+    std::vector<int32_t> wr_i;
+    std::vector<uint64_t> wr_dep;
     {
         uint64_t any = 0;
         for (int i = 0; i < d->n_forces; ++i) {
@@ -471,9 +489,34 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
             dp_off.push_back((int32_t)dp_cfg.size());
             any |= m;
         }
+        for (int i = 0; i < d->n_forces; ++i) {
+            const int kind = d->force_kind[i];
+            if (kind < TREPB_FORCE_BODY_WRENCH) continue;
+            const int f = d->force_i[4 * i], io = d->force_i[4 * i + 1], dof = d->force_i[4 * i + 2];
+            const int pt = point_of(f, (size_t)npc, 64);
+            wr_i.push_back(kind); wr_i.push_back(pt);
+            for (int k = 0; k < 6; ++k) wr_i.push_back(d->ipool[io + k]);
+            for (int k = 0; k < 6; ++k) wr_d.push_back(d->dpool[dof + k]);
+            for (int k = 0; k < 9; ++k) wr_d.push_back(fx[f].R[k]);
+            uint64_t m = 0;
+            for (int x = pt_link[pt]; x >= 0; x = l_par[x]) m |= 1ull << l_cfg[x];
+            wr_dep.push_back(m);
+            any |= m;
+        }
         for (int j = 0; j < nq; ++j) if ((any >> j) & 1ull) { xf_idx[j] = (int32_t)xf_cfg.size(); xf_cfg.push_back(j); }
     }
-    const int nfd = (int)da_a.size(), nqf = (int)xf_cfg.size();
+    const int nfd = (int)da_a.size(), nqf = (int)xf_cfg.size(), nw = (int)wr_dep.size();
+    // ---- NonlinearConfigSpring tables
+    std::vector<int32_t> nsp_i;
+    std::vector<double> nsp_d, nsp_tab;
+    for (int i = 0; i < d->n_potentials; ++i) {
+        if (d->pot_kind[i] != TREPB_POT_NONLINEAR_CONFIG_SPRING) continue;
+        const int c = d->pot_i[4 * i], off = d->pot_i[4 * i + 1], n = d->pot_i[4 * i + 2];
+        nsp_i.push_back(c); nsp_i.push_back((int32_t)nsp_tab.size()); nsp_i.push_back(n);
+        nsp_d.push_back(d->pot_d[4 * i]); nsp_d.push_back(d->pot_d[4 * i + 1]);
+        for (int e = 0; e < n + 6 * (n - 1); ++e) nsp_tab.push_back(d->dpool[off + e]);
+    }
+    const int nns = (int)nsp_i.size() / 3;
     const int np = (int)pt_link.size();
     std::vector<int32_t> cd_off(nc + 1, 0), cd_cfg, cd_nd(nc > 0 ? nc : 1, 0);
     for (int c = 0; c < nc; ++c) {
@@ -536,7 +579,7 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     P.proto.np = np; P.proto.npairs = npairs; P.proto.nlevels = nlevels;
     P.proto.ndc = ndc; P.proto.nqc = nqc; P.proto.nsl = nsl;
     P.proto.ns = ns; P.proto.nqs = nqs; P.proto.npc = npc;
-    P.proto.nfd = nfd; P.proto.nqf = nqf;
+    P.proto.nfd = nfd; P.proto.nqf = nqf; P.proto.nns = nns; P.proto.nw = nw;
     P.proto.has_gravity = has_grav;
     for (int k = 0; k < 3; ++k) P.proto.grav[k] = grav[k];
     int k = 0;
@@ -566,6 +609,8 @@ inline CoopPack coop_pack(const trepb_sysdesc* d) {
     put(da_a.data(), 4 * (size_t)nfd); put(da_b.data(), 4 * (size_t)nfd); put(da_c.data(), 8 * (size_t)nfd);
     put(dp_off.data(), 4 * dp_off.size()); put(dp_cfg.data(), 4 * dp_cfg.size());
     put(xf_idx.data(), 4 * (size_t)nq); put(xf_cfg.data(), 4 * (size_t)nqf);
+    put(nsp_i.data(), 4 * nsp_i.size()); put(nsp_d.data(), 8 * nsp_d.size()); put(nsp_tab.data(), 8 * nsp_tab.size());
+    put(wr_i.data(), 4 * wr_i.size()); put(wr_d.data(), 8 * wr_d.size()); put(wr_dep.data(), 8 * wr_dep.size());
     P.blob.resize((P.blob.size() + 15) & ~size_t(15), 0);
     P.ok = true;
     return P;

@@ -184,7 +184,7 @@ def device_count():
 def coop_dims(desc):
     """Shape the compile-time-size cooperative kernels are instantiated for: (nd, nk, nu, nc, links, points,
     chain pairs, levels, constrained dynamic configs, constrained configs), or None when they do not apply
-    (wrenches / spline springs: no cooperative kernels; LinearSpring / LinearDamper: run-time sizes only)."""
+    (LinearSpring / LinearDamper / NonlinearConfigSpring / wrenches: the run-time-size cooperative flavour only)."""
     cd, keep = D.to_c(desc)
     out = (C.c_int32 * 10)()
     if _lib.trepb_coop_dims(C.byref(cd), out) != 0:
