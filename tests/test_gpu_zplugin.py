@@ -87,3 +87,34 @@ def test_cooperative_plugin_for_a_user_shape(lib):
     for k in G.RAW:
         G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
     assert np.array_equal(out["iters"], g["case_iters"])
+
+
+def test_cooperative_plugin_for_a_shape_with_springs(lib):
+    """CtDims<..., 1>: compile-time sizes for everything but the spring / damper / wrench counts."""
+    from trep_b200 import build
+    name = "spring_arms"
+    d = G.desc(name)
+    g = G.golden(name)
+    assert lib.System(d, cooperative=True).kernel_name == "cooperative"
+    path = os.path.join(os.path.dirname(build.LIB), "libtrepb_plugin_spring_arms_coop.so")
+    if shutil.which(build.NVCC) is not None:
+        path = build.build_plugin(d, "spring_arms_coop", kind="coop")
+    elif not os.path.exists(path):
+        pytest.skip("plug-in not prebuilt and no nvcc on this box")
+    assert lib.load_plugin(path) == 1
+    s = lib.System(d, cooperative=True)
+    assert s.cooperative and s.kernel_name == "cooperative/spring_arms_coop"
+    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
+                      q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+    assert np.all(out["status"] == 0)
+    for k in ("q2", "p2", "lambda1", "A", "B"):
+        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
+    for k in G.RAW:
+        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
+    assert np.array_equal(out["iters"], g["case_iters"])
+    # the in-kernel stepping of the same flavour (solve-only layout with the run-time tail)
+    dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
+    p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])
+    st = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, u1=g["roll_u"][None], k2=g["roll_k2"][None], sample_every=1)
+    assert st["status"][0] == 0
+    G.assert_close(st["traj_q"][0], g["roll_q"][1:], "coop plugin traj q", rtol=1e-7)

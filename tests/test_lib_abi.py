@@ -71,16 +71,16 @@ def test_specialised_registry_and_codegen():
 def test_cooperative_shapes_and_generated_instantiation():
     """trepb_coop_dims: the link-level shape of a system; the build instantiates the
     compile-time-size cooperative kernels for exactly that shape."""
-    assert lib.coop_dims(G.desc("puppet")) == (22, 18, 0, 6, 34, 12, 157, 10, 20, 38)
-    assert lib.coop_dims(G.desc("pendulum5")) == (5, 0, 0, 0, 5, 0, 15, 5, 0, 0)
-    assert lib.coop_dims(G.desc("dual_pendulums")) is None      # LinearSpring / LinearDamper: run-time-size flavour only
-    assert lib.coop_dims(G.desc("wrench_arm")) is None          # wrenches: run-time-size flavour only
+    assert lib.coop_dims(G.desc("puppet")) == (22, 18, 0, 6, 34, 12, 157, 10, 20, 38, 0)
+    assert lib.coop_dims(G.desc("pendulum5")) == (5, 0, 0, 0, 5, 0, 15, 5, 0, 0, 0)
+    # LinearSpring / LinearDamper / wrenches: the eleventh entry asks for the run-time tail of the layout
+    assert lib.coop_dims(G.desc("dual_pendulums"))[10] == 1 and lib.coop_dims(G.desc("wrench_arm"))[10] == 1
     for name in build.COOP_AOT_SYSTEMS:
         text = open(os.path.join(build.GEN, "coop_%s.cu" % name)).read()
         dims = ", ".join(str(v) for v in lib.coop_dims(G.desc(name)))
         assert "CtDims<%s>" % dims in text
     # tests/host_math_check.cc runs the same instantiation on the CPU
-    assert "CtDims<%s>" % ", ".join(str(v) for v in lib.coop_dims(G.desc("puppet"))) in \
+    assert "CtDims<%s>" % ", ".join(str(v) for v in lib.coop_dims(G.desc("puppet"))[:10]) in \
         open(os.path.join(ROOT, "tests", "host_math_check.cc")).read()
 
 
@@ -144,4 +144,9 @@ def test_plugin_adds_a_specialised_kernel_for_a_user_system():
         lib.load_plugin(path)            # already loaded: registers nothing
     # kind="coop": compile-time-size cooperative kernels for a shape the library was not built with
     path = build.build_plugin(systems.named_desc("rod"), "rod_coop", kind="coop")
+    assert lib.load_plugin(path) == 1
+    # ... also for a shape with LinearSprings (their counts stay run-time data: CtDims<..., 1>)
+    path = build.build_plugin(systems.named_desc("spring_arms"), "spring_arms_coop", kind="coop")
+    assert "38, 1>" not in open(os.path.join(build.GEN, "plugin_rod_coop.cu")).read()
+    assert ", 1>;" in open(os.path.join(build.GEN, "plugin_spring_arms_coop.cu")).read()
     assert lib.load_plugin(path) == 1

@@ -56,12 +56,10 @@ int trepb_coop_dims(const trepb_sysdesc* desc, int32_t* out) {
     CoopPack C = coop_pack(desc);
     if (!C.ok) { last_error() = "cooperative kernels do not apply: " + C.why; return TREPB_ERR_UNSUPPORTED; }
     const CoopSys& s = C.proto;
-    if (s.ns > 0 || s.nfd > 0 || s.nns > 0 || s.nw > 0) {   // such systems run on the run-time-size cooperative flavour only (CtDims::matches)
-        last_error() = "compile-time-size cooperative kernels do not apply: LinearSpring / LinearDamper / NonlinearConfigSpring / wrenches";
-        return TREPB_ERR_UNSUPPORTED;
-    }
-    const int32_t v[10] = {s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, s.nlevels, s.ndc, s.nqc};
-    for (int i = 0; i < 10; ++i) out[i] = v[i];
+    // the eleventh entry: 1 when the system has LinearSprings / LinearDampers / spline springs / wrenches (CtDims<..., 1>)
+    const int32_t v[11] = {s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, s.nlevels, s.ndc, s.nqc,
+                           (s.ns + s.nfd + s.nns + s.nw) > 0 ? 1 : 0};
+    for (int i = 0; i < 11; ++i) out[i] = v[i];
     return TREPB_OK;
 }
 

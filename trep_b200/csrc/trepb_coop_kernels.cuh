@@ -53,6 +53,15 @@ __device__ __forceinline__ Team make_team() {
     }
 }
 
+// layout of a compile-time-size flavour: constants from the template dimensions, plus - for CtDims<..., 1> - the
+// run-time tail of the plugin kinds only some systems have (the same function the host sized the workspace with)
+template <class D>
+__device__ __forceinline__ CoopLayout static_layout(const CoopSys& gs, bool solve_only) {
+    CoopLayout lay = D::layout(solve_only);
+    if constexpr (D::kExtras) lay.append_extras(D::ND, D::ND + D::NK, D::NU, gs.nqs, gs.nqf, gs.nns, gs.nw);
+    return lay;
+}
+
 template <class Team>
 __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, const CoopLayout& lay) {
     extern __shared__ double smem_[];
@@ -71,7 +80,7 @@ template <class D, class Team>
 __global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout(true);
+    if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -143,7 +152,7 @@ template <class D, class Team>
 __global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout(true);
+    if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -219,7 +228,7 @@ template <class D, class Team>
 __global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
 coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout(true);
+    if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;
@@ -257,7 +266,7 @@ template <class D, class Team>
 __global__ void __launch_bounds__(8 * Team::kSize, 1)
 coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
     CoopLayout lay = lay_;
-    if constexpr (D::kStatic) lay = D::layout(false);
+    if constexpr (D::kStatic) lay = static_layout<D>(gs, false);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
     const CoopSys& S = st.S;
     double* w = st.w;

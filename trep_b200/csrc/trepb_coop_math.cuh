@@ -91,7 +91,7 @@ struct PairTeam {
 // sizes: run-time or compile-time
 // ---------------------------------------------------------------------------------------------
 struct RtDims {
-    static constexpr bool kStatic = false;
+    static constexpr bool kStatic = false, kExtras = true;
     static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1, NDC = 0, NQC = 0;
 };
 
@@ -106,6 +106,7 @@ struct CoopLayout {
     int FD, FX, FQ, FV;              // LinearDampers: force [nd], dx scratch [nq], f_dq / f_ddq blocks [nqf][nqf]
     int KS;                          // config stiffness at the evaluation point [nq]: ConfigSpring k + spline springs' -d2V/dq2
     int FUW;                         // wrenches: d f / d u at the evaluation point [nd][nu] (on top of the constant ConfigForce part)
+    int SC;                          // scratch of the spring / damper Hessians: dA, dB, dx of one potential or force [7 nq]
     int Dh1, Dh2, hc;
     int N;                           // Newton augmented matrix [nr][ldf]; aliases the link region
     int Y;                           // DDh.lambda block / right-hand sides [nd][ldy] (first-derivative kernels only)
@@ -141,7 +142,7 @@ struct CoopLayout {
         L.p1 = o; o += nd; L.p2 = o; o += nd; L.u1 = o; o += nu; L.lam = o; o += nc; L.vk = o; o += nk;
         const int link0 = o;
         L.R = o; o += 9 * nl; L.p = o; o += 3 * nl; L.V = o; o += 6 * nl;
-        L.comp = o; o += ((nqs > 0 || nqf > 0) && 7 * nq > 16 * nl) ? 7 * nq : 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
+        L.comp = o; o += 16 * nl; L.cs = L.comp + 14 * nl; L.pts = o; o += 3 * np;
         const int nN = nr * L.ldf;
         const int need = nd * L.ldm + nd * nd > nN ? nd * L.ldm + nd * nd : nN;
         if (o - link0 < need) o = link0 + need;
@@ -152,10 +153,6 @@ struct CoopLayout {
         L.fr = L.Lq; L.scl = L.Lv;
         L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
-        L.XS = o; o += nqs * nqs;
-        L.KS = o; o += nns > 0 ? nq : 0;
-        L.FUW = o; o += nw > 0 ? nd * nu : 0;
-        L.FD = o; o += nqf > 0 ? nd : 0; L.FX = o; o += nqf > 0 ? nq : 0; L.FQ = o; o += nqf * nqf; L.FV = o; o += nqf * nqf;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
         L.Y = o; o += solve_only ? 0 : nY;
         L.Z = o; o += (stat || solve_only) ? 0 : nc * L.ldy;
@@ -163,16 +160,32 @@ struct CoopLayout {
         L.rdM = o; o += nr; L.rdP = o; o += solve_only ? 0 : nc;
         L.ints = o; o += (2 * nr + 2 * nc + 2) / 2 + 1;   // + the first-warp flag
         L.total = (o + 1) & ~1;
+        L.append_extras(nd, nq, nu, nqs, nqf, nns, nw);
         return L;
+    }
+    // The blocks of the plugin kinds that only some systems have (LinearSpring, LinearDamper, NonlinearConfigSpring,
+    // wrenches) sit behind everything else, so that the offsets of a compile-time-size flavour stay constants and
+    // only this tail is laid out from run-time counts (CtDims<..., 1>).
+    TREPB_HD constexpr void append_extras(int nd, int nq, int nu, int nqs, int nqf, int nns, int nw) {
+        int o = total;
+        XS = o; o += nqs * nqs;
+        KS = o; o += nns > 0 ? nq : 0;
+        FUW = o; o += nw > 0 ? nd * nu : 0;
+        FD = o; o += nqf > 0 ? nd : 0; FX = o; o += nqf > 0 ? nq : 0; FQ = o; o += nqf * nqf; FV = o; o += nqf * nqf;
+        SC = o; o += (nqs > 0 || nqf > 0) ? 7 * nq : 0;
+        total = (o + 1) & ~1;
     }
     TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
         *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf, s.nns, s.nw);
     }
 };
 
-template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_, int NDC_, int NQC_>
+// EX_ = 1: the shape of a system that also has LinearSprings / LinearDampers / spline springs / wrenches: their
+// counts stay run-time data (tail of the layout), everything else is compile-time as usual
+template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int NLEVELS_, int NDC_, int NQC_, int EX_ = 0>
 struct CtDims {
     static constexpr bool kStatic = true;
+    static constexpr bool kExtras = EX_ != 0;
     static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_,
                          NDC = NDC_, NQC = NQC_;
     TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
@@ -180,7 +193,7 @@ struct CtDims {
     }
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
-               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && s.ns == 0 && s.nfd == 0 && s.nns == 0 && s.nw == 0;   // springs / dampers / wrenches: run-time-size flavour only
+               s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && (kExtras || (s.ns == 0 && s.nfd == 0 && s.nns == 0 && s.nw == 0));
     }
 };
 
@@ -475,11 +488,11 @@ struct Coop {
     TREPB_DIM(NL, NL, nl) TREPB_DIM(NP, NP, np) TREPB_DIM(NPAIRS, NPAIRS, npairs) TREPB_DIM(NLEVELS, NLEVELS, nlevels)
 #undef TREPB_DIM
     TREPB_HD int NQ() const { return ND() + NK(); }
-    // LinearSprings: run-time-size flavour only (CtDims::matches), so the compile-time flavours drop the code
-    TREPB_HD int NS() const { if constexpr (D::kStatic) return 0; else return S.ns; }
-    TREPB_HD int NFD() const { if constexpr (D::kStatic) return 0; else return S.nfd; }
-    TREPB_HD int NNS() const { if constexpr (D::kStatic) return 0; else return S.nns; }
-    TREPB_HD int NW() const { if constexpr (D::kStatic) return 0; else return S.nw; }
+    // the plugin kinds only some systems have: flavours instantiated without them (CtDims<..., 0>) drop the code
+    TREPB_HD int NS() const { if constexpr (!D::kExtras) return 0; else return S.ns; }
+    TREPB_HD int NFD() const { if constexpr (!D::kExtras) return 0; else return S.nfd; }
+    TREPB_HD int NNS() const { if constexpr (!D::kExtras) return 0; else return S.nns; }
+    TREPB_HD int NW() const { if constexpr (!D::kExtras) return 0; else return S.nw; }
     TREPB_HD int NPF() const { return NFD() + NW(); }     // forces acting through world points: dampers, wrenches
     TREPB_HD double fu_eff(int j, int u) const {
         const double c = S.Fu()[j * NU() + u];
@@ -860,7 +873,7 @@ struct Coop {
         if (NPF() == 0) return;
         const int lane = t.lane(), nqf = S.nqf, nls = L.nls, nd = ND();
         for (int e = lane; e < nqf * nqf; e += Team::kSize) { w[L.FQ + e] = 0.0; w[L.FV + e] = 0.0; }
-        double* DA = w + L.comp;
+        double* DA = w + L.SC;
         for (int f = 0; f < NFD(); ++f) {
             const int off = S.dp_off()[f], m = S.dp_off()[f + 1] - off;
             const int* list = S.dp_cfg() + off;
@@ -1051,7 +1064,7 @@ struct Coop {
         if (NS() == 0) return;
         const int lane = t.lane(), nqs = S.nqs, nls = L.nls;
         for (int e = lane; e < nqs * nqs; e += Team::kSize) w[L.XS + e] = 0.0;
-        double* DA = w + L.comp;
+        double* DA = w + L.SC;
         for (int sp = 0; sp < NS(); ++sp) {
             const int off = S.sp_off()[sp], m = S.sp_off()[sp + 1] - off;
             const int* list = S.sp_cfg() + off;

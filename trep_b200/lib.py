@@ -183,10 +183,11 @@ def device_count():
 
 def coop_dims(desc):
     """Shape the compile-time-size cooperative kernels are instantiated for: (nd, nk, nu, nc, links, points,
-    chain pairs, levels, constrained dynamic configs, constrained configs), or None when they do not apply
-    (LinearSpring / LinearDamper / NonlinearConfigSpring / wrenches: the run-time-size cooperative flavour only)."""
+    chain pairs, levels, constrained dynamic configs, constrained configs, extras), or None when the cooperative
+    kernels do not apply; extras = 1 for a system with LinearSprings / LinearDampers / spline springs / wrenches
+    (their counts stay run-time data of the instantiation)."""
     cd, keep = D.to_c(desc)
-    out = (C.c_int32 * 10)()
+    out = (C.c_int32 * 11)()
     if _lib.trepb_coop_dims(C.byref(cd), out) != 0:
         return None
     return tuple(out)
