@@ -172,6 +172,63 @@ def test_parity_random_vs_reference(lib, ref, name):
         assert int(np.sum(out["iters"][ok] != want["iters"][ok])) <= 1, label
 
 
+@pytest.mark.parametrize("name", ["fourbar", "loop3d", "spring_arms", "dual_pendulums"])
+def test_wide_cooperative_instantiations(lib, ref, name):
+    """Shapes with small workspaces run more teams per CTA on a second instantiation of every cooperative kernel
+    (16 / 24 warps at 128 / 80 registers, trepb_coop_kernels.cuh Launch::kWide); a batch only reaches it when it
+    fills the SMs.  A filling batch against the reference on a sample and against the base instantiation
+    (TREPB_COOP_WARPS caps the teams) on every instance: linearize and a 5-step rollout."""
+    rng = np.random.default_rng(5)
+    system, mvi = ref.make_mvi(name)
+    nq, nd, nu, nk = mvi.nq, mvi.nd, mvi.nu, mvi.nk
+    g = G.golden(name)
+    B = 148 * 24 * 2 + 37
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+    q1 = g["roll_q"][idx].copy(); p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, nd))
+    q1[:, :nd] += rng.normal(0, 0.01, (B, nd))
+    u1 = (g["roll_u"][idx] if "roll_u" in g else np.zeros((B, nu))) + rng.normal(0, 0.1, (B, nu))
+    k2 = (g["roll_k2"][idx] if "roll_k2" in g else np.zeros((B, nk))) + rng.normal(0, 1e-3, (B, nk))
+    lam = g["roll_lambda"][idx - 1] if g["roll_lambda"].shape[-1] else None
+    t1 = rng.uniform(0, 5, B); t2 = t1 + 0.01
+    n_ref = 160
+    want = ref.run_cases(mvi, t1[:n_ref], t2[:n_ref], q1[:n_ref], p1[:n_ref], u1[:n_ref], k2[:n_ref],
+                         lambda_guess=None if lam is None else lam[:n_ref])
+    kinds = [dict(specialize=False, cooperative=True)]
+    if name in COOP_STATIC:
+        kinds.append(dict(cooperative=True, coop_one_warp=True))
+    for kw in kinds:
+        wide = lib.System(G.desc(name), **kw)
+        os.environ["TREPB_COOP_WARPS"] = "8"
+        try:
+            base = lib.System(G.desc(name), **kw)
+        finally:
+            del os.environ["TREPB_COOP_WARPS"]
+        label = wide.kernel_name
+        assert wide.cooperative and base.kernel_name == label
+        assert wide.kernel_info(2)["block"] > 8 * 32 and wide.kernel_info(0)["block"] > 12 * 32, wide.kernel_info(2)
+        assert wide.kernel_info(2)["regs"] <= 128
+        assert base.kernel_info(2)["block"] == 8 * 32
+        a = wide.linearize(q1, p1, u1, k2, t1=t1, t2=t2, lambda_guess=lam)
+        b = base.linearize(q1, p1, u1, k2, t1=t1, t2=t2, lambda_guess=lam)
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"]), label
+        assert np.array_equal(a["status"][:n_ref], want["status"]), label
+        ok = a["status"] == 0
+        assert ok.mean() > 0.95
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(a[k][ok], b[k][ok], "%s[%s] wide vs base %s" % (name, label, k), rtol=1e-12)
+            okr = want["status"] == 0
+            G.assert_close(a[k][:n_ref][okr], want[k][okr], "%s[%s] %s" % (name, label, k))
+        ns = 5
+        uu = np.repeat(u1[:, None, :], ns, axis=1); kk = np.repeat(k2[:, None, :], ns, axis=1)
+        a = wide.step(q1, p1, 0.0, 0.01, nsteps=ns, u1=uu, k2=kk, lambda_guess=lam)
+        b = base.step(q1, p1, 0.0, 0.01, nsteps=ns, u1=uu, k2=kk, lambda_guess=lam)
+        assert np.array_equal(a["status"], b["status"]) and np.array_equal(a["iters"], b["iters"]), label
+        ok = a["status"] == 0
+        for k in ("q2", "p2", "lambda1"):
+            G.assert_close(a[k][ok], b[k][ok], "%s[%s] wide vs base rollout %s" % (name, label, k), rtol=1e-12)
+        wide.close(); base.close()
+
+
 # ---- parity at scale --------------------------------------------------------------------------------------
 SCALE = {
     #  name            rollouts  steps   (>= 1e7 DEL steps each)

@@ -9,7 +9,8 @@ up = lambda a: lib.DeviceBuffer(0, a.shape, a.dtype).upload(np.ascontiguousarray
 rng = np.random.default_rng(0)
 for name, B in (("pendulum5", 1 << 18), ("pccd", 1 << 16), ("pend_on_cart2", 1 << 20)):
     d = systems.named_desc(name)
-    for label, kw in (("general", dict(specialize=False, cooperative=False)), ("coop", dict(specialize=False, cooperative=True))):
+    for label, kw in (("general", dict(specialize=False, cooperative=False)), ("coop", dict(specialize=False, cooperative=True)),
+                      ("coop-ct", dict(specialize=True, cooperative=True))):
         try:
             s = lib.System(d, **kw)
         except lib.TrepbError as e:
@@ -31,7 +32,7 @@ for name, B in (("pendulum5", 1 << 18), ("pccd", 1 << 16), ("pend_on_cart2", 1 <
             s.linearize_raw(True, B, dq, dp, du, None, st, t1_scalar=0.0, dt_scalar=0.01, A=A, B=Bm, lambda_guess=lam)
             lib.synchronize(0)
             ms = s.last_kernel_ms()
-        print("%-14s %-8s kernel=%-12s B=%d  %.3f ms -> %.3e lin/s  ok=%.4f" % (name, label, s.kernel_name, B, ms, B / ms * 1e3, (st.download() == 0).mean()))
+        print("%-14s %-8s kernel=%-18s B=%d  %.3f ms -> %.3e lin/s  ok=%.4f  %s" % (name, label, s.kernel_name, B, ms, B / ms * 1e3, (st.download() == 0).mean(), s.kernel_info(2)))
         for b in (dq, dp, du, st, A, Bm, lam):
             if b is not None: b.free()
         s.close()

@@ -225,9 +225,11 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
             const size_t ws_b = (size_t)s->clay.total * 8;
             const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
             int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
-            if (warps > 8) warps = 8;
+            const int lin_cap = cks->max_teams > coopk::kLinTeams ? cks->max_teams : coopk::kLinTeams;
+            const int solve_cap = cks->max_teams > coopk::kSolveTeams ? cks->max_teams : coopk::kSolveTeams;
+            if (warps > lin_cap) warps = lin_cap;
             int warps_solve = cap > blob_d ? (int)((cap - blob_d) / ((size_t)s->clay_solve.total * 8)) : 0;
-            if (warps_solve > coopk::kSolveTeams) warps_solve = coopk::kSolveTeams;
+            if (warps_solve > solve_cap) warps_solve = solve_cap;
             if (const char* e = getenv("TREPB_COOP_WARPS")) {   // diagnostic: fewer instances in flight per SM
                 const int w = atoi(e);
                 if (w >= 1 && w < warps) warps = w;
@@ -339,12 +341,13 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
     KernelInfo ki;
     int b = 0;
     if (s->coop) {
-        CU(s->cks->info(which, &ki));
+        const bool lin = which == 2;
+        const int teams = lin ? s->coop_warps : s->coop_warps_solve;
+        const bool wide = teams > (lin ? coopk::kLinTeams : coopk::kSolveTeams);   // the instantiation a full batch runs
+        CU(s->cks->info(which + (wide ? 4 : 0), &ki));
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
         if (blocks_per_sm) *blocks_per_sm = 1;
-        const bool lin = which == 2;
-        const int teams = lin ? s->coop_warps : s->coop_warps_solve;
         if (block) *block = 32 * (lin ? s->cks->team_warps : 1) * teams;
         if (smem_bytes) *smem_bytes = (int32_t)((size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8 + (size_t)teams * (lin ? s->clay : s->clay_solve).total * 8);
         return TREPB_OK;

@@ -10,6 +10,15 @@ namespace coopk {
 // most instances (one warp each) a CTA of the solve-only kernels (step, project, p2 / f) holds: their workspace
 // is smaller than the linearize kernel's (CoopLayout::make, solve_only), 12 x 18.0 KB for the marionette
 constexpr int kSolveTeams = 12;
+// most instances a CTA of the linearize kernel holds (255 registers per thread with one warp per instance)
+constexpr int kLinTeams = 8;
+// teams per CTA of the wide instantiations (shapes with small workspaces): 16 warps at 128 registers for the
+// compile-time-size flavours, kWideTeamsRt warps for the run-time-size one
+constexpr int kWideTeamsCt = 16;
+#ifndef TREPB_WIDE_RT
+#define TREPB_WIDE_RT 24
+#endif
+constexpr int kWideTeamsRt = TREPB_WIDE_RT;
 }  // namespace coopk
 
 struct CoopLaunch {
@@ -27,6 +36,7 @@ struct CoopKernelSet {
     const char* name;
     int specialized;
     int team_warps;         // warps that work on one instance (1: WarpTeam, 2: PairTeam)
+    int max_teams;          // teams per CTA of the wide instantiations (0: none; then kLinTeams / kSolveTeams bound)
     bool (*matches)(const CoopSys&);
     cudaError_t (*step)(const CoopLaunch&, const StepParams&);
     cudaError_t (*p2)(const CoopLaunch&, const P2Params&);

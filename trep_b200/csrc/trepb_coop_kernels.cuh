@@ -76,8 +76,8 @@ __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, c
     return st;
 }
 
-template <class D, class Team>
-__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
+template <class D, class Team, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
 coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
@@ -148,8 +148,8 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
 // DSystem.project / armijo_simulate (trep/discopt/dsystem.py:426-457): closed-loop rollouts, one warp per
 // candidate, the affine feedback U[k] = bU[k] - K[k](X[k] - bX[k]) evaluated by the lanes (one input
 // component each) inside the time loop.
-template <class D, class Team>
-__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
+template <class D, class Team, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
 coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
@@ -224,8 +224,8 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
     }
 }
 
-template <class D, class Team>
-__global__ void __launch_bounds__(kSolveTeams * Team::kSize, 1)
+template <class D, class Team, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
 coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
@@ -262,8 +262,8 @@ coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, co
     }
 }
 
-template <class D, class Team>
-__global__ void __launch_bounds__(8 * Team::kSize, 1)
+template <class D, class Team, int TEAMS>
+__global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
 coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, false);
@@ -338,36 +338,83 @@ cudaError_t prep(K kernel, size_t smem) {
     return cudaSuccess;
 }
 
+// Two instantiations per kernel: the base one (kSolveTeams / kLinTeams teams per CTA, up to 168 / 255 registers
+// per thread) and, for shapes whose workspace is small enough that more teams fit in shared memory, a wide one
+// (kWideTeamsCt / kWideTeamsRt teams, 128 / 64 registers): these kernels are latency-bound, their throughput grows almost linearly
+// with the instances in flight per SM (marionette linearize: 1.41 / 2.73 / 3.82 / 4.92e6 /s at 2 / 4 / 6 / 8).
+template <class D>
+constexpr bool wide_fits() {
+    if constexpr (D::kStatic) return (size_t)D::layout(true).total * 8 * (kSolveTeams + 1) <= 200 * 1024;
+    else return true;
+}
 template <class D, class Team>
 struct Launch {
+    static constexpr bool kWide = Team::kWarps == 1 && wide_fits<D>();
+    static constexpr int kWideTeams = D::kStatic ? kWideTeamsCt : kWideTeamsRt;
     static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
-        cudaError_t e = prep(coop_step_kernel<D, WarpTeam>, c.smem);
+        if constexpr (kWide) if (c.warps > kSolveTeams) {
+            cudaError_t e = prep(coop_step_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            if (e != cudaSuccess) return e;
+            coop_step_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            return cudaGetLastError();
+        }
+        cudaError_t e = prep(coop_step_kernel<D, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_step_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_step_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
-        cudaError_t e = prep(coop_p2_kernel<D, WarpTeam>, c.smem);
+        if constexpr (kWide) if (c.warps > kSolveTeams) {
+            cudaError_t e = prep(coop_p2_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            if (e != cudaSuccess) return e;
+            coop_p2_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            return cudaGetLastError();
+        }
+        cudaError_t e = prep(coop_p2_kernel<D, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_p2_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_p2_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
-        cudaError_t e = prep(coop_lin_kernel<D, Team>, c.smem);
+        if constexpr (kWide) if (c.warps > kLinTeams) {
+            cudaError_t e = prep(coop_lin_kernel<D, Team, kWideTeams>, c.smem);
+            if (e != cudaSuccess) return e;
+            coop_lin_kernel<D, Team, kWideTeams><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+            return cudaGetLastError();
+        }
+        cudaError_t e = prep(coop_lin_kernel<D, Team, kLinTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_lin_kernel<D, Team><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+        coop_lin_kernel<D, Team, kLinTeams><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
         return cudaGetLastError();
     }
     static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
-        cudaError_t e = prep(coop_project_kernel<D, WarpTeam>, c.smem);
+        if constexpr (kWide) if (c.warps > kSolveTeams) {
+            cudaError_t e = prep(coop_project_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            if (e != cudaSuccess) return e;
+            coop_project_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            return cudaGetLastError();
+        }
+        cudaError_t e = prep(coop_project_kernel<D, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_project_kernel<D, WarpTeam><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_project_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
+    // which: 0 step, 1 p2, 2 lin, 3 project; + 4 for the wide instantiation
     static cudaError_t info(int which, KernelInfo* ki) {
-        const void* fn = which == 0 ? (const void*)coop_step_kernel<D, WarpTeam>
-                       : which == 1 ? (const void*)coop_p2_kernel<D, WarpTeam>
-                       : which == 2 ? (const void*)coop_lin_kernel<D, Team> : (const void*)coop_project_kernel<D, WarpTeam>;
+        const void* fn = nullptr;
+        if (which >= 4) {
+            if constexpr (kWide) {
+                fn = which == 4 ? (const void*)coop_step_kernel<D, WarpTeam, kWideTeams>
+                   : which == 5 ? (const void*)coop_p2_kernel<D, WarpTeam, kWideTeams>
+                   : which == 6 ? (const void*)coop_lin_kernel<D, Team, kWideTeams> : (const void*)coop_project_kernel<D, WarpTeam, kWideTeams>;
+            } else {
+                return cudaErrorInvalidValue;
+            }
+        } else {
+            fn = which == 0 ? (const void*)coop_step_kernel<D, WarpTeam, kSolveTeams>
+               : which == 1 ? (const void*)coop_p2_kernel<D, WarpTeam, kSolveTeams>
+               : which == 2 ? (const void*)coop_lin_kernel<D, Team, kLinTeams> : (const void*)coop_project_kernel<D, WarpTeam, kSolveTeams>;
+        }
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
         if (e != cudaSuccess) return e;
@@ -391,6 +438,7 @@ CoopKernelSet make_coop_kernelset(const char* name) {
     k.name = name;
     k.specialized = D::kStatic ? 1 : 0;
     k.team_warps = Team::kWarps;
+    k.max_teams = coopk::Launch<D, Team>::kWide ? coopk::Launch<D, Team>::kWideTeams : 0;
     k.matches = &coopk::Launch<D, Team>::matches;
     k.step = &coopk::Launch<D, Team>::step;
     k.p2 = &coopk::Launch<D, Team>::p2;
