@@ -269,9 +269,11 @@ int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double to
                    const double* q2_guess, const double* lam_guess, double* q2, double* p2,
                    double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
     CoopLayout L;
-    L.set(S, D::kStatic);
+    L.set(S, D::kStatic, false, D::kExt);
     std::vector<double> slab(L.total + 8, 0.0);
-    Coop<HostTeam, D> c(S, L, slab.data(), HostTeam());
+    // poisoned external slab: every entry read must have been written for this instance
+    std::vector<double> xslab(L.xtotal + 8, 1e300);
+    Coop<HostTeam, D> c(S, L, slab.data(), HostTeam(), xslab.data());
     double* w = slab.data();
     const int nd = S.nd, nk = S.nk, nq = S.nq, nu = S.nu, nc = S.nc;
     for (int i = 0; i < nq; ++i) { w[L.q1 + i] = q1[i]; w[L.q2 + i] = q1[i]; }
@@ -322,6 +324,9 @@ int th_coop_linearize(const trepb_sysdesc* d, int static_dims, int nsteps, doubl
     CoopSys S = P.view(P.blob.data());
     if (static_dims) {
         if (!PuppetDims::matches(S)) return -201;
+        if (static_dims == 2)   // external-slab layout of the first-derivative workspace
+            return coop_linearize<ExtDims<PuppetDims>>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess,
+                                                       q2, p2, lam, iters, A, B, raw, aux);
         return coop_linearize<PuppetDims>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess, q2, p2,
                                           lam, iters, A, B, raw, aux);
     }

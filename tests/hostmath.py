@@ -157,7 +157,7 @@ def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, 
     ptrs = (C.POINTER(C.c_double) * 12)(*[_dp(raw[n]) for n in RAW])
     aux = np.zeros(4 * (desc.nd + desc.nc + 2) ** 2)
     lib.th_coop_linearize.restype = C.c_int
-    rc = lib.th_coop_linearize(C.byref(cd), C.c_int(1 if static_dims else 0), C.c_int(nsteps), C.c_double(t1), C.c_double(t2 - t1), C.c_double(tol),
+    rc = lib.th_coop_linearize(C.byref(cd), C.c_int(int(static_dims)), C.c_int(nsteps), C.c_double(t1), C.c_double(t2 - t1), C.c_double(tol),
                                C.c_int(maxit), _dp(q1), _dp(p1), _dp(u1), _dp(k2), _dp(q2g), _dp(lg), _dp(q2),
                                _dp(p2), _dp(lam), C.byref(it), _dp(A), _dp(B), ptrs if derivs else None, _dp(aux))
     out = {n: raw[n][:int(np.prod(shapes[n]))].reshape(shapes[n]) for n in RAW}

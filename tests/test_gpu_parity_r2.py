@@ -58,7 +58,10 @@ def flavours(lib, name):
         out.append(("coop", c))
         if name in COOP_STATIC:
             c = lib.System(d, cooperative=True)
-            if c.kernel_name.endswith("/pair"):     # two warps per instance: the default where it was built
+            if c.kernel_name.endswith("/ext"):      # external-slab layout: the default where it was built
+                assert c.kernel_name == "cooperative/" + name + "/ext"
+                out.append(("coop-static-ext", c))
+                c = lib.System(d, cooperative=True, coop_two_warps=True)
                 assert c.kernel_name == "cooperative/" + name + "/pair"
                 out.append(("coop-static-pair", c))
                 c = lib.System(d, cooperative=True, coop_one_warp=True)

@@ -111,6 +111,7 @@ struct trepb_system {
     bool d2jac_ok = false;       // pass B's per-CTA working set fits in shared memory for this shape
     bool d2_use_jac = false;     // second derivatives by the per-parameter scheme (trepb_d2jac.cuh)
     DevBuf ws_du, d2g;
+    DevBuf coop_ext;             // external slabs of the cooperative linearize kernel (ext flavours)
     // staging for the host-pointer entry points
     DevBuf hb[72];
     cudaStream_t hs[2] = {nullptr, nullptr};   // the two streams the chunked host-pointer calls alternate between
@@ -217,15 +218,15 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
         s->CP = coop_pack(desc);
         if (s->CP.ok) {
             CoopSys hv = s->CP.view(s->CP.blob.data());
-            const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE), (flags & TREPB_FLAG_COOP_ONE_WARP) ? 1 : 0);
-            s->clay.set(hv, cks->specialized != 0);
+            const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE), (flags & TREPB_FLAG_COOP_ONE_WARP) ? 1 : ((flags & TREPB_FLAG_COOP_TWO_WARPS) ? 2 : 0));
+            s->clay.set(hv, cks->specialized != 0, false, cks->ext != 0);
             s->clay_solve.set(hv, cks->specialized != 0, true);
             s->coop_blob_bytes = (int)s->CP.blob.size();
             const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
             const size_t ws_b = (size_t)s->clay.total * 8;
             const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
             int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
-            const int lin_cap = cks->max_teams > coopk::kLinTeams ? cks->max_teams : coopk::kLinTeams;
+            const int lin_cap = cks->max_teams > cks->lin_teams ? cks->max_teams : cks->lin_teams;
             const int solve_cap = cks->max_teams > coopk::kSolveTeams ? cks->max_teams : coopk::kSolveTeams;
             if (warps > lin_cap) warps = lin_cap;
             int warps_solve = cap > blob_d ? (int)((cap - blob_d) / ((size_t)s->clay_solve.total * 8)) : 0;
@@ -309,6 +310,7 @@ void trepb_system_destroy(trepb_system* s) {
     s->ws.release();
     s->ws_hd.release();
     s->ws_du.release();
+    s->coop_ext.release();
     s->d2g.release();
     for (auto& b : s->d2s) b.release();
     for (auto& b : s->hb) b.release();
@@ -343,7 +345,7 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
     if (s->coop) {
         const bool lin = which == 2;
         const int teams = lin ? s->coop_warps : s->coop_warps_solve;
-        const bool wide = teams > (lin ? coopk::kLinTeams : coopk::kSolveTeams);   // the instantiation a full batch runs
+        const bool wide = teams > (lin ? s->cks->lin_teams : coopk::kSolveTeams);   // the instantiation a full batch runs
         CU(s->cks->info(which + (wide ? 4 : 0), &ki));
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
@@ -428,6 +430,7 @@ void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch
     c->sys = s->cview;
     c->blob_bytes = s->coop_blob_bytes;
     c->lay = lay;
+    c->ext = nullptr;
 }
 
 // Orders launches that use the handle's scratch across streams: wait for the previous user before the
@@ -617,6 +620,12 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
         make_coop(s, a->batch, stream, &cl, false);
         AuxLayout al;
         al.set(ps.nd, ps.nc);
+        // ext flavours: one slab per team of the persistent grid (handle scratch: ordered across streams)
+        ScratchGuard sg(s, stream, cl.lay.ext != 0);
+        if (cl.lay.ext) {
+            CU(s->coop_ext.ensure((size_t)cl.grid * cl.warps * cl.lay.xtotal * sizeof(double)));
+            cl.ext = (double*)s->coop_ext.p;
+        }
         Timed t(s, cl.stream);
         CU(s->cks->lin(cl, p, al));
         return TREPB_OK;

@@ -12,6 +12,8 @@ namespace coopk {
 constexpr int kSolveTeams = 12;
 // most instances a CTA of the linearize kernel holds (255 registers per thread with one warp per instance)
 constexpr int kLinTeams = 8;
+// the same for the flavours that keep part of the first-derivative workspace in global memory (ExtDims)
+constexpr int kExtLinTeams = 12;
 // teams per CTA of the wide instantiations (shapes with small workspaces): 16 warps at 128 registers for the
 // compile-time-size flavours, kWideTeamsRt warps for the run-time-size one
 constexpr int kWideTeamsCt = 16;
@@ -28,6 +30,7 @@ struct CoopLaunch {
     CoopSys sys;            // view whose base is the DEVICE copy of the blob
     int blob_bytes;
     CoopLayout lay;
+    double* ext;            // external slabs, grid x warps x lay.xtotal doubles (linearize kernels of ext flavours), or null
 };
 
 // One set per size flavour: run-time sizes ("cooperative") or a CtDims instantiation that serves
@@ -36,7 +39,9 @@ struct CoopKernelSet {
     const char* name;
     int specialized;
     int team_warps;         // warps that work on one instance (1: WarpTeam, 2: PairTeam)
-    int max_teams;          // teams per CTA of the wide instantiations (0: none; then kLinTeams / kSolveTeams bound)
+    int max_teams;          // teams per CTA of the wide instantiations (0: none; then lin_teams / kSolveTeams bound)
+    int lin_teams;          // teams per CTA the base linearize instantiation is built for
+    int ext;                // 1: the linearize kernel keeps blocks in an external slab (CoopLayout::make, ext)
     bool (*matches)(const CoopSys&);
     cudaError_t (*step)(const CoopLaunch&, const StepParams&);
     cudaError_t (*p2)(const CoopLaunch&, const P2Params&);

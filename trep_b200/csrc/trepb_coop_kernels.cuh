@@ -264,7 +264,8 @@ coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, co
 
 template <class D, class Team, int TEAMS>
 __global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
-coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al) {
+coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const LinParams p, const AuxLayout al,
+                double* __restrict__ ext) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, false);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
@@ -272,7 +273,10 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     double* w = st.w;
     const Team tm = make_team<Team>();
     constexpr int TS = Team::kSize;
-    Coop<Team, D> c(S, lay, w, tm);
+    // D::kExt: this team's slab of the external region (one per team of the persistent grid)
+    double* xs = nullptr;
+    if constexpr (D::kExt) xs = ext + ((long)blockIdx.x * (blockDim.x / TS) + team_index<Team>()) * lay.xtotal;
+    Coop<Team, D> c(S, lay, w, tm, xs);
     const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const long nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
@@ -351,52 +355,53 @@ template <class D, class Team>
 struct Launch {
     static constexpr bool kWide = Team::kWarps == 1 && wide_fits<D>();
     static constexpr int kWideTeams = D::kStatic ? kWideTeamsCt : kWideTeamsRt;
+    static constexpr int kLin = D::kExt ? kExtLinTeams : kLinTeams;   // teams per CTA of the base linearize instantiation
     static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
         if constexpr (kWide) if (c.warps > kSolveTeams) {
-            cudaError_t e = prep(coop_step_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            cudaError_t e = prep(coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_step_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_step_kernel<D, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_step_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
         if constexpr (kWide) if (c.warps > kSolveTeams) {
-            cudaError_t e = prep(coop_p2_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            cudaError_t e = prep(coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_p2_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_p2_kernel<D, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_p2_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
-        if constexpr (kWide) if (c.warps > kLinTeams) {
+        if constexpr (kWide) if (c.warps > kLin) {
             cudaError_t e = prep(coop_lin_kernel<D, Team, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_lin_kernel<D, Team, kWideTeams><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+            coop_lin_kernel<D, Team, kWideTeams><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al, c.ext);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_lin_kernel<D, Team, kLinTeams>, c.smem);
+        cudaError_t e = prep(coop_lin_kernel<D, Team, kLin>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_lin_kernel<D, Team, kLinTeams><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al);
+        coop_lin_kernel<D, Team, kLin><<<c.grid, Team::kSize * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, al, c.ext);
         return cudaGetLastError();
     }
     static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
         if constexpr (kWide) if (c.warps > kSolveTeams) {
-            cudaError_t e = prep(coop_project_kernel<D, WarpTeam, kWideTeams>, c.smem);
+            cudaError_t e = prep(coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_project_kernel<D, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_project_kernel<D, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_project_kernel<D, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
         return cudaGetLastError();
     }
     // which: 0 step, 1 p2, 2 lin, 3 project; + 4 for the wide instantiation
@@ -404,16 +409,16 @@ struct Launch {
         const void* fn = nullptr;
         if (which >= 4) {
             if constexpr (kWide) {
-                fn = which == 4 ? (const void*)coop_step_kernel<D, WarpTeam, kWideTeams>
-                   : which == 5 ? (const void*)coop_p2_kernel<D, WarpTeam, kWideTeams>
-                   : which == 6 ? (const void*)coop_lin_kernel<D, Team, kWideTeams> : (const void*)coop_project_kernel<D, WarpTeam, kWideTeams>;
+                fn = which == 4 ? (const void*)coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams>
+                   : which == 5 ? (const void*)coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams>
+                   : which == 6 ? (const void*)coop_lin_kernel<D, Team, kWideTeams> : (const void*)coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams>;
             } else {
                 return cudaErrorInvalidValue;
             }
         } else {
-            fn = which == 0 ? (const void*)coop_step_kernel<D, WarpTeam, kSolveTeams>
-               : which == 1 ? (const void*)coop_p2_kernel<D, WarpTeam, kSolveTeams>
-               : which == 2 ? (const void*)coop_lin_kernel<D, Team, kLinTeams> : (const void*)coop_project_kernel<D, WarpTeam, kSolveTeams>;
+            fn = which == 0 ? (const void*)coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams>
+               : which == 1 ? (const void*)coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams>
+               : which == 2 ? (const void*)coop_lin_kernel<D, Team, kLin> : (const void*)coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams>;
         }
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
@@ -439,6 +444,8 @@ CoopKernelSet make_coop_kernelset(const char* name) {
     k.specialized = D::kStatic ? 1 : 0;
     k.team_warps = Team::kWarps;
     k.max_teams = coopk::Launch<D, Team>::kWide ? coopk::Launch<D, Team>::kWideTeams : 0;
+    k.lin_teams = coopk::Launch<D, Team>::kLin;
+    k.ext = D::kExt ? 1 : 0;
     k.matches = &coopk::Launch<D, Team>::matches;
     k.step = &coopk::Launch<D, Team>::step;
     k.p2 = &coopk::Launch<D, Team>::p2;

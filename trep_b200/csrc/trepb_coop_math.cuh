@@ -91,7 +91,8 @@ struct PairTeam {
 // sizes: run-time or compile-time
 // ---------------------------------------------------------------------------------------------
 struct RtDims {
-    static constexpr bool kStatic = false, kExtras = true;
+    static constexpr bool kStatic = false, kExtras = true, kExt = false;
+    using Solve = RtDims;
     static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1, NDC = 0, NQC = 0;
 };
 
@@ -114,6 +115,7 @@ struct CoopLayout {
     int fr, scl, rdM, rdP;
     int ints;                        // pivM[nr] swpM[nr] pivP[nc] swpP[nc] flag  (int32)
     int total;
+    int ext, xtotal;                 // blocks Y, UP, DN in the team's external slab of xtotal doubles (make(), ext)
 
     TREPB_HD static constexpr int odd(int n) { return n | 1; }
     // stat: the compile-time-size flavour (right-hand-side columns in registers: no Z block, the
@@ -126,10 +128,18 @@ struct CoopLayout {
     // solve_only: the layout of the kernels that never call deriv1 (step, project, p2 / f): no DDh.lambda
     // block, no projection factors, two pair arrays instead of four (dyn_second) - 18.0 instead of 27.0 KB
     // per marionette instance, 12 instead of 8 instances per SM.
+    // ext: the layout of the flavours that keep the blocks only calc_deriv1's column phase reads with one gather
+    // per entry - the DDh.lambda block Y and two of the four pair-combination arrays (UP, DN) - in a per-team
+    // slab of global memory (L2-resident: 8.6 KB per marionette instance) instead of shared memory, and the
+    // projection factors over the midpoint / velocity vectors that are dead by then: 17.7 instead of 26.4 KB per
+    // marionette instance, 12 instead of 8 instances per SM.  Offsets Y, UP, DN then index the external slab.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
                                               bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false,
-                                              int nqs = 0, int nqf = 0, int nns = 0, int nw = 0) {
+                                              int nqs = 0, int nqf = 0, int nns = 0, int nw = 0, bool ext = false) {
         CoopLayout L{};
+        const bool sx = ext && !solve_only;
+        int xo = 0;
+        L.ext = sx ? 1 : 0;
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
         L.ldf = odd(nr + 1);
@@ -151,15 +161,20 @@ struct CoopLayout {
         const int nlq = nq > nr ? nq : nr;
         L.Lq = o; o += nlq; L.Lv = o; o += nlq;
         L.fr = L.Lq; L.scl = L.Lv;
-        L.VV = o; o += npairs; L.QQ = o; o += npairs; L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs;
+        L.VV = o; o += npairs; L.QQ = o; o += npairs;
+        if (sx) { L.UP = xo; xo += npairs; L.DN = xo; xo += npairs; }
+        else { L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs; }
         L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
-        L.Y = o; o += solve_only ? 0 : nY;
+        if (sx) { L.Y = xo; xo += nY; }
+        else { L.Y = o; o += solve_only ? 0 : nY; }
         L.Z = o; o += (stat || solve_only) ? 0 : nc * L.ldy;
-        L.PJ = o; o += solve_only ? 0 : nc * L.ldp;
+        if (sx && nc * L.ldp <= 2 * nq) L.PJ = L.qe;   // qe, dq: last read by the pose sweeps
+        else { L.PJ = o; o += solve_only ? 0 : nc * L.ldp; }
         L.rdM = o; o += nr; L.rdP = o; o += solve_only ? 0 : nc;
         L.ints = o; o += (2 * nr + 2 * nc + 2) / 2 + 1;   // + the first-warp flag
         L.total = (o + 1) & ~1;
+        L.xtotal = (xo + 1) & ~1;
         L.append_extras(nd, nq, nu, nqs, nqf, nns, nw);
         return L;
     }
@@ -175,8 +190,8 @@ struct CoopLayout {
         SC = o; o += (nqs > 0 || nqf > 0) ? 7 * nq : 0;
         total = (o + 1) & ~1;
     }
-    TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false) {
-        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf, s.nns, s.nw);
+    TREPB_HD void set(const CoopSys& s, bool stat = false, bool solve_only = false, bool ext_ = false) {
+        *this = make(s.nd, s.nk, s.nu, s.nc, s.nl, s.np, s.npairs, stat, s.ndc, s.nqc, solve_only, s.nqs, s.nqf, s.nns, s.nw, ext_);
     }
 };
 
@@ -186,6 +201,8 @@ template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int
 struct CtDims {
     static constexpr bool kStatic = true;
     static constexpr bool kExtras = EX_ != 0;
+    static constexpr bool kExt = false;
+    using Solve = CtDims;   // the flavour of the kernels that never call deriv1
     static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_,
                          NDC = NDC_, NQC = NQC_;
     TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
@@ -194,6 +211,17 @@ struct CtDims {
     TREPB_HD static bool matches(const CoopSys& s) {
         return s.nd == ND && s.nk == NK && s.nu == NU && s.nc == NC && s.nl == NL && s.np == NP && s.npairs == NPAIRS &&
                s.nlevels == NLEVELS && s.ndc == NDC && s.nqc == NQC && (kExtras || (s.ns == 0 && s.nfd == 0 && s.nns == 0 && s.nw == 0));
+    }
+};
+
+// The same shape with the external-slab layout (CoopLayout::make, ext) for the first-derivative kernel
+template <class Dims>
+struct ExtDims : Dims {
+    static constexpr bool kExt = true;
+    using Solve = Dims;
+    TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
+        return CoopLayout::make(Dims::ND, Dims::NK, Dims::NU, Dims::NC, Dims::NL, Dims::NP, Dims::NPAIRS, true, Dims::NDC,
+                                Dims::NQC, solve_only, 0, 0, 0, 0, true);
     }
 };
 
@@ -476,11 +504,15 @@ struct Coop {
     const CoopSys& S;
     const CoopLayout L;
     double* w;      // workspace base of this instance
+    double* x;      // the team's external slab (D::kExt flavours: blocks Y, UP, DN), else unused
     Team t;
 
-    TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team) : S(s), L(l), w(base), t(team) {
+    TREPB_HD Coop(const CoopSys& s, const CoopLayout& l, double* base, Team team, double* ext = nullptr)
+        : S(s), L(l), w(base), x(ext), t(team) {
         use_pose(false);
     }
+    // base of a block that the ext layout keeps in the external slab
+    TREPB_HD double* xw(int off) const { if constexpr (D::kExt) return x + off; else return w + off; }
 
 #define TREPB_DIM(fn, CT, rt) \
     TREPB_HD int fn() const { if constexpr (D::kStatic) return D::CT; else return S.rt; }
@@ -1166,8 +1198,8 @@ struct Coop {
                 w[L.QQ + e] = 0.5 * dn - 0.5 * sG;   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
             } else {
                 w[L.VV + e] = vv;
-                w[L.UP + e] = sG;
-                w[L.DN + e] = dn;
+                xw(L.UP)[e] = sG;
+                xw(L.DN)[e] = dn;
                 w[L.QQ + e] = WG;
             }
         }
@@ -1188,11 +1220,11 @@ struct Coop {
             const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
             double qq = w[L.QQ + e];
             if (i == j) qq -= ks_eff(S.l_cfg()[i]);
-            const double Q = 0.25 * dt * qq, V = 1.0 / dt * w[L.VV + e], U = 0.5 * w[L.UP + e], Dn = 0.5 * w[L.DN + e];
+            const double Q = 0.25 * dt * qq, V = 1.0 / dt * w[L.VV + e], U = 0.5 * xw(L.UP)[e], Dn = 0.5 * xw(L.DN)[e];
             w[L.VV + e] = (Q + V) + U + Dn;
             w[L.QQ + e] = (Q + V) - U - Dn;
-            w[L.UP + e] = (Q - V) + U - Dn;
-            w[L.DN + e] = (Q - V) - U + Dn;
+            xw(L.UP)[e] = (Q - V) + U - Dn;
+            xw(L.DN)[e] = (Q - V) - U + Dn;
         }
         t.sync();
     }
@@ -1205,8 +1237,8 @@ struct Coop {
         if (m == 0) val = a == b ? 0.25 * dt * -ks_eff(a) : 0.0;
         else {
             const int e = (m > 0 ? m : -m) - 1;
-            const int off = which == 0 ? L.VV : (which == 1 ? L.QQ : (((which == 2) == (m > 0)) ? L.UP : L.DN));
-            val = w[off + e];
+            if (which < 2) val = w[(which == 0 ? L.VV : L.QQ) + e];
+            else val = xw(((which == 2) == (m > 0)) ? L.UP : L.DN)[e];
         }
         if (NS() > 0) {   // Q = dt/4 L_dqdq enters all four combinations with a plus sign; L_dqdq -= d2V/dqdq
             const int xa = S.xs_idx()[a], xb = S.xs_idx()[b];
@@ -1711,7 +1743,7 @@ struct Coop {
         const int nd = ND(), nk = NK(), nq = NQ(), nc = NC(), nu = NU(), lane = t.lane();
         const int nX = 2 * nq, nU = nu + nk;
         const double dt = t2 - t1;
-        double* Y = w + L.Y;
+        double* Y = xw(L.Y);
         const int ldy = L.ldd;   // leading dimension of the DDh.lambda block (== L.ldy for run-time sizes)
         TREPB_TICK_INIT
         dyn_second();   // tables at the converged midpoint

@@ -402,14 +402,16 @@ class System:
     """Handle of a flattened system resident on one GPU (trepb_system)."""
 
     def __init__(self, desc: D.SystemDesc, device=0, specialize=True, cooperative=None, d2_pairwise=False, literal=True,
-                 coop_one_warp=False):
+                 coop_one_warp=False, coop_two_warps=False):
         """specialize=False: skip the ahead-of-time specialised kernels.  cooperative: None = let
         the library choose between one thread and one warp per instance for a table-driven system,
         False = always one thread, True = always the cooperative kernels (their compile-time-size
         flavour when one was built for this shape, unless specialize=False).  d2_pairwise: second
         derivatives of a table-driven system by one hyper-dual residual evaluation per parameter
-        pair instead of one dual evaluation of the Jacobian tables per parameter.  coop_one_warp: one
-        warp per instance even where the two-warp flavour of the cooperative kernels exists."""
+        pair instead of one dual evaluation of the Jacobian tables per parameter.  coop_one_warp /
+        coop_two_warps: for shapes whose cooperative kernels were built in several flavours, the one-warp
+        flavour with the whole workspace in shared memory / the two-warps-per-instance flavour instead of
+        the default (TREPB_FLAG_COOP_ONE_WARP, TREPB_FLAG_COOP_TWO_WARPS)."""
         self.desc = desc
         self.device = device
         cd, self._keep = D.to_c(desc)
@@ -423,6 +425,8 @@ class System:
             flags |= 8
         if coop_one_warp:
             flags |= 32
+        if coop_two_warps:
+            flags |= 64
         if not literal:
             flags |= 16     # skip an all-literal instantiation: the run-time-parameter kernel of the structure
         _check(_lib.trepb_system_create(C.byref(cd), device, flags, C.byref(h)))
