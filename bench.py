@@ -356,7 +356,8 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
     if os.path.exists(fj):
         prof = json.load(open(fj))
         fl = prof.get("puppet_coop_lin_flops_per_linearization")
-        tb = prof.get("puppet_coop_lin_dram_bytes_per_linearization")
+        tb = prof.get("puppet_coop_ext_lin_dram_bytes_per_linearization" if s.kernel_name.endswith("/ext")
+                      else "puppet_coop_lin_dram_bytes_per_linearization")
         alg = 8 * (d.nq + d.nd + d.nk + d.nc) + 8 * (d.nX * d.nX + d.nX * d.nU + d.nq + d.nd + d.nc) + 8
         if fl:
             ach = fl * B / (t * 1e-3) / 1e12
@@ -364,11 +365,13 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                                  "flops_per_unit": fl, "traffic": tb * B if tb else None,
                                  "hbm": {"achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                          "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg},
-                                 "note": "cooperative kernel: two warps per instance, link tables + 27 KB workspace per instance in shared "
-                                         "memory (8 instances = 16 warps per SM); DRAM traffic is the A/B output only. Latency-bound on "
-                                         "chip: 65 k warp instructions per linearization at ~6.5 cycles each, fp64 pipe ~15 % active; the "
-                                         "flops are the kernel's executed count (ncu sass counters), so frac is pipe utilisation "
-                                         "(ncu: profiles/r02i_coop_lin_pair_lines.txt; DESIGN.md section 4b)"}
+                                 "note": "cooperative kernel: one warp per instance, link tables + 17.7 KB workspace per instance in shared "
+                                         "memory and 8.6 KB (DDh.lambda block, two pair-combination arrays) in an L2-resident slab: 12 "
+                                         "instances per SM; DRAM traffic is the A/B output plus write-backs of the slab. Latency-bound on "
+                                         "chip: 66 k warp instructions per linearization at ~6 cycles each per warp, throughput grows "
+                                         "almost linearly with the instances in flight; the flops are the executed count of the two-warp "
+                                         "flavour (4.98e5, ncu sass counters; this flavour executes 5.85e5 for the same result), so frac "
+                                         "is pipe utilisation (ncu: profiles/r02v_coop_lin_ext_*.txt; DESIGN.md section 4b)"}
     out.append(entry)
     # the same batch through the thread-per-instance table-driven kernel (the round's starting point)
     s_thr = lib.System(d, device=device, cooperative=False)

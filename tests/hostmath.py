@@ -150,8 +150,8 @@ def coop_linearize(desc, t1, t2, q1, p1, u1, k2, q2_guess=None, lam_guess=None, 
     lg = None if lam_guess is None else _c(lam_guess)
     q2, p2, lam = np.zeros(desc.nq), np.zeros(desc.nd), np.zeros(max(desc.nc, 1))
     it = C.c_int(0)
-    A = np.zeros((desc.nX, desc.nX))
-    B = np.zeros((desc.nX, max(desc.nU, 1)))
+    A = np.full((desc.nX, desc.nX), 1e300)          # poisoned: every entry of A and B must be written
+    B = np.full((desc.nX, max(desc.nU, 1)), 1e300)
     shapes = raw_shapes(desc)
     raw = {n: np.zeros(max(int(np.prod(shapes[n])), 1)) for n in RAW}
     ptrs = (C.POINTER(C.c_double) * 12)(*[_dp(raw[n]) for n in RAW])

@@ -1669,8 +1669,12 @@ struct Coop {
             double c = -(comb(1, col, j, dt) - fv);   // T11(col, j)
             if (NC() > 0) {
                 if constexpr (D::kStatic) {
+                    // unconditional load (the column phase issues its 22 gathers back to back: with D::kExt they
+                    // come from the L2-resident slab)
                     const int r = S.dd_row()[j], cc = S.dd_col()[col];
-                    if (r >= 0 && cc >= 0) c += Y[r * ldy + cc];
+                    const bool in = r >= 0 && cc >= 0;
+                    const double yv = Y[in ? r * ldy + cc : 0];
+                    c += in ? yv : 0.0;
                 } else {
                     c += Y[j * ldy + col];
                 }
@@ -1838,10 +1842,21 @@ struct Coop {
             }
         }
         TREPB_TICK(28);
-        // ---- constant blocks of A and B (dsystem.py:284-317): zero everything with wide stores, then the
-        // few non-zero constants; the computed columns are written afterwards by the column loop
-        if (o.A) fill_zero(o.A, nX * nX);
-        if (o.B) fill_zero(o.B, nX * nU);
+        // ---- constant blocks of A and B (dsystem.py:284-317): zeros with wide stores over what the column loop
+        // below does not write - the kinematic rows of both halves and, in A's dynamic rows, the nk trailing
+        // columns - then the few non-zero constants
+        if (o.A) {
+            fill_zero(o.A + (long)nd * nX, nk * nX);
+            fill_zero(o.A + (long)(nq + nd) * nX, nk * nX);
+            for (int e = lane; e < 2 * nd * nk; e += Team::kSize) {
+                const int r = e / nk, c = e - r * nk;
+                o.A[(long)(r < nd ? r : nq + r - nd) * nX + nq + nd + c] = 0.0;
+            }
+        }
+        if (o.B) {
+            fill_zero(o.B + (long)nd * nU, nk * nU);
+            fill_zero(o.B + (long)(nq + nd) * nU, nk * nU);
+        }
         t.sync();
         for (int i = lane; i < nk; i += Team::kSize) {
             if (o.A) o.A[(nq + nd + i) * nX + nd + i] = -1.0 / dt;
