@@ -67,6 +67,13 @@ int th_step(const trepb_sysdesc* d, int nsteps, double t0, double dt, double tol
     return 0;
 }
 
+// doubles of the thread-per-instance workspace (what trepb_system_create compares with its cooperative threshold)
+int th_ws_doubles(const trepb_sysdesc* d) {
+    Host h;
+    if (!h.init(d)) return -100;
+    return (int)h.slab.size();
+}
+
 int th_calc_p2(const trepb_sysdesc* d, double dt, const double* q0, const double* q1, double* p) {
     Host h;
     if (!h.init(d)) return -100;

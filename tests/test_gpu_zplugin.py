@@ -90,7 +90,9 @@ def test_cooperative_plugin_for_a_user_shape(lib):
 
 
 def test_cooperative_plugin_for_a_shape_with_springs(lib):
-    """CtDims<..., 1>: compile-time sizes for everything but the spring / damper / wrench counts."""
+    """CtDims<..., 1>: compile-time sizes for everything but the spring / damper / wrench counts; built with
+    ext=True, so the plug-in also carries the external-slab flavour of the linearize kernel (the default once
+    loaded; TREPB_FLAG_COOP_ONE_WARP selects the plain one)."""
     from trep_b200 import build
     name = "spring_arms"
     d = G.desc(name)
@@ -98,20 +100,21 @@ def test_cooperative_plugin_for_a_shape_with_springs(lib):
     assert lib.System(d, cooperative=True).kernel_name == "cooperative"
     path = os.path.join(os.path.dirname(build.LIB), "libtrepb_plugin_spring_arms_coop.so")
     if shutil.which(build.NVCC) is not None:
-        path = build.build_plugin(d, "spring_arms_coop", kind="coop")
+        path = build.build_plugin(d, "spring_arms_coop", kind="coop", ext=True)
     elif not os.path.exists(path):
         pytest.skip("plug-in not prebuilt and no nvcc on this box")
-    assert lib.load_plugin(path) == 1
-    s = lib.System(d, cooperative=True)
-    assert s.cooperative and s.kernel_name == "cooperative/spring_arms_coop"
-    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
-                      q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
-    assert np.all(out["status"] == 0)
-    for k in ("q2", "p2", "lambda1", "A", "B"):
-        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
-    for k in G.RAW:
-        G.assert_close(out[k], g["case_" + k], "coop plugin %s" % k)
-    assert np.array_equal(out["iters"], g["case_iters"])
+    assert lib.load_plugin(path) == 2
+    for kw, kname in ((dict(), "cooperative/spring_arms_coop/ext"), (dict(coop_one_warp=True), "cooperative/spring_arms_coop")):
+        s = lib.System(d, cooperative=True, **kw)
+        assert s.cooperative and s.kernel_name == kname
+        out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], t1=g["case_t1"], t2=g["case_t2"],
+                          q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+        assert np.all(out["status"] == 0)
+        for k in ("q2", "p2", "lambda1", "A", "B"):
+            G.assert_close(out[k], g["case_" + k], "coop plugin %s %s" % (kname, k))
+        for k in G.RAW:
+            G.assert_close(out[k], g["case_" + k], "coop plugin %s %s" % (kname, k))
+        assert np.array_equal(out["iters"], g["case_iters"])
     # the in-kernel stepping of the same flavour (solve-only layout with the run-time tail)
     dt, nsteps = float(g["roll_dt"]), int(g["roll_nsteps"])
     p0 = s.calc_p2(dt, g["roll_q0"], g["roll_q1"])

@@ -236,7 +236,10 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
                 if (w >= 1 && w < warps) warps = w;
                 if (w >= 1 && w < warps_solve) warps_solve = w;
             }
-            const bool wanted = (flags & TREPB_FLAG_FORCE_COOP) || s->ws_doubles > 2048;
+            // measured crossover of the table-driven kernels (tools/time_midsize.py, B200): up to ~1000 doubles of thread
+            // workspace one thread per instance wins (rod, 656: 1.9x; 5-link pendulum, 955: even), above it the
+            // cooperative kernels do (loop3d, 1320: 1.1x linearize / 1.45x step; spring arms, 1461: 1.06x / 1.7x; pccd, 2128: 3.6x / 2.8x)
+            const bool wanted = (flags & TREPB_FLAG_FORCE_COOP) || s->ws_doubles > 1200;
             if (warps >= 1 && wanted) {
                 CUS(cudaMalloc((void**)&s->dcoop, blob_d));
                 CUS(cudaMemset(s->dcoop, 0, blob_d));
