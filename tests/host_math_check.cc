@@ -276,7 +276,7 @@ int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double to
                    const double* q2_guess, const double* lam_guess, double* q2, double* p2,
                    double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
     CoopLayout L;
-    L.set(S, D::kStatic, false, D::kExt);
+    L.set(S, D::kStatic, D::kExtS, D::kExt || D::kExtS);   // kExtS: the solve-only layout (callers pass raw = null)
     std::vector<double> slab(L.total + 8, 0.0);
     // poisoned external slab: every entry read must have been written for this instance
     std::vector<double> xslab(L.xtotal + 8, 1e300);
@@ -331,6 +331,11 @@ int th_coop_linearize(const trepb_sysdesc* d, int static_dims, int nsteps, doubl
     CoopSys S = P.view(P.blob.data());
     if (static_dims) {
         if (!PuppetDims::matches(S)) return -201;
+        if (static_dims == 3) {  // solve-only external-slab layout (step / project / p2 kernels): no derivatives
+            if (raw) return -202;
+            return coop_linearize<ExtSolveDims<PuppetDims>>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess,
+                                                            q2, p2, lam, iters, A, B, raw, aux);
+        }
         if (static_dims == 2)   // external-slab layout of the first-derivative workspace
             return coop_linearize<ExtDims<PuppetDims>>(S, nsteps, t1, dt, tol, maxit, q1, p1, u1, k2, q2_guess, lam_guess,
                                                        q2, p2, lam, iters, A, B, raw, aux);

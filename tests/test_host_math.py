@@ -55,6 +55,29 @@ def test_cooperative_math_cases(name):
     assert flips == 0
 
 
+def test_cooperative_solve_only_slab_layout():
+    """The step / project / p2 kernels of the external-slab flavour keep the pair arrays and both constraint Jacobians
+    in the slab (ExtSolveDims): the Newton solve on that layout, with a poisoned slab, against the goldens."""
+    g = G.golden("puppet")
+    d = G.desc("puppet")
+    for c in range(g["case_q1"].shape[0]):
+        out = H.coop_linearize(d, float(g["case_t1"][c]), float(g["case_t2"][c]), g["case_q1"][c], g["case_p1"][c],
+                               g["case_u1"][c], g["case_k2"][c], q2_guess=g["case_q2_guess"][c],
+                               lam_guess=g["case_lambda_guess"][c], static_dims=3, derivs=False)
+        assert out["rc"] == 0 and out["iters"] == int(g["case_iters"][c])
+        for k in ("q2", "p2", "lambda1"):
+            G.assert_close(out[k], g["case_" + k][c], "solve-only slab case %d %s" % (c, k))
+    # a rollout on the same layout (the kernels' time loop keeps the slab across steps)
+    dt, n = float(g["roll_dt"]), 12
+    p0 = H.coop_calc_p2(d, dt, g["roll_q0"], g["roll_q1"])
+    args = (d, dt, 2 * dt, g["roll_q1"], p0, np.zeros((n, d.nu)), g["roll_k2"][:n])
+    out = H.coop_linearize(*args, nsteps=n, static_dims=3, derivs=False)
+    want = H.coop_linearize(*args, nsteps=n, static_dims=1, derivs=False)
+    assert out["rc"] == 0 and want["rc"] == 0 and out["iters"] == want["iters"] > 0
+    for k in ("q2", "p2", "lambda1"):
+        assert np.array_equal(out[k], want[k]), k
+
+
 def test_cooperative_aux_export_matches_thread_path():
     """The factorizations the cooperative linearize kernel exports for the second-derivative
     kernel are in LU_decomp's convention (math-code.c:337-432): same factors and permutation as the

@@ -220,14 +220,14 @@ int trepb_system_create(const trepb_sysdesc* desc, int device, int flags, trepb_
             CoopSys hv = s->CP.view(s->CP.blob.data());
             const CoopKernelSet* cks = coop_select(hv, !(flags & TREPB_FLAG_NO_SPECIALIZE), (flags & TREPB_FLAG_COOP_ONE_WARP) ? 1 : ((flags & TREPB_FLAG_COOP_TWO_WARPS) ? 2 : 0));
             s->clay.set(hv, cks->specialized != 0, false, cks->ext != 0);
-            s->clay_solve.set(hv, cks->specialized != 0, true);
+            s->clay_solve.set(hv, cks->specialized != 0, true, cks->ext != 0);
             s->coop_blob_bytes = (int)s->CP.blob.size();
             const size_t blob_d = (size_t)(((s->coop_blob_bytes + 7) / 8 + 1) & ~1) * 8;
             const size_t ws_b = (size_t)s->clay.total * 8;
             const size_t cap = (size_t)prop.sharedMemPerBlockOptin;
             int warps = cap > blob_d ? (int)((cap - blob_d) / ws_b) : 0;
             const int lin_cap = cks->max_teams > cks->lin_teams ? cks->max_teams : cks->lin_teams;
-            const int solve_cap = cks->max_teams > coopk::kSolveTeams ? cks->max_teams : coopk::kSolveTeams;
+            const int solve_cap = cks->max_teams > cks->solve_teams ? cks->max_teams : cks->solve_teams;
             if (warps > lin_cap) warps = lin_cap;
             int warps_solve = cap > blob_d ? (int)((cap - blob_d) / ((size_t)s->clay_solve.total * 8)) : 0;
             if (warps_solve > solve_cap) warps_solve = solve_cap;
@@ -348,7 +348,7 @@ int trepb_kernel_info(trepb_system* s, int which, int32_t* regs, int32_t* local_
     if (s->coop) {
         const bool lin = which == 2;
         const int teams = lin ? s->coop_warps : s->coop_warps_solve;
-        const bool wide = teams > (lin ? s->cks->lin_teams : coopk::kSolveTeams);   // the instantiation a full batch runs
+        const bool wide = teams > (lin ? s->cks->lin_teams : s->cks->solve_teams);   // the instantiation a full batch runs
         CU(s->cks->info(which + (wide ? 4 : 0), &ki));
         if (regs) *regs = ki.regs;
         if (local_bytes) *local_bytes = (int32_t)ki.local_bytes;
@@ -436,6 +436,14 @@ void make_coop(trepb_system* s, long long batch, cudaStream_t stream, CoopLaunch
     c->ext = nullptr;
 }
 
+// ext flavours of the cooperative kernels: one slab of lay.xtotal doubles per team of the persistent grid
+int attach_slabs(trepb_system* s, CoopLaunch* c) {
+    if (!c->lay.ext || c->lay.xtotal == 0) return TREPB_OK;
+    CU(s->coop_ext.ensure((size_t)c->grid * c->warps * c->lay.xtotal * sizeof(double)));
+    c->ext = (double*)s->coop_ext.p;
+    return TREPB_OK;
+}
+
 // Orders launches that use the handle's scratch across streams: wait for the previous user before the
 // launch, mark the end of this one after it.  The caller holds s->mu.
 struct ScratchGuard {
@@ -484,6 +492,8 @@ int trepb_step_batch_dev(trepb_system* s, const trepb_step_args* a, void* stream
     if (s->coop) {
         CoopLaunch cl;
         make_coop(s, a->batch, (cudaStream_t)stream, &cl, true);
+        ScratchGuard sg(s, (cudaStream_t)stream, cl.lay.ext != 0);   // ext flavours: slabs owned by the handle
+        if (int rc = attach_slabs(s, &cl)) return rc;
         Timed t(s, cl.stream);
         CU(s->cks->step(cl, p));
         return TREPB_OK;
@@ -518,6 +528,8 @@ int trepb_project_batch_dev(trepb_system* s, const trepb_project_args* a, void* 
     if (s->coop) {
         CoopLaunch cl;
         make_coop(s, a->batch, (cudaStream_t)stream, &cl, true);
+        ScratchGuard sg(s, (cudaStream_t)stream, cl.lay.ext != 0);   // ext flavours: slabs owned by the handle
+        if (int rc = attach_slabs(s, &cl)) return rc;
         Timed t(s, cl.stream);
         CU(s->cks->proj(cl, p));
         return TREPB_OK;
@@ -542,6 +554,8 @@ int eval_launch(trepb_system* s, const P2Params& p, void* stream) {
     if (s->coop) {
         CoopLaunch cl;
         make_coop(s, p.batch, (cudaStream_t)stream, &cl, true);
+        ScratchGuard sg(s, (cudaStream_t)stream, cl.lay.ext != 0);   // ext flavours: slabs owned by the handle
+        if (int rc = attach_slabs(s, &cl)) return rc;
         Timed t(s, cl.stream);
         CU(s->cks->p2(cl, p));
         return TREPB_OK;
@@ -625,10 +639,7 @@ int lin_launch(trepb_system* s, const trepb_lin_args* a, cudaStream_t stream, do
         al.set(ps.nd, ps.nc);
         // ext flavours: one slab per team of the persistent grid (handle scratch: ordered across streams)
         ScratchGuard sg(s, stream, cl.lay.ext != 0);
-        if (cl.lay.ext) {
-            CU(s->coop_ext.ensure((size_t)cl.grid * cl.warps * cl.lay.xtotal * sizeof(double)));
-            cl.ext = (double*)s->coop_ext.p;
-        }
+        if (int rc = attach_slabs(s, &cl)) return rc;
         Timed t(s, cl.stream);
         CU(s->cks->lin(cl, p, al));
         return TREPB_OK;

@@ -14,6 +14,7 @@ constexpr int kSolveTeams = 12;
 constexpr int kLinTeams = 8;
 // the same for the flavours that keep part of the first-derivative workspace in global memory (ExtDims)
 constexpr int kExtLinTeams = 12;
+constexpr int kExtSolveTeams = 16;
 // teams per CTA of the wide instantiations (shapes with small workspaces): 16 warps at 128 registers for the
 // compile-time-size flavours, kWideTeamsRt warps for the run-time-size one
 constexpr int kWideTeamsCt = 16;
@@ -41,6 +42,7 @@ struct CoopKernelSet {
     int team_warps;         // warps that work on one instance (1: WarpTeam, 2: PairTeam)
     int max_teams;          // teams per CTA of the wide instantiations (0: none; then lin_teams / kSolveTeams bound)
     int lin_teams;          // teams per CTA the base linearize instantiation is built for
+    int solve_teams;        // ... and the base step / project / p2 instantiations
     int ext;                // 1: the linearize kernel keeps blocks in an external slab (CoopLayout::make, ext)
     bool (*matches)(const CoopSys&);
     cudaError_t (*step)(const CoopLaunch&, const StepParams&);

@@ -62,6 +62,15 @@ __device__ __forceinline__ CoopLayout static_layout(const CoopSys& gs, bool solv
     return lay;
 }
 
+// D::kExt / D::kExtS: this team's slab of the external region (one per team of the persistent grid)
+template <class D, class Team>
+__device__ __forceinline__ double* team_slab(double* ext, const CoopLayout& lay) {
+    if constexpr (D::kExt || D::kExtS)
+        return ext + ((long)blockIdx.x * (blockDim.x / Team::kSize) + team_index<Team>()) * lay.xtotal;
+    else
+        return nullptr;
+}
+
 template <class Team>
 __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, const CoopLayout& lay) {
     extern __shared__ double smem_[];
@@ -78,7 +87,7 @@ __device__ __forceinline__ Stage coop_stage(const CoopSys& gs, int blob_bytes, c
 
 template <class D, class Team, int TEAMS>
 __global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
-coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p) {
+coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const StepParams p, double* __restrict__ ext) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
@@ -86,7 +95,7 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
     double* w = st.w;
     const Team tm = make_team<Team>();
     constexpr int TS = Team::kSize;
-    Coop<Team, D> c(S, lay, w, tm);
+    Coop<Team, D> c(S, lay, w, tm, team_slab<D, Team>(ext, lay));
     const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     // the warps of a CTA take every step together (see coop_lin_kernel)
@@ -150,7 +159,7 @@ coop_step_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, 
 // component each) inside the time loop.
 template <class D, class Team, int TEAMS>
 __global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
-coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p) {
+coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const ProjParams p, double* __restrict__ ext) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
@@ -158,7 +167,7 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
     double* w = st.w;
     const Team tm = make_team<Team>();
     constexpr int TS = Team::kSize;
-    Coop<Team, D> c(S, lay, w, tm);
+    Coop<Team, D> c(S, lay, w, tm, team_slab<D, Team>(ext, lay));
     const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const int nX = 2 * nq, nU = nu + nk, K = p.nsteps;
@@ -226,7 +235,7 @@ coop_project_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay
 
 template <class D, class Team, int TEAMS>
 __global__ void __launch_bounds__(TEAMS * Team::kSize, 1)
-coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p) {
+coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, const P2Params p, double* __restrict__ ext) {
     CoopLayout lay = lay_;
     if constexpr (D::kStatic) lay = static_layout<D>(gs, true);
     Stage st = coop_stage<Team>(gs, blob_bytes, lay);
@@ -234,7 +243,7 @@ coop_p2_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, co
     double* w = st.w;
     const Team tm = make_team<Team>();
     constexpr int TS = Team::kSize;
-    Coop<Team, D> c(S, lay, w, tm);
+    Coop<Team, D> c(S, lay, w, tm, team_slab<D, Team>(ext, lay));
     const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     for (long b = (long)blockIdx.x * wpc + team_index<Team>(); b < p.batch; b += (long)gridDim.x * wpc) {
@@ -273,10 +282,7 @@ coop_lin_kernel(const CoopSys gs, const int blob_bytes, const CoopLayout lay_, c
     double* w = st.w;
     const Team tm = make_team<Team>();
     constexpr int TS = Team::kSize;
-    // D::kExt: this team's slab of the external region (one per team of the persistent grid)
-    double* xs = nullptr;
-    if constexpr (D::kExt) xs = ext + ((long)blockIdx.x * (blockDim.x / TS) + team_index<Team>()) * lay.xtotal;
-    Coop<Team, D> c(S, lay, w, tm, xs);
+    Coop<Team, D> c(S, lay, w, tm, team_slab<D, Team>(ext, lay));
     const int lane = tm.lane(), wpc = blockDim.x / TS;
     const int nd = c.ND(), nk = c.NK(), nq = c.NQ(), nu = c.NU(), nc = c.NC();
     const long nX = 2 * nq, nU = nu + nk, nA = nX * nX, nB = nX * nU;
@@ -353,31 +359,32 @@ constexpr bool wide_fits() {
 }
 template <class D, class Team>
 struct Launch {
-    static constexpr bool kWide = Team::kWarps == 1 && wide_fits<D>();
+    static constexpr bool kWide = Team::kWarps == 1 && !D::kExt && !D::Solve::kExtS && wide_fits<D>();
     static constexpr int kWideTeams = D::kStatic ? kWideTeamsCt : kWideTeamsRt;
     static constexpr int kLin = D::kExt ? kExtLinTeams : kLinTeams;   // teams per CTA of the base linearize instantiation
+    static constexpr int kSolve = D::Solve::kExtS ? kExtSolveTeams : kSolveTeams;   // ... of the step / project / p2 ones
     static cudaError_t step(const CoopLaunch& c, const StepParams& p) {
-        if constexpr (kWide) if (c.warps > kSolveTeams) {
+        if constexpr (kWide) if (c.warps > kSolve) {
             cudaError_t e = prep(coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_step_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_step_kernel<typename D::Solve, WarpTeam, kSolve>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_step_kernel<typename D::Solve, WarpTeam, kSolve><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
         return cudaGetLastError();
     }
     static cudaError_t p2(const CoopLaunch& c, const P2Params& p) {
-        if constexpr (kWide) if (c.warps > kSolveTeams) {
+        if constexpr (kWide) if (c.warps > kSolve) {
             cudaError_t e = prep(coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_p2_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_p2_kernel<typename D::Solve, WarpTeam, kSolve>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_p2_kernel<typename D::Solve, WarpTeam, kSolve><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
         return cudaGetLastError();
     }
     static cudaError_t lin(const CoopLaunch& c, const LinParams& p, const AuxLayout& al) {
@@ -393,15 +400,15 @@ struct Launch {
         return cudaGetLastError();
     }
     static cudaError_t proj(const CoopLaunch& c, const ProjParams& p) {
-        if constexpr (kWide) if (c.warps > kSolveTeams) {
+        if constexpr (kWide) if (c.warps > kSolve) {
             cudaError_t e = prep(coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams>, c.smem);
             if (e != cudaSuccess) return e;
-            coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+            coop_project_kernel<typename D::Solve, WarpTeam, kWideTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
             return cudaGetLastError();
         }
-        cudaError_t e = prep(coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams>, c.smem);
+        cudaError_t e = prep(coop_project_kernel<typename D::Solve, WarpTeam, kSolve>, c.smem);
         if (e != cudaSuccess) return e;
-        coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p);
+        coop_project_kernel<typename D::Solve, WarpTeam, kSolve><<<c.grid, 32 * c.warps, c.smem, c.stream>>>(c.sys, c.blob_bytes, c.lay, p, c.ext);
         return cudaGetLastError();
     }
     // which: 0 step, 1 p2, 2 lin, 3 project; + 4 for the wide instantiation
@@ -416,9 +423,9 @@ struct Launch {
                 return cudaErrorInvalidValue;
             }
         } else {
-            fn = which == 0 ? (const void*)coop_step_kernel<typename D::Solve, WarpTeam, kSolveTeams>
-               : which == 1 ? (const void*)coop_p2_kernel<typename D::Solve, WarpTeam, kSolveTeams>
-               : which == 2 ? (const void*)coop_lin_kernel<D, Team, kLin> : (const void*)coop_project_kernel<typename D::Solve, WarpTeam, kSolveTeams>;
+            fn = which == 0 ? (const void*)coop_step_kernel<typename D::Solve, WarpTeam, kSolve>
+               : which == 1 ? (const void*)coop_p2_kernel<typename D::Solve, WarpTeam, kSolve>
+               : which == 2 ? (const void*)coop_lin_kernel<D, Team, kLin> : (const void*)coop_project_kernel<typename D::Solve, WarpTeam, kSolve>;
         }
         cudaFuncAttributes a;
         cudaError_t e = cudaFuncGetAttributes(&a, fn);
@@ -445,6 +452,7 @@ CoopKernelSet make_coop_kernelset(const char* name) {
     k.team_warps = Team::kWarps;
     k.max_teams = coopk::Launch<D, Team>::kWide ? coopk::Launch<D, Team>::kWideTeams : 0;
     k.lin_teams = coopk::Launch<D, Team>::kLin;
+    k.solve_teams = coopk::Launch<D, Team>::kSolve;
     k.ext = D::kExt ? 1 : 0;
     k.matches = &coopk::Launch<D, Team>::matches;
     k.step = &coopk::Launch<D, Team>::step;

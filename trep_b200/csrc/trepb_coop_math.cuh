@@ -91,7 +91,7 @@ struct PairTeam {
 // sizes: run-time or compile-time
 // ---------------------------------------------------------------------------------------------
 struct RtDims {
-    static constexpr bool kStatic = false, kExtras = true, kExt = false;
+    static constexpr bool kStatic = false, kExtras = true, kExt = false, kExtS = false;
     using Solve = RtDims;
     static constexpr int ND = 1, NK = 0, NU = 0, NC = 0, NL = 1, NP = 0, NPAIRS = 1, NLEVELS = 1, NDC = 0, NQC = 0;
 };
@@ -138,8 +138,11 @@ struct CoopLayout {
                                               int nqs = 0, int nqf = 0, int nns = 0, int nw = 0, bool ext = false) {
         CoopLayout L{};
         const bool sx = ext && !solve_only;
+        // ext with solve_only (the step / project / p2 kernels of the same flavours): the two pair arrays and both
+        // constraint Jacobians in the slab - 12.2 instead of 18.0 KB per marionette instance, 16 instead of 12 per SM
+        const bool sxs = ext && solve_only;
         int xo = 0;
-        L.ext = sx ? 1 : 0;
+        L.ext = ext ? 1 : 0;
         const int nq = nd + nk, nr = nd + nc;
         L.nls = nl;
         L.ldf = odd(nr + 1);
@@ -161,10 +164,13 @@ struct CoopLayout {
         const int nlq = nq > nr ? nq : nr;
         L.Lq = o; o += nlq; L.Lv = o; o += nlq;
         L.fr = L.Lq; L.scl = L.Lv;
-        L.VV = o; o += npairs; L.QQ = o; o += npairs;
+        if (sxs) { L.VV = xo; xo += npairs; L.QQ = xo; xo += npairs; }
+        else { L.VV = o; o += npairs; L.QQ = o; o += npairs; }
         if (sx) { L.UP = xo; xo += npairs; L.DN = xo; xo += npairs; }
         else { L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs; }
-        L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; L.hc = o; o += nc;
+        if (sxs) { L.Dh1 = xo; xo += nc * nd; L.Dh2 = xo; xo += nc * nq; }
+        else { L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; }
+        L.hc = o; o += nc;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
         if (sx) { L.Y = xo; xo += nY; }
         else { L.Y = o; o += solve_only ? 0 : nY; }
@@ -201,7 +207,7 @@ template <int ND_, int NK_, int NU_, int NC_, int NL_, int NP_, int NPAIRS_, int
 struct CtDims {
     static constexpr bool kStatic = true;
     static constexpr bool kExtras = EX_ != 0;
-    static constexpr bool kExt = false;
+    static constexpr bool kExt = false, kExtS = false;
     using Solve = CtDims;   // the flavour of the kernels that never call deriv1
     static constexpr int ND = ND_, NK = NK_, NU = NU_, NC = NC_, NL = NL_, NP = NP_, NPAIRS = NPAIRS_, NLEVELS = NLEVELS_,
                          NDC = NDC_, NQC = NQC_;
@@ -214,11 +220,22 @@ struct CtDims {
     }
 };
 
-// The same shape with the external-slab layout (CoopLayout::make, ext) for the first-derivative kernel
+// The same shape with the external-slab layouts (CoopLayout::make, ext): ExtSolveDims for the kernels that never
+// call deriv1 (pair arrays and constraint Jacobians in the slab), ExtDims for the first-derivative kernel (DDh.lambda
+// block and the two pair-combination arrays only deriv1 uses)
+template <class Dims>
+struct ExtSolveDims : Dims {
+    static constexpr bool kExt = false, kExtS = true;
+    using Solve = ExtSolveDims;
+    TREPB_HD static constexpr CoopLayout layout(bool = true) {
+        return CoopLayout::make(Dims::ND, Dims::NK, Dims::NU, Dims::NC, Dims::NL, Dims::NP, Dims::NPAIRS, true, Dims::NDC,
+                                Dims::NQC, true, 0, 0, 0, 0, true);
+    }
+};
 template <class Dims>
 struct ExtDims : Dims {
-    static constexpr bool kExt = true;
-    using Solve = Dims;
+    static constexpr bool kExt = true, kExtS = false;
+    using Solve = ExtSolveDims<Dims>;
     TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
         return CoopLayout::make(Dims::ND, Dims::NK, Dims::NU, Dims::NC, Dims::NL, Dims::NP, Dims::NPAIRS, true, Dims::NDC,
                                 Dims::NQC, solve_only, 0, 0, 0, 0, true);
@@ -513,6 +530,8 @@ struct Coop {
     }
     // base of a block that the ext layout keeps in the external slab
     TREPB_HD double* xw(int off) const { if constexpr (D::kExt) return x + off; else return w + off; }
+    // ... and of one the solve-only ext layout keeps there (VV, QQ, Dh1, Dh2)
+    TREPB_HD double* xv(int off) const { if constexpr (D::kExtS) return x + off; else return w + off; }
 
 #define TREPB_DIM(fn, CT, rt) \
     TREPB_HD int fn() const { if constexpr (D::kStatic) return D::CT; else return S.rt; }
@@ -1194,13 +1213,13 @@ struct Coop {
             }
             const double vv = dot6(s6, H), dn = i == j ? sG : dot6(W6, H);
             if (newton_dt != 0.0) {
-                w[L.VV + e] = 0.25 * newton_dt * WG - 1.0 / newton_dt * vv;
-                w[L.QQ + e] = 0.5 * dn - 0.5 * sG;   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
+                xv(L.VV)[e] = 0.25 * newton_dt * WG - 1.0 / newton_dt * vv;
+                xv(L.QQ)[e] = 0.5 * dn - 0.5 * sG;   // + 1/2 L_ddqdq(i,k) - 1/2 L_ddqdq(k,i)
             } else {
-                w[L.VV + e] = vv;
+                xv(L.VV)[e] = vv;
                 xw(L.UP)[e] = sG;
                 xw(L.DN)[e] = dn;
-                w[L.QQ + e] = WG;
+                xv(L.QQ)[e] = WG;
             }
         }
         t.sync();
@@ -1218,11 +1237,11 @@ struct Coop {
     TREPB_HD void pair_combos(double dt) {
         for (int e = t.lane(); e < NPAIRS(); e += Team::kSize) {
             const int ij = S.pair_ij()[e], i = ij & 255, j = ij >> 8;
-            double qq = w[L.QQ + e];
+            double qq = xv(L.QQ)[e];
             if (i == j) qq -= ks_eff(S.l_cfg()[i]);
-            const double Q = 0.25 * dt * qq, V = 1.0 / dt * w[L.VV + e], U = 0.5 * xw(L.UP)[e], Dn = 0.5 * xw(L.DN)[e];
-            w[L.VV + e] = (Q + V) + U + Dn;
-            w[L.QQ + e] = (Q + V) - U - Dn;
+            const double Q = 0.25 * dt * qq, V = 1.0 / dt * xv(L.VV)[e], U = 0.5 * xw(L.UP)[e], Dn = 0.5 * xw(L.DN)[e];
+            xv(L.VV)[e] = (Q + V) + U + Dn;
+            xv(L.QQ)[e] = (Q + V) - U - Dn;
             xw(L.UP)[e] = (Q - V) + U - Dn;
             xw(L.DN)[e] = (Q - V) - U + Dn;
         }
@@ -1237,7 +1256,7 @@ struct Coop {
         if (m == 0) val = a == b ? 0.25 * dt * -ks_eff(a) : 0.0;
         else {
             const int e = (m > 0 ? m : -m) - 1;
-            if (which < 2) val = w[(which == 0 ? L.VV : L.QQ) + e];
+            if (which < 2) val = xv(which == 0 ? L.VV : L.QQ)[e];
             else val = xw(((which == 2) == (m > 0)) ? L.UP : L.DN)[e];
         }
         if (NS() > 0) {   // Q = dt/4 L_dqdq enters all four combinations with a plus sign; L_dqdq -= d2V/dqdq
@@ -1339,7 +1358,7 @@ struct Coop {
         }
         if (dh) {
             const int ncol = dh == 1 ? nd : nq;
-            double* Dm = w + (dh == 1 ? L.Dh1 : L.Dh2);
+            double* Dm = xv(dh == 1 ? L.Dh1 : L.Dh2);
             for (int e = lane; e < nc * ncol; e += Team::kSize) {
                 const int c = e / ncol, j = e - c * ncol;
                 double val = 0.0;
@@ -1504,7 +1523,7 @@ struct Coop {
             for (int j = lane; j < nd; j += Team::kSize) {
                 const double fo = ext_force(j);
                 double f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
-                for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
+                for (int c = 0; c < nc; ++c) f -= xv(L.Dh1)[c * nd + j] * w[L.lam + c];
                 // p2 = D2L2 of this midpoint (midpointvi.c:742-743, 491-504): the value of the last
                 // (converged) evaluation is the step's result; fr aliases Lq, so form it here
                 w[L.p2 + j] = 0.5 * dt * w[L.Lq + j] + w[L.Lv + j];
@@ -1533,8 +1552,8 @@ struct Coop {
                 double v = 0.0;
                 if (i == nr) v = w[L.fr + k];
                 else if (k < nd && i < nd) { if (k == i) v = -S.damp()[k] - 0.25 * dt * ks_eff(k); }
-                else if (k < nd) v = -w[L.Dh1 + (i - nd) * nd + k];
-                else if (i < nd) v = w[L.Dh2 + (k - nd) * nq + i];
+                else if (k < nd) v = -xv(L.Dh1)[(i - nd) * nd + k];
+                else if (i < nd) v = xv(L.Dh2)[(k - nd) * nq + i];
                 A[k * ld + i] = v;
             }
             t.sync();
@@ -1542,10 +1561,10 @@ struct Coop {
                 const int ij = S.pair_ij()[e];
                 const int ci = S.l_cfg()[ij & 255], cj = S.l_cfg()[ij >> 8];   // ci above-or-equal cj
                 if (ci >= nd || cj >= nd) continue;
-                const double base = w[L.VV + e];   // dt/4 L_dqdq - 1/dt L_ddqddq (dyn_second, Newton form)
+                const double base = xv(L.VV)[e];   // dt/4 L_dqdq - 1/dt L_ddqddq (dyn_second, Newton form)
                 if (ci == cj) A[ci * ld + ci] += base;
                 else {
-                    const double asym = w[L.QQ + e];
+                    const double asym = xv(L.QQ)[e];
                     A[ci * ld + cj] += base + asym;
                     A[cj * ld + ci] += base - asym;
                 }
@@ -1638,7 +1657,7 @@ struct Coop {
         for (int j = lane; j < nd; j += Team::kSize) {
             const double fo = ext_force(j);
             f = w[L.p1 + j] + (0.5 * dt * w[L.Lq + j] - w[L.Lv + j]) + dt * fo;
-            for (int c = 0; c < nc; ++c) f -= w[L.Dh1 + c * nd + j] * w[L.lam + c];
+            for (int c = 0; c < nc; ++c) f -= xv(L.Dh1)[c * nd + j] * w[L.lam + c];
             w[L.fr + j] = f;
         }
         for (int c = lane; c < nc; c += Team::kSize) w[L.fr + nd + c] = w[L.hc + c];
@@ -1773,7 +1792,7 @@ struct Coop {
         }
         for (int e = lane; e < nd * nc; e += Team::kSize) {
             const int a = e / nc, c = e - a * nc;
-            M2[a * ldm + nd + c] = w[L.Dh1 + c * nd + a];
+            M2[a * ldm + nd + c] = xv(L.Dh1)[c * nd + a];
         }
         t.sync();
         TREPB_TICK(27);
@@ -1806,7 +1825,7 @@ struct Coop {
             for (int e = lane; e < nc * nc; e += Team::kSize) {
                 const int a = e / nc, b = e - a * nc;
                 double s = 0.0;
-                for (int k = 0; k < nd; ++k) s += w[L.Dh2 + a * nq + k] * M2[k * ldm + nd + b];
+                for (int k = 0; k < nd; ++k) s += xv(L.Dh2)[a * nq + k] * M2[k * ldm + nd + b];
                 PJ[a * ldp + b] = -s;
             }
             t.sync();
@@ -1837,8 +1856,8 @@ struct Coop {
             }
             for (int i = lane; i < nc; i += Team::kSize) aux[auxo[3] + i] = (double)ipivP()[i];
             for (int e = lane; e < nc * nd; e += Team::kSize) {
-                aux[auxo[4] + e] = w[L.Dh1 + e];
-                aux[auxo[5] + e] = w[L.Dh2 + (e / nd) * nq + e % nd];
+                aux[auxo[4] + e] = xv(L.Dh1)[e];
+                aux[auxo[5] + e] = xv(L.Dh2)[(e / nd) * nq + e % nd];
             }
         }
         TREPB_TICK(28);
@@ -1881,10 +1900,10 @@ struct Coop {
                 if (D::NC > 0) {
                     double zz[C];
                     TREPB_UNROLL
-                    for (int c = 0; c < C; ++c) zz[c] = kindv == 3 ? w[L.Dh2 + c * nq + nd + ci] : 0.0;
+                    for (int c = 0; c < C; ++c) zz[c] = kindv == 3 ? xv(L.Dh2)[c * nq + nd + ci] : 0.0;
                     TREPB_UNROLL
                     for (int j = 0; j < N; ++j) {
-                        TREPB_UNROLL for (int c = 0; c < C; ++c) zz[c] += w[L.Dh2 + c * nq + j] * y[j];
+                        TREPB_UNROLL for (int c = 0; c < C; ++c) zz[c] += xv(L.Dh2)[c * nq + j] * y[j];
                     }
                     TREPB_UNROLL
                     for (int c = 0; c < C; ++c) {
@@ -1929,8 +1948,8 @@ struct Coop {
                     if (nc > 0) {
                         for (int c = 0; c < nc; ++c) {
                             double s = 0.0;
-                            for (int j = 0; j < nd; ++j) s += w[L.Dh2 + c * nq + j] * y[j * ldy];
-                            if (kindv == 3) s += w[L.Dh2 + c * nq + nd + ci];
+                            for (int j = 0; j < nd; ++j) s += xv(L.Dh2)[c * nq + j] * y[j * ldy];
+                            if (kindv == 3) s += xv(L.Dh2)[c * nq + nd + ci];
                             z[c * ldy] = s;
                         }
                         col_solve(PJ, ldp, nc, iswpP(), w + L.rdP, z, ldy);
