@@ -121,3 +121,38 @@ def test_cooperative_plugin_for_a_shape_with_springs(lib):
     st = s.step(g["roll_q1"], p0, dt, dt, nsteps=nsteps, u1=g["roll_u"][None], k2=g["roll_k2"][None], sample_every=1)
     assert st["status"][0] == 0
     G.assert_close(st["traj_q"][0], g["roll_q"][1:], "coop plugin traj q", rtol=1e-7)
+
+
+def test_specialize_builds_and_loads_by_structure(lib):
+    """lib.specialize: one call builds (cached by structure hash) and loads the plug-in; a description with the same
+    structure and other numbers then runs on the same kernels."""
+    from trep_b200 import build
+    if shutil.which(build.NVCC) is None:
+        pytest.skip("no nvcc on this box")
+    name = "loop3d"
+    d = G.desc(name)
+    g = G.golden(name)
+    before = lib.System(d)
+    assert not before.specialized          # table-driven (the cooperative kernels built for this shape)
+    assert lib.specialize(d, kind="thread") == 1
+    assert lib.specialize(d, kind="thread") == 0
+    s = lib.System(d)
+    assert s.specialized and s.kernel_name.startswith("s") and s.kernel_name.endswith("_thread")
+    kw = dict(t1=g["case_t1"], t2=g["case_t2"], q2_guess=g["case_q2_guess"], lambda_guess=g["case_lambda_guess"], want_raw=True)
+    out = s.linearize(g["case_q1"], g["case_p1"], g["case_u1"], g["case_k2"], **kw)
+    assert np.all(out["status"] == 0) and np.array_equal(out["iters"], g["case_iters"])
+    for k in ("q2", "p2", "lambda1", "A", "B") + tuple(G.RAW):
+        G.assert_close(out[k], g["case_" + k], "specialize %s" % k)
+    rng = np.random.default_rng(3)
+    B = 1 << 16
+    idx = rng.integers(1, g["roll_q"].shape[0] - 1, B)
+    q1 = g["roll_q"][idx] + rng.normal(0, 0.01, (B, d.nq)); p1 = g["roll_p"][idx] + rng.normal(0, 0.05, (B, d.nd))
+    lam = g["roll_lambda"][idx - 1]
+    t = {}
+    for label, sysm in (("table-driven", before), ("specialised", s)):
+        o = sysm.linearize(q1, p1, np.zeros((B, d.nu)), np.zeros((B, d.nk)), t1=0.0, t2=0.01, lambda_guess=lam)
+        t[label] = (o, sysm.last_kernel_ms())
+    ok = (t["table-driven"][0]["status"] == 0) & (t["specialised"][0]["status"] == 0)
+    assert ok.mean() > 0.99
+    G.assert_close(t["specialised"][0]["A"][ok], t["table-driven"][0]["A"][ok], "specialize A vs table-driven")
+    print("loop3d 2^16 linearizations: %s %.2f ms, specialised %.2f ms" % (before.kernel_name, t["table-driven"][1], t["specialised"][1]))

@@ -212,6 +212,30 @@ def load_plugin(path):
     return int(n.value)
 
 
+def specialize(desc, kind="auto", ext=False, verbose=False):
+    """Builds (once per structure: the library is named by trepb_struct_hash and rebuilt only when older than the
+    headers) and loads a plug-in of kernels compiled for `desc`'s structure, so that System(desc) - and every other
+    description with the same structure, whatever its masses, lengths and gains - runs on them instead of the
+    table-driven kernels.  kind / ext as trep_b200.build.build_plugin.  Needs nvcc (a minute per structure); raises
+    RuntimeError without it: there is no silent fallback.  Returns the number of kernel sets added (0 if this
+    structure's plug-in was already loaded)."""
+    import shutil
+    from . import build
+    if kind == "auto":
+        kind = "thread" if desc.nd + desc.nk <= 6 else "coop"
+    name = "s%016x_%s%s" % (struct_hash(desc), kind, "_ext" if ext else "")
+    if name in _specialized:
+        return 0
+    if shutil.which(build.NVCC) is None:
+        raise RuntimeError("trep_b200.lib.specialize needs nvcc (%s) to build the plug-in" % build.NVCC)
+    n = load_plugin(build.build_plugin(desc, name, verbose=verbose, kind=kind, ext=ext))
+    _specialized.add(name)
+    return n
+
+
+_specialized = set()
+
+
 def lqr_last_kernel_ms(device=0):
     """Device time (CUDA events) of the last Riccati kernel launched on `device`."""
     ms = C.c_float()
