@@ -386,13 +386,14 @@ def secondary(lib, systems, device, fp64_peak, hbm_peak):
                                  "flops_per_unit": fl, "traffic": tb * B if tb else None,
                                  "hbm": {"achieved": alg * B / t / 1e6, "peak": hbm_peak, "unit": "GB/s",
                                          "frac": alg * B / t / 1e6 / hbm_peak, "bytes_per_unit": alg},
-                                 "note": "cooperative kernel: one warp per instance, link tables + 17.7 KB workspace per instance in shared "
-                                         "memory and 8.6 KB (DDh.lambda block, two pair-combination arrays) in an L2-resident slab: 12 "
-                                         "instances per SM; DRAM traffic is the A/B output plus write-backs of the slab. Latency-bound on "
-                                         "chip: 66 k warp instructions per linearization at ~6 cycles each per warp, throughput grows "
-                                         "almost linearly with the instances in flight; the flops are the executed count of the two-warp "
-                                         "flavour (4.98e5, ncu sass counters; this flavour executes 5.85e5 for the same result), so frac "
-                                         "is pipe utilisation (ncu: profiles/r02v_coop_lin_ext_*.txt; DESIGN.md section 4b)"}
+                                 "note": "cooperative kernel: one warp per instance, link tables + 12.3 KB workspace per instance in shared "
+                                         "memory and 14.1 KB (DDh.lambda block, pair arrays, constraint Jacobians) in an L2-resident slab: "
+                                         "16 instances per SM at 128 registers; DRAM traffic is the A/B output plus write-backs of the "
+                                         "slab. 68 k warp instructions per linearization; throughput grows almost linearly with the "
+                                         "instances in flight up to here (fp64 pipe 20 %, warps active 25 %, shared-memory pipe next); "
+                                         "the flops are the executed count of the two-warp flavour (4.98e5, ncu sass counters; this "
+                                         "flavour executes 5.84e5 for the same result), so frac is pipe utilisation "
+                                         "(ncu: profiles/r02zb_coop_lin_ext16_*.txt; DESIGN.md section 4b)"}
     out.append(entry)
     # the same batch through the thread-per-instance table-driven kernel (the round's starting point)
     s_thr = lib.System(d, device=device, cooperative=False)

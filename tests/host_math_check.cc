@@ -276,7 +276,7 @@ int coop_linearize(const CoopSys& S, int nsteps, double t1, double dt, double to
                    const double* q2_guess, const double* lam_guess, double* q2, double* p2,
                    double* lam, int* iters, double* A, double* B, double** raw, double* aux) {
     CoopLayout L;
-    L.set(S, D::kStatic, D::kExtS, D::kExt || D::kExtS);   // kExtS: the solve-only layout (callers pass raw = null)
+    L.set(S, D::kStatic, D::kExtS && !D::kExt, D::kExt || D::kExtS);   // ExtSolveDims: the solve-only layout (callers pass raw = null)
     std::vector<double> slab(L.total + 8, 0.0);
     // poisoned external slab: every entry read must have been written for this instance
     std::vector<double> xslab(L.xtotal + 8, 1e300);

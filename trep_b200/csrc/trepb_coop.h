@@ -13,7 +13,7 @@ constexpr int kSolveTeams = 12;
 // most instances a CTA of the linearize kernel holds (255 registers per thread with one warp per instance)
 constexpr int kLinTeams = 8;
 // the same for the flavours that keep part of the first-derivative workspace in global memory (ExtDims)
-constexpr int kExtLinTeams = 12;
+constexpr int kExtLinTeams = 16;
 constexpr int kExtSolveTeams = 16;
 // teams per CTA of the wide instantiations (shapes with small workspaces): 16 warps at 128 registers for the
 // compile-time-size flavours, kWideTeamsRt warps for the run-time-size one

@@ -164,11 +164,11 @@ struct CoopLayout {
         const int nlq = nq > nr ? nq : nr;
         L.Lq = o; o += nlq; L.Lv = o; o += nlq;
         L.fr = L.Lq; L.scl = L.Lv;
-        if (sxs) { L.VV = xo; xo += npairs; L.QQ = xo; xo += npairs; }
+        if (ext) { L.VV = xo; xo += npairs; L.QQ = xo; xo += npairs; }
         else { L.VV = o; o += npairs; L.QQ = o; o += npairs; }
         if (sx) { L.UP = xo; xo += npairs; L.DN = xo; xo += npairs; }
         else { L.UP = o; o += solve_only ? 0 : npairs; L.DN = o; o += solve_only ? 0 : npairs; }
-        if (sxs) { L.Dh1 = xo; xo += nc * nd; L.Dh2 = xo; xo += nc * nq; }
+        if (ext) { L.Dh1 = xo; xo += nc * nd; L.Dh2 = xo; xo += nc * nq; }
         else { L.Dh1 = o; o += nc * nd; L.Dh2 = o; o += nc * nq; }
         L.hc = o; o += nc;
         const int nY = stat ? ndc * nqc : nd * L.ldy;
@@ -234,7 +234,7 @@ struct ExtSolveDims : Dims {
 };
 template <class Dims>
 struct ExtDims : Dims {
-    static constexpr bool kExt = true, kExtS = false;
+    static constexpr bool kExt = true, kExtS = true;
     using Solve = ExtSolveDims<Dims>;
     TREPB_HD static constexpr CoopLayout layout(bool solve_only = false) {
         return CoopLayout::make(Dims::ND, Dims::NK, Dims::NU, Dims::NC, Dims::NL, Dims::NP, Dims::NPAIRS, true, Dims::NDC,
