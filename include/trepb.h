@@ -129,7 +129,7 @@ typedef struct trepb_system trepb_system; /* opaque */
 
 /* Cooperative kernels, shapes built in several flavours (the marionette's).  The default is the one with the highest
  * throughput on full batches: one warp per instance with part of the first-derivative workspace in an L2-resident
- * slab of global memory (12 instances per SM, name ".../ext"). */
+ * slab of global memory (16 instances per SM, name ".../ext"). */
 #define TREPB_FLAG_COOP_ONE_WARP 32  /* one warp per instance, the whole workspace in shared memory (8 per SM) */
 #define TREPB_FLAG_COOP_TWO_WARPS 64 /* two warps per instance (8 per SM): the lowest latency per linearization on
                                        batches that do not fill the GPU (name ".../pair") */

@@ -128,19 +128,17 @@ struct CoopLayout {
     // solve_only: the layout of the kernels that never call deriv1 (step, project, p2 / f): no DDh.lambda
     // block, no projection factors, two pair arrays instead of four (dyn_second) - 18.0 instead of 27.0 KB
     // per marionette instance, 12 instead of 8 instances per SM.
-    // ext: the layout of the flavours that keep the blocks only calc_deriv1's column phase reads with one gather
-    // per entry - the DDh.lambda block Y and two of the four pair-combination arrays (UP, DN) - in a per-team
-    // slab of global memory (L2-resident: 8.6 KB per marionette instance) instead of shared memory, and the
-    // projection factors over the midpoint / velocity vectors that are dead by then: 17.7 instead of 26.4 KB per
-    // marionette instance, 12 instead of 8 instances per SM.  Offsets Y, UP, DN then index the external slab.
+    // ext: the layout of the flavours that keep the blocks read with one gather per entry or written once per
+    // evaluation - the pair arrays VV, QQ (and UP, DN of deriv1), the constraint Jacobians Dh1, Dh2 and deriv1's
+    // DDh.lambda block Y - in a per-team slab of global memory (L2-resident: 14.1 KB per marionette instance, 5.4 KB
+    // for the solve-only kernels) instead of shared memory, and the projection factors over the midpoint / velocity
+    // vectors that are dead by then: 12.3 instead of 26.4 KB of shared memory per marionette instance (12.2 instead
+    // of 18.0 solve-only), 16 instances per SM instead of 8 (12).  Those offsets then index the external slab.
     TREPB_HD static constexpr CoopLayout make(int nd, int nk, int nu, int nc, int nl, int np, int npairs,
                                               bool stat = false, int ndc = 0, int nqc = 0, bool solve_only = false,
                                               int nqs = 0, int nqf = 0, int nns = 0, int nw = 0, bool ext = false) {
         CoopLayout L{};
         const bool sx = ext && !solve_only;
-        // ext with solve_only (the step / project / p2 kernels of the same flavours): the two pair arrays and both
-        // constraint Jacobians in the slab - 12.2 instead of 18.0 KB per marionette instance, 16 instead of 12 per SM
-        const bool sxs = ext && solve_only;
         int xo = 0;
         L.ext = ext ? 1 : 0;
         const int nq = nd + nk, nr = nd + nc;
@@ -221,8 +219,8 @@ struct CtDims {
 };
 
 // The same shape with the external-slab layouts (CoopLayout::make, ext): ExtSolveDims for the kernels that never
-// call deriv1 (pair arrays and constraint Jacobians in the slab), ExtDims for the first-derivative kernel (DDh.lambda
-// block and the two pair-combination arrays only deriv1 uses)
+// call deriv1 (pair arrays VV, QQ and constraint Jacobians in the slab: kExtS), ExtDims for the first-derivative
+// kernel (those plus the DDh.lambda block and the pair arrays UP, DN only deriv1 uses: kExt)
 template <class Dims>
 struct ExtSolveDims : Dims {
     static constexpr bool kExt = false, kExtS = true;
